@@ -1,0 +1,45 @@
+"""Builds the in-tree native libraries of iamf_b200 (nvcc, sm_100a only; cross-compiles without a GPU).
+
+    python -m iamf_b200.build            # build everything that is stale
+"""
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libiamf_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "--fmad=false",          # the reference is built without FMA contraction (x86-64 baseline): keep mul and add apart
+    "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_cuda(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "iamf_b200.h")]
+    if not force and not _stale(LIB, srcs):
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", LIB, os.path.join(CSRC, "iamfb_api.cu")]
+    print("[iamf_b200.build]", " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_all(force=False):
+    return build_cuda(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)

@@ -1,0 +1,964 @@
+// iamfb_api.cu - host side of the C ABI declared in include/iamf_b200.h: plans, batches, kernel sequencing.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "iamf_b200.h"
+#include "iamfb_kernels.cuh"
+#include "iamfb_matrices.inc"
+
+using namespace iamfb;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  fprintf(stderr, "[iamf_b200] error %d: %s\n", code, g_err);
+  return code;
+}
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_));     \
+  } while (0)
+
+extern "C" const char *iamfb_last_error(void) { return g_err; }
+extern "C" const char *iamfb_version(void) { return "iamf_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// static tables (host)
+// ---------------------------------------------------------------------------------------------------------------------
+// IAMF_utils.c:111-133
+static const int k_layout_count[10] = {1, 2, 6, 8, 10, 8, 10, 12, 6, 2};
+static const unsigned char k_layout_order[10][12] = {
+    {13}, {14, 15}, {1, 2, 3, 4, 20, 21}, {1, 2, 3, 4, 20, 21, 22, 23}, {1, 2, 3, 4, 20, 21, 9, 10, 11, 12},
+    {1, 2, 3, 4, 5, 6, 7, 8}, {1, 2, 3, 4, 5, 6, 7, 8, 22, 23}, {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12},
+    {18, 19, 3, 4, 16, 17}, {14, 15}};
+static const int k_layout_surround[10] = {1, 2, 5, 5, 5, 7, 7, 7, 3, 2};
+static const int k_layout_top[10] = {0, 0, 0, 2, 4, 0, 2, 4, 2, 0};
+// IAMF_decoder.c:208-219 (+LFE) / 3998-4008
+static const int k_target_channels[IAMFB_TARGET_COUNT] = {2, 6, 8, 10, 11, 12, 14, 24, 8, 12, 10, 6, 1, 2};
+
+extern "C" int iamfb_target_channels(int target) {
+  return (target >= 0 && target < IAMFB_TARGET_COUNT) ? k_target_channels[target] : 0;
+}
+extern "C" int iamfb_layout_channels(int layout, int32_t *chs) {
+  if (layout < 0 || layout > 9) return 0;
+  if (chs)
+    for (int i = 0; i < k_layout_count[layout]; ++i) chs[i] = k_layout_order[layout][i];
+  return k_layout_count[layout];
+}
+
+static inline float bits2f(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+extern "C" int iamfb_get_m2m_matrix(int layout, int target, int32_t *m, int32_t *n, float *mat) {
+  for (size_t i = 0; i < sizeof(k_m2m_index) / sizeof(k_m2m_index[0]); ++i)
+    if (k_m2m_index[i].in == layout && k_m2m_index[i].out == target) {
+      if (m) *m = k_m2m_index[i].m;
+      if (n) *n = k_m2m_index[i].n;
+      if (mat)
+        for (int k = 0; k < k_m2m_index[i].m * k_m2m_index[i].n; ++k) mat[k] = bits2f(k_matrix_pool[k_m2m_index[i].off + k]);
+      return IAMFB_OK;
+    }
+  return IAMFB_ERR_BAD_ARG;
+}
+
+extern "C" int iamfb_get_h2m_matrix(int order, int target, int32_t *m, int32_t *n, int32_t *lfe1, int32_t *lfe2, float *mat) {
+  for (size_t i = 0; i < sizeof(k_h2m_index) / sizeof(k_h2m_index[0]); ++i)
+    if (k_h2m_index[i].order == order && k_h2m_index[i].out == target) {
+      if (m) *m = k_h2m_index[i].m;
+      if (n) *n = k_h2m_index[i].n;
+      if (lfe1) *lfe1 = k_h2m_index[i].lfe1;
+      if (lfe2) *lfe2 = k_h2m_index[i].lfe2;
+      if (mat)
+        for (int k = 0; k < k_h2m_index[i].m * k_h2m_index[i].n; ++k) mat[k] = bits2f(k_matrix_pool[k_h2m_index[i].off + k]);
+      return IAMFB_OK;
+    }
+  return IAMFB_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------------------------------
+struct iamfb_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  uint64_t launches;
+};
+
+struct iamfb_plan {
+  iamfb_ctx *ctx;
+  iamfb_plan_desc desc;
+  KernelPlan kp;
+  int tmpl[kMaxEl];       // render kernel variant per element
+  // device constant arrays
+  float *d_start_win, *d_stop_win;   // recon cross-fade windows [overlap]
+  float *d_qf;                       // 256
+  float *d_sinc;                     // resampler table
+  int sinc_len;
+  float *d_acc;                      // limiter acceleration curve by time index
+  // initial per-stream state (host copy)
+  StreamState init_state;
+};
+
+struct iamfb_batch {
+  iamfb_plan *plan;
+  int S, Fmax;
+  int cap_a, cap_b;
+  size_t out_stride;       // bytes per stream for Fmax frames
+  StreamState *d_state;
+  FrameRec *d_frames;
+  SubmitRec *d_submit;
+  float *d_tl_a, *d_tl_b, *d_pk, *d_wm, *d_gn;
+  // staging for the host-resident path
+  float *d_in[kMaxEl];
+  float *d_ramp[kMaxEl];
+  float *d_oramp;
+  iamfb_frame_params *d_params;
+  char *d_pcm;
+  int32_t *d_counts;
+  size_t stage_frames;     // frames the staging buffers are sized for (0 = not allocated)
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int iamfb_ctx_create(int device, iamfb_ctx **out) {
+  if (!out) return fail(IAMFB_ERR_BAD_ARG, "ctx_create: null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(IAMFB_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(IAMFB_ERR_BAD_ARG, "device %d out of range (%d devices)", device, n);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(IAMFB_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  iamfb_ctx *c = new iamfb_ctx();
+  c->device = device;
+  c->launches = 0;
+  c->own_stream = true;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_ctx_set_stream(iamfb_ctx *c, void *stream) {
+  if (!c) return fail(IAMFB_ERR_BAD_ARG, "null ctx");
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)stream;
+  c->own_stream = false;
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_ctx_synchronize(iamfb_ctx *c) {
+  if (!c) return fail(IAMFB_ERR_BAD_ARG, "null ctx");
+  CU(cudaStreamSynchronize(c->stream));
+  return IAMFB_OK;
+}
+
+extern "C" void iamfb_ctx_destroy(iamfb_ctx *c) {
+  if (!c) return;
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" uint64_t iamfb_ctx_launch_count(const iamfb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" void *iamfb_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    fail(IAMFB_ERR_ALLOC_FAIL, "cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void iamfb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// plan construction (host arithmetic uses the same libm calls as the reference so that the tables are bit-identical)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// Kaiser window tables and quality map of the Speex resampler (resample.c:105-207); only quality 4 is used by the
+// decoder (IAMF_decoder.c:57 SPEEX_RESAMPLER_QUALITY) but Q0..Q8 share the code path.
+const double kKaiser8[36] = {
+    0.99635258, 1.00000000, 0.99635258, 0.98548012, 0.96759014, 0.94302200, 0.91223751, 0.87580811, 0.83439927,
+    0.78875245, 0.73966538, 0.68797126, 0.63451750, 0.58014482, 0.52566725, 0.47185369, 0.41941150, 0.36897272,
+    0.32108304, 0.27619388, 0.23465776, 0.19672670, 0.16255380, 0.13219758, 0.10562887, 0.08273982, 0.06335451,
+    0.04724088, 0.03412321, 0.02369490, 0.01563093, 0.00959968, 0.00527363, 0.00233883, 0.00050000, 0.00000000};
+constexpr int kQ4Len = 64, kQ4Over = 8, kWinOver = 32;
+constexpr float kQ4DownBw = 0.921f, kQ4UpBw = 0.940f;
+
+double kaiser_window(float x) {   // compute_func, resample.c:210-229
+  float y = x * kWinOver;
+  int ind = (int)floor(y);
+  float frac = (y - ind);
+  double i3 = -0.1666666667 * frac + 0.1666666667 * (frac * frac * frac);
+  double i2 = frac + 0.5 * (frac * frac) - 0.5 * (frac * frac * frac);
+  double i0 = -0.3333333333 * frac + 0.5 * (frac * frac) - 0.1666666667 * (frac * frac * frac);
+  double i1 = 1.f - i3 - i2 - i0;
+  return i0 * kKaiser8[ind] + i1 * kKaiser8[ind + 1] + i2 * kKaiser8[ind + 2] + i3 * kKaiser8[ind + 3];
+}
+
+float windowed_sinc(float cutoff, float x, int N) {   // sinc, resample.c:233-244
+  float xx = x * cutoff;
+  if (fabs(x) < 1e-6) return cutoff;
+  if (fabs(x) > .5 * N) return 0;
+  return cutoff * sin(M_PI * xx) / (M_PI * xx) * kaiser_window(fabs(2. * x / N));
+}
+
+uint32_t gcd_u32(uint32_t a, uint32_t b) {
+  while (b) { uint32_t t = a % b; a = b; b = t; }
+  return a;
+}
+
+// update_filter, resample.c:527-640 for a freshly created quality-4 resampler
+void build_resampler(KernelPlan &kp, std::vector<float> &table, uint32_t in_rate, uint32_t out_rate) {
+  uint32_t g = gcd_u32(in_rate, out_rate);
+  kp.rs_num = in_rate / g;
+  kp.rs_den = out_rate / g;
+  kp.rs_int_adv = kp.rs_num / kp.rs_den;
+  kp.rs_frac_adv = kp.rs_num % kp.rs_den;
+  uint32_t oversample = kQ4Over, filt_len = kQ4Len;
+  float cutoff;
+  if (kp.rs_num > kp.rs_den) {
+    cutoff = kQ4DownBw * kp.rs_den / kp.rs_num;
+    uint32_t major = filt_len / kp.rs_den, remain = filt_len % kp.rs_den;
+    filt_len = remain * kp.rs_num / kp.rs_den + major * kp.rs_num;
+    filt_len = ((filt_len - 1) & (~0x7U)) + 8;
+    if (2 * kp.rs_den < kp.rs_num) oversample >>= 1;
+    if (4 * kp.rs_den < kp.rs_num) oversample >>= 1;
+    if (8 * kp.rs_den < kp.rs_num) oversample >>= 1;
+    if (16 * kp.rs_den < kp.rs_num) oversample >>= 1;
+    if (oversample < 1) oversample = 1;
+  } else {
+    cutoff = kQ4UpBw;
+  }
+  kp.rs_filt_len = filt_len;
+  kp.rs_oversample = oversample;
+  kp.rs_direct = filt_len * kp.rs_den <= filt_len * oversample + 8;
+  if (kp.rs_direct) {
+    table.resize((size_t)filt_len * kp.rs_den);
+    for (uint32_t i = 0; i < kp.rs_den; ++i)
+      for (int32_t j = 0; j < (int32_t)filt_len; ++j)
+        table[i * filt_len + j] = windowed_sinc(cutoff, ((j - (int32_t)filt_len / 2 + 1) - ((float)i) / kp.rs_den), filt_len);
+  } else {
+    table.resize((size_t)filt_len * oversample + 8);
+    for (int32_t i = -4; i < (int32_t)(oversample * filt_len + 4); ++i)
+      table[i + 4] = windowed_sinc(cutoff, (i / (float)oversample - filt_len / 2), filt_len);
+  }
+}
+
+// curve_accel, audio_effect_peak_limiter.c:267-271
+float accel_curve(float x) {
+  if (1.0 < x) return 1.0f;
+  if (x < 0) return 0.0f;
+  return 1.0f - powf(x - 1, 2.0);
+}
+
+// The limiter's float time constant restarts at 0 on every trigger and then only accumulates incTC, so it walks a fixed
+// sequence T[j]; tabulate curve_accel along it (compute_target_gain, audio_effect_peak_limiter.c:237-256).
+void build_limiter(KernelPlan &kp, std::vector<float> &acc, float thr_db, int rate) {
+  const float atk = 0.001f, rel = 0.200f;   // audio_defines.h:39-40
+  const float inc = (float)1 / (float)rate;
+  kp.lim_thr = pow(10, thr_db / 20);         // double pow rounded to float on store (:79)
+  acc.clear();
+  acc.push_back(0.f);
+  float t = 0.0f;
+  int j = 0;
+  kp.lim_ja = -1;
+  for (;;) {
+    if (t < atk) {
+      t += inc; ++j;
+      acc.push_back(accel_curve(t / atk));
+    } else if (t < rel + atk) {
+      if (kp.lim_ja < 0) kp.lim_ja = j;
+      t += inc; ++j;
+      acc.push_back(accel_curve((t - atk) / rel));
+    } else {
+      break;
+    }
+    if (j > (1 << 22)) break;
+  }
+  if (kp.lim_ja < 0) kp.lim_ja = j;
+  kp.lim_jr = j;
+}
+
+template <typename T>
+int upload(T **dst, const T *src, size_t n) {
+  CU(cudaMalloc((void **)dst, n * sizeof(T) > 0 ? n * sizeof(T) : sizeof(T)));
+  if (n) CU(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return IAMFB_OK;
+}
+
+// dependency resolution of dmx_channel (demixer.c:380-419) on the host: which derivations does the layout need?
+struct Avail {
+  bool have[kChCount];
+  ElPlan *ep;
+  bool s2() {
+    if (!have[IAMFB_CH_L2]) return false;
+    if (have[IAMFB_CH_R2]) return true;
+    if (!have[IAMFB_CH_MONO]) return false;
+    ep->need_s2 = 1; have[IAMFB_CH_R2] = true; return true;
+  }
+  bool s3() {
+    if (have[IAMFB_CH_R3]) return true;
+    if (!s2()) return false;
+    if (!have[IAMFB_CH_C]) return false;
+    ep->need_s3 = 1; have[IAMFB_CH_L3] = have[IAMFB_CH_R3] = true; return true;
+  }
+  bool s5() {
+    if (have[IAMFB_CH_SR5]) return true;
+    if (!s3()) return false;
+    if (!have[IAMFB_CH_L5] || !have[IAMFB_CH_R5]) return false;
+    ep->need_s5 = 1; have[IAMFB_CH_SL5] = have[IAMFB_CH_SR5] = true; return true;
+  }
+  bool s7() {
+    if (have[IAMFB_CH_BR7]) return true;
+    if (!s5()) return false;
+    if (!have[IAMFB_CH_SL7] || !have[IAMFB_CH_SR7]) return false;
+    ep->need_s7 = 1; have[IAMFB_CH_BL7] = have[IAMFB_CH_BR7] = true; return true;
+  }
+  bool h2() {
+    if (have[IAMFB_CH_HR]) return true;
+    if (!have[IAMFB_CH_TL] || !have[IAMFB_CH_TR]) return false;
+    if (!s5()) return false;
+    ep->need_h2 = 1; have[IAMFB_CH_HL] = have[IAMFB_CH_HR] = true; return true;
+  }
+  bool h4() {
+    if (have[IAMFB_CH_HBR]) return true;
+    if (!h2()) return false;
+    if (!have[IAMFB_CH_HFR] || !have[IAMFB_CH_HFL]) return false;
+    ep->need_h4 = 1; have[IAMFB_CH_HBL] = have[IAMFB_CH_HBR] = true; return true;
+  }
+  bool channel(int ch) {
+    if (have[ch]) return true;
+    switch (ch) {
+      case IAMFB_CH_R2: return s2();
+      case IAMFB_CH_L3: case IAMFB_CH_R3: return s3();
+      case IAMFB_CH_SL5: case IAMFB_CH_SR5: return s5();
+      case IAMFB_CH_BL7: case IAMFB_CH_BR7: return s7();
+      case IAMFB_CH_HL: case IAMFB_CH_HR: return h2();
+      case IAMFB_CH_HBL: case IAMFB_CH_HBR: return h4();
+      default: return false;
+    }
+  }
+};
+
+int recon_flags_default(int l1, int l2) {   // iamf_recon_channels_get_flags, IAMF_decoder.c:371-407
+  if (l1 == l2) return 0;
+  int s1 = k_layout_surround[l1], s2 = k_layout_surround[l2], t1 = k_layout_top[l1], t2 = k_layout_top[l2];
+  int f = 0;
+  if (s1 != s2) {
+    if (s2 <= 3) f |= (1 << 0) | (1 << 2);
+    else if (s2 == 5) f |= (1 << 3) | (1 << 4);
+    else if (s2 == 7) f |= (1 << 7) | (1 << 8);
+  }
+  if (t2 != t1 && t2 == 4) f |= (1 << 9) | (1 << 10);
+  if (s2 == 5 && t1 && t2 == t1) f |= (1 << 5) | (1 << 6);
+  return f;
+}
+
+const unsigned char k_recon_map_host[9][12] = {
+    {13, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},        {14, 0, 15, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1, 3, 2, 20, 21, 0, 0, 0, 0, 0, 0, 4},       {1, 3, 2, 20, 21, 22, 23, 0, 0, 0, 0, 4},
+    {1, 3, 2, 20, 21, 9, 10, 0, 0, 11, 12, 4},    {1, 3, 2, 5, 6, 0, 0, 7, 8, 0, 0, 4},
+    {1, 3, 2, 5, 6, 22, 23, 7, 8, 0, 0, 4},       {1, 3, 2, 5, 6, 9, 10, 7, 8, 11, 12, 4},
+    {18, 3, 19, 0, 0, 16, 17, 0, 0, 0, 0, 4}};
+
+const float k_mix_gamma_host[8] = {0.707f, 0.707f, 0.866f, 0.f, 0.707f, 0.707f, 0.866f, 0.f};
+const float k_w_host[11] = {0.0f, 0.0179f, 0.0391f, 0.0658f, 0.1038f, 0.25f, 0.3962f, 0.4342f, 0.4609f, 0.4821f, 0.5f};
+
+bool valid_dmr_pair(int in, int out) {   // DMRenderer_open validity, downmix_renderer.c:77-91,131-139
+  if (in == out || in < 0 || in > 8 || out < 0 || out > 8) return false;
+  int s1 = k_layout_surround[in], s2 = k_layout_surround[out], t1 = k_layout_top[in], t2 = k_layout_top[out];
+  if (t1 && !t2) return false;
+  return !(s1 < s2 || t1 < t2);
+}
+
+}  // namespace
+
+static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &tmpl, StreamState &init) {
+  const iamfb_element_desc &ed = d.el[e];
+  ElPlan &ep = kp.el[e];
+  ElState &es = init.el[e];
+  memset(&ep, 0, sizeof(ep));
+  ep.kind = ed.kind;
+  ep.n_in = ed.n_in;
+  for (int c = 0; c < kChCount; ++c) ep.src_row[c] = -1;
+  for (int i = 0; i < kMaxOut; ++i) ep.out_slot[i] = -1;
+  const int co = kp.out_channels;
+
+  if (ed.kind == IAMFB_EL_CHANNEL) {
+    if (ed.layout < 0 || ed.layout > 9) return fail(IAMFB_ERR_BAD_ARG, "element %d: bad layout %d", e, ed.layout);
+    const int lay = ed.layout == IAMFB_LAYOUT_BINAURAL ? IAMFB_LAYOUT_STEREO : ed.layout;
+    ep.layout = lay;
+    ep.n_rec = k_layout_count[lay];
+    if (ed.n_in != ep.n_rec)   // demixer_demixing: chs_count must equal the layout's channel count (demixer.c:640-641)
+      return fail(IAMFB_ERR_BAD_ARG, "element %d: %d decoded channels but layout %d has %d", e, ed.n_in, lay, ep.n_rec);
+    Avail av;
+    memset(&av, 0, sizeof(av));
+    av.ep = &ep;
+    for (int i = 0; i < ed.n_in; ++i) {
+      int ch = ed.chs_in[i];
+      if (ch <= 0 || ch >= kChCount) return fail(IAMFB_ERR_BAD_ARG, "element %d: bad channel id %d", e, ch);
+      ep.src_row[ch] = (signed char)i;
+      av.have[ch] = true;
+    }
+    for (int i = 0; i < ed.n_out_gain; ++i) {
+      int ch = ed.out_gain_ch[i];
+      if (ch <= 0 || ch >= kChCount) continue;
+      if (ep.src_row[ch] < 0) continue;           // dmx_gainup skips channels without data
+      if ((ep.gain_mask >> ch) & 1u) return fail(IAMFB_ERR_UNIMPLEMENTED, "element %d: channel %d listed twice in output gain", e, ch);
+      ep.gain_mask |= 1u << ch;
+      ep.gain[ch] = ed.out_gain[i];
+    }
+    for (int m = 0; m < ep.n_rec; ++m) {
+      ep.rec_ch[m] = k_layout_order[lay][m];
+      if (!av.channel(ep.rec_ch[m]))
+        return fail(IAMFB_ERR_BAD_ARG, "element %d: layout channel %d cannot be reconstructed from the decoded channels", e, ep.rec_ch[m]);
+    }
+    ep.recon_present = ed.recon_present;
+    tmpl = lay;
+    // demixer initial state: iamf_stream_scale_demixer_configure, IAMF_decoder.c:2351-2401
+    es.mode = 0;
+    es.w_idx = 0;
+    if (ed.has_demix_info) {
+      int mode = ed.default_mode, w = ed.default_w_idx;
+      if (!(mode < 0 || mode == 3 || mode > 6)) {
+        if (w < 0 || w > 10) {
+          es.mode = mode;
+          es.w_idx = (mode >= 4) ? 1 : 0;
+        } else {
+          es.mode = mode;
+          es.w_idx = w;
+        }
+      }
+    }
+    for (int c = 0; c < kChCount; ++c) es.sfavg[c] = 1.0f;
+    if (ed.selected_layer > 0) {   // iamf_stream_scale_decoder_set_default_recon_gain, :2202-2236
+      int fl = recon_flags_default(ed.first_layer_layout, lay);
+      int n = 0;
+      for (int b = 0; b < 12; ++b)
+        if (fl & (1 << b)) { es.rch[n] = k_recon_map_host[lay][b]; es.rgain[n] = 1.f; ++n; }
+      if (fl) { es.rcount = n; es.rflags = fl; }
+    }
+    init.re_flags[e] = 0;
+    init.re_count[e] = 0;
+
+    if (ed.use_dmr) {
+      if (!valid_dmr_pair(lay, ed.dmr_out_layout))
+        return fail(IAMFB_ERR_BAD_ARG, "element %d: layouts %d -> %d are not a valid parametric down-mix", e, lay, ed.dmr_out_layout);
+      if (k_layout_count[ed.dmr_out_layout] != co)
+        return fail(IAMFB_ERR_BAD_ARG, "element %d: down-mix layout has %d channels, target %d", e, k_layout_count[ed.dmr_out_layout], co);
+      ep.renderer = kRdrDMR;
+      ep.dmr_n_out = k_layout_count[ed.dmr_out_layout];
+      for (int i = 0; i < ep.dmr_n_out; ++i) ep.dmr_out_ch[i] = k_layout_order[ed.dmr_out_layout][i];
+      for (int m = 0; m < ep.n_rec; ++m) ep.dmr_in_mask |= 1u << ep.rec_ch[m];
+      // DMRenderer_open + DMRenderer_set_mode_weight(default_mode, default_w_idx)
+      es.dmr_mode = -1;
+      es.dmr_w_idx = -1;
+      es.dmr_tl = 0.f;
+      int mode = ed.default_mode;
+      if (mode >= 0 && mode != 3 && mode < 7) {
+        es.dmr_mode = mode;
+        bool tl_derived = !((ep.dmr_in_mask >> IAMFB_CH_TL) & 1u) && !((ep.dmr_in_mask >> IAMFB_CH_TR) & 1u);
+        int w = ed.default_w_idx;
+        if (w < 0 || w > 10) {
+          int nw = (mode >= 4) ? 0 : 0;   // calc_w from w_idx -1: min(-1+1,10)=0 or max(-2,0)=0
+          es.dmr_w_idx = nw;
+          if (tl_derived) es.dmr_tl = k_mix_gamma_host[mode] * k_w_host[nw];
+        } else {
+          es.dmr_w_idx = w;
+          if (tl_derived) es.dmr_tl = k_mix_gamma_host[mode] * k_w_host[w];
+        }
+      }
+    } else {
+      ep.renderer = kRdrM2M;
+      int32_t m = 0, n = 0;
+      std::vector<float> mat(24 * 16);
+      // iamf_stream_render: a one-channel element renders as IAMF_MONO, else by its layout (IAMF_decoder.c:2593-2598)
+      if (iamfb_get_m2m_matrix(ed.layout, d.target, &m, &n, mat.data()) != IAMFB_OK)
+        return fail(IAMFB_ERR_BAD_ARG, "element %d: no channel matrix for layout %d -> target %d", e, ed.layout, d.target);
+      if (m != ep.n_rec || n != co) return fail(IAMFB_ERR_INTERNAL, "matrix shape %dx%d vs %dx%d", m, n, ep.n_rec, co);
+      ep.n_mat_out = n;
+      for (int o = 0; o < n; ++o) {
+        ep.out_slot[o] = (signed char)o;
+        for (int i = 0; i < m; ++i) ep.mat[o * ep.n_rec + i] = mat[i * n + o];   // [in][out] -> output-major
+      }
+    }
+  } else if (ed.kind == IAMFB_EL_SCENE) {
+    int nch = ed.ambi_channels;
+    int order = nch == 1 ? 0 : nch == 4 ? 1 : nch == 9 ? 2 : nch == 16 ? 3 : -1;   // iamf_stream_ambisionisc_order :2403-2413
+    if (order < 0) return fail(IAMFB_ERR_BAD_ARG, "element %d: %d ambisonics channels", e, nch);
+    ep.n_rec = nch;
+    ep.renderer = kRdrH2M;
+    ep.ambi_mode = ed.ambi_mode;
+    if (ed.ambi_mode == 0) {
+      for (int i = 0; i < nch; ++i) {
+        if (ed.ambi_map[i] >= ed.n_in) return fail(IAMFB_ERR_BAD_ARG, "element %d: ambisonics map[%d]=%d >= %d rows", e, i, ed.ambi_map[i], ed.n_in);
+        ep.ambi_map[i] = ed.ambi_map[i];
+      }
+    } else {
+      if (ed.ambi_cols <= 0 || ed.ambi_cols > 16 || ed.ambi_cols > ed.n_in) return fail(IAMFB_ERR_BAD_ARG, "element %d: projection columns %d", e, ed.ambi_cols);
+      ep.ambi_cols = ed.ambi_cols;
+      for (int l = 0; l < ed.ambi_cols; ++l)
+        for (int r = 0; r < nch; ++r) ep.ambi_mat[l * nch + r] = ed.ambi_matrix[l * nch + r];
+    }
+    int32_t m = 0, n = 0, l1 = -1, l2 = -1;
+    std::vector<float> mat(24 * 16);
+    if (iamfb_get_h2m_matrix(order, d.target, &m, &n, &l1, &l2, mat.data()) != IAMFB_OK)
+      return fail(IAMFB_ERR_BAD_ARG, "element %d: no HOA matrix for order %d -> target %d", e, order, d.target);
+    if (m != nch) return fail(IAMFB_ERR_INTERNAL, "HOA matrix inputs %d vs %d", m, nch);
+    ep.n_mat_out = n;
+    for (int i = 0; i < n * m; ++i) ep.mat[i] = mat[i];
+    // LFE slot shift (h2m_rdr.c:1114-1135); LFE rows themselves are zero (DISABLE_LFE_HOA, :1137-1150); rows the
+    // reference never writes (row 23 of sound system H) are zero here.
+    int map[24];
+    for (int i = 0; i < n; ++i) map[i] = i;
+    if (l1 >= 0 || l2 >= 0) {
+      int k = 0;
+      for (int i = 0; i < n; ++i) {
+        if (l1 == i) k++;
+        if (l2 == i) k++;
+        map[i] = k;
+        k++;
+      }
+    }
+    for (int i = 0; i < n; ++i)
+      if (map[i] < co) ep.out_slot[map[i]] = (signed char)i;
+    // a row later zeroed as an LFE slot: the reference moves first, then zeroes lfe1/lfe2 (:1137-1150)
+    if (l1 >= 0 && l1 < co) ep.out_slot[l1] = -1;
+    if (l2 >= 0 && l2 < co) ep.out_slot[l2] = -1;
+    tmpl = 10 + order;
+  } else {
+    return fail(IAMFB_ERR_BAD_ARG, "element %d: unknown kind %d", e, ed.kind);
+  }
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb_plan **out) {
+  if (!ctx || !d || !out) return fail(IAMFB_ERR_BAD_ARG, "plan_create: null argument");
+  if (d->frame_size <= 0 || d->frame_size > 32768) return fail(IAMFB_ERR_BAD_ARG, "frame_size %d", d->frame_size);
+  if (d->n_elements < 1 || d->n_elements > kMaxEl) return fail(IAMFB_ERR_BAD_ARG, "n_elements %d", d->n_elements);
+  if (d->target < 0 || d->target >= IAMFB_TARGET_COUNT) return fail(IAMFB_ERR_BAD_ARG, "target %d", d->target);
+  if (d->bit_depth != 0 && d->bit_depth != 16 && d->bit_depth != 24 && d->bit_depth != 32)
+    return fail(IAMFB_ERR_BAD_ARG, "bit_depth %d", d->bit_depth);
+  if (d->in_rate <= 0 || d->out_rate <= 0) return fail(IAMFB_ERR_BAD_ARG, "rates %d -> %d", d->in_rate, d->out_rate);
+  CU(cudaSetDevice(ctx->device));
+
+  iamfb_plan *p = new iamfb_plan();
+  memset(p, 0, sizeof(*p));
+  p->ctx = ctx;
+  p->desc = *d;
+  KernelPlan &kp = p->kp;
+  kp.frame_size = d->frame_size;
+  kp.n_elements = d->n_elements;
+  kp.out_channels = k_target_channels[d->target];
+  kp.overlap = (d->frame_size / 8) / 2;
+  kp.resample = d->in_rate != d->out_rate;
+  kp.limiter = d->limiter ? 1 : 0;
+  kp.hist = kp.limiter ? kLimDelay : 0;
+  kp.bit_depth = d->bit_depth;
+  kp.loud_gain = d->loudness_gain;
+  memset(&p->init_state, 0, sizeof(p->init_state));
+  for (int e = 0; e < d->n_elements; ++e) {
+    int r = build_element(*d, e, kp, p->tmpl[e], p->init_state);
+    if (r != IAMFB_OK) { delete p; return r; }
+  }
+  p->init_state.lim_j = -1;
+  p->init_state.lim_start = -1.f;
+  p->init_state.lim_end = -1.f;
+  p->init_state.lim_pad = kp.limiter ? kLimDelay : 0;
+  p->init_state.lim_init = 0;
+
+  // recon-gain cross-fade windows (demixer_open demixer.c:502-505 + demixer_set_frame_offset(0) :537-563)
+  {
+    int wl = d->frame_size / 8, ol = wl / 2;
+    std::vector<float> hann(wl > 0 ? wl : 1), sw(ol > 0 ? ol : 1), ew(ol > 0 ? ol : 1);
+    for (int i = 0; i < wl; ++i) hann[i] = (0.5 * (1.0 - cos(2.0 * M_PI * (double)i / (double)(wl - 1))));
+    for (int j = 0; j < ol; ++j) { sw[j] = hann[j]; ew[j] = hann[j + ol]; }
+    int r;
+    if ((r = upload(&p->d_start_win, sw.data(), (size_t)ol)) || (r = upload(&p->d_stop_win, ew.data(), (size_t)ol))) { delete p; return r; }
+  }
+  {   // qf_to_float(q, 8), fixedp11_5.c:53-55
+    float qf[256];
+    for (int q = 0; q < 256; ++q) qf[q] = ((float)q / (pow(2.0f, (float)8) - 1.0));
+    int r = upload(&p->d_qf, qf, 256);
+    if (r) { delete p; return r; }
+  }
+  if (kp.resample) {
+    std::vector<float> table;
+    build_resampler(kp, table, d->in_rate, d->out_rate);
+    if (kp.rs_filt_len - 1 > (unsigned)kRsHist) { delete p; return fail(IAMFB_ERR_UNIMPLEMENTED, "resampler filter length %u > %d (ratio %d:%d)", kp.rs_filt_len, kRsHist + 1, d->in_rate, d->out_rate); }
+    p->sinc_len = (int)table.size();
+    int r = upload(&p->d_sinc, table.data(), table.size());
+    if (r) { delete p; return r; }
+  }
+  if (kp.limiter) {
+    std::vector<float> acc;
+    build_limiter(kp, acc, d->limiter_threshold_db, d->out_rate);   // limiter runs at the requested rate (:3809-3815)
+    int r = upload(&p->d_acc, acc.data(), acc.size());
+    if (r) { delete p; return r; }
+  }
+  *out = p;
+  return IAMFB_OK;
+}
+
+extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
+  if (!p) return;
+  cudaFree(p->d_start_win); cudaFree(p->d_stop_win); cudaFree(p->d_qf); cudaFree(p->d_sinc); cudaFree(p->d_acc);
+  delete p;
+}
+
+extern "C" int iamfb_plan_out_channels(const iamfb_plan *p) { return p ? p->kp.out_channels : 0; }
+
+extern "C" int iamfb_plan_max_out_samples(const iamfb_plan *p, int n_frames) {
+  if (!p) return 0;
+  long long in = (long long)n_frames * p->kp.frame_size;
+  long long out = in;
+  if (p->kp.resample) out = (in * p->kp.rs_den + p->kp.rs_num - 1) / p->kp.rs_num + 2;
+  // a flush can add the limiter delay plus the resampler's output latency
+  long long flush = kLimDelay + 64;
+  return (int)(out > flush ? out : flush);
+}
+
+extern "C" size_t iamfb_plan_out_stride_bytes(const iamfb_plan *p, int n_frames) {
+  if (!p) return 0;
+  size_t bps = p->kp.bit_depth ? p->kp.bit_depth / 8 : 4;
+  size_t b = (size_t)iamfb_plan_max_out_samples(p, n_frames) * p->kp.out_channels * bps;
+  return (b + 15) & ~(size_t)15;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// batch
+// ---------------------------------------------------------------------------------------------------------------------
+static int round4(int x) { return (x + 3) & ~3; }
+
+extern "C" int iamfb_batch_reset(iamfb_batch *b) {
+  if (!b) return fail(IAMFB_ERR_BAD_ARG, "null batch");
+  iamfb_plan *p = b->plan;
+  CU(cudaSetDevice(p->ctx->device));
+  std::vector<StreamState> init(b->S, p->init_state);
+  CU(cudaMemcpyAsync(b->d_state, init.data(), sizeof(StreamState) * b->S, cudaMemcpyHostToDevice, p->ctx->stream));
+  const int co = p->kp.out_channels;
+  if (b->d_tl_a) CU(cudaMemsetAsync(b->d_tl_a, 0, sizeof(float) * (size_t)b->S * co * b->cap_a, p->ctx->stream));
+  CU(cudaMemsetAsync(b->d_tl_b, 0, sizeof(float) * (size_t)b->S * co * b->cap_b, p->ctx->stream));
+  if (b->d_pk) {
+    CU(cudaMemsetAsync(b->d_pk, 0, sizeof(float) * (size_t)b->S * b->cap_b, p->ctx->stream));
+    CU(cudaMemsetAsync(b->d_wm, 0, sizeof(float) * (size_t)b->S * b->cap_b, p->ctx->stream));
+    CU(cudaMemsetAsync(b->d_gn, 0, sizeof(float) * (size_t)b->S * b->cap_b, p->ctx->stream));
+  }
+  CU(cudaStreamSynchronize(p->ctx->stream));
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, iamfb_batch **out) {
+  if (!p || !out || n_streams <= 0 || max_frames <= 0) return fail(IAMFB_ERR_BAD_ARG, "batch_create: bad argument");
+  CU(cudaSetDevice(p->ctx->device));
+  iamfb_batch *b = new iamfb_batch();
+  memset(b, 0, sizeof(*b));
+  b->plan = p;
+  b->S = n_streams;
+  b->Fmax = max_frames;
+  const KernelPlan &kp = p->kp;
+  const int co = kp.out_channels;
+  b->cap_a = kp.resample ? round4(kRsHist + max_frames * kp.frame_size + 64) : 0;
+  b->cap_b = round4(kp.hist + iamfb_plan_max_out_samples(p, max_frames) + 64);
+  b->out_stride = iamfb_plan_out_stride_bytes(p, max_frames);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void **ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
+  alloc((void **)&b->d_state, sizeof(StreamState) * n_streams);
+  alloc((void **)&b->d_frames, sizeof(FrameRec) * (size_t)n_streams * max_frames);
+  alloc((void **)&b->d_submit, sizeof(SubmitRec) * n_streams);
+  if (kp.resample) alloc((void **)&b->d_tl_a, sizeof(float) * (size_t)n_streams * co * b->cap_a);
+  alloc((void **)&b->d_tl_b, sizeof(float) * (size_t)n_streams * co * b->cap_b);
+  if (kp.limiter) {
+    alloc((void **)&b->d_pk, sizeof(float) * (size_t)n_streams * b->cap_b);
+    alloc((void **)&b->d_wm, sizeof(float) * (size_t)n_streams * b->cap_b);
+    alloc((void **)&b->d_gn, sizeof(float) * (size_t)n_streams * b->cap_b);
+  }
+  if (e != cudaSuccess) {
+    int r = fail(IAMFB_ERR_ALLOC_FAIL, "device allocation failed: %s", cudaGetErrorString(e));
+    iamfb_batch_destroy(b);
+    return r;
+  }
+  int r = iamfb_batch_reset(b);
+  if (r) { iamfb_batch_destroy(b); return r; }
+  *out = b;
+  return IAMFB_OK;
+}
+
+static void free_staging(iamfb_batch *b) {
+  for (int e = 0; e < kMaxEl; ++e) { cudaFree(b->d_in[e]); cudaFree(b->d_ramp[e]); b->d_in[e] = b->d_ramp[e] = nullptr; }
+  cudaFree(b->d_oramp); cudaFree(b->d_params); cudaFree(b->d_pcm); cudaFree(b->d_counts);
+  b->d_oramp = nullptr; b->d_params = nullptr; b->d_pcm = nullptr; b->d_counts = nullptr;
+  b->stage_frames = 0;
+}
+
+extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
+  if (!b) return;
+  cudaFree(b->d_state); cudaFree(b->d_frames); cudaFree(b->d_submit);
+  cudaFree(b->d_tl_a); cudaFree(b->d_tl_b); cudaFree(b->d_pk); cudaFree(b->d_wm); cudaFree(b->d_gn);
+  free_staging(b);
+  delete b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel sequencing
+// ---------------------------------------------------------------------------------------------------------------------
+#define LAUNCH_CHECK(name)                                                                                      \
+  do {                                                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                                        \
+    if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    ++ctx->launches;                                                                                            \
+  } while (0)
+
+template <int VEC>
+static int launch_render(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const RenderArgs &ra, int blocks) {
+  cudaStream_t st = ctx->stream;
+#define RCASE(ID, LAYOUT, NREC) \
+  case ID: k_render<LAYOUT, NREC, VEC><<<blocks, 128, 0, st>>>(kp, ra); break;
+  switch (tmpl) {
+    RCASE(0, 0, 1) RCASE(1, 1, 2) RCASE(2, 2, 6) RCASE(3, 3, 8) RCASE(4, 4, 10) RCASE(5, 5, 8) RCASE(6, 6, 10)
+    RCASE(7, 7, 12) RCASE(8, 8, 6)
+    RCASE(10, -1, 1) RCASE(11, -1, 4) RCASE(12, -1, 9) RCASE(13, -1, 16)
+    default: return fail(IAMFB_ERR_INTERNAL, "no render kernel variant %d", tmpl);
+  }
+#undef RCASE
+  LAUNCH_CHECK("k_render");
+  return IAMFB_OK;
+}
+
+static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, void *pcm, int32_t *counts, size_t stride) {
+  iamfb_plan *p = b->plan;
+  iamfb_ctx *ctx = p->ctx;
+  const KernelPlan &kp = p->kp;
+  cudaStream_t st = ctx->stream;
+  const int S = b->S, N = kp.frame_size, co = kp.out_channels;
+
+  // K0
+  {
+    ResolveArgs a;
+    a.params = flush ? nullptr : io->params;
+    a.state = b->d_state;
+    a.frames = b->d_frames;
+    a.submit = b->d_submit;
+    a.out_counts = counts;
+    a.qf_table = p->d_qf;
+    a.n_streams = S;
+    a.n_frames = flush ? 0 : F;
+    a.flush = flush ? 1 : 0;
+    k_resolve<<<(S + 127) / 128, 128, 0, st>>>(kp, a);
+    LAUNCH_CHECK("k_resolve");
+  }
+  float *tl_first = kp.resample ? b->d_tl_a : b->d_tl_b;
+  const int cap_first = kp.resample ? b->cap_a : b->cap_b;
+  const int hist_first = kp.resample ? kRsHist : kp.hist;
+
+  if (!flush) {
+    // K1 per element
+    const bool vec4 = (N % 4) == 0;
+    const int vec = vec4 ? 4 : 1;
+    const int tiles = (N + 128 * vec - 1) / (128 * vec);
+    for (int e = 0; e < kp.n_elements; ++e) {
+      RenderArgs ra;
+      ra.in = io->in[e];
+      ra.frames = b->d_frames;
+      ra.gain_ramp = io->gain_ramp[e];
+      ra.out_gain_ramp = io->out_gain_ramp;
+      ra.start_win = p->d_start_win;
+      ra.stop_win = p->d_stop_win;
+      ra.tl = tl_first;
+      ra.pk = (!kp.resample && kp.limiter) ? b->d_pk : nullptr;
+      ra.cap = cap_first;
+      ra.hist = hist_first;
+      ra.n_frames = F;
+      ra.e = e;
+      ra.first = e == 0;
+      ra.last = e == kp.n_elements - 1;
+      ra.tiles_per_frame = tiles;
+      int blocks = S * F * tiles;
+      int r = vec4 ? launch_render<4>(ctx, p->tmpl[e], kp, ra, blocks) : launch_render<1>(ctx, p->tmpl[e], kp, ra, blocks);
+      if (r) return r;
+    }
+  } else {
+    // flush: the resampler is fed filt_len/2 zeros, the limiter the resampler tail followed by 240 zeros
+    if (kp.resample) {
+      for (int s = 0; s < 1; ++s) {}
+      CU(cudaMemset2DAsync(b->d_tl_a + kRsHist, sizeof(float) * b->cap_a, 0, sizeof(float) * 64, (size_t)S * co, st));
+    }
+    CU(cudaMemset2DAsync(b->d_tl_b + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * (kLimDelay + 64), (size_t)S * co, st));
+    if (b->d_pk) CU(cudaMemset2DAsync(b->d_pk + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * (kLimDelay + 64), (size_t)S, st));
+  }
+
+  const int max_out = flush ? (kLimDelay + 64) : iamfb_plan_max_out_samples(p, F);
+  if (kp.resample) {
+    ResampleArgs a;
+    a.src = b->d_tl_a;
+    a.dst = b->d_tl_b;
+    a.pk = b->d_pk;
+    a.submit = b->d_submit;
+    a.state = b->d_state;
+    a.sinc = p->d_sinc;
+    a.cap_a = b->cap_a;
+    a.cap_b = b->cap_b;
+    a.hist_b = kp.hist;
+    a.max_out = max_out;
+    a.flush = flush ? 1 : 0;
+    dim3 grid((max_out + 127) / 128, S);
+    size_t smem = p->sinc_len <= 12 * 1024 ? sizeof(float) * p->sinc_len : 0;
+    k_resample<<<grid, 128, smem, st>>>(kp, a);
+    LAUNCH_CHECK("k_resample");
+    if (!flush) {
+      CarryArgs c;
+      c.tl = b->d_tl_a; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_a; c.hist = kRsHist; c.use_in_len = 1;
+      k_carry<<<dim3(co, S), 256, 0, st>>>(c);
+      LAUNCH_CHECK("k_carry");
+    }
+  }
+  if (kp.limiter) {
+    WmaxArgs w;
+    w.pk = b->d_pk; w.wm = b->d_wm; w.submit = b->d_submit; w.cap = b->cap_b; w.hist = kp.hist; w.flush = flush;
+    k_window_max<<<dim3((max_out + kWmTile - 1) / kWmTile, S), 256, 0, st>>>(kp, w);
+    LAUNCH_CHECK("k_window_max");
+    ScanArgs sa;
+    sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = b->d_submit; sa.acc = p->d_acc;
+    sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = max_out;
+    k_limiter_scan<<<(S + 127) / 128, 128, 0, st>>>(kp, sa);
+    LAUNCH_CHECK("k_limiter_scan");
+  }
+  {
+    OutputArgs o;
+    o.tl = b->d_tl_b; o.gn = kp.limiter ? b->d_gn : nullptr; o.submit = b->d_submit; o.pcm = pcm;
+    o.stride_bytes = stride; o.cap = b->cap_b; o.hist = kp.hist;
+    k_output<<<dim3((max_out + 255) / 256, S), 256, 0, st>>>(kp, o);
+    LAUNCH_CHECK("k_output");
+  }
+  if (kp.limiter && !flush) {
+    CarryArgs c;
+    c.tl = b->d_tl_b; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_b; c.hist = kLimDelay; c.use_in_len = 0;
+    k_carry<<<dim3(co, S), 256, 0, st>>>(c);
+    LAUNCH_CHECK("k_carry");
+    c.tl = b->d_pk; c.rows = 1;
+    k_carry<<<dim3(1, S), 256, 0, st>>>(c);
+    LAUNCH_CHECK("k_carry");
+  }
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_batch_submit_device(iamfb_batch *b, const iamfb_io *io, int n_frames) {
+  if (!b || !io) return fail(IAMFB_ERR_BAD_ARG, "submit: null argument");
+  if (n_frames <= 0 || n_frames > b->Fmax) return fail(IAMFB_ERR_BAD_ARG, "submit: %d frames (batch sized for %d)", n_frames, b->Fmax);
+  for (int e = 0; e < b->plan->kp.n_elements; ++e)
+    if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
+  if (!io->params || !io->pcm) return fail(IAMFB_ERR_BAD_ARG, "submit: params / pcm is null");
+  CU(cudaSetDevice(b->plan->ctx->device));
+  return run_pipeline(b, io, n_frames, false, io->pcm, io->out_counts, iamfb_plan_out_stride_bytes(b->plan, n_frames));
+}
+
+extern "C" int iamfb_batch_flush_device(iamfb_batch *b, void *pcm, int32_t *counts) {
+  if (!b || !pcm) return fail(IAMFB_ERR_BAD_ARG, "flush: null argument");
+  CU(cudaSetDevice(b->plan->ctx->device));
+  if (!b->plan->kp.limiter && !b->plan->kp.resample) {   // iamf_delay_buffer_handle returns 0 (:3259-3260)
+    if (counts) CU(cudaMemsetAsync(counts, 0, sizeof(int32_t) * b->S, b->plan->ctx->stream));
+    return IAMFB_OK;
+  }
+  return run_pipeline(b, nullptr, 0, true, pcm, counts, iamfb_plan_out_stride_bytes(b->plan, 1));
+}
+
+static int ensure_staging(iamfb_batch *b, int F) {
+  if ((size_t)F <= b->stage_frames) return IAMFB_OK;
+  free_staging(b);
+  const KernelPlan &kp = b->plan->kp;
+  const size_t S = b->S, N = kp.frame_size;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void **ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
+  for (int el = 0; el < kp.n_elements; ++el) {
+    alloc((void **)&b->d_in[el], sizeof(float) * S * F * kp.el[el].n_in * N);
+    alloc((void **)&b->d_ramp[el], sizeof(float) * S * F * N);
+  }
+  alloc((void **)&b->d_oramp, sizeof(float) * S * F * N);
+  alloc((void **)&b->d_params, sizeof(iamfb_frame_params) * S * F);
+  alloc((void **)&b->d_pcm, S * iamfb_plan_out_stride_bytes(b->plan, F));
+  alloc((void **)&b->d_counts, sizeof(int32_t) * S * (F > 1 ? F : 1));
+  if (e != cudaSuccess) { free_staging(b); return fail(IAMFB_ERR_ALLOC_FAIL, "staging allocation failed: %s", cudaGetErrorString(e)); }
+  b->stage_frames = F;
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F) {
+  if (!b || !io) return fail(IAMFB_ERR_BAD_ARG, "submit: null argument");
+  if (F <= 0 || F > b->Fmax) return fail(IAMFB_ERR_BAD_ARG, "submit: %d frames (batch sized for %d)", F, b->Fmax);
+  if (!io->params || !io->pcm) return fail(IAMFB_ERR_BAD_ARG, "submit: params / pcm is null");
+  iamfb_plan *p = b->plan;
+  CU(cudaSetDevice(p->ctx->device));
+  int r = ensure_staging(b, F);
+  if (r) return r;
+  const KernelPlan &kp = p->kp;
+  cudaStream_t st = p->ctx->stream;
+  const size_t S = b->S, N = kp.frame_size;
+  iamfb_io dio;
+  memset(&dio, 0, sizeof(dio));
+  for (int e = 0; e < kp.n_elements; ++e) {
+    if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
+    CU(cudaMemcpyAsync(b->d_in[e], io->in[e], sizeof(float) * S * F * kp.el[e].n_in * N, cudaMemcpyHostToDevice, st));
+    dio.in[e] = b->d_in[e];
+    if (io->gain_ramp[e]) {
+      CU(cudaMemcpyAsync(b->d_ramp[e], io->gain_ramp[e], sizeof(float) * S * F * N, cudaMemcpyHostToDevice, st));
+      dio.gain_ramp[e] = b->d_ramp[e];
+    }
+  }
+  if (io->out_gain_ramp) {
+    CU(cudaMemcpyAsync(b->d_oramp, io->out_gain_ramp, sizeof(float) * S * F * N, cudaMemcpyHostToDevice, st));
+    dio.out_gain_ramp = b->d_oramp;
+  }
+  CU(cudaMemcpyAsync(b->d_params, io->params, sizeof(iamfb_frame_params) * S * F, cudaMemcpyHostToDevice, st));
+  dio.params = b->d_params;
+  dio.pcm = b->d_pcm;
+  dio.out_counts = b->d_counts;
+  const size_t stride = iamfb_plan_out_stride_bytes(p, F);
+  r = run_pipeline(b, &dio, F, false, b->d_pcm, b->d_counts, stride);
+  if (r) return r;
+  CU(cudaMemcpyAsync(io->pcm, b->d_pcm, S * stride, cudaMemcpyDeviceToHost, st));
+  if (io->out_counts) CU(cudaMemcpyAsync(io->out_counts, b->d_counts, sizeof(int32_t) * S * F, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_batch_flush_host(iamfb_batch *b, void *pcm, int32_t *counts) {
+  if (!b || !pcm) return fail(IAMFB_ERR_BAD_ARG, "flush: null argument");
+  iamfb_plan *p = b->plan;
+  CU(cudaSetDevice(p->ctx->device));
+  int r = ensure_staging(b, 1);
+  if (r) return r;
+  cudaStream_t st = p->ctx->stream;
+  const size_t stride = iamfb_plan_out_stride_bytes(p, 1);
+  r = iamfb_batch_flush_device(b, b->d_pcm, b->d_counts);
+  if (r) return r;
+  CU(cudaMemcpyAsync(pcm, b->d_pcm, (size_t)b->S * stride, cudaMemcpyDeviceToHost, st));
+  if (counts) CU(cudaMemcpyAsync(counts, b->d_counts, sizeof(int32_t) * b->S, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return IAMFB_OK;
+}

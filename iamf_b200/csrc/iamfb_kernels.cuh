@@ -1,0 +1,898 @@
+// iamfb_kernels.cuh - hand-written sm_100a kernels of the post-decode rendering path.
+//
+// Arithmetic contract: every expression below is evaluated in the SAME order and precision as the reference C code
+// it replaces (strict IEEE-754 binary32, one double-precision expression in the S2->S3 de-mixer), so this TU is
+// compiled with --fmad=false and uses true divisions.  Results are bit-identical to the reference, not merely
+// within tolerance; the reference location is cited beside each block.
+//
+// Data layout in HBM (S streams, F frames per submit, N samples per frame):
+//   in[e]      f32 [S][F][C_in][N]        decoded planar frames (as core decode hands them over)
+//   tl_a       f32 [S][C_out][cap_a]      pre-resample time line (kRsHist history + F*N), only when resampling
+//   tl_b       f32 [S][C_out][cap_b]      mixed time line entering the limiter: [hist | samples of this submit]
+//   pk         f32 [S][cap_b]             per-instant cross-channel peak max_c |x|, same time axis as tl_b
+//   gn         f32 [S][cap_b]             limiter gain per instant
+//   pcm        int16/24/32 [S][stride]    interleaved output
+#pragma once
+#include <cuda_runtime.h>
+
+#include "iamfb_types.cuh"
+
+namespace iamfb {
+
+// -------------------------------------------------------------------------------------------------------------------
+// small device helpers
+// -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+  // streaming read: decoded PCM is touched exactly once -> do not allocate it in L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// demixing_type_mat (demixer.c:62-72): mode -> alpha, beta, gamma, delta, w step
+__constant__ float c_mix_alpha[8] = {1.0f, 0.707f, 1.0f, 0.f, 1.0f, 0.707f, 1.0f, 0.f};
+__constant__ float c_mix_beta[8] = {1.0f, 0.707f, 0.866f, 0.f, 1.0f, 0.707f, 0.866f, 0.f};
+__constant__ float c_mix_gamma[8] = {0.707f, 0.707f, 0.866f, 0.f, 0.707f, 0.707f, 0.866f, 0.f};
+__constant__ float c_mix_delta[8] = {0.707f, 0.707f, 0.866f, 0.f, 0.707f, 0.707f, 0.866f, 0.f};
+__constant__ int c_mix_woff[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+// widx2w_table (fixedp11_5.c:81-82)
+__constant__ float c_w_table[11] = {0.0f, 0.0179f, 0.0391f, 0.0658f, 0.1038f, 0.25f, 0.3962f, 0.4342f, 0.4609f, 0.4821f, 0.5f};
+// recon channel bit -> IAChannel per layout (IAMF_decoder.c:409-448)
+__constant__ unsigned char c_recon_map[9][12] = {
+    {13, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},        {14, 0, 15, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+    {1, 3, 2, 20, 21, 0, 0, 0, 0, 0, 0, 4},       {1, 3, 2, 20, 21, 22, 23, 0, 0, 0, 0, 4},
+    {1, 3, 2, 20, 21, 9, 10, 0, 0, 11, 12, 4},    {1, 3, 2, 5, 6, 0, 0, 7, 8, 0, 0, 4},
+    {1, 3, 2, 5, 6, 22, 23, 7, 8, 0, 0, 4},       {1, 3, 2, 5, 6, 9, 10, 7, 8, 11, 12, 4},
+    {18, 3, 19, 0, 0, 16, 17, 0, 0, 0, 0, 4}};
+
+// -------------------------------------------------------------------------------------------------------------------
+// K0: parameter resolve - one thread per stream walks the F frames of the submit and turns raw parameter-block
+// values into the per-frame scalars the sample kernels need, carrying the metadata state machines of
+//   demixer_set_demixing_info / calc_w            demixer.c:592-619, fixedp11_5.c:83-90
+//   iamf_stream_scale_decoder_update_recon_gain   IAMF_decoder.c:2238-2274
+//   demixer_set_recon_gain + dmx_rms smoothing    demixer.c:621-634, 443-475
+//   DMRenderer_set_mode_weight                    downmix_renderer.c:180-216
+//   frame trimming / time-line placement          IAMF_decoder.c:3354-3407
+//   resampler output count (closed form)          resample.c:357-418, SURVEY 9.4-3
+//   limiter priming (padsize)                     audio_effect_peak_limiter.c:185-201
+// -------------------------------------------------------------------------------------------------------------------
+struct ResolveArgs {
+  const iamfb_frame_params *params;   // [S][F]
+  StreamState *state;                 // [S]
+  FrameRec *frames;                   // [S][F]
+  SubmitRec *submit;                  // [S]
+  int32_t *out_counts;                // [S][F] (device copy of what decode() returns per frame)
+  const float *qf_table;              // 256 entries: (float)(q / 255.0)  (fixedp11_5.c:53-55)
+  int n_streams, n_frames;
+  int flush;                          // end-of-stream pass: no frames, 240 limiter zeros (+ resampler tail)
+};
+
+__device__ __forceinline__ long long rs_outputs_until(const KernelPlan &p, long long in_total) {
+  // number of outputs n >= 0 with  filt_len/2 + int_adv*n + floor(frac_adv*n/den) < in_total
+  long long lim = in_total - (long long)(p.rs_filt_len / 2);
+  if (lim <= 0) return 0;
+  // q(n) = (num*n) / den  (num = int_adv*den + frac_adv);   q(n) < lim  <=>  num*n < lim*den
+  //   <=> n <= (lim*den - 1) / num
+  long long num = (long long)p.rs_num, den = (long long)p.rs_den;
+  return (lim * den - 1) / num + 1;
+}
+
+__global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.n_streams) return;
+  StreamState st = a.state[s];
+  const int N = plan.frame_size;
+  int t_off = 0;
+  long long rs_out0 = st.rs_out_total;
+  int pad_at_start = st.lim_pad;
+  int lim_in_total = 0;
+
+  for (int f = 0; f < a.n_frames; ++f) {
+    const iamfb_frame_params fp = a.params[(size_t)s * a.n_frames + f];
+    FrameRec fr;
+    for (int e = 0; e < plan.n_elements; ++e) {
+      const ElPlan &ep = plan.el[e];
+      ElState &es = st.el[e];
+      ElFrame &ef = fr.el[e];
+      ef.gain = fp.el[e].mix_gain;
+      ef.rmask = 0;
+      ef.mode = 0;
+      ef.w = 0.f;
+      ef.dmr_alpha = ef.dmr_beta = ef.dmr_gamma = ef.dmr_delta = ef.dmr_tl = 0.f;
+      for (int m = 0; m < IAMFB_MAX_LAYOUT_CH; ++m) { ef.rlast[m] = 1.f; ef.rcur[m] = 1.f; }
+      if (ep.kind != IAMFB_EL_CHANNEL) continue;
+
+      // --- recon gain list of the selected layer (latest received wins), IAMF_decoder.c:2238-2274
+      if (fp.el[e].has_recon) {
+        unsigned int fl = fp.el[e].recon_flags;
+        if (st.re_flags[e] ^ fl) {
+          st.re_flags[e] = fl;
+          int n = 0;
+          for (int b = 0; b < 12; ++b)
+            if (fl & (1u << b)) st.re_ch[e][n++] = c_recon_map[ep.layout][b];
+          st.re_count[e] = n;
+        }
+        for (int c = 0; c < st.re_count[e]; ++c) st.re_gain[e][c] = a.qf_table[fp.el[e].recon_gain[c]];
+      }
+      // --- demixer_set_recon_gain, demixer.c:621-634 (called every frame when the layer has a recon list)
+      if (ep.recon_present) {
+        unsigned int fl = st.re_flags[e];
+        int cnt = st.re_count[e];
+        if (fl && (fl ^ es.rflags)) {
+          for (int i = 0; i < cnt; ++i) es.rch[i] = st.re_ch[e][i];
+          es.rcount = cnt;
+          es.rflags = fl;
+        }
+        for (int i = 0; i < cnt; ++i) es.rgain[i] = st.re_gain[e][i];
+      }
+      // --- demixer_set_demixing_info(mode, -1), demixer.c:592-619
+      int mode = fp.el[e].dmx_mode;
+      if (mode >= 0 && mode != 3 && mode <= 6) {
+        es.mode = mode;
+        int off = c_mix_woff[mode];
+        es.w_idx = off > 0 ? min(es.w_idx + 1, 10) : max(es.w_idx - 1, 0);
+      }
+      ef.mode = es.mode;
+      ef.w = c_w_table[min(max(es.w_idx, 0), 10)];
+      // --- dmx_rms factor update, demixer.c:443-475: sfavg = 0.25*sf + 0.75*last
+      for (int c = 0; c < es.rcount; ++c) {
+        int ch = es.rch[c];
+        float sf = es.rgain[c];
+        float last = es.sfavg[ch];
+        float Nf = 7.f;
+        float sfavg = (2 / (Nf + 1)) * sf + (1 - 2 / (Nf + 1)) * last;
+        for (int m = 0; m < ep.n_rec; ++m)
+          if (ep.rec_ch[m] == ch) {
+            ef.rmask |= 1u << m;
+            ef.rlast[m] = last;
+            ef.rcur[m] = sfavg;
+          }
+        es.sfavg[ch] = sfavg;
+      }
+      // --- DMRenderer_set_mode_weight(mode, -1), downmix_renderer.c:180-216
+      if (ep.renderer == kRdrDMR) {
+        if (mode >= 0 && mode != 3 && mode < 7) {
+          es.dmr_mode = mode;
+          int nw = c_mix_woff[mode] > 0 ? min(es.dmr_w_idx + 1, 10) : max(es.dmr_w_idx - 1, 0);
+          es.dmr_w_idx = nw;
+          bool tl_derived = !((ep.dmr_in_mask >> IAMFB_CH_TL) & 1u) && !((ep.dmr_in_mask >> IAMFB_CH_TR) & 1u);
+          if (tl_derived) es.dmr_tl = c_mix_gamma[mode] * c_w_table[nw];
+        }
+        int dm = es.dmr_mode & 7;
+        ef.dmr_alpha = c_mix_alpha[dm];
+        ef.dmr_beta = c_mix_beta[dm];
+        ef.dmr_gamma = c_mix_gamma[dm];
+        ef.dmr_delta = c_mix_delta[dm];
+        ef.dmr_tl = es.dmr_tl;
+      }
+    }
+    fr.out_gain = fp.out_gain;
+    // --- trimming: a fully trimmed frame is decoded (state above advances) but dropped, IAMF_decoder.c:3354-3358
+    int ts = fp.trim_start, te = fp.trim_end;
+    int vlen = N - ts - te;
+    if (ts == N || te == N || vlen < 0) vlen = 0;
+    fr.vstart = ts;
+    fr.vlen = vlen;
+    fr.t_off = t_off;
+    t_off += vlen;
+    a.frames[(size_t)s * a.n_frames + f] = fr;
+
+    // --- per-frame sample count returned to the caller
+    int cnt = vlen;
+    if (vlen > 0 && plan.resample) {
+      long long before = rs_outputs_until(plan, st.rs_in_total);
+      st.rs_in_total += vlen;
+      long long after = rs_outputs_until(plan, st.rs_in_total);
+      cnt = (int)(after - before);
+    }
+    if (vlen > 0 && plan.limiter) {
+      lim_in_total += cnt;
+      if (!st.lim_init) {
+        if (st.lim_pad >= cnt) { st.lim_pad -= cnt; cnt = 0; }
+        else { cnt -= st.lim_pad; st.lim_pad = 0; st.lim_init = 1; }
+      }
+    } else if (vlen > 0) {
+      lim_in_total += cnt;
+    }
+    if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = cnt;
+  }
+
+  SubmitRec sr;
+  sr.in_len = t_off;
+  sr.rs_out_first = rs_out0;
+  if (a.flush) {
+    // iamf_delay_buffer_handle, IAMF_decoder.c:3250-3301: resampler fed filt_len/2 zeros (output capped at the
+    // output latency), then the limiter is fed that tail followed by delaySize zeros.
+    int tail = 0;
+    if (plan.resample) {
+      long long before = rs_outputs_until(plan, st.rs_in_total);
+      long long after = rs_outputs_until(plan, st.rs_in_total + plan.rs_filt_len / 2);
+      long long lat = ((long long)(plan.rs_filt_len / 2) * plan.rs_den + (plan.rs_num >> 1)) / plan.rs_num;
+      tail = (int)min(after - before, lat);
+      st.rs_in_total += plan.rs_filt_len / 2;
+    }
+    int cnt = tail;
+    if (plan.limiter) {
+      cnt = tail + kLimDelay;
+      lim_in_total = cnt;
+      if (!st.lim_init) {
+        if (st.lim_pad >= cnt) { st.lim_pad -= cnt; cnt = 0; }
+        else { cnt -= st.lim_pad; st.lim_pad = 0; st.lim_init = 1; }
+      }
+    } else {
+      lim_in_total = cnt;
+    }
+    sr.in_len = plan.resample ? (int)(plan.rs_filt_len / 2) : 0;
+    if (a.out_counts) a.out_counts[s] = cnt;
+  }
+  sr.lim_len = lim_in_total;
+  sr.out_skip = pad_at_start - st.lim_pad;
+  sr.out_len = lim_in_total - sr.out_skip;
+  st.rs_out_total = rs_out0 + (plan.resample ? (long long)lim_in_total - (a.flush && plan.limiter ? kLimDelay : 0) : 0);
+  a.submit[s] = sr;
+  a.state[s] = st;
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// K1: reconstruct + render + gains (+ element sum) for one audio element.
+//   thread = VEC consecutive samples of one (stream, frame); block = 128 threads = one 128*VEC-sample tile.
+//   Everything between the decoded frame and the mixed time line stays in registers.
+// -------------------------------------------------------------------------------------------------------------------
+struct RenderArgs {
+  const float *in;          // [S][F][n_in][N]
+  const FrameRec *frames;   // [S][F]
+  const float *gain_ramp;   // optional [S][F][N]
+  const float *out_gain_ramp;
+  const float *start_win;   // [overlap] hann[j]          (demixer.c:549-552)
+  const float *stop_win;    // [overlap] hann[j+overlap]
+  float *tl;                // destination time line [S][C_out][cap]
+  float *pk;                // [S][cap] or nullptr
+  int cap, hist;            // row stride and history offset of tl / pk
+  int n_frames, e;          // element index
+  int first, last;          // first element writes, later ones accumulate; the last applies output gain/loudness/peak
+  int tiles_per_frame;
+};
+
+template <int VEC>
+struct Vec {
+  float v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> load_row(const float *p, bool vec_ok, int valid) {
+  Vec<VEC> r;
+  if constexpr (VEC == 4) {
+    if (vec_ok) {
+      float4 t = ldg_stream4(p);
+      r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+      return r;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) r.v[k] = k < valid ? ldg_stream1(p + k) : 0.f;
+  return r;
+}
+
+// Channel-based reconstruction of the VEC samples held by this thread: fills v[IAChannel][k].
+// Follows dmx_gainup, dmx_s2..dmx_h4 and dmx_rms of demixer.c (skip == 0: codec delay is 0 on this path).
+template <int VEC>
+__device__ __forceinline__ void reconstruct_channels(const ElPlan &ep, const ElFrame &ef, const float *in_frame, int N,
+                                                     int i0, bool vec_ok, int valid, const float *start_win,
+                                                     const float *stop_win, int overlap, Vec<VEC> (&v)[kChCount]) {
+  // transmitted channels -> IAChannel slots (static register indices, uniform predicates)
+#pragma unroll
+  for (int c = 1; c < kChCount; ++c) {
+    int row = ep.src_row[c];
+    if (row >= 0) {
+      v[c] = load_row<VEC>(in_frame + (size_t)row * N + i0, vec_ok, valid);
+      if ((ep.gain_mask >> c) & 1u) {   // dmx_gainup, demixer.c:421-430
+        float g = ep.gain[c];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[c].v[k] *= g;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[c].v[k] = 0.f;
+    }
+  }
+  const int mode = ef.mode & 7;
+  if (ep.need_s2) {   // R2 = 2*Mono - L2, demixer.c:136-138
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[IAMFB_CH_R2].v[k] = 2 * v[IAMFB_CH_MONO].v[k] - v[IAMFB_CH_L2].v[k];
+  }
+  if (ep.need_s3) {   // L3 = L2 - 0.707*C evaluated in double, demixer.c:165-168
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      double c = (double)v[IAMFB_CH_C].v[k];
+      v[IAMFB_CH_L3].v[k] = (float)((double)v[IAMFB_CH_L2].v[k] - 0.707 * c);
+      v[IAMFB_CH_R3].v[k] = (float)((double)v[IAMFB_CH_R2].v[k] - 0.707 * c);
+    }
+  }
+  if (ep.need_s5) {   // Ls5 = (L3 - L5)/delta, demixer.c:213-218
+    float d = c_mix_delta[mode];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      v[IAMFB_CH_SL5].v[k] = (v[IAMFB_CH_L3].v[k] - v[IAMFB_CH_L5].v[k]) / d;
+      v[IAMFB_CH_SR5].v[k] = (v[IAMFB_CH_R3].v[k] - v[IAMFB_CH_R5].v[k]) / d;
+    }
+  }
+  if (ep.need_s7) {   // Lb7 = (Ls5 - alpha*Lss7)/beta, demixer.c:262-269
+    float al = c_mix_alpha[mode], be = c_mix_beta[mode];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      v[IAMFB_CH_BL7].v[k] = (v[IAMFB_CH_SL5].v[k] - v[IAMFB_CH_SL7].v[k] * al) / be;
+      v[IAMFB_CH_BR7].v[k] = (v[IAMFB_CH_SR5].v[k] - v[IAMFB_CH_SR7].v[k] * al) / be;
+    }
+  }
+  if (ep.need_h2) {   // Ltf2 = Ltf3 - delta*w*Ls5, demixer.c:318-323
+    float dw = c_mix_delta[mode] * ef.w;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      v[IAMFB_CH_HL].v[k] = v[IAMFB_CH_TL].v[k] - dw * v[IAMFB_CH_SL5].v[k];
+      v[IAMFB_CH_HR].v[k] = v[IAMFB_CH_TR].v[k] - dw * v[IAMFB_CH_SR5].v[k];
+    }
+  }
+  if (ep.need_h4) {   // Ltb = (Ltf2 - Ltf4)/gamma, demixer.c:363-368
+    float ga = c_mix_gamma[mode];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      v[IAMFB_CH_HBL].v[k] = (v[IAMFB_CH_HL].v[k] - v[IAMFB_CH_HFL].v[k]) / ga;
+      v[IAMFB_CH_HBR].v[k] = (v[IAMFB_CH_HR].v[k] - v[IAMFB_CH_HFR].v[k]) / ga;
+    }
+  }
+}
+
+// value of IAChannel `ch` as the parametric down-mixer computes it (downmix_renderer.c:65-75,115-129):
+// an input channel is passed through, everything else is the ordered two-term sum of its dependencies.
+template <int VEC>
+__device__ __forceinline__ void dmr_prepare(const ElPlan &ep, const ElFrame &ef, Vec<VEC> (&v)[kChCount]) {
+  const unsigned int inm = ep.dmr_in_mask;
+  auto is_in = [&](int c) { return (inm >> c) & 1u; };
+  auto two = [&](int dst, int a, float sa, int b, float sb) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float sum = 0.f;
+      sum += v[a].v[k] * sa;
+      sum += v[b].v[k] * sb;
+      v[dst].v[k] = sum;
+    }
+  };
+  // dependency order: SL5 <- SL7,BL7 ; L3 <- L5,SL5 ; L2 <- L3,C ; HL <- HFL,HBL ; TL <- HL,SL5 ; Mono <- R2,L2
+  if (!is_in(IAMFB_CH_SL5)) two(IAMFB_CH_SL5, IAMFB_CH_SL7, ef.dmr_alpha, IAMFB_CH_BL7, ef.dmr_beta);
+  if (!is_in(IAMFB_CH_SR5)) two(IAMFB_CH_SR5, IAMFB_CH_SR7, ef.dmr_alpha, IAMFB_CH_BR7, ef.dmr_beta);
+  if (!is_in(IAMFB_CH_L3)) two(IAMFB_CH_L3, IAMFB_CH_L5, 1.f, IAMFB_CH_SL5, ef.dmr_delta);
+  if (!is_in(IAMFB_CH_R3)) two(IAMFB_CH_R3, IAMFB_CH_R5, 1.f, IAMFB_CH_SR5, ef.dmr_delta);
+  if (!is_in(IAMFB_CH_L2)) two(IAMFB_CH_L2, IAMFB_CH_L3, 1.f, IAMFB_CH_C, 0.707f);
+  if (!is_in(IAMFB_CH_R2)) two(IAMFB_CH_R2, IAMFB_CH_R3, 1.f, IAMFB_CH_C, 0.707f);
+  if (!is_in(IAMFB_CH_HL)) two(IAMFB_CH_HL, IAMFB_CH_HFL, 1.f, IAMFB_CH_HBL, ef.dmr_gamma);
+  if (!is_in(IAMFB_CH_HR)) two(IAMFB_CH_HR, IAMFB_CH_HFR, 1.f, IAMFB_CH_HBR, ef.dmr_gamma);
+  if (!is_in(IAMFB_CH_TL)) two(IAMFB_CH_TL, IAMFB_CH_HL, 1.f, IAMFB_CH_SL5, ef.dmr_tl);
+  if (!is_in(IAMFB_CH_TR)) two(IAMFB_CH_TR, IAMFB_CH_HR, 1.f, IAMFB_CH_SR5, ef.dmr_tl);
+  if (!is_in(IAMFB_CH_MONO)) two(IAMFB_CH_MONO, IAMFB_CH_R2, 0.5f, IAMFB_CH_L2, 0.5f);
+}
+
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> pick_channel(const Vec<VEC> (&v)[kChCount], int ch) {
+  Vec<VEC> r;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) r.v[k] = 0.f;
+  // uniform switch with static register reads in every arm (avoids dynamically indexed registers)
+#pragma unroll
+  for (int c = 1; c < kChCount; ++c)
+    if (ch == c) r = v[c];
+  return r;
+}
+
+// LAYOUT >= 0: channel based element with that reconstructed layout (x[m] gathered with static indices);
+// LAYOUT == -1: scene based element (NREC = ambisonics channel count).
+template <int LAYOUT, int NREC, int VEC>
+__global__ void __launch_bounds__(128) k_render(const __grid_constant__ KernelPlan plan, RenderArgs a) {
+  const int N = plan.frame_size;
+  const int tile = blockIdx.x % a.tiles_per_frame;
+  const int sf = blockIdx.x / a.tiles_per_frame;          // s * F + f
+  const int s = sf / a.n_frames;
+  const int i0 = (tile * 128 + threadIdx.x) * VEC;         // first sample of this thread inside the frame
+  if (i0 >= N) return;
+  const FrameRec &fr = a.frames[sf];
+  const int vstart = fr.vstart, vlen = fr.vlen;
+  if (vlen <= 0) return;
+  // samples of this thread that survive trimming
+  const int lo = max(i0, vstart), hi = min(i0 + VEC, vstart + vlen);
+  if (lo >= hi) return;
+  const ElPlan &ep = plan.el[a.e];
+  const ElFrame &ef = fr.el[a.e];
+  const int valid = min(VEC, N - i0);
+  const bool vec_ok = (VEC == 4) && ((N & 3) == 0) && valid == VEC;
+  const float *in_frame = a.in + (size_t)sf * ep.n_in * N;
+
+  Vec<VEC> x[NREC];   // channels entering the renderer, in renderer order
+  Vec<VEC> v[(LAYOUT >= 0) ? kChCount : 1];
+
+  if constexpr (LAYOUT >= 0) {
+    reconstruct_channels<VEC>(ep, ef, in_frame, N, i0, vec_ok, valid, a.start_win, a.stop_win, plan.overlap, v);
+    // dmx_rms cross-fade, demixer.c:461-468: x *= last*stop[i] + cur*start[i]
+    constexpr unsigned char kOrder[9][12] = {
+        {13}, {14, 15}, {1, 2, 3, 4, 20, 21}, {1, 2, 3, 4, 20, 21, 22, 23}, {1, 2, 3, 4, 20, 21, 9, 10, 11, 12},
+        {1, 2, 3, 4, 5, 6, 7, 8}, {1, 2, 3, 4, 5, 6, 7, 8, 22, 23}, {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12},
+        {18, 19, 3, 4, 16, 17}};
+#pragma unroll
+    for (int m = 0; m < NREC; ++m) {
+      x[m] = v[kOrder[LAYOUT][m]];
+      if ((ef.rmask >> m) & 1u) {
+        const float last = ef.rlast[m], cur = ef.rcur[m];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          int i = i0 + k;
+          float st = 0.f, sw = 1.f;
+          if (i < plan.overlap) { st = a.stop_win[i]; sw = a.start_win[i]; }
+          float f = last * st + cur * sw;
+          x[m].v[k] *= f;
+        }
+      }
+    }
+    if (ep.renderer == kRdrDMR) {
+      // the down-mixer works on IAChannel slots: write the (recon-gained) layout channels back
+#pragma unroll
+      for (int m = 0; m < NREC; ++m) v[kOrder[LAYOUT][m]] = x[m];
+      dmr_prepare<VEC>(ep, ef, v);
+    }
+  } else {
+    // scene based: mono mapping is a row permutation, projection an ordered mat-vec (IAMF_core_decoder.c:105-130)
+    if (ep.ambi_mode == 0) {
+#pragma unroll
+      for (int m = 0; m < NREC; ++m) x[m] = load_row<VEC>(in_frame + (size_t)ep.ambi_map[m] * N + i0, vec_ok, valid);
+    } else {
+#pragma unroll
+      for (int m = 0; m < NREC; ++m)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) x[m].v[k] = .0f;
+      for (int l = 0; l < ep.ambi_cols; ++l) {
+        Vec<VEC> t = load_row<VEC>(in_frame + (size_t)l * N + i0, vec_ok, valid);
+#pragma unroll
+        for (int m = 0; m < NREC; ++m) {
+          float c = ep.ambi_mat[l * NREC + m];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) x[m].v[k] += t.v[k] * c;
+        }
+      }
+    }
+  }
+
+  // ---- render + gains, one output channel at a time so that only x[] stays live
+  const int co = plan.out_channels;
+  const size_t row0 = (size_t)s * co * a.cap;
+  const int t0 = a.hist + fr.t_off + (i0 - vstart);        // time-line index of sample i0
+  const bool st_vec = (VEC == 4) && lo == i0 && hi == i0 + VEC && ((t0 & 3) == 0) && ((a.cap & 3) == 0);
+  Vec<VEC> eg, og;   // element / output gain per sample
+  {
+    const bool eg_on = a.gain_ramp || (ef.gain != 1.f && ef.gain > 0.f);   // iamf_frame_gain, IAMF_decoder.c:1392
+    const bool og_on = a.out_gain_ramp || (fr.out_gain != 1.f && fr.out_gain > 0.f);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      int j = i0 + k - vstart;   // index inside the trimmed frame
+      bool in_rng = (i0 + k) >= lo && (i0 + k) < hi;
+      eg.v[k] = (a.gain_ramp && in_rng) ? a.gain_ramp[(size_t)sf * N + j] : (eg_on ? ef.gain : 1.f);
+      og.v[k] = (a.out_gain_ramp && in_rng) ? a.out_gain_ramp[(size_t)sf * N + j] : (og_on ? fr.out_gain : 1.f);
+    }
+  }
+  const bool loud_on = !plan.resample && plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
+  Vec<VEC> peak;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) peak.v[k] = 0.f;
+
+  for (int oc = 0; oc < co; ++oc) {
+    Vec<VEC> y;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) y.v[k] = 0.f;
+    if (ep.renderer == kRdrDMR) {
+      if constexpr (LAYOUT >= 0) {
+        if (oc < ep.dmr_n_out) y = pick_channel<VEC>(v, ep.dmr_out_ch[oc]);
+      }
+    } else {
+      // which matrix row lands on output channel oc (identity for M2M; LFE slots are zero for H2M)
+      int n = ep.out_slot[oc];
+      if (n >= 0) {
+        // IAMF_element_renderer_render_M2M / _H2M: out = 0; out += mat*in over inputs ascending
+        const float *mrow = ep.mat + n * NREC;
+#pragma unroll
+        for (int m = 0; m < NREC; ++m) {
+          const float c = mrow[m];
+          if (c != 0.f) {   // adding +-0 never changes the running sum (it starts at +0): exact skip
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) y.v[k] += c * x[m].v[k];
+          }
+        }
+      }
+    }
+    // element mix gain, IAMF_decoder.c:1392-1405
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (a.gain_ramp || eg.v[k] != 1.f) y.v[k] *= eg.v[k];
+
+    float *dst = a.tl + row0 + (size_t)oc * a.cap + t0;
+    // iamf_mixer_mix, IAMF_decoder.c:2719-2730: acc = 0; acc += e0; acc += e1
+    if (a.first) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) y.v[k] = 0.f + y.v[k];
+    } else {
+      if (st_vec) {
+        float4 p = *reinterpret_cast<const float4 *>(dst);
+        y.v[0] = p.x + y.v[0]; y.v[1 % VEC] = p.y + y.v[1 % VEC]; y.v[2 % VEC] = p.z + y.v[2 % VEC]; y.v[3 % VEC] = p.w + y.v[3 % VEC];
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          if ((i0 + k) >= lo && (i0 + k) < hi) y.v[k] = dst[k] + y.v[k];
+      }
+    }
+    if (a.last) {
+      // output mix gain (IAMF_decoder.c:3463-3469) then loudness (IAMF_decoder.c:3480-3484) when not resampling
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        if (a.out_gain_ramp || og.v[k] != 1.f) y.v[k] *= og.v[k];
+        if (loud_on) y.v[k] *= plan.loud_gain;
+        peak.v[k] = fmaxf(peak.v[k], fabsf(y.v[k]));
+      }
+    }
+    if (st_vec) {
+      *reinterpret_cast<float4 *>(dst) = make_float4(y.v[0], y.v[1 % VEC], y.v[2 % VEC], y.v[3 % VEC]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if ((i0 + k) >= lo && (i0 + k) < hi) dst[k] = y.v[k];
+    }
+  }
+  if (a.last && a.pk) {
+    float *pd = a.pk + (size_t)s * a.cap + t0;
+    if (st_vec) {
+      *reinterpret_cast<float4 *>(pd) = make_float4(peak.v[0], peak.v[1 % VEC], peak.v[2 % VEC], peak.v[3 % VEC]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if ((i0 + k) >= lo && (i0 + k) < hi) pd[k] = peak.v[k];
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// K2: Speex resampler, closed form.  Output n of a stream reads filt_len consecutive inputs ending at stream position
+//   q(n) = filt_len/2 + int_adv*n + floor(frac_adv*n/den)  with phase  phi(n) = (frac_adv*n) mod den
+// (resampler_basic_interpolate_single / _direct_single, resample.c:258-313,357-418; chunking of
+// speex_resampler_process_float :917-972 does not change results).  Output is clamped to +-1 (:84,959), then the
+// loudness gain is applied (IAMF_decoder.c:3480-3484) and the per-instant peak for the limiter is reduced.
+// thread = one output instant of one stream, looping over channels (taps are reused across channels).
+// -------------------------------------------------------------------------------------------------------------------
+struct ResampleArgs {
+  const float *src;        // tl_a [S][C][cap_a], history kRsHist.. input position p of this submit at kRsHist + p
+  float *dst;              // tl_b [S][C][cap_b]
+  float *pk;               // [S][cap_b]
+  const SubmitRec *submit;
+  const StreamState *state;   // state AFTER resolve (rs_in_total includes this submit)
+  const float *sinc;       // table
+  int cap_a, cap_b, hist_b;
+  int max_out;             // grid covers this many outputs per stream
+  int flush;
+};
+
+__global__ void __launch_bounds__(128) k_resample(const __grid_constant__ KernelPlan plan, ResampleArgs a) {
+  extern __shared__ float s_sinc[];
+  const int use_direct = plan.rs_direct;
+  const int tab_len = use_direct ? plan.rs_filt_len * plan.rs_den : plan.rs_filt_len * plan.rs_oversample + 8;
+  const bool tab_smem = tab_len <= 12 * 1024;
+  if (tab_smem)
+    for (int i = threadIdx.x; i < tab_len; i += blockDim.x) s_sinc[i] = a.sinc[i];
+  __syncthreads();
+  const float *tab = tab_smem ? s_sinc : a.sinc;
+
+  const int s = blockIdx.y;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const SubmitRec sr = a.submit[s];
+  const int n_out = a.flush ? (sr.lim_len - (plan.limiter ? kLimDelay : 0)) : sr.lim_len;
+  if (u >= n_out) return;
+  const long long n = sr.rs_out_first + u;
+  const int Nf = plan.rs_filt_len;
+  // stream position of the last input sample this output needs, and where this submit's input starts
+  const long long num = plan.rs_num, den = plan.rs_den;
+  const long long q = (long long)(Nf / 2) + (n * num) / den;
+  const unsigned int frac_num = (unsigned int)((n * (long long)plan.rs_frac_adv) % den);
+  const long long in_start = a.state[s].rs_in_total - sr.in_len;     // stream position of tl_a[kRsHist]
+  // first tap reads stream position q - (Nf-1)
+  const long long p0 = q - (Nf - 1) - in_start + kRsHist;             // index into tl_a row
+  const int co = plan.out_channels;
+  const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f && !a.flush;
+  float peak = 0.f;
+
+  int offset = 0;
+  float interp[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!use_direct) {
+    offset = frac_num * plan.rs_oversample / plan.rs_den;
+    const float frac = ((float)((frac_num * plan.rs_oversample) % plan.rs_den)) / plan.rs_den;
+    // cubic_coef, resample.c:246-256 (interp[2] is a double expression rounded once)
+    interp[0] = -0.16667f * frac + 0.16667f * frac * frac * frac;
+    interp[1] = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
+    interp[3] = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
+    interp[2] = (float)(1. - (double)interp[0] - (double)interp[1] - (double)interp[3]);
+  }
+
+  for (int c = 0; c < co; ++c) {
+    const float *row = a.src + ((size_t)s * co + c) * a.cap_a;
+    float sum;
+    if (use_direct) {
+      const float *sinct = tab + (size_t)frac_num * Nf;
+      sum = 0.f;
+      for (int j = 0; j < Nf; ++j) {
+        long long idx = p0 + j;
+        float xin = idx >= 0 ? row[idx] : 0.f;
+        sum += sinct[j] * xin;
+      }
+    } else {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const int os = plan.rs_oversample;
+      for (int j = 0; j < Nf; ++j) {
+        long long idx = p0 + j;
+        float xin = idx >= 0 ? row[idx] : 0.f;
+        const float *t = tab + 4 + (j + 1) * os - offset;
+        a0 += xin * t[-2];
+        a1 += xin * t[-1];
+        a2 += xin * t[0];
+        a3 += xin * t[1];
+      }
+      sum = interp[0] * a0 + interp[1] * a1 + interp[2] * a2 + interp[3] * a3;
+    }
+    // FLTADJUST, resample.c:84
+    sum = (sum < -1.0f) ? -1.0f : ((sum > 1.0f) ? 1.0f : sum);
+    if (loud_on) sum *= plan.loud_gain;
+    a.dst[((size_t)s * co + c) * a.cap_b + a.hist_b + u] = sum;
+    peak = fmaxf(peak, fabsf(sum));
+  }
+  if (a.pk) a.pk[(size_t)s * a.cap_b + a.hist_b + u] = peak;
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// K3a: sliding maximum.  wm[k] = max(pk[k-240 .. k-1]) = the `peak` the reference limiter looks up for instant k
+// (audio_effect_peak_limiter.c:109-133; the arg-max cache there is only an optimisation).
+// Doubling in shared memory: windows of 1,2,4,...,128 then 240 = 128+64+32+16.
+// block = (stream, 1024-instant tile); the time axis has kLimDelay history in front.
+// -------------------------------------------------------------------------------------------------------------------
+struct WmaxArgs {
+  const float *pk;     // [S][cap]
+  float *wm;           // [S][cap]   wm[hist + k] for k in [0, lim_len)
+  const SubmitRec *submit;
+  int cap, hist;
+  int flush;
+};
+
+constexpr int kWmTile = 1024;
+
+__global__ void __launch_bounds__(256) k_window_max(const __grid_constant__ KernelPlan plan, WmaxArgs a) {
+  __shared__ float sa[kWmTile + kLimDelay + 16];
+  __shared__ float sb[kWmTile + kLimDelay + 16];
+  const int s = blockIdx.y;
+  const int len = a.submit[s].lim_len;
+  const int k0 = blockIdx.x * kWmTile;
+  if (k0 >= len) return;
+  const float *row = a.pk + (size_t)s * a.cap + a.hist;   // row[k] = pk of instant k of this submit
+  const int span = kWmTile + kLimDelay;                    // instants k0-240 .. k0+1023
+  for (int i = threadIdx.x; i < span + 16; i += blockDim.x) {
+    int k = k0 - kLimDelay + i;
+    sa[i] = (i < span && k < len) ? row[k] : 0.f;          // k >= -240 always inside the history
+  }
+  __syncthreads();
+  // after the pass with step d: buf[i] = max(pk[i .. i+2d-1])
+  float *src = sa, *dst = sb;
+  // the 16/32/64 windows are snapshotted into registers as the passes go by: every thread owns output instants i = threadIdx.x + r*256 (r < 4) and needs
+  //   W16[i+224], W32[i+192], W64[i+128], W128[i]   (window start index i corresponds to instant k0-240+i)
+  float r16[4], r32[4], r64[4];
+  for (int d = 1; d <= 64; d <<= 1) {
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+      int j = i + d;
+      dst[i] = fmaxf(src[i], j < span ? src[j] : 0.f);
+    }
+    __syncthreads();
+    float *t = src; src = dst; dst = t;
+    // src now holds windows of 2d
+    if (2 * d == 16) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) r16[r] = src[threadIdx.x + r * 256 + 224];
+    } else if (2 * d == 32) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) r32[r] = src[threadIdx.x + r * 256 + 192];
+    } else if (2 * d == 64) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) r64[r] = src[threadIdx.x + r * 256 + 128];
+    }
+  }
+  // src holds windows of 128
+  float *out = a.wm + (size_t)s * a.cap + a.hist;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int i = threadIdx.x + r * 256;
+    int k = k0 + i;
+    if (k < len) out[k] = fmaxf(fmaxf(src[i], r64[r]), fmaxf(r32[r], r16[r]));
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// K3b: limiter gain recurrence (compute_target_gain, audio_effect_peak_limiter.c:237-271).
+// The float time constant of the reference only ever takes the values T[j] = j-fold float accumulation of 1/fs from 0
+// (it restarts at 0 on every trigger), so the state is the integer j; acc[j] = curve_accel(...) is precomputed on the
+// host with the same libm.  One lane per stream; a warp stages 32x32 tiles through shared memory so that global
+// accesses stay coalesced.  Tiles in which every lane is idle and below threshold are answered without the serial walk.
+// -------------------------------------------------------------------------------------------------------------------
+struct ScanArgs {
+  const float *wm;      // [S][cap]
+  float *gn;            // [S][cap]
+  StreamState *state;
+  const SubmitRec *submit;
+  const float *acc;     // [jr + 1]
+  int cap, hist, n_streams;
+  int max_len;
+};
+
+__global__ void __launch_bounds__(128) k_limiter_scan(const __grid_constant__ KernelPlan plan, ScanArgs a) {
+  __shared__ float tile[4][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = (blockIdx.x * 4 + warp) * 32;
+  if (s0 >= a.n_streams) return;
+  const int s = s0 + lane;
+  const bool live = s < a.n_streams;
+  int len = live ? a.submit[s].lim_len : 0;
+  int j = -1;
+  float start = -1.f, end = -1.f;
+  if (live) { j = a.state[s].lim_j; start = a.state[s].lim_start; end = a.state[s].lim_end; }
+  const float thr = plan.lim_thr;
+  const int ja = plan.lim_ja, jr = plan.lim_jr;
+  int max_len = len;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+  float (*t)[33] = tile[warp];
+
+  for (int k0 = 0; k0 < max_len; k0 += 32) {
+    // coalesced load of 32 streams x 32 instants
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      int sr = s0 + r;
+      int k = k0 + lane;
+      int lr = __shfl_sync(0xffffffffu, len, r);
+      t[r][lane] = (sr < a.n_streams && k < lr) ? a.wm[(size_t)sr * a.cap + a.hist + k] : 0.f;
+    }
+    __syncwarp();
+    // fast path: idle and the tile never crosses the threshold
+    float tmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, t[lane][i]);
+    const bool idle = (j < 0 || j >= jr);
+    const bool quiet = idle && !(tmax * 1.0f > thr);
+    if (!__all_sync(0xffffffffu, quiet)) {
+      const int nk = min(32, len - k0);
+      for (int i = 0; i < nk; ++i) {
+        const float peak = t[lane][i];
+        float g;
+        if (j >= 0 && j < ja) {
+          ++j;
+          g = start - a.acc[j] * (start - end);
+        } else if (j >= 0 && j < jr) {
+          ++j;
+          g = end + a.acc[j] * (1.0f - end);
+        } else {
+          g = 1.0f;
+        }
+        if (peak * g > thr) {
+          start = g;
+          end = thr / peak;
+          j = 0;
+        }
+        t[lane][i] = g;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[lane][i] = 1.0f;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      int sr = s0 + r;
+      int k = k0 + lane;
+      int lr = __shfl_sync(0xffffffffu, len, r);
+      if (sr < a.n_streams && k < lr) a.gn[(size_t)sr * a.cap + a.hist + k] = t[r][lane];
+    }
+    __syncwarp();
+  }
+  if (live) { a.state[s].lim_j = j; a.state[s].lim_start = start; a.state[s].lim_end = end; }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// K3c: apply the gain to the 240-sample delayed signal, quantise and interleave
+// (audio_effect_peak_limiter.c:139-147 + iamf_decoder_plane2stride_out / FLOAT2INT*, IAMF_decoder.c:100-167).
+// thread = one output instant of one stream (all channels); the first kLimDelay priming outputs of a stream are
+// dropped (padsize, :185-201).  Without a limiter the time line is quantised as is.
+// -------------------------------------------------------------------------------------------------------------------
+struct OutputArgs {
+  const float *tl;     // [S][C][cap]; sample of instant k sits at hist + k, the delayed one at hist + k - delay
+  const float *gn;     // [S][cap] or nullptr
+  const SubmitRec *submit;
+  void *pcm;
+  size_t stride_bytes; // per stream
+  int cap, hist;
+};
+
+__device__ __forceinline__ int quant16(float x) {
+  x = x * 32768.f;
+  x = x > -32768.f ? x : -32768.f;
+  x = x < 32767.f ? x : 32767.f;
+  return __float2int_rn(x);
+}
+__device__ __forceinline__ int quant24(float x) {
+  x = x * 8388608.f;
+  x = x > -8388608.f ? x : -8388608.f;
+  x = x < 8388607.f ? x : 8388607.f;
+  return __float2int_rn(x);
+}
+__device__ __forceinline__ int quant32(float x) {
+  x = x * 2147483648.f;
+  x = x > -2147483648.f ? x : -2147483648.f;
+  x = x < 2147483647.f ? x : 2147483647.f;   // 2147483647.f == 2^31: positive full scale wraps like the reference
+  return (int)__float2ll_rn(x);
+}
+
+__global__ void __launch_bounds__(256) k_output(const __grid_constant__ KernelPlan plan, OutputArgs a) {
+  const int s = blockIdx.y;
+  const SubmitRec sr = a.submit[s];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // limiter instant of this submit
+  if (k >= sr.lim_len || k < sr.out_skip) return;
+  const int o = k - sr.out_skip;                         // output sample index
+  const int co = plan.out_channels;
+  const int delay = plan.limiter ? kLimDelay : 0;
+  const float g = a.gn ? a.gn[(size_t)s * a.cap + a.hist + k] : 1.f;
+  const float *base = a.tl + (size_t)s * co * a.cap + a.hist + k - delay;
+  char *out = (char *)a.pcm + (size_t)s * a.stride_bytes;
+  for (int c = 0; c < co; ++c) {
+    float x = base[(size_t)c * a.cap];
+    if (a.gn) x = x * g;
+    if (plan.bit_depth == 16) {
+      ((int16_t *)out)[(size_t)o * co + c] = (int16_t)quant16(x);
+    } else if (plan.bit_depth == 24) {
+      int v = quant24(x);
+      unsigned char *p = (unsigned char *)out + ((size_t)o * co + c) * 3;
+      p[0] = v & 0xff;
+      p[1] = (v >> 8) & 0xff;
+      p[2] = ((v >> 16) & 0x7f) | ((v >> 24) & 0x80);
+    } else if (plan.bit_depth == 32) {
+      ((int32_t *)out)[(size_t)o * co + c] = quant32(x);
+    } else {
+      ((float *)out)[(size_t)o * co + c] = x;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// K4: carry the history (limiter delay line / peak ring / resampler memory) to the front of the time line for the
+// next submit.  Tiny: S x C x hist floats.
+// -------------------------------------------------------------------------------------------------------------------
+struct CarryArgs {
+  float *tl;          // [S][rows][cap]
+  const SubmitRec *submit;
+  int rows, cap, hist;
+  int use_in_len;     // 1: advance by in_len (pre-resample line), 0: by lim_len
+};
+
+__global__ void __launch_bounds__(256) k_carry(CarryArgs a) {
+  __shared__ float tmp[256];
+  const int s = blockIdx.y, r = blockIdx.x;
+  const int len = a.use_in_len ? a.submit[s].in_len : a.submit[s].lim_len;
+  if (len == 0) return;
+  float *row = a.tl + ((size_t)s * a.rows + r) * a.cap;
+  // hist <= 256: stage through shared memory because source and destination overlap when len < hist
+  int i = threadIdx.x;
+  if (i < a.hist) tmp[i] = row[len + i];
+  __syncthreads();
+  if (i < a.hist) row[i] = tmp[i];
+}
+
+}  // namespace iamfb

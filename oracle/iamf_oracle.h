@@ -169,6 +169,7 @@ typedef struct OrcElementCfg {
   int chs_in[ORC_MAX_LAYOUT_CH];   /* transmission order */
   int n_out_gain; int out_gain_ch[ORC_MAX_LAYOUT_CH]; float out_gain[ORC_MAX_LAYOUT_CH];
   int has_demix_info; int default_mode; int default_w_idx;
+  int first_layer_layout; int selected_layer;   /* default recon-gain list, IAMF_decoder.c:2202-2236 */
   int use_dmr; int dmr_out_layout;  /* DMRenderer instead of matrix, IAMF_decoder.c:2448-2478 */
   /* scene-based */
   int ambi_mode;            /* 1 mono map, 2 projection */

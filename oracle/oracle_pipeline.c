@@ -42,6 +42,20 @@ OrcStream *orc_stream_open(const OrcStreamCfg *cfg) {
       orc_demixer_set_channels_order(d, el->chs_in, el->n_in);
       orc_demixer_set_output_gain(d, el->out_gain_ch, el->out_gain, el->n_out_gain);
       if (el->has_demix_info) orc_demixer_set_demixing_info(d, el->default_mode, el->default_w_idx);
+      { /* iamf_stream_scale_decoder_set_default_recon_gain, IAMF_decoder.c:2202-2236 */
+        int chs[ORC_MAX_LAYOUT_CH], n = 0;
+        float ones[ORC_MAX_LAYOUT_CH];
+        uint32_t fl = 0;
+        if (el->selected_layer > 0) {
+          fl = orc_recon_flags(el->first_layer_layout, el->layout);
+          n = orc_recon_order(el->layout, fl, chs);
+          for (int i = 0; i < n; ++i) ones[i] = 1.f;
+        }
+        orc_demixer_set_recon_gain(d, n, chs, ones, fl);
+      }
+      /* first decode: iamf_stream_decoder_update_delay -> demixer_set_frame_offset(delay = 0), IAMF_decoder.c:2176-2185:
+         this is what installs the Hann cross-fade windows */
+      orc_demixer_set_frame_offset(d, 0);
       s->dmx[e] = d;
       if (el->use_dmr) { /* iamf_stream_renderer_enable_downmix, IAMF_decoder.c:2448-2478 */
         s->dmr[e] = orc_dmr_open(el->layout, el->dmr_out_layout);

@@ -1,0 +1,36 @@
+"""Runs a Scenario through the product's C ABI (host-resident submits) and returns, per stream, the per-call sample
+counts and the concatenated PCM bytes in the same form scenarios.run_oracle() returns them."""
+import numpy as np
+
+import scenarios as S
+from iamf_b200 import Engine
+
+
+def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0):
+    n_streams, F = P.shape
+    splits = splits or [F]
+    assert sum(splits) == F
+    eng = Engine(S.plan_desc(sc), n_streams, max(splits), device=device)
+    co = eng.out_channels
+    bps = eng.bytes_per_sample
+    counts = [[] for _ in range(n_streams)]
+    chunks = [[] for _ in range(n_streams)]
+    f0 = 0
+    for n in splits:
+        sl = slice(f0, f0 + n)
+        pcm, cnt = eng.submit_host([x[:, sl] for x in inputs], P[:, sl],
+                                   [r[:, sl] if r is not None else None for r in ramps] if ramps else None,
+                                   oramp[:, sl] if oramp is not None else None)
+        for s in range(n_streams):
+            counts[s].extend(int(c) for c in cnt[s])
+            tot = int(cnt[s].sum())
+            chunks[s].append(pcm[s, : tot * co * bps].copy())
+        f0 += n
+    if flush:
+        pcm, cnt = eng.flush_host()
+        for s in range(n_streams):
+            counts[s].append(int(cnt[s]))
+            chunks[s].append(pcm[s, : int(cnt[s]) * co * bps].copy())
+    launches = eng.launch_count()
+    eng.close()
+    return {s: (counts[s], np.concatenate(chunks[s]) if chunks[s] else np.zeros(0, np.uint8)) for s in range(n_streams)}, launches

@@ -18,6 +18,7 @@ class ElementCfg(C.Structure):
     _fields_ = [("type", C.c_int), ("n_in", C.c_int), ("layout", C.c_int), ("chs_in", C.c_int * MAXL),
                 ("n_out_gain", C.c_int), ("out_gain_ch", C.c_int * MAXL), ("out_gain", C.c_float * MAXL),
                 ("has_demix_info", C.c_int), ("default_mode", C.c_int), ("default_w_idx", C.c_int),
+                ("first_layer_layout", C.c_int), ("selected_layer", C.c_int),
                 ("use_dmr", C.c_int), ("dmr_out_layout", C.c_int),
                 ("ambi_mode", C.c_int), ("ambi_map", C.c_uint8 * 16), ("ambi_matrix", f32p), ("ambi_cols", C.c_int),
                 ("mat", f32p), ("mat_in", C.c_int), ("mat_out", C.c_int), ("lfe1", C.c_int), ("lfe2", C.c_int)]

@@ -1,0 +1,353 @@
+"""Seeded synthetic workloads shared by the parity tests, the golden-fixture generator, smoke() and bench.py.
+
+A Scenario describes one pipeline signature (the shapes named in BASELINE.json's configs plus edge cases); from it we
+derive BOTH the product's plan descriptor (include/iamf_b200.h) and the oracle's stream configuration
+(oracle/iamf_oracle.h), the per-stream decoded frames (int16-quantised like Opus/AAC/ipcm16 hand them over) and the
+per-frame parameters.  Test infrastructure only.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+# IAChannel ids
+L7, R7, CC, LFE, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, MONO, L2, R2, TL, TR, L3, R3, SL5, SR5, HL, HR = range(1, 24)
+L5, R5 = L7, R7
+LY_MONO, LY_STEREO, LY_510, LY_512, LY_514, LY_710, LY_712, LY_714, LY_312, LY_BIN = range(10)
+LAYOUT_COUNT = [1, 2, 6, 8, 10, 8, 10, 12, 6, 2]
+TGT_A, TGT_B, TGT_C, TGT_D, TGT_E, TGT_F, TGT_G, TGT_H, TGT_I, TGT_J, TGT_712, TGT_312, TGT_MONO, TGT_BIN = range(14)
+TARGET_CH = [2, 6, 8, 10, 11, 12, 14, 24, 8, 12, 10, 6, 1, 2]
+RECON_MAP = [  # IAMF_decoder.c:409-448
+    [13, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0], [14, 0, 15, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+    [1, 3, 2, 20, 21, 0, 0, 0, 0, 0, 0, 4], [1, 3, 2, 20, 21, 22, 23, 0, 0, 0, 0, 4],
+    [1, 3, 2, 20, 21, 9, 10, 0, 0, 11, 12, 4], [1, 3, 2, 5, 6, 0, 0, 7, 8, 0, 0, 4],
+    [1, 3, 2, 5, 6, 22, 23, 7, 8, 0, 0, 4], [1, 3, 2, 5, 6, 9, 10, 7, 8, 11, 12, 4],
+    [18, 3, 19, 0, 0, 16, 17, 0, 0, 0, 0, 4]]
+
+
+@dataclass
+class El:
+    kind: str                                  # "channel" | "scene"
+    # channel
+    layout: int = 0
+    chs_in: List[int] = field(default_factory=list)
+    out_gain: List[tuple] = field(default_factory=list)     # [(IAChannel, linear)]
+    demix: Optional[tuple] = None              # (default mode, default w idx)
+    first_layer_layout: Optional[int] = None
+    selected_layer: int = 0
+    recon_flags: int = 0                       # 0 => the layer carries no recon-gain list
+    dmr_out_layout: Optional[int] = None
+    # scene
+    channels: int = 0
+    mapping: Optional[list] = None
+    projection: Optional[np.ndarray] = None    # [cols][rows]
+    mix_gain: float = 1.0
+
+    @property
+    def n_in(self):
+        if self.kind == "channel":
+            return len(self.chs_in)
+        if self.projection is not None:
+            return self.projection.shape[0]
+        return (max(self.mapping) + 1) if self.mapping is not None else self.channels
+
+
+@dataclass
+class Scenario:
+    name: str
+    elements: List[El]
+    target: int
+    frame_size: int = 960
+    in_rate: int = 48000
+    out_rate: int = 48000
+    loudness_gain: float = 0.0
+    limiter: bool = True
+    threshold_db: float = -1.0
+    bit_depth: int = 16
+    out_gain: float = 1.0
+    demix_modes: tuple = (1, 2, 4, 5, 6, 0)    # cycled every `mode_period` frames
+    mode_period: int = 3
+    ramp: bool = False                         # animated element/output mix gains
+    trims: Optional[dict] = None               # {frame index: (trim_start, trim_end)}
+    peak_db: tuple = (-12.0, 2.0)              # per-stream peak level range (uniform), SURVEY 8d
+
+    @property
+    def out_channels(self):
+        return TARGET_CH[self.target]
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the five BASELINE.json configurations + edge cases
+# --------------------------------------------------------------------------------------------------------------------
+def c1_stereo(**kw):
+    return Scenario("c1_stereo_to_A", [El("channel", LY_STEREO, [L2, R2])], TGT_A, **kw)
+
+
+def c2_714_to_B(**kw):
+    el = El("channel", LY_714, [L2, R2, L5, R5, SL7, SR7, HFL, HFR, HBL, HBR, CC, LFE],
+            out_gain=[(L2, 1.1220184543), (R2, 1.1220184543)], demix=(1, 0), first_layer_layout=LY_STEREO,
+            selected_layer=1, recon_flags=0x780)
+    return Scenario("c2_714_scalable_to_B", [el], TGT_B, **kw)
+
+
+def c3_toa_to_H(**kw):
+    return Scenario("c3_toa_to_H", [El("scene", channels=16)], TGT_H, **kw)
+
+
+def c4_714_foa_binaural(**kw):
+    g = 0.70794578438  # -3 dB
+    e0 = El("channel", LY_714, [L7, R7, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, CC, LFE], mix_gain=g)
+    e1 = El("scene", channels=4, mix_gain=g)
+    return Scenario("c4_714_foa_to_binaural", [e0, e1], TGT_BIN, **kw)
+
+
+def c5_resample(**kw):
+    kw.setdefault("frame_size", 1024)
+    return Scenario("c5_stereo_44k1_to_48k_loud_lim", [El("channel", LY_STEREO, [L2, R2])], TGT_A, in_rate=44100,
+                    out_rate=48000, loudness_gain=0.3981071705535, **kw)  # db2lin(-24 - -16)
+
+
+def edge_cases():
+    rng = np.random.default_rng(3)
+    proj = (rng.integers(-20000, 20000, (5, 4)) / np.float32(32768)).astype(np.float32)
+    return [
+        Scenario("4layer_312_512_714_to_J",
+                 [El("channel", LY_714, [L2, R2, TL, TR, CC, LFE, L5, R5, SL7, SR7, HFL, HFR], out_gain=[(L2, 1.25), (R2, 1.25)],
+                     demix=(2, 3), first_layer_layout=LY_STEREO, selected_layer=3, recon_flags=0x780)], TGT_J),
+        Scenario("mono_to_stereo_scalable_24bit",
+                 [El("channel", LY_STEREO, [MONO, L2], demix=None, first_layer_layout=LY_MONO, selected_layer=1,
+                     recon_flags=0x5)], TGT_A, bit_depth=24),
+        Scenario("714_dmr_to_312", [El("channel", LY_714, [L7, R7, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, CC, LFE],
+                                       demix=(1, 2), dmr_out_layout=LY_312)], TGT_312),
+        Scenario("510_dmr_to_stereo_32bit", [El("channel", LY_510, [L5, R5, SL5, SR5, CC, LFE], demix=(4, 9),
+                                                dmr_out_layout=LY_STEREO)], TGT_A, bit_depth=32, peak_db=(-3.0, 3.0)),
+        Scenario("foa_projection_to_D_float", [El("scene", channels=4, projection=proj)], TGT_D, bit_depth=0),
+        Scenario("soa_mapped_to_F_nolimiter", [El("scene", channels=9, mapping=[8, 7, 6, 5, 4, 3, 2, 1, 0])], TGT_F,
+                 limiter=False),
+        Scenario("stereo_ramps_trims", [El("channel", LY_STEREO, [L2, R2], mix_gain=0.8)], TGT_B, ramp=True,
+                 trims={0: (312, 0), 2: (960, 0), 5: (0, 100), 6: (0, 960)}, out_gain=1.2),
+        Scenario("stereo_48k_to_96k", [El("channel", LY_STEREO, [L2, R2])], TGT_A, in_rate=48000, out_rate=96000),
+        Scenario("stereo_48k_to_44k1_odd_frame", [El("channel", LY_STEREO, [L2, R2])], TGT_A, frame_size=1021,
+                 in_rate=48000, out_rate=44100, bit_depth=24),
+        Scenario("714_foa_to_H_two_elements", [El("scene", channels=4, mix_gain=0.5),
+                                               El("channel", LY_714, [L7, R7, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, CC, LFE])],
+                 TGT_H),
+        Scenario("stereo_tiny_frames", [El("channel", LY_STEREO, [L2, R2])], TGT_A, frame_size=128, peak_db=(-2.0, 3.0)),
+    ]
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# synthetic decoded PCM + parameters
+# --------------------------------------------------------------------------------------------------------------------
+def synth_inputs(sc: Scenario, n_streams: int, n_frames: int, seed: int = 0x1A3F):
+    """per element float32 [S][F][n_in][N]: 3 sines + noise per channel, peak uniformly in sc.peak_db dBFS per
+    stream, quantised to int16 then /32768 (the codec glue's contract, opus/IAMF_opus_decoder.c:133-135)."""
+    N, F = sc.frame_size, n_frames
+    T = N * F
+    t = np.arange(T, dtype=np.float64) / sc.in_rate
+    out = [np.zeros((n_streams, F, el.n_in, N), np.float32) for el in sc.elements]
+    for s in range(n_streams):
+        rng = np.random.default_rng(seed + s)
+        peak = 10.0 ** (rng.uniform(*sc.peak_db) / 20.0)
+        for e, el in enumerate(sc.elements):
+            C_ = el.n_in
+            freqs = rng.uniform(50.0, 12000.0, (C_, 3))
+            phases = rng.uniform(0, 2 * np.pi, (C_, 3))
+            x = np.sin(2 * np.pi * freqs[:, :, None] * t[None, None, :] + phases[:, :, None]).sum(axis=1)
+            x += rng.uniform(-0.3, 0.3, (C_, T))
+            x *= peak / np.abs(x).max()
+            q = np.clip(np.rint(x * 32768.0), -32768, 32767).astype(np.int16)
+            xf = (q.astype(np.float32) / np.float32(32768.0)).reshape(C_, F, N).transpose(1, 0, 2)
+            out[e][s] = xf
+    return out
+
+
+def synth_params(sc: Scenario, n_streams: int, n_frames: int, seed: int = 0x77):
+    """iamfb_frame_params as a numpy structured array + the animated gain ramps (or None)"""
+    from iamf_b200.binding import frame_params_array
+    P = frame_params_array(n_streams, n_frames)
+    rng = np.random.default_rng(seed)
+    for e, el in enumerate(sc.elements):
+        P[f"mix_gain{e}"] = el.mix_gain
+        if el.kind != "channel":
+            continue
+        if el.demix is not None:
+            off = rng.integers(0, len(sc.demix_modes), n_streams)
+            for f in range(n_frames):
+                P[f"dmx_mode{e}"][:, f] = np.asarray(sc.demix_modes)[(off + f // sc.mode_period) % len(sc.demix_modes)]
+        if el.recon_flags:
+            nb = bin(el.recon_flags).count("1")
+            P[f"has_recon{e}"] = 1
+            P[f"recon_flags{e}"] = el.recon_flags
+            g = rng.integers(0, 256, (n_streams, n_frames, 12)).astype(np.uint8)
+            g[:, :, nb:] = 0
+            P[f"recon_gain{e}"] = g
+            # every 7th frame of every 3rd stream carries no recon block (the previous list keeps applying)
+            P[f"has_recon{e}"][::3, 6::7] = 0
+    P["out_gain"] = sc.out_gain
+    if sc.trims:
+        for f, (ts, te) in sc.trims.items():
+            if f < n_frames:
+                P["trim_start"][:, f] = ts
+                P["trim_end"][:, f] = te
+    ramps, oramp = None, None
+    if sc.ramp:
+        N = sc.frame_size
+        ramps = []
+        for e in range(len(sc.elements)):
+            r = (0.5 + 0.5 * rng.random((n_streams, n_frames, 1)) * np.linspace(0.2, 1.0, N)[None, None, :]).astype(np.float32)
+            ramps.append(r)
+        oramp = (1.0 - 0.4 * np.linspace(0.0, 1.0, N)[None, None, :] * rng.random((n_streams, n_frames, 1))).astype(np.float32)
+    return P, ramps, oramp
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# product plan descriptor
+# --------------------------------------------------------------------------------------------------------------------
+def plan_desc(sc: Scenario):
+    from iamf_b200.binding import PlanDesc, channel_element, scene_element
+    d = PlanDesc()
+    d.frame_size, d.in_rate, d.out_rate = sc.frame_size, sc.in_rate, sc.out_rate
+    d.n_elements = len(sc.elements)
+    for e, el in enumerate(sc.elements):
+        if el.kind == "channel":
+            d.el[e] = channel_element(el.layout, el.chs_in, el.out_gain, el.demix, el.first_layer_layout,
+                                      el.selected_layer, bool(el.recon_flags), el.dmr_out_layout)
+        else:
+            d.el[e] = scene_element(el.channels, el.n_in, el.mapping, el.projection)
+    d.target = sc.target
+    d.loudness_gain = sc.loudness_gain
+    d.limiter = 1 if sc.limiter else 0
+    d.limiter_threshold_db = sc.threshold_db
+    d.bit_depth = sc.bit_depth
+    return d
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# oracle run (one stream at a time, frame by frame, exactly like repeated IAMF_decoder_decode calls)
+# --------------------------------------------------------------------------------------------------------------------
+def _orc_cfg(sc: Scenario, keep):
+    import orcbind
+    from iamf_b200.binding import get_h2m_matrix, get_m2m_matrix
+    cfg = orcbind.StreamCfg()
+    cfg.frame_size, cfg.in_rate, cfg.out_rate = sc.frame_size, sc.in_rate, sc.out_rate
+    cfg.n_elements = len(sc.elements)
+    cfg.out_channels = sc.out_channels
+    cfg.loudness_gain = sc.loudness_gain
+    cfg.limiter = 1 if sc.limiter else 0
+    cfg.limiter_threshold_db = sc.threshold_db
+    cfg.bit_depth = sc.bit_depth
+    for e, el in enumerate(sc.elements):
+        oe = cfg.el[e]
+        oe.n_in = el.n_in
+        if el.kind == "channel":
+            oe.type = 0
+            oe.layout = LY_STEREO if el.layout == LY_BIN else el.layout
+            for i, c in enumerate(el.chs_in):
+                oe.chs_in[i] = c
+            oe.n_out_gain = len(el.out_gain)
+            for i, (c, g) in enumerate(el.out_gain):
+                oe.out_gain_ch[i] = c
+                oe.out_gain[i] = g
+            if el.demix is not None:
+                oe.has_demix_info, oe.default_mode, oe.default_w_idx = 1, el.demix[0], el.demix[1]
+            oe.first_layer_layout = el.layout if el.first_layer_layout is None else el.first_layer_layout
+            oe.selected_layer = el.selected_layer
+            if el.dmr_out_layout is not None:
+                oe.use_dmr, oe.dmr_out_layout = 1, el.dmr_out_layout
+            else:
+                mat = np.ascontiguousarray(get_m2m_matrix(el.layout, sc.target), np.float32)
+                keep.append(mat)
+                oe.mat = mat.ctypes.data_as(orcbind.f32p)
+                oe.mat_in, oe.mat_out = mat.shape
+        else:
+            oe.type = 1
+            order = {1: 0, 4: 1, 9: 2, 16: 3}[el.channels]
+            mat, l1, l2 = get_h2m_matrix(order, sc.target)
+            mat = np.ascontiguousarray(mat, np.float32)
+            keep.append(mat)
+            oe.mat = mat.ctypes.data_as(orcbind.f32p)
+            oe.mat_out, oe.mat_in = mat.shape
+            oe.lfe1, oe.lfe2 = l1, l2
+            oe.n_in = el.channels          # rows produced by the ambisonics conversion
+            if el.projection is not None:
+                pm = np.ascontiguousarray(el.projection, np.float32)
+                keep.append(pm)
+                oe.ambi_mode = 2
+                oe.ambi_matrix = pm.ctypes.data_as(orcbind.f32p)
+                oe.ambi_cols = pm.shape[0]
+            else:
+                oe.ambi_mode = 1
+                mp = el.mapping if el.mapping is not None else list(range(el.channels))
+                for i, m in enumerate(mp):
+                    oe.ambi_map[i] = m
+    return cfg
+
+
+def run_oracle(sc: Scenario, inputs, P, ramps=None, oramp=None, streams=None, flush=True):
+    """returns per stream: (list of per-call sample counts incl. the flush call, concatenated PCM array)"""
+    import orcbind
+    L = orcbind.lib()
+    S, F = P.shape
+    N, co = sc.frame_size, sc.out_channels
+    results = {}
+    bps = sc.bit_depth // 8 if sc.bit_depth else 4
+    for s in (range(S) if streams is None else streams):
+        keep = []
+        cfg = _orc_cfg(sc, keep)
+        h = L.orc_stream_open(C.byref(cfg))
+        re_state = []
+        for e, el in enumerate(sc.elements):
+            re_state.append({"flags": 0, "chs": [], "gains": []})
+        counts, chunks = [], []
+        cap = 4 * (N * (sc.out_rate // sc.in_rate + 2) + 600) * co * max(bps, 4)
+        buf = C.create_string_buffer(cap)
+        for f in range(F):
+            fps = (orcbind.FrameParams * 2)()
+            in_ptrs = (orcbind.f32p * 2)()
+            frames = []
+            for e, el in enumerate(sc.elements):
+                x = np.ascontiguousarray(inputs[e][s, f]).copy()
+                frames.append(x)
+                in_ptrs[e] = x.ctypes.data_as(orcbind.f32p)
+                fp = fps[e]
+                fp.dmx_mode = int(P[f"dmx_mode{e}"][s, f])
+                fp.gain_const = float(P[f"mix_gain{e}"][s, f])
+                if ramps is not None and ramps[e] is not None:
+                    r = np.ascontiguousarray(ramps[e][s, f])
+                    frames.append(r)
+                    fp.gain_ramp = r.ctypes.data_as(orcbind.f32p)
+                if el.kind == "channel":
+                    st = re_state[e]
+                    if P[f"has_recon{e}"][s, f]:
+                        fl = int(P[f"recon_flags{e}"][s, f])
+                        if fl != st["flags"]:
+                            st["flags"] = fl
+                            st["chs"] = [RECON_MAP[el.layout][b] for b in range(12) if fl & (1 << b)]
+                        st["gains"] = [float(L.orc_qf_to_float(int(q), 8)) for q in P[f"recon_gain{e}"][s, f][: len(st["chs"])]]
+                    if el.recon_flags:
+                        fp.has_recon = 1
+                        fp.recon_flags = st["flags"]
+                        fp.n_recon = len(st["chs"])
+                        for i, c in enumerate(st["chs"]):
+                            fp.recon_ch[i] = c
+                            fp.recon_gain[i] = st["gains"][i]
+            og_r = None
+            if oramp is not None:
+                og_r = np.ascontiguousarray(oramp[s, f])
+            n = L.orc_stream_decode(h, in_ptrs, fps, float(P["out_gain"][s, f]),
+                                    og_r.ctypes.data_as(orcbind.f32p) if og_r is not None else None,
+                                    int(P["trim_start"][s, f]), int(P["trim_end"][s, f]), buf)
+            counts.append(n)
+            if n > 0:
+                chunks.append(buf.raw[: n * co * bps])
+        if flush:
+            n = L.orc_stream_flush(h, buf)
+            counts.append(n)
+            if n > 0:
+                chunks.append(buf.raw[: n * co * bps])
+        L.orc_stream_close(h)
+        raw = np.frombuffer(b"".join(chunks), np.uint8)
+        results[s] = (counts, raw)
+    return results
