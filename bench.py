@@ -1,0 +1,401 @@
+#!/usr/bin/env python3
+"""bench.py - rendered audio-seconds per second of the post-decode rendering path on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                 # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # the reference's own CPU implementation
+
+A "step" is one pass of the hot path over one batch of synthetic input: S streams x F consecutive frames of the
+configuration BASELINE.json's metric is quoted on (configs[1]: 1024 concurrent 7.1.4-scalable streams with recon-gain
+demixing rendered to sound system B).  Streams shard independently over the GPUs (weak scaling, no collective on the
+data path; torch.distributed only provides the barrier and the max-over-ranks of the device time).
+
+  value     whole-job audio-s/s with the decoded PCM already resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the host-buffer entry point of the C ABI (pinned host -> H2D -> kernels -> D2H)
+  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event time, vs the measured HBM copy peak
+  cpu_baseline  the reference decoder (oracle/_ref, else our C port) on a bounded sample, all host cores
+
+Input sets are larger than L2 (126 MB), so consecutive steps never find their input cached.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    "c1": dict(streams=1024, frames=32, desc="simple-profile stereo -> sound system A"),
+    "c2": dict(streams=1024, frames=16, desc="1024 base-profile streams, 7.1.4 scalable (2.0 -> 7.1.4) with recon-gain demixing -> sound system B (0+5+0)"),
+    "c3": dict(streams=4096, frames=4, desc="4096 streams of 3rd-order ambisonics (16 ch) -> sound system H (9+10+3)"),
+    "c4": dict(streams=2048, frames=8, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural (as built: stereo matrices)"),
+    "c5": dict(streams=2048, frames=16, desc="2048 streams/GPU, stereo 44.1->48 kHz resample, loudness -24 LKFS, limiter, 16-bit"),
+}
+
+
+def alg_bytes_per_audio_second(sc):
+    """f32 planar decoded input + integer interleaved output, every byte once"""
+    bps = sc.bit_depth // 8 if sc.bit_depth else 4
+    return sum(el.n_in for el in sc.elements) * 4 * sc.in_rate + sc.out_channels * bps * sc.out_rate
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU leg: the reference's own implementation on host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    cfg, streams, n_frames, kind, seed, barrier_path, n_workers, idx = args
+    import refbind
+    import refstreams
+    import scenarios as S
+    sc, st, api_kw, unit_kw = refstreams.case(cfg)
+    n = len(streams)
+    inputs = S.synth_inputs(sc, n, n_frames, seed=seed + 1000 * idx)
+    P, ramps, oramp = S.synth_params(sc, n, n_frames, seed=seed + idx)
+    refstreams.no_param_gaps(sc, P)
+    out_samples = 0
+    if kind == "reference":
+        import iamfapi
+        api = iamfapi.Api(refbind.REF_SO)
+        desc = st.descriptors()
+        units = [refstreams.temporal_units(sc, st, inputs, P, unit_kw, s) for s in range(n)]
+        # crude cross-process barrier through the file system so that all workers time the same interval
+        open(f"{barrier_path}.{idx}", "w").close()
+        while sum(os.path.exists(f"{barrier_path}.{i}") for i in range(n_workers)) < n_workers:
+            time.sleep(0.001)
+        t0 = time.monotonic()
+        for s in range(n):
+            pcm, counts = api.render(desc, units[s], **api_kw)
+            out_samples += pcm.shape[0]
+        t1 = time.monotonic()
+    else:
+        open(f"{barrier_path}.{idx}", "w").close()
+        while sum(os.path.exists(f"{barrier_path}.{i}") for i in range(n_workers)) < n_workers:
+            time.sleep(0.001)
+        t0 = time.monotonic()
+        res = S.run_oracle(sc, inputs, P, ramps, oramp)
+        t1 = time.monotonic()
+        bps = sc.bit_depth // 8 if sc.bit_depth else 4
+        out_samples = sum(len(r[1]) // (bps * sc.out_channels) for r in res.values())
+    return t0, t1, out_samples / float(sc.out_rate)
+
+
+def cpu_reference(cfg, n_streams, n_frames, seed=0):
+    """times the reference CPU implementation over n_streams x n_frames on all host cores.
+    returns dict(value audio-s/s, cores, kind, sample, seconds)"""
+    import multiprocessing as mp
+    import tempfile
+    import refbind
+    kind = "reference" if refbind.have_ref() else "port"
+    if kind == "port":
+        import orcbind
+        orcbind.lib()   # make sure liboracle.so exists before forking
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, n_streams))
+    chunks = [list(range(i, n_streams, workers)) for i in range(workers)]
+    bdir = tempfile.mkdtemp(prefix="iamfb_bar_")
+    bpath = os.path.join(bdir, "ready")
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, [(cfg, chunks[i], n_frames, kind, seed, bpath, workers, i) for i in range(workers)])
+    t0 = min(r[0] for r in res)
+    t1 = max(r[1] for r in res)
+    audio = sum(r[2] for r in res)
+    for i in range(workers):
+        try:
+            os.remove(f"{bpath}.{i}")
+        except OSError:
+            pass
+    return dict(value=audio / (t1 - t0), unit="audio-s/s", cores=workers, kind=kind,
+                sample=f"{n_streams} streams x {n_frames} frames of the same workload, public-API decode calls only"
+                if kind == "reference" else f"{n_streams} streams x {n_frames} frames, C port of the path (oracle/)",
+                seconds=t1 - t0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 8 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 8 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) >= 8:
+                for n, v in zip(names, s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def make_inputs_torch(sc, S, F, seed, device):
+    """device-resident decoded PCM: 3 sines + noise per channel, per-stream peak uniformly in sc.peak_db dBFS,
+    quantised to int16 and scaled by 1/32768 (the codec glue's contract).  [S][F][C][N] float32 per element."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    N = sc.frame_size
+    T = F * N
+    t = torch.arange(T, device=device, dtype=torch.float32) / sc.in_rate
+    outs = []
+    peak = 10.0 ** ((sc.peak_db[0] + (sc.peak_db[1] - sc.peak_db[0]) * torch.rand(S, generator=g, device=device)) / 20.0)
+    for el in sc.elements:
+        C = el.n_in
+        x = torch.empty((S, C, T), device=device, dtype=torch.float32)
+        step = max(1, 256 // C)
+        for s0 in range(0, S, step):
+            s1 = min(S, s0 + step)
+            n = s1 - s0
+            fr = 50.0 + 11950.0 * torch.rand((n, C, 3, 1), generator=g, device=device)
+            ph = 6.2831853 * torch.rand((n, C, 3, 1), generator=g, device=device)
+            y = torch.sin(6.2831853 * fr * t.view(1, 1, 1, T) + ph).sum(dim=2)
+            y += 0.6 * torch.rand((n, C, T), generator=g, device=device) - 0.3
+            y *= (peak[s0:s1] / y.abs().amax(dim=(1, 2))).view(n, 1, 1)
+            x[s0:s1] = torch.clamp(torch.round(y * 32768.0), -32768, 32767) / 32768.0
+        outs.append(x.view(S, C, F, N).permute(0, 2, 1, 3).contiguous())
+    return outs
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import scenarios as S
+    import refstreams
+    from iamf_b200 import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    cfg = args.config
+    sc, _, _, _ = refstreams.case(cfg)
+    S_, F = args.streams or CONFIGS[cfg]["streams"], args.frames or CONFIGS[cfg]["frames"]
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is busy
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu = cpu_reference(cfg, n_streams=max(cores, 8), n_frames=args.cpu_frames)
+
+    stream = torch.cuda.current_stream()
+    eng = Engine(S.plan_desc(sc), S_, F, device=local, cuda_stream=stream.cuda_stream)
+    inputs = make_inputs_torch(sc, S_, F, seed=0x1A3F + 7919 * rank, device=dev)
+    P, _, _ = S.synth_params(sc, S_, F, seed=0x77 + rank)
+    refstreams.no_param_gaps(sc, P)
+    d_params = torch.from_numpy(P.view(np.uint8).reshape(S_, F * 48).copy()).to(dev)
+    stride = eng.out_stride_bytes(F)
+    d_pcm = torch.zeros((S_, stride), dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros((S_, F), dtype=torch.int32, device=dev)
+    in_ptrs = [x.data_ptr() for x in inputs]
+
+    def step():
+        eng.submit_device(in_ptrs, d_params.data_ptr(), d_pcm.data_ptr(), d_counts.data_ptr(), F)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # samples produced in one steady-state step (all streams of this rank)
+    out_per_step = int(d_counts.sum().item())
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tot = torch.tensor([float(out_per_step)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    audio_per_step = float(tot.item()) / sc.out_rate
+    value = audio_per_step * args.steps / (ms_max / 1e3)
+
+    # ---- per-kernel CUDA-event timing (separate pass so that the events do not perturb `value`)
+    eng.set_timing(True)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    timing = eng.get_timing()
+    eng.set_timing(False)
+    kernels = {k: dict(ms_per_launch=v[0] / max(v[1], 1), launches_per_step=v[1] / args.steps,
+                       ms_per_step=v[0] / args.steps) for k, v in timing.items()}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    alg_bytes_step = alg_bytes_per_audio_second(sc) * (out_per_step / sc.out_rate)
+    dom_launches = max(kernels[dom]["launches_per_step"], 1e-9)
+    achieved = alg_bytes_step / dom_launches / (kernels[dom]["ms_per_launch"] / 1e3) / 1e9
+    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
+                    traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_launch=alg_bytes_step / dom_launches,
+                    pipeline=dict(achieved=alg_bytes_step / (ms_max / args.steps / 1e3) / 1e9,
+                                  frac=alg_bytes_step / (ms_max / args.steps / 1e3) / 1e9 / peak_gbs,
+                                  note="all kernels of the step, algorithmic bytes / step time"),
+                    kernels=kernels)
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, H2D + kernels + D2H every step)
+    Fe = min(F, args.e2e_frames)
+    eng_e = Engine(S.plan_desc(sc), S_, Fe, device=local, cuda_stream=stream.cuda_stream)
+    h_in = [x[:, :Fe].contiguous().cpu().pin_memory() for x in inputs]
+    h_params = np.ascontiguousarray(P[:, :Fe])
+    stride_e = eng_e.out_stride_bytes(Fe)
+    h_pcm = torch.zeros((S_, stride_e), dtype=torch.uint8).pin_memory()
+    h_counts = torch.zeros((S_, Fe), dtype=torch.int32).pin_memory()
+    import ctypes as C
+    from iamf_b200.binding import Io, _check
+    io = Io()
+    for e, x in enumerate(h_in):
+        io.in_[e] = x.data_ptr()
+    io.params = h_params.ctypes.data
+    io.pcm = h_pcm.data_ptr()
+    io.out_counts = h_counts.data_ptr()
+
+    def step_e2e():
+        _check(eng_e.L.iamfb_batch_submit_host(eng_e.batch, C.byref(io), Fe), "iamfb_batch_submit_host")
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ke = max(2, min(args.steps, 6))
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        step_e2e()
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    out_e = float(h_counts.sum().item())
+    te_t = torch.tensor([te], device=dev, dtype=torch.float64)
+    oe_t = torch.tensor([out_e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(oe_t, op=dist.ReduceOp.SUM)
+    e2e_value = float(oe_t.item()) / sc.out_rate * ke / float(te_t.item())
+    h2d = sum(x.numel() * 4 for x in h_in) + h_params.nbytes
+    d2h = S_ * stride_e + h_counts.numel() * 4
+
+    if rank == 0:
+        clocks = sampler.summary()
+        line = {
+            "metric": "rendered audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{cfg}: {CONFIGS[cfg]['desc']}", "streams_per_gpu": S_, "frames_per_step": F,
+                       "frame_size": sc.frame_size, "input_bytes_per_step_per_gpu": int(sum(x.numel() * 4 for x in inputs)),
+                       "l2_policy": "inputs larger than L2 (126 MB); nothing re-read across steps",
+                       "limiter_active_peak_range_db": list(sc.peak_db)},
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "frames_per_step": Fe, "steps": ke},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    eng.close()
+    eng_e.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import refstreams
+    cfg = args.config
+    sc, _, _, _ = refstreams.case(cfg)
+    cores = os.cpu_count() or 1
+    n_streams = max(cores, 8) * 2
+    vals, secs = [], []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_reference(cfg, n_streams=n_streams, n_frames=args.cpu_frames, seed=i)
+        if i >= args.warmup:
+            vals.append(res["value"])
+            secs.append(res["seconds"])
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "rendered audio-sec/sec", "value": value, "unit": "audio-s/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{cfg}: {CONFIGS[cfg]['desc']}", "sample_streams": n_streams, "sample_frames": args.cpu_frames},
+        "cpu_baseline": dict(value=value, unit="audio-s/s", cores=res["cores"], kind=res["kind"], sample=res["sample"]),
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--frames", type=int, default=0)
+    ap.add_argument("--e2e-frames", type=int, default=4)
+    ap.add_argument("--cpu-frames", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,9 @@ def lib():
     L.iamfb_host_free.restype = None
     L.iamfb_ctx_launch_count.argtypes = [vp]
     L.iamfb_ctx_launch_count.restype = C.c_uint64
+    L.iamfb_ctx_set_timing.argtypes = [vp, C.c_int]
+    L.iamfb_ctx_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_uint64)]
     L.iamfb_target_channels.argtypes = [C.c_int]
     L.iamfb_layout_channels.argtypes = [C.c_int, C.POINTER(C.c_int32)]
     L.iamfb_get_m2m_matrix.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -225,6 +228,19 @@ class Engine:
 
     def launch_count(self):
         return self.L.iamfb_ctx_launch_count(self.ctx)
+
+    def set_timing(self, enable):
+        _check(self.L.iamfb_ctx_set_timing(self.ctx, 1 if enable else 0), "iamfb_ctx_set_timing")
+
+    def get_timing(self):
+        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream"""
+        out, i = {}, 0
+        while True:
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_uint64()
+            if self.L.iamfb_ctx_get_timing(self.ctx, i, C.byref(name), C.byref(ms), C.byref(n)) != 0:
+                return out
+            out[name.value.decode()] = (ms.value, n.value)
+            i += 1
 
     def synchronize(self):
         _check(self.L.iamfb_ctx_synchronize(self.ctx), "iamfb_ctx_synchronize")

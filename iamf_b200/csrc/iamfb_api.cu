@@ -95,11 +95,47 @@ extern "C" int iamfb_get_h2m_matrix(int order, int target, int32_t *m, int32_t *
 // ---------------------------------------------------------------------------------------------------------------------
 // objects
 // ---------------------------------------------------------------------------------------------------------------------
+struct KernelTimer {
+  const char *name;
+  double total_ms;
+  uint64_t launches;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
 struct iamfb_ctx {
   int device;
   cudaStream_t stream;
   bool own_stream;
   uint64_t launches;
+  bool timing;
+  std::vector<KernelTimer> timers;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+// optional per-kernel CUDA-event timing (bench.py's roofline leg); events are recorded on the launching stream
+struct ScopedKernelTimer {
+  iamfb_ctx *ctx;
+  KernelTimer *t = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get(iamfb_ctx *c) {
+    cudaEvent_t e;
+    if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+  }
+  ScopedKernelTimer(iamfb_ctx *c, const char *name) : ctx(c) {
+    if (!c->timing) return;
+    for (auto &k : c->timers) if (k.name == name) t = &k;
+    if (!t) { c->timers.push_back(KernelTimer{name, 0.0, 0, {}}); t = &c->timers.back(); }
+    a = get(c); b = get(c);
+    cudaEventRecord(a, c->stream);
+  }
+  ~ScopedKernelTimer() {
+    if (!t) return;
+    cudaEventRecord(b, ctx->stream);
+    t->pending.emplace_back(a, b);
+    ++t->launches;
+  }
 };
 
 struct iamfb_plan {
@@ -155,6 +191,7 @@ extern "C" int iamfb_ctx_create(int device, iamfb_ctx **out) {
   iamfb_ctx *c = new iamfb_ctx();
   c->device = device;
   c->launches = 0;
+  c->timing = false;
   c->own_stream = true;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   *out = c;
@@ -182,6 +219,33 @@ extern "C" void iamfb_ctx_destroy(iamfb_ctx *c) {
 }
 
 extern "C" uint64_t iamfb_ctx_launch_count(const iamfb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int iamfb_ctx_set_timing(iamfb_ctx *c, int enable) {
+  if (!c) return fail(IAMFB_ERR_BAD_ARG, "null ctx");
+  c->timing = enable != 0;
+  if (enable) c->timers.clear();
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_ctx_get_timing(iamfb_ctx *c, int index, const char **name, double *total_ms, uint64_t *launches) {
+  if (!c || index < 0 || index >= (int)c->timers.size()) return IAMFB_ERR_BAD_ARG;
+  KernelTimer &k = c->timers[index];
+  if (!k.pending.empty()) {
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto &p : k.pending) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, p.first, p.second);
+      k.total_ms += ms;
+      c->event_pool.push_back(p.first);
+      c->event_pool.push_back(p.second);
+    }
+    k.pending.clear();
+  }
+  if (name) *name = k.name;
+  if (total_ms) *total_ms = k.total_ms;
+  if (launches) *launches = k.launches;
+  return IAMFB_OK;
+}
 
 extern "C" void *iamfb_host_alloc(size_t bytes) {
   void *p = nullptr;
@@ -611,7 +675,9 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
   if (kp.resample) {
     std::vector<float> table;
     build_resampler(kp, table, d->in_rate, d->out_rate);
-    if (kp.rs_filt_len - 1 > (unsigned)kRsHist) { delete p; return fail(IAMFB_ERR_UNIMPLEMENTED, "resampler filter length %u > %d (ratio %d:%d)", kp.rs_filt_len, kRsHist + 1, d->in_rate, d->out_rate); }
+    kp.rs_hist = (int)((kp.rs_filt_len - 1 + 3) & ~3u);
+    if (kp.rs_hist < 64) kp.rs_hist = 64;
+    if (kp.rs_hist > kMaxRsHist) { delete p; return fail(IAMFB_ERR_UNIMPLEMENTED, "resampler filter length %u > %d (ratio %d:%d)", kp.rs_filt_len, kMaxRsHist, d->in_rate, d->out_rate); }
     p->sinc_len = (int)table.size();
     int r = upload(&p->d_sinc, table.data(), table.size());
     if (r) { delete p; return r; }
@@ -640,7 +706,7 @@ extern "C" int iamfb_plan_max_out_samples(const iamfb_plan *p, int n_frames) {
   long long out = in;
   if (p->kp.resample) out = (in * p->kp.rs_den + p->kp.rs_num - 1) / p->kp.rs_num + 2;
   // a flush can add the limiter delay plus the resampler's output latency
-  long long flush = kLimDelay + 64;
+  long long flush = kLimDelay + 64 + (p->kp.resample ? (long long)p->kp.rs_filt_len * p->kp.rs_den / p->kp.rs_num : 0);
   return (int)(out > flush ? out : flush);
 }
 
@@ -684,7 +750,7 @@ extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, 
   b->Fmax = max_frames;
   const KernelPlan &kp = p->kp;
   const int co = kp.out_channels;
-  b->cap_a = kp.resample ? round4(kRsHist + max_frames * kp.frame_size + 64) : 0;
+  b->cap_a = kp.resample ? round4(kp.rs_hist + max_frames * kp.frame_size + (int)kp.rs_filt_len) : 0;
   b->cap_b = round4(kp.hist + iamfb_plan_max_out_samples(p, max_frames) + 64);
   b->out_stride = iamfb_plan_out_stride_bytes(p, max_frames);
   cudaError_t e = cudaSuccess;
@@ -739,7 +805,7 @@ template <int VEC>
 static int launch_render(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const RenderArgs &ra, int blocks) {
   cudaStream_t st = ctx->stream;
 #define RCASE(ID, LAYOUT, NREC) \
-  case ID: k_render<LAYOUT, NREC, VEC><<<blocks, 128, 0, st>>>(kp, ra); break;
+  case ID: { ScopedKernelTimer tm_(ctx, "k_render"); k_render<LAYOUT, NREC, VEC><<<blocks, 128, 0, st>>>(kp, ra); } break;
   switch (tmpl) {
     RCASE(0, 0, 1) RCASE(1, 1, 2) RCASE(2, 2, 6) RCASE(3, 3, 8) RCASE(4, 4, 10) RCASE(5, 5, 8) RCASE(6, 6, 10)
     RCASE(7, 7, 12) RCASE(8, 8, 6)
@@ -770,12 +836,12 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     a.n_streams = S;
     a.n_frames = flush ? 0 : F;
     a.flush = flush ? 1 : 0;
-    k_resolve<<<(S + 127) / 128, 128, 0, st>>>(kp, a);
+    { ScopedKernelTimer tm_(ctx, "k_resolve"); k_resolve<<<(S + 127) / 128, 128, 0, st>>>(kp, a); }
     LAUNCH_CHECK("k_resolve");
   }
   float *tl_first = kp.resample ? b->d_tl_a : b->d_tl_b;
   const int cap_first = kp.resample ? b->cap_a : b->cap_b;
-  const int hist_first = kp.resample ? kRsHist : kp.hist;
+  const int hist_first = kp.resample ? kp.rs_hist : kp.hist;
 
   if (!flush) {
     // K1 per element
@@ -806,14 +872,14 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   } else {
     // flush: the resampler is fed filt_len/2 zeros, the limiter the resampler tail followed by 240 zeros
     if (kp.resample) {
-      for (int s = 0; s < 1; ++s) {}
-      CU(cudaMemset2DAsync(b->d_tl_a + kRsHist, sizeof(float) * b->cap_a, 0, sizeof(float) * 64, (size_t)S * co, st));
+      CU(cudaMemset2DAsync(b->d_tl_a + kp.rs_hist, sizeof(float) * b->cap_a, 0, sizeof(float) * (kp.rs_filt_len / 2), (size_t)S * co, st));
     }
-    CU(cudaMemset2DAsync(b->d_tl_b + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * (kLimDelay + 64), (size_t)S * co, st));
-    if (b->d_pk) CU(cudaMemset2DAsync(b->d_pk + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * (kLimDelay + 64), (size_t)S, st));
+    const size_t zlen = (size_t)iamfb_plan_max_out_samples(p, 0);
+    CU(cudaMemset2DAsync(b->d_tl_b + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * zlen, (size_t)S * co, st));
+    if (b->d_pk) CU(cudaMemset2DAsync(b->d_pk + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * zlen, (size_t)S, st));
   }
 
-  const int max_out = flush ? (kLimDelay + 64) : iamfb_plan_max_out_samples(p, F);
+  const int max_out = flush ? iamfb_plan_max_out_samples(p, 0) : iamfb_plan_max_out_samples(p, F);
   if (kp.resample) {
     ResampleArgs a;
     a.src = b->d_tl_a;
@@ -829,40 +895,40 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     a.flush = flush ? 1 : 0;
     dim3 grid((max_out + 127) / 128, S);
     size_t smem = p->sinc_len <= 12 * 1024 ? sizeof(float) * p->sinc_len : 0;
-    k_resample<<<grid, 128, smem, st>>>(kp, a);
+    { ScopedKernelTimer tm_(ctx, "k_resample"); k_resample<<<grid, 128, smem, st>>>(kp, a); }
     LAUNCH_CHECK("k_resample");
     if (!flush) {
       CarryArgs c;
-      c.tl = b->d_tl_a; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_a; c.hist = kRsHist; c.use_in_len = 1;
-      k_carry<<<dim3(co, S), 256, 0, st>>>(c);
+      c.tl = b->d_tl_a; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_a; c.hist = kp.rs_hist; c.use_in_len = 1;
+      { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
       LAUNCH_CHECK("k_carry");
     }
   }
   if (kp.limiter) {
     WmaxArgs w;
     w.pk = b->d_pk; w.wm = b->d_wm; w.submit = b->d_submit; w.cap = b->cap_b; w.hist = kp.hist; w.flush = flush;
-    k_window_max<<<dim3((max_out + kWmTile - 1) / kWmTile, S), 256, 0, st>>>(kp, w);
+    { ScopedKernelTimer tm_(ctx, "k_window_max"); k_window_max<<<dim3((max_out + kWmTile - 1) / kWmTile, S), 256, 0, st>>>(kp, w); }
     LAUNCH_CHECK("k_window_max");
     ScanArgs sa;
     sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = b->d_submit; sa.acc = p->d_acc;
     sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = max_out;
-    k_limiter_scan<<<(S + 127) / 128, 128, 0, st>>>(kp, sa);
+    { ScopedKernelTimer tm_(ctx, "k_limiter_scan"); k_limiter_scan<<<(S + 127) / 128, 128, 0, st>>>(kp, sa); }
     LAUNCH_CHECK("k_limiter_scan");
   }
   {
     OutputArgs o;
     o.tl = b->d_tl_b; o.gn = kp.limiter ? b->d_gn : nullptr; o.submit = b->d_submit; o.pcm = pcm;
     o.stride_bytes = stride; o.cap = b->cap_b; o.hist = kp.hist;
-    k_output<<<dim3((max_out + 255) / 256, S), 256, 0, st>>>(kp, o);
+    { ScopedKernelTimer tm_(ctx, "k_output"); k_output<<<dim3((max_out + 255) / 256, S), 256, 0, st>>>(kp, o); }
     LAUNCH_CHECK("k_output");
   }
   if (kp.limiter && !flush) {
     CarryArgs c;
     c.tl = b->d_tl_b; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_b; c.hist = kLimDelay; c.use_in_len = 0;
-    k_carry<<<dim3(co, S), 256, 0, st>>>(c);
+    { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
     LAUNCH_CHECK("k_carry");
     c.tl = b->d_pk; c.rows = 1;
-    k_carry<<<dim3(1, S), 256, 0, st>>>(c);
+    { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(1, S), 256, 0, st>>>(c); }
     LAUNCH_CHECK("k_carry");
   }
   return IAMFB_OK;

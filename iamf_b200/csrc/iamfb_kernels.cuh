@@ -7,7 +7,7 @@
 //
 // Data layout in HBM (S streams, F frames per submit, N samples per frame):
 //   in[e]      f32 [S][F][C_in][N]        decoded planar frames (as core decode hands them over)
-//   tl_a       f32 [S][C_out][cap_a]      pre-resample time line (kRsHist history + F*N), only when resampling
+//   tl_a       f32 [S][C_out][cap_a]      pre-resample time line (rs_hist history + F*N), only when resampling
 //   tl_b       f32 [S][C_out][cap_b]      mixed time line entering the limiter: [hist | samples of this submit]
 //   pk         f32 [S][cap_b]             per-instant cross-channel peak max_c |x|, same time axis as tl_b
 //   gn         f32 [S][cap_b]             limiter gain per instant
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(128) k_render(const __grid_constant__ KernelPl
 // thread = one output instant of one stream, looping over channels (taps are reused across channels).
 // -------------------------------------------------------------------------------------------------------------------
 struct ResampleArgs {
-  const float *src;        // tl_a [S][C][cap_a], history kRsHist.. input position p of this submit at kRsHist + p
+  const float *src;        // tl_a [S][C][cap_a]: rs_hist history samples, then the inputs of this submit
   float *dst;              // tl_b [S][C][cap_b]
   float *pk;               // [S][cap_b]
   const SubmitRec *submit;
@@ -601,9 +601,9 @@ __global__ void __launch_bounds__(128) k_resample(const __grid_constant__ Kernel
   const long long num = plan.rs_num, den = plan.rs_den;
   const long long q = (long long)(Nf / 2) + (n * num) / den;
   const unsigned int frac_num = (unsigned int)((n * (long long)plan.rs_frac_adv) % den);
-  const long long in_start = a.state[s].rs_in_total - sr.in_len;     // stream position of tl_a[kRsHist]
+  const long long in_start = a.state[s].rs_in_total - sr.in_len;     // stream position of tl_a[rs_hist]
   // first tap reads stream position q - (Nf-1)
-  const long long p0 = q - (Nf - 1) - in_start + kRsHist;             // index into tl_a row
+  const long long p0 = q - (Nf - 1) - in_start + plan.rs_hist;             // index into tl_a row
   const int co = plan.out_channels;
   const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f && !a.flush;
   float peak = 0.f;

@@ -11,8 +11,7 @@ constexpr int kMaxOut = IAMFB_MAX_OUT_CH;
 constexpr int kMaxRec = 16;            // reconstructed channels feeding a render matrix (12 layout / 16 HOA)
 constexpr int kChCount = IAMFB_CH_COUNT;
 constexpr int kLimDelay = IAMFB_LIMITER_DELAY;
-constexpr int kRsHist = 64;            // resampler history kept in front of every chunk (filt_len - 1 rounded up)
-constexpr int kMaxFiltLen = 256;
+constexpr int kMaxRsHist = 256;       // upper bound of the resampler history (filt_len - 1 rounded up to 4) -> ratios down to 4:1
 
 enum Renderer : int { kRdrM2M = 0, kRdrH2M = 1, kRdrDMR = 2 };
 
@@ -56,6 +55,7 @@ struct KernelPlan {
   // resampler
   unsigned int rs_num, rs_den, rs_filt_len, rs_oversample;
   int rs_int_adv, rs_frac_adv, rs_direct;
+  int rs_hist;              // input history kept in front of the pre-resample time line (>= filt_len - 1)
   ElPlan el[kMaxEl];
 };
 

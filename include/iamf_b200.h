@@ -199,6 +199,11 @@ void iamfb_host_free(void *p);
 /* number of kernel launches issued by this library since the context was created (bench.py's gpu_launches) */
 uint64_t iamfb_ctx_launch_count(const iamfb_ctx *ctx);
 
+/* optional per-kernel timing with CUDA events recorded on the context's stream (used by bench.py for the roofline
+ * figure; off by default).  iamfb_ctx_get_timing iterates index = 0,1,... until it returns non-zero. */
+int iamfb_ctx_set_timing(iamfb_ctx *ctx, int enable);
+int iamfb_ctx_get_timing(iamfb_ctx *ctx, int index, const char **name, double *total_ms, uint64_t *launches);
+
 /* ---- table accessors (host side, no device needed) ---- */
 int iamfb_target_channels(int target);                      /* IAMF_layout_sound_system_channels_count */
 int iamfb_layout_channels(int layout, int32_t *chs);        /* rendering order, IAMF_utils.c:117-133 */
