@@ -367,6 +367,7 @@ void build_limiter(KernelPlan &kp, std::vector<float> &acc, float thr_db, int ra
   }
   if (kp.lim_ja < 0) kp.lim_ja = j;
   kp.lim_jr = j;
+  for (int k = 0; k < 3; ++k) acc.push_back(0.f);   // padding: the scan kernel prefetches up to index j+3
 }
 
 template <typename T>
@@ -909,10 +910,18 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     w.pk = b->d_pk; w.wm = b->d_wm; w.submit = b->d_submit; w.cap = b->cap_b; w.hist = kp.hist; w.flush = flush;
     { ScopedKernelTimer tm_(ctx, "k_window_max"); k_window_max<<<dim3((max_out + kWmTile - 1) / kWmTile, S), 256, 0, st>>>(kp, w); }
     LAUNCH_CHECK("k_window_max");
+    const size_t scan_smem = (kp.lim_jr + 4) <= kScanAccSmem ? sizeof(float) * (kp.lim_jr + 4) : 0;
     ScanArgs sa;
     sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = b->d_submit; sa.acc = p->d_acc;
     sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = max_out;
-    { ScopedKernelTimer tm_(ctx, "k_limiter_scan"); k_limiter_scan<<<(S + 127) / 128, 128, 0, st>>>(kp, sa); }
+    {
+      ScopedKernelTimer tm_(ctx, "k_limiter_scan");
+      if (scan_smem) {
+        CU(cudaFuncSetAttribute(k_limiter_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+        k_limiter_scan<true><<<(S + 31) / 32, 32, scan_smem, st>>>(kp, sa);
+      }
+      else { k_limiter_scan<false><<<(S + 31) / 32, 32, 0, st>>>(kp, sa); }
+    }
     LAUNCH_CHECK("k_limiter_scan");
   }
   {

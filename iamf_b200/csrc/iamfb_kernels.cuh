@@ -286,21 +286,26 @@ template <int VEC>
 __device__ __forceinline__ void reconstruct_channels(const ElPlan &ep, const ElFrame &ef, const float *in_frame, int N,
                                                      int i0, bool vec_ok, int valid, const float *start_win,
                                                      const float *stop_win, int overlap, Vec<VEC> (&v)[kChCount]) {
-  // transmitted channels -> IAChannel slots (static register indices, uniform predicates)
+  // transmitted channels -> IAChannel slots (static register indices, uniform predicates).  All loads are issued
+  // before the first use so that a thread has its whole input (n_in x 16 B) in flight at once.
 #pragma unroll
   for (int c = 1; c < kChCount; ++c) {
     int row = ep.src_row[c];
     if (row >= 0) {
       v[c] = load_row<VEC>(in_frame + (size_t)row * N + i0, vec_ok, valid);
-      if ((ep.gain_mask >> c) & 1u) {   // dmx_gainup, demixer.c:421-430
-        float g = ep.gain[c];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v[c].v[k] *= g;
-      }
     } else {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) v[c].v[k] = 0.f;
     }
+  }
+  if (ep.gain_mask) {   // dmx_gainup, demixer.c:421-430
+#pragma unroll
+    for (int c = 1; c < kChCount; ++c)
+      if ((ep.gain_mask >> c) & 1u) {
+        float g = ep.gain[c];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[c].v[k] *= g;
+      }
   }
   const int mode = ef.mode & 7;
   if (ep.need_s2) {   // R2 = 2*Mono - L2, demixer.c:136-138
@@ -735,72 +740,105 @@ struct ScanArgs {
   int max_len;
 };
 
-__global__ void __launch_bounds__(128) k_limiter_scan(const __grid_constant__ KernelPlan plan, ScanArgs a) {
-  __shared__ float tile[4][32][33];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s0 = (blockIdx.x * 4 + warp) * 32;
-  if (s0 >= a.n_streams) return;
+// One warp per block (32 streams); the acceleration curve is staged in shared memory when it fits (ACC_SMEM).
+// The serial loop is branch-free and keeps every memory access off the dependent chain:
+//   * both the attack and the release candidate are formed every step and selected;
+//   * the curve values for the next two steps (acc[j+1], acc[j+2]) live in registers and acc[j+3] is fetched two steps
+//     ahead (after a trigger the indices restart at 1, 2 - constants);
+//   * peak and thr/peak (needed only when a trigger fires, IEEE division precomputed for the whole tile in the parallel
+//     load phase) are fetched together with one 64-bit shared load.
+// Dependent chain per sample: sub, mul, add, select, mul, compare, select.
+constexpr int kScanAccSmem = 50 * 1024;   // floats of the curve kept in shared memory (200 KB, opt-in dynamic smem)
+
+template <bool ACC_SMEM>
+__global__ void __launch_bounds__(32) k_limiter_scan(const __grid_constant__ KernelPlan plan, ScanArgs a) {
+  __shared__ float2 t_in[32][33];   // {peak, thr/peak}
+  __shared__ float t_g[32][33];
+  extern __shared__ float s_acc[];
+  const int lane = threadIdx.x;
+  const int s0 = blockIdx.x * 32;
   const int s = s0 + lane;
   const bool live = s < a.n_streams;
+  const int ja = plan.lim_ja, jr = plan.lim_jr;
+  // table has jr + 4 entries (zero padded) so that j+3 never runs off the end
+  if (ACC_SMEM) {
+    for (int i = lane; i < jr + 4; i += 32) s_acc[i] = a.acc[i];
+    __syncwarp();
+  }
+  auto acc_at = [&](int i) -> float { return ACC_SMEM ? s_acc[i] : __ldg(a.acc + i); };
   int len = live ? a.submit[s].lim_len : 0;
   int j = -1;
   float start = -1.f, end = -1.f;
   if (live) { j = a.state[s].lim_j; start = a.state[s].lim_start; end = a.state[s].lim_end; }
+  if (j > jr) j = jr;
   const float thr = plan.lim_thr;
-  const int ja = plan.lim_ja, jr = plan.lim_jr;
+  const float a1 = acc_at(1), a2 = acc_at(2);
   int max_len = len;
 #pragma unroll
   for (int o = 16; o; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
-  float (*t)[33] = tile[warp];
 
-  for (int k0 = 0; k0 < max_len; k0 += 32) {
-    // coalesced load of 32 streams x 32 instants
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      int sr = s0 + r;
-      int k = k0 + lane;
-      int lr = __shfl_sync(0xffffffffu, len, r);
-      t[r][lane] = (sr < a.n_streams && k < lr) ? a.wm[(size_t)sr * a.cap + a.hist + k] : 0.f;
-    }
-    __syncwarp();
-    // fast path: idle and the tile never crosses the threshold
-    float tmax = 0.f;
+  // software pipeline: the 32 row loads of tile k0+32 are issued before the serial walk over tile k0 and land while
+  // it runs (one DRAM latency per tile instead of one per row)
+  float nxt[32];
+  int lens[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, t[lane][i]);
+  for (int r = 0; r < 32; ++r) lens[r] = __shfl_sync(0xffffffffu, len, r);
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    int sr = s0 + r;
+    nxt[r] = (sr < a.n_streams && lane < lens[r]) ? a.wm[(size_t)sr * a.cap + a.hist + lane] : 0.f;
+  }
+  for (int k0 = 0; k0 < max_len; k0 += 32) {
+    // publish the prefetched tile; thr/peak for the whole tile (IEEE division, :259)
+    float tmax_part = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t_in[r][lane] = make_float2(nxt[r], thr / nxt[r]);
+    __syncwarp();
+    if (k0 + 32 < max_len) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        int sr = s0 + r;
+        int k = k0 + 32 + lane;
+        nxt[r] = (sr < a.n_streams && k < lens[r]) ? a.wm[(size_t)sr * a.cap + a.hist + k] : 0.f;
+      }
+    }
+    float tmax = tmax_part;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, t_in[lane][i].x);
     const bool idle = (j < 0 || j >= jr);
     const bool quiet = idle && !(tmax * 1.0f > thr);
     if (!__all_sync(0xffffffffu, quiet)) {
       const int nk = min(32, len - k0);
+      const int jc = min(max(j, 0), jr);
+      float p1 = acc_at(jc + 1), p2 = acc_at(jc + 2);
+#pragma unroll 8
       for (int i = 0; i < nk; ++i) {
-        const float peak = t[lane][i];
-        float g;
-        if (j >= 0 && j < ja) {
-          ++j;
-          g = start - a.acc[j] * (start - end);
-        } else if (j >= 0 && j < jr) {
-          ++j;
-          g = end + a.acc[j] * (1.0f - end);
-        } else {
-          g = 1.0f;
-        }
-        if (peak * g > thr) {
-          start = g;
-          end = thr / peak;
-          j = 0;
-        }
-        t[lane][i] = g;
+        const float2 in = t_in[lane][i];
+        const float p3 = acc_at(min(max(j, 0), jr) + 3);   // lands two steps from now
+        const bool active = (j >= 0) && (j < jr);
+        const bool attack = active && (j < ja);
+        const float ga = start - p1 * (start - end);
+        const float gr = end + p1 * (1.0f - end);
+        const float g = active ? (attack ? ga : gr) : 1.0f;
+        const int jn = active ? j + 1 : j;
+        const bool trig = in.x * g > thr;
+        start = trig ? g : start;
+        end = trig ? in.y : end;
+        j = trig ? 0 : jn;
+        p1 = trig ? a1 : p2;
+        p2 = trig ? a2 : p3;
+        t_g[lane][i] = g;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) t[lane][i] = 1.0f;
+      for (int i = 0; i < 32; ++i) t_g[lane][i] = 1.0f;
     }
     __syncwarp();
-#pragma unroll 4
+#pragma unroll
     for (int r = 0; r < 32; ++r) {
       int sr = s0 + r;
       int k = k0 + lane;
-      int lr = __shfl_sync(0xffffffffu, len, r);
-      if (sr < a.n_streams && k < lr) a.gn[(size_t)sr * a.cap + a.hist + k] = t[r][lane];
+      if (sr < a.n_streams && k < lens[r]) a.gn[(size_t)sr * a.cap + a.hist + k] = t_g[r][lane];
     }
     __syncwarp();
   }
@@ -852,21 +890,29 @@ __global__ void __launch_bounds__(256) k_output(const __grid_constant__ KernelPl
   const float g = a.gn ? a.gn[(size_t)s * a.cap + a.hist + k] : 1.f;
   const float *base = a.tl + (size_t)s * co * a.cap + a.hist + k - delay;
   char *out = (char *)a.pcm + (size_t)s * a.stride_bytes;
-  for (int c = 0; c < co; ++c) {
-    float x = base[(size_t)c * a.cap];
-    if (a.gn) x = x * g;
-    if (plan.bit_depth == 16) {
-      ((int16_t *)out)[(size_t)o * co + c] = (int16_t)quant16(x);
-    } else if (plan.bit_depth == 24) {
-      int v = quant24(x);
-      unsigned char *p = (unsigned char *)out + ((size_t)o * co + c) * 3;
-      p[0] = v & 0xff;
-      p[1] = (v >> 8) & 0xff;
-      p[2] = ((v >> 16) & 0x7f) | ((v >> 24) & 0x80);
-    } else if (plan.bit_depth == 32) {
-      ((int32_t *)out)[(size_t)o * co + c] = quant32(x);
-    } else {
-      ((float *)out)[(size_t)o * co + c] = x;
+  for (int c0 = 0; c0 < co; c0 += 8) {
+    float xs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xs[u] = (c0 + u < co) ? base[(size_t)(c0 + u) * a.cap] : 0.f;   // 8 loads in flight
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + u;
+      if (c >= co) break;
+      float x = xs[u];
+      if (a.gn) x = x * g;
+      if (plan.bit_depth == 16) {
+        ((int16_t *)out)[(size_t)o * co + c] = (int16_t)quant16(x);
+      } else if (plan.bit_depth == 24) {
+        int v = quant24(x);
+        unsigned char *p = (unsigned char *)out + ((size_t)o * co + c) * 3;
+        p[0] = v & 0xff;
+        p[1] = (v >> 8) & 0xff;
+        p[2] = ((v >> 16) & 0x7f) | ((v >> 24) & 0x80);
+      } else if (plan.bit_depth == 32) {
+        ((int32_t *)out)[(size_t)o * co + c] = quant32(x);
+      } else {
+        ((float *)out)[(size_t)o * co + c] = x;
+      }
     }
   }
 }
