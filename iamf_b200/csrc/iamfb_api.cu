@@ -110,6 +110,10 @@ struct iamfb_ctx {
   bool timing;
   std::vector<KernelTimer> timers;
   std::vector<cudaEvent_t> event_pool;
+  // second stream for the latency-bound limiter scan, so that it overlaps the bandwidth-bound kernels of the
+  // neighbouring sub-chunks; ordered against the main stream with events
+  cudaStream_t aux;
+  cudaEvent_t ev_w[kMaxSub], ev_s[kMaxSub];
 };
 
 // optional per-kernel CUDA-event timing (bench.py's roofline leg); events are recorded on the launching stream
@@ -123,16 +127,17 @@ struct ScopedKernelTimer {
     cudaEventCreate(&e);
     return e;
   }
-  ScopedKernelTimer(iamfb_ctx *c, const char *name) : ctx(c) {
+  cudaStream_t st;
+  ScopedKernelTimer(iamfb_ctx *c, const char *name, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
     if (!c->timing) return;
     for (auto &k : c->timers) if (k.name == name) t = &k;
     if (!t) { c->timers.push_back(KernelTimer{name, 0.0, 0, {}}); t = &c->timers.back(); }
     a = get(c); b = get(c);
-    cudaEventRecord(a, c->stream);
+    cudaEventRecord(a, st);
   }
   ~ScopedKernelTimer() {
     if (!t) return;
-    cudaEventRecord(b, ctx->stream);
+    cudaEventRecord(b, st);
     t->pending.emplace_back(a, b);
     ++t->launches;
   }
@@ -194,6 +199,11 @@ extern "C" int iamfb_ctx_create(int device, iamfb_ctx **out) {
   c->timing = false;
   c->own_stream = true;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+  for (int i = 0; i < kMaxSub; ++i) {
+    CU(cudaEventCreateWithFlags(&c->ev_w[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_s[i], cudaEventDisableTiming));
+  }
   *out = c;
   return IAMFB_OK;
 }
@@ -215,6 +225,8 @@ extern "C" int iamfb_ctx_synchronize(iamfb_ctx *c) {
 extern "C" void iamfb_ctx_destroy(iamfb_ctx *c) {
   if (!c) return;
   if (c->own_stream) cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->aux);
+  for (int i = 0; i < kMaxSub; ++i) { cudaEventDestroy(c->ev_w[i]); cudaEventDestroy(c->ev_s[i]); }
   delete c;
 }
 
@@ -232,6 +244,7 @@ extern "C" int iamfb_ctx_get_timing(iamfb_ctx *c, int index, const char **name, 
   KernelTimer &k = c->timers[index];
   if (!k.pending.empty()) {
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->aux));
     for (auto &p : k.pending) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, p.first, p.second);
@@ -802,6 +815,33 @@ extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
     ++ctx->launches;                                                                                            \
   } while (0)
 
+static int launch_render_bulk(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const RenderArgs &ra, int n_tiles) {
+  cudaStream_t st = ctx->stream;
+  const size_t smem = sizeof(float) * (size_t)kRenderStages * kp.el[ra.e].n_in * kRenderTile;
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  int grid = dev_sms * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+#define BCASE(ID, LAYOUT, NREC)                                                                                      \
+  case ID: {                                                                                                         \
+    CU(cudaFuncSetAttribute(k_render_bulk<LAYOUT, NREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    ScopedKernelTimer tm_(ctx, "k_render");                                                                          \
+    k_render_bulk<LAYOUT, NREC><<<grid, 128, smem, st>>>(kp, ra, n_tiles);                                          \
+  } break;
+  switch (tmpl) {
+    BCASE(0, 0, 1) BCASE(1, 1, 2) BCASE(2, 2, 6) BCASE(3, 3, 8) BCASE(4, 4, 10) BCASE(5, 5, 8) BCASE(6, 6, 10)
+    BCASE(7, 7, 12) BCASE(8, 8, 6)
+    BCASE(10, -1, 1) BCASE(11, -1, 4) BCASE(12, -1, 9) BCASE(13, -1, 16)
+    default: return fail(IAMFB_ERR_INTERNAL, "no render kernel variant %d", tmpl);
+  }
+#undef BCASE
+  LAUNCH_CHECK("k_render_bulk");
+  return IAMFB_OK;
+}
+
 template <int VEC>
 static int launch_render(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const RenderArgs &ra, int blocks) {
   cudaStream_t st = ctx->stream;
@@ -818,12 +858,25 @@ static int launch_render(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const R
   return IAMFB_OK;
 }
 
+static int n_subchunks(const KernelPlan &kp, int F, bool flush) {
+  if (flush || !kp.limiter || kp.resample) return 1;
+  const char *env = getenv("IAMFB_SUBCHUNKS");
+  int n = env ? atoi(env) : (F >= 8 ? 4 : (F >= 4 ? 2 : 1));
+  if (n < 1) n = 1;
+  if (n > kMaxSub) n = kMaxSub;
+  if (n > F) n = F;
+  return n;
+}
+
 static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, void *pcm, int32_t *counts, size_t stride) {
   iamfb_plan *p = b->plan;
   iamfb_ctx *ctx = p->ctx;
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
   const int S = b->S, N = kp.frame_size, co = kp.out_channels;
+  const int n_sub = n_subchunks(kp, F, flush);
+  int sub_frame[kMaxSub + 1];
+  for (int c = 0; c <= kMaxSub; ++c) sub_frame[c] = flush ? 0 : (c >= n_sub ? F : (int)((long long)F * c / n_sub));
 
   // K0
   {
@@ -837,6 +890,8 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     a.n_streams = S;
     a.n_frames = flush ? 0 : F;
     a.flush = flush ? 1 : 0;
+    a.n_sub = n_sub;
+    for (int c = 0; c <= kMaxSub; ++c) a.sub_frame[c] = sub_frame[c];
     { ScopedKernelTimer tm_(ctx, "k_resolve"); k_resolve<<<(S + 127) / 128, 128, 0, st>>>(kp, a); }
     LAUNCH_CHECK("k_resolve");
   }
@@ -844,8 +899,16 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   const int cap_first = kp.resample ? b->cap_a : b->cap_b;
   const int hist_first = kp.resample ? kp.rs_hist : kp.hist;
 
-  if (!flush) {
-    // K1 per element
+  if (flush) {
+    // the resampler is fed filt_len/2 zeros, the limiter the resampler tail followed by 240 zeros
+    if (kp.resample)
+      CU(cudaMemset2DAsync(b->d_tl_a + kp.rs_hist, sizeof(float) * b->cap_a, 0, sizeof(float) * (kp.rs_filt_len / 2), (size_t)S * co, st));
+    const size_t zlen = (size_t)iamfb_plan_max_out_samples(p, 0);
+    CU(cudaMemset2DAsync(b->d_tl_b + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * zlen, (size_t)S * co, st));
+    if (b->d_pk) CU(cudaMemset2DAsync(b->d_pk + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * zlen, (size_t)S, st));
+  }
+
+  auto render = [&](int f_lo, int nf) -> int {
     const bool vec4 = (N % 4) == 0;
     const int vec = vec4 ? 4 : 1;
     const int tiles = (N + 128 * vec - 1) / (128 * vec);
@@ -863,82 +926,126 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       ra.hist = hist_first;
       ra.n_frames = F;
       ra.e = e;
+      ra.f_lo = f_lo;
+      ra.nf = nf;
       ra.first = e == 0;
       ra.last = e == kp.n_elements - 1;
       ra.tiles_per_frame = tiles;
-      int blocks = S * F * tiles;
-      int r = vec4 ? launch_render<4>(ctx, p->tmpl[e], kp, ra, blocks) : launch_render<1>(ctx, p->tmpl[e], kp, ra, blocks);
+      int blocks = S * nf * tiles;
+      // the bulk-copy staged variant is bit-identical but measured slower than the direct one on B200 (1.01 vs 0.57 ms
+      // on configs[1]: the kernel is instruction-issue bound, not load-latency bound) - kept selectable for profiling
+      static const bool use_bulk = getenv("IAMFB_RENDER_BULK") && atoi(getenv("IAMFB_RENDER_BULK")) == 1;
+      int r;
+      if (vec4 && use_bulk) {
+        ra.tiles_per_frame = (N + kRenderTile - 1) / kRenderTile;
+        r = launch_render_bulk(ctx, p->tmpl[e], kp, ra, S * nf * ra.tiles_per_frame);
+      } else {
+        r = vec4 ? launch_render<4>(ctx, p->tmpl[e], kp, ra, blocks) : launch_render<1>(ctx, p->tmpl[e], kp, ra, blocks);
+      }
       if (r) return r;
     }
-  } else {
-    // flush: the resampler is fed filt_len/2 zeros, the limiter the resampler tail followed by 240 zeros
-    if (kp.resample) {
-      CU(cudaMemset2DAsync(b->d_tl_a + kp.rs_hist, sizeof(float) * b->cap_a, 0, sizeof(float) * (kp.rs_filt_len / 2), (size_t)S * co, st));
+    return IAMFB_OK;
+  };
+  auto output = [&](int sub, int max_len) -> int {
+    OutputArgs o;
+    o.tl = b->d_tl_b; o.gn = kp.limiter ? b->d_gn : nullptr; o.submit = b->d_submit; o.pcm = pcm;
+    o.stride_bytes = stride; o.cap = b->cap_b; o.hist = kp.hist; o.sub = sub;
+    {
+      ScopedKernelTimer tm_(ctx, "k_output");
+      dim3 grid((max_len / 4 + 1 + 255) / 256, S);
+      switch (kp.bit_depth) {
+        case 16: k_output<16><<<grid, 256, 0, st>>>(kp, o); break;
+        case 24: k_output<24><<<grid, 256, 0, st>>>(kp, o); break;
+        case 32: k_output<32><<<grid, 256, 0, st>>>(kp, o); break;
+        default: k_output<0><<<grid, 256, 0, st>>>(kp, o); break;
+      }
     }
-    const size_t zlen = (size_t)iamfb_plan_max_out_samples(p, 0);
-    CU(cudaMemset2DAsync(b->d_tl_b + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * zlen, (size_t)S * co, st));
-    if (b->d_pk) CU(cudaMemset2DAsync(b->d_pk + kp.hist, sizeof(float) * b->cap_b, 0, sizeof(float) * zlen, (size_t)S, st));
-  }
+    LAUNCH_CHECK("k_output");
+    return IAMFB_OK;
+  };
 
   const int max_out = flush ? iamfb_plan_max_out_samples(p, 0) : iamfb_plan_max_out_samples(p, F);
-  if (kp.resample) {
-    ResampleArgs a;
-    a.src = b->d_tl_a;
-    a.dst = b->d_tl_b;
-    a.pk = b->d_pk;
-    a.submit = b->d_submit;
-    a.state = b->d_state;
-    a.sinc = p->d_sinc;
-    a.cap_a = b->cap_a;
-    a.cap_b = b->cap_b;
-    a.hist_b = kp.hist;
-    a.max_out = max_out;
-    a.flush = flush ? 1 : 0;
-    dim3 grid((max_out + 127) / 128, S);
-    size_t smem = p->sinc_len <= 12 * 1024 ? sizeof(float) * p->sinc_len : 0;
-    { ScopedKernelTimer tm_(ctx, "k_resample"); k_resample<<<grid, 128, smem, st>>>(kp, a); }
-    LAUNCH_CHECK("k_resample");
-    if (!flush) {
-      CarryArgs c;
-      c.tl = b->d_tl_a; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_a; c.hist = kp.rs_hist; c.use_in_len = 1;
-      { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
-      LAUNCH_CHECK("k_carry");
+  if (n_sub == 1) {
+    if (!flush) { int r = render(0, F); if (r) return r; }
+    if (kp.resample) {
+      ResampleArgs a;
+      a.src = b->d_tl_a;
+      a.dst = b->d_tl_b;
+      a.pk = b->d_pk;
+      a.submit = b->d_submit;
+      a.state = b->d_state;
+      a.sinc = p->d_sinc;
+      a.cap_a = b->cap_a;
+      a.cap_b = b->cap_b;
+      a.hist_b = kp.hist;
+      a.max_out = max_out;
+      a.flush = flush ? 1 : 0;
+      dim3 grid((max_out + 127) / 128, S);
+      size_t smem = p->sinc_len <= 12 * 1024 ? sizeof(float) * p->sinc_len : 0;
+      { ScopedKernelTimer tm_(ctx, "k_resample"); k_resample<<<grid, 128, smem, st>>>(kp, a); }
+      LAUNCH_CHECK("k_resample");
+      if (!flush) {
+        CarryArgs c;
+        c.tl = b->d_tl_a; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_a; c.hist = kp.rs_hist; c.use_in_len = 1;
+        { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
+        LAUNCH_CHECK("k_carry");
+      }
     }
   }
   if (kp.limiter) {
-    WmaxArgs w;
-    w.pk = b->d_pk; w.wm = b->d_wm; w.submit = b->d_submit; w.cap = b->cap_b; w.hist = kp.hist; w.flush = flush;
-    { ScopedKernelTimer tm_(ctx, "k_window_max"); k_window_max<<<dim3((max_out + kWmTile - 1) / kWmTile, S), 256, 0, st>>>(kp, w); }
-    LAUNCH_CHECK("k_window_max");
     const size_t scan_smem = (kp.lim_jr + 4) <= kScanAccSmem ? sizeof(float) * (kp.lim_jr + 4) : 0;
-    ScanArgs sa;
-    sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = b->d_submit; sa.acc = p->d_acc;
-    sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = max_out;
-    {
-      ScopedKernelTimer tm_(ctx, "k_limiter_scan");
-      if (scan_smem) {
-        CU(cudaFuncSetAttribute(k_limiter_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-        k_limiter_scan<true><<<(S + 31) / 32, 32, scan_smem, st>>>(kp, sa);
+    if (scan_smem) CU(cudaFuncSetAttribute(k_limiter_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    cudaStream_t scan_st = n_sub > 1 ? ctx->aux : st;
+    for (int c = 0; c < n_sub; ++c) {
+      const int sub_len = n_sub == 1 ? max_out : (sub_frame[c + 1] - sub_frame[c]) * N;
+      if (n_sub > 1) { int r = render(sub_frame[c], sub_frame[c + 1] - sub_frame[c]); if (r) return r; }
+      WmaxArgs w;
+      w.pk = b->d_pk; w.wm = b->d_wm; w.submit = b->d_submit; w.cap = b->cap_b; w.hist = kp.hist; w.flush = flush; w.sub = c;
+      { ScopedKernelTimer tm_(ctx, "k_window_max"); k_window_max<<<dim3((sub_len + kWmTile - 1) / kWmTile, S), 256, 0, st>>>(kp, w); }
+      LAUNCH_CHECK("k_window_max");
+      if (n_sub > 1) {
+        CU(cudaEventRecord(ctx->ev_w[c], st));
+        CU(cudaStreamWaitEvent(scan_st, ctx->ev_w[c], 0));
       }
-      else { k_limiter_scan<false><<<(S + 31) / 32, 32, 0, st>>>(kp, sa); }
+      ScanArgs sa;
+      sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = b->d_submit; sa.acc = p->d_acc;
+      sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = sub_len; sa.sub = c;
+      { const char *dbg = getenv("IAMFB_SCAN_DEBUG"); sa.debug = dbg ? atoi(dbg) : 0; }
+      {
+        ScopedKernelTimer tm_(ctx, "k_limiter_scan", scan_st);
+        if (scan_smem) k_limiter_scan<true><<<(S + 31) / 32, kScanThreads, scan_smem, scan_st>>>(kp, sa);
+        else k_limiter_scan<false><<<(S + 31) / 32, kScanThreads, 0, scan_st>>>(kp, sa);
+      }
+      LAUNCH_CHECK("k_limiter_scan");
+      if (n_sub > 1) {
+        CU(cudaEventRecord(ctx->ev_s[c], scan_st));
+        if (c > 0) {   // quantise the previous sub-chunk while this one is being scanned
+          CU(cudaStreamWaitEvent(st, ctx->ev_s[c - 1], 0));
+          int r = output(c - 1, (sub_frame[c] - sub_frame[c - 1]) * N);
+          if (r) return r;
+        }
+      }
     }
-    LAUNCH_CHECK("k_limiter_scan");
-  }
-  {
-    OutputArgs o;
-    o.tl = b->d_tl_b; o.gn = kp.limiter ? b->d_gn : nullptr; o.submit = b->d_submit; o.pcm = pcm;
-    o.stride_bytes = stride; o.cap = b->cap_b; o.hist = kp.hist;
-    { ScopedKernelTimer tm_(ctx, "k_output"); k_output<<<dim3((max_out + 255) / 256, S), 256, 0, st>>>(kp, o); }
-    LAUNCH_CHECK("k_output");
-  }
-  if (kp.limiter && !flush) {
-    CarryArgs c;
-    c.tl = b->d_tl_b; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_b; c.hist = kLimDelay; c.use_in_len = 0;
-    { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
-    LAUNCH_CHECK("k_carry");
-    c.tl = b->d_pk; c.rows = 1;
-    { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(1, S), 256, 0, st>>>(c); }
-    LAUNCH_CHECK("k_carry");
+    if (n_sub > 1) {
+      CU(cudaStreamWaitEvent(st, ctx->ev_s[n_sub - 1], 0));
+      int r = output(n_sub - 1, (sub_frame[n_sub] - sub_frame[n_sub - 1]) * N);
+      if (r) return r;
+    } else {
+      int r = output(0, max_out);
+      if (r) return r;
+    }
+    if (!flush) {
+      CarryArgs c;
+      c.tl = b->d_tl_b; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_b; c.hist = kLimDelay; c.use_in_len = 0;
+      { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
+      LAUNCH_CHECK("k_carry");
+      c.tl = b->d_pk; c.rows = 1;
+      { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(1, S), 256, 0, st>>>(c); }
+      LAUNCH_CHECK("k_carry");
+    }
+  } else {
+    int r = output(0, max_out);
+    if (r) return r;
   }
   return IAMFB_OK;
 }

@@ -72,6 +72,8 @@ struct ResolveArgs {
   const float *qf_table;              // 256 entries: (float)(q / 255.0)  (fixedp11_5.c:53-55)
   int n_streams, n_frames;
   int flush;                          // end-of-stream pass: no frames, 240 limiter zeros (+ resampler tail)
+  int n_sub;                          // sub-chunks of this submit
+  int sub_frame[kMaxSub + 1];         // frame index where each sub-chunk starts (sub_frame[n_sub] == n_frames)
 };
 
 __device__ __forceinline__ long long rs_outputs_until(const KernelPlan &p, long long in_total) {
@@ -93,8 +95,11 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelP
   long long rs_out0 = st.rs_out_total;
   int pad_at_start = st.lim_pad;
   int lim_in_total = 0;
+  SubmitRec sr;
+  int sub = 0;
 
   for (int f = 0; f < a.n_frames; ++f) {
+    while (sub <= a.n_sub && a.sub_frame[sub] == f) sr.sub_off[sub++] = lim_in_total;
     const iamfb_frame_params fp = a.params[(size_t)s * a.n_frames + f];
     FrameRec fr;
     for (int e = 0; e < plan.n_elements; ++e) {
@@ -204,7 +209,6 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelP
     if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = cnt;
   }
 
-  SubmitRec sr;
   sr.in_len = t_off;
   sr.rs_out_first = rs_out0;
   if (a.flush) {
@@ -233,6 +237,8 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelP
     if (a.out_counts) a.out_counts[s] = cnt;
   }
   sr.lim_len = lim_in_total;
+  for (; sub <= kMaxSub; ++sub) sr.sub_off[sub] = lim_in_total;
+  if (a.flush) sr.sub_off[0] = 0;
   sr.out_skip = pad_at_start - st.lim_pad;
   sr.out_len = lim_in_total - sr.out_skip;
   st.rs_out_total = rs_out0 + (plan.resample ? (long long)lim_in_total - (a.flush && plan.limiter ? kLimDelay : 0) : 0);
@@ -255,7 +261,8 @@ struct RenderArgs {
   float *tl;                // destination time line [S][C_out][cap]
   float *pk;                // [S][cap] or nullptr
   int cap, hist;            // row stride and history offset of tl / pk
-  int n_frames, e;          // element index
+  int n_frames, e;          // frames per stream in this submit, element index
+  int f_lo, nf;             // this launch covers frames [f_lo, f_lo + nf)
   int first, last;          // first element writes, later ones accumulate; the last applies output gain/loudness/peak
   int tiles_per_frame;
 };
@@ -265,34 +272,39 @@ struct Vec {
   float v[VEC];
 };
 
-template <int VEC>
+// SMEM: the source is a shared-memory tile staged by bulk async copies (k_render_bulk), else global memory
+template <int VEC, bool SMEM>
 __device__ __forceinline__ Vec<VEC> load_row(const float *p, bool vec_ok, int valid) {
   Vec<VEC> r;
   if constexpr (VEC == 4) {
     if (vec_ok) {
-      float4 t = ldg_stream4(p);
+      float4 t;
+      if constexpr (SMEM) t = *reinterpret_cast<const float4 *>(p);
+      else t = ldg_stream4(p);
       r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
       return r;
     }
   }
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) r.v[k] = k < valid ? ldg_stream1(p + k) : 0.f;
+  for (int k = 0; k < VEC; ++k) {
+    if constexpr (SMEM) r.v[k] = k < valid ? p[k] : 0.f;
+    else r.v[k] = k < valid ? ldg_stream1(p + k) : 0.f;
+  }
   return r;
 }
 
 // Channel-based reconstruction of the VEC samples held by this thread: fills v[IAChannel][k].
 // Follows dmx_gainup, dmx_s2..dmx_h4 and dmx_rms of demixer.c (skip == 0: codec delay is 0 on this path).
-template <int VEC>
-__device__ __forceinline__ void reconstruct_channels(const ElPlan &ep, const ElFrame &ef, const float *in_frame, int N,
-                                                     int i0, bool vec_ok, int valid, const float *start_win,
-                                                     const float *stop_win, int overlap, Vec<VEC> (&v)[kChCount]) {
+template <int VEC, bool SMEM>
+__device__ __forceinline__ void reconstruct_channels(const ElPlan &ep, const ElFrame &ef, const float *src, int row_stride,
+                                                     bool vec_ok, int valid, Vec<VEC> (&v)[kChCount]) {
   // transmitted channels -> IAChannel slots (static register indices, uniform predicates).  All loads are issued
   // before the first use so that a thread has its whole input (n_in x 16 B) in flight at once.
 #pragma unroll
   for (int c = 1; c < kChCount; ++c) {
     int row = ep.src_row[c];
     if (row >= 0) {
-      v[c] = load_row<VEC>(in_frame + (size_t)row * N + i0, vec_ok, valid);
+      v[c] = load_row<VEC, SMEM>(src + (size_t)row * row_stride, vec_ok, valid);
     } else {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) v[c].v[k] = 0.f;
@@ -397,14 +409,12 @@ __device__ __forceinline__ Vec<VEC> pick_channel(const Vec<VEC> (&v)[kChCount], 
 
 // LAYOUT >= 0: channel based element with that reconstructed layout (x[m] gathered with static indices);
 // LAYOUT == -1: scene based element (NREC = ambisonics channel count).
-template <int LAYOUT, int NREC, int VEC>
-__global__ void __launch_bounds__(128) k_render(const __grid_constant__ KernelPlan plan, RenderArgs a) {
+// One thread's share of the work: VEC samples starting at frame offset i0 of (stream s, frame index sf).
+// src points at the thread's first sample of decoded row 0, rows are row_stride floats apart.
+template <int LAYOUT, int NREC, int VEC, bool SMEM>
+__device__ __forceinline__ void render_thread(const KernelPlan &plan, const RenderArgs &a, int s, int sf, int i0,
+                                              const float *src, int row_stride) {
   const int N = plan.frame_size;
-  const int tile = blockIdx.x % a.tiles_per_frame;
-  const int sf = blockIdx.x / a.tiles_per_frame;          // s * F + f
-  const int s = sf / a.n_frames;
-  const int i0 = (tile * 128 + threadIdx.x) * VEC;         // first sample of this thread inside the frame
-  if (i0 >= N) return;
   const FrameRec &fr = a.frames[sf];
   const int vstart = fr.vstart, vlen = fr.vlen;
   if (vlen <= 0) return;
@@ -415,13 +425,12 @@ __global__ void __launch_bounds__(128) k_render(const __grid_constant__ KernelPl
   const ElFrame &ef = fr.el[a.e];
   const int valid = min(VEC, N - i0);
   const bool vec_ok = (VEC == 4) && ((N & 3) == 0) && valid == VEC;
-  const float *in_frame = a.in + (size_t)sf * ep.n_in * N;
 
   Vec<VEC> x[NREC];   // channels entering the renderer, in renderer order
   Vec<VEC> v[(LAYOUT >= 0) ? kChCount : 1];
 
   if constexpr (LAYOUT >= 0) {
-    reconstruct_channels<VEC>(ep, ef, in_frame, N, i0, vec_ok, valid, a.start_win, a.stop_win, plan.overlap, v);
+    reconstruct_channels<VEC, SMEM>(ep, ef, src, row_stride, vec_ok, valid, v);
     // dmx_rms cross-fade, demixer.c:461-468: x *= last*stop[i] + cur*start[i]
     constexpr unsigned char kOrder[9][12] = {
         {13}, {14, 15}, {1, 2, 3, 4, 20, 21}, {1, 2, 3, 4, 20, 21, 22, 23}, {1, 2, 3, 4, 20, 21, 9, 10, 11, 12},
@@ -452,14 +461,14 @@ __global__ void __launch_bounds__(128) k_render(const __grid_constant__ KernelPl
     // scene based: mono mapping is a row permutation, projection an ordered mat-vec (IAMF_core_decoder.c:105-130)
     if (ep.ambi_mode == 0) {
 #pragma unroll
-      for (int m = 0; m < NREC; ++m) x[m] = load_row<VEC>(in_frame + (size_t)ep.ambi_map[m] * N + i0, vec_ok, valid);
+      for (int m = 0; m < NREC; ++m) x[m] = load_row<VEC, SMEM>(src + (size_t)ep.ambi_map[m] * row_stride, vec_ok, valid);
     } else {
 #pragma unroll
       for (int m = 0; m < NREC; ++m)
 #pragma unroll
         for (int k = 0; k < VEC; ++k) x[m].v[k] = .0f;
       for (int l = 0; l < ep.ambi_cols; ++l) {
-        Vec<VEC> t = load_row<VEC>(in_frame + (size_t)l * N + i0, vec_ok, valid);
+        Vec<VEC> t = load_row<VEC, SMEM>(src + (size_t)l * row_stride, vec_ok, valid);
 #pragma unroll
         for (int m = 0; m < NREC; ++m) {
           float c = ep.ambi_mat[l * NREC + m];
@@ -562,6 +571,107 @@ __global__ void __launch_bounds__(128) k_render(const __grid_constant__ KernelPl
       for (int k = 0; k < VEC; ++k)
         if ((i0 + k) >= lo && (i0 + k) < hi) pd[k] = peak.v[k];
     }
+  }
+}
+
+// direct variant: every thread reads its samples straight from global memory (any frame size)
+template <int LAYOUT, int NREC, int VEC>
+__global__ void __launch_bounds__(128, 4) k_render(const __grid_constant__ KernelPlan plan, RenderArgs a) {
+  const int N = plan.frame_size;
+  const int tile = blockIdx.x % a.tiles_per_frame;
+  const int sfl = blockIdx.x / a.tiles_per_frame;
+  const int s = sfl / a.nf;
+  const int sf = s * a.n_frames + a.f_lo + sfl % a.nf;    // s * F + f
+  const int i0 = (tile * 128 + threadIdx.x) * VEC;         // first sample of this thread inside the frame
+  if (i0 >= N) return;
+  const float *src = a.in + (size_t)sf * plan.el[a.e].n_in * N + i0;
+  render_thread<LAYOUT, NREC, VEC, false>(plan, a, s, sf, i0, src, N);
+}
+
+// ---- bulk-copy (TMA) staged variant ---------------------------------------------------------------------------------
+// Persistent CTAs walk the (stream, frame, 512-sample tile) list.  One elected thread issues cp.async.bulk copies of
+// the tile's n_in rows (2 KB each) into a ring of shared-memory stages guarded by mbarriers; the 128 compute threads
+// wait for a stage, read their float4 per channel from shared memory (conflict free) and run the same arithmetic.
+// The copy engine keeps kRenderStages tiles in flight per CTA independent of register pressure.
+constexpr int kRenderStages = 3;
+constexpr int kRenderTile = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int LAYOUT, int NREC>
+__global__ void __launch_bounds__(128, 3) k_render_bulk(const __grid_constant__ KernelPlan plan, RenderArgs a, int n_tiles_total) {
+  extern __shared__ __align__(128) float s_stage[];            // [kRenderStages][n_in][kRenderTile]
+  __shared__ __align__(8) uint64_t s_full[kRenderStages];
+  const int N = plan.frame_size;
+  const int n_in = plan.el[a.e].n_in;
+  const int stage_floats = n_in * kRenderTile;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < kRenderStages; ++i) mbar_init(&s_full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int tile_id, int stage) {
+    // tile_id -> (stream, frame, tile inside the frame)
+    const int tile = tile_id % a.tiles_per_frame;
+    const int sfl = tile_id / a.tiles_per_frame;
+    const int s = sfl / a.nf;
+    const int sf = s * a.n_frames + a.f_lo + sfl % a.nf;
+    const int t0 = tile * kRenderTile;
+    const int len = min(kRenderTile, N - t0);
+    const float *g = a.in + (size_t)sf * n_in * N + t0;
+    float *d = s_stage + (size_t)stage * stage_floats;
+    mbar_expect_tx(&s_full[stage], (uint32_t)(n_in * len * sizeof(float)));
+    for (int r = 0; r < n_in; ++r) bulk_g2s(d + r * kRenderTile, g + (size_t)r * N, (uint32_t)(len * sizeof(float)), &s_full[stage]);
+  };
+
+  const int first = blockIdx.x, stride = gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRenderStages; ++i)
+      if (first + i * stride < n_tiles_total) issue(first + i * stride, i);
+  }
+  int it = 0;
+  for (int tile_id = first; tile_id < n_tiles_total; tile_id += stride, ++it) {
+    const int stage = it % kRenderStages;
+    const uint32_t parity = (it / kRenderStages) & 1;
+    mbar_wait(&s_full[stage], parity);
+    const int tile = tile_id % a.tiles_per_frame;
+    const int sfl = tile_id / a.tiles_per_frame;
+    const int s = sfl / a.nf;
+    const int sf = s * a.n_frames + a.f_lo + sfl % a.nf;
+    const int i0 = tile * kRenderTile + threadIdx.x * 4;
+    if (i0 < N) {
+      const float *src = s_stage + (size_t)stage * stage_floats + threadIdx.x * 4;
+      render_thread<LAYOUT, NREC, 4, true>(plan, a, s, sf, i0, src, kRenderTile);
+    }
+    __syncthreads();                                            // everyone is done reading this stage
+    const int next = tile_id + kRenderStages * stride;
+    if (threadIdx.x == 0 && next < n_tiles_total) issue(next, stage);
   }
 }
 
@@ -671,6 +781,7 @@ struct WmaxArgs {
   const SubmitRec *submit;
   int cap, hist;
   int flush;
+  int sub;             // sub-chunk processed by this launch
 };
 
 constexpr int kWmTile = 1024;
@@ -679,8 +790,8 @@ __global__ void __launch_bounds__(256) k_window_max(const __grid_constant__ Kern
   __shared__ float sa[kWmTile + kLimDelay + 16];
   __shared__ float sb[kWmTile + kLimDelay + 16];
   const int s = blockIdx.y;
-  const int len = a.submit[s].lim_len;
-  const int k0 = blockIdx.x * kWmTile;
+  const int len = a.submit[s].sub_off[a.sub + 1];          // instants [sub_off[sub], sub_off[sub+1]) of this submit
+  const int k0 = a.submit[s].sub_off[a.sub] + blockIdx.x * kWmTile;
   if (k0 >= len) return;
   const float *row = a.pk + (size_t)s * a.cap + a.hist;   // row[k] = pk of instant k of this submit
   const int span = kWmTile + kLimDelay;                    // instants k0-240 .. k0+1023
@@ -738,111 +849,170 @@ struct ScanArgs {
   const float *acc;     // [jr + 1]
   int cap, hist, n_streams;
   int max_len;
+  int sub;              // sub-chunk processed by this launch
+  int debug;            // profiling aid: 1 = scanner skips the serial walk (results wrong), 0 = normal
 };
 
-// One warp per block (32 streams); the acceleration curve is staged in shared memory when it fits (ACC_SMEM).
+// Warp-specialised block of 16 warps per 32 streams:
+//   warp 0 ("scanner")  one lane per stream, runs ONLY the serial recurrence over 32x32 tiles held in shared memory;
+//   warps 1-15 ("movers") stream the tiles: coalesced global loads of the sliding-max values one tile ahead (held in
+//                        registers across the barrier), thr/peak (IEEE division, :259) and the per-stream tile maximum
+//                        computed on the way into shared memory, and the coalesced write-back of the gains one tile
+//                        behind.  The tiles are double buffered, one __syncthreads per tile.
 // The serial loop is branch-free and keeps every memory access off the dependent chain:
 //   * both the attack and the release candidate are formed every step and selected;
 //   * the curve values for the next two steps (acc[j+1], acc[j+2]) live in registers and acc[j+3] is fetched two steps
 //     ahead (after a trigger the indices restart at 1, 2 - constants);
-//   * peak and thr/peak (needed only when a trigger fires, IEEE division precomputed for the whole tile in the parallel
-//     load phase) are fetched together with one 64-bit shared load.
-// Dependent chain per sample: sub, mul, add, select, mul, compare, select.
+//   * peak and thr/peak are fetched together with one 64-bit shared load.
+// Tiles in which a lane is idle and below threshold cost it nothing; a tile where that holds for all 32 lanes is
+// answered without the walk.
 constexpr int kScanAccSmem = 50 * 1024;   // floats of the curve kept in shared memory (200 KB, opt-in dynamic smem)
+constexpr int kScanThreads = 512;      // 1 scanner warp + 15 mover warps
+constexpr int kScanMovers = kScanThreads / 32 - 1;
 
 template <bool ACC_SMEM>
-__global__ void __launch_bounds__(32) k_limiter_scan(const __grid_constant__ KernelPlan plan, ScanArgs a) {
-  __shared__ float2 t_in[32][33];   // {peak, thr/peak}
-  __shared__ float t_g[32][33];
+__global__ void __launch_bounds__(kScanThreads) k_limiter_scan(const __grid_constant__ KernelPlan plan, ScanArgs a) {
+  __shared__ float2 t_in[2][32][33];   // {peak, thr/peak}
+  __shared__ float t_g[2][32][33];
+  __shared__ float t_max[2][32];
+  __shared__ int s_lo[32], s_len[32];
   extern __shared__ float s_acc[];
-  const int lane = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s0 = blockIdx.x * 32;
-  const int s = s0 + lane;
-  const bool live = s < a.n_streams;
   const int ja = plan.lim_ja, jr = plan.lim_jr;
-  // table has jr + 4 entries (zero padded) so that j+3 never runs off the end
-  if (ACC_SMEM) {
-    for (int i = lane; i < jr + 4; i += 32) s_acc[i] = a.acc[i];
-    __syncwarp();
-  }
-  auto acc_at = [&](int i) -> float { return ACC_SMEM ? s_acc[i] : __ldg(a.acc + i); };
-  int len = live ? a.submit[s].lim_len : 0;
-  int j = -1;
-  float start = -1.f, end = -1.f;
-  if (live) { j = a.state[s].lim_j; start = a.state[s].lim_start; end = a.state[s].lim_end; }
-  if (j > jr) j = jr;
   const float thr = plan.lim_thr;
-  const float a1 = acc_at(1), a2 = acc_at(2);
-  int max_len = len;
+  if (ACC_SMEM)
+    for (int i = threadIdx.x; i < jr + 4; i += kScanThreads) s_acc[i] = a.acc[i];   // jr + 4 entries, zero padded
+  if (warp == 0) {
+    const int s = s0 + lane;
+    const bool live = s < a.n_streams;
+    const int lo = live ? a.submit[s].sub_off[a.sub] : 0;
+    s_lo[lane] = lo;
+    s_len[lane] = live ? a.submit[s].sub_off[a.sub + 1] - lo : 0;
+  }
+  __syncthreads();
+  int max_len = s_len[lane];
 #pragma unroll
   for (int o = 16; o; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+  const int n_tiles = (max_len + 31) / 32;
+  auto acc_at = [&](int i) -> float { return ACC_SMEM ? s_acc[i] : __ldg(a.acc + i); };
 
-  // software pipeline: the 32 row loads of tile k0+32 are issued before the serial walk over tile k0 and land while
-  // it runs (one DRAM latency per tile instead of one per row)
-  float nxt[32];
-  int lens[32];
-#pragma unroll
-  for (int r = 0; r < 32; ++r) lens[r] = __shfl_sync(0xffffffffu, len, r);
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    int sr = s0 + r;
-    nxt[r] = (sr < a.n_streams && lane < lens[r]) ? a.wm[(size_t)sr * a.cap + a.hist + lane] : 0.f;
+  // scanner state
+  int j = -1, len = 0;
+  float start = -1.f, end = -1.f, a1 = 0.f, a2 = 0.f;
+  if (warp == 0) {
+    const int s = s0 + lane;
+    len = s_len[lane];
+    if (s < a.n_streams) { j = a.state[s].lim_j; start = a.state[s].lim_start; end = a.state[s].lim_end; }
+    if (j > jr) j = jr;
+    a1 = acc_at(1);
+    a2 = acc_at(2);
   }
-  for (int k0 = 0; k0 < max_len; k0 += 32) {
-    // publish the prefetched tile; thr/peak for the whole tile (IEEE division, :259)
-    float tmax_part = 0.f;
+  // mover state: rows r = warp-1, warp-1+15, ... (3 or 2 rows per mover warp), column = lane
+  constexpr int kRowsPerMover = (32 + kScanMovers - 1) / kScanMovers;
+  float pre[kRowsPerMover];
+  auto mover_load = [&](int t) {
 #pragma unroll
-    for (int r = 0; r < 32; ++r) t_in[r][lane] = make_float2(nxt[r], thr / nxt[r]);
-    __syncwarp();
-    if (k0 + 32 < max_len) {
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        int sr = s0 + r;
-        int k = k0 + 32 + lane;
-        nxt[r] = (sr < a.n_streams && k < lens[r]) ? a.wm[(size_t)sr * a.cap + a.hist + k] : 0.f;
-      }
+    for (int q = 0; q < kRowsPerMover; ++q) {
+      const int r = (warp - 1) + kScanMovers * q;
+      const int k = t * 32 + lane;
+      pre[q] = (r < 32 && s0 + r < a.n_streams && k < s_len[r])
+                   ? a.wm[(size_t)(s0 + r) * a.cap + a.hist + s_lo[r] + k] : 0.f;
     }
-    float tmax = tmax_part;
+  };
+  if (warp > 0 && n_tiles > 0) mover_load(0);
+
+  for (int t = 0; t < n_tiles + 2; ++t) {
+    if (warp > 0) {
+      if (t < n_tiles) {
+        // publish tile t (loaded last iteration), then start the loads of tile t+1
+        const int b = t & 1;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, t_in[lane][i].x);
-    const bool idle = (j < 0 || j >= jr);
-    const bool quiet = idle && !(tmax * 1.0f > thr);
-    if (!__all_sync(0xffffffffu, quiet)) {
-      const int nk = min(32, len - k0);
-      const int jc = min(max(j, 0), jr);
-      float p1 = acc_at(jc + 1), p2 = acc_at(jc + 2);
+        for (int q = 0; q < kRowsPerMover; ++q) {
+          const int r = (warp - 1) + kScanMovers * q;
+          const float v = pre[q];
+          const float e = thr / v;
+          // the scanner only needs to know whether ANY instant of the row's tile can cross the threshold at gain 1
+          const bool hot = __any_sync(0xffffffffu, v * 1.0f > thr);
+          if (r < 32) {
+            t_in[b][r][lane] = make_float2(v, e);
+            if (lane == 0) t_max[b][r] = hot ? 1.0f : 0.0f;
+          }
+        }
+        if (t + 1 < n_tiles) mover_load(t + 1);
+      }
+      if (t >= 2) {
+        // write back the gains of tile t-2
+        const int b = t & 1;
+#pragma unroll
+        for (int q = 0; q < kRowsPerMover; ++q) {
+          const int r = (warp - 1) + kScanMovers * q;
+          const int k = (t - 2) * 32 + lane;
+          if (r < 32 && s0 + r < a.n_streams && k < s_len[r])
+            a.gn[(size_t)(s0 + r) * a.cap + a.hist + s_lo[r] + k] = t_g[b][r][lane];
+        }
+      }
+    } else if (t >= 1 && t <= n_tiles) {
+      const int b = (t - 1) & 1;
+      const int k0 = (t - 1) * 32;
+      const bool idle = (j < 0 || j >= jr);
+      const bool quiet = idle && t_max[b][lane] == 0.0f;
+      if (!__all_sync(0xffffffffu, quiet) && a.debug != 1) {
+        const int nk = min(32, len - k0);
+        // Speculative form of compute_target_gain (:237-265).  cont(m) = the gain m steps ahead if no trigger fires
+        // until then; it only depends on the state at the last trigger (start S, end E, D = S-E, R = 1-E) and on the
+        // time index, so it is formed ahead of time.  Each step computes the candidates for "a trigger fires now"
+        // (index restarts: curve values a1..a3 are constants) next to them and selects - the dependent chain per
+        // sample is g -> g-e -> a1*(g-e) -> g-(..) -> select.
+        float S = start, E = end, D = start - end, R = 1.0f - end;
+        auto cont = [&](int jpre, float p) -> float {   // gain of the step whose pre-increment index is jpre
+          const float ga = S - p * D;
+          const float gr = E + p * R;
+          return (jpre >= 0 && jpre < jr) ? (jpre < ja ? ga : gr) : 1.0f;
+        };
+        const int jc = min(max(j, 0), jr);
+        float g = cont(j, acc_at(min(jc + 1, jr + 3)));                              // gain of the coming step
+        float n1 = cont(j < 0 ? j : j + 1, acc_at(min(jc + 2, jr + 3)));             // one step later, no trigger
+        float n2 = cont(j < 0 ? j : j + 2, acc_at(min(jc + 3, jr + 3)));             // two steps later, no triggers
+        float pq = acc_at(min(jc + 4, jr + 3));                                      // curve value for index j+4
+        const float a3 = acc_at(3), a4 = acc_at(4 < jr + 3 ? 4 : jr + 3);
+        // j is the pre-increment index of the coming step; saturate so that j+4 stays inside the padded table
 #pragma unroll 8
-      for (int i = 0; i < nk; ++i) {
-        const float2 in = t_in[lane][i];
-        const float p3 = acc_at(min(max(j, 0), jr) + 3);   // lands two steps from now
-        const bool active = (j >= 0) && (j < jr);
-        const bool attack = active && (j < ja);
-        const float ga = start - p1 * (start - end);
-        const float gr = end + p1 * (1.0f - end);
-        const float g = active ? (attack ? ga : gr) : 1.0f;
-        const int jn = active ? j + 1 : j;
-        const bool trig = in.x * g > thr;
-        start = trig ? g : start;
-        end = trig ? in.y : end;
-        j = trig ? 0 : jn;
-        p1 = trig ? a1 : p2;
-        p2 = trig ? a2 : p3;
-        t_g[lane][i] = g;
+        for (int i = 0; i < nk; ++i) {
+          const float2 in = t_in[b][lane][i];
+          const int jl = min(max(j, 0), jr);
+          const float pl = acc_at(min(jl + 5, jr + 3));       // used next iteration (if no trigger fires now)
+          const bool trig = in.x * g > thr;
+          const float d = g - in.y;
+          const float c1 = g - a1 * d, c2 = g - a2 * d, c3 = g - a3 * d;
+          // no-trigger continuation three steps ahead (pre-increment index j+3), from the current trigger state
+          const float n3 = cont(j < 0 ? j : j + 3, pq);
+          t_g[b][lane][i] = g;
+          // state after this step
+          S = trig ? g : S;
+          E = trig ? in.y : E;
+          D = trig ? d : D;
+          R = trig ? (1.0f - in.y) : R;
+          const bool active = (j >= 0) && (j < jr);
+          j = trig ? 0 : (active ? j + 1 : j);
+          g = trig ? c1 : n1;
+          n1 = trig ? c2 : n2;
+          n2 = trig ? c3 : n3;
+          pq = trig ? a4 : pl;
+        }
+        start = S;
+        end = E;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t_g[b][lane][i] = 1.0f;
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) t_g[lane][i] = 1.0f;
     }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      int sr = s0 + r;
-      int k = k0 + lane;
-      if (sr < a.n_streams && k < lens[r]) a.gn[(size_t)sr * a.cap + a.hist + k] = t_g[r][lane];
-    }
-    __syncwarp();
+    __syncthreads();
   }
-  if (live) { a.state[s].lim_j = j; a.state[s].lim_start = start; a.state[s].lim_end = end; }
+  if (warp == 0 && s0 + lane < a.n_streams) {
+    const int s = s0 + lane;
+    a.state[s].lim_j = j; a.state[s].lim_start = start; a.state[s].lim_end = end;
+  }
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -858,6 +1028,7 @@ struct OutputArgs {
   void *pcm;
   size_t stride_bytes; // per stream
   int cap, hist;
+  int sub;             // sub-chunk processed by this launch
 };
 
 __device__ __forceinline__ int quant16(float x) {
@@ -879,40 +1050,84 @@ __device__ __forceinline__ int quant32(float x) {
   return (int)__float2ll_rn(x);
 }
 
+// thread = 4 consecutive output samples of one stream (all channels): 16-byte loads along time per channel, and the
+// 4 x C_out quantised values of a thread form one contiguous byte range of the interleaved output, written with the
+// widest aligned stores available.
+template <int BITS>
+__device__ __forceinline__ void store_sample(char *out, size_t idx, float x) {
+  if (BITS == 16) {
+    ((int16_t *)out)[idx] = (int16_t)quant16(x);
+  } else if (BITS == 24) {
+    int v = quant24(x);
+    unsigned char *p = (unsigned char *)out + idx * 3;
+    p[0] = v & 0xff;
+    p[1] = (v >> 8) & 0xff;
+    p[2] = ((v >> 16) & 0x7f) | ((v >> 24) & 0x80);
+  } else if (BITS == 32) {
+    ((int32_t *)out)[idx] = quant32(x);
+  } else {
+    ((float *)out)[idx] = x;
+  }
+}
+
+template <int BITS>
 __global__ void __launch_bounds__(256) k_output(const __grid_constant__ KernelPlan plan, OutputArgs a) {
   const int s = blockIdx.y;
   const SubmitRec sr = a.submit[s];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // limiter instant of this submit
-  if (k >= sr.lim_len || k < sr.out_skip) return;
-  const int o = k - sr.out_skip;                         // output sample index
+  const int lo = sr.sub_off[a.sub], hi = sr.sub_off[a.sub + 1];
+  // instants are grouped in fours aligned on the time line (so that the float4 loads are aligned)
+  const int k4 = ((lo >> 2) + blockIdx.x * blockDim.x + threadIdx.x) << 2;
+  if (k4 >= hi) return;
   const int co = plan.out_channels;
   const int delay = plan.limiter ? kLimDelay : 0;
-  const float g = a.gn ? a.gn[(size_t)s * a.cap + a.hist + k] : 1.f;
-  const float *base = a.tl + (size_t)s * co * a.cap + a.hist + k - delay;
+  const int kbeg = max(max(k4, lo), sr.out_skip), kend = min(k4 + 4, hi);
+  if (kbeg >= kend) return;
   char *out = (char *)a.pcm + (size_t)s * a.stride_bytes;
-  for (int c0 = 0; c0 < co; c0 += 8) {
-    float xs[8];
+  const bool full = (kbeg == k4) && (kend == k4 + 4) && ((a.cap & 3) == 0) && (((a.hist - delay) & 3) == 0);
+  float g[4] = {1.f, 1.f, 1.f, 1.f};
+  if (a.gn) {
+    const float *gp = a.gn + (size_t)s * a.cap + a.hist + k4;
+    if (full && ((a.hist & 3) == 0)) {
+      float4 t = *reinterpret_cast<const float4 *>(gp);
+      g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+    } else {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) xs[u] = (c0 + u < co) ? base[(size_t)(c0 + u) * a.cap] : 0.f;   // 8 loads in flight
+      for (int u = 0; u < 4; ++u) if (k4 + u >= kbeg && k4 + u < kend) g[u] = gp[u];
+    }
+  }
+  const float *base = a.tl + (size_t)s * co * a.cap + a.hist + k4 - delay;
+  const size_t o0 = (size_t)(k4 - sr.out_skip);   // output sample index of instant k4
+  if (full && BITS == 16 && (co & 1) == 0 && (((o0 * co) & 1) == 0)) {
+    // fast path: channel pairs packed into 32-bit words
+    for (int c = 0; c < co; c += 2) {
+      const float4 x0 = *reinterpret_cast<const float4 *>(base + (size_t)c * a.cap);
+      const float4 x1 = *reinterpret_cast<const float4 *>(base + (size_t)(c + 1) * a.cap);
+      const float v0[4] = {x0.x, x0.y, x0.z, x0.w}, v1[4] = {x1.x, x1.y, x1.z, x1.w};
+      uint32_t *w = (uint32_t *)((int16_t *)out + o0 * co + c);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = c0 + u;
-      if (c >= co) break;
-      float x = xs[u];
-      if (a.gn) x = x * g;
-      if (plan.bit_depth == 16) {
-        ((int16_t *)out)[(size_t)o * co + c] = (int16_t)quant16(x);
-      } else if (plan.bit_depth == 24) {
-        int v = quant24(x);
-        unsigned char *p = (unsigned char *)out + ((size_t)o * co + c) * 3;
-        p[0] = v & 0xff;
-        p[1] = (v >> 8) & 0xff;
-        p[2] = ((v >> 16) & 0x7f) | ((v >> 24) & 0x80);
-      } else if (plan.bit_depth == 32) {
-        ((int32_t *)out)[(size_t)o * co + c] = quant32(x);
-      } else {
-        ((float *)out)[(size_t)o * co + c] = x;
+      for (int u = 0; u < 4; ++u) {
+        float y0 = v0[u], y1 = v1[u];
+        if (a.gn) { y0 = y0 * g[u]; y1 = y1 * g[u]; }
+        w[(size_t)u * (co >> 1)] = (uint32_t)(quant16(y0) & 0xffff) | ((uint32_t)quant16(y1) << 16);
       }
+    }
+    return;
+  }
+  for (int c = 0; c < co; ++c) {
+    float v[4];
+    if (full) {
+      const float4 x = *reinterpret_cast<const float4 *>(base + (size_t)c * a.cap);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (k4 + u >= kbeg && k4 + u < kend) ? base[(size_t)c * a.cap + u] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k4 + u < kbeg || k4 + u >= kend) continue;
+      float x = v[u];
+      if (a.gn) x = x * g[u];
+      store_sample<BITS>(out, (o0 + u) * co + c, x);
     }
   }
 }

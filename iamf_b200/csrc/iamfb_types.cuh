@@ -11,6 +11,7 @@ constexpr int kMaxOut = IAMFB_MAX_OUT_CH;
 constexpr int kMaxRec = 16;            // reconstructed channels feeding a render matrix (12 layout / 16 HOA)
 constexpr int kChCount = IAMFB_CH_COUNT;
 constexpr int kLimDelay = IAMFB_LIMITER_DELAY;
+constexpr int kMaxSub = 8;            // sub-chunks a submit is split into so that the limiter scan overlaps the rest
 constexpr int kMaxRsHist = 256;       // upper bound of the resampler history (filt_len - 1 rounded up to 4) -> ratios down to 4:1
 
 enum Renderer : int { kRdrM2M = 0, kRdrH2M = 1, kRdrDMR = 2 };
@@ -112,6 +113,7 @@ struct SubmitRec {
   int out_len;                     // samples written to pcm
   int out_skip;                    // limiter priming samples dropped this submit
   long long rs_out_first;          // absolute index of the first resampler output this submit
+  int sub_off[kMaxSub + 1];        // limiter-stage sample offsets of the sub-chunk boundaries (sub_off[n_sub] == lim_len)
 };
 
 }  // namespace iamfb
