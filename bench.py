@@ -189,7 +189,7 @@ def run_gpu(args):
     import torch.distributed as dist
     import scenarios as S
     import refstreams
-    from iamf_b200 import Engine
+    from iac_b200 import Engine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,7 +299,7 @@ def run_gpu(args):
     h_pcm = torch.zeros((S_, stride_e), dtype=torch.uint8).pin_memory()
     h_counts = torch.zeros((S_, Fe), dtype=torch.int32).pin_memory()
     import ctypes as C
-    from iamf_b200.binding import Io, _check
+    from iac_b200.binding import Io, _check
     io = Io()
     for e, x in enumerate(h_in):
         io.in_[e] = x.data_ptr()

@@ -72,13 +72,13 @@ _lib = None
 
 
 def lib():
-    """loads iamf_b200/libiamf_b200.so; raises if it was not built (python -m iamf_b200.build)"""
+    """loads iac_b200/libiamf_b200.so; raises if it was not built (python -m iac_b200.build)"""
     global _lib
     if _lib is not None:
         return _lib
     path = lib_path()
     if not os.path.exists(path):
-        raise IamfB200Error(f"{path} is missing: build it with `python -m iamf_b200.build` (nvcc, sm_100a). "
+        raise IamfB200Error(f"{path} is missing: build it with `python -m iac_b200.build` (nvcc, sm_100a). "
                             "There is no CPU fallback.")
     L = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
     vp = C.c_void_p

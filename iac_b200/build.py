@@ -1,6 +1,6 @@
-"""Builds the in-tree native libraries of iamf_b200 (nvcc, sm_100a only; cross-compiles without a GPU).
+"""Builds the in-tree native libraries of iac_b200 (nvcc, sm_100a only; cross-compiles without a GPU).
 
-    python -m iamf_b200.build            # build everything that is stale
+    python -m iac_b200.build            # build everything that is stale
 """
 import os
 import subprocess
@@ -32,7 +32,7 @@ def build_cuda(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
         "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", LIB, os.path.join(CSRC, "iamfb_api.cu")]
-    print("[iamf_b200.build]", " ".join(cmd), file=sys.stderr)
+    print("[iac_b200.build]", " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
     return LIB
 

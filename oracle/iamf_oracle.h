@@ -1,7 +1,7 @@
 /*
  * iamf_oracle.h - CPU restatement of libiamf's post-decode rendering path.
  *
- * TEST INFRASTRUCTURE ONLY.  Nothing under iamf_b200/ (the product) may include, link or dlopen anything in
+ * TEST INFRASTRUCTURE ONLY.  Nothing under iac_b200/ (the product) may include, link or dlopen anything in
  * oracle/.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, and
  * only as the checker.
  *

@@ -3,7 +3,7 @@ counts and the concatenated PCM bytes in the same form scenarios.run_oracle() re
 import numpy as np
 
 import scenarios as S
-from iamf_b200 import Engine
+from iac_b200 import Engine
 
 
 def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0):

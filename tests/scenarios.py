@@ -165,7 +165,7 @@ def synth_inputs(sc: Scenario, n_streams: int, n_frames: int, seed: int = 0x1A3F
 
 def synth_params(sc: Scenario, n_streams: int, n_frames: int, seed: int = 0x77):
     """iamfb_frame_params as a numpy structured array + the animated gain ramps (or None)"""
-    from iamf_b200.binding import frame_params_array
+    from iac_b200.binding import frame_params_array
     P = frame_params_array(n_streams, n_frames)
     rng = np.random.default_rng(seed)
     for e, el in enumerate(sc.elements):
@@ -206,7 +206,7 @@ def synth_params(sc: Scenario, n_streams: int, n_frames: int, seed: int = 0x77):
 # product plan descriptor
 # --------------------------------------------------------------------------------------------------------------------
 def plan_desc(sc: Scenario):
-    from iamf_b200.binding import PlanDesc, channel_element, scene_element
+    from iac_b200.binding import PlanDesc, channel_element, scene_element
     d = PlanDesc()
     d.frame_size, d.in_rate, d.out_rate = sc.frame_size, sc.in_rate, sc.out_rate
     d.n_elements = len(sc.elements)
@@ -229,7 +229,7 @@ def plan_desc(sc: Scenario):
 # --------------------------------------------------------------------------------------------------------------------
 def _orc_cfg(sc: Scenario, keep):
     import orcbind
-    from iamf_b200.binding import get_h2m_matrix, get_m2m_matrix
+    from iac_b200.binding import get_h2m_matrix, get_m2m_matrix
     cfg = orcbind.StreamCfg()
     cfg.frame_size, cfg.in_rate, cfg.out_rate = sc.frame_size, sc.in_rate, sc.out_rate
     cfg.n_elements = len(sc.elements)

@@ -8,8 +8,8 @@ import re
 import numpy as np
 import pytest
 
-import iamf_b200
-from iamf_b200 import binding
+import iac_b200
+from iac_b200 import binding
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 
@@ -20,7 +20,7 @@ def declared_symbols():
 
 
 def test_library_exports_every_declared_symbol():
-    L = iamf_b200.lib()
+    L = iac_b200.lib()
     syms = declared_symbols()
     assert len(syms) >= 25
     for s in syms:
@@ -36,7 +36,7 @@ def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    L = iamf_b200.lib()
+    L = iac_b200.lib()
     ctx = C.c_void_p()
     r = L.iamfb_ctx_create(0, C.byref(ctx))
     assert r == -100  # IAMFB_ERR_NO_DEVICE
@@ -44,7 +44,7 @@ def test_no_cpu_fallback():
 
 
 def test_matrix_table_pinned():
-    inc = os.path.join(ROOT, "iamf_b200", "csrc", "iamfb_matrices.inc")
+    inc = os.path.join(ROOT, "iac_b200", "csrc", "iamfb_matrices.inc")
     assert hashlib.sha256(open(inc, "rb").read()).hexdigest() == \
         "4e1f0997a441b5140698b8de718be00e8a03331e556402dca49a0ecc796797dc"
 
@@ -74,5 +74,5 @@ def test_matrices_equal_reference():
 
 
 def test_target_channel_counts():
-    L = iamf_b200.lib()
+    L = iac_b200.lib()
     assert [L.iamfb_target_channels(t) for t in range(14)] == [2, 6, 8, 10, 11, 12, 14, 24, 8, 12, 10, 6, 1, 2]
