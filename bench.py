@@ -48,73 +48,89 @@ def alg_bytes_per_audio_second(sc):
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU leg: the reference's own implementation on host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    cfg, streams, n_frames, kind, seed, barrier_path, n_workers, idx = args
+CPU_DISTINCT = 2      # distinct synthetic streams per worker (bounds host memory: ~20 MB per worker on c2)
+CPU_RENDERS = 16      # stream renders per worker per step (the distinct streams are cycled)
+
+
+def _cpu_worker(cfg, kind, n_frames, idx, reps, barrier, q):
+    """one worker = one host core.  Set-up (synthesis, bitstream packing) happens once and untimed; every rep renders
+    CPU_RENDERS whole streams start to finish through the reference's public API between two barriers."""
     import refbind
     import refstreams
     import scenarios as S
-    sc, st, api_kw, unit_kw = refstreams.case(cfg)
-    n = len(streams)
-    inputs = S.synth_inputs(sc, n, n_frames, seed=seed + 1000 * idx)
-    P, ramps, oramp = S.synth_params(sc, n, n_frames, seed=seed + idx)
-    refstreams.no_param_gaps(sc, P)
-    out_samples = 0
-    if kind == "reference":
-        import iamfapi
-        api = iamfapi.Api(refbind.REF_SO)
-        desc = st.descriptors()
-        units = [refstreams.temporal_units(sc, st, inputs, P, unit_kw, s) for s in range(n)]
-        # crude cross-process barrier through the file system so that all workers time the same interval
-        open(f"{barrier_path}.{idx}", "w").close()
-        while sum(os.path.exists(f"{barrier_path}.{i}") for i in range(n_workers)) < n_workers:
-            time.sleep(0.001)
-        t0 = time.monotonic()
-        for s in range(n):
-            pcm, counts = api.render(desc, units[s], **api_kw)
-            out_samples += pcm.shape[0]
-        t1 = time.monotonic()
-    else:
-        open(f"{barrier_path}.{idx}", "w").close()
-        while sum(os.path.exists(f"{barrier_path}.{i}") for i in range(n_workers)) < n_workers:
-            time.sleep(0.001)
-        t0 = time.monotonic()
-        res = S.run_oracle(sc, inputs, P, ramps, oramp)
-        t1 = time.monotonic()
+    try:
+        sc, st, api_kw, unit_kw = refstreams.case(cfg)
+        n = CPU_DISTINCT
+        inputs = S.synth_inputs(sc, n, n_frames, seed=0x1A3F + 1000 * idx)
+        P, ramps, oramp = S.synth_params(sc, n, n_frames, seed=0x77 + idx)
+        refstreams.no_param_gaps(sc, P)
         bps = sc.bit_depth // 8 if sc.bit_depth else 4
-        out_samples = sum(len(r[1]) // (bps * sc.out_channels) for r in res.values())
-    return t0, t1, out_samples / float(sc.out_rate)
+        if kind == "reference":
+            import iamfapi
+            api = iamfapi.Api(refbind.REF_SO)
+            desc = st.descriptors()
+            units = [refstreams.temporal_units(sc, st, inputs, P, unit_kw, s) for s in range(n)]
+        out = []
+        for _ in range(reps):
+            samples = 0
+            barrier.wait()
+            t0 = time.monotonic()
+            for r in range(CPU_RENDERS):
+                s = r % n
+                if kind == "reference":
+                    pcm, counts = api.render(desc, units[s], **api_kw)
+                    samples += pcm.shape[0]
+                else:
+                    res = S.run_oracle(sc, [x[s:s + 1] for x in inputs], P[s:s + 1],
+                                       [g[s:s + 1] for g in ramps] if ramps else None,
+                                       oramp[s:s + 1] if oramp is not None else None)
+                    samples += len(res[0][1]) // (bps * sc.out_channels)
+            t1 = time.monotonic()
+            out.append((t0, t1, samples / float(sc.out_rate)))
+        q.put((idx, out))
+    except Exception as e:  # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        q.put((idx, repr(e)))
 
 
-def cpu_reference(cfg, n_streams, n_frames, seed=0):
-    """times the reference CPU implementation over n_streams x n_frames on all host cores.
-    returns dict(value audio-s/s, cores, kind, sample, seconds)"""
+def cpu_reference(cfg, n_frames, reps=1, warm=0):
+    """times the reference CPU implementation of the path on ALL host cores: one process per core, each rendering
+    CPU_RENDERS streams x n_frames frames per rep.  Returns dict(value audio-s/s (mean over reps), per_rep, cores,
+    kind, sample, seconds)."""
     import multiprocessing as mp
-    import tempfile
     import refbind
     kind = "reference" if refbind.have_ref() else "port"
-    if kind == "port":
-        import orcbind
-        orcbind.lib()   # make sure liboracle.so exists before forking
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, n_streams))
-    chunks = [list(range(i, n_streams, workers)) for i in range(workers)]
-    bdir = tempfile.mkdtemp(prefix="iamfb_bar_")
-    bpath = os.path.join(bdir, "ready")
+    import orcbind
+    orcbind.lib()   # make sure liboracle.so exists before the workers start (refstreams uses its scalar helpers)
+    workers = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     ctx = mp.get_context("spawn")
-    with ctx.Pool(workers) as pool:
-        res = pool.map(_cpu_worker, [(cfg, chunks[i], n_frames, kind, seed, bpath, workers, i) for i in range(workers)])
-    t0 = min(r[0] for r in res)
-    t1 = max(r[1] for r in res)
-    audio = sum(r[2] for r in res)
-    for i in range(workers):
-        try:
-            os.remove(f"{bpath}.{i}")
-        except OSError:
-            pass
-    return dict(value=audio / (t1 - t0), unit="audio-s/s", cores=workers, kind=kind,
-                sample=f"{n_streams} streams x {n_frames} frames of the same workload, public-API decode calls only"
-                if kind == "reference" else f"{n_streams} streams x {n_frames} frames, C port of the path (oracle/)",
-                seconds=t1 - t0)
+    barrier = ctx.Barrier(workers)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(cfg, kind, n_frames, i, warm + reps, barrier, q), daemon=True)
+             for i in range(workers)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in range(workers)]
+    for p in procs:
+        p.join(timeout=30)
+    bad = [r for r in res if isinstance(r[1], str)]
+    if bad:
+        raise RuntimeError(f"cpu reference worker failed: {bad[0][1]}")
+    vals, secs = [], []
+    for k in range(warm, warm + reps):
+        t0 = min(r[1][k][0] for r in res)
+        t1 = max(r[1][k][1] for r in res)
+        audio = sum(r[1][k][2] for r in res)
+        vals.append(audio / (t1 - t0))
+        secs.append(t1 - t0)
+    what = (f"{workers} processes (one per host core) x {CPU_RENDERS} streams x {n_frames} frames of the same workload per step, "
+            + ("unmodified reference decoder (oracle/_ref) through IAMF_decoder_configure/decode on ipcm-coded streams"
+               if kind == "reference" else "C port of the path (oracle/)"))
+    return dict(value=float(np.mean(vals)), unit="audio-s/s", cores=workers, kind=kind, sample=what,
+                seconds=float(np.mean(secs)), per_rep=vals)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -191,9 +207,8 @@ def run_gpu(args):
     import refstreams
     from iac_b200 import Engine
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from iac_b200 import shard
+    rank, world, local = shard.rank_world()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -206,8 +221,8 @@ def run_gpu(args):
     # CPU baseline first (rank 0, N=1 only), before the GPU is busy
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
-        cores = os.cpu_count() or 1
-        cpu = cpu_reference(cfg, n_streams=8 * max(cores, 8), n_frames=args.cpu_frames)
+        cpu = cpu_reference(cfg, n_frames=args.cpu_frames, reps=1, warm=1)
+        cpu.pop("per_rep", None)
 
     stream = torch.cuda.current_stream()
     eng = Engine(S.plan_desc(sc), S_, F, device=local, cuda_stream=stream.cuda_stream)
@@ -246,14 +261,8 @@ def run_gpu(args):
     sampler.join(timeout=2)
     # samples produced in one steady-state step (all streams of this rank)
     out_per_step = int(d_counts.sum().item())
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    tot = torch.tensor([float(out_per_step)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
-    audio_per_step = float(tot.item()) / sc.out_rate
-    value = audio_per_step * args.steps / (ms_max / 1e3)
+    ms_max, out_total = shard.aggregate(ms, out_per_step, device=dev)     # MAX of device time, SUM of samples
+    value = shard.job_throughput(ms_max, out_total, sc.out_rate, steps=args.steps)
 
     if args.quick:
         if rank == 0:
@@ -320,12 +329,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
     te = time.perf_counter() - t0
     out_e = float(h_counts.sum().item())
-    te_t = torch.tensor([te], device=dev, dtype=torch.float64)
-    oe_t = torch.tensor([out_e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(oe_t, op=dist.ReduceOp.SUM)
-    e2e_value = float(oe_t.item()) / sc.out_rate * ke / float(te_t.item())
+    te_max_ms, oe_total = shard.aggregate(te * 1e3, out_e, device=dev)
+    e2e_value = shard.job_throughput(te_max_ms, oe_total, sc.out_rate, steps=ke)
     h2d = sum(x.numel() * 4 for x in h_in) + h_params.nbytes
     d2h = S_ * stride_e + h_counts.numel() * 4
 
@@ -354,28 +359,21 @@ def run_gpu(args):
 
 
 def run_reference(args):
+    """the reference's own CPU implementation of the path on all host cores (oracle/_ref when it was compiled,
+    else our C port); rank 0 only under torchrun"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import refstreams
     cfg = args.config
-    sc, _, _, _ = refstreams.case(cfg)
-    cores = os.cpu_count() or 1
-    n_streams = max(cores, 8) * 16
-    vals, secs = [], []
-    res = None
-    for i in range(args.warmup + args.steps):
-        res = cpu_reference(cfg, n_streams=n_streams, n_frames=args.cpu_frames, seed=i)
-        if i >= args.warmup:
-            vals.append(res["value"])
-            secs.append(res["seconds"])
-    value = float(np.mean(vals))
+    res = cpu_reference(cfg, n_frames=args.cpu_frames, reps=max(1, args.steps), warm=max(0, args.warmup))
+    value = res["value"]
     line = {
         "impl": "reference", "metric": "rendered audio-sec/sec", "value": value, "unit": "audio-s/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg}: {CONFIGS[cfg]['desc']}", "sample_streams": n_streams, "sample_frames": args.cpu_frames},
+        "config": {"workload": f"{cfg}: {CONFIGS[cfg]['desc']}", "sample_streams_per_step": res["cores"] * CPU_RENDERS,
+                   "sample_frames": args.cpu_frames},
         "cpu_baseline": dict(value=value, unit="audio-s/s", cores=res["cores"], kind=res["kind"], sample=res["sample"]),
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -393,7 +391,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--e2e-frames", type=int, default=4)
-    ap.add_argument("--cpu-frames", type=int, default=500)
+    ap.add_argument("--cpu-frames", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (used under ncu)")
     args = ap.parse_args()
