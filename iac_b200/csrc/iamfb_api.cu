@@ -11,6 +11,7 @@
 
 #include "iamf_b200.h"
 #include "iamfb_kernels.cuh"
+#include "iamfb_fused.cuh"
 #include "iamfb_matrices.inc"
 
 using namespace iamfb;
@@ -156,6 +157,10 @@ struct iamfb_plan {
   float *d_acc;                      // limiter acceleration curve by time index
   // initial per-stream state (host copy)
   StreamState init_state;
+  // fused single-kernel path (non-resampling pipelines whose element signature is instantiated)
+  bool fused;
+  int fused_tile;          // samples per tile
+  size_t fused_smem;       // dynamic shared memory per block
 };
 
 struct iamfb_batch {
@@ -167,6 +172,7 @@ struct iamfb_batch {
   FrameRec *d_frames;
   SubmitRec *d_submit;
   float *d_tl_a, *d_tl_b, *d_pk, *d_wm, *d_gn;
+  float *d_hist_y, *d_hist_pk;   // fused path: limiter delay line / peak ring carried between submits
   // staging for the host-resident path
   float *d_in[kMaxEl];
   float *d_ramp[kMaxEl];
@@ -633,6 +639,54 @@ static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &t
   } else {
     return fail(IAMFB_ERR_BAD_ARG, "element %d: unknown kind %d", e, ed.kind);
   }
+  // column-compressed copy of the render matrix, by OUTPUT CHANNEL (out_slot applied), zeros dropped
+  if (ep.renderer != kRdrDMR) {
+    int q = 0;
+    for (int m = 0; m < ep.n_rec; ++m) {
+      ep.csc_ptr[m] = (unsigned short)q;
+      for (int oc = 0; oc < co; ++oc) {
+        const int n = ep.out_slot[oc];
+        if (n < 0) continue;
+        const float c = ep.mat[n * ep.n_rec + m];
+        if (c != 0.f) { ep.csc_row[q] = (unsigned char)oc; ep.csc_val[q] = c; ++q; }
+      }
+    }
+    for (int m = ep.n_rec; m <= kMaxRec; ++m) ep.csc_ptr[m] = (unsigned short)q;
+  }
+  return IAMFB_OK;
+}
+
+// element-signature combinations the fused kernel is instantiated for: every single-element pipeline, and the
+// two-element pairs of the named configurations (7.1.4 + first-order ambisonics in either order); anything else
+// runs on the multi-kernel path
+static int fused_variant(const int *tmpl, int n_elements) {
+  if (n_elements == 1) return tmpl[0];
+  if (n_elements == 2 && tmpl[0] == 7 && tmpl[1] == 11) return 100;
+  if (n_elements == 2 && tmpl[0] == 11 && tmpl[1] == 7) return 101;
+  return -1;
+}
+
+static int launch_fused(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa, int S) {
+  const KernelPlan &kp = p->kp;
+  cudaStream_t st = ctx->stream;
+  const size_t smem = p->fused_smem;
+#define FCASE(ID, L0, N0, L1, N1)                                                                                   \
+  case ID: {                                                                                                        \
+    CU(cudaFuncSetAttribute(k_fused<L0, N0, L1, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    ScopedKernelTimer tm_(ctx, "k_fused");                                                                          \
+    k_fused<L0, N0, L1, N1><<<S, kFusedThreads, smem, st>>>(kp, fa);                                               \
+  } break;
+  switch (fused_variant(p->tmpl, kp.n_elements)) {
+    FCASE(0, 0, 1, 0, 0) FCASE(1, 1, 2, 0, 0) FCASE(2, 2, 6, 0, 0) FCASE(3, 3, 8, 0, 0) FCASE(4, 4, 10, 0, 0)
+    FCASE(5, 5, 8, 0, 0) FCASE(6, 6, 10, 0, 0) FCASE(7, 7, 12, 0, 0) FCASE(8, 8, 6, 0, 0)
+    FCASE(10, -1, 1, 0, 0) FCASE(11, -1, 4, 0, 0) FCASE(12, -1, 9, 0, 0) FCASE(13, -1, 16, 0, 0)
+    FCASE(100, 7, 12, -1, 4) FCASE(101, -1, 4, 7, 12)
+    default: return fail(IAMFB_ERR_INTERNAL, "no fused kernel variant");
+  }
+#undef FCASE
+  cudaError_t e_ = cudaGetLastError();
+  if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_fused failed: %s", cudaGetErrorString(e_));
+  ++ctx->launches;
   return IAMFB_OK;
 }
 
@@ -702,6 +756,34 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
     int r = upload(&p->d_acc, acc.data(), acc.size());
     if (r) { delete p; return r; }
   }
+  p->fused = false;
+  {
+    const char *env = getenv("IAMFB_FUSED");
+    const bool want = !env || atoi(env) != 0;
+    bool eligible = want && !kp.resample && (kp.frame_size & 3) == 0 && fused_variant(p->tmpl, kp.n_elements) >= 0;
+    int nin = 0;
+    for (int e = 0; e < kp.n_elements; ++e) {
+      nin += kp.el[e].n_in;
+      if (kp.el[e].renderer == kRdrDMR) eligible = false;          // the parametric down-mixer stays on the multi-kernel path
+    }
+    if (eligible) {
+      const int co = kp.out_channels, H = kp.limiter ? kLimDelay : 0;
+      const int two = kp.n_elements > 1 ? 1 : 0;
+      const int budget = 14080;                                   // floats: 55 KB per block -> 4 blocks per SM
+      int tl_max = (budget - 16 - 2 * kWmPad - (co + 1) * H) / (nin + co * (1 + two) + 6);
+      if (tl_max > 1024) tl_max = 1024;
+      tl_max &= ~3;
+      if (tl_max >= 64) {
+        const int n_tiles = (kp.frame_size + tl_max - 1) / tl_max;
+        int tl = (kp.frame_size + n_tiles - 1) / n_tiles;
+        tl = (tl + 3) & ~3;
+        p->fused = true;
+        p->fused_tile = tl;
+        p->fused_smem = sizeof(float) * ((size_t)nin * tl + (size_t)co * (H + tl) + (size_t)two * co * tl + (H + tl + 16) +
+                                         3 * (size_t)tl + 2 * ((size_t)tl + kWmPad));
+      }
+    }
+  }
   *out = p;
   return IAMFB_OK;
 }
@@ -744,7 +826,11 @@ extern "C" int iamfb_batch_reset(iamfb_batch *b) {
   CU(cudaMemcpyAsync(b->d_state, init.data(), sizeof(StreamState) * b->S, cudaMemcpyHostToDevice, p->ctx->stream));
   const int co = p->kp.out_channels;
   if (b->d_tl_a) CU(cudaMemsetAsync(b->d_tl_a, 0, sizeof(float) * (size_t)b->S * co * b->cap_a, p->ctx->stream));
-  CU(cudaMemsetAsync(b->d_tl_b, 0, sizeof(float) * (size_t)b->S * co * b->cap_b, p->ctx->stream));
+  if (b->d_tl_b) CU(cudaMemsetAsync(b->d_tl_b, 0, sizeof(float) * (size_t)b->S * co * b->cap_b, p->ctx->stream));
+  if (b->d_hist_y) {
+    CU(cudaMemsetAsync(b->d_hist_y, 0, sizeof(float) * (size_t)b->S * co * kLimDelay, p->ctx->stream));
+    CU(cudaMemsetAsync(b->d_hist_pk, 0, sizeof(float) * (size_t)b->S * kLimDelay, p->ctx->stream));
+  }
   if (b->d_pk) {
     CU(cudaMemsetAsync(b->d_pk, 0, sizeof(float) * (size_t)b->S * b->cap_b, p->ctx->stream));
     CU(cudaMemsetAsync(b->d_wm, 0, sizeof(float) * (size_t)b->S * b->cap_b, p->ctx->stream));
@@ -773,8 +859,15 @@ extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, 
   alloc((void **)&b->d_frames, sizeof(FrameRec) * (size_t)n_streams * max_frames);
   alloc((void **)&b->d_submit, sizeof(SubmitRec) * n_streams);
   if (kp.resample) alloc((void **)&b->d_tl_a, sizeof(float) * (size_t)n_streams * co * b->cap_a);
-  alloc((void **)&b->d_tl_b, sizeof(float) * (size_t)n_streams * co * b->cap_b);
-  if (kp.limiter) {
+  if (p->fused) {
+    if (kp.limiter) {
+      alloc((void **)&b->d_hist_y, sizeof(float) * (size_t)n_streams * co * kLimDelay);
+      alloc((void **)&b->d_hist_pk, sizeof(float) * (size_t)n_streams * kLimDelay);
+    }
+  } else {
+    alloc((void **)&b->d_tl_b, sizeof(float) * (size_t)n_streams * co * b->cap_b);
+  }
+  if (kp.limiter && !p->fused) {
     alloc((void **)&b->d_pk, sizeof(float) * (size_t)n_streams * b->cap_b);
     alloc((void **)&b->d_wm, sizeof(float) * (size_t)n_streams * b->cap_b);
     alloc((void **)&b->d_gn, sizeof(float) * (size_t)n_streams * b->cap_b);
@@ -801,6 +894,7 @@ extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
   if (!b) return;
   cudaFree(b->d_state); cudaFree(b->d_frames); cudaFree(b->d_submit);
   cudaFree(b->d_tl_a); cudaFree(b->d_tl_b); cudaFree(b->d_pk); cudaFree(b->d_wm); cudaFree(b->d_gn);
+  cudaFree(b->d_hist_y); cudaFree(b->d_hist_pk);
   free_staging(b);
   delete b;
 }
@@ -894,6 +988,27 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     for (int c = 0; c <= kMaxSub; ++c) a.sub_frame[c] = sub_frame[c];
     { ScopedKernelTimer tm_(ctx, "k_resolve"); k_resolve<<<(S + 127) / 128, 128, 0, st>>>(kp, a); }
     LAUNCH_CHECK("k_resolve");
+  }
+  if (p->fused) {
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    if (!flush)
+      for (int e = 0; e < kp.n_elements; ++e) { fa.in[e] = io->in[e]; fa.gain_ramp[e] = io->gain_ramp[e]; }
+    fa.out_gain_ramp = flush ? nullptr : io->out_gain_ramp;
+    fa.frames = b->d_frames;
+    fa.start_win = p->d_start_win;
+    fa.stop_win = p->d_stop_win;
+    fa.submit = b->d_submit;
+    fa.state = b->d_state;
+    fa.acc = p->d_acc;
+    fa.hist_y = b->d_hist_y;
+    fa.hist_pk = b->d_hist_pk;
+    fa.pcm = pcm;
+    fa.stride_bytes = stride;
+    fa.n_frames = flush ? 0 : F;
+    fa.flush = flush ? 1 : 0;
+    fa.tile = p->fused_tile;
+    return launch_fused(ctx, p, fa, S);
   }
   float *tl_first = kp.resample ? b->d_tl_a : b->d_tl_b;
   const int cap_first = kp.resample ? b->cap_a : b->cap_b;

@@ -1,0 +1,674 @@
+// iamfb_fused.cuh - the fused per-stream kernel of the non-resampling pipelines.
+//
+// One thread block owns one stream for the whole submit and walks its frames tile by tile (a tile = up to `tile`
+// consecutive samples of one frame).  Per tile, everything between the decoded planar input and the interleaved
+// integer PCM stays on chip:
+//
+//   stage    the tile's decoded rows are brought into shared memory by bulk async copies (cp.async.bulk + mbarrier,
+//            the TMA engine), issued one tile AHEAD: the copy of tile t+1 runs under the limiter / output phases of t
+//   render   reconstruct + render + gains + element sum of ALL audio elements -> mixed samples in shared memory
+//            (Y ring: 240 delayed samples + the tile) and the per-instant cross-channel peak (PK ring).  Channel
+//            sources are read from the staged rows by (uniform) row index, so nothing is indexed dynamically in
+//            registers; channel->channel matrices are applied column by column from a compressed (zero-free) copy,
+//            accumulating in the thread's own shared-memory slots
+//   wmax     240-sample sliding maximum of PK: windows of 8 in registers, then 16..128 by doubling with 16-byte
+//            shared-memory accesses, 240 = two overlapping windows of 128                       (limiter look-ahead)
+//   scan     the limiter's serial gain recurrence, run by warp 0 as a hybrid of
+//              - a 32-wide parallel search for the next trigger while the gain follows its attack/release curve, and
+//              - a speculative serial burst while the limiter re-triggers on every sample
+//   output   delayed sample x gain -> quantise -> interleaved PCM, written straight from shared memory
+//
+// so HBM sees the algorithmic bytes only: the decoded input once and the PCM once (plus 240 samples of history per
+// channel and stream carried between submits).  Arithmetic is the reference's, expression by expression (see the
+// citations in iamfb_kernels.cuh); results are bit-identical to the multi-kernel path and to the oracle.
+#pragma once
+#include "iamfb_kernels.cuh"
+
+namespace iamfb {
+
+struct FusedArgs {
+  const float *in[kMaxEl];      // [S][F][n_in][N]
+  const FrameRec *frames;       // [S][F]
+  const float *gain_ramp[kMaxEl];
+  const float *out_gain_ramp;
+  const float *start_win, *stop_win;
+  const SubmitRec *submit;      // [S]
+  StreamState *state;           // [S]
+  const float *acc;             // limiter curve by time index (jr + 4 entries)
+  float *hist_y;                // [S][co][kLimDelay]  limiter delay line carried between submits
+  float *hist_pk;               // [S][kLimDelay]      peak ring carried between submits
+  void *pcm;
+  size_t stride_bytes;
+  int n_frames, flush, tile;
+};
+
+constexpr int kFusedThreads = 128;
+constexpr int kWmPad = 320;     // scratch beyond the tile: 240 history + 64 (widest doubling step) + 16
+
+typedef Vec<4> V4;
+
+__device__ __forceinline__ V4 lds4(const float *p) {
+  const float4 t = *reinterpret_cast<const float4 *>(p);
+  V4 r;
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  return r;
+}
+__device__ __forceinline__ void sts4(float *p, const V4 &a) {
+  *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+// the thread's four slots of a time-line row: 16-byte access when aligned, else per sample
+__device__ __forceinline__ void ring_st(float *p, const V4 &a, bool al, int k_lo, int k_hi) {
+  if (al) { sts4(p, a); return; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k >= k_lo && k < k_hi) p[k] = a.v[k];
+}
+
+__device__ __forceinline__ constexpr int fused_order(int layout, int m) {   // IAMF_utils.c:117-133
+  constexpr unsigned char kOrder[9][12] = {
+      {13}, {14, 15}, {1, 2, 3, 4, 20, 21}, {1, 2, 3, 4, 20, 21, 22, 23}, {1, 2, 3, 4, 20, 21, 9, 10, 11, 12},
+      {1, 2, 3, 4, 5, 6, 7, 8}, {1, 2, 3, 4, 5, 6, 7, 8, 22, 23}, {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12},
+      {18, 19, 3, 4, 16, 17}};
+  return kOrder[layout][m];
+}
+
+// Channel-based reconstruction (demixer.c:127-378,421-475) from the staged rows.  ine = first staged row of the
+// element at this thread's four samples, rows tl floats apart.  Fills x[m] = layout channel m after recon gain.
+template <int LAYOUT, int NREC>
+__device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const FusedArgs &a, const ElPlan &ep,
+                                                  const ElFrame &ef, const float *ine, int tl, int i0, V4 (&x)[NREC]) {
+  // a transmitted channel: its staged row (zero when absent), with the output gain of dmx_gainup (demixer.c:421-430)
+  auto tx = [&](int ch) -> V4 {
+    const int row = ep.src_row[ch];
+    V4 r;
+    if (row >= 0) {
+      r = lds4(ine + (size_t)row * tl);
+      if ((ep.gain_mask >> ch) & 1u) {
+        const float g = ep.gain[ch];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.v[k] *= g;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r.v[k] = 0.f;
+    }
+    return r;
+  };
+  const int mode = ef.mode & 7;
+  V4 dR2, dL3, dR3, dSL5, dSR5, dBL7, dBR7, dHL, dHR, dHBL, dHBR;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    dR2.v[k] = dL3.v[k] = dR3.v[k] = dSL5.v[k] = dSR5.v[k] = dBL7.v[k] = dBR7.v[k] = dHL.v[k] = dHR.v[k] = dHBL.v[k] = dHBR.v[k] = 0.f;
+  if (ep.need_s2) {   // R2 = 2*Mono - L2, demixer.c:136-138
+    const V4 mo = tx(IAMFB_CH_MONO), l2 = tx(IAMFB_CH_L2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dR2.v[k] = 2 * mo.v[k] - l2.v[k];
+  }
+  if (ep.need_s3) {   // L3 = L2 - 0.707*C evaluated in double, demixer.c:165-168
+    const V4 l2 = tx(IAMFB_CH_L2), r2 = ep.need_s2 ? dR2 : tx(IAMFB_CH_R2), cc = tx(IAMFB_CH_C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double c = (double)cc.v[k];
+      dL3.v[k] = (float)((double)l2.v[k] - 0.707 * c);
+      dR3.v[k] = (float)((double)r2.v[k] - 0.707 * c);
+    }
+  }
+  if (ep.need_s5) {   // Ls5 = (L3 - L5)/delta, demixer.c:213-218
+    const V4 l3 = ep.need_s3 ? dL3 : tx(IAMFB_CH_L3), r3 = ep.need_s3 ? dR3 : tx(IAMFB_CH_R3);
+    const V4 l5 = tx(IAMFB_CH_L5), r5 = tx(IAMFB_CH_R5);
+    const float d = c_mix_delta[mode];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      dSL5.v[k] = (l3.v[k] - l5.v[k]) / d;
+      dSR5.v[k] = (r3.v[k] - r5.v[k]) / d;
+    }
+  }
+  if (ep.need_s7) {   // Lb7 = (Ls5 - alpha*Lss7)/beta, demixer.c:262-269
+    const V4 sl5 = ep.need_s5 ? dSL5 : tx(IAMFB_CH_SL5), sr5 = ep.need_s5 ? dSR5 : tx(IAMFB_CH_SR5);
+    const V4 sl7 = tx(IAMFB_CH_SL7), sr7 = tx(IAMFB_CH_SR7);
+    const float al = c_mix_alpha[mode], be = c_mix_beta[mode];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      dBL7.v[k] = (sl5.v[k] - sl7.v[k] * al) / be;
+      dBR7.v[k] = (sr5.v[k] - sr7.v[k] * al) / be;
+    }
+  }
+  if (ep.need_h2) {   // Ltf2 = Ltf3 - delta*w*Ls5, demixer.c:318-323
+    const V4 sl5 = ep.need_s5 ? dSL5 : tx(IAMFB_CH_SL5), sr5 = ep.need_s5 ? dSR5 : tx(IAMFB_CH_SR5);
+    const V4 tl_ = tx(IAMFB_CH_TL), tr_ = tx(IAMFB_CH_TR);
+    const float dw = c_mix_delta[mode] * ef.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      dHL.v[k] = tl_.v[k] - dw * sl5.v[k];
+      dHR.v[k] = tr_.v[k] - dw * sr5.v[k];
+    }
+  }
+  if (ep.need_h4) {   // Ltb = (Ltf2 - Ltf4)/gamma, demixer.c:363-368
+    const V4 hl = ep.need_h2 ? dHL : tx(IAMFB_CH_HL), hr = ep.need_h2 ? dHR : tx(IAMFB_CH_HR);
+    const V4 hfl = tx(IAMFB_CH_HFL), hfr = tx(IAMFB_CH_HFR);
+    const float ga = c_mix_gamma[mode];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      dHBL.v[k] = (hl.v[k] - hfl.v[k]) / ga;
+      dHBR.v[k] = (hr.v[k] - hfr.v[k]) / ga;
+    }
+  }
+  // gather in layout order; a derived pair replaces the transmitted one exactly when its step ran
+#pragma unroll
+  for (int m = 0; m < NREC; ++m) {
+    const int ch = fused_order(LAYOUT, m);
+    bool der = false;
+    V4 dv;
+    switch (ch) {
+      case IAMFB_CH_R2: der = ep.need_s2; dv = dR2; break;
+      case IAMFB_CH_L3: der = ep.need_s3; dv = dL3; break;
+      case IAMFB_CH_R3: der = ep.need_s3; dv = dR3; break;
+      case IAMFB_CH_SL5: der = ep.need_s5; dv = dSL5; break;
+      case IAMFB_CH_SR5: der = ep.need_s5; dv = dSR5; break;
+      case IAMFB_CH_BL7: der = ep.need_s7; dv = dBL7; break;
+      case IAMFB_CH_BR7: der = ep.need_s7; dv = dBR7; break;
+      case IAMFB_CH_HL: der = ep.need_h2; dv = dHL; break;
+      case IAMFB_CH_HR: der = ep.need_h2; dv = dHR; break;
+      case IAMFB_CH_HBL: der = ep.need_h4; dv = dHBL; break;
+      case IAMFB_CH_HBR: der = ep.need_h4; dv = dHBR; break;
+      default: dv = dR2; break;
+    }
+    x[m] = der ? dv : tx(ch);
+    if ((ef.rmask >> m) & 1u) {   // dmx_rms cross-fade, demixer.c:461-468: x *= last*stop[i] + cur*start[i]
+      const float lastf = ef.rlast[m], cur = ef.rcur[m];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        float st = 0.f, sw = 1.f;
+        if (i < plan.overlap) { st = a.stop_win[i]; sw = a.start_win[i]; }
+        const float f = lastf * st + cur * sw;
+        x[m].v[k] *= f;
+      }
+    }
+  }
+}
+
+// One element's contribution for the 4 samples [i0, i0+4) of this thread.
+//   ine   staged rows of the element at the thread's samples (rows tl apart)
+//   yt    the thread's slots in the mixed time line (&Y[0][ring position of sample i0], rows rs apart)
+//   acc   the thread's slots in the per-element accumulator: yt itself for a single element, else a scratch [co][tl]
+//   al    yt/acc slots are 16-byte aligned and all four samples are valid
+template <int LAYOUT, int NREC>
+__device__ __forceinline__ void fused_element(const KernelPlan &plan, const FusedArgs &a, int e, const FrameRec &fr,
+                                              int sf, int i0, int lo, int hi, bool first, bool last, const float *ine,
+                                              int tl, float *yt, int rs, float *acc, int acc_rs, bool acc_al, float *pkt,
+                                              bool al) {
+  const int N = plan.frame_size;
+  const ElPlan &ep = plan.el[e];
+  const ElFrame &ef = fr.el[e];
+  const int co = plan.out_channels;
+  const int k_lo = lo - i0, k_hi = hi - i0;
+  V4 x[NREC];
+  if constexpr (LAYOUT >= 0) {
+    fused_reconstruct<LAYOUT, NREC>(plan, a, ep, ef, ine, tl, i0, x);
+  } else {
+    // scene based: mono mapping is a row permutation, projection an ordered mat-vec (IAMF_core_decoder.c:105-130)
+    if (ep.ambi_mode == 0) {
+#pragma unroll
+      for (int m = 0; m < NREC; ++m) x[m] = lds4(ine + (size_t)ep.ambi_map[m] * tl);
+    } else {
+#pragma unroll
+      for (int m = 0; m < NREC; ++m)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[m].v[k] = .0f;
+      for (int l = 0; l < ep.ambi_cols; ++l) {
+        const V4 t = lds4(ine + (size_t)l * tl);
+#pragma unroll
+        for (int m = 0; m < NREC; ++m) {
+          const float c = ep.ambi_mat[l * NREC + m];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) x[m].v[k] += t.v[k] * c;
+        }
+      }
+    }
+  }
+
+  // ---- render: out = 0; out += mat * in over inputs ascending (m2m_rdr.c:1820-1840, h2m_rdr.c:1103-1112)
+  if constexpr (LAYOUT >= 0) {
+    // sparse channel matrix, column by column, accumulating in the thread's own shared-memory slots
+    V4 z;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z.v[k] = 0.f;
+    // (when the slots are not a whole aligned quad only the samples inside [lo, hi) may be touched: the neighbours
+    // belong to the history in front of the tile or to the next row)
+    for (int oc = 0; oc < co; ++oc) ring_st(acc + (size_t)oc * acc_rs, z, acc_al, k_lo, k_hi);
+#pragma unroll
+    for (int m = 0; m < NREC; ++m) {
+      const int q1 = ep.csc_ptr[m + 1];
+      for (int q = ep.csc_ptr[m]; q < q1; ++q) {
+        const float c = ep.csc_val[q];
+        float *p = acc + (size_t)ep.csc_row[q] * acc_rs;
+        V4 y;
+        if (acc_al) y = lds4(p);
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) y.v[k] = (k >= k_lo && k < k_hi) ? p[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y.v[k] += c * x[m].v[k];
+        ring_st(p, y, acc_al, k_lo, k_hi);
+      }
+    }
+  }
+
+  const int vstart = fr.vstart;
+  const float *gr = a.gain_ramp[e], *ogr = a.out_gain_ramp;
+  V4 eg, og;
+  {
+    const bool eg_on = gr || (ef.gain != 1.f && ef.gain > 0.f);   // iamf_frame_gain, IAMF_decoder.c:1392
+    const bool og_on = ogr || (fr.out_gain != 1.f && fr.out_gain > 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = i0 + k - vstart;
+      const bool in_rng = k >= k_lo && k < k_hi;
+      eg.v[k] = (gr && in_rng) ? gr[(size_t)sf * N + j] : (eg_on ? ef.gain : 1.f);
+      og.v[k] = (ogr && in_rng) ? ogr[(size_t)sf * N + j] : (og_on ? fr.out_gain : 1.f);
+    }
+  }
+  const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
+  V4 peak;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) peak.v[k] = 0.f;
+
+  for (int oc = 0; oc < co; ++oc) {
+    V4 y;
+    if constexpr (LAYOUT >= 0) {
+      const float *p = acc + (size_t)oc * acc_rs;
+      if (acc_al) y = lds4(p);
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y.v[k] = (k >= k_lo && k < k_hi) ? p[k] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y.v[k] = 0.f;
+      const int n = ep.out_slot[oc];
+      if (n >= 0) {
+        const float *mrow = ep.mat + n * NREC;
+#pragma unroll
+        for (int m = 0; m < NREC; ++m) {
+          const float c = mrow[m];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) y.v[k] += c * x[m].v[k];   // adding c == 0 terms is exact: the sum starts at +0
+        }
+      }
+    }
+    // element mix gain, IAMF_decoder.c:1392-1405
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (gr || eg.v[k] != 1.f) y.v[k] *= eg.v[k];
+    float *dst = yt + (size_t)oc * rs;
+    // iamf_mixer_mix, IAMF_decoder.c:2719-2730: acc = 0; acc += e0; acc += e1
+    if (first) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y.v[k] = 0.f + y.v[k];
+    } else {
+      V4 p;
+      if (al) p = lds4(dst);
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p.v[k] = (k >= k_lo && k < k_hi) ? dst[k] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y.v[k] = p.v[k] + y.v[k];
+    }
+    if (last) {
+      // output mix gain (IAMF_decoder.c:3463-3469) then loudness (:3480-3484)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (ogr || og.v[k] != 1.f) y.v[k] *= og.v[k];
+        if (loud_on) y.v[k] *= plan.loud_gain;
+        peak.v[k] = fmaxf(peak.v[k], fabsf(y.v[k]));
+      }
+    }
+    ring_st(dst, y, al, k_lo, k_hi);
+  }
+  if (last && pkt) ring_st(pkt, peak, al, k_lo, k_hi);
+}
+
+// Limiter gain recurrence over the n instants of a tile, run by ONE warp with warp-uniform state (j, S, E).
+//   j: number of time-constant increments since the last trigger (pre-increment index of the coming step),
+//      j < 0 = never triggered, j >= jr = released (gain 1);  S, E = targetStartGain / targetEndGain.
+//   wm[k] = look-ahead peak of instant k, ew[k] = thr / wm[k] (IEEE division, :259), g[k] receives the gain.
+// compute_target_gain (audio_effect_peak_limiter.c:237-265): the gain of a step depends only on (S, E, j); a trigger
+// (peak * gain > thr) restarts the curve from the current gain.  While no trigger fires the next 32 steps are
+// evaluated in parallel, one per lane, and the first lane whose test fires is found with a ballot; right after a
+// trigger the limiter usually fires again on every sample (the attack curve has not yet reached thr/peak), and that
+// run is walked serially, eight samples at a time speculatively, with every lane holding the same values.
+__device__ __forceinline__ void fused_scan(const float *wm, const float *ew, float *g, int n, int &j, float &S, float &E,
+                                           const float *__restrict__ acc, int ja, int jr, float thr, int lane) {
+  const float a1 = __ldg(acc + 1);
+  int pos = 0;
+  while (pos < n) {
+    // ---- parallel search for the next trigger
+    const int k = pos + lane;
+    const bool valid = k < n;
+    const float p = valid ? wm[k] : 0.f;
+    const int jj = j < 0 ? -1 : min(j + lane, jr);
+    const bool active = jj >= 0 && jj < jr;
+    const float ac = active ? __ldg(acc + jj + 1) : 0.f;
+    const float ga = S - ac * (S - E);
+    const float gr = E + ac * (1.0f - E);
+    const float gk = active ? (jj < ja ? ga : gr) : 1.0f;
+    const bool trig = valid && (p * gk > thr);
+    const unsigned mask = __ballot_sync(0xffffffffu, trig);
+    if (mask == 0u) {
+      const int cnt = min(32, n - pos);
+      if (valid) g[k] = gk;
+      if (j >= 0) j = min(j + cnt, jr);
+      pos += cnt;
+      continue;
+    }
+    const int first = __ffs(mask) - 1;
+    if (lane <= first) g[k] = gk;
+    S = __shfl_sync(0xffffffffu, gk, first);
+    E = __shfl_sync(0xffffffffu, valid ? ew[k] : 0.f, first);
+    j = 0;
+    pos += first + 1;
+    // ---- serial burst: the step after a trigger has gain S - acc[1]*(S - E); while it triggers again the state is
+    // (S = that gain, E = thr/peak, j = 0) and the next step has the same form
+    while (pos < n) {
+      const int m = min(8, n - pos);
+      float gs[8], es[8];
+      bool ts[8];
+      float s = S, e = E;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int q = min(pos + i, n - 1);
+        const float pi = wm[q];
+        const float ei = ew[q];
+        const float gi = s - a1 * (s - e);
+        gs[i] = gi;
+        es[i] = ei;
+        ts[i] = pi * gi > thr;
+        s = gi;
+        e = ei;
+      }
+      int lead = 0;   // number of leading steps that all triggered
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lead += (lead == i && i < m && ts[i]) ? 1 : 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < lead) {
+          if (lane == 0) g[pos + i] = gs[i];
+          S = gs[i];
+          E = es[i];
+        }
+      pos += lead;
+      if (lead < m) {
+        // step pos did not trigger: its gain is the curve value one increment after the last trigger
+        const float gi = S - a1 * (S - E);
+        if (lane == 0) g[pos] = gi;
+        j = 1;
+        pos += 1;
+        break;
+      }
+    }
+  }
+}
+
+template <int L0, int N0, int L1, int N1>
+__global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
+  extern __shared__ __align__(128) float fsm[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_lim[4];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = plan.frame_size, co = plan.out_channels;
+  const int H = plan.limiter ? kLimDelay : 0;
+  const int TL = a.tile;
+  const int rs = H + TL;                        // row stride of the rings (multiple of 4)
+  const int nin0 = plan.el[0].n_in, nin1 = N1 > 0 ? plan.el[1].n_in : 0;
+  float *IN = fsm;                              // [nin0 + nin1][TL] staged decoded rows
+  float *Y = IN + (size_t)(nin0 + nin1) * TL;   // [co][rs] mixed time line: 240 delayed samples, then the tile
+  float *YE = Y + (size_t)co * rs;              // [co][TL] per-element accumulator (two-element plans only)
+  float *PK = YE + (N1 > 0 ? (size_t)co * TL : 0);   // [rs + 16]
+  float *WM = PK + rs + 16;                     // [TL]
+  float *EW = WM + TL;                          // [TL]
+  float *G = EW + TL;                           // [TL]
+  float *SA = G + TL;                           // [TL + kWmPad]
+  float *SB = SA + TL + kWmPad;                 // [TL + kWmPad]
+
+  const SubmitRec sr = a.submit[s];
+  int lj = -1;
+  float lS = -1.f, lE = -1.f;
+  if (plan.limiter) {
+    const StreamState &st = a.state[s];
+    lj = st.lim_j; lS = st.lim_start; lE = st.lim_end;
+    if (lj > plan.lim_jr) lj = plan.lim_jr;
+    for (int i = tid; i < co * H; i += kFusedThreads) Y[(size_t)(i / H) * rs + (i % H)] = a.hist_y[(size_t)s * co * H + i];
+    for (int i = tid; i < H; i += kFusedThreads) PK[i] = a.hist_pk[(size_t)s * H + i];
+    for (int i = tid; i < TL + 16; i += kFusedThreads) PK[H + i] = 0.f;
+    for (int i = tid; i < TL + kWmPad; i += kFusedThreads) { SA[i] = 0.f; SB[i] = 0.f; }
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- tile iterator over (frame, offset): only tiles with at least one sample left after trimming
+  const int n_frames = a.flush ? 0 : a.n_frames;
+  auto tile_range = [&](int f, int t_off, int &lo_t, int &hi_t) {
+    const FrameRec &fr = a.frames[s * a.n_frames + f];
+    const int vs = fr.vstart, vl = fr.vlen;
+    lo_t = max(t_off, vs);
+    hi_t = min(min(t_off + TL, N), vs + vl);
+  };
+  auto advance = [&](int &f, int &t_off) {      // next non-empty tile after (f, t_off); f == n_frames when done
+    for (;;) {
+      t_off += TL;
+      if (t_off >= N) { t_off = 0; ++f; }
+      if (f >= n_frames) return;
+      int lo_t, hi_t;
+      tile_range(f, t_off, lo_t, hi_t);
+      if (hi_t > lo_t) return;
+    }
+  };
+  auto issue = [&](int f, int t_off) {          // one thread: bulk copies of the tile's rows into IN
+    const int len = min(TL, N - t_off);
+    const uint32_t row_bytes = (uint32_t)(len * sizeof(float));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(nin0 + nin1));
+    const size_t sf = (size_t)s * a.n_frames + f;
+    const float *g0 = a.in[0] + sf * nin0 * N + t_off;
+    for (int r = 0; r < nin0; ++r) bulk_g2s(IN + (size_t)r * TL, g0 + (size_t)r * N, row_bytes, &s_bar);
+    if constexpr (N1 > 0) {
+      const float *g1 = a.in[1] + sf * nin1 * N + t_off;
+      for (int r = 0; r < nin1; ++r) bulk_g2s(IN + (size_t)(nin0 + r) * TL, g1 + (size_t)r * N, row_bytes, &s_bar);
+    }
+  };
+
+  char *out = (char *)a.pcm + (size_t)s * a.stride_bytes;
+  int lim_done = 0;                             // limiter-stage instants of this submit already processed
+  uint32_t parity = 0;
+  int f = 0, t_off = -TL;
+  if (n_frames > 0) {
+    f = 0; t_off = -TL;
+    advance(f, t_off);
+    if (f < n_frames && tid == 0) issue(f, t_off);
+  }
+  bool flush_pending = a.flush != 0;
+
+  while (f < n_frames || flush_pending) {
+    int n, lo_t = 0, hi_t = 0;
+    const int sf = s * a.n_frames + f;
+    if (flush_pending) {
+      // end of stream: the limiter is fed 240 zeros (iamf_delay_buffer_handle, IAMF_decoder.c:3250-3301)
+      n = min(kLimDelay - lim_done, TL);
+      for (int i = tid; i < n; i += kFusedThreads) {
+        for (int c = 0; c < co; ++c) Y[(size_t)c * rs + H + i] = 0.f;
+        PK[H + i] = 0.f;
+      }
+      if (lim_done + n >= kLimDelay) flush_pending = false;
+    } else {
+      tile_range(f, t_off, lo_t, hi_t);
+      n = hi_t - lo_t;
+      // ---------------------------------------------------------------- render
+      mbar_wait(&s_bar, parity);
+      parity ^= 1u;
+      const FrameRec &fr = a.frames[sf];
+      const bool tile_al = ((lo_t - t_off) & 3) == 0;     // ring slots of a thread start on a 16-byte boundary
+      const int t_end = min(t_off + TL, N);
+      for (int i0 = t_off + tid * 4; i0 < t_end; i0 += kFusedThreads * 4) {
+        const int lo = max(i0, lo_t), hi = min(i0 + 4, hi_t);
+        if (lo >= hi) continue;
+        const int q = i0 - t_off;                         // position inside the staged tile
+        const bool al = tile_al && lo == i0 && hi == i0 + 4;
+        float *yt = Y + H + (i0 - lo_t);
+        float *pkt = plan.limiter ? PK + H + (i0 - lo_t) : nullptr;
+        if constexpr (N1 == 0) {
+          fused_element<L0, N0>(plan, a, 0, fr, sf, i0, lo, hi, true, true, IN + q, TL, yt, rs, yt, rs, al, pkt, al);
+        } else {
+          fused_element<L0, N0>(plan, a, 0, fr, sf, i0, lo, hi, true, false, IN + q, TL, yt, rs, YE + q, TL, true, pkt, al);
+          fused_element<L1, N1>(plan, a, 1, fr, sf, i0, lo, hi, false, true, IN + (size_t)nin0 * TL + q, TL, yt, rs, YE + q,
+                                TL, true, pkt, al);
+        }
+      }
+    }
+    __syncthreads();
+    // the staged rows are consumed: start the copy of the next tile under the rest of this one
+    if (!a.flush) {
+      advance(f, t_off);
+      if (f < n_frames && tid == 0) issue(f, t_off);
+    }
+    bool apply_gain = false;
+    if (plan.limiter) {
+      // ---------------------------------------------------------------- sliding maximum over 240 instants
+      // ring index i <-> instant i - 240 relative to the tile; WM[k] = max(PK[k .. k+239]), k < n
+      const int span4 = (n + kLimDelay + 3) >> 2;            // 16-byte items covering the ring
+      for (int v = tid; v < span4; v += kFusedThreads) {     // windows of 8, in registers
+        const float4 A = *reinterpret_cast<const float4 *>(PK + 4 * v);
+        const float4 B = *reinterpret_cast<const float4 *>(PK + 4 * v + 4);
+        const float4 C = *reinterpret_cast<const float4 *>(PK + 4 * v + 8);
+        const float m47 = fmaxf(fmaxf(B.x, B.y), fmaxf(B.z, B.w));
+        const float s3 = A.w, s2 = fmaxf(A.z, s3), s1 = fmaxf(A.y, s2), s0 = fmaxf(A.x, s1);
+        const float p9 = fmaxf(C.x, C.y), p10 = fmaxf(p9, C.z);
+        *reinterpret_cast<float4 *>(SA + 4 * v) =
+            make_float4(fmaxf(s0, m47), fmaxf(fmaxf(s1, m47), C.x), fmaxf(fmaxf(s2, m47), p9), fmaxf(fmaxf(s3, m47), p10));
+      }
+      __syncthreads();
+      float *src = SA, *dst = SB;
+#pragma unroll
+      for (int d = 8; d <= 64; d <<= 1) {                    // windows of 16, 32, 64, 128
+        for (int v = tid; v < span4; v += kFusedThreads) {
+          const float4 A = *reinterpret_cast<const float4 *>(src + 4 * v);
+          const float4 B = *reinterpret_cast<const float4 *>(src + 4 * v + d);
+          *reinterpret_cast<float4 *>(dst + 4 * v) = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
+        }
+        __syncthreads();
+        float *t = src; src = dst; dst = t;
+      }
+      bool hot = false;
+      const float thr = plan.lim_thr;
+      for (int v = tid; 4 * v < n; v += kFusedThreads) {     // 240 = two overlapping windows of 128
+        const float4 A = *reinterpret_cast<const float4 *>(src + 4 * v);
+        const float4 B = *reinterpret_cast<const float4 *>(src + 4 * v + 112);
+        const float4 W = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
+        *reinterpret_cast<float4 *>(WM + 4 * v) = W;
+        *reinterpret_cast<float4 *>(EW + 4 * v) = make_float4(thr / W.x, thr / W.y, thr / W.z, thr / W.w);
+        const int left = n - 4 * v;
+        hot |= (W.x > thr) || (left > 1 && W.y > thr) || (left > 2 && W.z > thr) || (left > 3 && W.w > thr);
+      }
+      const int any_hot = __syncthreads_or(hot ? 1 : 0);
+      // ---------------------------------------------------------------- gain recurrence
+      const bool idle = lj < 0 || lj >= plan.lim_jr;         // block-uniform
+      if (any_hot || !idle) {
+        apply_gain = true;
+        if (warp == 0) {
+          fused_scan(WM, EW, G, n, lj, lS, lE, a.acc, plan.lim_ja, plan.lim_jr, thr, lane);
+          if (lane == 0) { s_lim[0] = lj; s_lim[1] = __float_as_int(lS); s_lim[2] = __float_as_int(lE); }
+        }
+        __syncthreads();
+        lj = s_lim[0]; lS = __int_as_float(s_lim[1]); lE = __int_as_float(s_lim[2]);
+      }
+    }
+    // ------------------------------------------------------------------ output: delayed sample x gain -> PCM
+    {
+      const long long base = (long long)lim_done - sr.out_skip;   // output index of instant 0 of this tile
+      const int bits = plan.bit_depth;
+      for (int k4 = tid * 4; k4 < n; k4 += kFusedThreads * 4) {
+        float g4[4] = {1.f, 1.f, 1.f, 1.f};
+        if (apply_gain) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (k4 + u < n) g4[u] = G[k4 + u];
+        }
+        const long long o0 = base + k4;
+        const bool full = (k4 + 4 <= n) && o0 >= 0;
+        if (full && bits == 16 && (co & 1) == 0 && (((o0 * co) & 1) == 0)) {
+          for (int c = 0; c < co; c += 2) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(Y + (size_t)c * rs + k4);
+            const float4 x1 = *reinterpret_cast<const float4 *>(Y + (size_t)(c + 1) * rs + k4);
+            const float v0[4] = {x0.x, x0.y, x0.z, x0.w}, v1[4] = {x1.x, x1.y, x1.z, x1.w};
+            uint32_t *w = (uint32_t *)((int16_t *)out + o0 * co + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float y0 = v0[u], y1 = v1[u];
+              if (plan.limiter) { y0 = y0 * g4[u]; y1 = y1 * g4[u]; }
+              w[(size_t)u * (co >> 1)] = (uint32_t)(quant16(y0) & 0xffff) | ((uint32_t)quant16(y1) << 16);
+            }
+          }
+        } else {
+          for (int c = 0; c < co; ++c) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (k4 + u >= n || o0 + u < 0) continue;
+              float x = Y[(size_t)c * rs + k4 + u];
+              if (plan.limiter) x = x * g4[u];
+              const size_t idx = (size_t)(o0 + u) * co + c;
+              if (bits == 16) store_sample<16>(out, idx, x);
+              else if (bits == 24) store_sample<24>(out, idx, x);
+              else if (bits == 32) store_sample<32>(out, idx, x);
+              else store_sample<0>(out, idx, x);
+            }
+          }
+        }
+      }
+    }
+    lim_done += n;
+    // ------------------------------------------------------------------ carry the last 240 instants to the front
+    if (plan.limiter) {
+      __syncthreads();
+      if (n >= kLimDelay) {
+        for (int i = tid; i < (co + 1) * (kLimDelay / 4); i += kFusedThreads) {
+          const int r = i / (kLimDelay / 4), c = (i % (kLimDelay / 4)) * 4;
+          float *row = (r < co) ? Y + (size_t)r * rs : PK;
+          if ((n & 3) == 0) {
+            *reinterpret_cast<float4 *>(row + c) = *reinterpret_cast<const float4 *>(row + n + c);
+          } else {
+            const float t0 = row[n + c], t1 = row[n + c + 1], t2 = row[n + c + 2], t3 = row[n + c + 3];
+            row[c] = t0; row[c + 1] = t1; row[c + 2] = t2; row[c + 3] = t3;
+          }
+        }
+      } else {
+        for (int r = 0; r <= co; ++r) {
+          float *row = (r < co) ? Y + (size_t)r * rs : PK;
+          float t0 = 0.f, t1 = 0.f;
+          if (tid < kLimDelay) t0 = row[n + tid];
+          if (tid + kFusedThreads < kLimDelay) t1 = row[n + tid + kFusedThreads];
+          __syncthreads();
+          if (tid < kLimDelay) row[tid] = t0;
+          if (tid + kFusedThreads < kLimDelay) row[tid + kFusedThreads] = t1;
+          __syncthreads();
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (plan.limiter) {
+    for (int i = tid; i < co * H; i += kFusedThreads) a.hist_y[(size_t)s * co * H + i] = Y[(size_t)(i / H) * rs + (i % H)];
+    for (int i = tid; i < H; i += kFusedThreads) a.hist_pk[(size_t)s * H + i] = PK[i];
+    if (tid == 0) {
+      StreamState &st = a.state[s];
+      st.lim_j = lj; st.lim_start = lS; st.lim_end = lE;
+    }
+  }
+}
+
+}  // namespace iamfb

@@ -33,6 +33,11 @@ struct ElPlan {
   int n_mat_out;
   signed char out_slot[kMaxOut];   // matrix output row -> output channel (H2M LFE slot shift, h2m_rdr.c:1114-1135)
   float mat[kMaxOut * kMaxRec];
+  // the same matrix by input column (compressed sparse columns, zero entries dropped): entry q of column m adds
+  // csc_val[q] * x[m] to output channel csc_row[q]; visiting m in ascending order keeps every output's summation order
+  unsigned short csc_ptr[kMaxRec + 1];
+  unsigned char csc_row[kMaxOut * kMaxRec];
+  float csc_val[kMaxOut * kMaxRec];
   // DMR (downmix_renderer.c)
   int dmr_n_out;
   unsigned char dmr_out_ch[IAMFB_MAX_LAYOUT_CH];
