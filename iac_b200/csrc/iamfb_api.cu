@@ -639,20 +639,6 @@ static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &t
   } else {
     return fail(IAMFB_ERR_BAD_ARG, "element %d: unknown kind %d", e, ed.kind);
   }
-  // column-compressed copy of the render matrix, by OUTPUT CHANNEL (out_slot applied), zeros dropped
-  if (ep.renderer != kRdrDMR) {
-    int q = 0;
-    for (int m = 0; m < ep.n_rec; ++m) {
-      ep.csc_ptr[m] = (unsigned short)q;
-      for (int oc = 0; oc < co; ++oc) {
-        const int n = ep.out_slot[oc];
-        if (n < 0) continue;
-        const float c = ep.mat[n * ep.n_rec + m];
-        if (c != 0.f) { ep.csc_row[q] = (unsigned char)oc; ep.csc_val[q] = c; ++q; }
-      }
-    }
-    for (int m = ep.n_rec; m <= kMaxRec; ++m) ep.csc_ptr[m] = (unsigned short)q;
-  }
   return IAMFB_OK;
 }
 
@@ -765,12 +751,12 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
     for (int e = 0; e < kp.n_elements; ++e) {
       nin += kp.el[e].n_in;
       if (kp.el[e].renderer == kRdrDMR) eligible = false;          // the parametric down-mixer stays on the multi-kernel path
+      if (kp.el[e].n_rec > kp.el[e].n_in) eligible = false;        // reconstructed rows are written back over the staged ones
     }
     if (eligible) {
       const int co = kp.out_channels, H = kp.limiter ? kLimDelay : 0;
-      const int two = kp.n_elements > 1 ? 1 : 0;
       const int budget = 14080;                                   // floats: 55 KB per block -> 4 blocks per SM
-      int tl_max = (budget - 16 - 2 * kWmPad - (co + 1) * H) / (nin + co * (1 + two) + 6);
+      int tl_max = (budget - 16 - 2 * kWmPad - (co + 1) * H) / (nin + 1 + co + 6);
       if (tl_max > 1024) tl_max = 1024;
       tl_max &= ~3;
       if (tl_max >= 64) {
@@ -779,8 +765,36 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
         tl = (tl + 3) & ~3;
         p->fused = true;
         p->fused_tile = tl;
-        p->fused_smem = sizeof(float) * ((size_t)nin * tl + (size_t)co * (H + tl) + (size_t)two * co * tl + (H + tl + 16) +
-                                         3 * (size_t)tl + 2 * ((size_t)tl + kWmPad));
+        p->fused_smem = sizeof(float) * ((size_t)(nin + 1) * tl + (size_t)co * (H + tl) + (H + tl + 16) + 3 * (size_t)tl +
+                                         2 * ((size_t)tl + kWmPad));
+        // staged-row byte offsets and the row-compressed render matrix of the fused kernel
+        int row_base = 0;
+        for (int e = 0; e < kp.n_elements; ++e) {
+          ElPlan &ep = kp.el[e];
+          ep.f_row_off = row_base * tl * 4;
+          for (int c = 0; c < kChCount; ++c) {
+            ep.f_src_off[c] = (ep.kind == IAMFB_EL_CHANNEL && ep.src_row[c] >= 0) ? (row_base + ep.src_row[c]) * tl * 4 : nin * tl * 4;
+            ep.f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
+          }
+          int q = 0;
+          for (int oc = 0; oc < co; ++oc) {
+            ep.f_csr_ptr[oc] = (unsigned short)q;
+            const int n = ep.out_slot[oc];
+            if (n < 0) continue;
+            for (int m = 0; m < ep.n_rec; ++m) {
+              const float c = ep.mat[n * ep.n_rec + m];
+              if (c == 0.f) continue;       // adding +-0 never changes the running sum (it starts at +0): exact skip
+              // reconstructed channel m is written back over staged row m of the element; a mono-mapped ambisonics
+              // channel is read straight from the decoded row it maps to
+              const int xrow = (ep.kind == IAMFB_EL_SCENE && ep.ambi_mode == 0) ? ep.ambi_map[m] : m;
+              ep.f_csr_off[q] = (row_base + xrow) * tl * 4;
+              ep.f_csr_val[q] = c;
+              ++q;
+            }
+          }
+          for (int oc = co; oc <= kMaxOut; ++oc) ep.f_csr_ptr[oc] = (unsigned short)q;
+          row_base += ep.n_in;
+        }
       }
     }
   }

@@ -9,8 +9,8 @@
 //   render   reconstruct + render + gains + element sum of ALL audio elements -> mixed samples in shared memory
 //            (Y ring: 240 delayed samples + the tile) and the per-instant cross-channel peak (PK ring).  Channel
 //            sources are read from the staged rows by (uniform) row index, so nothing is indexed dynamically in
-//            registers; channel->channel matrices are applied column by column from a compressed (zero-free) copy,
-//            accumulating in the thread's own shared-memory slots
+//            registers: the reconstructed channels go back over the staged rows (each thread owns its four samples
+//            of every row) and the render matrix is applied row by row from a compressed (zero-free) copy
 //   wmax     240-sample sliding maximum of PK: windows of 8 in registers, then 16..128 by doubling with 16-byte
 //            shared-memory accesses, 240 = two overlapping windows of 128                       (limiter look-ahead)
 //   scan     the limiter's serial gain recurrence, run by warp 0 as a hybrid of
@@ -56,12 +56,11 @@ __device__ __forceinline__ V4 lds4(const float *p) {
 __device__ __forceinline__ void sts4(float *p, const V4 &a) {
   *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
 }
-// the thread's four slots of a time-line row: 16-byte access when aligned, else per sample
-__device__ __forceinline__ void ring_st(float *p, const V4 &a, bool al, int k_lo, int k_hi) {
-  if (al) { sts4(p, a); return; }
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k >= k_lo && k < k_hi) p[k] = a.v[k];
+__device__ __forceinline__ const float *byte_off(const float *base, int off) {
+  return reinterpret_cast<const float *>(reinterpret_cast<const char *>(base) + off);
+}
+__device__ __forceinline__ float *byte_off(float *base, int off) {
+  return reinterpret_cast<float *>(reinterpret_cast<char *>(base) + off);
 }
 
 __device__ __forceinline__ constexpr int fused_order(int layout, int m) {   // IAMF_utils.c:117-133
@@ -72,26 +71,44 @@ __device__ __forceinline__ constexpr int fused_order(int layout, int m) {   // I
   return kOrder[layout][m];
 }
 
-// Channel-based reconstruction (demixer.c:127-378,421-475) from the staged rows.  ine = first staged row of the
-// element at this thread's four samples, rows tl floats apart.  Fills x[m] = layout channel m after recon gain.
+// x / d, correctly rounded (IEEE-754 binary32, round to nearest even), for the de-mixer's divisors.
+// The reference divides by the float constants 1.0, 0.707 and 0.866 (demixer.c:62-72,213-218,262-269,363-368).
+// With r = RN(1/d):  q0 = RN(x*r),  rem = x - d*q0 (exact, one FMA),  q = RN(q0 + rem*r)  equals RN(x/d) for EVERY
+// finite x with 2^-100 <= |x| < 2^126 - verified exhaustively over all 2^32 inputs for each of the three divisors
+// (tools/check_fast_div.c); outside that range (and for d == 0) the ordinary division is used, +-0 maps to q0 = +-0.
+__device__ __noinline__ void slow_div4(V4 &q, const V4 &x, float d) {
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) q.v[k] = x.v[k] / d;
+}
+__device__ __forceinline__ V4 exact_div4(const V4 &x, float d, float r) {
+  V4 q;
+  unsigned int bad = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float q0 = x.v[k] * r;
+    const float rem = __fmaf_rn(-d, q0, x.v[k]);
+    q.v[k] = __fmaf_rn(rem, r, q0);
+    const unsigned int ax = __float_as_uint(x.v[k]) & 0x7fffffffu;
+    bad |= (ax - 0x0d800000u >= 0x7e800000u - 0x0d800000u) ? 1u : 0u;
+  }
+  if (bad | (d == 0.f ? 1u : 0u)) slow_div4(q, x, d);
+  return q;
+}
+__constant__ float c_mix_beta_r[8] = {1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f, 1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f};
+__constant__ float c_mix_gd_r[8] = {1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f, 1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f};
+
+// Channel-based reconstruction (demixer.c:127-378,421-475) from the staged rows.  in_q = the block's staged tile at
+// this thread's four samples; every IAChannel has a byte offset to its row (an all-zero row when absent) and an
+// output gain (1.0 by default).  Fills x[m] = layout channel m after recon gain.
 template <int LAYOUT, int NREC>
 __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const FusedArgs &a, const ElPlan &ep,
-                                                  const ElFrame &ef, const float *ine, int tl, int i0, V4 (&x)[NREC]) {
-  // a transmitted channel: its staged row (zero when absent), with the output gain of dmx_gainup (demixer.c:421-430)
+                                                  const ElFrame &ef, const float *in_q, int i0, V4 (&x)[NREC]) {
+  // a transmitted channel, with the output gain of dmx_gainup (demixer.c:421-430) applied on the fly
   auto tx = [&](int ch) -> V4 {
-    const int row = ep.src_row[ch];
-    V4 r;
-    if (row >= 0) {
-      r = lds4(ine + (size_t)row * tl);
-      if ((ep.gain_mask >> ch) & 1u) {
-        const float g = ep.gain[ch];
+    V4 r = lds4(byte_off(in_q, ep.f_src_off[ch]));
+    const float g = ep.f_gain[ch];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) r.v[k] *= g;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) r.v[k] = 0.f;
-    }
+    for (int k = 0; k < 4; ++k) r.v[k] *= g;
     return r;
   };
   const int mode = ef.mode & 7;
@@ -116,22 +133,21 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
   if (ep.need_s5) {   // Ls5 = (L3 - L5)/delta, demixer.c:213-218
     const V4 l3 = ep.need_s3 ? dL3 : tx(IAMFB_CH_L3), r3 = ep.need_s3 ? dR3 : tx(IAMFB_CH_R3);
     const V4 l5 = tx(IAMFB_CH_L5), r5 = tx(IAMFB_CH_R5);
-    const float d = c_mix_delta[mode];
+    V4 nl, nr;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      dSL5.v[k] = (l3.v[k] - l5.v[k]) / d;
-      dSR5.v[k] = (r3.v[k] - r5.v[k]) / d;
-    }
+    for (int k = 0; k < 4; ++k) { nl.v[k] = l3.v[k] - l5.v[k]; nr.v[k] = r3.v[k] - r5.v[k]; }
+    dSL5 = exact_div4(nl, c_mix_delta[mode], c_mix_gd_r[mode]);
+    dSR5 = exact_div4(nr, c_mix_delta[mode], c_mix_gd_r[mode]);
   }
   if (ep.need_s7) {   // Lb7 = (Ls5 - alpha*Lss7)/beta, demixer.c:262-269
     const V4 sl5 = ep.need_s5 ? dSL5 : tx(IAMFB_CH_SL5), sr5 = ep.need_s5 ? dSR5 : tx(IAMFB_CH_SR5);
     const V4 sl7 = tx(IAMFB_CH_SL7), sr7 = tx(IAMFB_CH_SR7);
-    const float al = c_mix_alpha[mode], be = c_mix_beta[mode];
+    const float al = c_mix_alpha[mode];
+    V4 nl, nr;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      dBL7.v[k] = (sl5.v[k] - sl7.v[k] * al) / be;
-      dBR7.v[k] = (sr5.v[k] - sr7.v[k] * al) / be;
-    }
+    for (int k = 0; k < 4; ++k) { nl.v[k] = sl5.v[k] - sl7.v[k] * al; nr.v[k] = sr5.v[k] - sr7.v[k] * al; }
+    dBL7 = exact_div4(nl, c_mix_beta[mode], c_mix_beta_r[mode]);
+    dBR7 = exact_div4(nr, c_mix_beta[mode], c_mix_beta_r[mode]);
   }
   if (ep.need_h2) {   // Ltf2 = Ltf3 - delta*w*Ls5, demixer.c:318-323
     const V4 sl5 = ep.need_s5 ? dSL5 : tx(IAMFB_CH_SL5), sr5 = ep.need_s5 ? dSR5 : tx(IAMFB_CH_SR5);
@@ -146,12 +162,21 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
   if (ep.need_h4) {   // Ltb = (Ltf2 - Ltf4)/gamma, demixer.c:363-368
     const V4 hl = ep.need_h2 ? dHL : tx(IAMFB_CH_HL), hr = ep.need_h2 ? dHR : tx(IAMFB_CH_HR);
     const V4 hfl = tx(IAMFB_CH_HFL), hfr = tx(IAMFB_CH_HFR);
-    const float ga = c_mix_gamma[mode];
+    V4 nl, nr;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      dHBL.v[k] = (hl.v[k] - hfl.v[k]) / ga;
-      dHBR.v[k] = (hr.v[k] - hfr.v[k]) / ga;
-    }
+    for (int k = 0; k < 4; ++k) { nl.v[k] = hl.v[k] - hfl.v[k]; nr.v[k] = hr.v[k] - hfr.v[k]; }
+    dHBL = exact_div4(nl, c_mix_gamma[mode], c_mix_gd_r[mode]);
+    dHBR = exact_div4(nr, c_mix_gamma[mode], c_mix_gd_r[mode]);
+  }
+  // recon-gain cross-fade window of this thread's samples (dmx_rms, demixer.c:461-468): hann start / stop inside the
+  // first frame_size/16 samples of the frame, 1 / 0 after
+  V4 st, sw;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { st.v[k] = 0.f; sw.v[k] = 1.f; }
+  if (ef.rmask && i0 < plan.overlap) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k < plan.overlap) { st.v[k] = a.stop_win[i0 + k]; sw.v[k] = a.start_win[i0 + k]; }
   }
   // gather in layout order; a derived pair replaces the transmitted one exactly when its step ran
 #pragma unroll
@@ -174,48 +199,46 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
       default: dv = dR2; break;
     }
     x[m] = der ? dv : tx(ch);
-    if ((ef.rmask >> m) & 1u) {   // dmx_rms cross-fade, demixer.c:461-468: x *= last*stop[i] + cur*start[i]
+    if ((ef.rmask >> m) & 1u) {   // x *= last*stop[i] + cur*start[i]
       const float lastf = ef.rlast[m], cur = ef.rcur[m];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k;
-        float st = 0.f, sw = 1.f;
-        if (i < plan.overlap) { st = a.stop_win[i]; sw = a.start_win[i]; }
-        const float f = lastf * st + cur * sw;
+        const float f = lastf * st.v[k] + cur * sw.v[k];
         x[m].v[k] *= f;
       }
     }
   }
 }
 
-// One element's contribution for the 4 samples [i0, i0+4) of this thread.
-//   ine   staged rows of the element at the thread's samples (rows tl apart)
-//   yt    the thread's slots in the mixed time line (&Y[0][ring position of sample i0], rows rs apart)
-//   acc   the thread's slots in the per-element accumulator: yt itself for a single element, else a scratch [co][tl]
-//   al    yt/acc slots are 16-byte aligned and all four samples are valid
+// One element's contribution for the 4 samples [i0, i0+4) of this thread; the whole tile is rendered as if untrimmed
+// (a trimmed tile is compacted afterwards), so every access is a whole aligned quad.
+//   in_q  the block's staged tile at the thread's samples (rows tl floats apart)
+//   yt    the thread's slots in the mixed time line (&Y[0][ring position], rows rs floats apart)
 template <int LAYOUT, int NREC>
 __device__ __forceinline__ void fused_element(const KernelPlan &plan, const FusedArgs &a, int e, const FrameRec &fr,
-                                              int sf, int i0, int lo, int hi, bool first, bool last, const float *ine,
-                                              int tl, float *yt, int rs, float *acc, int acc_rs, bool acc_al, float *pkt,
-                                              bool al) {
+                                              int sf, int i0, bool first, bool last, float *in_q, int tl, float *yt, int rs,
+                                              float *pkt) {
   const int N = plan.frame_size;
   const ElPlan &ep = plan.el[e];
   const ElFrame &ef = fr.el[e];
   const int co = plan.out_channels;
-  const int k_lo = lo - i0, k_hi = hi - i0;
-  V4 x[NREC];
+  float *ine = byte_off(in_q, ep.f_row_off);
   if constexpr (LAYOUT >= 0) {
-    fused_reconstruct<LAYOUT, NREC>(plan, a, ep, ef, ine, tl, i0, x);
-  } else {
-    // scene based: mono mapping is a row permutation, projection an ordered mat-vec (IAMF_core_decoder.c:105-130)
-    if (ep.ambi_mode == 0) {
+    V4 x[NREC];
+    fused_reconstruct<LAYOUT, NREC>(plan, a, ep, ef, in_q, i0, x);
+    // the reconstructed layout channels replace the staged rows (this thread's samples only; all its reads are done)
 #pragma unroll
-      for (int m = 0; m < NREC; ++m) x[m] = lds4(ine + (size_t)ep.ambi_map[m] * tl);
-    } else {
+    for (int m = 0; m < NREC; ++m) sts4(ine + (size_t)m * tl, x[m]);
+  } else {
+    // scene based: a mono mapping is a row permutation (folded into the matrix offsets), a projection an ordered
+    // mat-vec (IAMF_core_decoder.c:105-130) whose result replaces the staged rows
+    if (ep.ambi_mode != 0) {
+      V4 x[NREC];
 #pragma unroll
       for (int m = 0; m < NREC; ++m)
 #pragma unroll
         for (int k = 0; k < 4; ++k) x[m].v[k] = .0f;
+#pragma unroll 1
       for (int l = 0; l < ep.ambi_cols; ++l) {
         const V4 t = lds4(ine + (size_t)l * tl);
 #pragma unroll
@@ -225,110 +248,83 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
           for (int k = 0; k < 4; ++k) x[m].v[k] += t.v[k] * c;
         }
       }
+#pragma unroll
+      for (int m = 0; m < NREC; ++m) sts4(ine + (size_t)m * tl, x[m]);
     }
   }
 
-  // ---- render: out = 0; out += mat * in over inputs ascending (m2m_rdr.c:1820-1840, h2m_rdr.c:1103-1112)
-  if constexpr (LAYOUT >= 0) {
-    // sparse channel matrix, column by column, accumulating in the thread's own shared-memory slots
-    V4 z;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) z.v[k] = 0.f;
-    // (when the slots are not a whole aligned quad only the samples inside [lo, hi) may be touched: the neighbours
-    // belong to the history in front of the tile or to the next row)
-    for (int oc = 0; oc < co; ++oc) ring_st(acc + (size_t)oc * acc_rs, z, acc_al, k_lo, k_hi);
-#pragma unroll
-    for (int m = 0; m < NREC; ++m) {
-      const int q1 = ep.csc_ptr[m + 1];
-      for (int q = ep.csc_ptr[m]; q < q1; ++q) {
-        const float c = ep.csc_val[q];
-        float *p = acc + (size_t)ep.csc_row[q] * acc_rs;
-        V4 y;
-        if (acc_al) y = lds4(p);
-        else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) y.v[k] = (k >= k_lo && k < k_hi) ? p[k] : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) y.v[k] += c * x[m].v[k];
-        ring_st(p, y, acc_al, k_lo, k_hi);
-      }
-    }
-  }
-
-  const int vstart = fr.vstart;
-  const float *gr = a.gain_ramp[e], *ogr = a.out_gain_ramp;
+  // element mix gain / output mix gain: constants, or per-sample ramps (animated mix gain)
+  const float *gr = a.gain_ramp[e], *ogr = last ? a.out_gain_ramp : nullptr;
+  const bool eg_on = gr || (ef.gain != 1.f && ef.gain > 0.f);             // iamf_frame_gain, IAMF_decoder.c:1392
+  const bool og_on = last && (ogr || (fr.out_gain != 1.f && fr.out_gain > 0.f));
   V4 eg, og;
-  {
-    const bool eg_on = gr || (ef.gain != 1.f && ef.gain > 0.f);   // iamf_frame_gain, IAMF_decoder.c:1392
-    const bool og_on = ogr || (fr.out_gain != 1.f && fr.out_gain > 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { eg.v[k] = ef.gain; og.v[k] = fr.out_gain; }
+  if (gr || ogr) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int j = i0 + k - vstart;
-      const bool in_rng = k >= k_lo && k < k_hi;
-      eg.v[k] = (gr && in_rng) ? gr[(size_t)sf * N + j] : (eg_on ? ef.gain : 1.f);
-      og.v[k] = (ogr && in_rng) ? ogr[(size_t)sf * N + j] : (og_on ? fr.out_gain : 1.f);
+      const int j = min(max(i0 + k - fr.vstart, 0), N - 1);   // samples outside the trimmed frame are discarded later
+      if (gr) eg.v[k] = gr[(size_t)sf * N + j];
+      if (ogr) og.v[k] = ogr[(size_t)sf * N + j];
     }
   }
-  const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
+  const bool loud_on = last && plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
   V4 peak;
 #pragma unroll
   for (int k = 0; k < 4; ++k) peak.v[k] = 0.f;
 
+  // render: out = 0; out += mat * in over inputs ascending (m2m_rdr.c:1820-1840, h2m_rdr.c:1103-1112)
+#pragma unroll 1
   for (int oc = 0; oc < co; ++oc) {
     V4 y;
-    if constexpr (LAYOUT >= 0) {
-      const float *p = acc + (size_t)oc * acc_rs;
-      if (acc_al) y = lds4(p);
-      else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y.v[k] = (k >= k_lo && k < k_hi) ? p[k] : 0.f;
-      }
-    } else {
+    for (int k = 0; k < 4; ++k) y.v[k] = 0.f;
+    const int q1 = ep.f_csr_ptr[oc + 1];
+#pragma unroll 2
+    for (int q = ep.f_csr_ptr[oc]; q < q1; ++q) {
+      const float c = ep.f_csr_val[q];
+      const V4 xm = lds4(byte_off(in_q, ep.f_csr_off[q]));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y.v[k] = 0.f;
-      const int n = ep.out_slot[oc];
-      if (n >= 0) {
-        const float *mrow = ep.mat + n * NREC;
-#pragma unroll
-        for (int m = 0; m < NREC; ++m) {
-          const float c = mrow[m];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) y.v[k] += c * x[m].v[k];   // adding c == 0 terms is exact: the sum starts at +0
-        }
-      }
+      for (int k = 0; k < 4; ++k) y.v[k] += c * xm.v[k];
     }
     // element mix gain, IAMF_decoder.c:1392-1405
+    if (eg_on) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (gr || eg.v[k] != 1.f) y.v[k] *= eg.v[k];
+      for (int k = 0; k < 4; ++k) y.v[k] *= eg.v[k];
+    }
     float *dst = yt + (size_t)oc * rs;
     // iamf_mixer_mix, IAMF_decoder.c:2719-2730: acc = 0; acc += e0; acc += e1
     if (first) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) y.v[k] = 0.f + y.v[k];
     } else {
-      V4 p;
-      if (al) p = lds4(dst);
-      else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p.v[k] = (k >= k_lo && k < k_hi) ? dst[k] : 0.f;
-      }
+      const V4 p = lds4(dst);
 #pragma unroll
       for (int k = 0; k < 4; ++k) y.v[k] = p.v[k] + y.v[k];
     }
     if (last) {
       // output mix gain (IAMF_decoder.c:3463-3469) then loudness (:3480-3484)
+      if (og_on) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (ogr || og.v[k] != 1.f) y.v[k] *= og.v[k];
-        if (loud_on) y.v[k] *= plan.loud_gain;
-        peak.v[k] = fmaxf(peak.v[k], fabsf(y.v[k]));
+        for (int k = 0; k < 4; ++k) y.v[k] *= og.v[k];
       }
+      if (loud_on) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y.v[k] *= plan.loud_gain;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) peak.v[k] = fmaxf(peak.v[k], fabsf(y.v[k]));
     }
-    ring_st(dst, y, al, k_lo, k_hi);
+    sts4(dst, y);
   }
-  if (last && pkt) ring_st(pkt, peak, al, k_lo, k_hi);
+  if (last && pkt) sts4(pkt, peak);
+}
+
+__device__ __noinline__ void store_any(char *out, size_t idx, float x, int bits) {
+  if (bits == 16) store_sample<16>(out, idx, x);
+  else if (bits == 24) store_sample<24>(out, idx, x);
+  else if (bits == 32) store_sample<32>(out, idx, x);
+  else store_sample<0>(out, idx, x);
 }
 
 // Limiter gain recurrence over the n instants of a tile, run by ONE warp with warp-uniform state (j, S, E).
@@ -337,10 +333,14 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
 //   wm[k] = look-ahead peak of instant k, ew[k] = thr / wm[k] (IEEE division, :259), g[k] receives the gain.
 // compute_target_gain (audio_effect_peak_limiter.c:237-265): the gain of a step depends only on (S, E, j); a trigger
 // (peak * gain > thr) restarts the curve from the current gain.  While no trigger fires the next 32 steps are
-// evaluated in parallel, one per lane, and the first lane whose test fires is found with a ballot; right after a
-// trigger the limiter usually fires again on every sample (the attack curve has not yet reached thr/peak), and that
-// run is walked serially, eight samples at a time speculatively, with every lane holding the same values.
-__device__ __forceinline__ void fused_scan(const float *wm, const float *ew, float *g, int n, int &j, float &S, float &E,
+// evaluated in parallel, one per lane, and the first lane whose test fires is found with a ballot.  Right after a
+// trigger the limiter fires again on every sample for as long as the peak stays in the look-ahead window (the attack
+// curve never quite reaches thr/peak): that run is a strictly serial float recurrence  g' = g - acc[1]*(g - thr/peak)
+// and is walked sixteen samples at a time speculatively, every lane holding the same values, with nothing but the
+// three dependent float operations per sample on the critical path.
+constexpr int kBurst = 16;
+
+__device__ __noinline__ void fused_scan(const float *wm, const float *ew, float *g, int n, int &j, float &S, float &E,
                                            const float *__restrict__ acc, int ja, int jr, float thr, int lane) {
   const float a1 = __ldg(acc + 1);
   int pos = 0;
@@ -373,41 +373,49 @@ __device__ __forceinline__ void fused_scan(const float *wm, const float *ew, flo
     // ---- serial burst: the step after a trigger has gain S - acc[1]*(S - E); while it triggers again the state is
     // (S = that gain, E = thr/peak, j = 0) and the next step has the same form
     while (pos < n) {
-      const int m = min(8, n - pos);
-      float gs[8], es[8];
-      bool ts[8];
-      float s = S, e = E;
+      const int m = min(kBurst, n - pos);
+      float ps[kBurst], es[kBurst], gs[kBurst];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kBurst; ++i) {
         const int q = min(pos + i, n - 1);
-        const float pi = wm[q];
-        const float ei = ew[q];
+        ps[i] = wm[q];
+        es[i] = ew[q];
+      }
+      float s = S, e = E;
+      unsigned tm = 0u;
+#pragma unroll
+      for (int i = 0; i < kBurst; ++i) {
         const float gi = s - a1 * (s - e);
         gs[i] = gi;
-        es[i] = ei;
-        ts[i] = pi * gi > thr;
+        tm |= (ps[i] * gi > thr) ? (1u << i) : 0u;
         s = gi;
-        e = ei;
+        e = es[i];
       }
-      int lead = 0;   // number of leading steps that all triggered
+      // number of leading steps that all triggered (capped at m)
+      const int lead = min(__ffs(~tm) - 1, m);
+      if (lead == kBurst) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) lead += (lead == i && i < m && ts[i]) ? 1 : 0;
+        for (int i = 0; i < kBurst; ++i) g[pos + i] = gs[i];
+        S = gs[kBurst - 1];
+        E = es[kBurst - 1];
+        pos += kBurst;
+        continue;
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < kBurst; ++i)
         if (i < lead) {
-          if (lane == 0) g[pos + i] = gs[i];
+          g[pos + i] = gs[i];
           S = gs[i];
           E = es[i];
         }
       pos += lead;
       if (lead < m) {
         // step pos did not trigger: its gain is the curve value one increment after the last trigger
-        const float gi = S - a1 * (S - E);
-        if (lane == 0) g[pos] = gi;
+        g[pos] = S - a1 * (S - E);
         j = 1;
         pos += 1;
-        break;
       }
+      break;
     }
   }
 }
@@ -419,15 +427,16 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
   __shared__ int s_lim[4];
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // co-resident blocks run their serial scans on different warp schedulers
+  const int scan_warp = (blockIdx.x / 148) & 3;
   const int N = plan.frame_size, co = plan.out_channels;
   const int H = plan.limiter ? kLimDelay : 0;
   const int TL = a.tile;
   const int rs = H + TL;                        // row stride of the rings (multiple of 4)
   const int nin0 = plan.el[0].n_in, nin1 = N1 > 0 ? plan.el[1].n_in : 0;
-  float *IN = fsm;                              // [nin0 + nin1][TL] staged decoded rows
-  float *Y = IN + (size_t)(nin0 + nin1) * TL;   // [co][rs] mixed time line: 240 delayed samples, then the tile
-  float *YE = Y + (size_t)co * rs;              // [co][TL] per-element accumulator (two-element plans only)
-  float *PK = YE + (N1 > 0 ? (size_t)co * TL : 0);   // [rs + 16]
+  float *IN = fsm;                              // [nin0 + nin1 + 1][TL] staged decoded rows + one all-zero row
+  float *Y = IN + (size_t)(nin0 + nin1 + 1) * TL;   // [co][rs] mixed time line: 240 delayed samples, then the tile
+  float *PK = Y + (size_t)co * rs;              // [rs + 16]
   float *WM = PK + rs + 16;                     // [TL]
   float *EW = WM + TL;                          // [TL]
   float *G = EW + TL;                           // [TL]
@@ -437,12 +446,17 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
   const SubmitRec sr = a.submit[s];
   int lj = -1;
   float lS = -1.f, lE = -1.f;
+  for (int i = tid; i < TL; i += kFusedThreads) IN[(size_t)(nin0 + nin1) * TL + i] = 0.f;
   if (plan.limiter) {
     const StreamState &st = a.state[s];
     lj = st.lim_j; lS = st.lim_start; lE = st.lim_end;
     if (lj > plan.lim_jr) lj = plan.lim_jr;
-    for (int i = tid; i < co * H; i += kFusedThreads) Y[(size_t)(i / H) * rs + (i % H)] = a.hist_y[(size_t)s * co * H + i];
-    for (int i = tid; i < H; i += kFusedThreads) PK[i] = a.hist_pk[(size_t)s * H + i];
+#pragma unroll 1
+    for (int c = 0; c <= co; ++c) {
+      const float *src = c < co ? a.hist_y + ((size_t)s * co + c) * kLimDelay : a.hist_pk + (size_t)s * kLimDelay;
+      float *row = c < co ? Y + (size_t)c * rs : PK;
+      for (int i = tid; i < kLimDelay; i += kFusedThreads) row[i] = src[i];
+    }
     for (int i = tid; i < TL + 16; i += kFusedThreads) PK[H + i] = 0.f;
     for (int i = tid; i < TL + kWmPad; i += kFusedThreads) { SA[i] = 0.f; SB[i] = 0.f; }
   }
@@ -489,15 +503,13 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
   uint32_t parity = 0;
   int f = 0, t_off = -TL;
   if (n_frames > 0) {
-    f = 0; t_off = -TL;
     advance(f, t_off);
     if (f < n_frames && tid == 0) issue(f, t_off);
   }
   bool flush_pending = a.flush != 0;
 
   while (f < n_frames || flush_pending) {
-    int n, lo_t = 0, hi_t = 0;
-    const int sf = s * a.n_frames + f;
+    int n;
     if (flush_pending) {
       // end of stream: the limiter is fed 240 zeros (iamf_delay_buffer_handle, IAMF_decoder.c:3250-3301)
       n = min(kLimDelay - lim_done, TL);
@@ -507,27 +519,42 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
       }
       if (lim_done + n >= kLimDelay) flush_pending = false;
     } else {
+      int lo_t, hi_t;
       tile_range(f, t_off, lo_t, hi_t);
       n = hi_t - lo_t;
-      // ---------------------------------------------------------------- render
+      const int sf = s * a.n_frames + f;
+      // ---------------------------------------------------------------- render (the whole tile, as if untrimmed)
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
       const FrameRec &fr = a.frames[sf];
-      const bool tile_al = ((lo_t - t_off) & 3) == 0;     // ring slots of a thread start on a 16-byte boundary
       const int t_end = min(t_off + TL, N);
       for (int i0 = t_off + tid * 4; i0 < t_end; i0 += kFusedThreads * 4) {
-        const int lo = max(i0, lo_t), hi = min(i0 + 4, hi_t);
-        if (lo >= hi) continue;
         const int q = i0 - t_off;                         // position inside the staged tile
-        const bool al = tile_al && lo == i0 && hi == i0 + 4;
-        float *yt = Y + H + (i0 - lo_t);
-        float *pkt = plan.limiter ? PK + H + (i0 - lo_t) : nullptr;
-        if constexpr (N1 == 0) {
-          fused_element<L0, N0>(plan, a, 0, fr, sf, i0, lo, hi, true, true, IN + q, TL, yt, rs, yt, rs, al, pkt, al);
-        } else {
-          fused_element<L0, N0>(plan, a, 0, fr, sf, i0, lo, hi, true, false, IN + q, TL, yt, rs, YE + q, TL, true, pkt, al);
-          fused_element<L1, N1>(plan, a, 1, fr, sf, i0, lo, hi, false, true, IN + (size_t)nin0 * TL + q, TL, yt, rs, YE + q,
-                                TL, true, pkt, al);
+        float *yt = Y + H + q;
+        float *pkt = plan.limiter ? PK + H + q : nullptr;
+        fused_element<L0, N0>(plan, a, 0, fr, sf, i0, true, N1 == 0, IN + q, TL, yt, rs, pkt);
+        if constexpr (N1 > 0) fused_element<L1, N1>(plan, a, 1, fr, sf, i0, false, true, IN + q, TL, yt, rs, pkt);
+      }
+      // a trimmed tile: move its surviving samples [lo_t, hi_t) to the front of the tile (iamf_frame_trim,
+      // IAMF_decoder.c:1361-1381); rare (first / last frames), one row at a time through registers
+      const int shift = lo_t - t_off;
+      if (shift > 0) {
+        for (int r = 0; r <= co; ++r) {
+          if (r == co && !plan.limiter) break;
+          float *row = (r < co ? Y + (size_t)r * rs : PK) + H;
+          __syncthreads();
+          float t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = tid + u * kFusedThreads;
+            t[u] = i < n ? row[shift + i] : 0.f;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = tid + u * kFusedThreads;
+            if (i < n) row[i] = t[u];
+          }
         }
       }
     }
@@ -571,7 +598,6 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
         const float4 B = *reinterpret_cast<const float4 *>(src + 4 * v + 112);
         const float4 W = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
         *reinterpret_cast<float4 *>(WM + 4 * v) = W;
-        *reinterpret_cast<float4 *>(EW + 4 * v) = make_float4(thr / W.x, thr / W.y, thr / W.z, thr / W.w);
         const int left = n - 4 * v;
         hot |= (W.x > thr) || (left > 1 && W.y > thr) || (left > 2 && W.z > thr) || (left > 3 && W.w > thr);
       }
@@ -580,7 +606,13 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
       const bool idle = lj < 0 || lj >= plan.lim_jr;         // block-uniform
       if (any_hot || !idle) {
         apply_gain = true;
-        if (warp == 0) {
+        // thr / peak (targetEndGain of a trigger, :259): only tiles that can trigger need it
+        for (int v = tid; 4 * v < n; v += kFusedThreads) {
+          const float4 W = *reinterpret_cast<const float4 *>(WM + 4 * v);
+          *reinterpret_cast<float4 *>(EW + 4 * v) = make_float4(thr / W.x, thr / W.y, thr / W.z, thr / W.w);
+        }
+        __syncthreads();
+        if (warp == scan_warp) {
           fused_scan(WM, EW, G, n, lj, lS, lE, a.acc, plan.lim_ja, plan.lim_jr, thr, lane);
           if (lane == 0) { s_lim[0] = lj; s_lim[1] = __float_as_int(lS); s_lim[2] = __float_as_int(lE); }
         }
@@ -614,17 +646,14 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
             }
           }
         } else {
+#pragma unroll 1
           for (int c = 0; c < co; ++c) {
-#pragma unroll
+#pragma unroll 1
             for (int u = 0; u < 4; ++u) {
               if (k4 + u >= n || o0 + u < 0) continue;
               float x = Y[(size_t)c * rs + k4 + u];
-              if (plan.limiter) x = x * g4[u];
-              const size_t idx = (size_t)(o0 + u) * co + c;
-              if (bits == 16) store_sample<16>(out, idx, x);
-              else if (bits == 24) store_sample<24>(out, idx, x);
-              else if (bits == 32) store_sample<32>(out, idx, x);
-              else store_sample<0>(out, idx, x);
+              if (plan.limiter) x = x * (apply_gain ? G[k4 + u] : 1.0f);
+              store_any(out, (size_t)(o0 + u) * co + c, x, bits);
             }
           }
         }
@@ -634,18 +663,16 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
     // ------------------------------------------------------------------ carry the last 240 instants to the front
     if (plan.limiter) {
       __syncthreads();
-      if (n >= kLimDelay) {
+      if (n >= kLimDelay && (n & 3) == 0) {
+        // source [n, n+240) and destination [0, 240) do not overlap
+#pragma unroll 1
         for (int i = tid; i < (co + 1) * (kLimDelay / 4); i += kFusedThreads) {
-          const int r = i / (kLimDelay / 4), c = (i % (kLimDelay / 4)) * 4;
+          const int r = i / (kLimDelay / 4), c = (i - r * (kLimDelay / 4)) * 4;
           float *row = (r < co) ? Y + (size_t)r * rs : PK;
-          if ((n & 3) == 0) {
-            *reinterpret_cast<float4 *>(row + c) = *reinterpret_cast<const float4 *>(row + n + c);
-          } else {
-            const float t0 = row[n + c], t1 = row[n + c + 1], t2 = row[n + c + 2], t3 = row[n + c + 3];
-            row[c] = t0; row[c + 1] = t1; row[c + 2] = t2; row[c + 3] = t3;
-          }
+          *reinterpret_cast<float4 *>(row + c) = *reinterpret_cast<const float4 *>(row + n + c);
         }
       } else {
+#pragma unroll 1
         for (int r = 0; r <= co; ++r) {
           float *row = (r < co) ? Y + (size_t)r * rs : PK;
           float t0 = 0.f, t1 = 0.f;
@@ -654,7 +681,6 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
           __syncthreads();
           if (tid < kLimDelay) row[tid] = t0;
           if (tid + kFusedThreads < kLimDelay) row[tid + kFusedThreads] = t1;
-          __syncthreads();
         }
       }
     }
@@ -662,8 +688,12 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
   }
 
   if (plan.limiter) {
-    for (int i = tid; i < co * H; i += kFusedThreads) a.hist_y[(size_t)s * co * H + i] = Y[(size_t)(i / H) * rs + (i % H)];
-    for (int i = tid; i < H; i += kFusedThreads) a.hist_pk[(size_t)s * H + i] = PK[i];
+#pragma unroll 1
+    for (int c = 0; c <= co; ++c) {
+      float *dst = c < co ? a.hist_y + ((size_t)s * co + c) * kLimDelay : a.hist_pk + (size_t)s * kLimDelay;
+      const float *row = c < co ? Y + (size_t)c * rs : PK;
+      for (int i = tid; i < kLimDelay; i += kFusedThreads) dst[i] = row[i];
+    }
     if (tid == 0) {
       StreamState &st = a.state[s];
       st.lim_j = lj; st.lim_start = lS; st.lim_end = lE;

@@ -33,11 +33,16 @@ struct ElPlan {
   int n_mat_out;
   signed char out_slot[kMaxOut];   // matrix output row -> output channel (H2M LFE slot shift, h2m_rdr.c:1114-1135)
   float mat[kMaxOut * kMaxRec];
-  // the same matrix by input column (compressed sparse columns, zero entries dropped): entry q of column m adds
-  // csc_val[q] * x[m] to output channel csc_row[q]; visiting m in ascending order keeps every output's summation order
-  unsigned short csc_ptr[kMaxRec + 1];
-  unsigned char csc_row[kMaxOut * kMaxRec];
-  float csc_val[kMaxOut * kMaxRec];
+  // fused kernel (resolved once the tile size is known): byte offset of every IAChannel's staged row inside the
+  // block's input tile (absent channels point at an all-zero row), output gain per channel with 1.0 as the default
+  // (multiplying by 1.0f is exact); the render matrix by OUTPUT CHANNEL (compressed rows, zeros dropped, inputs
+  // ascending): entry q of row oc adds f_csr_val[q] * (staged/reconstructed row at byte offset f_csr_off[q])
+  int f_src_off[kChCount];
+  float f_gain[kChCount];
+  int f_row_off;                   // byte offset of the element's first staged row
+  unsigned short f_csr_ptr[kMaxOut + 1];
+  int f_csr_off[kMaxOut * kMaxRec];
+  float f_csr_val[kMaxOut * kMaxRec];
   // DMR (downmix_renderer.c)
   int dmr_n_out;
   unsigned char dmr_out_ch[IAMFB_MAX_LAYOUT_CH];
