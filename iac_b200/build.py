@@ -37,8 +37,34 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(PKG, "host")
+DROPIN = os.path.join(PKG, "libiamf.so")
+REF_OPUS = "/root/reference/dep_codecs/lib/libopus.a"
+
+
+def build_dropin(force=False):
+    """the drop-in libiamf.so: plain-C host layer (include/IAMF_decoder.h API) on top of libiamf_b200.so.
+    Opus entropy decode is linked from the reference tree's prebuilt libopus.a when that exists (authoring
+    container); without it the library is built ipcm-only."""
+    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".c")]
+    deps = srcs + [os.path.join(HOST, "iamf_host.h"), os.path.join(HOST, "libiamf.map"), os.path.join(ROOT, "include", "IAMF_decoder.h"),
+                   os.path.join(ROOT, "include", "iamf_b200.h"), LIB]
+    if not force and not _stale(DROPIN, deps):
+        return DROPIN
+    cmd = [os.environ.get("CC", "gcc"), "-std=c99", "-O2", "-Wall", "-fPIC", "-shared", "-fvisibility=default",
+           "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-o", DROPIN] + srcs
+    if os.path.exists(REF_OPUS):
+        cmd += ["-DIH_HAVE_OPUS", REF_OPUS]
+    cmd += ["-L" + PKG, "-l:libiamf_b200.so", "-Wl,-rpath,$ORIGIN", "-Wl,--exclude-libs,ALL",
+            "-Wl,--version-script=" + os.path.join(HOST, "libiamf.map"), "-lm"]
+    print("[iac_b200.build]", " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return DROPIN
+
+
 def build_all(force=False):
-    return build_cuda(force)
+    build_cuda(force)
+    return build_dropin(force)
 
 
 if __name__ == "__main__":

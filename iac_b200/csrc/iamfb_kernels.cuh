@@ -102,6 +102,17 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelP
     while (sub <= a.n_sub && a.sub_frame[sub] == f) sr.sub_off[sub++] = lim_in_total;
     const iamfb_frame_params fp = a.params[(size_t)s * a.n_frames + f];
     FrameRec fr;
+    if (fp.trim_start == 0xFFFFu) {
+      // "this stream has no frame in this step" (grouped handles stepping together, IAMF_decoder_decode_batch):
+      // nothing is decoded, so no state machine advances and nothing is produced
+      fr.out_gain = 1.f;
+      fr.vstart = 0;
+      fr.vlen = 0;
+      fr.t_off = t_off;
+      a.frames[(size_t)s * a.n_frames + f] = fr;
+      if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = 0;
+      continue;
+    }
     for (int e = 0; e < plan.n_elements; ++e) {
       const ElPlan &ep = plan.el[e];
       ElState &es = st.el[e];

@@ -1,8 +1,9 @@
 /*
- * iamf_codec.c - core (codec) decode of the drop-in host layer.  Entropy decoding is OUTSIDE the accelerated path:
- * linear PCM ('ipcm') is decoded here; Opus / AAC / FLAC belong to the reference codec libraries (libopus, fdk-aac,
- * libFLAC, README.md:118-130) which are not vendored into this repository, so streams using them are refused with
- * IAMF_ERR_UNIMPLEMENTED at configure time rather than rendered wrongly.
+ * iamf_codec.c - core (codec) decode of the drop-in host layer.  Entropy decoding is OUTSIDE the accelerated path and
+ * stays in the reference codec libraries (README.md:118-130): linear PCM ('ipcm') is decoded here; Opus is decoded by
+ * libopus through its public API when the library was available at build time (-DIH_HAVE_OPUS, linked from the
+ * reference tree's dep_codecs/lib/libopus.a, never copied into this repository); AAC / FLAC streams are refused with
+ * IAMF_ERR_UNIMPLEMENTED at configure time rather than rendered wrongly (fdk-aac is missing upstream for Linux).
  * Output contract (pcm/IAMF_pcm_decoder.c:52-151): planar float, integer sample / 2^(bits-1), coupled substreams
  * de-interleaved, substreams concatenated in transmission order.
  */
@@ -10,7 +11,20 @@
 
 #include "iamf_host.h"
 
-int ih_codec_supported(int codec) { return codec == IAMF_CODEC_PCM; }
+#ifdef IH_HAVE_OPUS
+/* public libopus API (opus.h) - declared here so that no third-party header is needed at build time */
+typedef struct OpusDecoder OpusDecoder;
+OpusDecoder *opus_decoder_create(int Fs, int channels, int *error);
+int opus_decode(OpusDecoder *st, const unsigned char *data, int len, short *pcm, int frame_size, int decode_fec);
+void opus_decoder_destroy(OpusDecoder *st);
+#endif
+
+int ih_codec_supported(int codec) {
+#ifdef IH_HAVE_OPUS
+  if (codec == IAMF_CODEC_OPUS) return 1;
+#endif
+  return codec == IAMF_CODEC_PCM;
+}
 
 static int rd16le(const uint8_t *p) { return (int16_t)(p[0] | p[1] << 8); }
 static int rd16be(const uint8_t *p) { return (int16_t)(p[0] << 8 | p[1]); }
@@ -53,8 +67,50 @@ static int pcm_decode(const ih_codec *cc, uint8_t *const *pkt, const uint32_t *p
   return samples;
 }
 
-int ih_codec_decode(const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size, int n_sub, int n_coupled,
-                    float *out, int frame_size) {
+#ifdef IH_HAVE_OPUS
+/* one OpusDecoder per sub-stream (stereo for coupled ones), int16 output scaled by 1/32768 like
+ * opus/IAMF_opus_decoder.c:119-138; coupled sub-streams first, planar output (opus_multistream2_decoder.c:125-165) */
+static int opus_decode_group(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size,
+                             int n_sub, int n_coupled, float *out, int frame_size) {
+  short buf[2 * 5760];
+  int ch = 0, samples = 0;
+  if (frame_size > 5760) return IAMF_ERR_BAD_ARG;
+  for (int c = 0; c < n_sub; ++c) {
+    const int nch = c < n_coupled ? 2 : 1;
+    OpusDecoder *dec = (OpusDecoder *)st->codec_state[first_sub + c];
+    if (!dec) {
+      int err = 0;
+      dec = opus_decoder_create(cc->rate, nch, &err);
+      if (!dec) return IAMF_ERR_INVALID_STATE;
+      st->codec_state[first_sub + c] = dec;
+    }
+    int n = opus_decode(dec, pkt[c], (int)pkt_size[c], buf, frame_size, 0);
+    if (n < 0) return IAMF_ERR_INTERNAL;
+    if (c && n != samples) return IAMF_ERR_INTERNAL;
+    samples = n;
+    for (int k = 0; k < nch; ++k)
+      for (int s = 0; s < n; ++s) out[(size_t)n * (ch + k) + s] = buf[s * nch + k] / 32768.f;
+    ch += nch;
+  }
+  return samples;
+}
+#endif
+
+void ih_codec_close(ih_stream *st) {
+  for (int i = 0; i < IH_MAX_SUBSTREAMS; ++i) {
+#ifdef IH_HAVE_OPUS
+    if (st->codec_state[i] && st->cc && st->cc->codec == IAMF_CODEC_OPUS) opus_decoder_destroy((OpusDecoder *)st->codec_state[i]);
+#endif
+    st->codec_state[i] = 0;
+  }
+}
+
+int ih_codec_decode(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size, int n_sub,
+                    int n_coupled, float *out, int frame_size) {
+  (void)st; (void)first_sub;
   if (cc->codec == IAMF_CODEC_PCM) return pcm_decode(cc, pkt, pkt_size, n_sub, n_coupled, out, frame_size);
+#ifdef IH_HAVE_OPUS
+  if (cc->codec == IAMF_CODEC_OPUS) return opus_decode_group(st, first_sub, cc, pkt, pkt_size, n_sub, n_coupled, out, frame_size);
+#endif
   return IAMF_ERR_UNIMPLEMENTED;
 }

@@ -150,6 +150,7 @@ typedef struct {
   uint8_t *pkt[IH_MAX_SUBSTREAMS];
   uint32_t pkt_size[IH_MAX_SUBSTREAMS];
   int pkt_count;
+  void *codec_state[IH_MAX_SUBSTREAMS]; /* per sub-stream core decoder (Opus), created on first use */
   uint64_t strim, etrim;
   ih_param_item *mix_gain, *demix, *recon;
   /* recon update delivered with the next frame */
@@ -189,10 +190,9 @@ struct IAMF_Decoder {
   const ih_mix *mix;
   int n_streams;
   ih_stream streams[IAMFB_MAX_ELEMENTS];
-  uint64_t out_gain_pid;
+  ih_param_item *out_gain_item;
   int out_channels;
-  int metadata_dmix;
-  int has_demix_param;
+  IAMF_extradata metadata;
   /* engine */
   iamfb_ctx *ctx;
   iamfb_plan *plan;
@@ -201,11 +201,14 @@ struct IAMF_Decoder {
   float *in[IAMFB_MAX_ELEMENTS];      /* pinned: decoded planar frame of each element */
   float *ramp[IAMFB_MAX_ELEMENTS], *out_ramp;
   uint8_t *pcm_stage;
-  size_t pcm_stage_size;
+  size_t pcm_stage_size;               /* bytes per stream */
+  iamfb_frame_params *fp_stage;
+  int32_t *counts_stage;
+  uint8_t *grp_flags;                  /* group leader: per member, which gain ramps it supplied this step */
   int frame_size;
   /* batch extension: handles stepping together share the engine of the group leader */
   struct IAMF_Decoder *leader;
-  int group_size, group_index;
+  int group_owner, group_size, group_index;
 };
 
 /* iamf_obu_parse.c */
@@ -233,7 +236,8 @@ int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rat
 /* iamf_codec.c */
 int ih_codec_supported(int codec);
 /* decodes the packets of `n_sub` substreams (the first n_coupled are stereo) into planar float; returns samples */
-int ih_codec_decode(const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size, int n_sub, int n_coupled,
-                    float *out, int frame_size);
+int ih_codec_decode(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size,
+                    int n_sub, int n_coupled, float *out, int frame_size);
+void ih_codec_close(ih_stream *st);
 
 #endif

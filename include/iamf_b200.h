@@ -134,7 +134,8 @@ typedef struct iamfb_frame_params {
     float mix_gain;             /* element mix gain (linear) when no ramp array is supplied */
   } el[IAMFB_MAX_ELEMENTS];
   float out_gain;               /* output mix gain (linear) when no ramp array is supplied */
-  uint16_t trim_start, trim_end;/* samples trimmed from this frame (OBU trimming, codec delay 0) */
+  uint16_t trim_start, trim_end;/* samples trimmed from this frame (OBU trimming, codec delay 0);
+                                   trim_start == 0xFFFF: the stream has NO frame in this step (its state is untouched) */
 } iamfb_frame_params;
 
 typedef struct iamfb_ctx iamfb_ctx;

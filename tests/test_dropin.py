@@ -1,0 +1,203 @@
+"""The drop-in boundary: iac_b200/libiamf.so exports the reference's public API (include/IAMF_decoder.h) on top of the
+CUDA engine.
+
+CPU (`-m "not gpu"`): the library loads, exports every public symbol, setters behave like the reference's, and - with
+no GPU - configure fails loudly instead of falling back to a CPU renderer.
+GPU (`-m gpu`): driven through the public API exactly like the compiled reference was when tests/golden/*.npz were
+made, it returns the same per-call sample counts and byte-identical PCM; the UNMODIFIED stock iamfplayer linked against
+it writes the same WAV files as the one linked against the reference; the additive batch call steps many handles in one
+launch with the same results.
+"""
+import ctypes as C
+import glob
+import importlib.util
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import iamfapi
+import iamfgen as G
+import refstreams
+import scenarios as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIBIAMF = os.path.join(ROOT, "iac_b200", "libiamf.so")
+PLAYER_OURS = os.path.join(ROOT, "oracle", "_ref", "iamfplayer_b200")
+PLAYER_REF = os.path.join(ROOT, "oracle", "_ref", "iamfplayer_ref")
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+MG = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(MG)
+
+PUBLIC = ["IAMF_decoder_open", "IAMF_decoder_close", "IAMF_decoder_configure", "IAMF_decoder_decode",
+          "IAMF_decoder_set_mix_presentation_id", "IAMF_decoder_output_layout_set_sound_system",
+          "IAMF_decoder_output_layout_set_binaural", "IAMF_layout_sound_system_channels_count",
+          "IAMF_layout_binaural_channels_count", "IAMF_decoder_get_codec_capability",
+          "IAMF_decoder_set_normalization_loudness", "IAMF_decoder_set_bit_depth", "IAMF_decoder_peak_limiter_enable",
+          "IAMF_decoder_peak_limiter_set_threshold", "IAMF_decoder_peak_limiter_get_threshold",
+          "IAMF_decoder_set_sampling_rate", "IAMF_decoder_get_stream_info", "IAMF_decoder_set_pts",
+          "IAMF_decoder_get_last_metadata", "IAMF_decoder_decode_batch"]
+
+
+def test_library_exports_the_public_api():
+    L = C.CDLL(LIBIAMF, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    for name in PUBLIC:
+        assert hasattr(L, name), name
+    # nothing internal leaks out
+    out = subprocess.run(["nm", "-D", "--defined-only", LIBIAMF], capture_output=True, text=True).stdout
+    assert " ih_" not in out and "iamfb_" not in out
+
+
+def test_setters_and_tables_match_the_reference_conventions():
+    L = C.CDLL(LIBIAMF, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    L.IAMF_decoder_open.restype = C.c_void_p
+    L.IAMF_decoder_peak_limiter_get_threshold.restype = C.c_float
+    L.IAMF_decoder_get_codec_capability.restype = C.c_void_p
+    vp = C.c_void_p
+    for f in ("IAMF_decoder_close", "IAMF_decoder_output_layout_set_binaural"):
+        getattr(L, f).argtypes = [vp]
+    L.IAMF_decoder_set_sampling_rate.argtypes = [vp, C.c_uint32]
+    L.IAMF_decoder_output_layout_set_sound_system.argtypes = [vp, C.c_int]
+    L.IAMF_decoder_peak_limiter_get_threshold.argtypes = [vp]
+    L.IAMF_decoder_decode.argtypes = [vp, C.c_char_p, C.c_int32, C.POINTER(C.c_uint32), vp]
+    # IAMF_decoder.c:208-219,3998-4008
+    assert [L.IAMF_layout_sound_system_channels_count(i) for i in range(13)] == [2, 6, 8, 10, 11, 12, 14, 24, 8, 12, 10, 6, 1]
+    assert L.IAMF_layout_sound_system_channels_count(13) == -1 and L.IAMF_layout_binaural_channels_count() == 2
+    h = L.IAMF_decoder_open()
+    assert h
+    assert L.IAMF_decoder_peak_limiter_get_threshold(h) == -1.0            # LIMITER_MaximumTruePeak
+    assert L.IAMF_decoder_set_sampling_rate(h, 44100) == 0
+    assert L.IAMF_decoder_set_sampling_rate(h, 12345) == -1                # IAMF_ERR_BAD_ARG
+    assert L.IAMF_decoder_output_layout_set_sound_system(h, 99) == -1
+    assert L.IAMF_decoder_output_layout_set_sound_system(h, 1) == 0
+    buf = C.create_string_buffer(64)
+    assert L.IAMF_decoder_decode(h, b"\x00", 1, None, buf) == -5           # IAMF_ERR_INVALID_STATE before configure
+    cap = C.string_at(L.IAMF_decoder_get_codec_capability())
+    assert b"iamf.001.001.ipcm" in cap
+    L.IAMF_decoder_close(h)
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU behaviour")
+def test_configure_fails_loudly_without_a_gpu():
+    """no CPU rendering path: descriptors parse, then the engine cannot be created -> IAMF_ERR_INTERNAL"""
+    L = C.CDLL(LIBIAMF, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    L.IAMF_decoder_open.restype = C.c_void_p
+    L.IAMF_decoder_configure.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.IAMF_decoder_output_layout_set_sound_system.argtypes = [C.c_void_p, C.c_int]
+    L.IAMF_decoder_set_bit_depth.argtypes = [C.c_void_p, C.c_uint32]
+    L.IAMF_decoder_close.argtypes = [C.c_void_p]
+    st = G.cfg_stereo()
+    x = np.zeros((2, 960), np.int16)
+    blob = st.descriptors() + st.temporal_unit([x])
+    h = L.IAMF_decoder_open()
+    L.IAMF_decoder_output_layout_set_sound_system(h, 0)
+    L.IAMF_decoder_set_bit_depth(h, 16)
+    r = C.c_uint32(0)
+    assert L.IAMF_decoder_configure(h, blob, len(blob), C.byref(r)) == -3    # IAMF_ERR_INTERNAL
+    assert r.value == len(st.descriptors())                                  # the descriptors themselves parsed
+    L.IAMF_decoder_close(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("entry", MG.CASES, ids=[c[0] for c in MG.CASES])
+def test_dropin_reproduces_reference_fixture(entry):
+    name, case, kw, n_streams, n_frames, seed_in, seed_p = entry
+    fx = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    sc, st, api_kw, unit_kw, inputs, P, _, _ = MG.build_case(case, kw, n_streams, n_frames, seed_in, seed_p)
+    api = iamfapi.Api(LIBIAMF)
+    for s in range(n_streams):
+        units = refstreams.temporal_units(sc, st, inputs, P, unit_kw, s)
+        pcm, counts = api.render(st.descriptors(), units, **api_kw)
+        assert counts == [int(c) for c in fx[f"counts{s}"]], f"{name}: stream {s} per-call sample counts"
+        assert pcm.tobytes() == fx[f"pcm{s}"].tobytes(), f"{name}: stream {s} PCM differs from the reference decoder"
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(PLAYER_OURS) and os.path.exists(PLAYER_REF)), reason="players not built (make -C oracle ref)")
+@pytest.mark.parametrize("case,args", [("c1", ["-o2", "-s0"]), ("c2", ["-o2", "-s1"]), ("c4", ["-o2", "-sb"]),
+                                       ("c5", ["-o2", "-s0", "-r", "48000", "-l", "-24"]), ("c3", ["-o2", "-s7", "-d", "24"])])
+def test_stock_iamfplayer_writes_identical_wav(case, args):
+    """the unmodified player (compiled against the reference's headers) linked against our libiamf.so vs the reference's"""
+    sc, st, api_kw, unit_kw = refstreams.case(case)
+    F = 12
+    inputs = S.synth_inputs(sc, 1, F, seed=77)
+    P, _, _ = S.synth_params(sc, 1, F, seed=78)
+    refstreams.no_param_gaps(sc, P)
+    blob = st.descriptors() + b"".join(refstreams.temporal_units(sc, st, inputs, P, unit_kw, 0))
+    outs = []
+    for player in (PLAYER_REF, PLAYER_OURS):
+        d = tempfile.mkdtemp(prefix="iamfplayer_")
+        try:
+            with open(os.path.join(d, "in.iamf"), "wb") as f:
+                f.write(blob)
+            r = subprocess.run([player] + args + ["in.iamf"], cwd=d, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            wavs = glob.glob(os.path.join(d, "*.wav"))
+            assert len(wavs) == 1, (wavs, r.stdout[-500:])
+            outs.append(open(wavs[0], "rb").read())
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    assert len(outs[0]) > 44 + 1000
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_decode_batch_matches_per_handle_decode():
+    """IAMF_decoder_decode_batch: 9 handles of configuration 2 step together; same bytes as one handle at a time"""
+    sc, st, api_kw, unit_kw = refstreams.case("c2")
+    n, F = 9, 7
+    inputs = S.synth_inputs(sc, n, F, seed=31)
+    P, _, _ = S.synth_params(sc, n, F, seed=32)
+    refstreams.no_param_gaps(sc, P)
+    desc = st.descriptors()
+    units = [refstreams.temporal_units(sc, st, inputs, P, unit_kw, s) for s in range(n)]
+    api = iamfapi.Api(LIBIAMF)
+    single = [api.render(desc, units[s], **api_kw) for s in range(n)]
+
+    L = api.L
+    vp = C.c_void_p
+    L.IAMF_decoder_decode_batch.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_int)]
+    hs = (vp * n)()
+    ch = 6
+    for s in range(n):
+        h = L.IAMF_decoder_open()
+        L.IAMF_decoder_peak_limiter_set_threshold(h, -1.0)
+        L.IAMF_decoder_set_bit_depth(h, 16)
+        L.IAMF_decoder_output_layout_set_sound_system(h, 1)
+        blob = desc + units[s][0]
+        r = C.c_uint32(0)
+        assert L.IAMF_decoder_configure(h, blob, len(blob), C.byref(r)) == 0
+        hs[s] = h
+    bufs = [C.create_string_buffer(2 * 6144 * ch) for _ in range(n)]
+    pcm = (vp * n)(*[C.cast(b, vp) for b in bufs])
+    got = [[] for _ in range(n)]
+    counts = [[] for _ in range(n)]
+    for f in range(F + 1):
+        data = (C.c_char_p * n)(*[(units[s][f] if f < F else None) for s in range(n)])
+        size = (C.c_int32 * n)(*[(len(units[s][f]) if f < F else 0) for s in range(n)])
+        rs = (C.c_uint32 * n)()
+        ret = (C.c_int * n)()
+        assert L.IAMF_decoder_decode_batch(hs, n, data, size, rs, pcm, ret) == 0
+        for s in range(n):
+            counts[s].append(ret[s])
+            if ret[s] > 0:
+                got[s].append(bufs[s].raw[: ret[s] * ch * 2])
+    for s in range(n):
+        assert counts[s] == single[s][1]
+        assert b"".join(got[s]) == single[s][0].tobytes()
+        L.IAMF_decoder_close(hs[s])
