@@ -65,7 +65,7 @@ def frame_params_array(n_streams, n_frames):
 
 class Io(C.Structure):
     _fields_ = [("in_", C.c_void_p * MAXE), ("params", C.c_void_p), ("gain_ramp", C.c_void_p * MAXE),
-                ("out_gain_ramp", C.c_void_p), ("pcm", C.c_void_p), ("out_counts", C.c_void_p)]
+                ("out_gain_ramp", C.c_void_p), ("pcm", C.c_void_p), ("out_counts", C.c_void_p), ("in_format", C.c_int32)]
 
 
 _lib = None
@@ -255,8 +255,10 @@ class Engine:
         F = params.shape[1]
         io = Io()
         keep = []
+        s16 = all(np.asarray(x).dtype == np.int16 for x in inputs)     # int16 in -> scaled by 1/32768 on the device
+        io.in_format = 1 if s16 else 0
         for e, x in enumerate(inputs):
-            x = np.ascontiguousarray(x, np.float32)
+            x = np.ascontiguousarray(x, np.int16 if s16 else np.float32)
             keep.append(x)
             io.in_[e] = x.ctypes.data
         if gain_ramps:

@@ -103,6 +103,8 @@ struct KernelTimer {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
+constexpr int kMaxChunks = 8;
+
 struct iamfb_ctx {
   int device;
   cudaStream_t stream;
@@ -115,6 +117,10 @@ struct iamfb_ctx {
   // neighbouring sub-chunks; ordered against the main stream with events
   cudaStream_t aux;
   cudaEvent_t ev_w[kMaxSub], ev_s[kMaxSub];
+  // host-resident submits: copy engines run on their own streams so that the upload of one group of streams, the
+  // kernels of the previous group and the download of the one before overlap (PCIe is full duplex)
+  cudaStream_t h2d, d2h;
+  cudaEvent_t ev_up[kMaxChunks], ev_done[kMaxChunks], ev_free;
 };
 
 // optional per-kernel CUDA-event timing (bench.py's roofline leg); events are recorded on the launching stream
@@ -175,6 +181,7 @@ struct iamfb_batch {
   float *d_hist_y, *d_hist_pk;   // fused path: limiter delay line / peak ring carried between submits
   // staging for the host-resident path
   float *d_in[kMaxEl];
+  int16_t *d_in16[kMaxEl];   // int16 uploads (IAMFB_IN_S16), widened to d_in on the device
   float *d_ramp[kMaxEl];
   float *d_oramp;
   iamfb_frame_params *d_params;
@@ -210,6 +217,13 @@ extern "C" int iamfb_ctx_create(int device, iamfb_ctx **out) {
     CU(cudaEventCreateWithFlags(&c->ev_w[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_s[i], cudaEventDisableTiming));
   }
+  CU(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < kMaxChunks; ++i) {
+    CU(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
   *out = c;
   return IAMFB_OK;
 }
@@ -232,7 +246,11 @@ extern "C" void iamfb_ctx_destroy(iamfb_ctx *c) {
   if (!c) return;
   if (c->own_stream) cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->aux);
+  cudaStreamDestroy(c->h2d);
+  cudaStreamDestroy(c->d2h);
   for (int i = 0; i < kMaxSub; ++i) { cudaEventDestroy(c->ev_w[i]); cudaEventDestroy(c->ev_s[i]); }
+  for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); }
+  cudaEventDestroy(c->ev_free);
   delete c;
 }
 
@@ -898,7 +916,11 @@ extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, 
 }
 
 static void free_staging(iamfb_batch *b) {
-  for (int e = 0; e < kMaxEl; ++e) { cudaFree(b->d_in[e]); cudaFree(b->d_ramp[e]); b->d_in[e] = b->d_ramp[e] = nullptr; }
+  for (int e = 0; e < kMaxEl; ++e) {
+    cudaFree(b->d_in[e]); cudaFree(b->d_ramp[e]); cudaFree(b->d_in16[e]);
+    b->d_in[e] = b->d_ramp[e] = nullptr;
+    b->d_in16[e] = nullptr;
+  }
   cudaFree(b->d_oramp); cudaFree(b->d_params); cudaFree(b->d_pcm); cudaFree(b->d_counts);
   b->d_oramp = nullptr; b->d_params = nullptr; b->d_pcm = nullptr; b->d_counts = nullptr;
   b->stage_frames = 0;
@@ -976,24 +998,30 @@ static int n_subchunks(const KernelPlan &kp, int F, bool flush) {
   return n;
 }
 
-static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, void *pcm, int32_t *counts, size_t stride) {
+// runs the kernels of one submit (or flush) for the streams [s_lo, s_lo + s_cnt) of the batch; all pointers in `io`,
+// `pcm` and `counts` are DEVICE pointers to the whole batch's arrays (stream 0 first)
+static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, void *pcm, int32_t *counts, size_t stride,
+                        int s_lo = 0, int s_cnt = -1) {
   iamfb_plan *p = b->plan;
   iamfb_ctx *ctx = p->ctx;
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
-  const int S = b->S, N = kp.frame_size, co = kp.out_channels;
-  const int n_sub = n_subchunks(kp, F, flush);
+  if (s_cnt < 0) s_cnt = b->S;
+  const int S = s_cnt, N = kp.frame_size, co = kp.out_channels;
+  if (!p->fused && (s_lo != 0 || s_cnt != b->S)) return fail(IAMFB_ERR_INTERNAL, "stream ranges need the fused path");
+  const int n_sub = p->fused ? 1 : n_subchunks(kp, F, flush);
   int sub_frame[kMaxSub + 1];
   for (int c = 0; c <= kMaxSub; ++c) sub_frame[c] = flush ? 0 : (c >= n_sub ? F : (int)((long long)F * c / n_sub));
+  const size_t fF = flush ? 0 : (size_t)F;   // frames per stream in the per-frame arrays of this call
 
   // K0
   {
     ResolveArgs a;
-    a.params = flush ? nullptr : io->params;
-    a.state = b->d_state;
-    a.frames = b->d_frames;
-    a.submit = b->d_submit;
-    a.out_counts = counts;
+    a.params = flush ? nullptr : io->params + (size_t)s_lo * fF;
+    a.state = b->d_state + s_lo;
+    a.frames = b->d_frames + (size_t)s_lo * fF;
+    a.submit = b->d_submit + s_lo;
+    a.out_counts = counts ? counts + (size_t)s_lo * (flush ? 1 : fF) : nullptr;
     a.qf_table = p->d_qf;
     a.n_streams = S;
     a.n_frames = flush ? 0 : F;
@@ -1007,17 +1035,20 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     FusedArgs fa;
     memset(&fa, 0, sizeof(fa));
     if (!flush)
-      for (int e = 0; e < kp.n_elements; ++e) { fa.in[e] = io->in[e]; fa.gain_ramp[e] = io->gain_ramp[e]; }
-    fa.out_gain_ramp = flush ? nullptr : io->out_gain_ramp;
-    fa.frames = b->d_frames;
+      for (int e = 0; e < kp.n_elements; ++e) {
+        fa.in[e] = io->in[e] + (size_t)s_lo * fF * kp.el[e].n_in * N;
+        fa.gain_ramp[e] = io->gain_ramp[e] ? io->gain_ramp[e] + (size_t)s_lo * fF * N : nullptr;
+      }
+    fa.out_gain_ramp = (flush || !io->out_gain_ramp) ? nullptr : io->out_gain_ramp + (size_t)s_lo * fF * N;
+    fa.frames = b->d_frames + (size_t)s_lo * fF;
     fa.start_win = p->d_start_win;
     fa.stop_win = p->d_stop_win;
-    fa.submit = b->d_submit;
-    fa.state = b->d_state;
+    fa.submit = b->d_submit + s_lo;
+    fa.state = b->d_state + s_lo;
     fa.acc = p->d_acc;
-    fa.hist_y = b->d_hist_y;
-    fa.hist_pk = b->d_hist_pk;
-    fa.pcm = pcm;
+    fa.hist_y = b->d_hist_y ? b->d_hist_y + (size_t)s_lo * co * kLimDelay : nullptr;
+    fa.hist_pk = b->d_hist_pk ? b->d_hist_pk + (size_t)s_lo * kLimDelay : nullptr;
+    fa.pcm = (char *)pcm + (size_t)s_lo * stride;
     fa.stride_bytes = stride;
     fa.n_frames = flush ? 0 : F;
     fa.flush = flush ? 1 : 0;
@@ -1185,6 +1216,7 @@ extern "C" int iamfb_batch_submit_device(iamfb_batch *b, const iamfb_io *io, int
   for (int e = 0; e < b->plan->kp.n_elements; ++e)
     if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
   if (!io->params || !io->pcm) return fail(IAMFB_ERR_BAD_ARG, "submit: params / pcm is null");
+  if (io->in_format != IAMFB_IN_F32) return fail(IAMFB_ERR_BAD_ARG, "submit_device takes float32 input (in_format %d)", io->in_format);
   CU(cudaSetDevice(b->plan->ctx->device));
   return run_pipeline(b, io, n_frames, false, io->pcm, io->out_counts, iamfb_plan_out_stride_bytes(b->plan, n_frames));
 }
@@ -1208,6 +1240,7 @@ static int ensure_staging(iamfb_batch *b, int F) {
   auto alloc = [&](void **ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
   for (int el = 0; el < kp.n_elements; ++el) {
     alloc((void **)&b->d_in[el], sizeof(float) * S * F * kp.el[el].n_in * N);
+    alloc((void **)&b->d_in16[el], sizeof(int16_t) * S * F * kp.el[el].n_in * N);
     alloc((void **)&b->d_ramp[el], sizeof(float) * S * F * N);
   }
   alloc((void **)&b->d_oramp, sizeof(float) * S * F * N);
@@ -1219,41 +1252,106 @@ static int ensure_staging(iamfb_batch *b, int F) {
   return IAMFB_OK;
 }
 
+// int16 -> float32 * 2^-15 (the codec glue's scaling, opus/IAMF_opus_decoder.c:133-135); 8 samples per thread
+__global__ void __launch_bounds__(256) k_widen_s16(const int16_t *__restrict__ src, float *__restrict__ dst, size_t n8, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n8) {
+    const int4 v = reinterpret_cast<const int4 *>(src)[i];
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = (float)(short)(w[k] & 0xffff) / 32768.f;
+      o[2 * k + 1] = (float)(short)(w[k] >> 16) / 32768.f;
+    }
+    reinterpret_cast<float4 *>(dst)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4 *>(dst)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else if (i == n8) {
+    for (size_t k = n8 * 8; k < n; ++k) dst[k] = (float)src[k] / 32768.f;
+  }
+}
+
 extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F) {
   if (!b || !io) return fail(IAMFB_ERR_BAD_ARG, "submit: null argument");
   if (F <= 0 || F > b->Fmax) return fail(IAMFB_ERR_BAD_ARG, "submit: %d frames (batch sized for %d)", F, b->Fmax);
   if (!io->params || !io->pcm) return fail(IAMFB_ERR_BAD_ARG, "submit: params / pcm is null");
+  if (io->in_format != IAMFB_IN_F32 && io->in_format != IAMFB_IN_S16) return fail(IAMFB_ERR_BAD_ARG, "submit: in_format %d", io->in_format);
   iamfb_plan *p = b->plan;
-  CU(cudaSetDevice(p->ctx->device));
+  iamfb_ctx *ctx = p->ctx;
+  CU(cudaSetDevice(ctx->device));
   int r = ensure_staging(b, F);
   if (r) return r;
   const KernelPlan &kp = p->kp;
-  cudaStream_t st = p->ctx->stream;
+  cudaStream_t st = ctx->stream;
   const size_t S = b->S, N = kp.frame_size;
+  const bool s16 = io->in_format == IAMFB_IN_S16;
+  for (int e = 0; e < kp.n_elements; ++e)
+    if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
   iamfb_io dio;
   memset(&dio, 0, sizeof(dio));
-  for (int e = 0; e < kp.n_elements; ++e) {
-    if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
-    CU(cudaMemcpyAsync(b->d_in[e], io->in[e], sizeof(float) * S * F * kp.el[e].n_in * N, cudaMemcpyHostToDevice, st));
-    dio.in[e] = b->d_in[e];
-    if (io->gain_ramp[e]) {
-      CU(cudaMemcpyAsync(b->d_ramp[e], io->gain_ramp[e], sizeof(float) * S * F * N, cudaMemcpyHostToDevice, st));
-      dio.gain_ramp[e] = b->d_ramp[e];
-    }
-  }
-  if (io->out_gain_ramp) {
-    CU(cudaMemcpyAsync(b->d_oramp, io->out_gain_ramp, sizeof(float) * S * F * N, cudaMemcpyHostToDevice, st));
-    dio.out_gain_ramp = b->d_oramp;
-  }
-  CU(cudaMemcpyAsync(b->d_params, io->params, sizeof(iamfb_frame_params) * S * F, cudaMemcpyHostToDevice, st));
+  for (int e = 0; e < kp.n_elements; ++e) dio.in[e] = b->d_in[e];
   dio.params = b->d_params;
   dio.pcm = b->d_pcm;
   dio.out_counts = b->d_counts;
   const size_t stride = iamfb_plan_out_stride_bytes(p, F);
-  r = run_pipeline(b, &dio, F, false, b->d_pcm, b->d_counts, stride);
-  if (r) return r;
-  CU(cudaMemcpyAsync(io->pcm, b->d_pcm, S * stride, cudaMemcpyDeviceToHost, st));
-  if (io->out_counts) CU(cudaMemcpyAsync(io->out_counts, b->d_counts, sizeof(int32_t) * S * F, cudaMemcpyDeviceToHost, st));
+  // groups of streams flow through upload -> kernels -> download on three streams; the fused path can run any stream
+  // range, the multi-kernel path runs the batch as one group
+  int n_chunks = 1;
+  if (p->fused && S >= 64) {
+    const char *env = getenv("IAMFB_HOST_CHUNKS");
+    n_chunks = env ? atoi(env) : 4;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > kMaxChunks) n_chunks = kMaxChunks;
+  }
+  // the staging buffers are reused by every submit: uploads must not start before the previous submit's kernels are done
+  CU(cudaEventRecord(ctx->ev_free, st));
+  CU(cudaStreamWaitEvent(ctx->h2d, ctx->ev_free, 0));
+  // rare whole-batch arrays first
+  for (int e = 0; e < kp.n_elements; ++e)
+    if (io->gain_ramp[e]) {
+      CU(cudaMemcpyAsync(b->d_ramp[e], io->gain_ramp[e], sizeof(float) * S * F * N, cudaMemcpyHostToDevice, ctx->h2d));
+      dio.gain_ramp[e] = b->d_ramp[e];
+    }
+  if (io->out_gain_ramp) {
+    CU(cudaMemcpyAsync(b->d_oramp, io->out_gain_ramp, sizeof(float) * S * F * N, cudaMemcpyHostToDevice, ctx->h2d));
+    dio.out_gain_ramp = b->d_oramp;
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t s_lo = S * c / n_chunks, s_hi = S * (c + 1) / n_chunks, cnt = s_hi - s_lo;
+    if (!cnt) continue;
+    CU(cudaMemcpyAsync(b->d_params + s_lo * F, io->params + s_lo * F, sizeof(iamfb_frame_params) * cnt * F, cudaMemcpyHostToDevice, ctx->h2d));
+    for (int e = 0; e < kp.n_elements; ++e) {
+      const size_t per = (size_t)F * kp.el[e].n_in * N;
+      if (s16)
+        CU(cudaMemcpyAsync(b->d_in16[e] + s_lo * per, (const int16_t *)io->in[e] + s_lo * per, sizeof(int16_t) * cnt * per, cudaMemcpyHostToDevice, ctx->h2d));
+      else
+        CU(cudaMemcpyAsync(b->d_in[e] + s_lo * per, io->in[e] + s_lo * per, sizeof(float) * cnt * per, cudaMemcpyHostToDevice, ctx->h2d));
+    }
+    CU(cudaEventRecord(ctx->ev_up[c], ctx->h2d));
+    CU(cudaStreamWaitEvent(st, ctx->ev_up[c], 0));
+    if (s16) {
+      for (int e = 0; e < kp.n_elements; ++e) {
+        const size_t per = (size_t)F * kp.el[e].n_in * N, n = cnt * per, n8 = n / 8;
+        const size_t off = s_lo * per;
+        if ((off & 7) == 0) {
+          ScopedKernelTimer tm_(ctx, "k_widen_s16");
+          k_widen_s16<<<(unsigned)((n8 + 1 + 255) / 256), 256, 0, st>>>(b->d_in16[e] + off, b->d_in[e] + off, n8, n);
+        } else {
+          ScopedKernelTimer tm_(ctx, "k_widen_s16");
+          k_widen_s16<<<1, 256, 0, st>>>(b->d_in16[e] + off, b->d_in[e] + off, 0, n);   // unaligned group start: scalar
+        }
+        LAUNCH_CHECK("k_widen_s16");
+      }
+    }
+    r = run_pipeline(b, &dio, F, false, b->d_pcm, b->d_counts, stride, (int)s_lo, (int)cnt);
+    if (r) return r;
+    CU(cudaEventRecord(ctx->ev_done[c], st));
+    CU(cudaStreamWaitEvent(ctx->d2h, ctx->ev_done[c], 0));
+    CU(cudaMemcpyAsync((char *)io->pcm + s_lo * stride, b->d_pcm + s_lo * stride, cnt * stride, cudaMemcpyDeviceToHost, ctx->d2h));
+    if (io->out_counts)
+      CU(cudaMemcpyAsync(io->out_counts + s_lo * F, b->d_counts + s_lo * F, sizeof(int32_t) * cnt * F, cudaMemcpyDeviceToHost, ctx->d2h));
+  }
+  CU(cudaStreamSynchronize(ctx->d2h));
   CU(cudaStreamSynchronize(st));
   return IAMFB_OK;
 }

@@ -144,7 +144,8 @@ typedef struct iamfb_batch iamfb_batch;
 
 /* Buffers of one submit.  All pointers are HOST pointers for iamfb_batch_submit_host and DEVICE pointers for
  * iamfb_batch_submit_device.  S = streams of the batch, F = n_frames of this call, N = frame_size.
- *   in[e]          float32 [S][F][n_in(e)][N]   decoded planar frames of element e (never modified)
+ *   in[e]          float32 [S][F][n_in(e)][N]   decoded planar frames of element e (never modified); int16 of the same
+ *                                               shape when in_format == IAMFB_IN_S16
  *   params         iamfb_frame_params [S][F]
  *   gain_ramp[e]   optional float32 [S][F][N]   per-sample element mix gains (animated mix gain), NULL = constants
  *   out_gain_ramp  optional float32 [S][F][N]
@@ -152,6 +153,8 @@ typedef struct iamfb_batch iamfb_batch;
  *   out_counts     int32 [S][F]                 samples per channel produced by each frame (what IAMF_decoder_decode
  *                                               returns for that temporal unit)
  */
+enum { IAMFB_IN_F32 = 0, IAMFB_IN_S16 = 1 };
+
 typedef struct iamfb_io {
   const float *in[IAMFB_MAX_ELEMENTS];
   const iamfb_frame_params *params;
@@ -159,6 +162,10 @@ typedef struct iamfb_io {
   const float *out_gain_ramp;
   void *pcm;
   int32_t *out_counts;
+  int32_t in_format;   /* IAMFB_IN_F32: `in` is float32 as above.  IAMFB_IN_S16: `in` points at int16 with the same
+                          [S][F][n_in][N] shape - what Opus / AAC / 16-bit ipcm core decode produces BEFORE the codec glue
+                          scales it by 1/32768 (opus/IAMF_opus_decoder.c:133-135); the scaling then happens on the
+                          device (exact: a power of two), halving the host-to-device traffic */
 } iamfb_io;
 
 /* ---- context: one per GPU / host thread ---- */

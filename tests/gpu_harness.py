@@ -6,7 +6,7 @@ import scenarios as S
 from iac_b200 import Engine
 
 
-def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0):
+def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0, s16=False):
     n_streams, F = P.shape
     splits = splits or [F]
     assert sum(splits) == F
@@ -18,7 +18,10 @@ def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, 
     f0 = 0
     for n in splits:
         sl = slice(f0, f0 + n)
-        pcm, cnt = eng.submit_host([x[:, sl] for x in inputs], P[:, sl],
+        ins = [x[:, sl] for x in inputs]
+        if s16:   # hand the int16 the codec produced instead of its float scaling (IAMFB_IN_S16)
+            ins = [np.rint(x.astype(np.float64) * 32768.0).astype(np.int16) for x in ins]
+        pcm, cnt = eng.submit_host(ins, P[:, sl],
                                    [r[:, sl] if r is not None else None for r in ramps] if ramps else None,
                                    oramp[:, sl] if oramp is not None else None)
         for s in range(n_streams):

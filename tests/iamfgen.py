@@ -107,12 +107,51 @@ class Element:
         return 300 + self.eid
 
 
+class OpusEncoders:
+    """libopus encoders (one per sub-stream) from oracle/_ref/libopus_ref.so - the reference tree's own prebuilt libopus"""
+    import os as _os
+    SO = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "..", "oracle", "_ref", "libopus_ref.so")
+
+    @classmethod
+    def available(cls):
+        import os
+        return os.path.exists(cls.SO)
+
+    def __init__(self, rate, bitrate=128000):
+        import ctypes as C
+        self.C = C
+        self.L = C.CDLL(self.SO)
+        self.L.opus_encoder_create.restype = C.c_void_p
+        self.L.opus_encoder_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        self.L.opus_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        self.L.opus_encoder_ctl.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.rate, self.bitrate, self.enc = rate, bitrate, {}
+
+    def encode(self, key, x):
+        """x: int16 [channels][n] -> packet bytes"""
+        C = self.C
+        ch = x.shape[0]
+        if key not in self.enc:
+            err = C.c_int(0)
+            e = self.L.opus_encoder_create(self.rate, ch, 2049, C.byref(err))     # OPUS_APPLICATION_AUDIO
+            assert e and err.value == 0
+            self.L.opus_encoder_ctl(e, 4002, self.bitrate * ch // 2)              # OPUS_SET_BITRATE
+            self.enc[key] = e
+        inter = np.ascontiguousarray(x.T).astype(np.int16)
+        buf = C.create_string_buffer(4000)
+        n = self.L.opus_encode(self.enc[key], inter.ctypes.data, x.shape[1], buf, 4000)
+        assert n > 0, n
+        return buf.raw[:n]
+
+
 @dataclass
 class Stream:
     elements: List[Element]
     frame_size: int = 960
     rate: int = 48000
     profile: int = 1
+    codec: str = "ipcm"            # "ipcm" (16-bit little-endian) | "opus" (needs oracle/_ref/libopus_ref.so)
+    _opus: Optional[object] = None
     out_gain_q78: int = 0
     layouts: List[tuple] = field(default_factory=lambda: [("ss", 0, 0)])  # ("ss", sound_system, loudness_q78) | ("bin", 0, q78)
     OUT_GAIN_PID = 400
@@ -120,8 +159,13 @@ class Stream:
     # ---------------------------------------------------------------- descriptors
     def descriptors(self) -> bytes:
         out = obu(OBU_SEQUENCE_HEADER, b"iamf" + bytes([self.profile, self.profile]))
-        # codec config: id 0, ipcm, 16-bit LE
-        cc = leb128(0) + b"ipcm" + leb128(self.frame_size) + s16be(0) + bytes([1, 16]) + struct.pack(">I", self.rate)
+        if self.codec == "opus":
+            # OpusHead-like decoder config, big endian (opus/IAMF_opus_decoder.c:56-99): version, channels(2), pre-skip,
+            # input rate, output gain, mapping family 0
+            cc = leb128(0) + b"Opus" + leb128(self.frame_size) + s16be(-4) + bytes([1, 2]) + struct.pack(">HIhB", 0, self.rate, 0, 0)
+        else:
+            # codec config: id 0, ipcm, 16-bit LE
+            cc = leb128(0) + b"ipcm" + leb128(self.frame_size) + s16be(0) + bytes([1, 16]) + struct.pack(">I", self.rate)
         out += obu(OBU_CODEC_CONFIG, cc)
         for e in self.elements:
             out += obu(OBU_AUDIO_ELEMENT, self._element(e))
@@ -207,12 +251,16 @@ class Stream:
                 [(e.n_substreams, e.ambi_coupled if e.ambi_mode else 0)]
             for nsub, ncoupled in groups:
                 for k in range(nsub):
-                    if k < ncoupled:
+                    nch = 2 if k < ncoupled else 1
+                    if self.codec == "opus":
+                        if self._opus is None:
+                            self._opus = OpusEncoders(self.rate)
+                        payload = self._opus.encode(sid, x[ch:ch + nch])
+                    elif nch == 2:
                         payload = np.ascontiguousarray(x[ch:ch + 2].T).astype("<i2").tobytes()
-                        ch += 2
                     else:
                         payload = x[ch].astype("<i2").tobytes()
-                        ch += 1
+                    ch += nch
                     if sid < 18:
                         out += obu(OBU_AUDIO_FRAME_ID0 + sid, payload, trim_start, trim_end)
                     else:
@@ -223,9 +271,9 @@ class Stream:
 
 
 # -------------------------------------------------------------------- canned configurations (BASELINE.json configs)
-def cfg_stereo(rate=48000, frame_size=960, loud_q78=0):
+def cfg_stereo(rate=48000, frame_size=960, loud_q78=0, codec="ipcm"):
     e = Element(0, "channel", [Layer(STEREO, 1, 1)])
-    return Stream([e], frame_size=frame_size, rate=rate, profile=0, layouts=[("ss", 0, loud_q78)])
+    return Stream([e], frame_size=frame_size, rate=rate, profile=0, layouts=[("ss", 0, loud_q78)], codec=codec)
 
 
 def cfg_714_scalable(two_layer=True):

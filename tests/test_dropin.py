@@ -156,6 +156,23 @@ def test_stock_iamfplayer_writes_identical_wav(case, args):
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not (G.OpusEncoders.available() and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libiamf_ref.so"))),
+                    reason="needs oracle/_ref (libopus_ref.so encoder + compiled reference)")
+def test_opus_coded_stereo_matches_reference():
+    """configuration 1 as named: simple profile, Opus-coded stereo -> sound system A; entropy decode happens in
+    libopus on the host in both libraries, everything after it on the GPU in ours"""
+    import refbind
+    sc = S.c1_stereo(peak_db=(-3.0, 3.0))
+    x = S.synth_inputs(sc, 1, 25, seed=5)[0][0]
+    st = G.cfg_stereo(codec="opus")
+    units = [st.temporal_unit([refstreams.to_i16(x[f])]) for f in range(x.shape[0])]
+    ref_pcm, ref_counts = iamfapi.Api(refbind.REF_SO).render(st.descriptors(), units, sound_system=0)
+    pcm, counts = iamfapi.Api(LIBIAMF).render(st.descriptors(), units, sound_system=0)
+    assert counts == ref_counts
+    assert pcm.tobytes() == ref_pcm.tobytes()
+
+
+@pytest.mark.gpu
 def test_decode_batch_matches_per_handle_decode():
     """IAMF_decoder_decode_batch: 9 handles of configuration 2 step together; same bytes as one handle at a time"""
     sc, st, api_kw, unit_kw = refstreams.case("c2")

@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 ALL = [S.c1_stereo(), S.c2_714_to_B(), S.c3_toa_to_H(), S.c4_714_foa_binaural(), S.c5_resample()] + S.edge_cases()
 
 
-def compare(sc, n_streams, F, splits, seed=0):
+def compare(sc, n_streams, F, splits, seed=0, s16=False):
     from gpu_harness import run_product
     inputs = S.synth_inputs(sc, n_streams, F, seed=0x1A3F + seed)
     P, ramps, oramp = S.synth_params(sc, n_streams, F, seed=0x77 + seed)
-    got, launches = run_product(sc, inputs, P, ramps, oramp, splits=splits)
+    got, launches = run_product(sc, inputs, P, ramps, oramp, splits=splits, s16=s16)
     ref = S.run_oracle(sc, inputs, P, ramps, oramp)
     assert launches > 0
     for s in range(n_streams):
@@ -47,3 +47,17 @@ def test_limiter_heavy_long():
 
 def test_fast_path_quiet_streams():
     compare(S.c1_stereo(peak_db=(-30.0, -20.0)), 64, 10, [10], seed=11)
+
+
+@pytest.mark.parametrize("sc", [S.c2_714_to_B(), S.c4_714_foa_binaural(), S.c5_resample()], ids=["c2", "c4", "c5"])
+def test_int16_upload_and_stream_groups(sc):
+    # int16 input scaled on the device (IAMFB_IN_S16); 200 streams so that the host path pipelines groups of streams
+    compare(sc, 200, 5, [2, 3], seed=21, s16=True)
+
+
+def test_multi_kernel_path_still_bit_exact(monkeypatch):
+    # the fused kernel is the default for these signatures; the multi-kernel path must stay correct behind IAMFB_FUSED=0
+    monkeypatch.setenv("IAMFB_FUSED", "0")
+    compare(S.c2_714_to_B(), 9, 6, [4, 2], seed=3)
+    compare(S.c3_toa_to_H(), 5, 4, [4], seed=4)
+    compare(S.c4_714_foa_binaural(), 7, 6, [1, 5], seed=5)
