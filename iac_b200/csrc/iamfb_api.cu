@@ -773,18 +773,26 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
     }
     if (eligible) {
       const int co = kp.out_channels, H = kp.limiter ? kLimDelay : 0;
-      const int budget = 14080;                                   // floats: 55 KB per block -> 4 blocks per SM
-      int tl_max = (budget - 16 - 2 * kWmPad - (co + 1) * H) / (nin + 1 + co + 6);
-      if (tl_max > 1024) tl_max = 1024;
-      tl_max &= ~3;
-      if (tl_max >= 64) {
+      // floats of shared memory per block for a tile of tl samples (layout in k_fused)
+      auto smem_floats = [&](int tl) { return (size_t)(nin + 1) * tl + (size_t)(co + 1) * (H + tl) + tl + 2 * ((size_t)tl + kWmPad); };
+      // as many blocks (= streams) per SM as possible while a tile still covers >= 240 samples (or the whole frame):
+      // 7, 6, 5, 4, 3 blocks of the 227 KB
+      int tl = 0;
+      for (int blocks = 7; blocks >= 3 && !tl; --blocks) {
+        const int budget = (int)((233472 / blocks - 1024 - 64) / 4);
+        int tl_max = (budget - 2 * kWmPad - (co + 1) * H) / (nin + 1 + co + 1 + 3);
+        if (tl_max > 1024) tl_max = 1024;
+        tl_max &= ~3;
+        if (tl_max < 64) continue;
         const int n_tiles = (kp.frame_size + tl_max - 1) / tl_max;
-        int tl = (kp.frame_size + n_tiles - 1) / n_tiles;
-        tl = (tl + 3) & ~3;
+        int t = (kp.frame_size + n_tiles - 1) / n_tiles;
+        t = (t + 3) & ~3;
+        if (t >= 240 || n_tiles == 1 || blocks == 3) tl = t;
+      }
+      if (tl >= 64) {
         p->fused = true;
         p->fused_tile = tl;
-        p->fused_smem = sizeof(float) * ((size_t)(nin + 1) * tl + (size_t)co * (H + tl) + (H + tl + 16) + 3 * (size_t)tl +
-                                         2 * ((size_t)tl + kWmPad));
+        p->fused_smem = sizeof(float) * smem_floats(tl);
         // staged-row byte offsets and the row-compressed render matrix of the fused kernel
         int row_base = 0;
         for (int e = 0; e < kp.n_elements; ++e) {

@@ -42,7 +42,7 @@ struct FusedArgs {
   int n_frames, flush, tile;
 };
 
-constexpr int kFusedThreads = 128;
+constexpr int kFusedThreads = 64;
 constexpr int kWmPad = 320;     // scratch beyond the tile: 240 history + 64 (widest doubling step) + 16
 
 typedef Vec<4> V4;
@@ -421,27 +421,28 @@ __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float 
 }
 
 template <int L0, int N0, int L1, int N1>
-__global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
+__global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
   extern __shared__ __align__(128) float fsm[];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(16) FrameRec s_fr;      // resolved parameters of the frame being rendered
   __shared__ int s_lim[4];
+  __shared__ int s_next[2];                    // (frame, offset) of the tile after the current one
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // co-resident blocks run their serial scans on different warp schedulers
-  const int scan_warp = (blockIdx.x / 148) & 3;
+  const int scan_warp = (blockIdx.x / 148) % (kFusedThreads / 32);
   const int N = plan.frame_size, co = plan.out_channels;
   const int H = plan.limiter ? kLimDelay : 0;
   const int TL = a.tile;
-  const int rs = H + TL;                        // row stride of the rings (multiple of 4)
+  const int C = H + TL;                         // capacity of the time-line rings (multiple of 4)
   const int nin0 = plan.el[0].n_in, nin1 = N1 > 0 ? plan.el[1].n_in : 0;
   float *IN = fsm;                              // [nin0 + nin1 + 1][TL] staged decoded rows + one all-zero row
-  float *Y = IN + (size_t)(nin0 + nin1 + 1) * TL;   // [co][rs] mixed time line: 240 delayed samples, then the tile
-  float *PK = Y + (size_t)co * rs;              // [rs + 16]
-  float *WM = PK + rs + 16;                     // [TL]
-  float *EW = WM + TL;                          // [TL]
-  float *G = EW + TL;                           // [TL]
-  float *SA = G + TL;                           // [TL + kWmPad]
-  float *SB = SA + TL + kWmPad;                 // [TL + kWmPad]
+  float *Y = IN + (size_t)(nin0 + nin1 + 1) * TL;   // [co][C] mixed time line, circular
+  float *PK = Y + (size_t)co * C;               // [C] per-instant peak, circular
+  float *WM = PK + C;                           // [TL] sliding maximum of the tile's instants
+  float *SA = WM + TL;                          // [TL + kWmPad] scratch; later thr / WM
+  float *SB = SA + TL + kWmPad;                 // [TL + kWmPad] scratch; later the gains
+  float *EW = SA, *G = SB;
 
   const SubmitRec sr = a.submit[s];
   int lj = -1;
@@ -454,17 +455,16 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
 #pragma unroll 1
     for (int c = 0; c <= co; ++c) {
       const float *src = c < co ? a.hist_y + ((size_t)s * co + c) * kLimDelay : a.hist_pk + (size_t)s * kLimDelay;
-      float *row = c < co ? Y + (size_t)c * rs : PK;
+      float *row = c < co ? Y + (size_t)c * C : PK;
       for (int i = tid; i < kLimDelay; i += kFusedThreads) row[i] = src[i];
     }
-    for (int i = tid; i < TL + 16; i += kFusedThreads) PK[H + i] = 0.f;
+    for (int i = tid; i < TL; i += kFusedThreads) PK[H + i] = 0.f;
     for (int i = tid; i < TL + kWmPad; i += kFusedThreads) { SA[i] = 0.f; SB[i] = 0.f; }
   }
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
 
   // ---- tile iterator over (frame, offset): only tiles with at least one sample left after trimming
   const int n_frames = a.flush ? 0 : a.n_frames;
@@ -491,9 +491,11 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
     mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(nin0 + nin1));
     const size_t sf = (size_t)s * a.n_frames + f;
     const float *g0 = a.in[0] + sf * nin0 * N + t_off;
+#pragma unroll 1
     for (int r = 0; r < nin0; ++r) bulk_g2s(IN + (size_t)r * TL, g0 + (size_t)r * N, row_bytes, &s_bar);
     if constexpr (N1 > 0) {
       const float *g1 = a.in[1] + sf * nin1 * N + t_off;
+#pragma unroll 1
       for (int r = 0; r < nin1; ++r) bulk_g2s(IN + (size_t)(nin0 + r) * TL, g1 + (size_t)r * N, row_bytes, &s_bar);
     }
   };
@@ -501,87 +503,121 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
   char *out = (char *)a.pcm + (size_t)s * a.stride_bytes;
   int lim_done = 0;                             // limiter-stage instants of this submit already processed
   uint32_t parity = 0;
-  int f = 0, t_off = -TL;
-  if (n_frames > 0) {
-    advance(f, t_off);
-    if (f < n_frames && tid == 0) issue(f, t_off);
+  int w = H;                                    // ring position of the next tile's first instant (16-byte aligned)
+  if (tid == 0) {
+    int f0 = 0, t0 = -TL;
+    if (n_frames > 0) {
+      advance(f0, t0);
+      if (f0 < n_frames) issue(f0, t0);
+    }
+    s_next[0] = f0; s_next[1] = t0;
   }
+  __syncthreads();
+  int f = s_next[0], t_off = s_next[1];
+  int fr_loaded = -1;
   bool flush_pending = a.flush != 0;
 
   while (f < n_frames || flush_pending) {
-    int n;
+    int n, shift = 0;
     if (flush_pending) {
       // end of stream: the limiter is fed 240 zeros (iamf_delay_buffer_handle, IAMF_decoder.c:3250-3301)
       n = min(kLimDelay - lim_done, TL);
       for (int i = tid; i < n; i += kFusedThreads) {
-        for (int c = 0; c < co; ++c) Y[(size_t)c * rs + H + i] = 0.f;
-        PK[H + i] = 0.f;
+        int pos = w + i;
+        if (pos >= C) pos -= C;
+        for (int c = 0; c < co; ++c) Y[(size_t)c * C + pos] = 0.f;
+        PK[pos] = 0.f;
       }
       if (lim_done + n >= kLimDelay) flush_pending = false;
     } else {
-      int lo_t, hi_t;
-      tile_range(f, t_off, lo_t, hi_t);
-      n = hi_t - lo_t;
       const int sf = s * a.n_frames + f;
+      if (fr_loaded != f) {
+        // this frame's resolved parameters -> shared memory (one coalesced read instead of per-use global loads)
+        const int *src = reinterpret_cast<const int *>(a.frames + sf);
+        int *dst = reinterpret_cast<int *>(&s_fr);
+        for (int i = tid; i < (int)(sizeof(FrameRec) / 4); i += kFusedThreads) dst[i] = src[i];
+        fr_loaded = f;
+        __syncthreads();
+      }
+      const FrameRec &fr = s_fr;
+      const int lo_t = max(t_off, fr.vstart), hi_t = min(min(t_off + TL, N), fr.vstart + fr.vlen);
+      n = hi_t - lo_t;
+      shift = lo_t - t_off;
       // ---------------------------------------------------------------- render (the whole tile, as if untrimmed)
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
-      const FrameRec &fr = a.frames[sf];
       const int t_end = min(t_off + TL, N);
       for (int i0 = t_off + tid * 4; i0 < t_end; i0 += kFusedThreads * 4) {
         const int q = i0 - t_off;                         // position inside the staged tile
-        float *yt = Y + H + q;
-        float *pkt = plan.limiter ? PK + H + q : nullptr;
-        fused_element<L0, N0>(plan, a, 0, fr, sf, i0, true, N1 == 0, IN + q, TL, yt, rs, pkt);
-        if constexpr (N1 > 0) fused_element<L1, N1>(plan, a, 1, fr, sf, i0, false, true, IN + q, TL, yt, rs, pkt);
+        int pos = w + q;
+        if (pos >= C) pos -= C;
+        float *yt = Y + pos;
+        float *pkt = plan.limiter ? PK + pos : nullptr;
+        fused_element<L0, N0>(plan, a, 0, fr, sf, i0, true, N1 == 0, IN + q, TL, yt, C, pkt);
+        if constexpr (N1 > 0) fused_element<L1, N1>(plan, a, 1, fr, sf, i0, false, true, IN + q, TL, yt, C, pkt);
       }
       // a trimmed tile: move its surviving samples [lo_t, hi_t) to the front of the tile (iamf_frame_trim,
       // IAMF_decoder.c:1361-1381); rare (first / last frames), one row at a time through registers
-      const int shift = lo_t - t_off;
       if (shift > 0) {
+#pragma unroll 1
         for (int r = 0; r <= co; ++r) {
           if (r == co && !plan.limiter) break;
-          float *row = (r < co ? Y + (size_t)r * rs : PK) + H;
+          float *row = r < co ? Y + (size_t)r * C : PK;
           __syncthreads();
-          float t[8];
+          float t[1024 / kFusedThreads];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 1024 / kFusedThreads; ++u) {
             const int i = tid + u * kFusedThreads;
-            t[u] = i < n ? row[shift + i] : 0.f;
+            int pos = w + shift + i;
+            if (pos >= C) pos -= C;
+            t[u] = i < n ? row[pos] : 0.f;
           }
           __syncthreads();
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 1024 / kFusedThreads; ++u) {
             const int i = tid + u * kFusedThreads;
-            if (i < n) row[i] = t[u];
+            int pos = w + i;
+            if (pos >= C) pos -= C;
+            if (i < n) row[pos] = t[u];
           }
         }
       }
     }
     __syncthreads();
-    // the staged rows are consumed: start the copy of the next tile under the rest of this one
-    if (!a.flush) {
-      advance(f, t_off);
-      if (f < n_frames && tid == 0) issue(f, t_off);
+    // the staged rows are consumed: one thread finds the next tile and starts its copy under the rest of this one
+    if (!a.flush && tid == 0) {
+      int f2 = f, t2 = t_off;
+      advance(f2, t2);
+      if (f2 < n_frames) issue(f2, t2);
+      s_next[0] = f2; s_next[1] = t2;
     }
+    const bool quads = (n & 3) == 0;           // every instant of the tile sits in a whole aligned quad
     bool apply_gain = false;
     if (plan.limiter) {
       // ---------------------------------------------------------------- sliding maximum over 240 instants
-      // ring index i <-> instant i - 240 relative to the tile; WM[k] = max(PK[k .. k+239]), k < n
-      const int span4 = (n + kLimDelay + 3) >> 2;            // 16-byte items covering the ring
+      // logical index i <-> ring position (w - 240 + i) mod C;  WM[k] = max(PK[k .. k+239]) for k < n
+      const int span4 = (n + kLimDelay + 3) >> 2;            // 16-byte items covering the window
+      int base = w - kLimDelay;
+      if (base < 0) base += C;
       for (int v = tid; v < span4; v += kFusedThreads) {     // windows of 8, in registers
-        const float4 A = *reinterpret_cast<const float4 *>(PK + 4 * v);
-        const float4 B = *reinterpret_cast<const float4 *>(PK + 4 * v + 4);
-        const float4 C = *reinterpret_cast<const float4 *>(PK + 4 * v + 8);
+        int p0 = base + 4 * v;
+        if (p0 >= C) p0 -= C;
+        int p1 = p0 + 4;
+        if (p1 >= C) p1 -= C;
+        int p2 = p1 + 4;
+        if (p2 >= C) p2 -= C;
+        const float4 A = *reinterpret_cast<const float4 *>(PK + p0);
+        const float4 B = *reinterpret_cast<const float4 *>(PK + p1);
+        const float4 Cq = *reinterpret_cast<const float4 *>(PK + p2);
         const float m47 = fmaxf(fmaxf(B.x, B.y), fmaxf(B.z, B.w));
         const float s3 = A.w, s2 = fmaxf(A.z, s3), s1 = fmaxf(A.y, s2), s0 = fmaxf(A.x, s1);
-        const float p9 = fmaxf(C.x, C.y), p10 = fmaxf(p9, C.z);
+        const float p9 = fmaxf(Cq.x, Cq.y), p10 = fmaxf(p9, Cq.z);
         *reinterpret_cast<float4 *>(SA + 4 * v) =
-            make_float4(fmaxf(s0, m47), fmaxf(fmaxf(s1, m47), C.x), fmaxf(fmaxf(s2, m47), p9), fmaxf(fmaxf(s3, m47), p10));
+            make_float4(fmaxf(s0, m47), fmaxf(fmaxf(s1, m47), Cq.x), fmaxf(fmaxf(s2, m47), p9), fmaxf(fmaxf(s3, m47), p10));
       }
       __syncthreads();
       float *src = SA, *dst = SB;
-#pragma unroll
+#pragma unroll 1
       for (int d = 8; d <= 64; d <<= 1) {                    // windows of 16, 32, 64, 128
         for (int v = tid; v < span4; v += kFusedThreads) {
           const float4 A = *reinterpret_cast<const float4 *>(src + 4 * v);
@@ -591,11 +627,12 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
         __syncthreads();
         float *t = src; src = dst; dst = t;
       }
+      // four passes: the windows of 128 are back in SA
       bool hot = false;
       const float thr = plan.lim_thr;
       for (int v = tid; 4 * v < n; v += kFusedThreads) {     // 240 = two overlapping windows of 128
-        const float4 A = *reinterpret_cast<const float4 *>(src + 4 * v);
-        const float4 B = *reinterpret_cast<const float4 *>(src + 4 * v + 112);
+        const float4 A = *reinterpret_cast<const float4 *>(SA + 4 * v);
+        const float4 B = *reinterpret_cast<const float4 *>(SA + 4 * v + 112);
         const float4 W = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
         *reinterpret_cast<float4 *>(WM + 4 * v) = W;
         const int left = n - 4 * v;
@@ -622,27 +659,31 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
     }
     // ------------------------------------------------------------------ output: delayed sample x gain -> PCM
     {
-      const long long base = (long long)lim_done - sr.out_skip;   // output index of instant 0 of this tile
+      const long long base_o = (long long)lim_done - sr.out_skip;   // output index of instant 0 of this tile
       const int bits = plan.bit_depth;
+      int rbase = w - H;                                            // ring position of the delayed instant 0
+      if (rbase < 0) rbase += C;
       for (int k4 = tid * 4; k4 < n; k4 += kFusedThreads * 4) {
-        float g4[4] = {1.f, 1.f, 1.f, 1.f};
-        if (apply_gain) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) if (k4 + u < n) g4[u] = G[k4 + u];
-        }
-        const long long o0 = base + k4;
+        const long long o0 = base_o + k4;
         const bool full = (k4 + 4 <= n) && o0 >= 0;
+        int pos = rbase + k4;
+        if (pos >= C) pos -= C;
         if (full && bits == 16 && (co & 1) == 0 && (((o0 * co) & 1) == 0)) {
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (apply_gain) g4 = *reinterpret_cast<const float4 *>(G + k4);
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+          uint32_t *wq = (uint32_t *)((int16_t *)out + o0 * co);
+          const int half = co >> 1;
+#pragma unroll 1
           for (int c = 0; c < co; c += 2) {
-            const float4 x0 = *reinterpret_cast<const float4 *>(Y + (size_t)c * rs + k4);
-            const float4 x1 = *reinterpret_cast<const float4 *>(Y + (size_t)(c + 1) * rs + k4);
+            const float4 x0 = *reinterpret_cast<const float4 *>(Y + (size_t)c * C + pos);
+            const float4 x1 = *reinterpret_cast<const float4 *>(Y + (size_t)(c + 1) * C + pos);
             const float v0[4] = {x0.x, x0.y, x0.z, x0.w}, v1[4] = {x1.x, x1.y, x1.z, x1.w};
-            uint32_t *w = (uint32_t *)((int16_t *)out + o0 * co + c);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float y0 = v0[u], y1 = v1[u];
-              if (plan.limiter) { y0 = y0 * g4[u]; y1 = y1 * g4[u]; }
-              w[(size_t)u * (co >> 1)] = (uint32_t)(quant16(y0) & 0xffff) | ((uint32_t)quant16(y1) << 16);
+              if (plan.limiter) { y0 = y0 * gg[u]; y1 = y1 * gg[u]; }
+              wq[u * half + (c >> 1)] = (uint32_t)(quant16(y0) & 0xffff) | ((uint32_t)quant16(y1) << 16);
             }
           }
         } else {
@@ -651,7 +692,9 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
 #pragma unroll 1
             for (int u = 0; u < 4; ++u) {
               if (k4 + u >= n || o0 + u < 0) continue;
-              float x = Y[(size_t)c * rs + k4 + u];
+              int pu = pos + u;
+              if (pu >= C) pu -= C;
+              float x = Y[(size_t)c * C + pu];
               if (plan.limiter) x = x * (apply_gain ? G[k4 + u] : 1.0f);
               store_any(out, (size_t)(o0 + u) * co + c, x, bits);
             }
@@ -660,39 +703,53 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused(const __grid_constan
       }
     }
     lim_done += n;
-    // ------------------------------------------------------------------ carry the last 240 instants to the front
-    if (plan.limiter) {
+    // ------------------------------------------------------------------ advance the ring
+    if (quads && shift == 0) {
+      w += n;
+      if (w >= C) w -= C;
+    } else if (plan.limiter) {
+      // an irregular tile (trimmed, or not a multiple of four instants) would leave the ring misaligned: move the
+      // last 240 instants to the front instead and restart at position 240
       __syncthreads();
-      if (n >= kLimDelay && (n & 3) == 0) {
-        // source [n, n+240) and destination [0, 240) do not overlap
+      int from = w + n - kLimDelay;
+      if (from < 0) from += C;
 #pragma unroll 1
-        for (int i = tid; i < (co + 1) * (kLimDelay / 4); i += kFusedThreads) {
-          const int r = i / (kLimDelay / 4), c = (i - r * (kLimDelay / 4)) * 4;
-          float *row = (r < co) ? Y + (size_t)r * rs : PK;
-          *reinterpret_cast<float4 *>(row + c) = *reinterpret_cast<const float4 *>(row + n + c);
+      for (int r = 0; r <= co; ++r) {
+        float *row = (r < co) ? Y + (size_t)r * C : PK;
+        float t[(kLimDelay + kFusedThreads - 1) / kFusedThreads];
+#pragma unroll
+        for (int u = 0; u < (kLimDelay + kFusedThreads - 1) / kFusedThreads; ++u) {
+          const int i = tid + u * kFusedThreads;
+          int pos = from + i;
+          if (pos >= C) pos -= C;
+          t[u] = i < kLimDelay ? row[pos] : 0.f;
         }
-      } else {
-#pragma unroll 1
-        for (int r = 0; r <= co; ++r) {
-          float *row = (r < co) ? Y + (size_t)r * rs : PK;
-          float t0 = 0.f, t1 = 0.f;
-          if (tid < kLimDelay) t0 = row[n + tid];
-          if (tid + kFusedThreads < kLimDelay) t1 = row[n + tid + kFusedThreads];
-          __syncthreads();
-          if (tid < kLimDelay) row[tid] = t0;
-          if (tid + kFusedThreads < kLimDelay) row[tid + kFusedThreads] = t1;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < (kLimDelay + kFusedThreads - 1) / kFusedThreads; ++u) {
+          const int i = tid + u * kFusedThreads;
+          if (i < kLimDelay) row[i] = t[u];
         }
       }
+      w = kLimDelay;
     }
     __syncthreads();
+    if (!a.flush) { f = s_next[0]; t_off = s_next[1]; }
   }
 
   if (plan.limiter) {
+    // the last 240 instants, in time order, are the history of the next submit
+    int from = w - kLimDelay;
+    if (from < 0) from += C;
 #pragma unroll 1
     for (int c = 0; c <= co; ++c) {
       float *dst = c < co ? a.hist_y + ((size_t)s * co + c) * kLimDelay : a.hist_pk + (size_t)s * kLimDelay;
-      const float *row = c < co ? Y + (size_t)c * rs : PK;
-      for (int i = tid; i < kLimDelay; i += kFusedThreads) dst[i] = row[i];
+      const float *row = c < co ? Y + (size_t)c * C : PK;
+      for (int i = tid; i < kLimDelay; i += kFusedThreads) {
+        int pos = from + i;
+        if (pos >= C) pos -= C;
+        dst[i] = row[pos];
+      }
     }
     if (tid == 0) {
       StreamState &st = a.state[s];
