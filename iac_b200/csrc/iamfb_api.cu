@@ -536,8 +536,12 @@ static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &t
       ep.gain_mask |= 1u << ch;
       ep.gain[ch] = ed.out_gain[i];
     }
+    for (int c = 0; c < kChCount; ++c) ep.slot_of[c] = ep.recon_bit[c] = -1;
+    for (int b = 0; b < 12; ++b)
+      if (k_recon_map_host[lay][b]) ep.recon_bit[k_recon_map_host[lay][b]] = (signed char)b;
     for (int m = 0; m < ep.n_rec; ++m) {
       ep.rec_ch[m] = k_layout_order[lay][m];
+      ep.slot_of[ep.rec_ch[m]] = (signed char)m;
       if (!av.channel(ep.rec_ch[m]))
         return fail(IAMFB_ERR_BAD_ARG, "element %d: layout channel %d cannot be reconstructed from the decoded channels", e, ep.rec_ch[m]);
     }
@@ -563,11 +567,10 @@ static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &t
       int fl = recon_flags_default(ed.first_layer_layout, lay);
       int n = 0;
       for (int b = 0; b < 12; ++b)
-        if (fl & (1 << b)) { es.rch[n] = k_recon_map_host[lay][b]; es.rgain[n] = 1.f; ++n; }
-      if (fl) { es.rcount = n; es.rflags = fl; }
+        if (fl & (1 << b)) { es.rgain[k_recon_map_host[lay][b]] = 1.f; ++n; }
+      if (fl) es.rflags = fl;
     }
-    init.re_flags[e] = 0;
-    init.re_count[e] = 0;
+    es.re_flags = 0;
 
     if (ed.use_dmr) {
       if (!valid_dmr_pair(lay, ed.dmr_out_layout))
@@ -1036,7 +1039,7 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     a.flush = flush ? 1 : 0;
     a.n_sub = n_sub;
     for (int c = 0; c <= kMaxSub; ++c) a.sub_frame[c] = sub_frame[c];
-    { ScopedKernelTimer tm_(ctx, "k_resolve"); k_resolve<<<(S + 127) / 128, 128, 0, st>>>(kp, a); }
+    { ScopedKernelTimer tm_(ctx, "k_resolve"); k_resolve<<<(S + 63) / 64, 64, 0, st>>>(kp, a); }
     LAUNCH_CHECK("k_resolve");
   }
   if (p->fused) {

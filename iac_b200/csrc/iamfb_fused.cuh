@@ -106,9 +106,11 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
   // a transmitted channel, with the output gain of dmx_gainup (demixer.c:421-430) applied on the fly
   auto tx = [&](int ch) -> V4 {
     V4 r = lds4(byte_off(in_q, ep.f_src_off[ch]));
-    const float g = ep.f_gain[ch];
+    if ((ep.gain_mask >> ch) & 1u) {
+      const float g = ep.f_gain[ch];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r.v[k] *= g;
+      for (int k = 0; k < 4; ++k) r.v[k] *= g;
+    }
     return r;
   };
   const int mode = ef.mode & 7;
@@ -293,10 +295,13 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
       for (int k = 0; k < 4; ++k) y.v[k] *= eg.v[k];
     }
     float *dst = yt + (size_t)oc * rs;
-    // iamf_mixer_mix, IAMF_decoder.c:2719-2730: acc = 0; acc += e0; acc += e1
+    // iamf_mixer_mix, IAMF_decoder.c:2719-2730: acc = 0; acc += e0; acc += e1.  (0 + e0 == e0 bit for bit unless e0 is
+    // -0, and a sum that started at +0 is never -0 before it is scaled: only a caller-supplied ramp could make it so)
     if (first) {
+      if (gr) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y.v[k] = 0.f + y.v[k];
+        for (int k = 0; k < 4; ++k) y.v[k] = 0.f + y.v[k];
+      }
     } else {
       const V4 p = lds4(dst);
 #pragma unroll
@@ -370,52 +375,51 @@ __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float 
     E = __shfl_sync(0xffffffffu, valid ? ew[k] : 0.f, first);
     j = 0;
     pos += first + 1;
-    // ---- serial burst: the step after a trigger has gain S - acc[1]*(S - E); while it triggers again the state is
-    // (S = that gain, E = thr/peak, j = 0) and the next step has the same form
-    while (pos < n) {
-      const int m = min(kBurst, n - pos);
-      float ps[kBurst], es[kBurst], gs[kBurst];
+    // ---- serial run: the step after a trigger has gain S - acc[1]*(S - E); while it triggers again the state is
+    // (S = that gain, E = thr/peak, j = 0) and the next step has the same form.  Sixteen steps at a time are
+    // evaluated speculatively from 16-byte shared-memory loads when the position is aligned, else one by one.
+    bool running = true;
+    while (running && pos < n) {
+      if ((pos & 3) == 0 && n - pos >= kBurst) {
+        float ps[kBurst], es[kBurst], gs[kBurst];
 #pragma unroll
-      for (int i = 0; i < kBurst; ++i) {
-        const int q = min(pos + i, n - 1);
-        ps[i] = wm[q];
-        es[i] = ew[q];
-      }
-      float s = S, e = E;
-      unsigned tm = 0u;
-#pragma unroll
-      for (int i = 0; i < kBurst; ++i) {
-        const float gi = s - a1 * (s - e);
-        gs[i] = gi;
-        tm |= (ps[i] * gi > thr) ? (1u << i) : 0u;
-        s = gi;
-        e = es[i];
-      }
-      // number of leading steps that all triggered (capped at m)
-      const int lead = min(__ffs(~tm) - 1, m);
-      if (lead == kBurst) {
-#pragma unroll
-        for (int i = 0; i < kBurst; ++i) g[pos + i] = gs[i];
-        S = gs[kBurst - 1];
-        E = es[kBurst - 1];
-        pos += kBurst;
-        continue;
-      }
-#pragma unroll
-      for (int i = 0; i < kBurst; ++i)
-        if (i < lead) {
-          g[pos + i] = gs[i];
-          S = gs[i];
-          E = es[i];
+        for (int i = 0; i < kBurst; i += 4) {
+          const float4 pw = *reinterpret_cast<const float4 *>(wm + pos + i);
+          const float4 pe = *reinterpret_cast<const float4 *>(ew + pos + i);
+          ps[i] = pw.x; ps[i + 1] = pw.y; ps[i + 2] = pw.z; ps[i + 3] = pw.w;
+          es[i] = pe.x; es[i + 1] = pe.y; es[i + 2] = pe.z; es[i + 3] = pe.w;
         }
-      pos += lead;
-      if (lead < m) {
-        // step pos did not trigger: its gain is the curve value one increment after the last trigger
-        g[pos] = S - a1 * (S - E);
-        j = 1;
-        pos += 1;
+        float s = S, e = E;
+        bool all = true;
+#pragma unroll
+        for (int i = 0; i < kBurst; ++i) {
+          const float gi = s - a1 * (s - e);
+          gs[i] = gi;
+          all = all && (ps[i] * gi > thr);
+          s = gi;
+          e = es[i];
+        }
+        if (all) {
+#pragma unroll
+          for (int i = 0; i < kBurst; i += 4)
+            *reinterpret_cast<float4 *>(g + pos + i) = make_float4(gs[i], gs[i + 1], gs[i + 2], gs[i + 3]);
+          S = gs[kBurst - 1];
+          E = es[kBurst - 1];
+          pos += kBurst;
+          continue;
+        }
       }
-      break;
+      // one step
+      const float gi = S - a1 * (S - E);
+      g[pos] = gi;
+      if (wm[pos] * gi > thr) {
+        S = gi;
+        E = ew[pos];
+      } else {
+        j = 1;               // no trigger: the curve continues one increment after the last trigger
+        running = false;
+      }
+      pos += 1;
     }
   }
 }

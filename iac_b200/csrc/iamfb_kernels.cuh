@@ -86,136 +86,164 @@ __device__ __forceinline__ long long rs_outputs_until(const KernelPlan &p, long 
   return (lim * den - 1) / num + 1;
 }
 
-__global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per stream.  Pass 1 walks the frames once per audio element with that element's whole state machine in
+// registers (recon gains are kept per IAChannel, so every array index is a compile-time constant) and writes the
+// element's part of each frame record straight to global memory; pass 2 walks the frames for the stream-level
+// bookkeeping (trimming, time-line placement, sample counts).
+__global__ void __launch_bounds__(64) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.n_streams) return;
-  StreamState st = a.state[s];
+  StreamState &gst = a.state[s];
   const int N = plan.frame_size;
-  int t_off = 0;
-  long long rs_out0 = st.rs_out_total;
-  int pad_at_start = st.lim_pad;
-  int lim_in_total = 0;
-  SubmitRec sr;
-  int sub = 0;
+  const iamfb_frame_params *params = a.params + (size_t)s * a.n_frames;
+  FrameRec *frames = a.frames + (size_t)s * a.n_frames;
 
-  for (int f = 0; f < a.n_frames; ++f) {
-    while (sub <= a.n_sub && a.sub_frame[sub] == f) sr.sub_off[sub++] = lim_in_total;
-    const iamfb_frame_params fp = a.params[(size_t)s * a.n_frames + f];
-    FrameRec fr;
-    if (fp.trim_start == 0xFFFFu) {
-      // "this stream has no frame in this step" (grouped handles stepping together, IAMF_decoder_decode_batch):
-      // nothing is decoded, so no state machine advances and nothing is produced
-      fr.out_gain = 1.f;
-      fr.vstart = 0;
-      fr.vlen = 0;
-      fr.t_off = t_off;
-      a.frames[(size_t)s * a.n_frames + f] = fr;
-      if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = 0;
+  // ---------------------------------------------------------------- pass 1: per element
+  for (int e = 0; e < plan.n_elements; ++e) {
+    const ElPlan &ep = plan.el[e];
+    if (ep.kind != IAMFB_EL_CHANNEL) {
+      for (int f = 0; f < a.n_frames; ++f) {
+        if (params[f].trim_start == 0xFFFFu) continue;
+        ElFrame &ef = frames[f].el[e];
+        ef.gain = params[f].el[e].mix_gain;
+        ef.rmask = 0;
+        ef.mode = 0;
+        ef.w = 0.f;
+      }
       continue;
     }
-    for (int e = 0; e < plan.n_elements; ++e) {
-      const ElPlan &ep = plan.el[e];
-      ElState &es = st.el[e];
-      ElFrame &ef = fr.el[e];
-      ef.gain = fp.el[e].mix_gain;
-      ef.rmask = 0;
-      ef.mode = 0;
-      ef.w = 0.f;
-      ef.dmr_alpha = ef.dmr_beta = ef.dmr_gamma = ef.dmr_delta = ef.dmr_tl = 0.f;
-      for (int m = 0; m < IAMFB_MAX_LAYOUT_CH; ++m) { ef.rlast[m] = 1.f; ef.rcur[m] = 1.f; }
-      if (ep.kind != IAMFB_EL_CHANNEL) continue;
+    ElState &ges = gst.el[e];
+    int mode = ges.mode, w_idx = ges.w_idx, dmr_mode = ges.dmr_mode, dmr_w_idx = ges.dmr_w_idx;
+    float dmr_tl = ges.dmr_tl;
+    unsigned int rflags = ges.rflags, re_flags = ges.re_flags;
+    float rgain[kChCount], re_gain[kChCount], sfavg[kChCount];
+#pragma unroll
+    for (int c = 1; c < kChCount; ++c) { rgain[c] = ges.rgain[c]; re_gain[c] = ges.re_gain[c]; sfavg[c] = ges.sfavg[c]; }
+    const bool tl_derived = !((ep.dmr_in_mask >> IAMFB_CH_TL) & 1u) && !((ep.dmr_in_mask >> IAMFB_CH_TR) & 1u);
 
+    for (int f = 0; f < a.n_frames; ++f) {
+      const iamfb_frame_params &fp = params[f];
+      // "this stream has no frame in this step" (grouped handles stepping together, IAMF_decoder_decode_batch):
+      // nothing is decoded, so no state machine advances
+      if (fp.trim_start == 0xFFFFu) continue;
+      ElFrame &ef = frames[f].el[e];
       // --- recon gain list of the selected layer (latest received wins), IAMF_decoder.c:2238-2274
       if (fp.el[e].has_recon) {
-        unsigned int fl = fp.el[e].recon_flags;
-        if (st.re_flags[e] ^ fl) {
-          st.re_flags[e] = fl;
-          int n = 0;
-          for (int b = 0; b < 12; ++b)
-            if (fl & (1u << b)) st.re_ch[e][n++] = c_recon_map[ep.layout][b];
-          st.re_count[e] = n;
+        const unsigned int fl = fp.el[e].recon_flags;
+        re_flags = fl;
+        const unsigned int g0 = *reinterpret_cast<const unsigned int *>(fp.el[e].recon_gain);
+        const unsigned int g1 = *reinterpret_cast<const unsigned int *>(fp.el[e].recon_gain + 4);
+        const unsigned int g2 = *reinterpret_cast<const unsigned int *>(fp.el[e].recon_gain + 8);
+#pragma unroll
+        for (int c = 1; c < kChCount; ++c) {
+          const int b = ep.recon_bit[c];
+          if (b >= 0 && ((fl >> b) & 1u)) {
+            const int pos = __popc(fl & ((1u << b) - 1u));          // list position = set bits below
+            const unsigned int wsel = pos < 4 ? g0 : (pos < 8 ? g1 : g2);
+            re_gain[c] = a.qf_table[(wsel >> (8 * (pos & 3))) & 0xffu];
+          }
         }
-        for (int c = 0; c < st.re_count[e]; ++c) st.re_gain[e][c] = a.qf_table[fp.el[e].recon_gain[c]];
       }
       // --- demixer_set_recon_gain, demixer.c:621-634 (called every frame when the layer has a recon list)
-      if (ep.recon_present) {
-        unsigned int fl = st.re_flags[e];
-        int cnt = st.re_count[e];
-        if (fl && (fl ^ es.rflags)) {
-          for (int i = 0; i < cnt; ++i) es.rch[i] = st.re_ch[e][i];
-          es.rcount = cnt;
-          es.rflags = fl;
+      if (ep.recon_present && re_flags) {
+        rflags = re_flags;
+#pragma unroll
+        for (int c = 1; c < kChCount; ++c) {
+          const int b = ep.recon_bit[c];
+          if (b >= 0 && ((re_flags >> b) & 1u)) rgain[c] = re_gain[c];
         }
-        for (int i = 0; i < cnt; ++i) es.rgain[i] = st.re_gain[e][i];
       }
       // --- demixer_set_demixing_info(mode, -1), demixer.c:592-619
-      int mode = fp.el[e].dmx_mode;
-      if (mode >= 0 && mode != 3 && mode <= 6) {
-        es.mode = mode;
-        int off = c_mix_woff[mode];
-        es.w_idx = off > 0 ? min(es.w_idx + 1, 10) : max(es.w_idx - 1, 0);
+      const int m_in = fp.el[e].dmx_mode;
+      if (m_in >= 0 && m_in != 3 && m_in <= 6) {
+        mode = m_in;
+        w_idx = c_mix_woff[m_in] > 0 ? min(w_idx + 1, 10) : max(w_idx - 1, 0);
       }
-      ef.mode = es.mode;
-      ef.w = c_w_table[min(max(es.w_idx, 0), 10)];
-      // --- dmx_rms factor update, demixer.c:443-475: sfavg = 0.25*sf + 0.75*last
-      for (int c = 0; c < es.rcount; ++c) {
-        int ch = es.rch[c];
-        float sf = es.rgain[c];
-        float last = es.sfavg[ch];
-        float Nf = 7.f;
-        float sfavg = (2 / (Nf + 1)) * sf + (1 - 2 / (Nf + 1)) * last;
-        for (int m = 0; m < ep.n_rec; ++m)
-          if (ep.rec_ch[m] == ch) {
-            ef.rmask |= 1u << m;
-            ef.rlast[m] = last;
-            ef.rcur[m] = sfavg;
+      ef.mode = mode;
+      ef.w = c_w_table[min(max(w_idx, 0), 10)];
+      ef.gain = fp.el[e].mix_gain;
+      // --- dmx_rms factor update, demixer.c:443-475: sfavg = 0.25*sf + 0.75*last, for every channel of the list
+      unsigned int rmask = 0;
+#pragma unroll
+      for (int c = 1; c < kChCount; ++c) {
+        const int b = ep.recon_bit[c];
+        if (b >= 0 && ((rflags >> b) & 1u)) {
+          const float sf = rgain[c], last = sfavg[c];
+          const float Nf = 7.f;
+          const float cur = (2 / (Nf + 1)) * sf + (1 - 2 / (Nf + 1)) * last;
+          const int slot = ep.slot_of[c];
+          if (slot >= 0) {
+            rmask |= 1u << slot;
+            ef.rlast[slot] = last;
+            ef.rcur[slot] = cur;
           }
-        es.sfavg[ch] = sfavg;
+          sfavg[c] = cur;
+        }
       }
+      ef.rmask = rmask;
       // --- DMRenderer_set_mode_weight(mode, -1), downmix_renderer.c:180-216
       if (ep.renderer == kRdrDMR) {
-        if (mode >= 0 && mode != 3 && mode < 7) {
-          es.dmr_mode = mode;
-          int nw = c_mix_woff[mode] > 0 ? min(es.dmr_w_idx + 1, 10) : max(es.dmr_w_idx - 1, 0);
-          es.dmr_w_idx = nw;
-          bool tl_derived = !((ep.dmr_in_mask >> IAMFB_CH_TL) & 1u) && !((ep.dmr_in_mask >> IAMFB_CH_TR) & 1u);
-          if (tl_derived) es.dmr_tl = c_mix_gamma[mode] * c_w_table[nw];
+        if (m_in >= 0 && m_in != 3 && m_in < 7) {
+          dmr_mode = m_in;
+          dmr_w_idx = c_mix_woff[m_in] > 0 ? min(dmr_w_idx + 1, 10) : max(dmr_w_idx - 1, 0);
+          if (tl_derived) dmr_tl = c_mix_gamma[m_in] * c_w_table[dmr_w_idx];
         }
-        int dm = es.dmr_mode & 7;
+        const int dm = dmr_mode & 7;
         ef.dmr_alpha = c_mix_alpha[dm];
         ef.dmr_beta = c_mix_beta[dm];
         ef.dmr_gamma = c_mix_gamma[dm];
         ef.dmr_delta = c_mix_delta[dm];
-        ef.dmr_tl = es.dmr_tl;
+        ef.dmr_tl = dmr_tl;
       }
+    }
+    ges.mode = mode; ges.w_idx = w_idx; ges.dmr_mode = dmr_mode; ges.dmr_w_idx = dmr_w_idx; ges.dmr_tl = dmr_tl;
+    ges.rflags = rflags; ges.re_flags = re_flags;
+#pragma unroll
+    for (int c = 1; c < kChCount; ++c) { ges.rgain[c] = rgain[c]; ges.re_gain[c] = re_gain[c]; ges.sfavg[c] = sfavg[c]; }
+  }
+
+  // ---------------------------------------------------------------- pass 2: stream-level bookkeeping
+  long long rs_in_total = gst.rs_in_total;
+  const long long rs_out0 = gst.rs_out_total;
+  int lim_pad = gst.lim_pad, lim_init = gst.lim_init;
+  const int pad_at_start = lim_pad;
+  int t_off = 0, lim_in_total = 0, sub = 0;
+  SubmitRec sr;
+  for (int f = 0; f < a.n_frames; ++f) {
+    while (sub <= a.n_sub && a.sub_frame[sub] == f) sr.sub_off[sub++] = lim_in_total;
+    const iamfb_frame_params &fp = params[f];
+    FrameRec &fr = frames[f];
+    if (fp.trim_start == 0xFFFFu) {
+      fr.out_gain = 1.f;
+      fr.vstart = 0;
+      fr.vlen = 0;
+      fr.t_off = t_off;
+      if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = 0;
+      continue;
     }
     fr.out_gain = fp.out_gain;
     // --- trimming: a fully trimmed frame is decoded (state above advances) but dropped, IAMF_decoder.c:3354-3358
-    int ts = fp.trim_start, te = fp.trim_end;
+    const int ts = fp.trim_start, te = fp.trim_end;
     int vlen = N - ts - te;
     if (ts == N || te == N || vlen < 0) vlen = 0;
     fr.vstart = ts;
     fr.vlen = vlen;
     fr.t_off = t_off;
     t_off += vlen;
-    a.frames[(size_t)s * a.n_frames + f] = fr;
-
     // --- per-frame sample count returned to the caller
     int cnt = vlen;
     if (vlen > 0 && plan.resample) {
-      long long before = rs_outputs_until(plan, st.rs_in_total);
-      st.rs_in_total += vlen;
-      long long after = rs_outputs_until(plan, st.rs_in_total);
+      const long long before = rs_outputs_until(plan, rs_in_total);
+      rs_in_total += vlen;
+      const long long after = rs_outputs_until(plan, rs_in_total);
       cnt = (int)(after - before);
     }
-    if (vlen > 0 && plan.limiter) {
+    if (vlen > 0) {
       lim_in_total += cnt;
-      if (!st.lim_init) {
-        if (st.lim_pad >= cnt) { st.lim_pad -= cnt; cnt = 0; }
-        else { cnt -= st.lim_pad; st.lim_pad = 0; st.lim_init = 1; }
+      if (plan.limiter && !lim_init) {
+        if (lim_pad >= cnt) { lim_pad -= cnt; cnt = 0; }
+        else { cnt -= lim_pad; lim_pad = 0; lim_init = 1; }
       }
-    } else if (vlen > 0) {
-      lim_in_total += cnt;
     }
     if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = cnt;
   }
@@ -227,19 +255,19 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelP
     // output latency), then the limiter is fed that tail followed by delaySize zeros.
     int tail = 0;
     if (plan.resample) {
-      long long before = rs_outputs_until(plan, st.rs_in_total);
-      long long after = rs_outputs_until(plan, st.rs_in_total + plan.rs_filt_len / 2);
-      long long lat = ((long long)(plan.rs_filt_len / 2) * plan.rs_den + (plan.rs_num >> 1)) / plan.rs_num;
+      const long long before = rs_outputs_until(plan, rs_in_total);
+      const long long after = rs_outputs_until(plan, rs_in_total + plan.rs_filt_len / 2);
+      const long long lat = ((long long)(plan.rs_filt_len / 2) * plan.rs_den + (plan.rs_num >> 1)) / plan.rs_num;
       tail = (int)min(after - before, lat);
-      st.rs_in_total += plan.rs_filt_len / 2;
+      rs_in_total += plan.rs_filt_len / 2;
     }
     int cnt = tail;
     if (plan.limiter) {
       cnt = tail + kLimDelay;
       lim_in_total = cnt;
-      if (!st.lim_init) {
-        if (st.lim_pad >= cnt) { st.lim_pad -= cnt; cnt = 0; }
-        else { cnt -= st.lim_pad; st.lim_pad = 0; st.lim_init = 1; }
+      if (!lim_init) {
+        if (lim_pad >= cnt) { lim_pad -= cnt; cnt = 0; }
+        else { cnt -= lim_pad; lim_pad = 0; lim_init = 1; }
       }
     } else {
       lim_in_total = cnt;
@@ -250,11 +278,13 @@ __global__ void __launch_bounds__(128) k_resolve(const __grid_constant__ KernelP
   sr.lim_len = lim_in_total;
   for (; sub <= kMaxSub; ++sub) sr.sub_off[sub] = lim_in_total;
   if (a.flush) sr.sub_off[0] = 0;
-  sr.out_skip = pad_at_start - st.lim_pad;
+  sr.out_skip = pad_at_start - lim_pad;
   sr.out_len = lim_in_total - sr.out_skip;
-  st.rs_out_total = rs_out0 + (plan.resample ? (long long)lim_in_total - (a.flush && plan.limiter ? kLimDelay : 0) : 0);
+  gst.rs_in_total = rs_in_total;
+  gst.rs_out_total = rs_out0 + (plan.resample ? (long long)lim_in_total - (a.flush && plan.limiter ? kLimDelay : 0) : 0);
+  gst.lim_pad = lim_pad;
+  gst.lim_init = lim_init;
   a.submit[s] = sr;
-  a.state[s] = st;
 }
 
 // -------------------------------------------------------------------------------------------------------------------

@@ -29,6 +29,8 @@ struct ElPlan {
   float gain[kChCount];
   unsigned char need_s2, need_s3, need_s5, need_s7, need_h2, need_h4;   // derivation chain (demixer.c:127-378)
   unsigned char rec_ch[kMaxRec];   // layout order: slot m -> IAChannel id
+  signed char slot_of[kChCount];   // IAChannel id -> layout slot or -1
+  signed char recon_bit[kChCount]; // IAChannel id -> recon-gain flag bit of this layout or -1 (IAMF_decoder.c:409-448)
   // render matrix, output-major: out n = sum_m mat[n*n_rec + m] * x[m]
   int n_mat_out;
   signed char out_slot[kMaxOut];   // matrix output row -> output channel (H2M LFE slot shift, h2m_rdr.c:1114-1135)
@@ -75,20 +77,18 @@ struct ElState {
   int mode, w_idx;                 // demixer: demixing_mode, weight_state_idx
   int dmr_mode, dmr_w_idx;         // DMRenderer: mode, w_idx
   float dmr_tl;                    // DMRenderer deps[TL][1].s  (gamma * w)
-  unsigned int rflags;             // demixer chs_recon_gain_list.flags
-  int rcount;
-  unsigned char rch[12];
-  float rgain[12];
+  // recon gain, kept PER IAChannel (a list position of the reference maps to a channel through the flag bit order,
+  // IAMF_decoder.c:409-448): the de-mixer's list (demixer.c chs_recon_gain_list) and the latest list received for the
+  // selected layer (ChannelLayerContext conf_s[layer].recon_gain)
+  unsigned int rflags;             // flags of the de-mixer's list
+  unsigned int re_flags;           // flags of the latest received list
+  float rgain[kChCount];           // de-mixer: recon gain of the channel
+  float re_gain[kChCount];         // latest received gain of the channel
   float sfavg[kChCount];           // ch_last_sfavg
 };
 
 struct StreamState {
   ElState el[kMaxEl];
-  // recon "re" (ChannelLayerContext conf_s[layer].recon_gain): latest received list per element
-  unsigned int re_flags[kMaxEl];
-  int re_count[kMaxEl];
-  unsigned char re_ch[kMaxEl][12];
-  float re_gain[kMaxEl][12];
   // resampler (closed form)
   long long rs_in_total;           // input samples supplied so far
   long long rs_out_total;          // outputs emitted so far
