@@ -600,47 +600,116 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
     if (plan.limiter) {
       // ---------------------------------------------------------------- sliding maximum over 240 instants
       // logical index i <-> ring position (w - 240 + i) mod C;  WM[k] = max(PK[k .. k+239]) for k < n
-      const int span4 = (n + kLimDelay + 3) >> 2;            // 16-byte items covering the window
-      int base = w - kLimDelay;
-      if (base < 0) base += C;
-      for (int v = tid; v < span4; v += kFusedThreads) {     // windows of 8, in registers
-        int p0 = base + 4 * v;
-        if (p0 >= C) p0 -= C;
-        int p1 = p0 + 4;
-        if (p1 >= C) p1 -= C;
-        int p2 = p1 + 4;
-        if (p2 >= C) p2 -= C;
-        const float4 A = *reinterpret_cast<const float4 *>(PK + p0);
-        const float4 B = *reinterpret_cast<const float4 *>(PK + p1);
-        const float4 Cq = *reinterpret_cast<const float4 *>(PK + p2);
-        const float m47 = fmaxf(fmaxf(B.x, B.y), fmaxf(B.z, B.w));
-        const float s3 = A.w, s2 = fmaxf(A.z, s3), s1 = fmaxf(A.y, s2), s0 = fmaxf(A.x, s1);
-        const float p9 = fmaxf(Cq.x, Cq.y), p10 = fmaxf(p9, Cq.z);
-        *reinterpret_cast<float4 *>(SA + 4 * v) =
-            make_float4(fmaxf(s0, m47), fmaxf(fmaxf(s1, m47), Cq.x), fmaxf(fmaxf(s2, m47), p9), fmaxf(fmaxf(s3, m47), p10));
-      }
-      __syncthreads();
-      float *src = SA, *dst = SB;
-#pragma unroll 1
-      for (int d = 8; d <= 64; d <<= 1) {                    // windows of 16, 32, 64, 128
-        for (int v = tid; v < span4; v += kFusedThreads) {
-          const float4 A = *reinterpret_cast<const float4 *>(src + 4 * v);
-          const float4 B = *reinterpret_cast<const float4 *>(src + 4 * v + d);
-          *reinterpret_cast<float4 *>(dst + 4 * v) = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
-        }
-        __syncthreads();
-        float *t = src; src = dst; dst = t;
-      }
-      // four passes: the windows of 128 are back in SA
       bool hot = false;
       const float thr = plan.lim_thr;
-      for (int v = tid; 4 * v < n; v += kFusedThreads) {     // 240 = two overlapping windows of 128
-        const float4 A = *reinterpret_cast<const float4 *>(SA + 4 * v);
-        const float4 B = *reinterpret_cast<const float4 *>(SA + 4 * v + 112);
-        const float4 W = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
-        *reinterpret_cast<float4 *>(WM + 4 * v) = W;
-        const int left = n - 4 * v;
-        hot |= (W.x > thr) || (left > 1 && W.y > thr) || (left > 2 && W.z > thr) || (left > 3 && W.w > thr);
+      int base = w - kLimDelay;
+      if (base < 0) base += C;
+      if (n % kLimDelay == 0) {
+        // van Herk / Gil-Werman with blocks of exactly one window: the logical array (240 of history, then the tile)
+        // is cut into blocks B_j of 240; the window starting at 240j + r is the suffix of B_j from r plus the prefix
+        // of B_j+1 up to r-1.  Every block's prefix / suffix maxima come from one warp-wide max-scan (8 instants per
+        // lane, 30 lanes), so the whole stage needs one block barrier.  SA[240j + r] = max(B_j[r ..]),
+        // SB[240j + r] = max(B_j+1[.. r-1]) (0 for r = 0: peaks are >= 0).
+        const int nblk = n / kLimDelay;
+        for (int job = warp; job < 2 * nblk; job += kFusedThreads / 32) {
+          const bool suffix = job < nblk;
+          const int j = suffix ? job : job - nblk + 1;       // block of the logical array
+          float v[8];
+          if (lane < 30) {
+            int p0 = base + j * kLimDelay + 8 * lane;
+            if (p0 >= C) p0 -= C;
+            if (p0 >= C) p0 -= C;
+            int p1 = p0 + 4;
+            if (p1 >= C) p1 -= C;
+            const float4 A = *reinterpret_cast<const float4 *>(PK + p0);
+            const float4 B = *reinterpret_cast<const float4 *>(PK + p1);
+            v[0] = A.x; v[1] = A.y; v[2] = A.z; v[3] = A.w; v[4] = B.x; v[5] = B.y; v[6] = B.z; v[7] = B.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          }
+          if (suffix) {
+#pragma unroll
+            for (int i = 6; i >= 0; --i) v[i] = fmaxf(v[i], v[i + 1]);      // v[i] = max of the lane's instants i..7
+            float t = v[0];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float o = __shfl_down_sync(0xffffffffu, t, d);
+              if (lane + d < 32) t = fmaxf(t, o);
+            }
+            float ex = __shfl_down_sync(0xffffffffu, t, 1);                 // maximum of all later lanes
+            if (lane == 31) ex = 0.f;
+            if (lane < 30) {
+              float *dst = SA + (j * kLimDelay + 8 * lane);
+              *reinterpret_cast<float4 *>(dst) = make_float4(fmaxf(v[0], ex), fmaxf(v[1], ex), fmaxf(v[2], ex), fmaxf(v[3], ex));
+              *reinterpret_cast<float4 *>(dst + 4) = make_float4(fmaxf(v[4], ex), fmaxf(v[5], ex), fmaxf(v[6], ex), fmaxf(v[7], ex));
+            }
+          } else {
+#pragma unroll
+            for (int i = 1; i < 8; ++i) v[i] = fmaxf(v[i], v[i - 1]);       // v[i] = max of the lane's instants 0..i
+            float t = v[7];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const float o = __shfl_up_sync(0xffffffffu, t, d);
+              if (lane >= d) t = fmaxf(t, o);
+            }
+            float ex = __shfl_up_sync(0xffffffffu, t, 1);                   // maximum of all earlier lanes
+            if (lane == 0) ex = 0.f;
+            if (lane < 30) {
+              float *dst = SB + ((j - 1) * kLimDelay + 8 * lane);            // shifted by one: prefix up to r-1
+              *reinterpret_cast<float4 *>(dst) = make_float4(ex, fmaxf(v[0], ex), fmaxf(v[1], ex), fmaxf(v[2], ex));
+              *reinterpret_cast<float4 *>(dst + 4) = make_float4(fmaxf(v[3], ex), fmaxf(v[4], ex), fmaxf(v[5], ex), fmaxf(v[6], ex));
+            }
+          }
+        }
+        __syncthreads();
+        for (int v4 = tid; 4 * v4 < n; v4 += kFusedThreads) {
+          const float4 A = *reinterpret_cast<const float4 *>(SA + 4 * v4);
+          const float4 B = *reinterpret_cast<const float4 *>(SB + 4 * v4);
+          const float4 W = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
+          *reinterpret_cast<float4 *>(WM + 4 * v4) = W;
+          hot |= (W.x > thr) || (W.y > thr) || (W.z > thr) || (W.w > thr);
+        }
+      } else {
+        // any other tile length (trimmed frames, frame sizes that are no multiple of 240): log-step doubling
+        const int span4 = (n + kLimDelay + 3) >> 2;            // 16-byte items covering the window
+        for (int v = tid; v < span4; v += kFusedThreads) {     // windows of 8, in registers
+          int p0 = base + 4 * v;
+          if (p0 >= C) p0 -= C;
+          int p1 = p0 + 4;
+          if (p1 >= C) p1 -= C;
+          int p2 = p1 + 4;
+          if (p2 >= C) p2 -= C;
+          const float4 A = *reinterpret_cast<const float4 *>(PK + p0);
+          const float4 B = *reinterpret_cast<const float4 *>(PK + p1);
+          const float4 Cq = *reinterpret_cast<const float4 *>(PK + p2);
+          const float m47 = fmaxf(fmaxf(B.x, B.y), fmaxf(B.z, B.w));
+          const float s3 = A.w, s2 = fmaxf(A.z, s3), s1 = fmaxf(A.y, s2), s0 = fmaxf(A.x, s1);
+          const float p9 = fmaxf(Cq.x, Cq.y), p10 = fmaxf(p9, Cq.z);
+          *reinterpret_cast<float4 *>(SA + 4 * v) =
+              make_float4(fmaxf(s0, m47), fmaxf(fmaxf(s1, m47), Cq.x), fmaxf(fmaxf(s2, m47), p9), fmaxf(fmaxf(s3, m47), p10));
+        }
+        __syncthreads();
+        float *src = SA, *dst = SB;
+#pragma unroll 1
+        for (int d = 8; d <= 64; d <<= 1) {                    // windows of 16, 32, 64, 128
+          for (int v = tid; v < span4; v += kFusedThreads) {
+            const float4 A = *reinterpret_cast<const float4 *>(src + 4 * v);
+            const float4 B = *reinterpret_cast<const float4 *>(src + 4 * v + d);
+            *reinterpret_cast<float4 *>(dst + 4 * v) = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
+          }
+          __syncthreads();
+          float *t = src; src = dst; dst = t;
+        }
+        // four passes: the windows of 128 are back in SA
+        for (int v = tid; 4 * v < n; v += kFusedThreads) {     // 240 = two overlapping windows of 128
+          const float4 A = *reinterpret_cast<const float4 *>(SA + 4 * v);
+          const float4 B = *reinterpret_cast<const float4 *>(SA + 4 * v + 112);
+          const float4 W = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
+          *reinterpret_cast<float4 *>(WM + 4 * v) = W;
+          const int left = n - 4 * v;
+          hot |= (W.x > thr) || (left > 1 && W.y > thr) || (left > 2 && W.z > thr) || (left > 3 && W.w > thr);
+        }
       }
       const int any_hot = __syncthreads_or(hot ? 1 : 0);
       // ---------------------------------------------------------------- gain recurrence
