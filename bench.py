@@ -216,6 +216,8 @@ def run_gpu(args):
 
     cfg = args.config
     sc, _, _, _ = refstreams.case(cfg)
+    if args.peak_db:   # experiment knob (not the benchmark workload): per-stream peak range in dBFS
+        sc.peak_db = tuple(float(v) for v in args.peak_db.split(","))
     S_, F = args.streams or CONFIGS[cfg]["streams"], args.frames or CONFIGS[cfg]["frames"]
 
     # CPU baseline first (rank 0, N=1 only), before the GPU is busy
@@ -400,6 +402,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (used under ncu)")
+    ap.add_argument("--peak-db", default="", help="experiment: override the per-stream peak range, e.g. -40,-30")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -42,19 +42,31 @@ struct FusedArgs {
   int n_frames, flush, tile;
 };
 
-constexpr int kFusedThreads = 64;
+constexpr int kFusedThreads = 128;
 constexpr int kWmPad = 320;     // scratch beyond the tile: 240 history + 64 (widest doubling step) + 16
 
-typedef Vec<4> V4;
+// samples per thread in the render / output stages.  The per-tile latency of a block is one thread's serial
+// instruction stream, so FEWER samples per thread (more threads per tile) shortens the critical path of a stream
+constexpr int kVec = 2;
+typedef Vec<kVec> V4;   // "the thread's samples" (historical name: four when kVec == 4)
 
 __device__ __forceinline__ V4 lds4(const float *p) {
-  const float4 t = *reinterpret_cast<const float4 *>(p);
   V4 r;
-  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  if constexpr (kVec == 4) {
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    r.v[0] = t.x; r.v[1 % kVec] = t.y; r.v[2 % kVec] = t.z; r.v[3 % kVec] = t.w;
+  } else if constexpr (kVec == 2) {
+    const float2 t = *reinterpret_cast<const float2 *>(p);
+    r.v[0] = t.x; r.v[1 % kVec] = t.y;
+  } else {
+    r.v[0] = *p;
+  }
   return r;
 }
 __device__ __forceinline__ void sts4(float *p, const V4 &a) {
-  *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  if constexpr (kVec == 4) *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1 % kVec], a.v[2 % kVec], a.v[3 % kVec]);
+  else if constexpr (kVec == 2) *reinterpret_cast<float2 *>(p) = make_float2(a.v[0], a.v[1 % kVec]);
+  else *p = a.v[0];
 }
 __device__ __forceinline__ const float *byte_off(const float *base, int off) {
   return reinterpret_cast<const float *>(reinterpret_cast<const char *>(base) + off);
@@ -78,13 +90,13 @@ __device__ __forceinline__ constexpr int fused_order(int layout, int m) {   // I
 // (tools/check_fast_div.c); outside that range (and for d == 0) the ordinary division is used, +-0 maps to q0 = +-0.
 __device__ __noinline__ void slow_div4(V4 &q, const V4 &x, float d) {
 #pragma unroll 1
-  for (int k = 0; k < 4; ++k) q.v[k] = x.v[k] / d;
+  for (int k = 0; k < kVec; ++k) q.v[k] = x.v[k] / d;
 }
 __device__ __forceinline__ V4 exact_div4(const V4 &x, float d, float r) {
   V4 q;
   unsigned int bad = 0u;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < kVec; ++k) {
     const float q0 = x.v[k] * r;
     const float rem = __fmaf_rn(-d, q0, x.v[k]);
     q.v[k] = __fmaf_rn(rem, r, q0);
@@ -109,24 +121,24 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     if ((ep.gain_mask >> ch) & 1u) {
       const float g = ep.f_gain[ch];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) r.v[k] *= g;
+      for (int k = 0; k < kVec; ++k) r.v[k] *= g;
     }
     return r;
   };
   const int mode = ef.mode & 7;
   V4 dR2, dL3, dR3, dSL5, dSR5, dBL7, dBR7, dHL, dHR, dHBL, dHBR;
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < kVec; ++k)
     dR2.v[k] = dL3.v[k] = dR3.v[k] = dSL5.v[k] = dSR5.v[k] = dBL7.v[k] = dBR7.v[k] = dHL.v[k] = dHR.v[k] = dHBL.v[k] = dHBR.v[k] = 0.f;
   if (ep.need_s2) {   // R2 = 2*Mono - L2, demixer.c:136-138
     const V4 mo = tx(IAMFB_CH_MONO), l2 = tx(IAMFB_CH_L2);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dR2.v[k] = 2 * mo.v[k] - l2.v[k];
+    for (int k = 0; k < kVec; ++k) dR2.v[k] = 2 * mo.v[k] - l2.v[k];
   }
   if (ep.need_s3) {   // L3 = L2 - 0.707*C evaluated in double, demixer.c:165-168
     const V4 l2 = tx(IAMFB_CH_L2), r2 = ep.need_s2 ? dR2 : tx(IAMFB_CH_R2), cc = tx(IAMFB_CH_C);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kVec; ++k) {
       const double c = (double)cc.v[k];
       dL3.v[k] = (float)((double)l2.v[k] - 0.707 * c);
       dR3.v[k] = (float)((double)r2.v[k] - 0.707 * c);
@@ -137,7 +149,7 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     const V4 l5 = tx(IAMFB_CH_L5), r5 = tx(IAMFB_CH_R5);
     V4 nl, nr;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { nl.v[k] = l3.v[k] - l5.v[k]; nr.v[k] = r3.v[k] - r5.v[k]; }
+    for (int k = 0; k < kVec; ++k) { nl.v[k] = l3.v[k] - l5.v[k]; nr.v[k] = r3.v[k] - r5.v[k]; }
     dSL5 = exact_div4(nl, c_mix_delta[mode], c_mix_gd_r[mode]);
     dSR5 = exact_div4(nr, c_mix_delta[mode], c_mix_gd_r[mode]);
   }
@@ -147,7 +159,7 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     const float al = c_mix_alpha[mode];
     V4 nl, nr;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { nl.v[k] = sl5.v[k] - sl7.v[k] * al; nr.v[k] = sr5.v[k] - sr7.v[k] * al; }
+    for (int k = 0; k < kVec; ++k) { nl.v[k] = sl5.v[k] - sl7.v[k] * al; nr.v[k] = sr5.v[k] - sr7.v[k] * al; }
     dBL7 = exact_div4(nl, c_mix_beta[mode], c_mix_beta_r[mode]);
     dBR7 = exact_div4(nr, c_mix_beta[mode], c_mix_beta_r[mode]);
   }
@@ -156,7 +168,7 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     const V4 tl_ = tx(IAMFB_CH_TL), tr_ = tx(IAMFB_CH_TR);
     const float dw = c_mix_delta[mode] * ef.w;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kVec; ++k) {
       dHL.v[k] = tl_.v[k] - dw * sl5.v[k];
       dHR.v[k] = tr_.v[k] - dw * sr5.v[k];
     }
@@ -166,7 +178,7 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     const V4 hfl = tx(IAMFB_CH_HFL), hfr = tx(IAMFB_CH_HFR);
     V4 nl, nr;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { nl.v[k] = hl.v[k] - hfl.v[k]; nr.v[k] = hr.v[k] - hfr.v[k]; }
+    for (int k = 0; k < kVec; ++k) { nl.v[k] = hl.v[k] - hfl.v[k]; nr.v[k] = hr.v[k] - hfr.v[k]; }
     dHBL = exact_div4(nl, c_mix_gamma[mode], c_mix_gd_r[mode]);
     dHBR = exact_div4(nr, c_mix_gamma[mode], c_mix_gd_r[mode]);
   }
@@ -174,10 +186,10 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
   // first frame_size/16 samples of the frame, 1 / 0 after
   V4 st, sw;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { st.v[k] = 0.f; sw.v[k] = 1.f; }
+  for (int k = 0; k < kVec; ++k) { st.v[k] = 0.f; sw.v[k] = 1.f; }
   if (ef.rmask && i0 < plan.overlap) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < kVec; ++k)
       if (i0 + k < plan.overlap) { st.v[k] = a.stop_win[i0 + k]; sw.v[k] = a.start_win[i0 + k]; }
   }
   // gather in layout order; a derived pair replaces the transmitted one exactly when its step ran
@@ -204,7 +216,7 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     if ((ef.rmask >> m) & 1u) {   // x *= last*stop[i] + cur*start[i]
       const float lastf = ef.rlast[m], cur = ef.rcur[m];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kVec; ++k) {
         const float f = lastf * st.v[k] + cur * sw.v[k];
         x[m].v[k] *= f;
       }
@@ -239,7 +251,7 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
 #pragma unroll
       for (int m = 0; m < NREC; ++m)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) x[m].v[k] = .0f;
+        for (int k = 0; k < kVec; ++k) x[m].v[k] = .0f;
 #pragma unroll 1
       for (int l = 0; l < ep.ambi_cols; ++l) {
         const V4 t = lds4(ine + (size_t)l * tl);
@@ -247,7 +259,7 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
         for (int m = 0; m < NREC; ++m) {
           const float c = ep.ambi_mat[l * NREC + m];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) x[m].v[k] += t.v[k] * c;
+          for (int k = 0; k < kVec; ++k) x[m].v[k] += t.v[k] * c;
         }
       }
 #pragma unroll
@@ -261,10 +273,10 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
   const bool og_on = last && (ogr || (fr.out_gain != 1.f && fr.out_gain > 0.f));
   V4 eg, og;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { eg.v[k] = ef.gain; og.v[k] = fr.out_gain; }
+  for (int k = 0; k < kVec; ++k) { eg.v[k] = ef.gain; og.v[k] = fr.out_gain; }
   if (gr || ogr) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kVec; ++k) {
       const int j = min(max(i0 + k - fr.vstart, 0), N - 1);   // samples outside the trimmed frame are discarded later
       if (gr) eg.v[k] = gr[(size_t)sf * N + j];
       if (ogr) og.v[k] = ogr[(size_t)sf * N + j];
@@ -273,26 +285,26 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
   const bool loud_on = last && plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
   V4 peak;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) peak.v[k] = 0.f;
+  for (int k = 0; k < kVec; ++k) peak.v[k] = 0.f;
 
   // render: out = 0; out += mat * in over inputs ascending (m2m_rdr.c:1820-1840, h2m_rdr.c:1103-1112)
 #pragma unroll 1
   for (int oc = 0; oc < co; ++oc) {
     V4 y;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) y.v[k] = 0.f;
+    for (int k = 0; k < kVec; ++k) y.v[k] = 0.f;
     const int q1 = ep.f_csr_ptr[oc + 1];
 #pragma unroll 2
     for (int q = ep.f_csr_ptr[oc]; q < q1; ++q) {
       const float c = ep.f_csr_val[q];
       const V4 xm = lds4(byte_off(in_q, ep.f_csr_off[q]));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y.v[k] += c * xm.v[k];
+      for (int k = 0; k < kVec; ++k) y.v[k] += c * xm.v[k];
     }
     // element mix gain, IAMF_decoder.c:1392-1405
     if (eg_on) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y.v[k] *= eg.v[k];
+      for (int k = 0; k < kVec; ++k) y.v[k] *= eg.v[k];
     }
     float *dst = yt + (size_t)oc * rs;
     // iamf_mixer_mix, IAMF_decoder.c:2719-2730: acc = 0; acc += e0; acc += e1.  (0 + e0 == e0 bit for bit unless e0 is
@@ -300,25 +312,25 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
     if (first) {
       if (gr) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y.v[k] = 0.f + y.v[k];
+        for (int k = 0; k < kVec; ++k) y.v[k] = 0.f + y.v[k];
       }
     } else {
       const V4 p = lds4(dst);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y.v[k] = p.v[k] + y.v[k];
+      for (int k = 0; k < kVec; ++k) y.v[k] = p.v[k] + y.v[k];
     }
     if (last) {
       // output mix gain (IAMF_decoder.c:3463-3469) then loudness (:3480-3484)
       if (og_on) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y.v[k] *= og.v[k];
+        for (int k = 0; k < kVec; ++k) y.v[k] *= og.v[k];
       }
       if (loud_on) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y.v[k] *= plan.loud_gain;
+        for (int k = 0; k < kVec; ++k) y.v[k] *= plan.loud_gain;
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) peak.v[k] = fmaxf(peak.v[k], fabsf(y.v[k]));
+      for (int k = 0; k < kVec; ++k) peak.v[k] = fmaxf(peak.v[k], fabsf(y.v[k]));
     }
     sts4(dst, y);
   }
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
       const int t_end = min(t_off + TL, N);
-      for (int i0 = t_off + tid * 4; i0 < t_end; i0 += kFusedThreads * 4) {
+      for (int i0 = t_off + tid * kVec; i0 < t_end; i0 += kFusedThreads * kVec) {
         const int q = i0 - t_off;                         // position inside the staged tile
         int pos = w + q;
         if (pos >= C) pos -= C;
@@ -736,26 +748,25 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
       const int bits = plan.bit_depth;
       int rbase = w - H;                                            // ring position of the delayed instant 0
       if (rbase < 0) rbase += C;
-      for (int k4 = tid * 4; k4 < n; k4 += kFusedThreads * 4) {
+      for (int k4 = tid * kVec; k4 < n; k4 += kFusedThreads * kVec) {
         const long long o0 = base_o + k4;
-        const bool full = (k4 + 4 <= n) && o0 >= 0;
+        const bool full = (k4 + kVec <= n) && o0 >= 0;
         int pos = rbase + k4;
         if (pos >= C) pos -= C;
         if (full && bits == 16 && (co & 1) == 0 && (((o0 * co) & 1) == 0)) {
-          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (apply_gain) g4 = *reinterpret_cast<const float4 *>(G + k4);
-          const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+          V4 gg;
+#pragma unroll
+          for (int u = 0; u < kVec; ++u) gg.v[u] = 1.f;
+          if (apply_gain) gg = lds4(G + k4);
           uint32_t *wq = (uint32_t *)((int16_t *)out + o0 * co);
           const int half = co >> 1;
 #pragma unroll 1
           for (int c = 0; c < co; c += 2) {
-            const float4 x0 = *reinterpret_cast<const float4 *>(Y + (size_t)c * C + pos);
-            const float4 x1 = *reinterpret_cast<const float4 *>(Y + (size_t)(c + 1) * C + pos);
-            const float v0[4] = {x0.x, x0.y, x0.z, x0.w}, v1[4] = {x1.x, x1.y, x1.z, x1.w};
+            const V4 v0 = lds4(Y + (size_t)c * C + pos), v1 = lds4(Y + (size_t)(c + 1) * C + pos);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float y0 = v0[u], y1 = v1[u];
-              if (plan.limiter) { y0 = y0 * gg[u]; y1 = y1 * gg[u]; }
+            for (int u = 0; u < kVec; ++u) {
+              float y0 = v0.v[u], y1 = v1.v[u];
+              if (plan.limiter) { y0 = y0 * gg.v[u]; y1 = y1 * gg.v[u]; }
               wq[u * half + (c >> 1)] = (uint32_t)(quant16(y0) & 0xffff) | ((uint32_t)quant16(y1) << 16);
             }
           }
@@ -763,7 +774,7 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
 #pragma unroll 1
           for (int c = 0; c < co; ++c) {
 #pragma unroll 1
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kVec; ++u) {
               if (k4 + u >= n || o0 + u < 0) continue;
               int pu = pos + u;
               if (pu >= C) pu -= C;
