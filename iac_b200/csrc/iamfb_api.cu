@@ -805,6 +805,14 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
             ep.f_src_off[c] = (ep.kind == IAMFB_EL_CHANNEL && ep.src_row[c] >= 0) ? (row_base + ep.src_row[c]) * tl * 4 : nin * tl * 4;
             ep.f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
           }
+          ep.f_n_gain = 0;
+          if (ep.kind == IAMFB_EL_CHANNEL)
+            for (int c = 1; c < kChCount; ++c)
+              if (((ep.gain_mask >> c) & 1u) && ep.src_row[c] >= 0 && ep.f_n_gain < IAMFB_MAX_LAYOUT_CH) {
+                ep.f_gain_off[ep.f_n_gain] = ep.f_src_off[c];
+                ep.f_gain_val[ep.f_n_gain] = ep.gain[c];
+                ++ep.f_n_gain;
+              }
           int q = 0;
           for (int oc = 0; oc < co; ++oc) {
             ep.f_csr_ptr[oc] = (unsigned short)q;

@@ -115,15 +115,18 @@ __constant__ float c_mix_gd_r[8] = {1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f,
 template <int LAYOUT, int NREC>
 __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const FusedArgs &a, const ElPlan &ep,
                                                   const ElFrame &ef, const float *in_q, int i0, V4 (&x)[NREC]) {
-  // a transmitted channel, with the output gain of dmx_gainup (demixer.c:421-430) applied on the fly
-  auto tx = [&](int ch) -> V4 {
-    V4 r = lds4(byte_off(in_q, ep.f_src_off[ch]));
-    if ((ep.gain_mask >> ch) & 1u) {
-      const float g = ep.f_gain[ch];
+  // dmx_gainup (demixer.c:421-430): the output gains scale the transmitted channels in place before anything reads them
+  for (int i = 0; i < ep.f_n_gain; ++i) {
+    float *p = byte_off(const_cast<float *>(in_q), ep.f_gain_off[i]);
+    V4 r = lds4(p);
+    const float g = ep.f_gain_val[i];
 #pragma unroll
-      for (int k = 0; k < kVec; ++k) r.v[k] *= g;
-    }
-    return r;
+    for (int k = 0; k < kVec; ++k) r.v[k] *= g;
+    sts4(p, r);
+  }
+  // a transmitted channel (an all-zero row when absent)
+  auto tx = [&](int ch) -> V4 {
+    return lds4(byte_off(in_q, ep.f_src_off[ch]));
   };
   const int mode = ef.mode & 7;
   V4 dR2, dL3, dR3, dSL5, dSR5, dBL7, dBR7, dHL, dHR, dHBL, dHBR;
@@ -355,7 +358,6 @@ __device__ __noinline__ void store_any(char *out, size_t idx, float x, int bits)
 // curve never quite reaches thr/peak): that run is a strictly serial float recurrence  g' = g - acc[1]*(g - thr/peak)
 // and is walked sixteen samples at a time speculatively, every lane holding the same values, with nothing but the
 // three dependent float operations per sample on the critical path.
-constexpr int kBurst = 16;
 
 __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float *g, int n, int &j, float &S, float &E,
                                            const float *__restrict__ acc, int ja, int jr, float thr, int lane) {
@@ -388,47 +390,52 @@ __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float 
     j = 0;
     pos += first + 1;
     // ---- serial run: the step after a trigger has gain S - acc[1]*(S - E); while it triggers again the state is
-    // (S = that gain, E = thr/peak, j = 0) and the next step has the same form.  Sixteen steps at a time are
-    // evaluated speculatively from 16-byte shared-memory loads when the position is aligned, else one by one.
+    // (S = that gain, E = thr/peak, j = 0) and the next step has the same form.  Up to 32 steps at a time are walked
+    // speculatively - nothing but the three dependent float operations per step, thr/peak from 16-byte loads, gains
+    // stored four at a time - and then checked in parallel, lane i testing step i; the first step that did not
+    // trigger ends the run (its gain is still the right one: it only depends on the trigger before it).
     bool running = true;
     while (running && pos < n) {
-      if ((pos & 3) == 0 && n - pos >= kBurst) {
-        float ps[kBurst], es[kBurst], gs[kBurst];
-#pragma unroll
-        for (int i = 0; i < kBurst; i += 4) {
-          const float4 pw = *reinterpret_cast<const float4 *>(wm + pos + i);
-          const float4 pe = *reinterpret_cast<const float4 *>(ew + pos + i);
-          ps[i] = pw.x; ps[i + 1] = pw.y; ps[i + 2] = pw.z; ps[i + 3] = pw.w;
-          es[i] = pe.x; es[i + 1] = pe.y; es[i + 2] = pe.z; es[i + 3] = pe.w;
+      const int B = min(32, (n - pos) & ~3);
+      if ((pos & 3) == 0 && B >= 4) {
+        float sg = S, se = E;
+#pragma unroll 1
+        for (int i = 0; i < B; i += 4) {
+          const float4 e4 = *reinterpret_cast<const float4 *>(ew + pos + i);
+          const float g0 = sg - a1 * (sg - se);
+          const float g1 = g0 - a1 * (g0 - e4.x);
+          const float g2 = g1 - a1 * (g1 - e4.y);
+          const float g3 = g2 - a1 * (g2 - e4.z);
+          *reinterpret_cast<float4 *>(g + pos + i) = make_float4(g0, g1, g2, g3);
+          sg = g3;
+          se = e4.w;
         }
-        float s = S, e = E;
-        bool all = true;
-#pragma unroll
-        for (int i = 0; i < kBurst; ++i) {
-          const float gi = s - a1 * (s - e);
-          gs[i] = gi;
-          all = all && (ps[i] * gi > thr);
-          s = gi;
-          e = es[i];
-        }
-        if (all) {
-#pragma unroll
-          for (int i = 0; i < kBurst; i += 4)
-            *reinterpret_cast<float4 *>(g + pos + i) = make_float4(gs[i], gs[i + 1], gs[i + 2], gs[i + 3]);
-          S = gs[kBurst - 1];
-          E = es[kBurst - 1];
-          pos += kBurst;
+        __syncwarp();
+        const bool mine = lane < B;
+        const float gl = mine ? g[pos + lane] : 0.f;
+        const float pl = mine ? wm[pos + lane] : 0.f;
+        const unsigned ok = __ballot_sync(0xffffffffu, !mine || (pl * gl > thr));
+        if (ok == 0xffffffffu) {
+          S = sg;
+          E = se;
+          pos += B;
           continue;
         }
+        const int f = __ffs(~ok) - 1;          // first step of the burst that did not trigger
+        if (f > 0) { S = g[pos + f - 1]; E = ew[pos + f - 1]; }
+        j = 1;                                 // the curve continues one increment after the last trigger
+        pos += f + 1;
+        running = false;
+        continue;
       }
-      // one step
+      // one step (unaligned position or fewer than four instants left)
       const float gi = S - a1 * (S - E);
       g[pos] = gi;
       if (wm[pos] * gi > thr) {
         S = gi;
         E = ew[pos];
       } else {
-        j = 1;               // no trigger: the curve continues one increment after the last trigger
+        j = 1;
         running = false;
       }
       pos += 1;

@@ -41,6 +41,9 @@ struct ElPlan {
   // ascending): entry q of row oc adds f_csr_val[q] * (staged/reconstructed row at byte offset f_csr_off[q])
   int f_src_off[kChCount];
   float f_gain[kChCount];
+  int f_n_gain;                    // transmitted channels with an output gain: staged-row byte offset and gain
+  int f_gain_off[IAMFB_MAX_LAYOUT_CH];
+  float f_gain_val[IAMFB_MAX_LAYOUT_CH];
   int f_row_off;                   // byte offset of the element's first staged row
   unsigned short f_csr_ptr[kMaxOut + 1];
   int f_csr_off[kMaxOut * kMaxRec];
