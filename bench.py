@@ -245,11 +245,13 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end leg (the timed region of K
+    # sub-millisecond steps alone is shorter than one nvidia-smi query)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -259,14 +261,13 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     # samples produced in one steady-state step (all streams of this rank)
     out_per_step = int(d_counts.sum().item())
     ms_max, out_total = shard.aggregate(ms, out_per_step, device=dev)     # MAX of device time, SUM of samples
     value = shard.job_throughput(ms_max, out_total, sc.out_rate, steps=args.steps)
 
     if args.quick:
+        sampler.stop_flag = True
         if rank == 0:
             print(json.dumps({"metric": "rendered audio-sec/sec", "value": value, "ms_per_step": ms_max / args.steps,
                               "gpu_launches": int(launches), "quick": True}))
@@ -341,6 +342,8 @@ def run_gpu(args):
     h2d = sum(x.numel() * 2 for x in h_in) + h_params.numel()
     d2h = S_ * stride_e + h_counts.numel() * 4
 
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
     if rank == 0:
         clocks = sampler.summary()
         line = {

@@ -42,12 +42,12 @@ struct FusedArgs {
   int n_frames, flush, tile;
 };
 
-constexpr int kFusedThreads = 128;
+constexpr int kFusedThreads = 64;
 constexpr int kWmPad = 320;     // scratch beyond the tile: 240 history + 64 (widest doubling step) + 16
 
 // samples per thread in the render / output stages.  The per-tile latency of a block is one thread's serial
 // instruction stream, so FEWER samples per thread (more threads per tile) shortens the critical path of a stream
-constexpr int kVec = 2;
+constexpr int kVec = 4;
 typedef Vec<kVec> V4;   // "the thread's samples" (historical name: four when kVec == 4)
 
 __device__ __forceinline__ V4 lds4(const float *p) {
