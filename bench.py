@@ -294,8 +294,16 @@ def run_gpu(args):
     alg_bytes_step = alg_bytes_per_audio_second(sc) * (out_per_step / sc.out_rate)
     dom_launches = max(kernels[dom]["launches_per_step"], 1e-9)
     achieved = alg_bytes_step / dom_launches / (kernels[dom]["ms_per_launch"] / 1e3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu capture (same workload shape), else null
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg, {}).get(dom)
+        if t and t["streams"] == S_ and t["frames"] == F:
+            traffic = t["bytes_per_launch"]
+    except Exception:
+        pass
     roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
-                    traffic=None, peak_source=peak_src,
+                    traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes_step / dom_launches,
                     pipeline=dict(achieved=alg_bytes_step / (ms_max / args.steps / 1e3) / 1e9,
                                   frac=alg_bytes_step / (ms_max / args.steps / 1e3) / 1e9 / peak_gbs,
