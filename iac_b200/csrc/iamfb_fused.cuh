@@ -359,9 +359,11 @@ __device__ __noinline__ void store_any(char *out, size_t idx, float x, int bits)
 // and is walked sixteen samples at a time speculatively, every lane holding the same values, with nothing but the
 // three dependent float operations per sample on the critical path.
 
+constexpr int kAccCache = 128;   // first entries of the limiter curve kept in shared memory (the ones right after a trigger)
+
 __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float *g, int n, int &j, float &S, float &E,
-                                           const float *__restrict__ acc, int ja, int jr, float thr, int lane) {
-  const float a1 = __ldg(acc + 1);
+                                           const float *__restrict__ acc, const float *acc_s, int ja, int jr, float thr, int lane) {
+  const float a1 = acc_s[1];
   int pos = 0;
   while (pos < n) {
     // ---- parallel search for the next trigger
@@ -370,7 +372,7 @@ __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float 
     const float p = valid ? wm[k] : 0.f;
     const int jj = j < 0 ? -1 : min(j + lane, jr);
     const bool active = jj >= 0 && jj < jr;
-    const float ac = active ? __ldg(acc + jj + 1) : 0.f;
+    const float ac = active ? (jj + 1 < kAccCache ? acc_s[jj + 1] : __ldg(acc + jj + 1)) : 0.f;
     const float ga = S - ac * (S - E);
     const float gr = E + ac * (1.0f - E);
     const float gk = active ? (jj < ja ? ga : gr) : 1.0f;
@@ -450,6 +452,7 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
   __shared__ __align__(16) FrameRec s_fr;      // resolved parameters of the frame being rendered
   __shared__ int s_lim[4];
   __shared__ int s_next[2];                    // (frame, offset) of the tile after the current one
+  __shared__ float s_acc[kAccCache];
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // co-resident blocks run their serial scans on different warp schedulers
@@ -472,6 +475,7 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
   float lS = -1.f, lE = -1.f;
   for (int i = tid; i < TL; i += kFusedThreads) IN[(size_t)(nin0 + nin1) * TL + i] = 0.f;
   if (plan.limiter) {
+    for (int i = tid; i < kAccCache; i += kFusedThreads) s_acc[i] = i <= plan.lim_jr + 3 ? a.acc[i] : 0.f;
     const StreamState &st = a.state[s];
     lj = st.lim_j; lS = st.lim_start; lE = st.lim_end;
     if (lj > plan.lim_jr) lj = plan.lim_jr;
@@ -742,7 +746,7 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
         }
         __syncthreads();
         if (warp == scan_warp) {
-          fused_scan(WM, EW, G, n, lj, lS, lE, a.acc, plan.lim_ja, plan.lim_jr, thr, lane);
+          fused_scan(WM, EW, G, n, lj, lS, lE, a.acc, s_acc, plan.lim_ja, plan.lim_jr, thr, lane);
           if (lane == 0) { s_lim[0] = lj; s_lim[1] = __float_as_int(lS); s_lim[2] = __float_as_int(lE); }
         }
         __syncthreads();
