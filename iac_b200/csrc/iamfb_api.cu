@@ -160,6 +160,8 @@ struct iamfb_plan {
   float *d_qf;                       // 256
   float *d_sinc;                     // resampler table
   int sinc_len;
+  float4 *d_tab4;                    // interpolating resampler: the four neighbouring taps per (offset, input) as one item
+  int rs_span;                       // inputs staged per block of 128 outputs
   float *d_acc;                      // limiter acceleration curve by time index
   // initial per-stream state (host copy)
   StreamState init_state;
@@ -756,6 +758,23 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
     p->sinc_len = (int)table.size();
     int r = upload(&p->d_sinc, table.data(), table.size());
     if (r) { delete p; return r; }
+    if (!kp.rs_direct) {
+      const int Nf = (int)kp.rs_filt_len, os = (int)kp.rs_oversample, trow = Nf + 1;
+      std::vector<float4> t4((size_t)os * trow);
+      for (int o = 0; o < os; ++o)
+        for (int j = 0; j < trow; ++j) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < Nf) {
+            const float *t = table.data() + 4 + (j + 1) * os - o;
+            v = make_float4(t[-2], t[-1], t[0], t[1]);
+          }
+          t4[(size_t)o * trow + j] = v;
+        }
+      r = upload(&p->d_tab4, t4.data(), t4.size());
+      if (r) { delete p; return r; }
+      // inputs spanned by 128 consecutive outputs: floor(127 * num / den) + 1, plus the filter length
+      p->rs_span = (int)((127ull * kp.rs_num) / kp.rs_den + 2 + kp.rs_filt_len + 3) & ~3;
+    }
   }
   if (kp.limiter) {
     std::vector<float> acc;
@@ -841,7 +860,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
 
 extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
   if (!p) return;
-  cudaFree(p->d_start_win); cudaFree(p->d_stop_win); cudaFree(p->d_qf); cudaFree(p->d_sinc); cudaFree(p->d_acc);
+  cudaFree(p->d_start_win); cudaFree(p->d_stop_win); cudaFree(p->d_qf); cudaFree(p->d_sinc); cudaFree(p->d_acc); cudaFree(p->d_tab4);
   delete p;
 }
 
@@ -1160,8 +1179,19 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       a.max_out = max_out;
       a.flush = flush ? 1 : 0;
       dim3 grid((max_out + 127) / 128, S);
-      size_t smem = p->sinc_len <= 12 * 1024 ? sizeof(float) * p->sinc_len : 0;
-      { ScopedKernelTimer tm_(ctx, "k_resample"); k_resample<<<grid, 128, smem, st>>>(kp, a); }
+      const size_t smem2 = p->d_tab4 ? sizeof(float4) * kp.rs_oversample * (kp.rs_filt_len + 1) + sizeof(float) * 2 * p->rs_span : 0;
+      static const bool old_rs = getenv("IAMFB_RESAMPLE_OLD") && atoi(getenv("IAMFB_RESAMPLE_OLD")) == 1;
+      if (p->d_tab4 && smem2 <= 200 * 1024 && !old_rs) {
+        Resample2Args a2;
+        a2.r = a;
+        a2.tab4 = p->d_tab4;
+        a2.span = p->rs_span;
+        CU(cudaFuncSetAttribute(k_resample_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        { ScopedKernelTimer tm_(ctx, "k_resample"); k_resample_interp<<<grid, 128, smem2, st>>>(kp, a2); }
+      } else {
+        size_t smem = p->sinc_len <= 12 * 1024 ? sizeof(float) * p->sinc_len : 0;
+        { ScopedKernelTimer tm_(ctx, "k_resample"); k_resample<<<grid, 128, smem, st>>>(kp, a); }
+      }
       LAUNCH_CHECK("k_resample");
       if (!flush) {
         CarryArgs c;

@@ -810,6 +810,91 @@ __global__ void __launch_bounds__(128) k_resample(const __grid_constant__ Kernel
   if (a.pk) a.pk[(size_t)s * a.cap_b + a.hist_b + u] = peak;
 }
 
+// K2b: the interpolating resampler (the 44.1 -> 48 kHz case and every other non-integer-phase ratio) with everything
+// on chip.  block = 128 consecutive outputs of one stream.  The four neighbouring taps an output needs per input
+// sample are stored as ONE 16-byte item, tab4[offset][j] = sinc[4 + (j+1)*oversample - offset - {2,1,0,-1}] (rows padded
+// to an odd number of items so that lanes with different phases hit different banks); the inputs the block's outputs
+// span are staged per channel pair in shared memory, and the taps are reused for both channels.  The accumulation is
+// the reference's: four accumulators per channel over j ascending, cubic blend, clamp (resample.c:357-418,84).
+struct Resample2Args {
+  ResampleArgs r;
+  const float4 *tab4;      // [oversample][filt_len + 1]
+  int span;                // staged inputs per channel: inputs spanned by 128 consecutive outputs + filt_len (multiple of 4)
+};
+
+__global__ void __launch_bounds__(128) k_resample_interp(const __grid_constant__ KernelPlan plan, Resample2Args b) {
+  extern __shared__ __align__(16) float rs_smem[];
+  const ResampleArgs &a = b.r;
+  const int Nf = plan.rs_filt_len, os = plan.rs_oversample;
+  const int trow = Nf + 1;
+  float4 *s_tab = reinterpret_cast<float4 *>(rs_smem);              // [os][Nf + 1]
+  float *s_x = rs_smem + (size_t)4 * os * trow;                      // [2][span]
+  for (int i = threadIdx.x; i < os * trow; i += blockDim.x) s_tab[i] = b.tab4[i];
+
+  const int s = blockIdx.y;
+  const int u0 = blockIdx.x * blockDim.x, u = u0 + threadIdx.x;
+  const SubmitRec sr = a.submit[s];
+  const int n_out = a.flush ? (sr.lim_len - (plan.limiter ? kLimDelay : 0)) : sr.lim_len;
+  if (u0 >= n_out) return;
+  const long long num = plan.rs_num, den = plan.rs_den;
+  const long long in_start = a.state[s].rs_in_total - sr.in_len;     // stream position of tl_a[rs_hist]
+  // first input (index into the tl_a row) needed by the block's first output
+  const long long nb = sr.rs_out_first + u0;
+  const long long pb = (long long)(Nf / 2) + (nb * num) / den - (Nf - 1) - in_start + plan.rs_hist;
+  const bool live = u < n_out;
+  const long long n = sr.rs_out_first + (live ? u : n_out - 1);
+  const long long q = (long long)(Nf / 2) + (n * num) / den;
+  const unsigned int frac_num = (unsigned int)((n * (long long)plan.rs_frac_adv) % den);
+  const int rel = (int)(q - (Nf - 1) - in_start + plan.rs_hist - pb);   // first tap inside the staged span
+  const int offset = frac_num * plan.rs_oversample / plan.rs_den;
+  const float frac = ((float)((frac_num * plan.rs_oversample) % plan.rs_den)) / plan.rs_den;
+  // cubic_coef, resample.c:246-256 (interp[2] is a double expression rounded once)
+  float interp[4];
+  interp[0] = -0.16667f * frac + 0.16667f * frac * frac * frac;
+  interp[1] = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
+  interp[3] = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
+  interp[2] = (float)(1. - (double)interp[0] - (double)interp[1] - (double)interp[3]);
+  const float4 *trow_p = s_tab + (size_t)offset * trow;
+  const int co = plan.out_channels;
+  const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f && !a.flush;
+  float peak = 0.f;
+
+  for (int c0 = 0; c0 < co; c0 += 2) {
+    const int nc = min(2, co - c0);
+    __syncthreads();                                                  // table staged / previous pair consumed
+    for (int i = threadIdx.x; i < nc * b.span; i += blockDim.x) {
+      const int cc = i / b.span, k = i - cc * b.span;
+      const long long idx = pb + k;
+      const float *row = a.src + ((size_t)s * co + c0 + cc) * a.cap_a;
+      s_x[cc * b.span + k] = (idx >= 0 && idx < a.cap_a) ? row[idx] : 0.f;
+    }
+    __syncthreads();
+    if (!live) continue;
+    const float *x0 = s_x + rel, *x1 = s_x + (nc > 1 ? b.span : 0) + rel;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < Nf; ++j) {
+      const float4 t = trow_p[j];
+      const float xa = x0[j], xb = x1[j];
+      a0 += xa * t.x; a1 += xa * t.y; a2 += xa * t.z; a3 += xa * t.w;
+      b0 += xb * t.x; b1 += xb * t.y; b2 += xb * t.z; b3 += xb * t.w;
+    }
+    float sum0 = interp[0] * a0 + interp[1] * a1 + interp[2] * a2 + interp[3] * a3;
+    float sum1 = interp[0] * b0 + interp[1] * b1 + interp[2] * b2 + interp[3] * b3;
+    // FLTADJUST, resample.c:84
+    sum0 = (sum0 < -1.0f) ? -1.0f : ((sum0 > 1.0f) ? 1.0f : sum0);
+    sum1 = (sum1 < -1.0f) ? -1.0f : ((sum1 > 1.0f) ? 1.0f : sum1);
+    if (loud_on) { sum0 *= plan.loud_gain; sum1 *= plan.loud_gain; }
+    a.dst[((size_t)s * co + c0) * a.cap_b + a.hist_b + u] = sum0;
+    peak = fmaxf(peak, fabsf(sum0));
+    if (nc > 1) {
+      a.dst[((size_t)s * co + c0 + 1) * a.cap_b + a.hist_b + u] = sum1;
+      peak = fmaxf(peak, fabsf(sum1));
+    }
+  }
+  if (live && a.pk) a.pk[(size_t)s * a.cap_b + a.hist_b + u] = peak;
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // K3a: sliding maximum.  wm[k] = max(pk[k-240 .. k-1]) = the `peak` the reference limiter looks up for instant k
 // (audio_effect_peak_limiter.c:109-133; the arg-max cache there is only an optimisation).
