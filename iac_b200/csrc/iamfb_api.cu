@@ -167,6 +167,7 @@ struct iamfb_plan {
   StreamState init_state;
   // fused single-kernel path (non-resampling pipelines whose element signature is instantiated)
   bool fused;
+  int fused_variant;       // 0: 4 samples per thread, 64 threads; 1: 2 samples, 128 threads; 2: 1 sample, 256 threads
   int fused_tile;          // samples per tile
   size_t fused_smem;       // dynamic shared memory per block
 };
@@ -679,19 +680,30 @@ static int launch_fused(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
   const size_t smem = p->fused_smem;
-#define FCASE(ID, L0, N0, L1, N1)                                                                                   \
-  case ID: {                                                                                                        \
-    CU(cudaFuncSetAttribute(k_fused<L0, N0, L1, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    ScopedKernelTimer tm_(ctx, "k_fused");                                                                          \
-    k_fused<L0, N0, L1, N1><<<S, kFusedThreads, smem, st>>>(kp, fa);                                               \
-  } break;
+#define FLAUNCH(L0, N0, L1, N1, VEC, THREADS)                                                                         \
+  {                                                                                                                   \
+    CU(cudaFuncSetAttribute(k_fused<L0, N0, L1, N1, VEC, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ScopedKernelTimer tm_(ctx, "k_fused");                                                                            \
+    k_fused<L0, N0, L1, N1, VEC, THREADS><<<S, THREADS, smem, st>>>(kp, fa);                                         \
+  }
+#define FCASE(ID, L0, N0, L1, N1) \
+  case ID: FLAUNCH(L0, N0, L1, N1, 4, 64) break;
+  // scene-based pipelines with many output channels fit few streams per SM: lighter threads, more of them
+#define FCASE3(ID, L0, N0, L1, N1)                                    \
+  case ID:                                                            \
+    if (p->fused_variant == 2) FLAUNCH(L0, N0, L1, N1, 1, 256)        \
+    else if (p->fused_variant == 1) FLAUNCH(L0, N0, L1, N1, 2, 128)   \
+    else FLAUNCH(L0, N0, L1, N1, 4, 64)                               \
+    break;
   switch (fused_variant(p->tmpl, kp.n_elements)) {
     FCASE(0, 0, 1, 0, 0) FCASE(1, 1, 2, 0, 0) FCASE(2, 2, 6, 0, 0) FCASE(3, 3, 8, 0, 0) FCASE(4, 4, 10, 0, 0)
     FCASE(5, 5, 8, 0, 0) FCASE(6, 6, 10, 0, 0) FCASE(7, 7, 12, 0, 0) FCASE(8, 8, 6, 0, 0)
-    FCASE(10, -1, 1, 0, 0) FCASE(11, -1, 4, 0, 0) FCASE(12, -1, 9, 0, 0) FCASE(13, -1, 16, 0, 0)
+    FCASE3(10, -1, 1, 0, 0) FCASE3(11, -1, 4, 0, 0) FCASE3(12, -1, 9, 0, 0) FCASE3(13, -1, 16, 0, 0)
     FCASE(100, 7, 12, -1, 4) FCASE(101, -1, 4, 7, 12)
     default: return fail(IAMFB_ERR_INTERNAL, "no fused kernel variant");
   }
+#undef FCASE3
+#undef FLAUNCH
 #undef FCASE
   cudaError_t e_ = cudaGetLastError();
   if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_fused failed: %s", cudaGetErrorString(e_));
@@ -799,7 +811,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
       auto smem_floats = [&](int tl) { return (size_t)(nin + 1) * tl + (size_t)(co + 1) * (H + tl) + tl + 2 * ((size_t)tl + kWmPad); };
       // as many blocks (= streams) per SM as possible while a tile still covers >= 240 samples (or the whole frame):
       // 7, 6, 5, 4, 3 blocks of the 227 KB
-      int tl = 0;
+      int tl = 0, blocks_per_sm = 0;
       for (int blocks = 7; blocks >= 3 && !tl; --blocks) {
         const int budget = (int)((233472 / blocks - 1024 - 64) / 4);
         int tl_max = (budget - 2 * kWmPad - (co + 1) * H) / (nin + 1 + co + 1 + 3);
@@ -809,11 +821,19 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
         const int n_tiles = (kp.frame_size + tl_max - 1) / tl_max;
         int t = (kp.frame_size + n_tiles - 1) / n_tiles;
         t = (t + 3) & ~3;
-        if (t >= 240 || n_tiles == 1 || blocks == 3) tl = t;
+        if (t >= 240 || n_tiles == 1 || blocks == 3) { tl = t; blocks_per_sm = blocks; }
       }
       if (tl >= 64) {
         p->fused = true;
         p->fused_tile = tl;
+        // few streams per SM (large rings): spread each tile over more, lighter threads (scene-based signatures only)
+        p->fused_variant = 0;
+        if (kp.n_elements == 1 && kp.el[0].kind == IAMFB_EL_SCENE) {
+          const char *env = getenv("IAMFB_FUSED_VARIANT");
+          if (env) p->fused_variant = atoi(env);
+          else p->fused_variant = blocks_per_sm <= 5 ? 1 : 0;   // measured on C3 (3 streams per SM): 2.93 ms vs 3.45 (variant 0) and 4.0 (variant 2)
+          if (p->fused_variant < 0 || p->fused_variant > 2) p->fused_variant = 0;
+        }
         p->fused_smem = sizeof(float) * smem_floats(tl);
         // staged-row byte offsets and the row-compressed render matrix of the fused kernel
         int row_base = 0;

@@ -42,16 +42,16 @@ struct FusedArgs {
   int n_frames, flush, tile;
 };
 
-constexpr int kFusedThreads = 64;
 constexpr int kWmPad = 320;     // scratch beyond the tile: 240 history + 64 (widest doubling step) + 16
 
 // samples per thread in the render / output stages.  The per-tile latency of a block is one thread's serial
 // instruction stream, so FEWER samples per thread (more threads per tile) shortens the critical path of a stream
-constexpr int kVec = 4;
-typedef Vec<kVec> V4;   // "the thread's samples" (historical name: four when kVec == 4)
+// (template parameter VEC of everything below; the host picks it per plan together with the block size)
 
-__device__ __forceinline__ V4 lds4(const float *p) {
-  V4 r;
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ldsv(const float *p) {
+  constexpr int kVec = VEC;
+  Vec<VEC> r;
   if constexpr (kVec == 4) {
     const float4 t = *reinterpret_cast<const float4 *>(p);
     r.v[0] = t.x; r.v[1 % kVec] = t.y; r.v[2 % kVec] = t.z; r.v[3 % kVec] = t.w;
@@ -63,7 +63,9 @@ __device__ __forceinline__ V4 lds4(const float *p) {
   }
   return r;
 }
-__device__ __forceinline__ void sts4(float *p, const V4 &a) {
+template <int VEC>
+__device__ __forceinline__ void stsv(float *p, const Vec<VEC> &a) {
+  constexpr int kVec = VEC;
   if constexpr (kVec == 4) *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1 % kVec], a.v[2 % kVec], a.v[3 % kVec]);
   else if constexpr (kVec == 2) *reinterpret_cast<float2 *>(p) = make_float2(a.v[0], a.v[1 % kVec]);
   else *p = a.v[0];
@@ -88,11 +90,15 @@ __device__ __forceinline__ constexpr int fused_order(int layout, int m) {   // I
 // With r = RN(1/d):  q0 = RN(x*r),  rem = x - d*q0 (exact, one FMA),  q = RN(q0 + rem*r)  equals RN(x/d) for EVERY
 // finite x with 2^-100 <= |x| < 2^126 - verified exhaustively over all 2^32 inputs for each of the three divisors
 // (tools/check_fast_div.c); outside that range (and for d == 0) the ordinary division is used, +-0 maps to q0 = +-0.
-__device__ __noinline__ void slow_div4(V4 &q, const V4 &x, float d) {
+template <int VEC>
+__device__ __noinline__ void slow_div4(Vec<VEC> &q, const Vec<VEC> &x, float d) {
 #pragma unroll 1
-  for (int k = 0; k < kVec; ++k) q.v[k] = x.v[k] / d;
+  for (int k = 0; k < VEC; ++k) q.v[k] = x.v[k] / d;
 }
-__device__ __forceinline__ V4 exact_div4(const V4 &x, float d, float r) {
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> exact_div4(const Vec<VEC> &x, float d, float r) {
+  constexpr int kVec = VEC;
+  typedef Vec<VEC> V4;
   V4 q;
   unsigned int bad = 0u;
 #pragma unroll
@@ -103,7 +109,7 @@ __device__ __forceinline__ V4 exact_div4(const V4 &x, float d, float r) {
     const unsigned int ax = __float_as_uint(x.v[k]) & 0x7fffffffu;
     bad |= (ax - 0x0d800000u >= 0x7e800000u - 0x0d800000u) ? 1u : 0u;
   }
-  if (bad | (d == 0.f ? 1u : 0u)) slow_div4(q, x, d);
+  if (bad | (d == 0.f ? 1u : 0u)) slow_div4<VEC>(q, x, d);
   return q;
 }
 __constant__ float c_mix_beta_r[8] = {1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f, 1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f};
@@ -112,21 +118,23 @@ __constant__ float c_mix_gd_r[8] = {1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f,
 // Channel-based reconstruction (demixer.c:127-378,421-475) from the staged rows.  in_q = the block's staged tile at
 // this thread's four samples; every IAChannel has a byte offset to its row (an all-zero row when absent) and an
 // output gain (1.0 by default).  Fills x[m] = layout channel m after recon gain.
-template <int LAYOUT, int NREC>
+template <int LAYOUT, int NREC, int VEC>
 __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const FusedArgs &a, const ElPlan &ep,
-                                                  const ElFrame &ef, const float *in_q, int i0, V4 (&x)[NREC]) {
+                                                  const ElFrame &ef, const float *in_q, int i0, Vec<VEC> (&x)[NREC]) {
+  constexpr int kVec = VEC;
+  typedef Vec<VEC> V4;   // "the thread's samples" (historical name: four when VEC == 4)
   // dmx_gainup (demixer.c:421-430): the output gains scale the transmitted channels in place before anything reads them
   for (int i = 0; i < ep.f_n_gain; ++i) {
     float *p = byte_off(const_cast<float *>(in_q), ep.f_gain_off[i]);
-    V4 r = lds4(p);
+    V4 r = ldsv<VEC>(p);
     const float g = ep.f_gain_val[i];
 #pragma unroll
     for (int k = 0; k < kVec; ++k) r.v[k] *= g;
-    sts4(p, r);
+    stsv<VEC>(p, r);
   }
   // a transmitted channel (an all-zero row when absent)
   auto tx = [&](int ch) -> V4 {
-    return lds4(byte_off(in_q, ep.f_src_off[ch]));
+    return ldsv<VEC>(byte_off(in_q, ep.f_src_off[ch]));
   };
   const int mode = ef.mode & 7;
   V4 dR2, dL3, dR3, dSL5, dSR5, dBL7, dBR7, dHL, dHR, dHBL, dHBR;
@@ -153,8 +161,8 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     V4 nl, nr;
 #pragma unroll
     for (int k = 0; k < kVec; ++k) { nl.v[k] = l3.v[k] - l5.v[k]; nr.v[k] = r3.v[k] - r5.v[k]; }
-    dSL5 = exact_div4(nl, c_mix_delta[mode], c_mix_gd_r[mode]);
-    dSR5 = exact_div4(nr, c_mix_delta[mode], c_mix_gd_r[mode]);
+    dSL5 = exact_div4<VEC>(nl, c_mix_delta[mode], c_mix_gd_r[mode]);
+    dSR5 = exact_div4<VEC>(nr, c_mix_delta[mode], c_mix_gd_r[mode]);
   }
   if (ep.need_s7) {   // Lb7 = (Ls5 - alpha*Lss7)/beta, demixer.c:262-269
     const V4 sl5 = ep.need_s5 ? dSL5 : tx(IAMFB_CH_SL5), sr5 = ep.need_s5 ? dSR5 : tx(IAMFB_CH_SR5);
@@ -163,8 +171,8 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     V4 nl, nr;
 #pragma unroll
     for (int k = 0; k < kVec; ++k) { nl.v[k] = sl5.v[k] - sl7.v[k] * al; nr.v[k] = sr5.v[k] - sr7.v[k] * al; }
-    dBL7 = exact_div4(nl, c_mix_beta[mode], c_mix_beta_r[mode]);
-    dBR7 = exact_div4(nr, c_mix_beta[mode], c_mix_beta_r[mode]);
+    dBL7 = exact_div4<VEC>(nl, c_mix_beta[mode], c_mix_beta_r[mode]);
+    dBR7 = exact_div4<VEC>(nr, c_mix_beta[mode], c_mix_beta_r[mode]);
   }
   if (ep.need_h2) {   // Ltf2 = Ltf3 - delta*w*Ls5, demixer.c:318-323
     const V4 sl5 = ep.need_s5 ? dSL5 : tx(IAMFB_CH_SL5), sr5 = ep.need_s5 ? dSR5 : tx(IAMFB_CH_SR5);
@@ -182,8 +190,8 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
     V4 nl, nr;
 #pragma unroll
     for (int k = 0; k < kVec; ++k) { nl.v[k] = hl.v[k] - hfl.v[k]; nr.v[k] = hr.v[k] - hfr.v[k]; }
-    dHBL = exact_div4(nl, c_mix_gamma[mode], c_mix_gd_r[mode]);
-    dHBR = exact_div4(nr, c_mix_gamma[mode], c_mix_gd_r[mode]);
+    dHBL = exact_div4<VEC>(nl, c_mix_gamma[mode], c_mix_gd_r[mode]);
+    dHBR = exact_div4<VEC>(nr, c_mix_gamma[mode], c_mix_gd_r[mode]);
   }
   // recon-gain cross-fade window of this thread's samples (dmx_rms, demixer.c:461-468): hann start / stop inside the
   // first frame_size/16 samples of the frame, 1 / 0 after
@@ -231,10 +239,12 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
 // (a trimmed tile is compacted afterwards), so every access is a whole aligned quad.
 //   in_q  the block's staged tile at the thread's samples (rows tl floats apart)
 //   yt    the thread's slots in the mixed time line (&Y[0][ring position], rows rs floats apart)
-template <int LAYOUT, int NREC>
+template <int LAYOUT, int NREC, int VEC>
 __device__ __forceinline__ void fused_element(const KernelPlan &plan, const FusedArgs &a, int e, const FrameRec &fr,
                                               int sf, int i0, bool first, bool last, float *in_q, int tl, float *yt, int rs,
                                               float *pkt) {
+  constexpr int kVec = VEC;
+  typedef Vec<VEC> V4;
   const int N = plan.frame_size;
   const ElPlan &ep = plan.el[e];
   const ElFrame &ef = fr.el[e];
@@ -242,10 +252,10 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
   float *ine = byte_off(in_q, ep.f_row_off);
   if constexpr (LAYOUT >= 0) {
     V4 x[NREC];
-    fused_reconstruct<LAYOUT, NREC>(plan, a, ep, ef, in_q, i0, x);
+    fused_reconstruct<LAYOUT, NREC, VEC>(plan, a, ep, ef, in_q, i0, x);
     // the reconstructed layout channels replace the staged rows (this thread's samples only; all its reads are done)
 #pragma unroll
-    for (int m = 0; m < NREC; ++m) sts4(ine + (size_t)m * tl, x[m]);
+    for (int m = 0; m < NREC; ++m) stsv<VEC>(ine + (size_t)m * tl, x[m]);
   } else {
     // scene based: a mono mapping is a row permutation (folded into the matrix offsets), a projection an ordered
     // mat-vec (IAMF_core_decoder.c:105-130) whose result replaces the staged rows
@@ -257,7 +267,7 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
         for (int k = 0; k < kVec; ++k) x[m].v[k] = .0f;
 #pragma unroll 1
       for (int l = 0; l < ep.ambi_cols; ++l) {
-        const V4 t = lds4(ine + (size_t)l * tl);
+        const V4 t = ldsv<VEC>(ine + (size_t)l * tl);
 #pragma unroll
         for (int m = 0; m < NREC; ++m) {
           const float c = ep.ambi_mat[l * NREC + m];
@@ -266,7 +276,7 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
         }
       }
 #pragma unroll
-      for (int m = 0; m < NREC; ++m) sts4(ine + (size_t)m * tl, x[m]);
+      for (int m = 0; m < NREC; ++m) stsv<VEC>(ine + (size_t)m * tl, x[m]);
     }
   }
 
@@ -297,12 +307,34 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
 #pragma unroll
     for (int k = 0; k < kVec; ++k) y.v[k] = 0.f;
     const int q1 = ep.f_csr_ptr[oc + 1];
+    if constexpr (LAYOUT >= 0) {
+      // channel matrices: a handful of entries per row
 #pragma unroll 2
-    for (int q = ep.f_csr_ptr[oc]; q < q1; ++q) {
-      const float c = ep.f_csr_val[q];
-      const V4 xm = lds4(byte_off(in_q, ep.f_csr_off[q]));
+      for (int q = ep.f_csr_ptr[oc]; q < q1; ++q) {
+        const float c = ep.f_csr_val[q];
+        const V4 xm = ldsv<VEC>(byte_off(in_q, ep.f_csr_off[q]));
 #pragma unroll
-      for (int k = 0; k < kVec; ++k) y.v[k] += c * xm.v[k];
+        for (int k = 0; k < kVec; ++k) y.v[k] += c * xm.v[k];
+      }
+    } else {
+      // HOA matrices are dense (up to 16 entries per row): batch the loads of eight entries ahead of their use
+      int q = ep.f_csr_ptr[oc];
+      for (; q + 8 <= q1; q += 8) {
+        float c[8];
+        V4 xm[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { c[i] = ep.f_csr_val[q + i]; xm[i] = ldsv<VEC>(byte_off(in_q, ep.f_csr_off[q + i])); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int k = 0; k < kVec; ++k) y.v[k] += c[i] * xm[i].v[k];
+      }
+      for (; q < q1; ++q) {
+        const float c = ep.f_csr_val[q];
+        const V4 xm = ldsv<VEC>(byte_off(in_q, ep.f_csr_off[q]));
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) y.v[k] += c * xm.v[k];
+      }
     }
     // element mix gain, IAMF_decoder.c:1392-1405
     if (eg_on) {
@@ -318,7 +350,7 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
         for (int k = 0; k < kVec; ++k) y.v[k] = 0.f + y.v[k];
       }
     } else {
-      const V4 p = lds4(dst);
+      const V4 p = ldsv<VEC>(dst);
 #pragma unroll
       for (int k = 0; k < kVec; ++k) y.v[k] = p.v[k] + y.v[k];
     }
@@ -335,9 +367,9 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
 #pragma unroll
       for (int k = 0; k < kVec; ++k) peak.v[k] = fmaxf(peak.v[k], fabsf(y.v[k]));
     }
-    sts4(dst, y);
+    stsv<VEC>(dst, y);
   }
-  if (last && pkt) sts4(pkt, peak);
+  if (last && pkt) stsv<VEC>(pkt, peak);
 }
 
 __device__ __noinline__ void store_any(char *out, size_t idx, float x, int bits) {
@@ -445,8 +477,15 @@ __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float 
   }
 }
 
-template <int L0, int N0, int L1, int N1>
-__global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
+// VEC samples per thread in the render / output stages, THREADS per block.  The per-tile latency of a block is one
+// thread's serial instruction stream: pipelines that fit many streams per SM (small tiles) run 4 samples per thread
+// in 64-thread blocks (fewest instructions); pipelines whose rings are large (few streams per SM) spread a tile over
+// more, lighter threads to keep the SM's schedulers fed.
+template <int L0, int N0, int L1, int N1, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 ? 4 : 2))) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
+  constexpr int kVec = VEC;
+  constexpr int kFusedThreads = THREADS;
+  typedef Vec<VEC> V4;
   extern __shared__ __align__(128) float fsm[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ __align__(16) FrameRec s_fr;      // resolved parameters of the frame being rendered
@@ -580,8 +619,8 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
         if (pos >= C) pos -= C;
         float *yt = Y + pos;
         float *pkt = plan.limiter ? PK + pos : nullptr;
-        fused_element<L0, N0>(plan, a, 0, fr, sf, i0, true, N1 == 0, IN + q, TL, yt, C, pkt);
-        if constexpr (N1 > 0) fused_element<L1, N1>(plan, a, 1, fr, sf, i0, false, true, IN + q, TL, yt, C, pkt);
+        fused_element<L0, N0, VEC>(plan, a, 0, fr, sf, i0, true, N1 == 0, IN + q, TL, yt, C, pkt);
+        if constexpr (N1 > 0) fused_element<L1, N1, VEC>(plan, a, 1, fr, sf, i0, false, true, IN + q, TL, yt, C, pkt);
       }
       // a trimmed tile: move its surviving samples [lo_t, hi_t) to the front of the tile (iamf_frame_trim,
       // IAMF_decoder.c:1361-1381); rare (first / last frames), one row at a time through registers
@@ -768,12 +807,12 @@ __global__ void __launch_bounds__(kFusedThreads, 7) k_fused(const __grid_constan
           V4 gg;
 #pragma unroll
           for (int u = 0; u < kVec; ++u) gg.v[u] = 1.f;
-          if (apply_gain) gg = lds4(G + k4);
+          if (apply_gain) gg = ldsv<VEC>(G + k4);
           uint32_t *wq = (uint32_t *)((int16_t *)out + o0 * co);
           const int half = co >> 1;
 #pragma unroll 1
           for (int c = 0; c < co; c += 2) {
-            const V4 v0 = lds4(Y + (size_t)c * C + pos), v1 = lds4(Y + (size_t)(c + 1) * C + pos);
+            const V4 v0 = ldsv<VEC>(Y + (size_t)c * C + pos), v1 = ldsv<VEC>(Y + (size_t)(c + 1) * C + pos);
 #pragma unroll
             for (int u = 0; u < kVec; ++u) {
               float y0 = v0.v[u], y1 = v1.v[u];
