@@ -170,6 +170,11 @@ struct iamfb_plan {
   int fused_variant;       // 0: 4 samples per thread, 64 threads; 1: 2 samples, 128 threads; 2: 1 sample, 256 threads
   int fused_tile;          // samples per tile
   size_t fused_smem;       // dynamic shared memory per block
+  // pipelined variant of the fused kernel (scanner warp off the critical path), for the streams without trims
+  bool pipe;
+  int pipe_tile;
+  size_t pipe_smem;
+  KernelPlan kp_pipe;      // kp with the staged-row offsets of the pipelined kernel's tile size
 };
 
 struct iamfb_batch {
@@ -711,6 +716,70 @@ static int launch_fused(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa
   return IAMFB_OK;
 }
 
+// staged-row byte offsets and the row-compressed render matrix of the fused kernels, for a tile of tl samples
+static void fill_fused_offsets(KernelPlan &kp, int tl, int nin) {
+  const int co = kp.out_channels;
+  int row_base = 0;
+  for (int e = 0; e < kp.n_elements; ++e) {
+    ElPlan &ep = kp.el[e];
+    ep.f_row_off = row_base * tl * 4;
+    for (int c = 0; c < kChCount; ++c) {
+      ep.f_src_off[c] = (ep.kind == IAMFB_EL_CHANNEL && ep.src_row[c] >= 0) ? (row_base + ep.src_row[c]) * tl * 4 : nin * tl * 4;
+      ep.f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
+    }
+    ep.f_n_gain = 0;
+    if (ep.kind == IAMFB_EL_CHANNEL)
+      for (int c = 1; c < kChCount; ++c)
+        if (((ep.gain_mask >> c) & 1u) && ep.src_row[c] >= 0 && ep.f_n_gain < IAMFB_MAX_LAYOUT_CH) {
+          ep.f_gain_off[ep.f_n_gain] = ep.f_src_off[c];
+          ep.f_gain_val[ep.f_n_gain] = ep.gain[c];
+          ++ep.f_n_gain;
+        }
+    int q = 0;
+    for (int oc = 0; oc < co; ++oc) {
+      ep.f_csr_ptr[oc] = (unsigned short)q;
+      const int n = ep.out_slot[oc];
+      if (n < 0) continue;
+      for (int m = 0; m < ep.n_rec; ++m) {
+        const float c = ep.mat[n * ep.n_rec + m];
+        if (c == 0.f) continue;       // adding +-0 never changes the running sum (it starts at +0): exact skip
+        // reconstructed channel m is written back over staged row m of the element; a mono-mapped ambisonics
+        // channel is read straight from the decoded row it maps to
+        const int xrow = (ep.kind == IAMFB_EL_SCENE && ep.ambi_mode == 0) ? ep.ambi_map[m] : m;
+        ep.f_csr_off[q] = (row_base + xrow) * tl * 4;
+        ep.f_csr_val[q] = c;
+        ++q;
+      }
+    }
+    for (int oc = co; oc <= kMaxOut; ++oc) ep.f_csr_ptr[oc] = (unsigned short)q;
+    row_base += ep.n_in;
+  }
+}
+
+static bool pipe_variant_exists(int v) { return v == 1 || v == 2 || v == 5 || v == 7 || v == 100 || v == 101; }
+
+static int launch_fused_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa, int S) {
+  const KernelPlan &kp = p->kp_pipe;
+  cudaStream_t st = ctx->stream;
+  const size_t smem = p->pipe_smem;
+#define PCASE(ID, L0, N0, L1, N1)                                                                                       \
+  case ID: {                                                                                                            \
+    CU(cudaFuncSetAttribute(k_fused_pipe<L0, N0, L1, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    ScopedKernelTimer tm_(ctx, "k_fused_pipe");                                                                         \
+    k_fused_pipe<L0, N0, L1, N1><<<S, kPipeThreads, smem, st>>>(kp, fa);                                               \
+  } break;
+  switch (fused_variant(p->tmpl, kp.n_elements)) {
+    PCASE(1, 1, 2, 0, 0) PCASE(2, 2, 6, 0, 0) PCASE(5, 5, 8, 0, 0) PCASE(7, 7, 12, 0, 0)
+    PCASE(100, 7, 12, -1, 4) PCASE(101, -1, 4, 7, 12)
+    default: return fail(IAMFB_ERR_INTERNAL, "no pipelined fused kernel variant");
+  }
+#undef PCASE
+  cudaError_t e_ = cudaGetLastError();
+  if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_fused_pipe failed: %s", cudaGetErrorString(e_));
+  ++ctx->launches;
+  return IAMFB_OK;
+}
+
 extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb_plan **out) {
   if (!ctx || !d || !out) return fail(IAMFB_ERR_BAD_ARG, "plan_create: null argument");
   if (d->frame_size <= 0 || d->frame_size > 32768) return fail(IAMFB_ERR_BAD_ARG, "frame_size %d", d->frame_size);
@@ -835,41 +904,34 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
           if (p->fused_variant < 0 || p->fused_variant > 2) p->fused_variant = 0;
         }
         p->fused_smem = sizeof(float) * smem_floats(tl);
-        // staged-row byte offsets and the row-compressed render matrix of the fused kernel
-        int row_base = 0;
-        for (int e = 0; e < kp.n_elements; ++e) {
-          ElPlan &ep = kp.el[e];
-          ep.f_row_off = row_base * tl * 4;
-          for (int c = 0; c < kChCount; ++c) {
-            ep.f_src_off[c] = (ep.kind == IAMFB_EL_CHANNEL && ep.src_row[c] >= 0) ? (row_base + ep.src_row[c]) * tl * 4 : nin * tl * 4;
-            ep.f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
-          }
-          ep.f_n_gain = 0;
-          if (ep.kind == IAMFB_EL_CHANNEL)
-            for (int c = 1; c < kChCount; ++c)
-              if (((ep.gain_mask >> c) & 1u) && ep.src_row[c] >= 0 && ep.f_n_gain < IAMFB_MAX_LAYOUT_CH) {
-                ep.f_gain_off[ep.f_n_gain] = ep.f_src_off[c];
-                ep.f_gain_val[ep.f_n_gain] = ep.gain[c];
-                ++ep.f_n_gain;
-              }
-          int q = 0;
-          for (int oc = 0; oc < co; ++oc) {
-            ep.f_csr_ptr[oc] = (unsigned short)q;
-            const int n = ep.out_slot[oc];
-            if (n < 0) continue;
-            for (int m = 0; m < ep.n_rec; ++m) {
-              const float c = ep.mat[n * ep.n_rec + m];
-              if (c == 0.f) continue;       // adding +-0 never changes the running sum (it starts at +0): exact skip
-              // reconstructed channel m is written back over staged row m of the element; a mono-mapped ambisonics
-              // channel is read straight from the decoded row it maps to
-              const int xrow = (ep.kind == IAMFB_EL_SCENE && ep.ambi_mode == 0) ? ep.ambi_map[m] : m;
-              ep.f_csr_off[q] = (row_base + xrow) * tl * 4;
-              ep.f_csr_val[q] = c;
-              ++q;
+        // pipelined variant: tiles that divide the frame, rings of 240 + 2 tiles, doubled WM / thr/WM / gain buffers,
+        // 7 streams per SM
+        p->pipe = false;
+        {
+          const char *penv = getenv("IAMFB_PIPE");
+          // measured on configs[1]: 0.91 ms quiet / 1.02 ms default against 0.48 / 0.77 ms for the sequential kernel - the
+          // scan does leave the critical path, but smaller tiles (160) and the generic sliding maximum cost more issue
+          // slots than the overlap wins back.  Kept selectable (IAMFB_PIPE=1) and tested; off by default.
+          const bool pwant = penv && atoi(penv) != 0;
+          if (pwant && kp.limiter && pipe_variant_exists(fused_variant(p->tmpl, kp.n_elements))) {
+            const int budget = (int)((233472 / 7 - 1024 - 1024) / 4);
+            // floats(t) = (nin+1) t + (co+1)(240 + 2t) + 6t + 2(t + kWmPad)
+            const int t_max = (budget - (co + 1) * kLimDelay - 2 * kWmPad) / (nin + 1 + 2 * (co + 1) + 8);
+            int best = 0;
+            for (int t = 64; t <= t_max && t <= 512; t += 4)
+              if (kp.frame_size % t == 0) best = t;
+            if (best >= 96) {
+              p->pipe = true;
+              p->pipe_tile = best;
+              p->pipe_smem = sizeof(float) * ((size_t)(nin + 1) * best + (size_t)(co + 1) * (kLimDelay + 2 * best) + 6 * (size_t)best +
+                                              2 * ((size_t)best + kWmPad));
             }
           }
-          for (int oc = co; oc <= kMaxOut; ++oc) ep.f_csr_ptr[oc] = (unsigned short)q;
-          row_base += ep.n_in;
+        }
+        fill_fused_offsets(kp, tl, nin);
+        if (p->pipe) {
+          p->kp_pipe = kp;
+          fill_fused_offsets(p->kp_pipe, p->pipe_tile, nin);
         }
       }
     }
@@ -1111,6 +1173,15 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     fa.n_frames = flush ? 0 : F;
     fa.flush = flush ? 1 : 0;
     fa.tile = p->fused_tile;
+    fa.only_irregular = 0;
+    if (p->pipe && !flush) {
+      // untrimmed streams: the pipelined kernel; whatever it left alone (k_resolve flags them): the sequential one
+      FusedArgs fp2 = fa;
+      fp2.tile = p->pipe_tile;
+      int r = launch_fused_pipe(ctx, p, fp2, S);
+      if (r) return r;
+      fa.only_irregular = 1;
+    }
     return launch_fused(ctx, p, fa, S);
   }
   float *tl_first = kp.resample ? b->d_tl_a : b->d_tl_b;

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(64) k_resolve(const __grid_constant__ KernelPl
   const long long rs_out0 = gst.rs_out_total;
   int lim_pad = gst.lim_pad, lim_init = gst.lim_init;
   const int pad_at_start = lim_pad;
-  int t_off = 0, lim_in_total = 0, sub = 0;
+  int t_off = 0, lim_in_total = 0, sub = 0, irregular = a.flush ? 1 : 0;
   SubmitRec sr;
   for (int f = 0; f < a.n_frames; ++f) {
     while (sub <= a.n_sub && a.sub_frame[sub] == f) sr.sub_off[sub++] = lim_in_total;
@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(64) k_resolve(const __grid_constant__ KernelPl
       fr.vstart = 0;
       fr.vlen = 0;
       fr.t_off = t_off;
+      irregular = 1;
       if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = 0;
       continue;
     }
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(64) k_resolve(const __grid_constant__ KernelPl
     fr.vlen = vlen;
     fr.t_off = t_off;
     t_off += vlen;
+    if (ts != 0 || vlen != N) irregular = 1;
     // --- per-frame sample count returned to the caller
     int cnt = vlen;
     if (vlen > 0 && plan.resample) {
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(64) k_resolve(const __grid_constant__ KernelPl
     if (a.out_counts) a.out_counts[s] = cnt;
   }
   sr.lim_len = lim_in_total;
+  sr.irregular = irregular;
   for (; sub <= kMaxSub; ++sub) sr.sub_off[sub] = lim_in_total;
   if (a.flush) sr.sub_off[0] = 0;
   sr.out_skip = pad_at_start - lim_pad;

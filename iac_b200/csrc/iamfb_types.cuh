@@ -125,6 +125,8 @@ struct SubmitRec {
   int lim_len;                     // samples entering the limiter stage this submit
   int out_len;                     // samples written to pcm
   int out_skip;                    // limiter priming samples dropped this submit
+  int irregular;                   // some frame of this submit is trimmed / missing (or this is a flush): the stream
+                                   // takes the sequential fused kernel instead of the pipelined one
   long long rs_out_first;          // absolute index of the first resampler output this submit
   int sub_off[kMaxSub + 1];        // limiter-stage sample offsets of the sub-chunk boundaries (sub_off[n_sub] == lim_len)
 };
