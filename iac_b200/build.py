@@ -14,6 +14,7 @@ LIB = os.path.join(PKG, "libiamf_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "--fmad=false",          # the reference is built without FMA contraction (x86-64 baseline): keep mul and add apart
+    "--expt-relaxed-constexpr",   # constexpr table look-ups (iamfb_stream.cuh) are evaluated at compile time on both sides
     "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
 ]
 

@@ -13,6 +13,7 @@
 #include "iamfb_kernels.cuh"
 #include "iamfb_fused.cuh"
 #include "iamfb_matrices.inc"
+#include "iamfb_stream.cuh"
 
 using namespace iamfb;
 
@@ -175,6 +176,11 @@ struct iamfb_plan {
   int pipe_tile;
   size_t pipe_smem;
   KernelPlan kp_pipe;      // kp with the staged-row offsets of the pipelined kernel's tile size
+  // register-resident pipelined kernel (k_stream) for the channel-based single-element signatures it is instantiated
+  // for; streams with trims / flushes / animated gains still take k_fused
+  bool stream;
+  int stream_sig;          // layout * 16 + target
+  size_t stream_smem;
 };
 
 struct iamfb_batch {
@@ -780,6 +786,35 @@ static int launch_fused_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArg
   return IAMFB_OK;
 }
 
+// (layout, target) pairs k_stream is instantiated for
+#define IAMFB_STREAM_SIGS(X) X(7, 1) X(1, 0)
+static bool stream_sig_exists(int layout, int target) {
+#define X(L, T) if (layout == L && target == T) return true;
+  IAMFB_STREAM_SIGS(X)
+#undef X
+  return false;
+}
+static int launch_stream(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa, int S) {
+  const KernelPlan &kp = p->kp;
+  cudaStream_t st = ctx->stream;
+  const size_t smem = p->stream_smem;
+  bool done = false;
+#define X(L, T)                                                                                                       \
+  if (!done && p->stream_sig == L * 16 + T) {                                                                         \
+    CU(cudaFuncSetAttribute(k_stream<L, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    ScopedKernelTimer tm_(ctx, "k_stream");                                                                           \
+    k_stream<L, T><<<S, kStreamThreads, smem, st>>>(kp, fa);                                                          \
+    done = true;                                                                                                      \
+  }
+  IAMFB_STREAM_SIGS(X)
+#undef X
+  if (!done) return fail(IAMFB_ERR_INTERNAL, "no k_stream variant");
+  cudaError_t e_ = cudaGetLastError();
+  if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_stream failed: %s", cudaGetErrorString(e_));
+  ++ctx->launches;
+  return IAMFB_OK;
+}
+
 extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb_plan **out) {
   if (!ctx || !d || !out) return fail(IAMFB_ERR_BAD_ARG, "plan_create: null argument");
   if (d->frame_size <= 0 || d->frame_size > 32768) return fail(IAMFB_ERR_BAD_ARG, "frame_size %d", d->frame_size);
@@ -925,6 +960,32 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
               p->pipe_tile = best;
               p->pipe_smem = sizeof(float) * ((size_t)(nin + 1) * best + (size_t)(co + 1) * (kLimDelay + 2 * best) + 6 * (size_t)best +
                                               2 * ((size_t)best + kWmPad));
+            }
+          }
+        }
+        // k_stream: one channel-based element through a channel->channel matrix that matches the compile-time table,
+        // limiter on, 16-bit output, frames that are whole limiter windows
+        p->stream = false;
+        {
+          const char *senv = getenv("IAMFB_STREAM");
+          const bool swant = !senv || atoi(senv) != 0;
+          const ElPlan &ep = kp.el[0];
+          if (swant && kp.n_elements == 1 && ep.kind == IAMFB_EL_CHANNEL && ep.renderer == kRdrM2M && kp.limiter && kp.bit_depth == 16 &&
+              kp.frame_size % kStreamTile == 0 && stream_sig_exists(ep.layout, d->target)) {
+            const int idx = m2m_find(ep.layout, d->target);
+            bool same = idx >= 0 && k_m2m_index[idx].m == ep.n_rec && k_m2m_index[idx].n == co && ep.n_mat_out == co;
+            for (int oc = 0; same && oc < co; ++oc) {
+              if (ep.out_slot[oc] != oc) same = false;
+              for (int m = 0; same && m < ep.n_rec; ++m) {
+                uint32_t bits;
+                memcpy(&bits, &ep.mat[oc * ep.n_rec + m], 4);
+                if (bits != k_matrix_pool[k_m2m_index[idx].off + m * co + oc]) same = false;
+              }
+            }
+            if (same) {
+              p->stream = true;
+              p->stream_sig = ep.layout * 16 + d->target;
+              p->stream_smem = sizeof(float) * ((size_t)co * 3 * kStreamTile + 10 * (size_t)kStreamTile);
             }
           }
         }
@@ -1174,7 +1235,12 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     fa.flush = flush ? 1 : 0;
     fa.tile = p->fused_tile;
     fa.only_irregular = 0;
-    if (p->pipe && !flush) {
+    if (p->stream && !flush && !io->gain_ramp[0] && !io->out_gain_ramp) {
+      // untrimmed streams: the register-resident pipelined kernel; the rest (flagged by k_resolve): k_fused
+      int r = launch_stream(ctx, p, fa, S);
+      if (r) return r;
+      fa.only_irregular = 1;
+    } else if (p->pipe && !flush) {
       // untrimmed streams: the pipelined kernel; whatever it left alone (k_resolve flags them): the sequential one
       FusedArgs fp2 = fa;
       fp2.tile = p->pipe_tile;

@@ -46,7 +46,7 @@ def test_no_cpu_fallback():
 def test_matrix_table_pinned():
     inc = os.path.join(ROOT, "iac_b200", "csrc", "iamfb_matrices.inc")
     assert hashlib.sha256(open(inc, "rb").read()).hexdigest() == \
-        "4e1f0997a441b5140698b8de718be00e8a03331e556402dca49a0ecc796797dc"
+        "5f28d753d607602c7ee6011aed58e096da621a7df8142bb82ffb63e92fecfddd"
 
 
 def test_matrices_equal_reference():

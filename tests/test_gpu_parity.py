@@ -70,3 +70,18 @@ def test_pipelined_fused_kernel_bit_exact(monkeypatch):
     compare(S.c2_714_to_B(peak_db=(-3.0, 3.0)), 21, 9, [4, 5], seed=13)
     compare(S.c1_stereo(trims={0: (312, 0), 5: (0, 100)}, peak_db=(0.0, 2.0)), 6, 8, [8], seed=14)
     compare(S.c4_714_foa_binaural(), 9, 6, [2, 4], seed=15)
+
+
+def test_sequential_fused_kernel_still_bit_exact(monkeypatch):
+    # k_stream (register-resident, pipelined) is the default for the signatures it is instantiated for; k_fused must
+    # stay correct for them behind IAMFB_STREAM=0 (it also renders their trimmed / flushed streams)
+    monkeypatch.setenv("IAMFB_STREAM", "0")
+    compare(S.c2_714_to_B(), 9, 6, [4, 2], seed=3)
+    compare(S.c1_stereo(peak_db=(-3.0, 3.0)), 5, 6, [6], seed=4)
+
+
+def test_stream_kernel_mixed_with_trimmed_submits():
+    # first submit untrimmed (k_stream), later submits carry trimmed frames (k_fused takes those streams): the limiter
+    # history and state must hand over between the two kernels
+    compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31)
+    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32)
