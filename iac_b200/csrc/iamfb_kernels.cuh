@@ -163,7 +163,13 @@ __global__ void __launch_bounds__(64) k_resolve(const __grid_constant__ KernelPl
       ef.w = c_w_table[min(max(w_idx, 0), 10)];
       ef.gain = fp.el[e].mix_gain;
       // --- dmx_rms factor update, demixer.c:443-475: sfavg = 0.25*sf + 0.75*last, for every channel of the list
+      // (slots without a recon gain hold 1.0, which the branch-free multiply of k_stream relies on)
       unsigned int rmask = 0;
+      {
+        float4 *rl = reinterpret_cast<float4 *>(ef.rlast);
+#pragma unroll
+        for (int i = 0; i < 2 * IAMFB_MAX_LAYOUT_CH / 4; ++i) rl[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+      }
 #pragma unroll
       for (int c = 1; c < kChCount; ++c) {
         const int b = ep.recon_bit[c];

@@ -45,6 +45,8 @@ struct ElPlan {
   int f_gain_off[IAMFB_MAX_LAYOUT_CH];
   float f_gain_val[IAMFB_MAX_LAYOUT_CH];
   int f_row_off;                   // byte offset of the element's first staged row
+  // k_stream: byte offset of every IAChannel's row inside the staged tile ([n_in][240] floats), -1 when not transmitted
+  int s_row_off[kChCount];
   unsigned short f_csr_ptr[kMaxOut + 1];
   int f_csr_off[kMaxOut * kMaxRec];
   float f_csr_val[kMaxOut * kMaxRec];
@@ -108,11 +110,12 @@ struct ElFrame {
   float w;                         // get_w(weight_state_idx)
   float dmr_alpha, dmr_beta, dmr_gamma, dmr_delta, dmr_tl;
   unsigned int rmask;              // layout slots with a recon gain this frame
-  float rlast[IAMFB_MAX_LAYOUT_CH], rcur[IAMFB_MAX_LAYOUT_CH];   // by layout slot
+  float rlast[IAMFB_MAX_LAYOUT_CH], rcur[IAMFB_MAX_LAYOUT_CH];   // by layout slot; 1.0 in the slots outside rmask
   float gain;                      // element mix gain constant
+  int pad_[3];                     // rlast / rcur start on 16-byte boundaries in every element of a FrameRec
 };
 
-struct FrameRec {
+struct __align__(16) FrameRec {
   ElFrame el[kMaxEl];
   float out_gain;
   int vstart, vlen;                // valid samples of this frame after trimming
