@@ -982,7 +982,12 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
                 if (bits != k_matrix_pool[k_m2m_index[idx].off + m * co + oc]) same = false;
               }
             }
+            // an output gain on a channel of the reconstructed layout itself (not on the layers it is derived from):
+            // rare, left to k_fused
+            for (int m = 0; same && m < ep.n_rec; ++m)
+              if ((ep.gain_mask >> ep.rec_ch[m]) & 1u) same = false;
             if (same) {
+              for (int c = 0; c < kChCount; ++c) kp.el[0].f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
               for (int c = 0; c < kChCount; ++c)
                 kp.el[0].s_row_off[c] = ep.src_row[c] >= 0 ? ep.src_row[c] * kStreamTile * 4 : -1;
               p->stream = true;

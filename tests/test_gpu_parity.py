@@ -85,3 +85,10 @@ def test_stream_kernel_mixed_with_trimmed_submits():
     # history and state must hand over between the two kernels
     compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31)
     compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32)
+
+
+def test_stream_kernel_clipping_quantiser():
+    # limiter threshold above full scale: samples beyond +-1.0 reach the quantiser and must saturate like
+    # FLOAT2INT16 (IAMF_decoder.c:100-103) does
+    compare(S.c1_stereo(threshold_db=6.0, peak_db=(0.0, 8.0)), 9, 6, [6], seed=41)
+    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42)
