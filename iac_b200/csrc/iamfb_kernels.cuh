@@ -72,6 +72,7 @@ struct ResolveArgs {
   const float *qf_table;              // 256 entries: (float)(q / 255.0)  (fixedp11_5.c:53-55)
   int n_streams, n_frames;
   int flush;                          // end-of-stream pass: no frames, 240 limiter zeros (+ resampler tail)
+  int stage_params;                   // the block's raw parameters fit in shared memory
   int n_sub;                          // sub-chunks of this submit
   int sub_frame[kMaxSub + 1];         // frame index where each sub-chunk starts (sub_frame[n_sub] == n_frames)
 };
@@ -90,12 +91,27 @@ __device__ __forceinline__ long long rs_outputs_until(const KernelPlan &p, long 
 // registers (recon gains are kept per IAChannel, so every array index is a compile-time constant) and writes the
 // element's part of each frame record straight to global memory; pass 2 walks the frames for the stream-level
 // bookkeeping (trimming, time-line placement, sample counts).
-__global__ void __launch_bounds__(64) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// The raw parameters of the block's streams (contiguous: [stream][frame] records of 48 bytes) are first brought into
+// shared memory with coalesced 16-byte loads when they fit (a.stage_params), so that the serial walk over the frames
+// does not pay one global-memory round trip per frame.
+constexpr int kResolveThreads = 32;
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  const int s0 = blockIdx.x * blockDim.x;
+  const int s = s0 + threadIdx.x;
+  if (a.stage_params && a.n_frames > 0) {
+    const int n_str = min((int)blockDim.x, a.n_streams - s0);
+    const size_t n16 = (size_t)n_str * a.n_frames * sizeof(iamfb_frame_params) / 16;
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.params + (size_t)s0 * a.n_frames);
+    uint4 *dst = reinterpret_cast<uint4 *>(rsm);
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
   if (s >= a.n_streams) return;
   StreamState &gst = a.state[s];
   const int N = plan.frame_size;
-  const iamfb_frame_params *params = a.params + (size_t)s * a.n_frames;
+  const iamfb_frame_params *params = a.stage_params ? reinterpret_cast<const iamfb_frame_params *>(rsm) + (size_t)threadIdx.x * a.n_frames
+                                                     : a.params + (size_t)s * a.n_frames;
   FrameRec *frames = a.frames + (size_t)s * a.n_frames;
 
   // ---------------------------------------------------------------- pass 1: per element
