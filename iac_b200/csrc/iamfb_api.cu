@@ -1216,11 +1216,11 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     a.flush = flush ? 1 : 0;
     a.n_sub = n_sub;
     for (int c = 0; c <= kMaxSub; ++c) a.sub_frame[c] = sub_frame[c];
-    static_assert(sizeof(iamfb_frame_params) % 16 == 0, "k_resolve stages the parameter records with 16-byte loads");
-    const size_t rsmem = (size_t)kResolveThreads * a.n_frames * sizeof(iamfb_frame_params);
-    a.stage_params = (a.n_frames > 0 && rsmem <= 160 * 1024 && ((size_t)a.params & 15) == 0) ? 1 : 0;
-    if (a.stage_params && rsmem > 48 * 1024) CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    { ScopedKernelTimer tm_(ctx, "k_resolve"); k_resolve<<<(S + kResolveThreads - 1) / kResolveThreads, kResolveThreads, a.stage_params ? rsmem : 0, st>>>(kp, a); }
+    {
+      const int per_block = kResolveThreads / 32;   // one warp per stream
+      ScopedKernelTimer tm_(ctx, "k_resolve");
+      k_resolve<<<(S + per_block - 1) / per_block, kResolveThreads, 0, st>>>(kp, a);
+    }
     LAUNCH_CHECK("k_resolve");
   }
   if (p->fused) {

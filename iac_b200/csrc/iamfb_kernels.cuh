@@ -72,7 +72,6 @@ struct ResolveArgs {
   const float *qf_table;              // 256 entries: (float)(q / 255.0)  (fixedp11_5.c:53-55)
   int n_streams, n_frames;
   int flush;                          // end-of-stream pass: no frames, 240 limiter zeros (+ resampler tail)
-  int stage_params;                   // the block's raw parameters fit in shared memory
   int n_sub;                          // sub-chunks of this submit
   int sub_frame[kMaxSub + 1];         // frame index where each sub-chunk starts (sub_frame[n_sub] == n_frames)
 };
@@ -87,44 +86,52 @@ __device__ __forceinline__ long long rs_outputs_until(const KernelPlan &p, long 
   return (lim * den - 1) / num + 1;
 }
 
-// One thread per stream.  Pass 1 walks the frames once per audio element with that element's whole state machine in
-// registers (recon gains are kept per IAChannel, so every array index is a compile-time constant) and writes the
-// element's part of each frame record straight to global memory; pass 2 walks the frames for the stream-level
-// bookkeeping (trimming, time-line placement, sample counts).
-// The raw parameters of the block's streams (contiguous: [stream][frame] records of 48 bytes) are first brought into
-// shared memory with coalesced 16-byte loads when they fit (a.stage_params), so that the serial walk over the frames
-// does not pay one global-memory round trip per frame.
-constexpr int kResolveThreads = 32;
+// One WARP per stream.  The raw parameter records of up to 32 frames are loaded at once, lane f holding the 12 words
+// of frame f (one coalesced read per chunk instead of a round trip per frame), and handed to the whole warp frame by
+// frame with shuffles.  Pass 1 walks the frames once per audio element: lane c owns IAChannel c - its recon gain as
+// received, as used by the de-mixer, and its smoothed factor - while the scalar state machines (de-mixing mode, w
+// index, down-mixer mode) run redundantly in every lane; each lane writes its own slot of the frame record.  Pass 2
+// walks the frames for the stream-level bookkeeping (trimming, time-line placement, sample counts), every lane
+// computing the same scalars and lane 0 storing them.
+constexpr int kResolveThreads = 128;   // 4 streams per block
 __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
-  extern __shared__ __align__(16) unsigned char rsm[];
-  const int s0 = blockIdx.x * blockDim.x;
-  const int s = s0 + threadIdx.x;
-  if (a.stage_params && a.n_frames > 0) {
-    const int n_str = min((int)blockDim.x, a.n_streams - s0);
-    const size_t n16 = (size_t)n_str * a.n_frames * sizeof(iamfb_frame_params) / 16;
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.params + (size_t)s0 * a.n_frames);
-    uint4 *dst = reinterpret_cast<uint4 *>(rsm);
-    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
+  __shared__ float s_qf[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_qf[i] = a.qf_table[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (kResolveThreads / 32) + (threadIdx.x >> 5);
   if (s >= a.n_streams) return;
+  constexpr unsigned kFull = 0xffffffffu;
   StreamState &gst = a.state[s];
   const int N = plan.frame_size;
-  const iamfb_frame_params *params = a.stage_params ? reinterpret_cast<const iamfb_frame_params *>(rsm) + (size_t)threadIdx.x * a.n_frames
-                                                     : a.params + (size_t)s * a.n_frames;
+  const uint32_t *pwords = reinterpret_cast<const uint32_t *>(a.params + (size_t)s * a.n_frames);
   FrameRec *frames = a.frames + (size_t)s * a.n_frames;
+  constexpr int kPW = (int)(sizeof(iamfb_frame_params) / 4);   // 12 words: el[0] 0-4, el[1] 5-9, out_gain 10, trims 11
+  static_assert(kPW == 12 && kMaxEl == 2, "parameter record layout");
+  // the chunk of frames [fb, fb + 32): lane l holds frame fb + l
+  uint32_t pw[kPW];
+  auto load_chunk = [&](int fb) {
+    const int f = fb + lane;
+#pragma unroll
+    for (int i = 0; i < kPW; ++i) pw[i] = f < a.n_frames ? __ldg(pwords + (size_t)f * kPW + i) : 0u;
+  };
 
   // ---------------------------------------------------------------- pass 1: per element
+  const int c = lane;                       // this lane's IAChannel id (1 .. kChCount-1 are channels)
+  const bool is_ch = c >= 1 && c < kChCount;
   for (int e = 0; e < plan.n_elements; ++e) {
     const ElPlan &ep = plan.el[e];
     if (ep.kind != IAMFB_EL_CHANNEL) {
-      for (int f = 0; f < a.n_frames; ++f) {
-        if (params[f].trim_start == 0xFFFFu) continue;
-        ElFrame &ef = frames[f].el[e];
-        ef.gain = params[f].el[e].mix_gain;
-        ef.rmask = 0;
-        ef.mode = 0;
-        ef.w = 0.f;
+      for (int fb = 0; fb < a.n_frames; fb += 32) {
+        load_chunk(fb);
+        const int f = fb + lane;
+        if (f < a.n_frames && (pw[11] & 0xffffu) != 0xFFFFu) {
+          ElFrame &ef = frames[f].el[e];
+          ef.gain = __uint_as_float(pw[5 * e + 4]);
+          ef.rmask = 0;
+          ef.mode = 0;
+          ef.w = 0.f;
+        }
       }
       continue;
     }
@@ -132,96 +139,92 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_consta
     int mode = ges.mode, w_idx = ges.w_idx, dmr_mode = ges.dmr_mode, dmr_w_idx = ges.dmr_w_idx;
     float dmr_tl = ges.dmr_tl;
     unsigned int rflags = ges.rflags, re_flags = ges.re_flags;
-    float rgain[kChCount], re_gain[kChCount], sfavg[kChCount];
-#pragma unroll
-    for (int c = 1; c < kChCount; ++c) { rgain[c] = ges.rgain[c]; re_gain[c] = ges.re_gain[c]; sfavg[c] = ges.sfavg[c]; }
+    float rgain = 0.f, re_gain = 0.f, sfavg = 0.f;
+    if (is_ch) { rgain = ges.rgain[c]; re_gain = ges.re_gain[c]; sfavg = ges.sfavg[c]; }
+    const int rbit = is_ch ? ep.recon_bit[c] : -1;     // recon-gain flag bit of this lane's channel, or -1
+    const int slot = is_ch ? ep.slot_of[c] : -1;       // its slot in the layout, or -1
     const bool tl_derived = !((ep.dmr_in_mask >> IAMFB_CH_TL) & 1u) && !((ep.dmr_in_mask >> IAMFB_CH_TR) & 1u);
 
-    for (int f = 0; f < a.n_frames; ++f) {
-      const iamfb_frame_params &fp = params[f];
-      // "this stream has no frame in this step" (grouped handles stepping together, IAMF_decoder_decode_batch):
-      // nothing is decoded, so no state machine advances
-      if (fp.trim_start == 0xFFFFu) continue;
-      ElFrame &ef = frames[f].el[e];
-      // --- recon gain list of the selected layer (latest received wins), IAMF_decoder.c:2238-2274
-      if (fp.el[e].has_recon) {
-        const unsigned int fl = fp.el[e].recon_flags;
-        re_flags = fl;
-        const unsigned int g0 = *reinterpret_cast<const unsigned int *>(fp.el[e].recon_gain);
-        const unsigned int g1 = *reinterpret_cast<const unsigned int *>(fp.el[e].recon_gain + 4);
-        const unsigned int g2 = *reinterpret_cast<const unsigned int *>(fp.el[e].recon_gain + 8);
-#pragma unroll
-        for (int c = 1; c < kChCount; ++c) {
-          const int b = ep.recon_bit[c];
-          if (b >= 0 && ((fl >> b) & 1u)) {
-            const int pos = __popc(fl & ((1u << b) - 1u));          // list position = set bits below
+    for (int fb = 0; fb < a.n_frames; fb += 32) {
+      load_chunk(fb);
+      const int nf = min(32, a.n_frames - fb);
+      for (int fl = 0; fl < nf; ++fl) {
+        const uint32_t w0 = __shfl_sync(kFull, pw[5 * e + 0], fl);
+        const uint32_t g0 = __shfl_sync(kFull, pw[5 * e + 1], fl);
+        const uint32_t g1 = __shfl_sync(kFull, pw[5 * e + 2], fl);
+        const uint32_t g2 = __shfl_sync(kFull, pw[5 * e + 3], fl);
+        const float mix_gain = __uint_as_float(__shfl_sync(kFull, pw[5 * e + 4], fl));
+        const uint32_t trims = __shfl_sync(kFull, pw[11], fl);
+        // "this stream has no frame in this step" (grouped handles stepping together, IAMF_decoder_decode_batch):
+        // nothing is decoded, so no state machine advances
+        if ((trims & 0xffffu) == 0xFFFFu) continue;
+        ElFrame &ef = frames[fb + fl].el[e];
+        // --- recon gain list of the selected layer (latest received wins), IAMF_decoder.c:2238-2274
+        if ((w0 >> 8) & 0xffu) {
+          const unsigned int fl_ = w0 >> 16;
+          re_flags = fl_;
+          if (rbit >= 0 && ((fl_ >> rbit) & 1u)) {
+            const int pos = __popc(fl_ & ((1u << rbit) - 1u));          // list position = set bits below
             const unsigned int wsel = pos < 4 ? g0 : (pos < 8 ? g1 : g2);
-            re_gain[c] = a.qf_table[(wsel >> (8 * (pos & 3))) & 0xffu];
+            re_gain = s_qf[(wsel >> (8 * (pos & 3))) & 0xffu];
           }
         }
-      }
-      // --- demixer_set_recon_gain, demixer.c:621-634 (called every frame when the layer has a recon list)
-      if (ep.recon_present && re_flags) {
-        rflags = re_flags;
-#pragma unroll
-        for (int c = 1; c < kChCount; ++c) {
-          const int b = ep.recon_bit[c];
-          if (b >= 0 && ((re_flags >> b) & 1u)) rgain[c] = re_gain[c];
+        // --- demixer_set_recon_gain, demixer.c:621-634 (called every frame when the layer has a recon list)
+        if (ep.recon_present && re_flags) {
+          rflags = re_flags;
+          if (rbit >= 0 && ((re_flags >> rbit) & 1u)) rgain = re_gain;
         }
-      }
-      // --- demixer_set_demixing_info(mode, -1), demixer.c:592-619
-      const int m_in = fp.el[e].dmx_mode;
-      if (m_in >= 0 && m_in != 3 && m_in <= 6) {
-        mode = m_in;
-        w_idx = c_mix_woff[m_in] > 0 ? min(w_idx + 1, 10) : max(w_idx - 1, 0);
-      }
-      ef.mode = mode;
-      ef.w = c_w_table[min(max(w_idx, 0), 10)];
-      ef.gain = fp.el[e].mix_gain;
-      // --- dmx_rms factor update, demixer.c:443-475: sfavg = 0.25*sf + 0.75*last, for every channel of the list
-      // (slots without a recon gain hold 1.0, which the branch-free multiply of k_stream relies on)
-      unsigned int rmask = 0;
-      {
-        float4 *rl = reinterpret_cast<float4 *>(ef.rlast);
-#pragma unroll
-        for (int i = 0; i < 2 * IAMFB_MAX_LAYOUT_CH / 4; ++i) rl[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-      }
-#pragma unroll
-      for (int c = 1; c < kChCount; ++c) {
-        const int b = ep.recon_bit[c];
-        if (b >= 0 && ((rflags >> b) & 1u)) {
-          const float sf = rgain[c], last = sfavg[c];
+        // --- demixer_set_demixing_info(mode, -1), demixer.c:592-619
+        const int m_in = (int)(signed char)(w0 & 0xffu);
+        if (m_in >= 0 && m_in != 3 && m_in <= 6) {
+          mode = m_in;
+          w_idx = c_mix_woff[m_in] > 0 ? min(w_idx + 1, 10) : max(w_idx - 1, 0);
+        }
+        // --- dmx_rms factor update, demixer.c:443-475: sfavg = 0.25*sf + 0.75*last, for every channel of the list
+        // (slots without a recon gain hold 1.0, which the branch-free multiply of k_stream relies on)
+        const bool upd = rbit >= 0 && ((rflags >> rbit) & 1u);
+        float last = sfavg, cur = sfavg;
+        if (upd) {
+          const float sf = rgain;
           const float Nf = 7.f;
-          const float cur = (2 / (Nf + 1)) * sf + (1 - 2 / (Nf + 1)) * last;
-          const int slot = ep.slot_of[c];
-          if (slot >= 0) {
-            rmask |= 1u << slot;
-            ef.rlast[slot] = last;
-            ef.rcur[slot] = cur;
+          cur = (2 / (Nf + 1)) * sf + (1 - 2 / (Nf + 1)) * last;
+          sfavg = cur;
+        }
+        const unsigned int rmask = __reduce_or_sync(kFull, (upd && slot >= 0) ? (1u << slot) : 0u);
+        if (upd && slot >= 0) {
+          ef.rlast[slot] = last;
+          ef.rcur[slot] = cur;
+        }
+        if (lane < 2 * IAMFB_MAX_LAYOUT_CH && !((rmask >> (lane % IAMFB_MAX_LAYOUT_CH)) & 1u)) ef.rlast[lane] = 1.f;   // rlast | rcur are contiguous
+        // --- DMRenderer_set_mode_weight(mode, -1), downmix_renderer.c:180-216
+        if (ep.renderer == kRdrDMR) {
+          if (m_in >= 0 && m_in != 3 && m_in < 7) {
+            dmr_mode = m_in;
+            dmr_w_idx = c_mix_woff[m_in] > 0 ? min(dmr_w_idx + 1, 10) : max(dmr_w_idx - 1, 0);
+            if (tl_derived) dmr_tl = c_mix_gamma[m_in] * c_w_table[dmr_w_idx];
           }
-          sfavg[c] = cur;
         }
-      }
-      ef.rmask = rmask;
-      // --- DMRenderer_set_mode_weight(mode, -1), downmix_renderer.c:180-216
-      if (ep.renderer == kRdrDMR) {
-        if (m_in >= 0 && m_in != 3 && m_in < 7) {
-          dmr_mode = m_in;
-          dmr_w_idx = c_mix_woff[m_in] > 0 ? min(dmr_w_idx + 1, 10) : max(dmr_w_idx - 1, 0);
-          if (tl_derived) dmr_tl = c_mix_gamma[m_in] * c_w_table[dmr_w_idx];
+        if (lane == 0) {
+          ef.mode = mode;
+          ef.w = c_w_table[min(max(w_idx, 0), 10)];
+          ef.gain = mix_gain;
+          ef.rmask = rmask;
+          if (ep.renderer == kRdrDMR) {
+            const int dm = dmr_mode & 7;
+            ef.dmr_alpha = c_mix_alpha[dm];
+            ef.dmr_beta = c_mix_beta[dm];
+            ef.dmr_gamma = c_mix_gamma[dm];
+            ef.dmr_delta = c_mix_delta[dm];
+            ef.dmr_tl = dmr_tl;
+          }
         }
-        const int dm = dmr_mode & 7;
-        ef.dmr_alpha = c_mix_alpha[dm];
-        ef.dmr_beta = c_mix_beta[dm];
-        ef.dmr_gamma = c_mix_gamma[dm];
-        ef.dmr_delta = c_mix_delta[dm];
-        ef.dmr_tl = dmr_tl;
       }
     }
-    ges.mode = mode; ges.w_idx = w_idx; ges.dmr_mode = dmr_mode; ges.dmr_w_idx = dmr_w_idx; ges.dmr_tl = dmr_tl;
-    ges.rflags = rflags; ges.re_flags = re_flags;
-#pragma unroll
-    for (int c = 1; c < kChCount; ++c) { ges.rgain[c] = rgain[c]; ges.re_gain[c] = re_gain[c]; ges.sfavg[c] = sfavg[c]; }
+    if (lane == 0) {
+      ges.mode = mode; ges.w_idx = w_idx; ges.dmr_mode = dmr_mode; ges.dmr_w_idx = dmr_w_idx; ges.dmr_tl = dmr_tl;
+      ges.rflags = rflags; ges.re_flags = re_flags;
+    }
+    if (is_ch) { ges.rgain[c] = rgain; ges.re_gain[c] = re_gain; ges.sfavg[c] = sfavg; }
   }
 
   // ---------------------------------------------------------------- pass 2: stream-level bookkeeping
@@ -231,45 +234,55 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_consta
   const int pad_at_start = lim_pad;
   int t_off = 0, lim_in_total = 0, sub = 0, irregular = a.flush ? 1 : 0;
   SubmitRec sr;
-  for (int f = 0; f < a.n_frames; ++f) {
-    while (sub <= a.n_sub && a.sub_frame[sub] == f) sr.sub_off[sub++] = lim_in_total;
-    const iamfb_frame_params &fp = params[f];
-    FrameRec &fr = frames[f];
-    if (fp.trim_start == 0xFFFFu) {
-      fr.out_gain = 1.f;
-      fr.vstart = 0;
-      fr.vlen = 0;
-      fr.t_off = t_off;
-      irregular = 1;
-      if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = 0;
-      continue;
-    }
-    fr.out_gain = fp.out_gain;
-    // --- trimming: a fully trimmed frame is decoded (state above advances) but dropped, IAMF_decoder.c:3354-3358
-    const int ts = fp.trim_start, te = fp.trim_end;
-    int vlen = N - ts - te;
-    if (ts == N || te == N || vlen < 0) vlen = 0;
-    fr.vstart = ts;
-    fr.vlen = vlen;
-    fr.t_off = t_off;
-    t_off += vlen;
-    if (ts != 0 || vlen != N) irregular = 1;
-    // --- per-frame sample count returned to the caller
-    int cnt = vlen;
-    if (vlen > 0 && plan.resample) {
-      const long long before = rs_outputs_until(plan, rs_in_total);
-      rs_in_total += vlen;
-      const long long after = rs_outputs_until(plan, rs_in_total);
-      cnt = (int)(after - before);
-    }
-    if (vlen > 0) {
-      lim_in_total += cnt;
-      if (plan.limiter && !lim_init) {
-        if (lim_pad >= cnt) { lim_pad -= cnt; cnt = 0; }
-        else { cnt -= lim_pad; lim_pad = 0; lim_init = 1; }
+  for (int fb = 0; fb < a.n_frames; fb += 32) {
+    load_chunk(fb);
+    const int nf = min(32, a.n_frames - fb);
+    for (int fl = 0; fl < nf; ++fl) {
+      const int f = fb + fl;
+      const float out_gain = __uint_as_float(__shfl_sync(kFull, pw[10], fl));
+      const uint32_t trims = __shfl_sync(kFull, pw[11], fl);
+      while (sub <= a.n_sub && a.sub_frame[sub] == f) sr.sub_off[sub++] = lim_in_total;
+      FrameRec &fr = frames[f];
+      if ((trims & 0xffffu) == 0xFFFFu) {
+        if (lane == 0) {
+          fr.out_gain = 1.f;
+          fr.vstart = 0;
+          fr.vlen = 0;
+          fr.t_off = t_off;
+          if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = 0;
+        }
+        irregular = 1;
+        continue;
       }
+      // --- trimming: a fully trimmed frame is decoded (state above advances) but dropped, IAMF_decoder.c:3354-3358
+      const int ts = (int)(trims & 0xffffu), te = (int)(trims >> 16);
+      int vlen = N - ts - te;
+      if (ts == N || te == N || vlen < 0) vlen = 0;
+      if (lane == 0) {
+        fr.out_gain = out_gain;
+        fr.vstart = ts;
+        fr.vlen = vlen;
+        fr.t_off = t_off;
+      }
+      t_off += vlen;
+      if (ts != 0 || vlen != N) irregular = 1;
+      // --- per-frame sample count returned to the caller
+      int cnt = vlen;
+      if (vlen > 0 && plan.resample) {
+        const long long before = rs_outputs_until(plan, rs_in_total);
+        rs_in_total += vlen;
+        const long long after = rs_outputs_until(plan, rs_in_total);
+        cnt = (int)(after - before);
+      }
+      if (vlen > 0) {
+        lim_in_total += cnt;
+        if (plan.limiter && !lim_init) {
+          if (lim_pad >= cnt) { lim_pad -= cnt; cnt = 0; }
+          else { cnt -= lim_pad; lim_pad = 0; lim_init = 1; }
+        }
+      }
+      if (lane == 0 && a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = cnt;
     }
-    if (a.out_counts) a.out_counts[(size_t)s * a.n_frames + f] = cnt;
   }
 
   sr.in_len = t_off;
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_consta
       lim_in_total = cnt;
     }
     sr.in_len = plan.resample ? (int)(plan.rs_filt_len / 2) : 0;
-    if (a.out_counts) a.out_counts[s] = cnt;
+    if (lane == 0 && a.out_counts) a.out_counts[s] = cnt;
   }
   sr.lim_len = lim_in_total;
   sr.irregular = irregular;
@@ -305,11 +318,13 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_consta
   if (a.flush) sr.sub_off[0] = 0;
   sr.out_skip = pad_at_start - lim_pad;
   sr.out_len = lim_in_total - sr.out_skip;
-  gst.rs_in_total = rs_in_total;
-  gst.rs_out_total = rs_out0 + (plan.resample ? (long long)lim_in_total - (a.flush && plan.limiter ? kLimDelay : 0) : 0);
-  gst.lim_pad = lim_pad;
-  gst.lim_init = lim_init;
-  a.submit[s] = sr;
+  if (lane == 0) {
+    gst.rs_in_total = rs_in_total;
+    gst.rs_out_total = rs_out0 + (plan.resample ? (long long)lim_in_total - (a.flush && plan.limiter ? kLimDelay : 0) : 0);
+    gst.lim_pad = lim_pad;
+    gst.lim_init = lim_init;
+    a.submit[s] = sr;
+  }
 }
 
 // -------------------------------------------------------------------------------------------------------------------
