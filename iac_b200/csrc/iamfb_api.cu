@@ -992,7 +992,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
                 kp.el[0].s_row_off[c] = ep.src_row[c] >= 0 ? ep.src_row[c] * kStreamTile * 4 : -1;
               p->stream = true;
               p->stream_sig = ep.layout * 16 + d->target;
-              p->stream_smem = sizeof(float) * ((size_t)(ep.n_in + 2 * co + 8) * kStreamTile);
+              p->stream_smem = sizeof(float) * ((size_t)(ep.n_in + 2 * co + 6) * kStreamTile);
             }
           }
         }
