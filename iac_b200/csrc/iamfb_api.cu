@@ -171,11 +171,6 @@ struct iamfb_plan {
   int fused_variant;       // 0: 4 samples per thread, 64 threads; 1: 2 samples, 128 threads; 2: 1 sample, 256 threads
   int fused_tile;          // samples per tile
   size_t fused_smem;       // dynamic shared memory per block
-  // pipelined variant of the fused kernel (scanner warp off the critical path), for the streams without trims
-  bool pipe;
-  int pipe_tile;
-  size_t pipe_smem;
-  KernelPlan kp_pipe;      // kp with the staged-row offsets of the pipelined kernel's tile size
   // register-resident pipelined kernel (k_stream) for the channel-based single-element signatures it is instantiated
   // for; streams with trims / flushes / animated gains still take k_fused
   bool stream;
@@ -762,30 +757,6 @@ static void fill_fused_offsets(KernelPlan &kp, int tl, int nin) {
   }
 }
 
-static bool pipe_variant_exists(int v) { return v == 1 || v == 2 || v == 5 || v == 7 || v == 100 || v == 101; }
-
-static int launch_fused_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa, int S) {
-  const KernelPlan &kp = p->kp_pipe;
-  cudaStream_t st = ctx->stream;
-  const size_t smem = p->pipe_smem;
-#define PCASE(ID, L0, N0, L1, N1)                                                                                       \
-  case ID: {                                                                                                            \
-    CU(cudaFuncSetAttribute(k_fused_pipe<L0, N0, L1, N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    ScopedKernelTimer tm_(ctx, "k_fused_pipe");                                                                         \
-    k_fused_pipe<L0, N0, L1, N1><<<S, kPipeThreads, smem, st>>>(kp, fa);                                               \
-  } break;
-  switch (fused_variant(p->tmpl, kp.n_elements)) {
-    PCASE(1, 1, 2, 0, 0) PCASE(2, 2, 6, 0, 0) PCASE(5, 5, 8, 0, 0) PCASE(7, 7, 12, 0, 0)
-    PCASE(100, 7, 12, -1, 4) PCASE(101, -1, 4, 7, 12)
-    default: return fail(IAMFB_ERR_INTERNAL, "no pipelined fused kernel variant");
-  }
-#undef PCASE
-  cudaError_t e_ = cudaGetLastError();
-  if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_fused_pipe failed: %s", cudaGetErrorString(e_));
-  ++ctx->launches;
-  return IAMFB_OK;
-}
-
 // (layout, target) pairs k_stream is instantiated for
 #define IAMFB_STREAM_SIGS(X) X(7, 1) X(1, 0)
 static bool stream_sig_exists(int layout, int target) {
@@ -939,30 +910,6 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
           if (p->fused_variant < 0 || p->fused_variant > 2) p->fused_variant = 0;
         }
         p->fused_smem = sizeof(float) * smem_floats(tl);
-        // pipelined variant: tiles that divide the frame, rings of 240 + 2 tiles, doubled WM / thr/WM / gain buffers,
-        // 7 streams per SM
-        p->pipe = false;
-        {
-          const char *penv = getenv("IAMFB_PIPE");
-          // measured on configs[1]: 0.91 ms quiet / 1.02 ms default against 0.48 / 0.77 ms for the sequential kernel - the
-          // scan does leave the critical path, but smaller tiles (160) and the generic sliding maximum cost more issue
-          // slots than the overlap wins back.  Kept selectable (IAMFB_PIPE=1) and tested; off by default.
-          const bool pwant = penv && atoi(penv) != 0;
-          if (pwant && kp.limiter && pipe_variant_exists(fused_variant(p->tmpl, kp.n_elements))) {
-            const int budget = (int)((233472 / 7 - 1024 - 1024) / 4);
-            // floats(t) = (nin+1) t + (co+1)(240 + 2t) + 6t + 2(t + kWmPad)
-            const int t_max = (budget - (co + 1) * kLimDelay - 2 * kWmPad) / (nin + 1 + 2 * (co + 1) + 8);
-            int best = 0;
-            for (int t = 64; t <= t_max && t <= 512; t += 4)
-              if (kp.frame_size % t == 0) best = t;
-            if (best >= 96) {
-              p->pipe = true;
-              p->pipe_tile = best;
-              p->pipe_smem = sizeof(float) * ((size_t)(nin + 1) * best + (size_t)(co + 1) * (kLimDelay + 2 * best) + 6 * (size_t)best +
-                                              2 * ((size_t)best + kWmPad));
-            }
-          }
-        }
         // k_stream: one channel-based element through a channel->channel matrix that matches the compile-time table,
         // limiter on, 16-bit output, frames that are whole limiter windows
         p->stream = false;
@@ -997,10 +944,6 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
           }
         }
         fill_fused_offsets(kp, tl, nin);
-        if (p->pipe) {
-          p->kp_pipe = kp;
-          fill_fused_offsets(p->kp_pipe, p->pipe_tile, nin);
-        }
       }
     }
   }
@@ -1249,13 +1192,6 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     if (p->stream && !flush && !io->gain_ramp[0] && !io->out_gain_ramp) {
       // untrimmed streams: the register-resident pipelined kernel; the rest (flagged by k_resolve): k_fused
       int r = launch_stream(ctx, p, fa, S);
-      if (r) return r;
-      fa.only_irregular = 1;
-    } else if (p->pipe && !flush) {
-      // untrimmed streams: the pipelined kernel; whatever it left alone (k_resolve flags them): the sequential one
-      FusedArgs fp2 = fa;
-      fp2.tile = p->pipe_tile;
-      int r = launch_fused_pipe(ctx, p, fp2, S);
       if (r) return r;
       fa.only_irregular = 1;
     }

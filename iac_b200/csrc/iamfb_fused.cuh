@@ -40,7 +40,7 @@ struct FusedArgs {
   void *pcm;
   size_t stride_bytes;
   int n_frames, flush, tile;
-  int only_irregular;           // sequential kernel: 1 = only the streams the pipelined kernel left alone
+  int only_irregular;           // 1 = only the streams k_stream left alone (trimmed / missing frames)
 };
 
 constexpr int kWmPad = 320;     // scratch beyond the tile: 240 history + 64 (widest doubling step) + 16
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 
   float *EW = SA, *G = SB;
 
   const SubmitRec sr = a.submit[s];
-  if (a.only_irregular && !sr.irregular) return;   // rendered by k_fused_pipe
+  if (a.only_irregular && !sr.irregular) return;   // rendered by k_stream
   int lj = -1;
   float lS = -1.f, lE = -1.f;
   for (int i = tid; i < TL; i += kFusedThreads) IN[(size_t)(nin0 + nin1) * TL + i] = 0.f;
@@ -891,281 +891,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 
       StreamState &st = a.state[s];
       st.lim_j = lj; st.lim_start = lS; st.lim_end = lE;
     }
-  }
-}
-
-// -------------------------------------------------------------------------------------------------------------------
-// k_fused_pipe: the same stages, software-pipelined inside the block so that the serial limiter recurrence leaves
-// the critical path of a stream.  128 threads: warps 0-2 are WORKERS (stage-in, render, sliding maximum, output),
-// warp 3 is the SCANNER.  In iteration t the scanner walks tile t while the workers write out tile t-1 (with the
-// gains of the previous iteration), render tile t+1 and compute its sliding maximum:
-//
-//     workers   out(t-1) | render(t+1) | wmax(t+1)        (worker-only named barrier between the stages)
-//     scanner   scan(t)
-//     ------------------ __syncthreads ------------------
-//
-// The rings hold 240 + 2 tiles (the delayed samples out(t) will read are exactly the slots render(t+2) overwrites),
-// WM / thr/WM / gain buffers are doubled.  Only streams whose frames are all untrimmed take this kernel (k_resolve
-// flags the others, which the sequential k_fused renders right after); no flush.
-// -------------------------------------------------------------------------------------------------------------------
-constexpr int kPipeThreads = 96, kPipeWorkers = 64, kPipeVec = 4;
-
-__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity) {   // label-free (inlined at several sites)
-  uint32_t ok = 0;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-
-template <int L0, int N0, int L1, int N1>
-__global__ void __launch_bounds__(kPipeThreads, 7) k_fused_pipe(const __grid_constant__ KernelPlan plan, FusedArgs a) {
-  constexpr int VEC = kPipeVec, WN = kPipeWorkers;
-  typedef Vec<VEC> V4;
-  extern __shared__ __align__(128) float fsm[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ __align__(16) FrameRec s_fr;
-  __shared__ float s_acc[kAccCache];
-  __shared__ int s_hot[2], s_apply[2];
-  const int s = blockIdx.x;
-  const SubmitRec sr = a.submit[s];
-  if (sr.irregular) return;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const bool worker = tid < WN;
-  const int N = plan.frame_size, co = plan.out_channels;
-  const int TL = a.tile;
-  const int C = kLimDelay + 2 * TL;
-  const int nin0 = plan.el[0].n_in, nin1 = N1 > 0 ? plan.el[1].n_in : 0;
-  float *IN = fsm;                                   // [nin + 1][TL]
-  float *Y = IN + (size_t)(nin0 + nin1 + 1) * TL;    // [co][C]
-  float *PK = Y + (size_t)co * C;                    // [C]
-  float *WM = PK + C;                                // [2][TL]
-  float *EW = WM + 2 * TL;                           // [2][TL]
-  float *G = EW + 2 * TL;                            // [2][TL]
-  float *SA = G + 2 * TL;                            // [TL + kWmPad]
-  float *SB = SA + TL + kWmPad;                      // [TL + kWmPad]
-  const int tpf = N / TL;                            // tiles per frame
-  const int T = a.n_frames * tpf;
-  const float thr = plan.lim_thr;
-
-  for (int i = tid; i < TL; i += kPipeThreads) IN[(size_t)(nin0 + nin1) * TL + i] = 0.f;
-  for (int i = tid; i < kAccCache; i += kPipeThreads) s_acc[i] = i <= plan.lim_jr + 3 ? a.acc[i] : 0.f;
-#pragma unroll 1
-  for (int c = 0; c <= co; ++c) {
-    const float *src = c < co ? a.hist_y + ((size_t)s * co + c) * kLimDelay : a.hist_pk + (size_t)s * kLimDelay;
-    float *row = c < co ? Y + (size_t)c * C : PK;
-    for (int i = tid; i < kLimDelay; i += kPipeThreads) row[i] = src[i];
-  }
-  for (int i = tid; i < TL + kWmPad; i += kPipeThreads) { SA[i] = 0.f; SB[i] = 0.f; }
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    s_hot[0] = s_hot[1] = 0;
-    s_apply[0] = s_apply[1] = 0;
-  }
-  __syncthreads();
-
-  auto ring_pos = [&](int t) { return (kLimDelay + t * TL) % C; };
-  auto issue = [&](int t) {                          // one thread: bulk copies of tile t's rows into IN
-    const int f = t / tpf, t_off = (t - f * tpf) * TL;
-    const uint32_t row_bytes = (uint32_t)(TL * sizeof(float));
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(nin0 + nin1));
-    const size_t sf = (size_t)s * a.n_frames + f;
-    const float *g0 = a.in[0] + sf * nin0 * N + t_off;
-#pragma unroll 1
-    for (int r = 0; r < nin0; ++r) bulk_g2s(IN + (size_t)r * TL, g0 + (size_t)r * N, row_bytes, &s_bar);
-    if constexpr (N1 > 0) {
-      const float *g1 = a.in[1] + sf * nin1 * N + t_off;
-#pragma unroll 1
-      for (int r = 0; r < nin1; ++r) bulk_g2s(IN + (size_t)(nin0 + r) * TL, g1 + (size_t)r * N, row_bytes, &s_bar);
-    }
-  };
-
-  uint32_t parity = 0;
-  int fr_loaded = -1;
-  // ---- worker stages -------------------------------------------------------------------------------------------------
-  auto render = [&](int t) {
-    const int f = t / tpf, t_off = (t - f * tpf) * TL, sf = s * a.n_frames + f;
-    if (fr_loaded != f) {
-      const int *src = reinterpret_cast<const int *>(a.frames + sf);
-      int *dst = reinterpret_cast<int *>(&s_fr);
-      for (int i = tid; i < (int)(sizeof(FrameRec) / 4); i += WN) dst[i] = src[i];
-      fr_loaded = f;
-      bar_workers();
-    }
-    const FrameRec &fr = s_fr;
-    mbar_wait_poll(&s_bar, parity);
-    parity ^= 1u;
-    const int w = ring_pos(t);
-    for (int q = tid * VEC; q < TL; q += WN * VEC) {
-      int pos = w + q;
-      if (pos >= C) pos -= C;
-      fused_element<L0, N0, VEC>(plan, a, 0, fr, sf, t_off + q, true, N1 == 0, IN + q, TL, Y + pos, C, PK + pos);
-      if constexpr (N1 > 0) fused_element<L1, N1, VEC>(plan, a, 1, fr, sf, t_off + q, false, true, IN + q, TL, Y + pos, C, PK + pos);
-    }
-  };
-  auto wmax = [&](int t) {
-    const int b = t & 1, n = TL;
-    float *wm = WM + b * TL, *ew = EW + b * TL;
-    int base = ring_pos(t) - kLimDelay;
-    if (base < 0) base += C;
-    const int span4 = (n + kLimDelay + 3) >> 2;
-    for (int v = tid; v < span4; v += WN) {              // windows of 8, in registers
-      int p0 = base + 4 * v;
-      if (p0 >= C) p0 -= C;
-      int p1 = p0 + 4;
-      if (p1 >= C) p1 -= C;
-      int p2 = p1 + 4;
-      if (p2 >= C) p2 -= C;
-      const float4 A = *reinterpret_cast<const float4 *>(PK + p0);
-      const float4 B = *reinterpret_cast<const float4 *>(PK + p1);
-      const float4 Cq = *reinterpret_cast<const float4 *>(PK + p2);
-      const float m47 = fmaxf(fmaxf(B.x, B.y), fmaxf(B.z, B.w));
-      const float s3 = A.w, s2 = fmaxf(A.z, s3), s1 = fmaxf(A.y, s2), s0 = fmaxf(A.x, s1);
-      const float p9 = fmaxf(Cq.x, Cq.y), p10 = fmaxf(p9, Cq.z);
-      *reinterpret_cast<float4 *>(SA + 4 * v) =
-          make_float4(fmaxf(s0, m47), fmaxf(fmaxf(s1, m47), Cq.x), fmaxf(fmaxf(s2, m47), p9), fmaxf(fmaxf(s3, m47), p10));
-    }
-    bar_workers();
-    float *src = SA, *dst = SB;
-#pragma unroll 1
-    for (int d = 8; d <= 64; d <<= 1) {                  // windows of 16, 32, 64, 128
-      for (int v = tid; v < span4; v += WN) {
-        const float4 A = *reinterpret_cast<const float4 *>(src + 4 * v);
-        const float4 B = *reinterpret_cast<const float4 *>(src + 4 * v + d);
-        *reinterpret_cast<float4 *>(dst + 4 * v) = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
-      }
-      bar_workers();
-      float *tt = src; src = dst; dst = tt;
-    }
-    bool hot = false;
-    for (int v = tid; 4 * v < n; v += WN) {               // 240 = two overlapping windows of 128
-      const float4 A = *reinterpret_cast<const float4 *>(SA + 4 * v);
-      const float4 B = *reinterpret_cast<const float4 *>(SA + 4 * v + 112);
-      const float4 W = make_float4(fmaxf(A.x, B.x), fmaxf(A.y, B.y), fmaxf(A.z, B.z), fmaxf(A.w, B.w));
-      *reinterpret_cast<float4 *>(wm + 4 * v) = W;
-      hot |= (W.x > thr) || (W.y > thr) || (W.z > thr) || (W.w > thr);
-    }
-    if (hot) s_hot[b] = 1;
-    bar_workers();
-    if (s_hot[b]) {
-      for (int v = tid; 4 * v < n; v += WN) {
-        const float4 W = *reinterpret_cast<const float4 *>(wm + 4 * v);
-        *reinterpret_cast<float4 *>(ew + 4 * v) = make_float4(thr / W.x, thr / W.y, thr / W.z, thr / W.w);
-      }
-    }
-  };
-  char *out = (char *)a.pcm + (size_t)s * a.stride_bytes;
-  auto output = [&](int t) {
-    const int b = t & 1, n = TL;
-    const float *g = G + b * TL;
-    const bool apply_gain = s_apply[b] != 0;
-    const long long base_o = (long long)t * TL - sr.out_skip;
-    const int bits = plan.bit_depth;
-    int rbase = ring_pos(t) - kLimDelay;
-    if (rbase < 0) rbase += C;
-    for (int k4 = tid * VEC; k4 < n; k4 += WN * VEC) {
-      const long long o0 = base_o + k4;
-      const bool full = o0 >= 0;
-      int pos = rbase + k4;
-      if (pos >= C) pos -= C;
-      if (full && bits == 16 && (co & 1) == 0 && (((o0 * co) & 1) == 0)) {
-        V4 gg;
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) gg.v[u] = 1.f;
-        if (apply_gain) gg = ldsv<VEC>(g + k4);
-        uint32_t *wq = (uint32_t *)((int16_t *)out + o0 * co);
-        const int half = co >> 1;
-#pragma unroll 1
-        for (int c = 0; c < co; c += 2) {
-          const V4 v0 = ldsv<VEC>(Y + (size_t)c * C + pos), v1 = ldsv<VEC>(Y + (size_t)(c + 1) * C + pos);
-#pragma unroll
-          for (int u = 0; u < VEC; ++u) {
-            const float y0 = v0.v[u] * gg.v[u], y1 = v1.v[u] * gg.v[u];
-            wq[u * half + (c >> 1)] = (uint32_t)(quant16(y0) & 0xffff) | ((uint32_t)quant16(y1) << 16);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < co; ++c) {
-#pragma unroll 1
-          for (int u = 0; u < VEC; ++u) {
-            if (o0 + u < 0) continue;
-            int pu = pos + u;
-            if (pu >= C) pu -= C;
-            const float x = Y[(size_t)c * C + pu] * (apply_gain ? g[k4 + u] : 1.0f);
-            store_any(out, (size_t)(o0 + u) * co + c, x, bits);
-          }
-        }
-      }
-    }
-  };
-
-  // ---- scanner state ---------------------------------------------------------------------------------------------------
-  int lj = -1;
-  float lS = -1.f, lE = -1.f;
-  if (!worker) {
-    const StreamState &st = a.state[s];
-    lj = st.lim_j; lS = st.lim_start; lE = st.lim_end;
-    if (lj > plan.lim_jr) lj = plan.lim_jr;
-  }
-
-  // ---- prologue: tile 0 rendered and its sliding maximum taken -----------------------------------------------------
-  if (worker) {
-    if (tid == 0) issue(0);
-    render(0);
-    bar_workers();
-    if (tid == 0 && T > 1) issue(1);
-    wmax(0);
-  }
-  __syncthreads();
-  for (int t = 0; t < T; ++t) {
-    if (worker) {
-      if (tid == 0) s_hot[(t + 1) & 1] = 0;
-      if (t >= 1) output(t - 1);
-      bar_workers();                       // out(t-1) has read the slots render(t+1) is about to overwrite
-      if (t + 1 < T) {
-        render(t + 1);
-        bar_workers();
-        if (tid == 0 && t + 2 < T) issue(t + 2);
-        wmax(t + 1);
-      }
-    } else {
-      const int b = t & 1;
-      const bool idle = lj < 0 || lj >= plan.lim_jr;
-      const bool run = s_hot[b] != 0 || !idle;
-      if (run) fused_scan(WM + b * TL, EW + b * TL, G + b * TL, TL, lj, lS, lE, a.acc, s_acc, plan.lim_ja, plan.lim_jr, thr, lane);
-      if (lane == 0) s_apply[b] = run ? 1 : 0;
-    }
-    __syncthreads();
-  }
-  if (worker) output(T - 1);
-  __syncthreads();
-  // the last 240 instants, in time order, are the history of the next submit
-  int from = ring_pos(T) - kLimDelay;
-  if (from < 0) from += C;
-#pragma unroll 1
-  for (int c = 0; c <= co; ++c) {
-    float *dst = c < co ? a.hist_y + ((size_t)s * co + c) * kLimDelay : a.hist_pk + (size_t)s * kLimDelay;
-    const float *row = c < co ? Y + (size_t)c * C : PK;
-    for (int i = tid; i < kLimDelay; i += kPipeThreads) {
-      int pos = from + i;
-      if (pos >= C) pos -= C;
-      dst[i] = row[pos];
-    }
-  }
-  if (tid == WN) {
-    StreamState &st = a.state[s];
-    st.lim_j = lj; st.lim_start = lS; st.lim_end = lE;
   }
 }
 

@@ -63,15 +63,6 @@ def test_multi_kernel_path_still_bit_exact(monkeypatch):
     compare(S.c4_714_foa_binaural(), 7, 6, [1, 5], seed=5)
 
 
-def test_pipelined_fused_kernel_bit_exact(monkeypatch):
-    # k_fused_pipe (scanner warp overlapped with the next tile's render) is off by default; it must stay bit-exact.
-    # trims force the irregular streams of the same submit through the sequential kernel
-    monkeypatch.setenv("IAMFB_PIPE", "1")
-    compare(S.c2_714_to_B(peak_db=(-3.0, 3.0)), 21, 9, [4, 5], seed=13)
-    compare(S.c1_stereo(trims={0: (312, 0), 5: (0, 100)}, peak_db=(0.0, 2.0)), 6, 8, [8], seed=14)
-    compare(S.c4_714_foa_binaural(), 9, 6, [2, 4], seed=15)
-
-
 def test_sequential_fused_kernel_still_bit_exact(monkeypatch):
     # k_stream (register-resident, pipelined) is the default for the signatures it is instantiated for; k_fused must
     # stay correct for them behind IAMFB_STREAM=0 (it also renders their trimmed / flushed streams)
