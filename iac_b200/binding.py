@@ -93,6 +93,8 @@ def lib():
     L.iamfb_plan_destroy.argtypes = [vp]
     L.iamfb_plan_destroy.restype = None
     L.iamfb_plan_out_channels.argtypes = [vp]
+    L.iamfb_plan_kernel_path.argtypes = [vp]
+    L.iamfb_plan_kernel_path.restype = C.c_int
     L.iamfb_plan_max_out_samples.argtypes = [vp, C.c_int]
     L.iamfb_plan_out_stride_bytes.argtypes = [vp, C.c_int]
     L.iamfb_plan_out_stride_bytes.restype = C.c_size_t
@@ -205,6 +207,7 @@ class Engine:
         _check(L.iamfb_plan_create(self.ctx, C.byref(desc), C.byref(self.plan)), "iamfb_plan_create")
         _check(L.iamfb_batch_create(self.plan, n_streams, max_frames, C.byref(self.batch)), "iamfb_batch_create")
         self.out_channels = L.iamfb_plan_out_channels(self.plan)
+        self.kernel_path = L.iamfb_plan_kernel_path(self.plan)   # 0 multi-kernel, 1 k_fused, 2 k_stream
         self.bytes_per_sample = desc.bit_depth // 8 if desc.bit_depth else 4
 
     def close(self):

@@ -758,7 +758,8 @@ static void fill_fused_offsets(KernelPlan &kp, int tl, int nin) {
 }
 
 // (layout, target) pairs k_stream is instantiated for
-#define IAMFB_STREAM_SIGS(X) X(7, 1) X(1, 0)
+// (7.1.4 / 7.1 / 5.1.4 / 5.1 / stereo sources to stereo, 5.1 and the binaural target as the reference builds it)
+#define IAMFB_STREAM_SIGS(X) X(7, 1) X(1, 0) X(7, 0) X(7, 13) X(5, 1) X(4, 1) X(2, 1) X(2, 0) X(1, 1) X(1, 13)
 static bool stream_sig_exists(int layout, int target) {
 #define X(L, T) if (layout == L && target == T) return true;
   IAMFB_STREAM_SIGS(X)
@@ -958,6 +959,11 @@ extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
 }
 
 extern "C" int iamfb_plan_out_channels(const iamfb_plan *p) { return p ? p->kp.out_channels : 0; }
+
+extern "C" int iamfb_plan_kernel_path(const iamfb_plan *p) {
+  if (!p || !p->fused) return IAMFB_PATH_MULTI;
+  return p->stream ? IAMFB_PATH_STREAM : IAMFB_PATH_FUSED;
+}
 
 extern "C" int iamfb_plan_max_out_samples(const iamfb_plan *p, int n_frames) {
   if (!p) return 0;

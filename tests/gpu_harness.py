@@ -6,11 +6,13 @@ import scenarios as S
 from iac_b200 import Engine
 
 
-def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0, s16=False):
+def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0, s16=False, expect_path=None):
     n_streams, F = P.shape
     splits = splits or [F]
     assert sum(splits) == F
     eng = Engine(S.plan_desc(sc), n_streams, max(splits), device=device)
+    if expect_path is not None:
+        assert eng.kernel_path == expect_path, f"{sc.name}: kernel path {eng.kernel_path}, expected {expect_path}"
     co = eng.out_channels
     bps = eng.bytes_per_sample
     counts = [[] for _ in range(n_streams)]

@@ -351,3 +351,24 @@ def run_oracle(sc: Scenario, inputs, P, ramps=None, oramp=None, streams=None, fl
         raw = np.frombuffer(b"".join(chunks), np.uint8)
         results[s] = (counts, raw)
     return results
+
+
+def stream_kernel_cases():
+    """more (layout, target) pairs of the register-resident pipelined kernel (k_stream), with scalable layers"""
+    return [
+        Scenario("714_scalable_to_A", [El("channel", LY_714, [L2, R2, L5, R5, SL7, SR7, HFL, HFR, HBL, HBR, CC, LFE],
+                                         out_gain=[(L2, 0.9)], demix=(2, 4), first_layer_layout=LY_STEREO, selected_layer=1,
+                                         recon_flags=0x780)], TGT_A, peak_db=(-6.0, 3.0)),
+        Scenario("714_to_binaural_as_built", [El("channel", LY_714, [L7, R7, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, CC, LFE])],
+                 TGT_BIN, peak_db=(-9.0, 0.0)),
+        Scenario("510_from_stereo_to_B", [El("channel", LY_510, [L2, R2, L5, R5, CC, LFE], out_gain=[(L2, 1.2), (R2, 1.2)],
+                                            demix=(1, 0), first_layer_layout=LY_STEREO, selected_layer=1, recon_flags=0x18)],
+                 TGT_B, peak_db=(-6.0, 3.0)),
+        Scenario("510_from_stereo_to_A", [El("channel", LY_510, [L2, R2, L5, R5, CC, LFE], demix=(5, 7),
+                                            first_layer_layout=LY_STEREO, selected_layer=1, recon_flags=0x18)], TGT_A),
+        Scenario("514_from_312_to_B", [El("channel", LY_514, [L3, R3, CC, LFE, TL, TR, L5, R5, HFL, HFR], demix=(2, 2),
+                                         first_layer_layout=LY_312, selected_layer=1, recon_flags=0x618)], TGT_B,
+                 peak_db=(-4.0, 4.0)),
+        Scenario("710_to_B", [El("channel", LY_710, [L7, R7, CC, LFE, SL7, SR7, BL7, BR7])], TGT_B, peak_db=(-3.0, 3.0)),
+        Scenario("stereo_to_B_and_binaural", [El("channel", LY_STEREO, [L2, R2])], TGT_BIN, peak_db=(-3.0, 3.0)),
+    ]

@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 ALL = [S.c1_stereo(), S.c2_714_to_B(), S.c3_toa_to_H(), S.c4_714_foa_binaural(), S.c5_resample()] + S.edge_cases()
 
 
-def compare(sc, n_streams, F, splits, seed=0, s16=False):
+def compare(sc, n_streams, F, splits, seed=0, s16=False, expect_path=None):
     from gpu_harness import run_product
     inputs = S.synth_inputs(sc, n_streams, F, seed=0x1A3F + seed)
     P, ramps, oramp = S.synth_params(sc, n_streams, F, seed=0x77 + seed)
-    got, launches = run_product(sc, inputs, P, ramps, oramp, splits=splits, s16=s16)
+    got, launches = run_product(sc, inputs, P, ramps, oramp, splits=splits, s16=s16, expect_path=expect_path)
     ref = S.run_oracle(sc, inputs, P, ramps, oramp)
     assert launches > 0
     for s in range(n_streams):
@@ -67,19 +67,28 @@ def test_sequential_fused_kernel_still_bit_exact(monkeypatch):
     # k_stream (register-resident, pipelined) is the default for the signatures it is instantiated for; k_fused must
     # stay correct for them behind IAMFB_STREAM=0 (it also renders their trimmed / flushed streams)
     monkeypatch.setenv("IAMFB_STREAM", "0")
-    compare(S.c2_714_to_B(), 9, 6, [4, 2], seed=3)
-    compare(S.c1_stereo(peak_db=(-3.0, 3.0)), 5, 6, [6], seed=4)
+    compare(S.c2_714_to_B(), 9, 6, [4, 2], seed=3, expect_path=1)   # IAMFB_PATH_FUSED
+    compare(S.c1_stereo(peak_db=(-3.0, 3.0)), 5, 6, [6], seed=4, expect_path=1)
 
 
 def test_stream_kernel_mixed_with_trimmed_submits():
     # first submit untrimmed (k_stream), later submits carry trimmed frames (k_fused takes those streams): the limiter
     # history and state must hand over between the two kernels
-    compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31)
-    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32)
+    compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31, expect_path=2)
+    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32, expect_path=2)
 
 
 def test_stream_kernel_clipping_quantiser():
     # limiter threshold above full scale: samples beyond +-1.0 reach the quantiser and must saturate like
     # FLOAT2INT16 (IAMF_decoder.c:100-103) does
-    compare(S.c1_stereo(threshold_db=6.0, peak_db=(0.0, 8.0)), 9, 6, [6], seed=41)
-    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42)
+    compare(S.c1_stereo(threshold_db=6.0, peak_db=(0.0, 8.0)), 9, 6, [6], seed=41, expect_path=2)
+    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42, expect_path=2)
+
+
+STREAM_CASES = S.stream_kernel_cases()
+
+
+@pytest.mark.parametrize("sc", STREAM_CASES, ids=[s.name for s in STREAM_CASES])
+def test_stream_kernel_signatures(sc):
+    # the other (layout, target) pairs k_stream is instantiated for, layered (de-mixing + recon gain) where the layout allows
+    compare(sc, 11, 9, [4, 5], seed=51, expect_path=2)   # IAMFB_PATH_STREAM
