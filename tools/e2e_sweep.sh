@@ -1,6 +1,6 @@
 #!/bin/bash
 # sweep of the host-resident (e2e) path: stream groups per submit x frames per submit (run under gpurun)
-for ch in 4 8; do for fr in 8 16; do
+for ch in ${CHUNKS:-4 8}; do for fr in ${FRAMES:-8 16}; do
   IAMFB_HOST_CHUNKS=$ch timeout 200 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-frames $fr 2>/dev/null | CH=$ch FR=$fr python -c '
 import json,sys,os
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
