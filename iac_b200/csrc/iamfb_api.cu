@@ -1,5 +1,6 @@
 // iamfb_api.cu - host side of the C ABI declared in include/iamf_b200.h: plans, batches, kernel sequencing.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -766,16 +767,51 @@ static bool stream_sig_exists(int layout, int target) {
 #undef X
   return false;
 }
+// Tensor map of one submit's decoded input [S*F*n_in rows][N] (f32): k_stream stages the n_in rows x 240 instants of a
+// tile with ONE cp.async.bulk.tensor instruction (a box of {240, n_in}) instead of one bulk copy per row - the per-row
+// copies took a per-lane issue loop on the worker warp that was a third of the tile's critical path (profiles/).
+// The encoder comes from the driver through the runtime (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+static int make_input_tmap(CUtensorMap *tm, const float *base, size_t rows, int N, int n_in) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return fail(IAMFB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  if ((((size_t)base) & 15) != 0) return fail(IAMFB_ERR_BAD_ARG, "decoded input must be 16-byte aligned");
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kStreamTile, (cuuint32_t)n_in};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IAMFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return IAMFB_OK;
+}
+
 static int launch_stream(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa, int S) {
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
   const size_t smem = p->stream_smem;
   bool done = false;
+  CUtensorMap tm;
+  {
+    int r = make_input_tmap(&tm, fa.in[0], (size_t)S * fa.n_frames * kp.el[0].n_in, kp.frame_size, kp.el[0].n_in);
+    if (r) return r;
+  }
 #define X(L, T)                                                                                                       \
   if (!done && p->stream_sig == L * 16 + T) {                                                                         \
     CU(cudaFuncSetAttribute(k_stream<L, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
     ScopedKernelTimer tm_(ctx, "k_stream");                                                                           \
-    k_stream<L, T><<<S, kStreamThreads, smem, st>>>(kp, fa);                                                          \
+    k_stream<L, T><<<S, kStreamThreads, smem, st>>>(kp, fa, tm);                                                          \
     done = true;                                                                                                      \
   }
   IAMFB_STREAM_SIGS(X)
