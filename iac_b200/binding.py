@@ -93,6 +93,7 @@ def lib():
     L.iamfb_plan_destroy.argtypes = [vp]
     L.iamfb_plan_destroy.restype = None
     L.iamfb_plan_out_channels.argtypes = [vp]
+    L.iamfb_selftest_quotient.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
     L.iamfb_plan_kernel_path.argtypes = [vp]
     L.iamfb_plan_kernel_path.restype = C.c_int
     L.iamfb_plan_max_out_samples.argtypes = [vp, C.c_int]

@@ -994,6 +994,37 @@ extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
   delete p;
 }
 
+// every float of [2^-60, 2^60]: bit patterns 0x21800000 .. 0x5d800000
+__global__ void __launch_bounds__(256) k_selftest_quotient(float thr, unsigned long long *mismatches) {
+  const uint32_t lo = 0x21800000u, hi = 0x5d800000u;
+  unsigned long long bad = 0;
+  for (uint64_t b = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= hi; b += (uint64_t)gridDim.x * blockDim.x) {
+    const float w = __uint_as_float((uint32_t)b);
+    bool ok;
+    const float q = stream_quot(thr, w, ok);
+    const float r = thr / w;
+    if (!ok || __float_as_uint(q) != __float_as_uint(r)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+extern "C" int iamfb_selftest_quotient(iamfb_ctx *ctx, float thr, uint64_t *mismatches) {
+  if (!ctx || !mismatches) return fail(IAMFB_ERR_BAD_ARG, "selftest_quotient: null argument");
+  if (!(thr >= kQuotThrLo && thr <= kQuotThrHi)) return fail(IAMFB_ERR_BAD_ARG, "selftest_quotient: thr %g outside the served range", thr);
+  CU(cudaSetDevice(ctx->device));
+  unsigned long long *d = nullptr;
+  CU(cudaMalloc(&d, sizeof(*d)));
+  CU(cudaMemsetAsync(d, 0, sizeof(*d), ctx->stream));
+  k_selftest_quotient<<<148 * 8, 256, 0, ctx->stream>>>(thr, d);
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(IAMFB_ERR_CUDA, "selftest_quotient: %s", cudaGetErrorString(e));
+  ++ctx->launches;
+  *mismatches = h;
+  return IAMFB_OK;
+}
+
 extern "C" int iamfb_plan_out_channels(const iamfb_plan *p) { return p ? p->kp.out_channels : 0; }
 
 extern "C" int iamfb_plan_kernel_path(const iamfb_plan *p) {

@@ -217,6 +217,11 @@ uint64_t iamfb_ctx_launch_count(const iamfb_ctx *ctx);
 int iamfb_ctx_set_timing(iamfb_ctx *ctx, int enable);
 int iamfb_ctx_get_timing(iamfb_ctx *ctx, int index, const char **name, double *total_ms, uint64_t *launches);
 
+/* self-test (used by tests/): compares the branch-free division of k_stream's limiter scan with the IEEE division
+ * `thr / w` for EVERY float w of the range the kernel uses it in (2^-60 .. 2^60); *mismatches receives the count of
+ * differing bit patterns (0 expected).  thr must lie in 2^-20 .. 2^20 (outside it the kernel uses the plain division). */
+int iamfb_selftest_quotient(iamfb_ctx *ctx, float thr, uint64_t *mismatches);
+
 /* ---- table accessors (host side, no device needed) ---- */
 int iamfb_target_channels(int target);                      /* IAMF_layout_sound_system_channels_count */
 int iamfb_layout_channels(int layout, int32_t *chs);        /* rendering order, IAMF_utils.c:117-133 */

@@ -92,3 +92,21 @@ STREAM_CASES = S.stream_kernel_cases()
 def test_stream_kernel_signatures(sc):
     # the other (layout, target) pairs k_stream is instantiated for, layered (de-mixing + recon gain) where the layout allows
     compare(sc, 11, 9, [4, 5], seed=51, expect_path=2)   # IAMFB_PATH_STREAM
+
+
+@pytest.mark.parametrize("thr_db", [-1.0, 0.0, -6.0, -0.1, -20.0, 3.0])
+def test_scan_quotient_exhaustive(thr_db):
+    """k_stream's limiter scan divides thr by the look-ahead peak with a branch-free sequence (so that the division is
+    scheduled into the gain chain); it must equal the IEEE division for every float of the range it serves."""
+    import ctypes as C
+    from iac_b200 import binding
+    L = binding.lib()
+    ctx = C.c_void_p()
+    assert L.iamfb_ctx_create(0, C.byref(ctx)) == 0
+    try:
+        thr = np.float32(10.0 ** (thr_db / 20.0))       # audio_effect_peak_limiter.c:73-92 (double pow, then float)
+        bad = C.c_uint64(12345)
+        assert L.iamfb_selftest_quotient(ctx, C.c_float(float(thr)), C.byref(bad)) == 0
+        assert bad.value == 0, f"{bad.value} quotients differ from thr / w at thr = {thr}"
+    finally:
+        L.iamfb_ctx_destroy(ctx)
