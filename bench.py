@@ -172,9 +172,16 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
-def make_inputs_torch(sc, S, F, seed, device):
+def make_inputs_torch(sc, S, F, seed, device, render_peak=None):
     """device-resident decoded PCM: 3 sines + noise per channel, per-stream peak uniformly in sc.peak_db dBFS,
-    quantised to int16 and scaled by 1/32768 (the codec glue's contract).  [S][F][C][N] float32 per element."""
+    quantised to int16 and scaled by 1/32768 (the codec glue's contract).  [S][F][C][N] float32 per element.
+
+    The level is the peak the LIMITER sees ("threshold is -1 dBFS, so ~20 % of streams exercise the limiter's
+    active path"): render_peak(inputs) -> [S] returns the pre-limiter peak of every stream's rendered mix for a trial
+    input, and - everything before the limiter being linear - the channels are rescaled so that this peak lands on the
+    stream's target.  render_peak=None scales the decoded channels themselves to the target instead (--peak-ref input:
+    after a 12 -> 6 channel down-mix that puts ~80 % of the tiles above the threshold).
+    Returns (inputs, per-stream target peak)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -183,6 +190,7 @@ def make_inputs_torch(sc, S, F, seed, device):
     t = torch.arange(T, device=device, dtype=torch.float32) / sc.in_rate
     outs = []
     peak = 10.0 ** ((sc.peak_db[0] + (sc.peak_db[1] - sc.peak_db[0]) * torch.rand(S, generator=g, device=device)) / 20.0)
+    trial = 0.125 if render_peak is not None else None      # trial level of the calibration pass (no clipping anywhere)
     for el in sc.elements:
         C = el.n_in
         x = torch.empty((S, C, T), device=device, dtype=torch.float32)
@@ -194,10 +202,45 @@ def make_inputs_torch(sc, S, F, seed, device):
             ph = 6.2831853 * torch.rand((n, C, 3, 1), generator=g, device=device)
             y = torch.sin(6.2831853 * fr * t.view(1, 1, 1, T) + ph).sum(dim=2)
             y += 0.6 * torch.rand((n, C, T), generator=g, device=device) - 0.3
-            y *= (peak[s0:s1] / y.abs().amax(dim=(1, 2))).view(n, 1, 1)
-            x[s0:s1] = torch.clamp(torch.round(y * 32768.0), -32768, 32767) / 32768.0
+            if trial is None:
+                y *= (peak[s0:s1] / y.abs().amax(dim=(1, 2))).view(n, 1, 1)
+                x[s0:s1] = torch.clamp(torch.round(y * 32768.0), -32768, 32767) / 32768.0
+            else:
+                x[s0:s1] = y * (trial / y.abs().amax(dim=(1, 2))).view(n, 1, 1)
         outs.append(x.view(S, C, F, N).permute(0, 2, 1, 3).contiguous())
-    return outs
+    if trial is not None:
+        rendered = render_peak(outs).clamp_min(1e-9)        # [S] pre-limiter peak of the mix at the trial level
+        for x in outs:
+            x *= (peak / rendered).view(S, 1, 1, 1)
+            torch.clamp(torch.round(x * 32768.0), -32768, 32767, out=x)
+            x /= 32768.0
+    return outs, peak
+
+
+def rendered_peak_fn(sc, S_, F, P, local, stream, dev):
+    """pre-limiter peak of every stream's rendered mix: the same plan with the limiter off and the float debug output
+    (bit_depth 0), run once through the engine (untimed, before the benchmark's own engine exists)"""
+    import dataclasses
+    import torch
+    import scenarios as S
+    from iac_b200 import Engine
+
+    def fn(inputs):
+        cal = dataclasses.replace(sc, limiter=False, bit_depth=0)
+        eng = Engine(S.plan_desc(cal), S_, F, device=local, cuda_stream=stream.cuda_stream)
+        d_params = torch.from_numpy(P.view(np.uint8).reshape(S_, F * 48).copy()).to(dev)
+        stride = eng.out_stride_bytes(F)
+        d_pcm = torch.zeros((S_, stride), dtype=torch.uint8, device=dev)
+        d_counts = torch.zeros((S_, F), dtype=torch.int32, device=dev)
+        eng.submit_device([x.data_ptr() for x in inputs], d_params.data_ptr(), d_pcm.data_ptr(), d_counts.data_ptr(), F)
+        torch.cuda.synchronize()
+        n = d_counts.sum(dim=1).to(torch.int64) * cal.out_channels          # floats written per stream
+        pcm = d_pcm.view(torch.float32).view(S_, -1)
+        mask = torch.arange(pcm.shape[1], device=dev).view(1, -1) < n.view(-1, 1)
+        pk = torch.where(mask, pcm.abs(), torch.zeros_like(pcm)).amax(dim=1)
+        eng.close()
+        return pk
+    return fn
 
 
 def run_gpu(args):
@@ -227,10 +270,13 @@ def run_gpu(args):
         cpu.pop("per_rep", None)
 
     stream = torch.cuda.current_stream()
-    eng = Engine(S.plan_desc(sc), S_, F, device=local, cuda_stream=stream.cuda_stream)
-    inputs = make_inputs_torch(sc, S_, F, seed=0x1A3F + 7919 * rank, device=dev)
     P, _, _ = S.synth_params(sc, S_, F, seed=0x77 + rank)
     refstreams.no_param_gaps(sc, P)
+    cal = rendered_peak_fn(sc, S_, F, P, local, stream, dev) if (args.peak_ref == "rendered" and sc.limiter) else None
+    inputs, target_peak = make_inputs_torch(sc, S_, F, seed=0x1A3F + 7919 * rank, device=dev, render_peak=cal)
+    thr_lin = 10.0 ** (sc.threshold_db / 20.0)
+    active_frac = float((target_peak > thr_lin).float().mean().item()) if cal is not None else None
+    eng = Engine(S.plan_desc(sc), S_, F, device=local, cuda_stream=stream.cuda_stream)
     d_params = torch.from_numpy(P.view(np.uint8).reshape(S_, F * 48).copy()).to(dev)
     stride = eng.out_stride_bytes(F)
     d_pcm = torch.zeros((S_, stride), dtype=torch.uint8, device=dev)
@@ -270,7 +316,8 @@ def run_gpu(args):
         sampler.stop_flag = True
         if rank == 0:
             print(json.dumps({"metric": "rendered audio-sec/sec", "value": value, "ms_per_step": ms_max / args.steps,
-                              "gpu_launches": int(launches), "quick": True}))
+                              "gpu_launches": int(launches), "quick": True, "peak_ref": args.peak_ref,
+                              "streams_above_limiter_threshold": active_frac}))
         eng.close()
         return
 
@@ -361,7 +408,9 @@ def run_gpu(args):
             "config": {"workload": f"{cfg}: {CONFIGS[cfg]['desc']}", "streams_per_gpu": S_, "frames_per_step": F,
                        "frame_size": sc.frame_size, "input_bytes_per_step_per_gpu": int(sum(x.numel() * 4 for x in inputs)),
                        "l2_policy": "inputs larger than L2 (126 MB); nothing re-read across steps",
-                       "limiter_active_peak_range_db": list(sc.peak_db)},
+                       "limiter_active_peak_range_db": list(sc.peak_db),
+                       "peak_reference": ("pre-limiter peak of the rendered mix" if cal is not None else "decoded input channels"),
+                       "streams_above_limiter_threshold": active_frac},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "frames_per_step": Fe, "steps": ke, "ms_per_step": te_max_ms / ke, "input": "int16 PCM as decoded (IAMFB_IN_S16)",
                     "gpu_launches": int(e2e_launches)},
@@ -414,6 +463,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (used under ncu)")
     ap.add_argument("--peak-db", default="", help="experiment: override the per-stream peak range, e.g. -40,-30")
+    ap.add_argument("--peak-ref", default="rendered", choices=["rendered", "input"],
+                    help="what the per-stream peak level refers to: the pre-limiter rendered mix (SURVEY 8d: ~20 %% of "
+                         "streams above the limiter threshold) or the decoded input channels")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
