@@ -811,7 +811,13 @@ static int launch_stream(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &f
   if (!done && p->stream_sig == L * 16 + T) {                                                                         \
     CU(cudaFuncSetAttribute(k_stream<L, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
     ScopedKernelTimer tm_(ctx, "k_stream");                                                                           \
-    k_stream<L, T><<<S, kStreamThreads, smem, st>>>(kp, fa, tm);                                                          \
+    cudaLaunchConfig_t lc_ = {};                                                                                      \
+    lc_.gridDim = dim3(S); lc_.blockDim = dim3(kStreamThreads); lc_.dynamicSmemBytes = smem; lc_.stream = st;         \
+    cudaLaunchAttribute at_[1];                                                                                       \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                   \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;   /* may start under k_resolve (see the kernels) */        \
+    lc_.attrs = at_; lc_.numAttrs = 1;                                                                                \
+    CU(cudaLaunchKernelEx(&lc_, k_stream<L, T>, kp, fa, tm));                                                         \
     done = true;                                                                                                      \
   }
   IAMFB_STREAM_SIGS(X)

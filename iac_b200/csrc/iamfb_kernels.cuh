@@ -95,6 +95,10 @@ __device__ __forceinline__ long long rs_outputs_until(const KernelPlan &p, long 
 // computing the same scalars and lane 0 storing them.
 constexpr int kResolveThreads = 128;   // 4 streams per block
 __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
+  // programmatic dependent launch: the kernel launched after this one (k_stream) may start its blocks right away - they
+  // load their limiter history and curve, which this kernel does not touch, and wait (griddepcontrol.wait) before they
+  // read anything written here
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ float s_qf[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_qf[i] = a.qf_table[i];
   __syncthreads();
