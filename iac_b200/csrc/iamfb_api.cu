@@ -691,7 +691,14 @@ static int launch_fused(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa
   {                                                                                                                   \
     CU(cudaFuncSetAttribute(k_fused<L0, N0, L1, N1, VEC, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     ScopedKernelTimer tm_(ctx, "k_fused");                                                                            \
-    k_fused<L0, N0, L1, N1, VEC, THREADS><<<S, THREADS, smem, st>>>(kp, fa);                                         \
+    cudaLaunchConfig_t lc_ = {};                                                                                      \
+    lc_.gridDim = dim3(S); lc_.blockDim = dim3(THREADS); lc_.dynamicSmemBytes = smem; lc_.stream = st;                \
+    cudaLaunchAttribute at_[1];                                                                                       \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                   \
+    /* the launch for the streams k_stream left alone touches none of k_stream's streams: it may run beside it */    \
+    at_[0].val.programmaticStreamSerializationAllowed = fa.only_irregular ? 1 : 0;                                    \
+    lc_.attrs = at_; lc_.numAttrs = 1;                                                                                \
+    CU(cudaLaunchKernelEx(&lc_, k_fused<L0, N0, L1, N1, VEC, THREADS>, kp, fa));                                      \
   }
 #define FCASE(ID, L0, N0, L1, N1) \
   case ID: FLAUNCH(L0, N0, L1, N1, 4, 64) break;
