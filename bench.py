@@ -450,6 +450,9 @@ def run_reference(args):
 
 
 def main():
+    # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
