@@ -11,10 +11,12 @@ pytestmark = pytest.mark.gpu
 ALL = [S.c1_stereo(), S.c2_714_to_B(), S.c3_toa_to_H(), S.c4_714_foa_binaural(), S.c5_resample()] + S.edge_cases()
 
 
-def compare(sc, n_streams, F, splits, seed=0, s16=False, expect_path=None):
+def compare(sc, n_streams, F, splits, seed=0, s16=False, expect_path=None, edit_params=None):
     from gpu_harness import run_product
     inputs = S.synth_inputs(sc, n_streams, F, seed=0x1A3F + seed)
     P, ramps, oramp = S.synth_params(sc, n_streams, F, seed=0x77 + seed)
+    if edit_params:
+        edit_params(P)
     got, launches = run_product(sc, inputs, P, ramps, oramp, splits=splits, s16=s16, expect_path=expect_path)
     ref = S.run_oracle(sc, inputs, P, ramps, oramp)
     assert launches > 0
@@ -76,6 +78,17 @@ def test_stream_kernel_mixed_with_trimmed_submits():
     # history and state must hand over between the two kernels
     compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31, expect_path=2)
     compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32, expect_path=2)
+
+
+def test_stream_and_fused_kernels_side_by_side_in_one_submit():
+    # trims on SOME streams only: within one submit those go to k_fused while the others stay on k_stream, and the two
+    # launches run beside each other (programmatic dependent launch) - disjoint streams, shared buffers
+    def trims_on_every_third_stream(P):
+        P["trim_start"][1::3, 2] = 96
+        P["trim_end"][2::3, 5] = 300
+        P["trim_start"][2::3, 7] = 959
+    compare(S.c2_714_to_B(peak_db=(-3.0, 3.0)), 23, 9, [3, 3, 3], seed=51, expect_path=2, edit_params=trims_on_every_third_stream)
+    compare(S.c1_stereo(peak_db=(-2.0, 3.0)), 40, 8, [4, 4], seed=52, expect_path=2, edit_params=trims_on_every_third_stream)
 
 
 def test_stream_kernel_clipping_quantiser():
