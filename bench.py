@@ -144,6 +144,11 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.marks = []
+
+    def mark(self):
+        """brackets the timed region: samples taken between the first two marks are reported apart"""
+        self.marks.append(len(self.samples))
 
     def run(self):
         while not self.stop_flag:
@@ -165,8 +170,13 @@ class ClockSampler(threading.Thread):
                 for n, v in zip(names, s[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        timed = None
+        if len(self.marks) >= 2:
+            tm = [float(x[0]) for x in self.samples[self.marks[0]:self.marks[1]] if len(x) >= 8 and x[0].replace(".", "").isdigit()]
+            timed = dict(sm_mhz=float(np.median(tm)) if tm else None, samples=len(tm))
+        return dict(sm_mhz=(timed["sm_mhz"] if timed and timed["sm_mhz"] else (float(np.median(sm)) if sm else None)),
+                    sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm),
+                    timed_region=timed, whole_run_sm_mhz=float(np.median(sm)) if sm else None)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -243,24 +253,136 @@ def rendered_peak_fn(sc, S_, F, P, local, stream, dev):
     return fn
 
 
+class DeviceWorkload:
+    """one configuration resident in HBM: synthetic decoded PCM, per-frame parameters, an engine and its output buffers"""
+
+    def __init__(self, cfg, S_, F, rank, local, dev, stream, peak_ref="rendered", peak_db="", in_format="f32"):
+        import torch
+        import scenarios as S
+        import refstreams
+        from iac_b200 import Engine
+        self.cfg, self.S, self.F, self.dev, self.stream = cfg, S_, F, dev, stream
+        sc, _, _, _ = refstreams.case(cfg)
+        if peak_db:   # experiment knob (not the benchmark workload): per-stream peak range in dBFS
+            sc.peak_db = tuple(float(v) for v in peak_db.split(","))
+        self.sc = sc
+        P, _, _ = S.synth_params(sc, S_, F, seed=0x77 + rank)
+        refstreams.no_param_gaps(sc, P)
+        self.P = P
+        cal = rendered_peak_fn(sc, S_, F, P, local, stream, dev) if (peak_ref == "rendered" and sc.limiter) else None
+        self.calibrated = cal is not None
+        inputs, target_peak = make_inputs_torch(sc, S_, F, seed=0x1A3F + 7919 * rank, device=dev, render_peak=cal)
+        thr_lin = 10.0 ** (sc.threshold_db / 20.0)
+        self.active_frac = float((target_peak > thr_lin).float().mean().item()) if cal is not None else None
+        self.inputs_f32 = inputs
+        self.in_format = in_format
+        if in_format == "s16":
+            # what core decode hands over BEFORE the codec glue's 1/32768 (opus/IAMF_opus_decoder.c:133-135): int16
+            inputs = [torch.round(x * 32768.0).to(torch.int16).contiguous() for x in inputs]
+        self.inputs = inputs
+        self.eng = Engine(S.plan_desc(sc), S_, F, device=local, cuda_stream=stream.cuda_stream)
+        self.d_params = torch.from_numpy(P.view(np.uint8).reshape(S_, F * 48).copy()).to(dev)
+        self.stride = self.eng.out_stride_bytes(F)
+        self.d_pcm = torch.zeros((S_, self.stride), dtype=torch.uint8, device=dev)
+        self.d_counts = torch.zeros((S_, F), dtype=torch.int32, device=dev)
+        self.in_ptrs = [x.data_ptr() for x in self.inputs]
+        self.input_bytes = int(sum(x.numel() * x.element_size() for x in self.inputs))
+
+    def submit(self):
+        self.eng.submit_device(self.in_ptrs, self.d_params.data_ptr(), self.d_pcm.data_ptr(), self.d_counts.data_ptr(), self.F,
+                               in_format=1 if self.in_format == "s16" else 0)
+
+    def out_per_submit(self):
+        return int(self.d_counts.sum().item())
+
+    def kernel_timing(self, submits):
+        """per-kernel CUDA-event timing (a separate pass, so that the events do not perturb the throughput number)"""
+        import torch
+        self.eng.set_timing(True)
+        for _ in range(submits):
+            self.submit()
+        torch.cuda.synchronize()
+        timing = self.eng.get_timing()
+        self.eng.set_timing(False)
+        return {k: dict(ms_per_launch=v[0] / max(v[1], 1), launches_per_submit=v[1] / submits, ms_per_submit=v[0] / submits)
+                for k, v in timing.items()}
+
+    def roofline(self, kernels, ms_per_submit, out_per_submit):
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_submit"])
+        alg = alg_bytes_per_audio_second(self.sc) * (out_per_submit / self.sc.out_rate)
+        dom_launches = max(kernels[dom]["launches_per_submit"], 1e-9)
+        achieved = alg / dom_launches / (kernels[dom]["ms_per_launch"] / 1e3) / 1e9
+        traffic = None   # DRAM traffic of the dominant kernel from the committed ncu capture (same workload shape), else null
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(self.cfg, {}).get(dom)
+            if t and t["streams"] == self.S and t["frames"] == self.F:
+                traffic = t["bytes_per_launch"]
+        except Exception:
+            pass
+        pipe = alg / (ms_per_submit / 1e3) / 1e9
+        return dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
+                    traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=alg / dom_launches,
+                    pipeline=dict(achieved=pipe, frac=pipe / peak_gbs, note="all kernels of a submit, algorithmic bytes / submit time"),
+                    kernels=kernels)
+
+    def close(self):
+        self.eng.close()
+
+
+def timed_submits(w, n_submits, barrier):
+    """device time of n_submits back-to-back submits (CUDA events on the launching stream)"""
+    import torch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(w.stream)
+    for _ in range(n_submits):
+        w.submit()
+    e1.record(w.stream)
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def copy_ceiling(h2d_bytes, d2h_bytes, dev, reps=5):
+    """the same bytes as plain pinned copies, both directions at once on two streams (what the box's host path can move)"""
+    import torch
+    up_h = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    dn_h = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    up_d = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    dn_d = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_up):
+            up_d.copy_(up_h, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            dn_h.copy_(dn_d, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     import scenarios as S
-    import refstreams
-    from iac_b200 import Engine
 
-    from iac_b200 import shard
+    from iac_b200 import Engine, shard
     rank, world, local = shard.rank_world()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-
     cfg = args.config
-    sc, _, _, _ = refstreams.case(cfg)
-    if args.peak_db:   # experiment knob (not the benchmark workload): per-stream peak range in dBFS
-        sc.peak_db = tuple(float(v) for v in args.peak_db.split(","))
     S_, F = args.streams or CONFIGS[cfg]["streams"], args.frames or CONFIGS[cfg]["frames"]
 
     # CPU baseline first (rank 0, N=1 only), before the GPU is busy
@@ -270,92 +392,50 @@ def run_gpu(args):
         cpu.pop("per_rep", None)
 
     stream = torch.cuda.current_stream()
-    P, _, _ = S.synth_params(sc, S_, F, seed=0x77 + rank)
-    refstreams.no_param_gaps(sc, P)
-    cal = rendered_peak_fn(sc, S_, F, P, local, stream, dev) if (args.peak_ref == "rendered" and sc.limiter) else None
-    inputs, target_peak = make_inputs_torch(sc, S_, F, seed=0x1A3F + 7919 * rank, device=dev, render_peak=cal)
-    thr_lin = 10.0 ** (sc.threshold_db / 20.0)
-    active_frac = float((target_peak > thr_lin).float().mean().item()) if cal is not None else None
-    eng = Engine(S.plan_desc(sc), S_, F, device=local, cuda_stream=stream.cuda_stream)
-    d_params = torch.from_numpy(P.view(np.uint8).reshape(S_, F * 48).copy()).to(dev)
-    stride = eng.out_stride_bytes(F)
-    d_pcm = torch.zeros((S_, stride), dtype=torch.uint8, device=dev)
-    d_counts = torch.zeros((S_, F), dtype=torch.int32, device=dev)
-    in_ptrs = [x.data_ptr() for x in inputs]
-
-    def step():
-        eng.submit_device(in_ptrs, d_params.data_ptr(), d_pcm.data_ptr(), d_counts.data_ptr(), F)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end leg (the timed region of K
-    # sub-millisecond steps alone is shorter than one nvidia-smi query)
+    w = DeviceWorkload(cfg, S_, F, rank, local, dev, stream, args.peak_ref, args.peak_db, args.in_format)
+    sc = w.sc
+
+    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end leg
     sampler = ClockSampler(local)
     sampler.start()
+    # A step = R consecutive submits of the same S x F batch (the streams simply go on: limiter / de-mixer state carries
+    # over), R chosen so that one step lasts ~args.step_ms and the timed region of K steps is >= 1 s: the clocks the
+    # number was taken at are sustained ones, not a 5 ms burst
+    for _ in range(3):
+        w.submit()
+    probe = timed_submits(w, 8, barrier) / 8.0
+    R = args.submits_per_step or max(1, int(round(args.step_ms / max(probe, 1e-3))))
     for _ in range(args.warmup):
-        step()
-    barrier()
-    l0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = eng.launch_count() - l0
-    # samples produced in one steady-state step (all streams of this rank)
-    out_per_step = int(d_counts.sum().item())
-    ms_max, out_total = shard.aggregate(ms, out_per_step, device=dev)     # MAX of device time, SUM of samples
+        for _ in range(R):
+            w.submit()
+    l0 = w.eng.launch_count()
+    sampler.mark()
+    ms = timed_submits(w, args.steps * R, barrier)
+    sampler.mark()
+    launches = w.eng.launch_count() - l0
+    out_per_submit = w.out_per_submit()                 # samples produced by one steady-state submit (this rank)
+    ms_max, out_total = shard.aggregate(ms, out_per_submit * R, device=dev)     # MAX of device time, SUM of samples
     value = shard.job_throughput(ms_max, out_total, sc.out_rate, steps=args.steps)
+    ms_per_submit = ms_max / (args.steps * R)
 
     if args.quick:
         sampler.stop_flag = True
         if rank == 0:
             print(json.dumps({"metric": "rendered audio-sec/sec", "value": value, "ms_per_step": ms_max / args.steps,
+                              "ms_per_submit": ms_per_submit, "submits_per_step": R,
                               "gpu_launches": int(launches), "quick": True, "peak_ref": args.peak_ref,
-                              "streams_above_limiter_threshold": active_frac}))
-        eng.close()
+                              "streams_above_limiter_threshold": w.active_frac, "kernel_path": w.eng.kernel_path}))
+        w.close()
         return
 
-    # ---- per-kernel CUDA-event timing (separate pass so that the events do not perturb `value`)
-    eng.set_timing(True)
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    timing = eng.get_timing()
-    eng.set_timing(False)
-    kernels = {k: dict(ms_per_launch=v[0] / max(v[1], 1), launches_per_step=v[1] / args.steps,
-                       ms_per_step=v[0] / args.steps) for k, v in timing.items()}
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    alg_bytes_step = alg_bytes_per_audio_second(sc) * (out_per_step / sc.out_rate)
-    dom_launches = max(kernels[dom]["launches_per_step"], 1e-9)
-    achieved = alg_bytes_step / dom_launches / (kernels[dom]["ms_per_launch"] / 1e3) / 1e9
-    # DRAM traffic of the dominant kernel from the committed ncu capture (same workload shape), else null
-    traffic = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg, {}).get(dom)
-        if t and t["streams"] == S_ and t["frames"] == F:
-            traffic = t["bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
-                    traffic=traffic, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=alg_bytes_step / dom_launches,
-                    pipeline=dict(achieved=alg_bytes_step / (ms_max / args.steps / 1e3) / 1e9,
-                                  frac=alg_bytes_step / (ms_max / args.steps / 1e3) / 1e9 / peak_gbs,
-                                  note="all kernels of the step, algorithmic bytes / step time"),
-                    kernels=kernels)
+    kernels = w.kernel_timing(min(args.steps * R, 40))
+    roofline = w.roofline(kernels, ms_per_submit, out_per_submit)
 
     # ---- end to end through the host-buffer entry point of the C ABI: pinned host memory -> H2D -> kernels -> D2H every
     # step.  The host buffers hold what core decode produces for this workload - int16 PCM (Opus / AAC / 16-bit ipcm),
@@ -363,8 +443,8 @@ def run_gpu(args):
     # engines and the compute stream.
     Fe = min(F, args.e2e_frames)
     eng_e = Engine(S.plan_desc(sc), S_, Fe, device=local, cuda_stream=stream.cuda_stream)
-    h_in = [torch.round(x[:, :Fe] * 32768.0).to(torch.int16).contiguous().cpu().pin_memory() for x in inputs]
-    h_params = torch.from_numpy(np.ascontiguousarray(P[:, :Fe]).view(np.uint8).reshape(S_, Fe * 48).copy()).pin_memory()
+    h_in = [torch.round(x[:, :Fe] * 32768.0).to(torch.int16).contiguous().cpu().pin_memory() for x in w.inputs_f32]
+    h_params = torch.from_numpy(np.ascontiguousarray(w.P[:, :Fe]).view(np.uint8).reshape(S_, Fe * 48).copy()).pin_memory()
     stride_e = eng_e.out_stride_bytes(Fe)
     h_pcm = torch.zeros((S_, stride_e), dtype=torch.uint8).pin_memory()
     h_counts = torch.zeros((S_, Fe), dtype=torch.int32).pin_memory()
@@ -396,6 +476,56 @@ def run_gpu(args):
     e2e_value = shard.job_throughput(te_max_ms, oe_total, sc.out_rate, steps=ke)
     h2d = sum(x.numel() * 2 for x in h_in) + h_params.numel()
     d2h = S_ * stride_e + h_counts.numel() * 4
+    eng_e.close()
+    # the same bytes as two plain pinned copies running against each other on this rank (all ranks at once under
+    # torchrun): the ceiling the host path of this box sets for the end-to-end step
+    barrier()
+    ceil_s = copy_ceiling(int(h2d), int(d2h), dev)
+    ceil_ms_max, _ = shard.aggregate(ceil_s * 1e3, 0.0, device=dev)
+    del h_in, h_pcm
+
+    # ---- the other BASELINE configurations and the input-referred level of this one, device-resident, ~0.3 s each
+    others = {}
+    value_input_referred = None
+    if not args.no_other_configs:
+        w_keep = w
+        if sc.limiter and args.peak_ref == "rendered":
+            w2 = DeviceWorkload(cfg, S_, F, rank, local, dev, stream, "input", "", args.in_format)
+            for _ in range(3):
+                w2.submit()
+            n2 = max(4, int(300.0 / max(ms_per_submit, 1e-3)))
+            t2 = timed_submits(w2, n2, barrier)
+            t2_max, o2 = shard.aggregate(t2, w2.out_per_submit() * n2, device=dev)
+            value_input_referred = dict(value=shard.job_throughput(t2_max, o2, sc.out_rate, steps=1),
+                                        ms_per_submit=t2_max / n2,
+                                        note="per-stream peak applied to the decoded input channels instead of the rendered mix")
+            w2.close()
+            del w2
+        for oc in sorted(CONFIGS):
+            if oc == cfg:
+                continue
+            torch.cuda.empty_cache()
+            wo = DeviceWorkload(oc, CONFIGS[oc]["streams"], CONFIGS[oc]["frames"], rank, local, dev, stream, args.peak_ref, "",
+                                args.in_format)
+            for _ in range(3):
+                wo.submit()
+            pr = timed_submits(wo, 4, barrier) / 4.0
+            no = max(4, int(300.0 / max(pr, 1e-3)))
+            to = timed_submits(wo, no, barrier)
+            ops = wo.out_per_submit()
+            to_max, oo = shard.aggregate(to, ops * no, device=dev)
+            ko = wo.kernel_timing(min(no, 20))
+            ro = wo.roofline(ko, to_max / no, ops)
+            others[oc] = dict(value=shard.job_throughput(to_max, oo, wo.sc.out_rate, steps=1), unit="audio-s/s",
+                              ms_per_submit=to_max / no, submits_timed=no, streams_per_gpu=wo.S, frames_per_submit=wo.F,
+                              workload=CONFIGS[oc]["desc"], kernel_path=wo.eng.kernel_path,
+                              streams_above_limiter_threshold=wo.active_frac,
+                              roofline=dict(kernel=ro["kernel"], achieved=ro["achieved"], peak=ro["peak"], frac=ro["frac"],
+                                            traffic=ro["traffic"], pipeline_frac=ro["pipeline"]["frac"],
+                                            kernels={k: round(v["ms_per_submit"], 5) for k, v in ko.items()}))
+            wo.close()
+            del wo
+        w = w_keep
 
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -405,23 +535,29 @@ def run_gpu(args):
             "metric": "rendered audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg}: {CONFIGS[cfg]['desc']}", "streams_per_gpu": S_, "frames_per_step": F,
-                       "frame_size": sc.frame_size, "input_bytes_per_step_per_gpu": int(sum(x.numel() * 4 for x in inputs)),
-                       "l2_policy": "inputs larger than L2 (126 MB); nothing re-read across steps",
+            "config": {"workload": f"{cfg}: {CONFIGS[cfg]['desc']}", "streams_per_gpu": S_, "frames_per_submit": F,
+                       "submits_per_step": R, "ms_per_submit": ms_per_submit,
+                       "frame_size": sc.frame_size, "input_bytes_per_submit_per_gpu": w.input_bytes,
+                       "input_format": ("int16 PCM as core decode produces it, scaled by 1/32768 on the device (IAMFB_IN_S16)"
+                                        if args.in_format == "s16" else "float32 (after the codec glue's 1/32768)"),
+                       "l2_policy": "the inputs of one submit are larger than L2 (126 MB); nothing is re-read from cache across submits",
                        "limiter_active_peak_range_db": list(sc.peak_db),
-                       "peak_reference": ("pre-limiter peak of the rendered mix" if cal is not None else "decoded input channels"),
-                       "streams_above_limiter_threshold": active_frac},
+                       "peak_reference": ("pre-limiter peak of the rendered mix" if w.calibrated else "decoded input channels"),
+                       "streams_above_limiter_threshold": w.active_frac, "kernel_path": w.eng.kernel_path},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "frames_per_step": Fe, "steps": ke, "ms_per_step": te_max_ms / ke, "input": "int16 PCM as decoded (IAMFB_IN_S16)",
-                    "gpu_launches": int(e2e_launches)},
+                    "gpu_launches": int(e2e_launches),
+                    "copy_ceiling_ms": ceil_ms_max, "frac_of_copy_ceiling": ceil_ms_max / (te_max_ms / ke),
+                    "copy_ceiling_note": "the step's H2D and D2H bytes as two plain pinned copies running against each other, all ranks at once"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "value_input_referred": value_input_referred,
+            "configs": others,
         }
         print(json.dumps(line))
-    eng.close()
-    eng_e.close()
+    w.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -465,6 +601,10 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (used under ncu)")
+    ap.add_argument("--step-ms", type=float, default=60.0, help="target duration of one step (a step = R back-to-back submits)")
+    ap.add_argument("--submits-per-step", type=int, default=0, help="R; 0 = derive it from --step-ms")
+    ap.add_argument("--in-format", default="f32", choices=["f32", "s16"], help="device-resident decoded input format")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--peak-db", default="", help="experiment: override the per-stream peak range, e.g. -40,-30")
     ap.add_argument("--peak-ref", default="rendered", choices=["rendered", "input"],
                     help="what the per-stream peak level refers to: the pre-limiter rendered mix (SURVEY 8d: ~20 %% of "

@@ -307,8 +307,9 @@ class Engine:
 
     # ---- device-resident (raw pointers) ----
     def submit_device(self, in_ptrs, params_ptr, pcm_ptr, counts_ptr, n_frames, gain_ramp_ptrs=None,
-                      out_gain_ramp_ptr=None):
+                      out_gain_ramp_ptr=None, in_format=0):
         io = Io()
+        io.in_format = in_format
         for e, p in enumerate(in_ptrs):
             io.in_[e] = p
         if gain_ramp_ptrs:

@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "--fmad=false",          # the reference is built without FMA contraction (x86-64 baseline): keep mul and add apart
     "--expt-relaxed-constexpr",   # constexpr table look-ups (iamfb_stream.cuh) are evaluated at compile time on both sides
-    "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+    "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
 ]
 
 
@@ -27,14 +27,31 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "iamf_b200.h")]
-    if not force and not _stale(LIB, srcs):
-        return LIB
+    """every csrc/*.cu is one translation unit (kernels + their launchers), compiled in parallel into build/*.o and
+    linked into ONE shared library; headers (*.cuh, *.inc, include/*.h) are dependencies of every unit"""
+    files = sorted(os.listdir(CSRC))
+    units = [f for f in files if f.endswith(".cu")]
+    hdrs = [os.path.join(CSRC, f) for f in files if not f.endswith(".cu")] + [os.path.join(ROOT, "include", "iamf_b200.h")]
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", LIB, os.path.join(CSRC, "iamfb_api.cu")]
-    print("[iac_b200.build]", " ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    procs, objs = [], []
+    for u in units:
+        src, obj = os.path.join(CSRC, u), os.path.join(objdir, u[:-3] + ".o")
+        objs.append(obj)
+        if not force and not _stale(obj, [src] + hdrs):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+            "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-c", "-o", obj, src]
+        print("[iac_b200.build]", " ".join(cmd), file=sys.stderr)
+        procs.append((u, subprocess.Popen(cmd)))
+    failed = [u for u, p in procs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for " + ", ".join(failed))
+    if force or procs or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        print("[iac_b200.build]", " ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
     return LIB
 
 

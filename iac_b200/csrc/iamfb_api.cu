@@ -191,7 +191,8 @@ struct iamfb_batch {
   float *d_hist_y, *d_hist_pk;   // fused path: limiter delay line / peak ring carried between submits
   // staging for the host-resident path
   float *d_in[kMaxEl];
-  int16_t *d_in16[kMaxEl];   // int16 uploads (IAMFB_IN_S16), widened to d_in on the device
+  int16_t *d_in16[kMaxEl];   // int16 uploads (IAMFB_IN_S16)
+  float *d_wide[kMaxEl];     // float32 copy of an int16 submit for the kernels that stage float32
   float *d_ramp[kMaxEl];
   float *d_oramp;
   iamfb_frame_params *d_params;
@@ -527,6 +528,8 @@ static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &t
     const int lay = ed.layout == IAMFB_LAYOUT_BINAURAL ? IAMFB_LAYOUT_STEREO : ed.layout;
     ep.layout = lay;
     ep.n_rec = k_layout_count[lay];
+    if (ed.first_layer_layout < 0 || ed.first_layer_layout > 9) return fail(IAMFB_ERR_BAD_ARG, "element %d: bad first-layer layout %d", e, ed.first_layer_layout);
+    if (ed.use_dmr && (ed.dmr_out_layout < 0 || ed.dmr_out_layout > 9)) return fail(IAMFB_ERR_BAD_ARG, "element %d: bad down-mix layout %d", e, ed.dmr_out_layout);
     if (ed.n_in != ep.n_rec)   // demixer_demixing: chs_count must equal the layout's channel count (demixer.c:640-641)
       return fail(IAMFB_ERR_BAD_ARG, "element %d: %d decoded channels but layout %d has %d", e, ed.n_in, lay, ep.n_rec);
     Avail av;
@@ -625,6 +628,7 @@ static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &t
     }
   } else if (ed.kind == IAMFB_EL_SCENE) {
     int nch = ed.ambi_channels;
+    if (ed.n_in < 1 || ed.n_in > IAMFB_MAX_SCENE_CH) return fail(IAMFB_ERR_BAD_ARG, "element %d: %d decoded rows of a scene-based element", e, ed.n_in);
     int order = nch == 1 ? 0 : nch == 4 ? 1 : nch == 9 ? 2 : nch == 16 ? 3 : -1;   // iamf_stream_ambisionisc_order :2403-2413
     if (order < 0) return fail(IAMFB_ERR_BAD_ARG, "element %d: %d ambisonics channels", e, nch);
     ep.n_rec = nch;
@@ -705,8 +709,7 @@ static int launch_fused(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa
   // scene-based pipelines with many output channels fit few streams per SM: lighter threads, more of them
 #define FCASE3(ID, L0, N0, L1, N1)                                    \
   case ID:                                                            \
-    if (p->fused_variant == 2) FLAUNCH(L0, N0, L1, N1, 1, 256)        \
-    else if (p->fused_variant == 1) FLAUNCH(L0, N0, L1, N1, 2, 128)   \
+    if (p->fused_variant == 1) FLAUNCH(L0, N0, L1, N1, 2, 128)        \
     else FLAUNCH(L0, N0, L1, N1, 4, 64)                               \
     break;
   switch (fused_variant(p->tmpl, kp.n_elements)) {
@@ -836,6 +839,8 @@ static int launch_stream(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &f
   return IAMFB_OK;
 }
 
+extern "C" void iamfb_plan_destroy(iamfb_plan *p);
+
 extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb_plan **out) {
   if (!ctx || !d || !out) return fail(IAMFB_ERR_BAD_ARG, "plan_create: null argument");
   if (d->frame_size <= 0 || d->frame_size > 32768) return fail(IAMFB_ERR_BAD_ARG, "frame_size %d", d->frame_size);
@@ -863,7 +868,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
   memset(&p->init_state, 0, sizeof(p->init_state));
   for (int e = 0; e < d->n_elements; ++e) {
     int r = build_element(*d, e, kp, p->tmpl[e], p->init_state);
-    if (r != IAMFB_OK) { delete p; return r; }
+    if (r != IAMFB_OK) { iamfb_plan_destroy(p); return r; }
   }
   p->init_state.lim_j = -1;
   p->init_state.lim_start = -1.f;
@@ -878,23 +883,23 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
     for (int i = 0; i < wl; ++i) hann[i] = (0.5 * (1.0 - cos(2.0 * M_PI * (double)i / (double)(wl - 1))));
     for (int j = 0; j < ol; ++j) { sw[j] = hann[j]; ew[j] = hann[j + ol]; }
     int r;
-    if ((r = upload(&p->d_start_win, sw.data(), (size_t)ol)) || (r = upload(&p->d_stop_win, ew.data(), (size_t)ol))) { delete p; return r; }
+    if ((r = upload(&p->d_start_win, sw.data(), (size_t)ol)) || (r = upload(&p->d_stop_win, ew.data(), (size_t)ol))) { iamfb_plan_destroy(p); return r; }
   }
   {   // qf_to_float(q, 8), fixedp11_5.c:53-55
     float qf[256];
     for (int q = 0; q < 256; ++q) qf[q] = ((float)q / (pow(2.0f, (float)8) - 1.0));
     int r = upload(&p->d_qf, qf, 256);
-    if (r) { delete p; return r; }
+    if (r) { iamfb_plan_destroy(p); return r; }
   }
   if (kp.resample) {
     std::vector<float> table;
     build_resampler(kp, table, d->in_rate, d->out_rate);
     kp.rs_hist = (int)((kp.rs_filt_len - 1 + 3) & ~3u);
     if (kp.rs_hist < 64) kp.rs_hist = 64;
-    if (kp.rs_hist > kMaxRsHist) { delete p; return fail(IAMFB_ERR_UNIMPLEMENTED, "resampler filter length %u > %d (ratio %d:%d)", kp.rs_filt_len, kMaxRsHist, d->in_rate, d->out_rate); }
+    if (kp.rs_hist > kMaxRsHist) { iamfb_plan_destroy(p); return fail(IAMFB_ERR_UNIMPLEMENTED, "resampler filter length %u > %d (ratio %d:%d)", kp.rs_filt_len, kMaxRsHist, d->in_rate, d->out_rate); }
     p->sinc_len = (int)table.size();
     int r = upload(&p->d_sinc, table.data(), table.size());
-    if (r) { delete p; return r; }
+    if (r) { iamfb_plan_destroy(p); return r; }
     if (!kp.rs_direct) {
       const int Nf = (int)kp.rs_filt_len, os = (int)kp.rs_oversample, trow = Nf + 1;
       std::vector<float4> t4((size_t)os * trow);
@@ -908,7 +913,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
           t4[(size_t)o * trow + j] = v;
         }
       r = upload(&p->d_tab4, t4.data(), t4.size());
-      if (r) { delete p; return r; }
+      if (r) { iamfb_plan_destroy(p); return r; }
       // inputs spanned by 128 consecutive outputs: floor(127 * num / den) + 1, plus the filter length
       p->rs_span = (int)((127ull * kp.rs_num) / kp.rs_den + 2 + kp.rs_filt_len + 3) & ~3;
     }
@@ -917,7 +922,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
     std::vector<float> acc;
     build_limiter(kp, acc, d->limiter_threshold_db, d->out_rate);   // limiter runs at the requested rate (:3809-3815)
     int r = upload(&p->d_acc, acc.data(), acc.size());
-    if (r) { delete p; return r; }
+    if (r) { iamfb_plan_destroy(p); return r; }
   }
   p->fused = false;
   {
@@ -954,10 +959,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
         // few streams per SM (large rings): spread each tile over more, lighter threads (scene-based signatures only)
         p->fused_variant = 0;
         if (kp.n_elements == 1 && kp.el[0].kind == IAMFB_EL_SCENE) {
-          const char *env = getenv("IAMFB_FUSED_VARIANT");
-          if (env) p->fused_variant = atoi(env);
-          else p->fused_variant = blocks_per_sm <= 5 ? 1 : 0;   // measured on C3 (3 streams per SM): 2.93 ms vs 3.45 (variant 0) and 4.0 (variant 2)
-          if (p->fused_variant < 0 || p->fused_variant > 2) p->fused_variant = 0;
+          p->fused_variant = blocks_per_sm <= 5 ? 1 : 0;   // measured on C3 (3 streams per SM): 2.93 ms vs 3.45 with 4 samples x 64 threads
         }
         p->fused_smem = sizeof(float) * smem_floats(tl);
         // k_stream: one channel-based element through a channel->channel matrix that matches the compile-time table,
@@ -1148,6 +1150,7 @@ extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
   cudaFree(b->d_state); cudaFree(b->d_frames); cudaFree(b->d_submit);
   cudaFree(b->d_tl_a); cudaFree(b->d_tl_b); cudaFree(b->d_pk); cudaFree(b->d_wm); cudaFree(b->d_gn);
   cudaFree(b->d_hist_y); cudaFree(b->d_hist_pk);
+  for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_wide[e]);
   free_staging(b);
   delete b;
 }
@@ -1161,33 +1164,6 @@ extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
     if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
     ++ctx->launches;                                                                                            \
   } while (0)
-
-static int launch_render_bulk(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const RenderArgs &ra, int n_tiles) {
-  cudaStream_t st = ctx->stream;
-  const size_t smem = sizeof(float) * (size_t)kRenderStages * kp.el[ra.e].n_in * kRenderTile;
-  int dev_sms = 148;
-  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  int per_sm = (int)((200 * 1024) / (smem + 1024));
-  if (per_sm > 3) per_sm = 3;
-  if (per_sm < 1) per_sm = 1;
-  int grid = dev_sms * per_sm;
-  if (grid > n_tiles) grid = n_tiles;
-#define BCASE(ID, LAYOUT, NREC)                                                                                      \
-  case ID: {                                                                                                         \
-    CU(cudaFuncSetAttribute(k_render_bulk<LAYOUT, NREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    ScopedKernelTimer tm_(ctx, "k_render");                                                                          \
-    k_render_bulk<LAYOUT, NREC><<<grid, 128, smem, st>>>(kp, ra, n_tiles);                                          \
-  } break;
-  switch (tmpl) {
-    BCASE(0, 0, 1) BCASE(1, 1, 2) BCASE(2, 2, 6) BCASE(3, 3, 8) BCASE(4, 4, 10) BCASE(5, 5, 8) BCASE(6, 6, 10)
-    BCASE(7, 7, 12) BCASE(8, 8, 6)
-    BCASE(10, -1, 1) BCASE(11, -1, 4) BCASE(12, -1, 9) BCASE(13, -1, 16)
-    default: return fail(IAMFB_ERR_INTERNAL, "no render kernel variant %d", tmpl);
-  }
-#undef BCASE
-  LAUNCH_CHECK("k_render_bulk");
-  return IAMFB_OK;
-}
 
 template <int VEC>
 static int launch_render(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const RenderArgs &ra, int blocks) {
@@ -1207,12 +1183,64 @@ static int launch_render(iamfb_ctx *ctx, int tmpl, const KernelPlan &kp, const R
 
 static int n_subchunks(const KernelPlan &kp, int F, bool flush) {
   if (flush || !kp.limiter || kp.resample) return 1;
-  const char *env = getenv("IAMFB_SUBCHUNKS");
-  int n = env ? atoi(env) : (F >= 8 ? 4 : (F >= 4 ? 2 : 1));
-  if (n < 1) n = 1;
-  if (n > kMaxSub) n = kMaxSub;
+  int n = F >= 8 ? 4 : (F >= 4 ? 2 : 1);
   if (n > F) n = F;
   return n;
+}
+
+// int16 -> float32 * 2^-15 (the codec glue's scaling, opus/IAMF_opus_decoder.c:133-135); 8 samples per thread
+__global__ void __launch_bounds__(256) k_widen_s16(const int16_t *__restrict__ src, float *__restrict__ dst, size_t n8, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n8) {
+    const int4 v = reinterpret_cast<const int4 *>(src)[i];
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = (float)(short)(w[k] & 0xffff) / 32768.f;
+      o[2 * k + 1] = (float)(short)(w[k] >> 16) / 32768.f;
+    }
+    reinterpret_cast<float4 *>(dst)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4 *>(dst)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else if (i == n8) {
+    for (size_t k = n8 * 8; k < n; ++k) dst[k] = (float)src[k] / 32768.f;
+  }
+}
+
+
+// float32 copy of an int16 submit for the kernels that stage float32 (everything but k_pipe): per element
+// [S][F][n_in][N], allocated on first use for the batch's Fmax
+static int ensure_wide(iamfb_batch *b) {
+  const KernelPlan &kp = b->plan->kp;
+  for (int e = 0; e < kp.n_elements; ++e)
+    if (!b->d_wide[e]) {
+      cudaError_t er = cudaMalloc((void **)&b->d_wide[e], sizeof(float) * (size_t)b->S * b->Fmax * kp.el[e].n_in * kp.frame_size);
+      if (er != cudaSuccess) return fail(IAMFB_ERR_ALLOC_FAIL, "float32 staging of an int16 submit: %s", cudaGetErrorString(er));
+    }
+  return IAMFB_OK;
+}
+static int widen_streams(iamfb_batch *b, const iamfb_io *io, int F, int s_lo, int s_cnt, iamfb_io *wio) {
+  iamfb_ctx *ctx = b->plan->ctx;
+  const KernelPlan &kp = b->plan->kp;
+  int r = ensure_wide(b);
+  if (r) return r;
+  *wio = *io;
+  wio->in_format = IAMFB_IN_F32;
+  for (int e = 0; e < kp.n_elements; ++e) {
+    const size_t per = (size_t)F * kp.el[e].n_in * kp.frame_size, n = (size_t)s_cnt * per, n8 = n / 8, off = (size_t)s_lo * per;
+    const int16_t *src = reinterpret_cast<const int16_t *>(io->in[e]) + off;
+    float *dst = b->d_wide[e] + off;
+    {
+      ScopedKernelTimer tm_(ctx, "k_widen_s16");
+      if ((off & 7) == 0 && (((size_t)src) & 15) == 0) k_widen_s16<<<(unsigned)((n8 + 1 + 255) / 256), 256, 0, ctx->stream>>>(src, dst, n8, n);
+      else k_widen_s16<<<1, 256, 0, ctx->stream>>>(src, dst, 0, n);   // unaligned group start: scalar
+    }
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_widen_s16 failed: %s", cudaGetErrorString(e_));
+    ++ctx->launches;
+    wio->in[e] = b->d_wide[e];
+  }
+  return IAMFB_OK;
 }
 
 // runs the kernels of one submit (or flush) for the streams [s_lo, s_lo + s_cnt) of the batch; all pointers in `io`,
@@ -1224,6 +1252,13 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
   if (s_cnt < 0) s_cnt = b->S;
+  iamfb_io wio;
+  if (!flush && io->in_format == IAMFB_IN_S16) {
+    // kernels that stage float32 get a widened copy (x / 32768 is exact)
+    int r = widen_streams(b, io, F, s_lo, s_cnt, &wio);
+    if (r) return r;
+    io = &wio;
+  }
   const int S = s_cnt, N = kp.frame_size, co = kp.out_channels;
   if (!p->fused && (s_lo != 0 || s_cnt != b->S)) return fail(IAMFB_ERR_INTERNAL, "stream ranges need the fused path");
   const int n_sub = p->fused ? 1 : n_subchunks(kp, F, flush);
@@ -1320,16 +1355,7 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       ra.last = e == kp.n_elements - 1;
       ra.tiles_per_frame = tiles;
       int blocks = S * nf * tiles;
-      // the bulk-copy staged variant is bit-identical but measured slower than the direct one on B200 (1.01 vs 0.57 ms
-      // on configs[1]: the kernel is instruction-issue bound, not load-latency bound) - kept selectable for profiling
-      static const bool use_bulk = getenv("IAMFB_RENDER_BULK") && atoi(getenv("IAMFB_RENDER_BULK")) == 1;
-      int r;
-      if (vec4 && use_bulk) {
-        ra.tiles_per_frame = (N + kRenderTile - 1) / kRenderTile;
-        r = launch_render_bulk(ctx, p->tmpl[e], kp, ra, S * nf * ra.tiles_per_frame);
-      } else {
-        r = vec4 ? launch_render<4>(ctx, p->tmpl[e], kp, ra, blocks) : launch_render<1>(ctx, p->tmpl[e], kp, ra, blocks);
-      }
+      int r = vec4 ? launch_render<4>(ctx, p->tmpl[e], kp, ra, blocks) : launch_render<1>(ctx, p->tmpl[e], kp, ra, blocks);
       if (r) return r;
     }
     return IAMFB_OK;
@@ -1370,8 +1396,7 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       a.flush = flush ? 1 : 0;
       dim3 grid((max_out + 127) / 128, S);
       const size_t smem2 = p->d_tab4 ? sizeof(float4) * kp.rs_oversample * (kp.rs_filt_len + 1) + sizeof(float) * 2 * p->rs_span : 0;
-      static const bool old_rs = getenv("IAMFB_RESAMPLE_OLD") && atoi(getenv("IAMFB_RESAMPLE_OLD")) == 1;
-      if (p->d_tab4 && smem2 <= 200 * 1024 && !old_rs) {
+      if (p->d_tab4 && smem2 <= 200 * 1024) {
         Resample2Args a2;
         a2.r = a;
         a2.tab4 = p->d_tab4;
@@ -1409,7 +1434,6 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       ScanArgs sa;
       sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = b->d_submit; sa.acc = p->d_acc;
       sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = sub_len; sa.sub = c;
-      { const char *dbg = getenv("IAMFB_SCAN_DEBUG"); sa.debug = dbg ? atoi(dbg) : 0; }
       {
         ScopedKernelTimer tm_(ctx, "k_limiter_scan", scan_st);
         if (scan_smem) k_limiter_scan<true><<<(S + 31) / 32, kScanThreads, scan_smem, scan_st>>>(kp, sa);
@@ -1455,7 +1479,7 @@ extern "C" int iamfb_batch_submit_device(iamfb_batch *b, const iamfb_io *io, int
   for (int e = 0; e < b->plan->kp.n_elements; ++e)
     if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
   if (!io->params || !io->pcm) return fail(IAMFB_ERR_BAD_ARG, "submit: params / pcm is null");
-  if (io->in_format != IAMFB_IN_F32) return fail(IAMFB_ERR_BAD_ARG, "submit_device takes float32 input (in_format %d)", io->in_format);
+  if (io->in_format != IAMFB_IN_F32 && io->in_format != IAMFB_IN_S16) return fail(IAMFB_ERR_BAD_ARG, "submit: in_format %d", io->in_format);
   CU(cudaSetDevice(b->plan->ctx->device));
   return run_pipeline(b, io, n_frames, false, io->pcm, io->out_counts, iamfb_plan_out_stride_bytes(b->plan, n_frames));
 }
@@ -1491,25 +1515,6 @@ static int ensure_staging(iamfb_batch *b, int F) {
   return IAMFB_OK;
 }
 
-// int16 -> float32 * 2^-15 (the codec glue's scaling, opus/IAMF_opus_decoder.c:133-135); 8 samples per thread
-__global__ void __launch_bounds__(256) k_widen_s16(const int16_t *__restrict__ src, float *__restrict__ dst, size_t n8, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n8) {
-    const int4 v = reinterpret_cast<const int4 *>(src)[i];
-    const int w[4] = {v.x, v.y, v.z, v.w};
-    float o[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      o[2 * k] = (float)(short)(w[k] & 0xffff) / 32768.f;
-      o[2 * k + 1] = (float)(short)(w[k] >> 16) / 32768.f;
-    }
-    reinterpret_cast<float4 *>(dst)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
-    reinterpret_cast<float4 *>(dst)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
-  } else if (i == n8) {
-    for (size_t k = n8 * 8; k < n; ++k) dst[k] = (float)src[k] / 32768.f;
-  }
-}
-
 extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F) {
   if (!b || !io) return fail(IAMFB_ERR_BAD_ARG, "submit: null argument");
   if (F <= 0 || F > b->Fmax) return fail(IAMFB_ERR_BAD_ARG, "submit: %d frames (batch sized for %d)", F, b->Fmax);
@@ -1528,7 +1533,8 @@ extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F
     if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
   iamfb_io dio;
   memset(&dio, 0, sizeof(dio));
-  for (int e = 0; e < kp.n_elements; ++e) dio.in[e] = b->d_in[e];
+  for (int e = 0; e < kp.n_elements; ++e) dio.in[e] = s16 ? reinterpret_cast<const float *>(b->d_in16[e]) : b->d_in[e];
+  dio.in_format = io->in_format;
   dio.params = b->d_params;
   dio.pcm = b->d_pcm;
   dio.out_counts = b->d_counts;
@@ -1537,10 +1543,7 @@ extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F
   // range, the multi-kernel path runs the batch as one group
   int n_chunks = 1;
   if (p->fused && S >= 64) {
-    const char *env = getenv("IAMFB_HOST_CHUNKS");
-    n_chunks = env ? atoi(env) : 8;   // measured on configs[1]: 2 -> 35.6k, 4 -> 38.9k, 8 -> 41.1k audio-s/s (the last group's download is the exposed tail)
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > kMaxChunks) n_chunks = kMaxChunks;
+    n_chunks = 8;   // measured on configs[1]: 2 -> 35.6k, 4 -> 38.9k, 8 -> 41.1k audio-s/s (the last group's download is the exposed tail)
   }
   // the staging buffers are reused by every submit: uploads must not start before the previous submit's kernels are done
   CU(cudaEventRecord(ctx->ev_free, st));
@@ -1568,20 +1571,6 @@ extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F
     }
     CU(cudaEventRecord(ctx->ev_up[c], ctx->h2d));
     CU(cudaStreamWaitEvent(st, ctx->ev_up[c], 0));
-    if (s16) {
-      for (int e = 0; e < kp.n_elements; ++e) {
-        const size_t per = (size_t)F * kp.el[e].n_in * N, n = cnt * per, n8 = n / 8;
-        const size_t off = s_lo * per;
-        if ((off & 7) == 0) {
-          ScopedKernelTimer tm_(ctx, "k_widen_s16");
-          k_widen_s16<<<(unsigned)((n8 + 1 + 255) / 256), 256, 0, st>>>(b->d_in16[e] + off, b->d_in[e] + off, n8, n);
-        } else {
-          ScopedKernelTimer tm_(ctx, "k_widen_s16");
-          k_widen_s16<<<1, 256, 0, st>>>(b->d_in16[e] + off, b->d_in[e] + off, 0, n);   // unaligned group start: scalar
-        }
-        LAUNCH_CHECK("k_widen_s16");
-      }
-    }
     r = run_pipeline(b, &dio, F, false, b->d_pcm, b->d_counts, stride, (int)s_lo, (int)cnt);
     if (r) return r;
     CU(cudaEventRecord(ctx->ev_done[c], st));

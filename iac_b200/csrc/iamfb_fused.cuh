@@ -113,8 +113,8 @@ __device__ __forceinline__ Vec<VEC> exact_div4(const Vec<VEC> &x, float d, float
   if (bad | (d == 0.f ? 1u : 0u)) slow_div4<VEC>(q, x, d);
   return q;
 }
-__constant__ float c_mix_beta_r[8] = {1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f, 1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f};
-__constant__ float c_mix_gd_r[8] = {1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f, 1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f};
+static __constant__ float c_mix_beta_r[8] = {1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f, 1.0f / 1.0f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f};
+static __constant__ float c_mix_gd_r[8] = {1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f, 1.0f / 0.707f, 1.0f / 0.707f, 1.0f / 0.866f, 0.f};
 
 // Channel-based reconstruction (demixer.c:127-378,421-475) from the staged rows.  in_q = the block's staged tile at
 // this thread's four samples; every IAChannel has a byte offset to its row (an all-zero row when absent) and an

@@ -37,15 +37,15 @@ __device__ __forceinline__ float ldg_stream1(const float *p) {
 }
 
 // demixing_type_mat (demixer.c:62-72): mode -> alpha, beta, gamma, delta, w step
-__constant__ float c_mix_alpha[8] = {1.0f, 0.707f, 1.0f, 0.f, 1.0f, 0.707f, 1.0f, 0.f};
-__constant__ float c_mix_beta[8] = {1.0f, 0.707f, 0.866f, 0.f, 1.0f, 0.707f, 0.866f, 0.f};
-__constant__ float c_mix_gamma[8] = {0.707f, 0.707f, 0.866f, 0.f, 0.707f, 0.707f, 0.866f, 0.f};
-__constant__ float c_mix_delta[8] = {0.707f, 0.707f, 0.866f, 0.f, 0.707f, 0.707f, 0.866f, 0.f};
-__constant__ int c_mix_woff[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+static __constant__ float c_mix_alpha[8] = {1.0f, 0.707f, 1.0f, 0.f, 1.0f, 0.707f, 1.0f, 0.f};
+static __constant__ float c_mix_beta[8] = {1.0f, 0.707f, 0.866f, 0.f, 1.0f, 0.707f, 0.866f, 0.f};
+static __constant__ float c_mix_gamma[8] = {0.707f, 0.707f, 0.866f, 0.f, 0.707f, 0.707f, 0.866f, 0.f};
+static __constant__ float c_mix_delta[8] = {0.707f, 0.707f, 0.866f, 0.f, 0.707f, 0.707f, 0.866f, 0.f};
+static __constant__ int c_mix_woff[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
 // widx2w_table (fixedp11_5.c:81-82)
-__constant__ float c_w_table[11] = {0.0f, 0.0179f, 0.0391f, 0.0658f, 0.1038f, 0.25f, 0.3962f, 0.4342f, 0.4609f, 0.4821f, 0.5f};
+static __constant__ float c_w_table[11] = {0.0f, 0.0179f, 0.0391f, 0.0658f, 0.1038f, 0.25f, 0.3962f, 0.4342f, 0.4609f, 0.4821f, 0.5f};
 // recon channel bit -> IAChannel per layout (IAMF_decoder.c:409-448)
-__constant__ unsigned char c_recon_map[9][12] = {
+static __constant__ unsigned char c_recon_map[9][12] = {
     {13, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},        {14, 0, 15, 0, 0, 0, 0, 0, 0, 0, 0, 0},
     {1, 3, 2, 20, 21, 0, 0, 0, 0, 0, 0, 4},       {1, 3, 2, 20, 21, 22, 23, 0, 0, 0, 0, 4},
     {1, 3, 2, 20, 21, 9, 10, 0, 0, 11, 12, 4},    {1, 3, 2, 5, 6, 0, 0, 7, 8, 0, 0, 4},
@@ -357,7 +357,7 @@ struct Vec {
   float v[VEC];
 };
 
-// SMEM: the source is a shared-memory tile staged by bulk async copies (k_render_bulk), else global memory
+// SMEM: the source is a shared-memory tile, else global memory
 template <int VEC, bool SMEM>
 __device__ __forceinline__ Vec<VEC> load_row(const float *p, bool vec_ok, int valid) {
   Vec<VEC> r;
@@ -673,14 +673,7 @@ __global__ void __launch_bounds__(128, 4) k_render(const __grid_constant__ Kerne
   render_thread<LAYOUT, NREC, VEC, false>(plan, a, s, sf, i0, src, N);
 }
 
-// ---- bulk-copy (TMA) staged variant ---------------------------------------------------------------------------------
-// Persistent CTAs walk the (stream, frame, 512-sample tile) list.  One elected thread issues cp.async.bulk copies of
-// the tile's n_in rows (2 KB each) into a ring of shared-memory stages guarded by mbarriers; the 128 compute threads
-// wait for a stage, read their float4 per channel from shared memory (conflict free) and run the same arithmetic.
-// The copy engine keeps kRenderStages tiles in flight per CTA independent of register pressure.
-constexpr int kRenderStages = 3;
-constexpr int kRenderTile = 512;
-
+// ---- bulk-copy (TMA) / mbarrier helpers used by the single-kernel paths
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -705,59 +698,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-
-template <int LAYOUT, int NREC>
-__global__ void __launch_bounds__(128, 3) k_render_bulk(const __grid_constant__ KernelPlan plan, RenderArgs a, int n_tiles_total) {
-  extern __shared__ __align__(128) float s_stage[];            // [kRenderStages][n_in][kRenderTile]
-  __shared__ __align__(8) uint64_t s_full[kRenderStages];
-  const int N = plan.frame_size;
-  const int n_in = plan.el[a.e].n_in;
-  const int stage_floats = n_in * kRenderTile;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < kRenderStages; ++i) mbar_init(&s_full[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  auto issue = [&](int tile_id, int stage) {
-    // tile_id -> (stream, frame, tile inside the frame)
-    const int tile = tile_id % a.tiles_per_frame;
-    const int sfl = tile_id / a.tiles_per_frame;
-    const int s = sfl / a.nf;
-    const int sf = s * a.n_frames + a.f_lo + sfl % a.nf;
-    const int t0 = tile * kRenderTile;
-    const int len = min(kRenderTile, N - t0);
-    const float *g = a.in + (size_t)sf * n_in * N + t0;
-    float *d = s_stage + (size_t)stage * stage_floats;
-    mbar_expect_tx(&s_full[stage], (uint32_t)(n_in * len * sizeof(float)));
-    for (int r = 0; r < n_in; ++r) bulk_g2s(d + r * kRenderTile, g + (size_t)r * N, (uint32_t)(len * sizeof(float)), &s_full[stage]);
-  };
-
-  const int first = blockIdx.x, stride = gridDim.x;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kRenderStages; ++i)
-      if (first + i * stride < n_tiles_total) issue(first + i * stride, i);
-  }
-  int it = 0;
-  for (int tile_id = first; tile_id < n_tiles_total; tile_id += stride, ++it) {
-    const int stage = it % kRenderStages;
-    const uint32_t parity = (it / kRenderStages) & 1;
-    mbar_wait(&s_full[stage], parity);
-    const int tile = tile_id % a.tiles_per_frame;
-    const int sfl = tile_id / a.tiles_per_frame;
-    const int s = sfl / a.nf;
-    const int sf = s * a.n_frames + a.f_lo + sfl % a.nf;
-    const int i0 = tile * kRenderTile + threadIdx.x * 4;
-    if (i0 < N) {
-      const float *src = s_stage + (size_t)stage * stage_floats + threadIdx.x * 4;
-      render_thread<LAYOUT, NREC, 4, true>(plan, a, s, sf, i0, src, kRenderTile);
-    }
-    __syncthreads();                                            // everyone is done reading this stage
-    const int next = tile_id + kRenderStages * stride;
-    if (threadIdx.x == 0 && next < n_tiles_total) issue(next, stage);
-  }
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -1020,7 +960,6 @@ struct ScanArgs {
   int cap, hist, n_streams;
   int max_len;
   int sub;              // sub-chunk processed by this launch
-  int debug;            // profiling aid: 1 = scanner skips the serial walk (results wrong), 0 = normal
 };
 
 // Warp-specialised block of 16 warps per 32 streams:
@@ -1127,7 +1066,7 @@ __global__ void __launch_bounds__(kScanThreads) k_limiter_scan(const __grid_cons
       const int k0 = (t - 1) * 32;
       const bool idle = (j < 0 || j >= jr);
       const bool quiet = idle && t_max[b][lane] == 0.0f;
-      if (!__all_sync(0xffffffffu, quiet) && a.debug != 1) {
+      if (!__all_sync(0xffffffffu, quiet)) {
         const int nk = min(32, len - k0);
         // Speculative form of compute_target_gain (:237-265).  cont(m) = the gain m steps ahead if no trigger fires
         // until then; it only depends on the state at the last trigger (start S, end E, D = S-E, R = 1-E) and on the

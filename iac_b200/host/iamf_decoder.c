@@ -864,7 +864,9 @@ static int prepare_frame(IAMF_DecoderHandle h, float *const in[], iamfb_frame_pa
     real = samples;
     if (st->mix_gain) { /* :3425-3433 */
       float g = 1.f;
-      int kind = ih_mix_gain_unit(st->mix_gain, pts, samples, st->cc->rate, &g, ramp[s]);
+      /* the gain time line is read at the frame's pts AFTER trimming: iamf_frame_trim does f->pts += strim (:1379)
+       * before get_mix_gain_unit(f->pts, f->samples) (:3425-3427) */
+      int kind = ih_mix_gain_unit(st->mix_gain, pts + (uint64_t)st->strim, samples, st->cc->rate, &g, ramp[s]);
       if (kind == 1) fp->el[s].mix_gain = g;
       else if (kind == 2) use_ramp[s] = 1;
     }
@@ -878,7 +880,8 @@ static int prepare_frame(IAMF_DecoderHandle h, float *const in[], iamfb_frame_pa
   }
   if (h->out_gain_item) { /* :3463-3469 */
     float g = 1.f;
-    int kind = ih_mix_gain_unit(h->out_gain_item, frame_pts, real, h->streams[0].cc->rate, &g, out_ramp);
+    /* the mixed frame carries the (trimmed) pts of the first element's frame (iamf_mixer_mix :2702-2733) */
+    int kind = ih_mix_gain_unit(h->out_gain_item, frame_pts + (uint64_t)h->streams[0].strim, real, h->streams[0].cc->rate, &g, out_ramp);
     if (kind == 1) fp->out_gain = g;
     else if (kind == 2) *use_out_ramp = 1;
   }

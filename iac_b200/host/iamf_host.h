@@ -20,6 +20,7 @@
 #define IH_MAX_PARAMS 32
 #define IH_MAX_LAYERS 6
 #define IH_MAX_SUBSTREAMS 32
+#define IH_MAX_SEGMENTS 4096 /* parameter-block segments accepted per block (a stream-supplied count) */
 #define IH_INVALID_ID ((uint64_t)-1)
 
 /* ---- byte / bit reader (MSB first; byte-aligned reads realign first, like bitstream.c:39-160) ---- */

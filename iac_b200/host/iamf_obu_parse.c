@@ -105,8 +105,12 @@ uint32_t ih_obu_split(const uint8_t *data, uint32_t size, ih_obu *o) {
   }
   if (extension) {
     uint64_t ext = ih_rd_leb128(&r);
+    /* a malformed / truncated OBU: the optional header fields must end inside the OBU (IAMF_OBU.c:79-138 reads them
+     * from the same bounded bit stream) */
+    if (ext == UINT64_MAX || ih_rd_tell(&r) > o->total_size || ext > (uint64_t)(o->total_size - ih_rd_tell(&r))) return 0;
     ih_rd_bytes(&r, 0, (uint32_t)ext);
   }
+  if (ih_rd_tell(&r) > o->total_size) return 0;
   o->payload = data + ih_rd_tell(&r);
   o->payload_size = o->total_size - ih_rd_tell(&r);
   return o->total_size;
@@ -217,6 +221,14 @@ int ih_parse_element(const ih_obu *o, ih_element *e) {
         l->out_gain_q = (int16_t)ih_rd_u16(&r);
       }
     }
+    {   /* the layers' sub-streams are the element's sub-streams (they index st->pkt, IH_MAX_SUBSTREAMS entries) */
+      int sum = 0;
+      for (int i = 0; i < e->n_layers; ++i) {
+        if (e->layers[i].n_coupled > e->layers[i].n_sub) return IAMF_ERR_INVALID_PACKET;
+        sum += e->layers[i].n_sub;
+      }
+      if (sum != e->n_sub) return IAMF_ERR_INVALID_PACKET;
+    }
   } else if (e->type == 1) {
     e->ambi_mode = (int)ih_rd_leb128(&r);
     if (e->ambi_mode == 0) {
@@ -231,6 +243,12 @@ int ih_parse_element(const ih_obu *o, ih_element *e) {
     } else {
       return IAMF_ERR_INVALID_PACKET;
     }
+    /* sub-stream counts index st->pkt / pkt_size / codec_state (IH_MAX_SUBSTREAMS entries) and the engine's 16-row
+     * scene input: they must agree with the element's own sub-stream list (IAMF_OBU.c:512-607 reads them from the same
+     * element) */
+    if (e->ambi_sub != e->n_sub || e->ambi_coupled > e->ambi_sub || e->ambi_sub + e->ambi_coupled > IAMFB_MAX_SCENE_CH ||
+        e->ambi_channels < 1 || e->ambi_channels > IAMFB_MAX_SCENE_CH)
+      return IAMF_ERR_INVALID_PACKET;
     if (e->ambi_map_size > (int)sizeof(e->ambi_map)) return IAMF_ERR_UNIMPLEMENTED;
     ih_rd_bytes(&r, e->ambi_map, (uint32_t)e->ambi_map_size);
   } else {
@@ -310,11 +328,18 @@ ih_segment *ih_parse_parameter_block(const ih_obu *o, uint64_t *pid_out, const i
   } else {
     duration = ih_rd_leb128(&r);
     const_iv = ih_rd_leb128(&r);
-    nseg = const_iv ? (int)((duration + const_iv - 1) / const_iv) : (int)ih_rd_leb128(&r);
+    uint64_t ns = const_iv ? (duration + const_iv - 1) / const_iv : ih_rd_leb128(&r);
+    if (duration == UINT64_MAX || const_iv == UINT64_MAX || ns > IH_MAX_SEGMENTS) return 0;
+    nseg = (int)ns;
   }
+  /* the segment count comes from the stream: every segment takes at least one payload byte (a demixing mode, a
+   * leb128 animation type, a recon flag word), so a count beyond the bytes left - or beyond a sane limit - is a
+   * malformed block, not a reason to allocate */
+  if (nseg < 0 || nseg > IH_MAX_SEGMENTS || (uint32_t)nseg > o->payload_size) return 0;
   ih_segment *head = 0, *tail = 0;
   uint64_t left = duration, iv = 0;
   for (int i = 0; i < nseg; ++i) {
+    if (ih_rd_tell(&r) > o->payload_size) break;   /* ran past the payload: stop (reads past the end return 0) */
     if (!const_iv) iv = def->mode ? ih_rd_leb128(&r) : (i < 16 ? def->seg_interval[i] : 0);
     uint64_t seg_iv = iv ? iv : (const_iv < left ? const_iv : left);
     left -= seg_iv;
