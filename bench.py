@@ -603,7 +603,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (used under ncu)")
     ap.add_argument("--step-ms", type=float, default=60.0, help="target duration of one step (a step = R back-to-back submits)")
     ap.add_argument("--submits-per-step", type=int, default=0, help="R; 0 = derive it from --step-ms")
-    ap.add_argument("--in-format", default="f32", choices=["f32", "s16"], help="device-resident decoded input format")
+    ap.add_argument("--in-format", default="s16", choices=["f32", "s16"], help="device-resident decoded input format")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--peak-db", default="", help="experiment: override the per-stream peak range, e.g. -40,-30")
     ap.add_argument("--peak-ref", default="rendered", choices=["rendered", "input"],

@@ -11,10 +11,12 @@
 #include <vector>
 
 #include "iamf_b200.h"
+#include "iamfb_internal.h"
 #include "iamfb_kernels.cuh"
 #include "iamfb_fused.cuh"
 #include "iamfb_matrices.inc"
 #include "iamfb_stream.cuh"
+#include "iamfb_pipe.cuh"
 
 using namespace iamfb;
 
@@ -22,7 +24,7 @@ using namespace iamfb;
 // errors
 // ---------------------------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int fail(int code, const char *fmt, ...) {
+int iamfb_fail(int code, const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -30,11 +32,6 @@ static int fail(int code, const char *fmt, ...) {
   fprintf(stderr, "[iamf_b200] error %d: %s\n", code, g_err);
   return code;
 }
-#define CU(call)                                                                                       \
-  do {                                                                                                 \
-    cudaError_t e_ = (call);                                                                           \
-    if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_));     \
-  } while (0)
 
 extern "C" const char *iamfb_last_error(void) { return g_err; }
 extern "C" const char *iamfb_version(void) { return "iamf_b200 0.1 (sm_100a)"; }
@@ -98,60 +95,6 @@ extern "C" int iamfb_get_h2m_matrix(int order, int target, int32_t *m, int32_t *
 // ---------------------------------------------------------------------------------------------------------------------
 // objects
 // ---------------------------------------------------------------------------------------------------------------------
-struct KernelTimer {
-  const char *name;
-  double total_ms;
-  uint64_t launches;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
-};
-
-constexpr int kMaxChunks = 32;
-
-struct iamfb_ctx {
-  int device;
-  cudaStream_t stream;
-  bool own_stream;
-  uint64_t launches;
-  bool timing;
-  std::vector<KernelTimer> timers;
-  std::vector<cudaEvent_t> event_pool;
-  // second stream for the latency-bound limiter scan, so that it overlaps the bandwidth-bound kernels of the
-  // neighbouring sub-chunks; ordered against the main stream with events
-  cudaStream_t aux;
-  cudaEvent_t ev_w[kMaxSub], ev_s[kMaxSub];
-  // host-resident submits: copy engines run on their own streams so that the upload of one group of streams, the
-  // kernels of the previous group and the download of the one before overlap (PCIe is full duplex)
-  cudaStream_t h2d, d2h;
-  cudaEvent_t ev_up[kMaxChunks], ev_done[kMaxChunks], ev_free;
-};
-
-// optional per-kernel CUDA-event timing (bench.py's roofline leg); events are recorded on the launching stream
-struct ScopedKernelTimer {
-  iamfb_ctx *ctx;
-  KernelTimer *t = nullptr;
-  cudaEvent_t a = nullptr, b = nullptr;
-  static cudaEvent_t get(iamfb_ctx *c) {
-    cudaEvent_t e;
-    if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
-    cudaEventCreate(&e);
-    return e;
-  }
-  cudaStream_t st;
-  ScopedKernelTimer(iamfb_ctx *c, const char *name, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
-    if (!c->timing) return;
-    for (auto &k : c->timers) if (k.name == name) t = &k;
-    if (!t) { c->timers.push_back(KernelTimer{name, 0.0, 0, {}}); t = &c->timers.back(); }
-    a = get(c); b = get(c);
-    cudaEventRecord(a, st);
-  }
-  ~ScopedKernelTimer() {
-    if (!t) return;
-    cudaEventRecord(b, st);
-    t->pending.emplace_back(a, b);
-    ++t->launches;
-  }
-};
-
 struct iamfb_plan {
   iamfb_ctx *ctx;
   iamfb_plan_desc desc;
@@ -177,6 +120,10 @@ struct iamfb_plan {
   bool stream;
   int stream_sig;          // layout * 16 + target
   size_t stream_smem;
+  // k_pipe (iamfb_pipe.cuh): double-buffered int16 / float32 staging, channel-based, scene-based and two-element signatures
+  bool pipe;
+  int pipe_sig;
+  bool s16_native;         // int16 submits (IAMFB_IN_S16) are staged as they are by k_pipe / k_fused
 };
 
 struct iamfb_batch {
@@ -793,15 +740,15 @@ static EncodeTiledFn tensor_map_encoder() {
   }();
   return fn;
 }
-static int make_input_tmap(CUtensorMap *tm, const float *base, size_t rows, int N, int n_in) {
+static int make_input_tmap(CUtensorMap *tm, const void *base, size_t rows, int N, int n_in, bool s16) {
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return fail(IAMFB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if ((((size_t)base) & 15) != 0) return fail(IAMFB_ERR_BAD_ARG, "decoded input must be 16-byte aligned");
   const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)N * sizeof(float)};
+  const cuuint64_t strides[1] = {(cuuint64_t)N * (s16 ? 2 : 4)};
   const cuuint32_t box[2] = {(cuuint32_t)kStreamTile, (cuuint32_t)n_in};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(tm, s16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(IAMFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return IAMFB_OK;
@@ -814,7 +761,7 @@ static int launch_stream(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &f
   bool done = false;
   CUtensorMap tm;
   {
-    int r = make_input_tmap(&tm, fa.in[0], (size_t)S * fa.n_frames * kp.el[0].n_in, kp.frame_size, kp.el[0].n_in);
+    int r = make_input_tmap(&tm, fa.in[0], (size_t)S * fa.n_frames * kp.el[0].n_in, kp.frame_size, kp.el[0].n_in, false);
     if (r) return r;
   }
 #define X(L, T)                                                                                                       \
@@ -946,11 +893,14 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
         const int budget = (int)((233472 / blocks - 1024 - 64) / 4);
         int tl_max = (budget - 2 * kWmPad - (co + 1) * H) / (nin + 1 + co + 1 + 3);
         if (tl_max > 1024) tl_max = 1024;
-        tl_max &= ~3;
+        // (frames that are multiples of 8 samples get tiles that are: int16 rows are then staged 16 bytes at a time)
+        const int tq = (kp.frame_size & 7) == 0 ? 8 : 4;
+        tl_max &= ~(tq - 1);
         if (tl_max < 64) continue;
         const int n_tiles = (kp.frame_size + tl_max - 1) / tl_max;
         int t = (kp.frame_size + n_tiles - 1) / n_tiles;
-        t = (t + 3) & ~3;
+        t = (t + tq - 1) & ~(tq - 1);
+        if (t > tl_max) continue;
         if (t >= 240 || n_tiles == 1 || blocks == 3) { tl = t; blocks_per_sm = blocks; }
       }
       if (tl >= 64) {
@@ -996,10 +946,139 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
           }
         }
         fill_fused_offsets(kp, tl, nin);
+        p->s16_native = (kp.frame_size & 7) == 0;
+        // k_pipe: every element either channel-based through a channel->channel matrix or scene-based with a mono
+        // channel mapping, the compile-time tables equal to the plan's matrices, frames that are whole limiter windows
+        p->pipe = false;
+        {
+          const char *penv = getenv("IAMFB_PIPE");
+          const bool pwant = !penv || atoi(penv) != 0;
+          int key[2][2] = {{0, 0}, {0, 0}};
+          bool ok = pwant && kp.frame_size % kStreamTile == 0 && (kp.frame_size & 7) == 0;
+          for (int e = 0; ok && e < kp.n_elements; ++e) {
+            const ElPlan &ep = kp.el[e];
+            if (ep.kind == IAMFB_EL_CHANNEL) {
+              if (ep.renderer != kRdrM2M) ok = false;
+              for (int m = 0; ok && m < ep.n_rec; ++m)
+                if ((ep.gain_mask >> ep.rec_ch[m]) & 1u) ok = false;     // output gain on a channel of the layout itself: k_fused
+              key[e][0] = ep.layout; key[e][1] = ep.n_rec;
+              const int idx = m2m_find(ep.layout, d->target);
+              if (idx < 0 || k_m2m_index[idx].m != ep.n_rec || k_m2m_index[idx].n != co || ep.n_mat_out != co) ok = false;
+              for (int oc = 0; ok && oc < co; ++oc) {
+                if (ep.out_slot[oc] != oc) ok = false;
+                for (int m = 0; ok && m < ep.n_rec; ++m) {
+                  uint32_t bits;
+                  memcpy(&bits, &ep.mat[oc * ep.n_rec + m], 4);
+                  if (bits != k_matrix_pool[k_m2m_index[idx].off + m * co + oc]) ok = false;
+                }
+              }
+            } else {
+              if (ep.ambi_mode != 0) ok = false;                         // projection matrices are run-time data: k_fused
+              key[e][0] = -1; key[e][1] = ep.n_rec;
+              const int order = ep.n_rec == 1 ? 0 : ep.n_rec == 4 ? 1 : ep.n_rec == 9 ? 2 : 3;
+              int idx = -1;
+              for (size_t i = 0; i < sizeof(k_h2m_index) / sizeof(k_h2m_index[0]); ++i)
+                if (k_h2m_index[i].order == order && k_h2m_index[i].out == d->target) idx = (int)i;
+              if (idx < 0 || k_h2m_index[idx].m != ep.n_rec || k_h2m_index[idx].n != ep.n_mat_out) ok = false;
+              for (int oc = 0; ok && oc < co; ++oc) {
+                const int n = ep.out_slot[oc];
+                if (n >= ep.n_mat_out) ok = false;
+                for (int m = 0; ok && n >= 0 && m < ep.n_rec; ++m) {
+                  uint32_t bits;
+                  memcpy(&bits, &ep.mat[n * ep.n_rec + m], 4);
+                  if (bits != k_matrix_pool[k_h2m_index[idx].off + n * ep.n_rec + m]) ok = false;
+                }
+              }
+            }
+          }
+          const PipeSigInfo *si = ok ? iamfb_pipe_find(key[0][0], key[0][1], kp.n_elements > 1 ? key[1][0] : 0, kp.n_elements > 1 ? key[1][1] : 0, d->target) : nullptr;
+          if (si) {
+            // the second element's rows follow the first's inside a stage: tensor copies land on 128-byte boundaries
+            const int n0 = kp.el[0].n_in;
+            if (kp.n_elements > 1 && (((n0 * kStreamTile * 2) & 127) != 0)) si = nullptr;
+          }
+          if (si) {
+            p->pipe = true;
+            p->pipe_sig = si->id;
+            p->stream = false;                                             // k_pipe supersedes k_stream where both exist
+          }
+        }
       }
     }
   }
   *out = p;
+  return IAMFB_OK;
+}
+
+// ---- k_pipe dispatch (the instantiations live in iamfb_pipe_g<N>.cu)
+static const PipeSigInfo k_pipe_sigs[] = {
+#define X(id, L0, N0, L1, N1, T, NW, VEC, MINB) {id, L0, N0, L1, N1, T, NW, VEC},
+    IAMFB_PIPE_SIGS(X)
+#undef X
+};
+const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target) {
+  for (const PipeSigInfo &si : k_pipe_sigs)
+    if (si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
+  return nullptr;
+}
+#define G(n) int iamfb_pipe_launch_g##n(iamfb_ctx *, int, bool, const KernelPlan &, const PipeArgs &, int, size_t, const CUtensorMap &, const CUtensorMap &);
+G(0) G(1) G(2) G(3) G(4) G(5) G(6)
+#undef G
+int iamfb_pipe_launch(iamfb_ctx *ctx, int sig_id, bool s16, const KernelPlan &kp, const PipeArgs &pa, int S, size_t smem, const CUtensorMap &m0,
+                      const CUtensorMap &m1) {
+  switch (IAMFB_PIPE_GROUP_OF(sig_id)) {
+    case 0: return iamfb_pipe_launch_g0(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    case 1: return iamfb_pipe_launch_g1(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    case 2: return iamfb_pipe_launch_g2(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    case 3: return iamfb_pipe_launch_g3(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    case 4: return iamfb_pipe_launch_g4(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    case 5: return iamfb_pipe_launch_g5(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    default: return iamfb_pipe_launch_g6(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+  }
+}
+
+static int make_input_tmap(CUtensorMap *tm, const void *base, size_t rows, int N, int n_in, bool s16);
+static int launch_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa, int S, bool s16) {
+  const KernelPlan &kp = p->kp;
+  const PipeSigInfo *si = nullptr;
+  for (const PipeSigInfo &k : k_pipe_sigs)
+    if (k.id == p->pipe_sig) si = &k;
+  if (!si) return fail(IAMFB_ERR_INTERNAL, "no k_pipe signature %d", p->pipe_sig);
+  PipeArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  int nin = 0;
+  CUtensorMap tm[2];
+  for (int e = 0; e < kp.n_elements; ++e) {
+    pa.in[e] = fa.in[e];
+    nin += kp.el[e].n_in;
+    int r = make_input_tmap(&tm[e], fa.in[e], (size_t)S * fa.n_frames * kp.el[e].n_in, kp.frame_size, kp.el[e].n_in, s16);
+    if (r) return r;
+  }
+  if (kp.n_elements == 1) tm[1] = tm[0];
+  pa.frames = fa.frames; pa.start_win = fa.start_win; pa.stop_win = fa.stop_win; pa.submit = fa.submit; pa.state = fa.state;
+  pa.acc = fa.acc; pa.hist_y = fa.hist_y; pa.hist_pk = fa.hist_pk; pa.pcm = fa.pcm; pa.stride_bytes = fa.stride_bytes;
+  pa.n_frames = fa.n_frames;
+  pa.row_bytes = kStreamTile * (s16 ? 2 : 4);
+  const int rec = (int)((sizeof(FrameRec) + 127) & ~(size_t)127);
+  pa.stage_bytes = (rec + nin * pa.row_bytes + 127) & ~127;
+  // active output channels of the signature (rows of the time line): every channel some matrix row of an element lands on
+  int ny = 0;
+  for (int oc = 0; oc < kp.out_channels; ++oc) {
+    bool any = false;
+    for (int e = 0; e < kp.n_elements; ++e) {
+      const ElPlan &ep = kp.el[e];
+      const int n = ep.out_slot[oc];
+      for (int m = 0; n >= 0 && m < ep.n_rec; ++m)
+        if (ep.mat[n * ep.n_rec + m] != 0.f) any = true;
+    }
+    ny += any ? 1 : 0;
+  }
+  const size_t smem = (((size_t)(ny * 2 + 6) * kStreamTile * 4 + 127) & ~(size_t)127) + (size_t)(s16 ? 2 : 1) * pa.stage_bytes;
+  int r = iamfb_pipe_launch(ctx, si->id, s16, kp, pa, S, smem, tm[0], tm[1]);
+  if (r) return r;
+  cudaError_t e_ = cudaGetLastError();
+  if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_pipe failed: %s", cudaGetErrorString(e_));
+  ++ctx->launches;
   return IAMFB_OK;
 }
 
@@ -1044,7 +1123,7 @@ extern "C" int iamfb_plan_out_channels(const iamfb_plan *p) { return p ? p->kp.o
 
 extern "C" int iamfb_plan_kernel_path(const iamfb_plan *p) {
   if (!p || !p->fused) return IAMFB_PATH_MULTI;
-  return p->stream ? IAMFB_PATH_STREAM : IAMFB_PATH_FUSED;
+  return p->pipe ? IAMFB_PATH_PIPE : (p->stream ? IAMFB_PATH_STREAM : IAMFB_PATH_FUSED);
 }
 
 extern "C" int iamfb_plan_max_out_samples(const iamfb_plan *p, int n_frames) {
@@ -1253,7 +1332,8 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   cudaStream_t st = ctx->stream;
   if (s_cnt < 0) s_cnt = b->S;
   iamfb_io wio;
-  if (!flush && io->in_format == IAMFB_IN_S16) {
+  const bool s16_in = !flush && io->in_format == IAMFB_IN_S16 && p->fused && p->s16_native && !(p->stream && !p->pipe);
+  if (!flush && io->in_format == IAMFB_IN_S16 && !s16_in) {
     // kernels that stage float32 get a widened copy (x / 32768 is exact)
     int r = widen_streams(b, io, F, s_lo, s_cnt, &wio);
     if (r) return r;
@@ -1292,7 +1372,8 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     memset(&fa, 0, sizeof(fa));
     if (!flush)
       for (int e = 0; e < kp.n_elements; ++e) {
-        fa.in[e] = io->in[e] + (size_t)s_lo * fF * kp.el[e].n_in * N;
+        fa.in[e] = s16_in ? reinterpret_cast<const float *>(reinterpret_cast<const int16_t *>(io->in[e]) + (size_t)s_lo * fF * kp.el[e].n_in * N)
+                          : io->in[e] + (size_t)s_lo * fF * kp.el[e].n_in * N;
         fa.gain_ramp[e] = io->gain_ramp[e] ? io->gain_ramp[e] + (size_t)s_lo * fF * N : nullptr;
       }
     fa.out_gain_ramp = (flush || !io->out_gain_ramp) ? nullptr : io->out_gain_ramp + (size_t)s_lo * fF * N;
@@ -1310,7 +1391,13 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     fa.flush = flush ? 1 : 0;
     fa.tile = p->fused_tile;
     fa.only_irregular = 0;
-    if (p->stream && !flush && !io->gain_ramp[0] && !io->out_gain_ramp) {
+    fa.in_s16 = s16_in ? 1 : 0;
+    if (p->pipe && !flush && !io->gain_ramp[0] && !io->gain_ramp[1] && !io->out_gain_ramp) {
+      // untrimmed streams: the pipelined kernel; the rest (flagged by k_resolve): k_fused
+      int r = launch_pipe(ctx, p, fa, S, s16_in);
+      if (r) return r;
+      fa.only_irregular = 1;
+    } else if (p->stream && !flush && !io->gain_ramp[0] && !io->out_gain_ramp) {
       // untrimmed streams: the register-resident pipelined kernel; the rest (flagged by k_resolve): k_fused
       int r = launch_stream(ctx, p, fa, S);
       if (r) return r;

@@ -40,7 +40,8 @@ struct FusedArgs {
   void *pcm;
   size_t stride_bytes;
   int n_frames, flush, tile;
-  int only_irregular;           // 1 = only the streams k_stream left alone (trimmed / missing frames)
+  int only_irregular;           // 1 = only the streams k_stream / k_pipe left alone (trimmed / missing frames)
+  int in_s16;                   // the decoded rows are int16 (IAMFB_IN_S16): widened in the stage right after the copy
 };
 
 constexpr int kWmPad = 320;     // scratch beyond the tile: 240 history + 64 (widest doubling step) + 16
@@ -92,7 +93,7 @@ __device__ __forceinline__ constexpr int fused_order(int layout, int m) {   // I
 // finite x with 2^-100 <= |x| < 2^126 - verified exhaustively over all 2^32 inputs for each of the three divisors
 // (tools/check_fast_div.c); outside that range (and for d == 0) the ordinary division is used, +-0 maps to q0 = +-0.
 template <int VEC>
-__device__ __noinline__ void slow_div4(Vec<VEC> &q, const Vec<VEC> &x, float d) {
+static __device__ __noinline__ void slow_div4(Vec<VEC> &q, const Vec<VEC> &x, float d) {
 #pragma unroll 1
   for (int k = 0; k < VEC; ++k) q.v[k] = x.v[k] / d;
 }
@@ -373,7 +374,7 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
   if (last && pkt) stsv<VEC>(pkt, peak);
 }
 
-__device__ __noinline__ void store_any(char *out, size_t idx, float x, int bits) {
+static __device__ __noinline__ void store_any(char *out, size_t idx, float x, int bits) {
   if (bits == 16) store_sample<16>(out, idx, x);
   else if (bits == 24) store_sample<24>(out, idx, x);
   else if (bits == 32) store_sample<32>(out, idx, x);
@@ -394,7 +395,7 @@ __device__ __noinline__ void store_any(char *out, size_t idx, float x, int bits)
 
 constexpr int kAccCache = 128;   // first entries of the limiter curve kept in shared memory (the ones right after a trigger)
 
-__device__ __noinline__ void fused_scan(const float *wm, const float *ew, float *g, int n, int &j, float &S, float &E,
+static __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float *g, int n, int &j, float &S, float &E,
                                            const float *__restrict__ acc, const float *acc_s, int ja, int jr, float thr, int lane) {
   const float a1 = acc_s[1];
   int pos = 0;
@@ -483,7 +484,7 @@ __device__ __noinline__ void fused_scan(const float *wm, const float *ew, float 
 // in 64-thread blocks (fewest instructions); pipelines whose rings are large (few streams per SM) spread a tile over
 // more, lighter threads to keep the SM's schedulers fed.
 template <int L0, int N0, int L1, int N1, int VEC, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 ? 4 : 2))) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
+static __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 ? 4 : 2))) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
   constexpr int kVec = VEC;
   constexpr int kFusedThreads = THREADS;
   typedef Vec<VEC> V4;
@@ -554,17 +555,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 
   };
   auto issue = [&](int f, int t_off) {          // one thread: bulk copies of the tile's rows into IN
     const int len = min(TL, N - t_off);
-    const uint32_t row_bytes = (uint32_t)(len * sizeof(float));
+    // int16 rows (IAMFB_IN_S16) land in the upper half of their float32 row and are widened in place after the copy
+    const int esz = a.in_s16 ? 2 : 4;
+    const uint32_t row_bytes = (uint32_t)(len * esz);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&s_bar, row_bytes * (uint32_t)(nin0 + nin1));
     const size_t sf = (size_t)s * a.n_frames + f;
-    const float *g0 = a.in[0] + sf * nin0 * N + t_off;
+    const char *g0 = reinterpret_cast<const char *>(a.in[0]) + (sf * nin0 * N + t_off) * esz;
+    char *d0 = reinterpret_cast<char *>(IN) + (a.in_s16 ? TL * 2 : 0);
 #pragma unroll 1
-    for (int r = 0; r < nin0; ++r) bulk_g2s(IN + (size_t)r * TL, g0 + (size_t)r * N, row_bytes, &s_bar);
+    for (int r = 0; r < nin0; ++r) bulk_g2s(d0 + (size_t)r * TL * 4, g0 + (size_t)r * N * esz, row_bytes, &s_bar);
     if constexpr (N1 > 0) {
-      const float *g1 = a.in[1] + sf * nin1 * N + t_off;
+      const char *g1 = reinterpret_cast<const char *>(a.in[1]) + (sf * nin1 * N + t_off) * esz;
 #pragma unroll 1
-      for (int r = 0; r < nin1; ++r) bulk_g2s(IN + (size_t)(nin0 + r) * TL, g1 + (size_t)r * N, row_bytes, &s_bar);
+      for (int r = 0; r < nin1; ++r) bulk_g2s(d0 + (size_t)(nin0 + r) * TL * 4, g1 + (size_t)r * N * esz, row_bytes, &s_bar);
     }
   };
 
@@ -615,6 +619,39 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
       const int t_end = min(t_off + TL, N);
+      if (a.in_s16) {
+        // x / 32768 (opus/IAMF_opus_decoder.c:133-135; exact): every thread reads its samples of every row, then all write
+        const int len8 = (t_end - t_off) >> 3;                       // (tiles of int16 plans are multiples of 8 samples)
+        constexpr int kW = (1024 / 8 + kFusedThreads - 1) / kFusedThreads;
+#pragma unroll 1
+        for (int r = 0; r < nin0 + nin1; ++r) {
+          float *row = IN + (size_t)r * TL;
+          const int4 *src = reinterpret_cast<const int4 *>(reinterpret_cast<const char *>(row) + TL * 2);
+          int4 v[kW];
+#pragma unroll
+          for (int u = 0; u < kW; ++u) {
+            const int i = tid + u * kFusedThreads;
+            v[u] = i < len8 ? src[i] : make_int4(0, 0, 0, 0);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int u = 0; u < kW; ++u) {
+            const int i = tid + u * kFusedThreads;
+            if (i < len8) {
+              const int w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                o[2 * k] = (float)(short)(w[k] & 0xffff) / 32768.f;
+                o[2 * k + 1] = (float)(short)(w[k] >> 16) / 32768.f;
+              }
+              reinterpret_cast<float4 *>(row)[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+              reinterpret_cast<float4 *>(row)[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+          }
+        }
+        __syncthreads();
+      }
       for (int i0 = t_off + tid * kVec; i0 < t_end; i0 += kFusedThreads * kVec) {
         const int q = i0 - t_off;                         // position inside the staged tile
         int pos = w + q;

@@ -94,7 +94,7 @@ __device__ __forceinline__ long long rs_outputs_until(const KernelPlan &p, long 
 // walks the frames for the stream-level bookkeeping (trimming, time-line placement, sample counts), every lane
 // computing the same scalars and lane 0 storing them.
 constexpr int kResolveThreads = 128;   // 4 streams per block
-__global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
+static __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid_constant__ KernelPlan plan, ResolveArgs a) {
   // programmatic dependent launch: the kernel launched after this one (k_stream) may start its blocks right away - they
   // load their limiter history and curve, which this kernel does not touch, and wait (griddepcontrol.wait) before they
   // read anything written here
@@ -661,7 +661,7 @@ __device__ __forceinline__ void render_thread(const KernelPlan &plan, const Rend
 
 // direct variant: every thread reads its samples straight from global memory (any frame size)
 template <int LAYOUT, int NREC, int VEC>
-__global__ void __launch_bounds__(128, 4) k_render(const __grid_constant__ KernelPlan plan, RenderArgs a) {
+static __global__ void __launch_bounds__(128, 4) k_render(const __grid_constant__ KernelPlan plan, RenderArgs a) {
   const int N = plan.frame_size;
   const int tile = blockIdx.x % a.tiles_per_frame;
   const int sfl = blockIdx.x / a.tiles_per_frame;
@@ -720,7 +720,7 @@ struct ResampleArgs {
   int flush;
 };
 
-__global__ void __launch_bounds__(128) k_resample(const __grid_constant__ KernelPlan plan, ResampleArgs a) {
+static __global__ void __launch_bounds__(128) k_resample(const __grid_constant__ KernelPlan plan, ResampleArgs a) {
   extern __shared__ float s_sinc[];
   const int use_direct = plan.rs_direct;
   const int tab_len = use_direct ? plan.rs_filt_len * plan.rs_den : plan.rs_filt_len * plan.rs_oversample + 8;
@@ -806,7 +806,7 @@ struct Resample2Args {
   int span;                // staged inputs per channel: inputs spanned by 128 consecutive outputs + filt_len (multiple of 4)
 };
 
-__global__ void __launch_bounds__(128) k_resample_interp(const __grid_constant__ KernelPlan plan, Resample2Args b) {
+static __global__ void __launch_bounds__(128) k_resample_interp(const __grid_constant__ KernelPlan plan, Resample2Args b) {
   extern __shared__ __align__(16) float rs_smem[];
   const ResampleArgs &a = b.r;
   const int Nf = plan.rs_filt_len, os = plan.rs_oversample;
@@ -896,7 +896,7 @@ struct WmaxArgs {
 
 constexpr int kWmTile = 1024;
 
-__global__ void __launch_bounds__(256) k_window_max(const __grid_constant__ KernelPlan plan, WmaxArgs a) {
+static __global__ void __launch_bounds__(256) k_window_max(const __grid_constant__ KernelPlan plan, WmaxArgs a) {
   __shared__ float sa[kWmTile + kLimDelay + 16];
   __shared__ float sb[kWmTile + kLimDelay + 16];
   const int s = blockIdx.y;
@@ -980,7 +980,7 @@ constexpr int kScanThreads = 512;      // 1 scanner warp + 15 mover warps
 constexpr int kScanMovers = kScanThreads / 32 - 1;
 
 template <bool ACC_SMEM>
-__global__ void __launch_bounds__(kScanThreads) k_limiter_scan(const __grid_constant__ KernelPlan plan, ScanArgs a) {
+static __global__ void __launch_bounds__(kScanThreads) k_limiter_scan(const __grid_constant__ KernelPlan plan, ScanArgs a) {
   __shared__ float2 t_in[2][32][33];   // {peak, thr/peak}
   __shared__ float t_g[2][32][33];
   __shared__ float t_max[2][32];
@@ -1180,7 +1180,7 @@ __device__ __forceinline__ void store_sample(char *out, size_t idx, float x) {
 }
 
 template <int BITS>
-__global__ void __launch_bounds__(256) k_output(const __grid_constant__ KernelPlan plan, OutputArgs a) {
+static __global__ void __launch_bounds__(256) k_output(const __grid_constant__ KernelPlan plan, OutputArgs a) {
   const int s = blockIdx.y;
   const SubmitRec sr = a.submit[s];
   const int lo = sr.sub_off[a.sub], hi = sr.sub_off[a.sub + 1];
@@ -1252,7 +1252,7 @@ struct CarryArgs {
   int use_in_len;     // 1: advance by in_len (pre-resample line), 0: by lim_len
 };
 
-__global__ void __launch_bounds__(256) k_carry(CarryArgs a) {
+static __global__ void __launch_bounds__(256) k_carry(CarryArgs a) {
   __shared__ float tmp[256];
   const int s = blockIdx.y, r = blockIdx.x;
   const int len = a.use_in_len ? a.submit[s].in_len : a.submit[s].lim_len;

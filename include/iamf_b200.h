@@ -183,8 +183,9 @@ void iamfb_plan_destroy(iamfb_plan *plan);
 int iamfb_plan_out_channels(const iamfb_plan *plan);
 /* diagnostic: which kernels serve this plan - IAMFB_PATH_MULTI (one kernel per stage), IAMFB_PATH_FUSED (k_fused: one
  * kernel per submit), IAMFB_PATH_STREAM (k_stream: pipelined per-stream kernel; trimmed / flushed streams of a submit
- * still take k_fused).  Results are bit-identical on every path. */
-enum { IAMFB_PATH_MULTI = 0, IAMFB_PATH_FUSED = 1, IAMFB_PATH_STREAM = 2 };
+ * still take k_fused), IAMFB_PATH_PIPE (k_pipe: the same pipeline with double-buffered int16 / float32 staging for
+ * channel-based, scene-based and two-element signatures).  Results are bit-identical on every path. */
+enum { IAMFB_PATH_MULTI = 0, IAMFB_PATH_FUSED = 1, IAMFB_PATH_STREAM = 2, IAMFB_PATH_PIPE = 3 };
 int iamfb_plan_kernel_path(const iamfb_plan *plan);
 /* upper bound of samples per channel one submit of n_frames can produce for one stream */
 int iamfb_plan_max_out_samples(const iamfb_plan *plan, int n_frames);

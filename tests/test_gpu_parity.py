@@ -69,15 +69,40 @@ def test_sequential_fused_kernel_still_bit_exact(monkeypatch):
     # k_stream (register-resident, pipelined) is the default for the signatures it is instantiated for; k_fused must
     # stay correct for them behind IAMFB_STREAM=0 (it also renders their trimmed / flushed streams)
     monkeypatch.setenv("IAMFB_STREAM", "0")
+    monkeypatch.setenv("IAMFB_PIPE", "0")
     compare(S.c2_714_to_B(), 9, 6, [4, 2], seed=3, expect_path=1)   # IAMFB_PATH_FUSED
     compare(S.c1_stereo(peak_db=(-3.0, 3.0)), 5, 6, [6], seed=4, expect_path=1)
+
+
+def test_pipe_kernel_serves_the_named_configurations():
+    # k_pipe (double-buffered int16 / float32 staging) serves configs 1-4: channel-based, scene-based and two-element mixes
+    for sc in (S.c1_stereo(), S.c2_714_to_B(), S.c3_toa_to_H(), S.c4_714_foa_binaural()):
+        compare(sc, 13, 8, [3, 5], seed=61, expect_path=3)             # float32 staging, one stage
+        compare(sc, 13, 8, [3, 5], seed=62, s16=True, expect_path=3)   # int16 staging, two stages
+    compare(S.edge_cases()[9], 9, 6, [2, 4], seed=63, s16=True, expect_path=3)   # FOA + 7.1.4 -> sound system H
+
+
+def test_pipe_kernel_other_output_depths():
+    import dataclasses
+    for bd in (24, 32, 0):
+        compare(dataclasses.replace(S.c2_714_to_B(peak_db=(-3.0, 3.0)), bit_depth=bd, name=f"c2_{bd}bit"), 7, 6, [2, 4], seed=64, expect_path=3)
+        compare(dataclasses.replace(S.c3_toa_to_H(), bit_depth=bd, name=f"c3_{bd}bit"), 5, 4, [4], seed=65, s16=True, expect_path=3)
+    compare(dataclasses.replace(S.c4_714_foa_binaural(), limiter=False, name="c4_nolimiter"), 7, 6, [2, 4], seed=66, expect_path=3)
+    compare(dataclasses.replace(S.c2_714_to_B(), limiter=False, bit_depth=0, name="c2_nolimiter_float"), 7, 6, [6], seed=67, s16=True, expect_path=3)
+
+
+def test_stream_kernel_still_bit_exact(monkeypatch):
+    # k_stream (single float32 stage) stays selectable behind IAMFB_PIPE=0 until k_pipe has replaced it everywhere
+    monkeypatch.setenv("IAMFB_PIPE", "0")
+    compare(S.c2_714_to_B(), 9, 6, [4, 2], seed=3, expect_path=2)
+    compare(S.c2_714_to_B(), 9, 6, [4, 2], seed=3, s16=True, expect_path=2)
 
 
 def test_stream_kernel_mixed_with_trimmed_submits():
     # first submit untrimmed (k_stream), later submits carry trimmed frames (k_fused takes those streams): the limiter
     # history and state must hand over between the two kernels
-    compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31, expect_path=2)
-    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32, expect_path=2)
+    compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31, expect_path=3)
+    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32, expect_path=3)
 
 
 def test_stream_and_fused_kernels_side_by_side_in_one_submit():
@@ -94,8 +119,8 @@ def test_stream_and_fused_kernels_side_by_side_in_one_submit():
 def test_stream_kernel_clipping_quantiser():
     # limiter threshold above full scale: samples beyond +-1.0 reach the quantiser and must saturate like
     # FLOAT2INT16 (IAMF_decoder.c:100-103) does
-    compare(S.c1_stereo(threshold_db=6.0, peak_db=(0.0, 8.0)), 9, 6, [6], seed=41, expect_path=2)
-    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42, expect_path=2)
+    compare(S.c1_stereo(threshold_db=6.0, peak_db=(0.0, 8.0)), 9, 6, [6], seed=41, expect_path=3)
+    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42, expect_path=3)
 
 
 STREAM_CASES = S.stream_kernel_cases()
@@ -104,7 +129,7 @@ STREAM_CASES = S.stream_kernel_cases()
 @pytest.mark.parametrize("sc", STREAM_CASES, ids=[s.name for s in STREAM_CASES])
 def test_stream_kernel_signatures(sc):
     # the other (layout, target) pairs k_stream is instantiated for, layered (de-mixing + recon gain) where the layout allows
-    compare(sc, 11, 9, [4, 5], seed=51, expect_path=2)   # IAMFB_PATH_STREAM
+    compare(sc, 11, 9, [4, 5], seed=51, expect_path=3)   # IAMFB_PATH_STREAM
 
 
 @pytest.mark.parametrize("thr_db", [-1.0, 0.0, -6.0, -0.1, -20.0, 3.0])
