@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 CONFIGS = {
     "c1": dict(streams=1024, frames=32, desc="simple-profile stereo -> sound system A"),
     "c2": dict(streams=1024, frames=16, desc="1024 base-profile streams, 7.1.4 scalable (2.0 -> 7.1.4) with recon-gain demixing -> sound system B (0+5+0)"),
-    "c3": dict(streams=4096, frames=4, desc="4096 streams of 3rd-order ambisonics (16 ch) -> sound system H (9+10+3)"),
+    "c3": dict(streams=4096, frames=8, desc="4096 streams of 3rd-order ambisonics (16 ch) -> sound system H (9+10+3)"),
     "c4": dict(streams=2048, frames=8, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural (as built: stereo matrices)"),
     "c5": dict(streams=2048, frames=16, desc="2048 streams/GPU, stereo 44.1->48 kHz resample, loudness -24 LKFS, limiter, 16-bit"),
 }
@@ -603,7 +603,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (used under ncu)")
     ap.add_argument("--step-ms", type=float, default=60.0, help="target duration of one step (a step = R back-to-back submits)")
     ap.add_argument("--submits-per-step", type=int, default=0, help="R; 0 = derive it from --step-ms")
-    ap.add_argument("--in-format", default="s16", choices=["f32", "s16"], help="device-resident decoded input format")
+    ap.add_argument("--in-format", default="f32", choices=["f32", "s16"], help="device-resident decoded input format")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--peak-db", default="", help="experiment: override the per-stream peak range, e.g. -40,-30")
     ap.add_argument("--peak-ref", default="rendered", choices=["rendered", "input"],

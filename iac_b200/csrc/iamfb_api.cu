@@ -1017,6 +1017,10 @@ static const PipeSigInfo k_pipe_sigs[] = {
 #undef X
 };
 const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target) {
+  const char *alt = getenv("IAMFB_PIPE_ALT");   // experiment: the alternative thread shape of a signature (ids >= 13)
+  if (alt && atoi(alt))
+    for (const PipeSigInfo &si : k_pipe_sigs)
+      if (si.id >= 13 && si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
   for (const PipeSigInfo &si : k_pipe_sigs)
     if (si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
   return nullptr;
@@ -1074,7 +1078,22 @@ static int launch_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa,
     ny += any ? 1 : 0;
   }
   const size_t smem = (((size_t)(ny * 2 + 6) * kStreamTile * 4 + 127) & ~(size_t)127) + (size_t)(s16 ? 2 : 1) * pa.stage_bytes;
-  int r = iamfb_pipe_launch(ctx, si->id, s16, kp, pa, S, smem, tm[0], tm[1]);
+  const unsigned tpf = (unsigned)(kp.frame_size / kStreamTile);
+  pa.neg_zero = -0.0f;
+  pa.tpf_magic = tpf <= 1 ? 0u : (unsigned)((0x100000000ull + tpf - 1) / tpf);
+  if ((long long)fa.n_frames * tpf >= 65536) return fail(IAMFB_ERR_BAD_ARG, "submit of %d frames is too long for k_pipe", fa.n_frames);
+  // staged-row byte offsets for this launch's input format (by IAChannel id; by ambisonics channel for a scene-based element)
+  static thread_local KernelPlan kpl;
+  kpl = kp;
+  for (int e = 0; e < kp.n_elements; ++e) {
+    ElPlan &ep = kpl.el[e];
+    if (ep.kind == IAMFB_EL_CHANNEL) {
+      for (int c = 0; c < kChCount; ++c) ep.s_row_off[c] = ep.src_row[c] >= 0 ? ep.src_row[c] * pa.row_bytes : -1;
+    } else {
+      for (int m = 0; m < ep.n_rec && m < kChCount; ++m) ep.s_row_off[m] = (int)ep.ambi_map[m] * pa.row_bytes;
+    }
+  }
+  int r = iamfb_pipe_launch(ctx, si->id, s16, kpl, pa, S, smem, tm[0], tm[1]);
   if (r) return r;
   cudaError_t e_ = cudaGetLastError();
   if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_pipe failed: %s", cudaGetErrorString(e_));

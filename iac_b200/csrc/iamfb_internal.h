@@ -82,8 +82,9 @@ struct ScopedKernelTimer {
   X(0, 7, 12, 0, 0, 1, 2, 4, 7)   X(1, 1, 2, 0, 0, 0, 2, 4, 7)   X(2, 7, 12, 0, 0, 0, 2, 4, 7)   X(3, 7, 12, 0, 0, 13, 2, 4, 7) \
   X(4, 5, 8, 0, 0, 1, 2, 4, 7)    X(5, 4, 10, 0, 0, 1, 2, 4, 7)  X(6, 2, 6, 0, 0, 1, 2, 4, 7)    X(7, 2, 6, 0, 0, 0, 2, 4, 7)   \
   X(8, 1, 2, 0, 0, 1, 2, 4, 7)    X(9, 1, 2, 0, 0, 13, 2, 4, 7)                                                                \
-  X(10, -1, 16, 0, 0, 7, 4, 2, 3) X(11, 7, 12, -1, 4, 13, 2, 4, 7) X(12, -1, 4, 7, 12, 7, 4, 2, 3)
-#define IAMFB_PIPE_GROUP_OF(id) ((id) == 0 ? 0 : ((id) == 10 ? 1 : ((id) == 12 ? 2 : ((id) == 11 ? 3 : (4 + (id) % 3)))))
+  X(10, -1, 16, 0, 0, 7, 4, 2, 3) X(11, 7, 12, -1, 4, 13, 2, 4, 7) X(12, -1, 4, 7, 12, 7, 4, 2, 3)                             \
+  X(13, 7, 12, 0, 0, 1, 4, 2, 7) X(14, -1, 16, 0, 0, 7, 2, 4, 3)
+#define IAMFB_PIPE_GROUP_OF(id) ((id) == 0 ? 0 : ((id) == 10 ? 1 : ((id) == 12 ? 2 : ((id) == 11 ? 3 : ((id) == 13 ? 4 : ((id) == 14 ? 5 : (4 + (id) % 3)))))))
 constexpr int kPipeGroups = 7;
 
 struct PipeSigInfo { int id, l0, n0, l1, n1, target, nw, vec; };

@@ -121,6 +121,8 @@ struct PipeSig {
     return n;
   }
   static constexpr int kEsz = S16 ? 2 : 4;
+  // dense (HOA) matrices go through the packed FP32 instructions; the sparse channel matrices stay scalar
+  static constexpr bool kPacked = (L0 < 0) || (N1 > 0 && L1 < 0);
   // 16-bit output of a thread's VEC instants x CO channels leaves as whole 16-byte pieces
   static constexpr bool kFast16 = (CO % 2 == 0) && ((VEC_ * CO) % 8 == 0);
   static_assert(NW_ * 32 * VEC_ >= kStreamTile, "workers must cover a tile");
@@ -141,6 +143,8 @@ struct PipeArgs {
   int n_frames;
   int row_bytes;                // bytes between the staged rows of a tile (240 instants)
   int stage_bytes;              // bytes between two input stages (frame record + rows, multiple of 128)
+  unsigned tpf_magic;           // ceil(2^32 / tiles per frame)
+  float neg_zero;               // -0.0f, opaque to the assembler (pipe_mul2)
 };
 
 template <int VEC>
@@ -204,13 +208,33 @@ __device__ __forceinline__ Vec<VEC> pipe_div(const Vec<VEC> &x, float d, float r
 
 // adds input m of element E (value v) to the running sums of the output channels it feeds (compile-time coefficients;
 // the first contribution to a channel initialises its sum)
+// Two instants at a time on the packed FP32 pipe (FFMA2 / FADD2), bit for bit the scalar multiply and add:
+//   p = fma(v, c, -0) is the correctly rounded product v * c (adding -0 changes neither the value nor the sign of a
+//   zero), then y + p is rounded separately.  The -0 comes from a kernel parameter: with a literal the assembler folds the
+//   fma back into a multiply and contracts multiply + add into one FFMA2 (it does so for f32x2 even with --fmad=false).
+// Half the issue slots of FMUL + FADD per instant; the FP32 pipe itself is as fast either way (tools/experiments/f32x2_bench.cu).
+__device__ __forceinline__ void pipe_mul2(float &p0, float &p1, float v0, float v1, float c, float nz) {
+  asm("{.reg .b64 rv, rc, rz, rt; mov.b64 rv, {%2,%3}; mov.b64 rc, {%4,%4}; mov.b64 rz, {%5,%5}; fma.rn.f32x2 rt, rv, rc, rz; mov.b64 {%0,%1}, rt;}"
+      : "=f"(p0), "=f"(p1) : "f"(v0), "f"(v1), "f"(c), "f"(nz));
+}
+__device__ __forceinline__ void pipe_mac2(float &y0, float &y1, float v0, float v1, float c, float nz) {
+  asm("{.reg .b64 rv, rc, rz, rt, ry; mov.b64 rv, {%2,%3}; mov.b64 rc, {%4,%4}; mov.b64 rz, {%5,%5}; fma.rn.f32x2 rt, rv, rc, rz; "
+      "mov.b64 ry, {%0,%1}; add.rn.f32x2 ry, ry, rt; mov.b64 {%0,%1}, ry;}"
+      : "+f"(y0), "+f"(y1) : "f"(v0), "f"(v1), "f"(c), "f"(nz));
+}
 template <class SIG, class E, int M, int OC, int VEC, int NYY>
-__device__ __forceinline__ void pipe_mat_col(Vec<VEC> (&y)[NYY], const Vec<VEC> &v) {
+__device__ __forceinline__ void pipe_mat_col(Vec<VEC> (&y)[NYY], const Vec<VEC> &v, float nz) {
   if constexpr (OC < SIG::CO) {
     if constexpr (E::nz(M, OC)) {
       constexpr int row = SIG::yrow(OC);
       const float c = __uint_as_float(E::coef(M, OC));
-      if constexpr (E::first_nz(M, OC)) {
+      if constexpr (SIG::kPacked && (VEC % 2 == 0)) {
+#pragma unroll
+        for (int k = 0; k < VEC; k += 2) {
+          if constexpr (E::first_nz(M, OC)) pipe_mul2(y[row].v[k], y[row].v[k + 1], v.v[k], v.v[k + 1], c, nz);
+          else pipe_mac2(y[row].v[k], y[row].v[k + 1], v.v[k], v.v[k + 1], c, nz);
+        }
+      } else if constexpr (E::first_nz(M, OC)) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) y[row].v[k] = c * v.v[k];
       } else {
@@ -218,7 +242,7 @@ __device__ __forceinline__ void pipe_mat_col(Vec<VEC> (&y)[NYY], const Vec<VEC> 
         for (int k = 0; k < VEC; ++k) y[row].v[k] += c * v.v[k];
       }
     }
-    pipe_mat_col<SIG, E, M, OC + 1, VEC, NYY>(y, v);
+    pipe_mat_col<SIG, E, M, OC + 1, VEC, NYY>(y, v, nz);
   }
 }
 
@@ -227,16 +251,16 @@ __device__ __forceinline__ void pipe_mat_col(Vec<VEC> (&y)[NYY], const Vec<VEC> 
 // rendered channels (time-line rows of SIG)
 template <class SIG, class E, int VEC, int NYY>
 __device__ __forceinline__ void pipe_render_channel(const KernelPlan &plan, const ElPlan &ep, const ElFrame &ef, const char *rows, int rowb,
-                                                    int i0, bool fade_w, const float *start_win, const float *stop_win, Vec<VEC> (&y)[NYY]) {
+                                                    int i0, bool fade_w, const float *start_win, const float *stop_win, Vec<VEC> (&y)[NYY], float nz) {
   constexpr int LAYOUT = E::kLayout, NREC = E::kN;
   constexpr bool S16 = SIG::kS16;
   typedef Vec<VEC> V;
-  auto ld_ch = [&](int ch) -> V {   // a transmitted IAChannel (zeros when absent), with its output gain (1.0 = none: exact)
-    const int row = ep.src_row[ch];
+  auto ld_ch = [&](int ch) -> V {   // a transmitted IAChannel (zeros when absent), with its output gain (dmx_gainup, demixer.c:421-430)
+    const int off = ep.s_row_off[ch];   // byte offset of its staged row for this launch's input format, < 0 when not transmitted
     V r = vzero<VEC>();
-    if (row >= 0) r = pipe_ld<VEC, S16>(rows + row * rowb);
-    if (ep.gain_mask) {
-      const float g = ep.f_gain[ch];
+    if (off >= 0) r = pipe_ld<VEC, S16>(rows + off);
+    if ((ep.gain_mask >> ch) & 1u) {
+      const float g = ep.gain[ch];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) r.v[k] *= g;
     }
@@ -323,7 +347,7 @@ __device__ __forceinline__ void pipe_render_channel(const KernelPlan &plan, cons
     if constexpr (stream_derivable(ch)) {
       if (stream_derived(ep, ch)) return xd[m];
     }
-    return pipe_ld<VEC, S16>(rows + ep.src_row[ch] * rowb);
+    return pipe_ld<VEC, S16>(rows + ep.s_row_off[ch]);
   };
   if (fade_w) {
     const unsigned rmask = ef.rmask;
@@ -341,7 +365,7 @@ __device__ __forceinline__ void pipe_render_channel(const KernelPlan &plan, cons
 #pragma unroll
         for (int k = 0; k < VEC; ++k) v.v[k] *= lm * st.v[k] + cm * sw.v[k];
       }
-      pipe_mat_col<SIG, E, m, 0, VEC, NYY>(y, v);
+      pipe_mat_col<SIG, E, m, 0, VEC, NYY>(y, v, nz);
     };
     stream_for<NREC>(column);
   } else {
@@ -351,7 +375,7 @@ __device__ __forceinline__ void pipe_render_channel(const KernelPlan &plan, cons
       const float cm = ef.rcur[m];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) v.v[k] *= cm;
-      pipe_mat_col<SIG, E, m, 0, VEC, NYY>(y, v);
+      pipe_mat_col<SIG, E, m, 0, VEC, NYY>(y, v, nz);
     };
     stream_for<NREC>(column);
   }
@@ -360,20 +384,20 @@ __device__ __forceinline__ void pipe_render_channel(const KernelPlan &plan, cons
 // ---- one scene-based element with a mono channel mapping (IAMF_core_decoder.c:105-116): ambisonics channel m is decoded
 // row ambi_map[m]; out = sum over m ascending (h2m_rdr.c:1103-1112), LFE slots shifted / zeroed at compile time
 template <class SIG, class E, int VEC, int NYY>
-__device__ __forceinline__ void pipe_render_scene(const ElPlan &ep, const char *rows, int rowb, Vec<VEC> (&y)[NYY]) {
+__device__ __forceinline__ void pipe_render_scene(const ElPlan &ep, const char *rows, int rowb, Vec<VEC> (&y)[NYY], float nz) {
   auto column = [&](auto m_c) {
     constexpr int m = decltype(m_c)::value;
-    const Vec<VEC> v = pipe_ld<VEC, SIG::kS16>(rows + (int)ep.ambi_map[m] * rowb);
-    pipe_mat_col<SIG, E, m, 0, VEC, NYY>(y, v);
+    const Vec<VEC> v = pipe_ld<VEC, SIG::kS16>(rows + ep.s_row_off[m]);   // (scene-based: indexed by ambisonics channel)
+    pipe_mat_col<SIG, E, m, 0, VEC, NYY>(y, v, nz);
   };
   stream_for<E::kN>(column);
 }
 
 template <class SIG, class E, int VEC, int NYY>
 __device__ __forceinline__ void pipe_render_element(const KernelPlan &plan, const ElPlan &ep, const ElFrame &ef, const char *rows, int rowb,
-                                                    int i0, bool fade_w, const float *start_win, const float *stop_win, Vec<VEC> (&y)[NYY]) {
-  if constexpr (E::kScene) pipe_render_scene<SIG, E, VEC, NYY>(ep, rows, rowb, y);
-  else pipe_render_channel<SIG, E, VEC, NYY>(plan, ep, ef, rows, rowb, i0, fade_w, start_win, stop_win, y);
+                                                    int i0, bool fade_w, const float *start_win, const float *stop_win, Vec<VEC> (&y)[NYY], float nz) {
+  if constexpr (E::kScene) pipe_render_scene<SIG, E, VEC, NYY>(ep, rows, rowb, y, nz);
+  else pipe_render_channel<SIG, E, VEC, NYY>(plan, ep, ef, rows, rowb, i0, fade_w, start_win, stop_win, y, nz);
 }
 
 // y[row of oc] += y1[row of oc] for the channels element 1 feeds (iamf_mixer_mix, IAMF_decoder.c:2719-2730: acc = 0;
@@ -466,6 +490,7 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
   typedef Vec<VEC> V;
   extern __shared__ __align__(128) float fsm[];
   __shared__ __align__(8) uint64_t s_bar[NS];
+  __shared__ __align__(8) uint64_t s_hbar;     // arrival of the previous submit's history
   __shared__ __align__(16) float s_es[2][32];  // scanner: thr / peak of the steps of a burst
   __shared__ float s_acc[kStreamAccCache];
   __shared__ int s_hot[2][NW], s_apply[2];
@@ -486,23 +511,36 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
   const int N = plan.frame_size;
   const int TPF = N / TL;
   const int T = a.n_frames * TPF;
+  const unsigned tpf_magic = a.tpf_magic;        // ceil(2^32 / TPF): tau / TPF == umulhi(tau, magic) for tau < 2^16
   const float thr = plan.lim_thr;
   const int bits = plan.bit_depth;
   const bool limiter = plan.limiter != 0;
 
-  for (int i = tid; i < kStreamAccCache; i += SIG::kThreads) s_acc[i] = (limiter && i <= plan.lim_jr + 3) ? a.acc[i] : 0.f;
-  if (limiter) {
+  // What the previous submit left - the limiter's delay line (tile -1: slot 1 of every time-line row) and the peaks of its
+  // last window (into WM's slot 1 for now) - comes in by bulk copies on their own barrier, under everything up to the first
+  // tile; under programmatic dependent launch all of this runs while k_resolve is still resolving this submit's frames
+  if (limiter && tid == 0) {
+    mbar_init(&s_hbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&s_hbar, (uint32_t)((NY + 1) * kLimDelay * sizeof(float)));
 #pragma unroll 1
     for (int c = 0; c < CO; ++c) {
       const int r = pipe_yrow_rt<SIG>(c);
-      if (r < 0) continue;
-      const float *src = a.hist_y + ((size_t)s * CO + c) * kLimDelay;
-      float *row = Y + (r * 2 + 1) * TL;
-      for (int i = tid; i < kLimDelay; i += SIG::kThreads) row[i] = src[i];
+      if (r >= 0) bulk_g2s(Y + (r * 2 + 1) * TL, a.hist_y + ((size_t)s * CO + c) * kLimDelay, (uint32_t)(kLimDelay * sizeof(float)), &s_hbar);
     }
+    bulk_g2s(WM + TL, a.hist_pk + (size_t)s * kLimDelay, (uint32_t)(kLimDelay * sizeof(float)), &s_hbar);
+  }
+  for (int i = tid; i < kStreamAccCache; i += SIG::kThreads) s_acc[i] = (limiter && i <= plan.lim_jr + 3) ? a.acc[i] : 0.f;
+  // From here on k_resolve's results are needed; the launch after this one (k_fused for the irregular streams of the submit,
+  // none of which are this kernel's) may start
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (limiter) {
+    __syncthreads();                   // the barrier's initialisation is visible to every thread
+    mbar_wait(&s_hbar, 0u);
     if (tid < 32) {
       // suffix maxima of the peaks of the tile before this submit (tile -1, slot 1): 8 instants per lane, 30 lanes
-      const float *src = a.hist_pk + (size_t)s * kLimDelay;
+      const float *src = WM + TL;
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = lane < 30 ? src[8 * lane + i] : 0.f;
@@ -522,10 +560,6 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
       }
     }
   }
-  // Everything above reads what the previous submit left (limiter history, curve): under programmatic dependent launch
-  // it runs while k_resolve is still resolving this submit's frames.  From here on its results are needed.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (a.submit[s].irregular) return;   // rendered by k_fused right after (block-uniform)
   if (tid == 0) {
 #pragma unroll
@@ -546,7 +580,7 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
     if (tid == 0) {
       int s_it = s;
       asm volatile("" : "+r"(s_it));   // (kept opaque: block-uniform pointers are rebuilt here, not carried in registers)
-      const int f = tau / TPF, t_off = (tau - f * TPF) * TL;
+      const int f = TPF == 1 ? tau : (int)__umulhi((unsigned)tau, tpf_magic), t_off = (tau - f * TPF) * TL;
       char *st = ST + (tau % NS) * a.stage_bytes;
       uint64_t *bar = &s_bar[tau % NS];
       const int sf = s_it * a.n_frames + f;
@@ -565,17 +599,19 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
 
   // tile tau (frame f, offset t_off) is in its stage: leaves the mixed samples of this thread's instants in yh and their
   // cross-channel peak in pkh
+  // (the lanes beyond the tile - 60..63 of the last warp when VEC = 4 - redo the tile's last piece instead of leaving: no
+  // divergence in front of the warp-wide scans that follow, and the compiler keeps the shuffles free of re-convergence code)
+  const int q0r = has ? q0 : TL - VEC;
   auto render = [&](int tau) {
-    if (!has) return;
-    const int f = tau / TPF, t_off = (tau - f * TPF) * TL;
+    const int f = TPF == 1 ? tau : (int)__umulhi((unsigned)tau, tpf_magic), t_off = (tau - f * TPF) * TL;
     const char *st = ST + (tau % NS) * a.stage_bytes;
     const FrameRec &fr = *reinterpret_cast<const FrameRec *>(st);
-    const char *rows = st + kRecBytes + q0 * SIG::kEsz;
-    const int i0 = t_off + q0;
+    const char *rows = st + kRecBytes + q0r * SIG::kEsz;
+    const int i0 = t_off + q0r;
     const bool fade_w = t_off + VEC * (tid & ~31) < plan.overlap;   // warp-uniform: some lane is inside the recon cross-fade
 #pragma unroll
     for (int r = 0; r < NY; ++r) yh[r] = vzero<VEC>();
-    pipe_render_element<SIG, E0, VEC, NY>(plan, ep0, fr.el[0], rows, a.row_bytes, i0, fade_w, a.start_win, a.stop_win, yh);
+    pipe_render_element<SIG, E0, VEC, NY>(plan, ep0, fr.el[0], rows, a.row_bytes, i0, fade_w, a.start_win, a.stop_win, yh, a.neg_zero);
     // element mix gain (iamf_frame_gain IAMF_decoder.c:1392): skipped when it is 1 (or not positive)
     {
       const float eg = fr.el[0].gain;
@@ -586,7 +622,7 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
 #pragma unroll
       for (int r = 0; r < NY; ++r) y1[r] = vzero<VEC>();
       pipe_render_element<SIG, E1, VEC, NY>(plan, plan.el[1], fr.el[1], rows + nin0 * a.row_bytes, a.row_bytes, i0, fade_w, a.start_win,
-                                            a.stop_win, y1);
+                                            a.stop_win, y1, a.neg_zero);
       const float eg = fr.el[1].gain;
       if (eg != 1.f && eg > 0.f) pipe_scale<SIG, E1, 0, VEC, NY>(y1, eg);
       pipe_mix<SIG, 0, VEC, NY>(yh, y1);
@@ -596,28 +632,27 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
     const bool og_on = ogain != 1.f && ogain > 0.f;
     const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
     V peak = vzero<VEC>();
+    if (og_on | loud_on | (bits == 0)) {          // (block-uniform; rarely taken)
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        // pass 0: output mix gain; 1: loudness; 2 (float output only): the sign of a zero is visible there - the reference's
+        // sums start at +0 (m2m_rdr.c:1826, iamf_mixer_mix :2719), so a zero result is +0
+        if (!(pass == 0 ? og_on : (pass == 1 ? loud_on : bits == 0))) continue;
+        const float g = pass == 0 ? ogain : plan.loud_gain;
 #pragma unroll
-    for (int r = 0; r < NY; ++r) {
-      if (og_on) {
+        for (int r = 0; r < NY; ++r)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) yh[r].v[k] *= ogain;
+          for (int k = 0; k < VEC; ++k) yh[r].v[k] = pass == 2 ? 0.f + yh[r].v[k] : yh[r].v[k] * g;
       }
-      if (loud_on) {
+    }
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) yh[r].v[k] *= plan.loud_gain;
-      }
-      if (bits == 0) {
-        // float output: the sign of a zero is visible - the reference's sums start at +0 (m2m_rdr.c:1826, iamf_mixer_mix
-        // :2719), so a zero result is +0
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) yh[r].v[k] = 0.f + yh[r].v[k];
-      }
+    for (int r = 0; r < NY; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) peak.v[k] = fmaxf(peak.v[k], fabsf(yh[r].v[k]));
-    }
-    pkh = peak;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) pkh.v[k] = has ? peak.v[k] : 0.f;
     // the peaks of the submit's last tile are the history the next submit starts from
-    if (limiter && tau == T - 1) stsv<VEC>(a.hist_pk + (size_t)s * kLimDelay + q0, peak);
+    if (limiter && tau == T - 1 && has) stsv<VEC>(a.hist_pk + (size_t)s * kLimDelay + q0, peak);
   };
 
   // Look-ahead maximum of tile t: WM[r] = max(previous tile's instants r.., this tile's instants ..r-1) (van Herk /
@@ -627,14 +662,15 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
   float pre[VEC], suf[VEC];
   auto wmax_scan = [&]() {
     float inc[VEC];                               // inclusive prefixes of the thread's instants
-    inc[0] = has ? pkh.v[0] : 0.f;
+    inc[0] = pkh.v[0];
 #pragma unroll
-    for (int k = 1; k < VEC; ++k) inc[k] = fmaxf(inc[k - 1], has ? pkh.v[k] : 0.f);
-    float sfx[VEC];                               // inclusive suffixes
-    sfx[VEC - 1] = has ? pkh.v[VEC - 1] : 0.f;
+    for (int k = 1; k < VEC; ++k) inc[k] = fmaxf(inc[k - 1], pkh.v[k]);
+    float sfx[VEC];                               // inclusive suffixes (sfx[0] is the total)
+    sfx[VEC - 1] = pkh.v[VEC - 1];
 #pragma unroll
-    for (int k = VEC - 2; k >= 0; --k) sfx[k] = fmaxf(sfx[k + 1], has ? pkh.v[k] : 0.f);
+    for (int k = VEC - 2; k >= 1; --k) sfx[k] = fmaxf(sfx[k + 1], pkh.v[k]);
     const float tot = inc[VEC - 1];
+    sfx[0] = tot;
     float up = tot, dn = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -685,20 +721,19 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
   // tile t+1 (held in yh since it was rendered) goes to: every row is read, then overwritten.
   // Without a limiter there is no delay: tile t itself is written out (from yh's slot after the store).
   auto output_and_store = [&](int t, bool do_out, bool do_store) {
-    if (!has) return;
     const int b = t & 1;
     float *yt = Y + (b ^ 1) * TL + q0;
     if (limiter) {
       const int o0 = t * TL + q0 - *(volatile int *)&s_skip;
       // limiter priming: the first 240 instants are dropped (:180-189).  A tile the limiter left alone (gain 1 throughout)
       // has already been written out by the scanner warp (s_apply == 0)
-      if (do_out && o0 >= 0 && s_apply[b] != 0) {
+      if (do_out && has && o0 >= 0 && s_apply[b] != 0) {
         int s_it = s;
         asm volatile("" : "+r"(s_it));
         pipe_emit<SIG>(yt, G + b * TL + q0, (char *)a.pcm + (size_t)s_it * a.stride_bytes, o0, VEC, bits);
       }
     }
-    if (do_store) {
+    if (do_store && has) {
 #pragma unroll
       for (int r = 0; r < NY; ++r) stsv<VEC>(yt + r * 2 * TL, yh[r]);
     }
@@ -779,19 +814,20 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
       st.lim_j = lj; st.lim_start = lS; st.lim_end = lE;
     }
   }
-  // the last 240 instants (= tile T-1) are the history of the next submit
-  if (limiter) {
+  // the last 240 instants (= tile T-1) are the history of the next submit: one bulk copy per time-line row (rows no
+  // matrix ever writes stay zero in the history, as batch_reset left them)
+  if (limiter && tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll 1
     for (int c = 0; c < CO; ++c) {
       const int r = pipe_yrow_rt<SIG>(c);
-      float *dst = a.hist_y + ((size_t)s * CO + c) * kLimDelay;
-      if (r < 0) {
-        for (int i = tid; i < kLimDelay; i += SIG::kThreads) dst[i] = 0.f;
-        continue;
-      }
-      const float *row = Y + (r * 2 + ((T + 1) & 1)) * TL;
-      for (int i = tid; i < kLimDelay; i += SIG::kThreads) dst[i] = row[i];
+      if (r < 0) continue;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.hist_y + ((size_t)s * CO + c) * kLimDelay),
+                   "r"(smem_u32(Y + (r * 2 + ((T + 1) & 1)) * TL)), "r"((uint32_t)(kLimDelay * sizeof(float)))
+                   : "memory");
     }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
 

@@ -112,8 +112,8 @@ def test_stream_and_fused_kernels_side_by_side_in_one_submit():
         P["trim_start"][1::3, 2] = 96
         P["trim_end"][2::3, 5] = 300
         P["trim_start"][2::3, 7] = 959
-    compare(S.c2_714_to_B(peak_db=(-3.0, 3.0)), 23, 9, [3, 3, 3], seed=51, expect_path=2, edit_params=trims_on_every_third_stream)
-    compare(S.c1_stereo(peak_db=(-2.0, 3.0)), 40, 8, [4, 4], seed=52, expect_path=2, edit_params=trims_on_every_third_stream)
+    compare(S.c2_714_to_B(peak_db=(-3.0, 3.0)), 23, 9, [3, 3, 3], seed=51, expect_path=3, edit_params=trims_on_every_third_stream)
+    compare(S.c1_stereo(peak_db=(-2.0, 3.0)), 40, 8, [4, 4], seed=52, expect_path=3, edit_params=trims_on_every_third_stream)
 
 
 def test_stream_kernel_clipping_quantiser():
