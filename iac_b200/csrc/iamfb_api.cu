@@ -17,6 +17,7 @@
 #include "iamfb_matrices.inc"
 #include "iamfb_stream.cuh"
 #include "iamfb_pipe.cuh"
+#include "iamfb_pipe_rs.cuh"
 
 using namespace iamfb;
 
@@ -124,6 +125,12 @@ struct iamfb_plan {
   bool pipe;
   int pipe_sig;
   bool s16_native;         // int16 submits (IAMFB_IN_S16) are staged as they are by k_pipe / k_fused
+  // k_pipe_rs (iamfb_pipe_rs.cuh): the resampling pipelines' regular streams; irregular ones and flushes: multi-kernel path
+  bool rs_pipe;
+  int rs_pipe_sig, rs_ring, rs_mirror;
+  float4 *d_interp4;       // k_pipe_rs: cubic interpolation weights per phase
+  float4 *d_tab4p;         // k_pipe_rs: the tap items with rs_tab_pad zero items on either side of every row
+  int rs_tab_row, rs_tab_pad;
 };
 
 struct iamfb_batch {
@@ -134,6 +141,9 @@ struct iamfb_batch {
   StreamState *d_state;
   FrameRec *d_frames;
   SubmitRec *d_submit;
+  int *d_gate;             // [2] "some stream of the submit is irregular", by submit parity (see ResolveArgs::gate)
+  unsigned submit_seq;
+  SubmitRec *d_submit_mk;  // resampling plans served by k_pipe_rs: the records the multi-kernel path works from (regular streams zeroed)
   float *d_tl_a, *d_tl_b, *d_pk, *d_wm, *d_gn;
   float *d_hist_y, *d_hist_pk;   // fused path: limiter delay line / peak ring carried between submits
   // staging for the host-resident path
@@ -1006,6 +1016,75 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
       }
     }
   }
+  // k_pipe_rs: one channel-based element through its channel->channel matrix, the interpolating resampler (the 44.1 -> 48 kHz
+  // kind: not the integer-ratio "direct" form), frames of a multiple of 8 samples that hold at least one limiter window
+  p->rs_pipe = false;
+  {
+    const char *penv = getenv("IAMFB_PIPE");
+    const bool pwant = !penv || atoi(penv) != 0;
+    const ElPlan &ep = kp.el[0];
+    const int co = kp.out_channels;
+    bool ok = pwant && kp.resample && !kp.rs_direct && kp.n_elements == 1 && ep.kind == IAMFB_EL_CHANNEL && ep.renderer == kRdrM2M &&
+              (kp.frame_size & 7) == 0 && kp.frame_size >= kStreamTile && kp.rs_filt_len <= 96 && kp.rs_hist >= (int)kp.rs_filt_len - 1 &&
+              (kp.rs_hist & 3) == 0 && p->d_tab4;
+    for (int m = 0; ok && m < ep.n_rec; ++m)
+      if ((ep.gain_mask >> ep.rec_ch[m]) & 1u) ok = false;
+    if (ok) {
+      const int idx = m2m_find(ep.layout, d->target);
+      if (idx < 0 || k_m2m_index[idx].m != ep.n_rec || k_m2m_index[idx].n != co || ep.n_mat_out != co) ok = false;
+      for (int oc = 0; ok && oc < co; ++oc) {
+        if (ep.out_slot[oc] != oc) ok = false;
+        for (int m = 0; ok && m < ep.n_rec; ++m) {
+          uint32_t bits;
+          memcpy(&bits, &ep.mat[oc * ep.n_rec + m], 4);
+          if (bits != k_matrix_pool[k_m2m_index[idx].off + m * co + oc]) ok = false;
+        }
+      }
+    }
+    int sig = -1;
+    const char *alt = getenv("IAMFB_PIPE_ALT");   // experiment: another thread shape of the signature
+    const int want_alt = alt ? atoi(alt) : 0;
+#define X(id, L0, N0, T, NW, VEC, MINB) if (ok && ep.layout == L0 && ep.n_rec == N0 && d->target == T && (sig < 0 || id == want_alt)) sig = id;
+    IAMFB_PIPE_RS_SIGS(X)
+#undef X
+    if (sig >= 0) {
+      // ring of pre-resample samples: the inputs 240 outputs span + the filter + one input tile rendered ahead
+      const int span = (int)((239ull * kp.rs_num) / kp.rs_den) + 2 + (int)kp.rs_filt_len + kStreamTile;
+      p->rs_ring = (span + 63) & ~63;
+      p->rs_mirror = ((int)kp.rs_filt_len + 3) & ~3;
+      // padded tap rows: the FIR walks the inputs of a thread's four outputs once, every output meeting zero taps outside its window
+      {
+        const int Nf = (int)kp.rs_filt_len, os = (int)kp.rs_oversample;
+        p->rs_tab_pad = 4 * (kp.rs_int_adv + 1);
+        p->rs_tab_row = (Nf + 2 * p->rs_tab_pad) | 1;
+        std::vector<float4> t4((size_t)os * p->rs_tab_row, make_float4(0.f, 0.f, 0.f, 0.f)), src((size_t)os * (Nf + 1));
+        int r = cudaMemcpy(src.data(), p->d_tab4, src.size() * sizeof(float4), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+        for (int o = 0; o < os && !r; ++o)
+          for (int j = 0; j < Nf; ++j) t4[(size_t)o * p->rs_tab_row + p->rs_tab_pad + j] = src[(size_t)o * (Nf + 1) + j];
+        if (r || upload(&p->d_tab4p, t4.data(), t4.size())) { iamfb_plan_destroy(p); return fail(IAMFB_ERR_CUDA, "resampler tap table upload failed"); }
+        p->rs_mirror = (Nf + 3 * (kp.rs_int_adv + 1) + 3) & ~3;
+        // cubic_coef (resample.c:246-256) per phase: frac = ((phi * oversample) % den) / den in float, interp[2] in double
+        std::vector<float4> ci(kp.rs_den);
+        for (unsigned phi = 0; phi < kp.rs_den; ++phi) {
+          volatile float frac = ((float)((phi * kp.rs_oversample) % kp.rs_den)) / kp.rs_den;
+          volatile float t0 = -0.16667f * frac, t1 = 0.16667f * frac, t2 = t1 * frac, t3 = t2 * frac;
+          volatile float i0 = t0 + t3;
+          volatile float h1 = 0.5f * frac, h2 = h1 * frac, h3 = h2 * frac;
+          volatile float i1a = frac + h2;
+          volatile float i1 = i1a - h3;
+          volatile float u0 = -0.33333f * frac, u1 = u0 + h2;
+          volatile float v1 = 0.16667f * frac, v2 = v1 * frac, v3 = v2 * frac;
+          volatile float i3 = u1 - v3;
+          const float i2 = (float)(1. - (double)i0 - (double)i1 - (double)i3);
+          ci[phi] = make_float4(i0, i1, i2, i3);
+        }
+        if (upload(&p->d_interp4, ci.data(), ci.size())) { iamfb_plan_destroy(p); return fail(IAMFB_ERR_CUDA, "resampler weight table upload failed"); }
+      }
+      p->rs_pipe = true;
+      p->rs_pipe_sig = sig;
+      for (int c = 0; c < kChCount; ++c) kp.el[0].f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
+    }
+  }
   *out = p;
   return IAMFB_OK;
 }
@@ -1063,8 +1142,7 @@ static int launch_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa,
   pa.acc = fa.acc; pa.hist_y = fa.hist_y; pa.hist_pk = fa.hist_pk; pa.pcm = fa.pcm; pa.stride_bytes = fa.stride_bytes;
   pa.n_frames = fa.n_frames;
   pa.row_bytes = kStreamTile * (s16 ? 2 : 4);
-  const int rec = (int)((sizeof(FrameRec) + 127) & ~(size_t)127);
-  pa.stage_bytes = (rec + nin * pa.row_bytes + 127) & ~127;
+  pa.stage_bytes = (nin * pa.row_bytes + 127) & ~127;
   // active output channels of the signature (rows of the time line): every channel some matrix row of an element lands on
   int ny = 0;
   for (int oc = 0; oc < kp.out_channels; ++oc) {
@@ -1101,9 +1179,59 @@ static int launch_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa,
   return IAMFB_OK;
 }
 
+static int launch_pipe_rs(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, const iamfb_io *io, int F, bool s16) {
+  const KernelPlan &kp = p->kp;
+  const int co = kp.out_channels;
+  PipeRsArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  PipeArgs &pa = ra.p;
+  pa.in[0] = io->in[0];
+  if ((((size_t)io->in[0]) & 15) != 0) return fail(IAMFB_ERR_BAD_ARG, "decoded input must be 16-byte aligned");
+  pa.frames = b->d_frames; pa.start_win = p->d_start_win; pa.stop_win = p->d_stop_win; pa.submit = b->d_submit; pa.state = b->d_state;
+  pa.acc = p->d_acc;
+  pa.hist_y = b->d_tl_b; pa.hist_pk = b->d_pk;
+  pa.pcm = io->pcm; pa.stride_bytes = iamfb_plan_out_stride_bytes(p, F);
+  pa.n_frames = F;
+  pa.row_bytes = kStreamTile * (s16 ? 2 : 4);
+  pa.stage_bytes = (kp.el[0].n_in * pa.row_bytes + 127) & ~127;
+  pa.neg_zero = -0.0f;
+  ra.hist_y_stride = b->cap_b; ra.hist_pk_stride = b->cap_b;
+  ra.hist_rs = b->d_tl_a; ra.hist_rs_stride = b->cap_a;
+  ra.tab4 = p->d_tab4p; ra.tab_row = p->rs_tab_row; ra.tab_pad = p->rs_tab_pad;
+  ra.interp4 = p->d_interp4;
+  ra.ring = p->rs_ring; ra.mirror = p->rs_mirror;
+  int ny = 0;
+  for (int oc = 0; oc < co; ++oc) {
+    bool any = false;
+    const ElPlan &ep = kp.el[0];
+    const int n = ep.out_slot[oc];
+    for (int m = 0; n >= 0 && m < ep.n_rec; ++m)
+      if (ep.mat[n * ep.n_rec + m] != 0.f) any = true;
+    ny += any ? 1 : 0;
+  }
+  const int np = (ny + 1) / 2;
+  int off = (ny * 2 + 6) * kStreamTile * 4;
+  ra.off_pkr = off; off += 2 * kStreamTile * 4;
+  ra.off_ring = off; off += np * (ra.ring + ra.mirror) * 8;
+  off = (off + 15) & ~15;
+  ra.off_tab = off; off += (int)(kp.rs_oversample * p->rs_tab_row * sizeof(float4));
+  off = (off + 127) & ~127;
+  ra.off_stage = off; off += 2 * pa.stage_bytes;
+  ra.smem_bytes = off;
+  static thread_local KernelPlan kpl;
+  kpl = kp;
+  for (int c = 0; c < kChCount; ++c) kpl.el[0].s_row_off[c] = kp.el[0].src_row[c] >= 0 ? kp.el[0].src_row[c] * pa.row_bytes : -1;
+  int r = iamfb_pipe_rs_launch(ctx, p->rs_pipe_sig, s16, kpl, ra, b->S);
+  if (r) return r;
+  cudaError_t e_ = cudaGetLastError();
+  if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_pipe_rs failed: %s", cudaGetErrorString(e_));
+  ++ctx->launches;
+  return IAMFB_OK;
+}
+
 extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
   if (!p) return;
-  cudaFree(p->d_start_win); cudaFree(p->d_stop_win); cudaFree(p->d_qf); cudaFree(p->d_sinc); cudaFree(p->d_acc); cudaFree(p->d_tab4);
+  cudaFree(p->d_start_win); cudaFree(p->d_stop_win); cudaFree(p->d_qf); cudaFree(p->d_sinc); cudaFree(p->d_acc); cudaFree(p->d_tab4); cudaFree(p->d_tab4p); cudaFree(p->d_interp4);
   delete p;
 }
 
@@ -1141,6 +1269,7 @@ extern "C" int iamfb_selftest_quotient(iamfb_ctx *ctx, float thr, uint64_t *mism
 extern "C" int iamfb_plan_out_channels(const iamfb_plan *p) { return p ? p->kp.out_channels : 0; }
 
 extern "C" int iamfb_plan_kernel_path(const iamfb_plan *p) {
+  if (p && p->rs_pipe) return IAMFB_PATH_PIPE;
   if (!p || !p->fused) return IAMFB_PATH_MULTI;
   return p->pipe ? IAMFB_PATH_PIPE : (p->stream ? IAMFB_PATH_STREAM : IAMFB_PATH_FUSED);
 }
@@ -1173,6 +1302,7 @@ extern "C" int iamfb_batch_reset(iamfb_batch *b) {
   CU(cudaSetDevice(p->ctx->device));
   std::vector<StreamState> init(b->S, p->init_state);
   CU(cudaMemcpyAsync(b->d_state, init.data(), sizeof(StreamState) * b->S, cudaMemcpyHostToDevice, p->ctx->stream));
+  if (b->d_gate) CU(cudaMemsetAsync(b->d_gate, 0, 2 * sizeof(int), p->ctx->stream));
   const int co = p->kp.out_channels;
   if (b->d_tl_a) CU(cudaMemsetAsync(b->d_tl_a, 0, sizeof(float) * (size_t)b->S * co * b->cap_a, p->ctx->stream));
   if (b->d_tl_b) CU(cudaMemsetAsync(b->d_tl_b, 0, sizeof(float) * (size_t)b->S * co * b->cap_b, p->ctx->stream));
@@ -1207,6 +1337,8 @@ extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, 
   alloc((void **)&b->d_state, sizeof(StreamState) * n_streams);
   alloc((void **)&b->d_frames, sizeof(FrameRec) * (size_t)n_streams * max_frames);
   alloc((void **)&b->d_submit, sizeof(SubmitRec) * n_streams);
+  if (p->rs_pipe) alloc((void **)&b->d_submit_mk, sizeof(SubmitRec) * n_streams);
+  if (p->rs_pipe) alloc((void **)&b->d_gate, 2 * sizeof(int));
   if (kp.resample) alloc((void **)&b->d_tl_a, sizeof(float) * (size_t)n_streams * co * b->cap_a);
   if (p->fused) {
     if (kp.limiter) {
@@ -1245,7 +1377,7 @@ static void free_staging(iamfb_batch *b) {
 
 extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
   if (!b) return;
-  cudaFree(b->d_state); cudaFree(b->d_frames); cudaFree(b->d_submit);
+  cudaFree(b->d_state); cudaFree(b->d_frames); cudaFree(b->d_submit); cudaFree(b->d_submit_mk); cudaFree(b->d_gate);
   cudaFree(b->d_tl_a); cudaFree(b->d_tl_b); cudaFree(b->d_pk); cudaFree(b->d_wm); cudaFree(b->d_gn);
   cudaFree(b->d_hist_y); cudaFree(b->d_hist_pk);
   for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_wide[e]);
@@ -1287,7 +1419,7 @@ static int n_subchunks(const KernelPlan &kp, int F, bool flush) {
 }
 
 // int16 -> float32 * 2^-15 (the codec glue's scaling, opus/IAMF_opus_decoder.c:133-135); 8 samples per thread
-__global__ void __launch_bounds__(256) k_widen_s16(const int16_t *__restrict__ src, float *__restrict__ dst, size_t n8, size_t n) {
+static __global__ void __launch_bounds__(256) k_widen_s16(const int16_t *__restrict__ src, float *__restrict__ dst, size_t n8, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n8) {
     const int4 v = reinterpret_cast<const int4 *>(src)[i];
@@ -1305,6 +1437,26 @@ __global__ void __launch_bounds__(256) k_widen_s16(const int16_t *__restrict__ s
   }
 }
 
+
+// the same for the rows of the streams a submit flags irregular only (per = elements per stream, a multiple of 8)
+static __global__ void __launch_bounds__(256) k_widen_s16_irregular(const int16_t *__restrict__ src, float *__restrict__ dst, size_t per,
+                                                                    const SubmitRec *__restrict__ submit, const int *gate) {
+  const int s = blockIdx.y;
+  if (*gate == 0 || !submit[s].irregular) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per / 8) return;
+  const int4 v = reinterpret_cast<const int4 *>(src + (size_t)s * per)[i];
+  const int w[4] = {v.x, v.y, v.z, v.w};
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[2 * k] = (float)(short)(w[k] & 0xffff) / 32768.f;
+    o[2 * k + 1] = (float)(short)(w[k] >> 16) / 32768.f;
+  }
+  float4 *d = reinterpret_cast<float4 *>(dst + (size_t)s * per);
+  d[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+  d[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+}
 
 // float32 copy of an int16 submit for the kernels that stage float32 (everything but k_pipe): per element
 // [S][F][n_in][N], allocated on first use for the batch's Fmax
@@ -1351,7 +1503,10 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   cudaStream_t st = ctx->stream;
   if (s_cnt < 0) s_cnt = b->S;
   iamfb_io wio;
-  const bool s16_in = !flush && io->in_format == IAMFB_IN_S16 && p->fused && p->s16_native && !(p->stream && !p->pipe);
+  // resampling plans: k_pipe_rs renders the regular streams, the multi-kernel path below the irregular ones
+  const bool rs_native = p->rs_pipe && !flush && !io->gain_ramp[0] && !io->out_gain_ramp;
+  const bool s16_in = !flush && io->in_format == IAMFB_IN_S16 &&
+                      ((p->fused && p->s16_native && !(p->stream && !p->pipe)) || rs_native);
   if (!flush && io->in_format == IAMFB_IN_S16 && !s16_in) {
     // kernels that stage float32 get a widened copy (x / 32768 is exact)
     int r = widen_streams(b, io, F, s_lo, s_cnt, &wio);
@@ -1372,6 +1527,9 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     a.state = b->d_state + s_lo;
     a.frames = b->d_frames + (size_t)s_lo * fF;
     a.submit = b->d_submit + s_lo;
+    a.submit_mk = rs_native ? b->d_submit_mk : nullptr;
+    a.gate = rs_native ? b->d_gate + (b->submit_seq & 1) : nullptr;
+    a.gate_next = rs_native ? b->d_gate + ((b->submit_seq + 1) & 1) : nullptr;
     a.out_counts = counts ? counts + (size_t)s_lo * (flush ? 1 : fF) : nullptr;
     a.qf_table = p->d_qf;
     a.n_streams = S;
@@ -1424,6 +1582,35 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     }
     return launch_fused(ctx, p, fa, S);
   }
+  const SubmitRec *mk_submit = b->d_submit;      // the records the kernels below work from
+  // streams per grid row: behind k_pipe_rs only the (rare) irregular streams are left - a small grid strides over the batch
+  const int gy = rs_native ? (S < 32 ? S : 32) : S;
+  const int *gate = rs_native ? b->d_gate + (b->submit_seq & 1) : nullptr;
+  if (rs_native) ++b->submit_seq;
+  if (rs_native) {
+    iamfb_io pio = *io;
+    pio.pcm = pcm;
+    int r = launch_pipe_rs(ctx, p, b, &pio, F, s16_in);
+    if (r) return r;
+    mk_submit = b->d_submit_mk;                    // regular streams: nothing left to do
+    if (s16_in) {
+      // the irregular streams' rows as float32 for k_render (regular streams are skipped)
+      r = ensure_wide(b);
+      if (r) return r;
+      wio = *io;
+      wio.in_format = IAMFB_IN_F32;
+      for (int e = 0; e < kp.n_elements; ++e) {
+        const size_t per = (size_t)F * kp.el[e].n_in * N;
+        {
+          ScopedKernelTimer tm_(ctx, "k_widen_s16");
+          k_widen_s16_irregular<<<dim3((unsigned)((per / 8 + 255) / 256), S), 256, 0, st>>>(reinterpret_cast<const int16_t *>(io->in[e]), b->d_wide[e], per, b->d_submit, gate);
+        }
+        LAUNCH_CHECK("k_widen_s16_irregular");
+        wio.in[e] = b->d_wide[e];
+      }
+      io = &wio;
+    }
+  }
   float *tl_first = kp.resample ? b->d_tl_a : b->d_tl_b;
   const int cap_first = kp.resample ? b->cap_a : b->cap_b;
   const int hist_first = kp.resample ? kp.rs_hist : kp.hist;
@@ -1460,7 +1647,10 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       ra.first = e == 0;
       ra.last = e == kp.n_elements - 1;
       ra.tiles_per_frame = tiles;
-      int blocks = S * nf * tiles;
+      ra.only_irregular = rs_native ? b->d_submit : nullptr;
+      ra.n_blocks = S * nf * tiles;
+      ra.gate = gate;
+      int blocks = rs_native ? (ra.n_blocks < 2048 ? ra.n_blocks : 2048) : ra.n_blocks;
       int r = vec4 ? launch_render<4>(ctx, p->tmpl[e], kp, ra, blocks) : launch_render<1>(ctx, p->tmpl[e], kp, ra, blocks);
       if (r) return r;
     }
@@ -1468,11 +1658,11 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   };
   auto output = [&](int sub, int max_len) -> int {
     OutputArgs o;
-    o.tl = b->d_tl_b; o.gn = kp.limiter ? b->d_gn : nullptr; o.submit = b->d_submit; o.pcm = pcm;
-    o.stride_bytes = stride; o.cap = b->cap_b; o.hist = kp.hist; o.sub = sub;
+    o.tl = b->d_tl_b; o.gn = kp.limiter ? b->d_gn : nullptr; o.submit = mk_submit; o.pcm = pcm;
+    o.stride_bytes = stride; o.cap = b->cap_b; o.hist = kp.hist; o.sub = sub; o.n_streams = S; o.gate = gate;
     {
       ScopedKernelTimer tm_(ctx, "k_output");
-      dim3 grid((max_len / 4 + 1 + 255) / 256, S);
+      dim3 grid((max_len / 4 + 1 + 255) / 256, gy);
       switch (kp.bit_depth) {
         case 16: k_output<16><<<grid, 256, 0, st>>>(kp, o); break;
         case 24: k_output<24><<<grid, 256, 0, st>>>(kp, o); break;
@@ -1492,7 +1682,7 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       a.src = b->d_tl_a;
       a.dst = b->d_tl_b;
       a.pk = b->d_pk;
-      a.submit = b->d_submit;
+      a.submit = mk_submit;
       a.state = b->d_state;
       a.sinc = p->d_sinc;
       a.cap_a = b->cap_a;
@@ -1500,7 +1690,9 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       a.hist_b = kp.hist;
       a.max_out = max_out;
       a.flush = flush ? 1 : 0;
-      dim3 grid((max_out + 127) / 128, S);
+      a.n_streams = S;
+      a.gate = gate;
+      dim3 grid((max_out + 127) / 128, gy);
       const size_t smem2 = p->d_tab4 ? sizeof(float4) * kp.rs_oversample * (kp.rs_filt_len + 1) + sizeof(float) * 2 * p->rs_span : 0;
       if (p->d_tab4 && smem2 <= 200 * 1024) {
         Resample2Args a2;
@@ -1516,7 +1708,7 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       LAUNCH_CHECK("k_resample");
       if (!flush) {
         CarryArgs c;
-        c.tl = b->d_tl_a; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_a; c.hist = kp.rs_hist; c.use_in_len = 1;
+        c.tl = b->d_tl_a; c.submit = mk_submit; c.rows = co; c.cap = b->cap_a; c.hist = kp.rs_hist; c.use_in_len = 1; c.gate = gate;
         { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
         LAUNCH_CHECK("k_carry");
       }
@@ -1530,16 +1722,16 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
       const int sub_len = n_sub == 1 ? max_out : (sub_frame[c + 1] - sub_frame[c]) * N;
       if (n_sub > 1) { int r = render(sub_frame[c], sub_frame[c + 1] - sub_frame[c]); if (r) return r; }
       WmaxArgs w;
-      w.pk = b->d_pk; w.wm = b->d_wm; w.submit = b->d_submit; w.cap = b->cap_b; w.hist = kp.hist; w.flush = flush; w.sub = c;
-      { ScopedKernelTimer tm_(ctx, "k_window_max"); k_window_max<<<dim3((sub_len + kWmTile - 1) / kWmTile, S), 256, 0, st>>>(kp, w); }
+      w.pk = b->d_pk; w.wm = b->d_wm; w.submit = mk_submit; w.cap = b->cap_b; w.hist = kp.hist; w.flush = flush; w.sub = c; w.n_streams = S; w.gate = gate;
+      { ScopedKernelTimer tm_(ctx, "k_window_max"); k_window_max<<<dim3((sub_len + kWmTile - 1) / kWmTile, gy), 256, 0, st>>>(kp, w); }
       LAUNCH_CHECK("k_window_max");
       if (n_sub > 1) {
         CU(cudaEventRecord(ctx->ev_w[c], st));
         CU(cudaStreamWaitEvent(scan_st, ctx->ev_w[c], 0));
       }
       ScanArgs sa;
-      sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = b->d_submit; sa.acc = p->d_acc;
-      sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = sub_len; sa.sub = c;
+      sa.wm = b->d_wm; sa.gn = b->d_gn; sa.state = b->d_state; sa.submit = mk_submit; sa.acc = p->d_acc;
+      sa.cap = b->cap_b; sa.hist = kp.hist; sa.n_streams = S; sa.max_len = sub_len; sa.sub = c; sa.gate = gate;
       {
         ScopedKernelTimer tm_(ctx, "k_limiter_scan", scan_st);
         if (scan_smem) k_limiter_scan<true><<<(S + 31) / 32, kScanThreads, scan_smem, scan_st>>>(kp, sa);
@@ -1565,7 +1757,7 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     }
     if (!flush) {
       CarryArgs c;
-      c.tl = b->d_tl_b; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_b; c.hist = kLimDelay; c.use_in_len = 0;
+      c.tl = b->d_tl_b; c.submit = mk_submit; c.rows = co; c.cap = b->cap_b; c.hist = kLimDelay; c.use_in_len = 0; c.gate = gate;
       { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
       LAUNCH_CHECK("k_carry");
       c.tl = b->d_pk; c.rows = 1;

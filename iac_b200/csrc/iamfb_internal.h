@@ -87,6 +87,9 @@ struct ScopedKernelTimer {
 #define IAMFB_PIPE_GROUP_OF(id) ((id) == 0 ? 0 : ((id) == 10 ? 1 : ((id) == 12 ? 2 : ((id) == 11 ? 3 : ((id) == 13 ? 4 : ((id) == 14 ? 5 : (4 + (id) % 3)))))))
 constexpr int kPipeGroups = 7;
 
+// ---- k_pipe_rs (iamfb_pipe_rs.cuh): resampling pipelines.  X(id, L0, N0, TARGET, NW, VEC, MINB): one channel-based element
+#define IAMFB_PIPE_RS_SIGS(X) X(32, 1, 2, 0, 2, 4, 4) X(33, 7, 12, 1, 2, 4, 4) X(34, 1, 2, 0, 4, 2, 7) X(35, 1, 2, 0, 4, 2, 5) X(36, 1, 2, 0, 2, 4, 6)
+
 struct PipeSigInfo { int id, l0, n0, l1, n1, target, nw, vec; };
 // signature serving (element kinds / layouts, target), or nullptr
 const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target);
@@ -95,3 +98,5 @@ namespace iamfb { struct PipeArgs; }
 // launches k_pipe<sig, s16> over S streams; returns IAMFB_OK or an error (the launch itself is checked by the caller)
 int iamfb_pipe_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelPlan &kp, const iamfb::PipeArgs &pa, int S, size_t smem,
                       const CUtensorMap &m0, const CUtensorMap &m1);
+namespace iamfb { struct PipeRsArgs; }
+int iamfb_pipe_rs_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelPlan &kp, const iamfb::PipeRsArgs &pa, int S);

@@ -68,6 +68,11 @@ struct ResolveArgs {
   StreamState *state;                 // [S]
   FrameRec *frames;                   // [S][F]
   SubmitRec *submit;                  // [S]
+  int *gate, *gate_next;              // optional: *gate |= (some stream of this submit is irregular); *gate_next = 0 (the flag
+                                      // of the submit after this one) - the multi-kernel launches behind k_pipe_rs return at once
+                                      // when the flag is clear
+  SubmitRec *submit_mk;               // optional [S]: the same records with the REGULAR streams' lengths zeroed - what the
+                                      // multi-kernel path works from when k_pipe_rs renders the regular streams of the submit
   int32_t *out_counts;                // [S][F] (device copy of what decode() returns per frame)
   const float *qf_table;              // 256 entries: (float)(q / 255.0)  (fixedp11_5.c:53-55)
   int n_streams, n_frames;
@@ -328,6 +333,17 @@ static __global__ void __launch_bounds__(kResolveThreads) k_resolve(const __grid
     gst.lim_pad = lim_pad;
     gst.lim_init = lim_init;
     a.submit[s] = sr;
+    if (a.gate) {
+      if (irregular) atomicOr(a.gate, 1);
+      if (s == 0) *a.gate_next = 0;
+    }
+    if (a.submit_mk) {
+      if (!irregular) {
+        sr.in_len = 0; sr.lim_len = 0; sr.out_len = 0; sr.out_skip = 0;
+        for (int i = 0; i <= kMaxSub; ++i) sr.sub_off[i] = 0;
+      }
+      a.submit_mk[s] = sr;
+    }
   }
 }
 
@@ -350,6 +366,9 @@ struct RenderArgs {
   int f_lo, nf;             // this launch covers frames [f_lo, f_lo + nf)
   int first, last;          // first element writes, later ones accumulate; the last applies output gain/loudness/peak
   int tiles_per_frame;
+  const SubmitRec *only_irregular;   // non-null: render only the streams flagged irregular (the others are k_pipe_rs's)
+  int n_blocks;                      // (stream, frame, tile) items of this launch
+  const int *gate;                   // non-null: return at once when *gate == 0 (no irregular stream in this submit)
 };
 
 template <int VEC>
@@ -663,14 +682,19 @@ __device__ __forceinline__ void render_thread(const KernelPlan &plan, const Rend
 template <int LAYOUT, int NREC, int VEC>
 static __global__ void __launch_bounds__(128, 4) k_render(const __grid_constant__ KernelPlan plan, RenderArgs a) {
   const int N = plan.frame_size;
-  const int tile = blockIdx.x % a.tiles_per_frame;
-  const int sfl = blockIdx.x / a.tiles_per_frame;
-  const int s = sfl / a.nf;
-  const int sf = s * a.n_frames + a.f_lo + sfl % a.nf;    // s * F + f
-  const int i0 = (tile * 128 + threadIdx.x) * VEC;         // first sample of this thread inside the frame
-  if (i0 >= N) return;
-  const float *src = a.in + (size_t)sf * plan.el[a.e].n_in * N + i0;
-  render_thread<LAYOUT, NREC, VEC, false>(plan, a, s, sf, i0, src, N);
+  if (a.gate && *a.gate == 0) return;
+  // (a launch for the irregular streams of a submit only uses a small grid and strides over the (stream, frame, tile) list)
+  for (int bx = blockIdx.x; bx < a.n_blocks; bx += gridDim.x) {
+    const int tile = bx % a.tiles_per_frame;
+    const int sfl = bx / a.tiles_per_frame;
+    const int s = sfl / a.nf;
+    const int sf = s * a.n_frames + a.f_lo + sfl % a.nf;    // s * F + f
+    const int i0 = (tile * 128 + threadIdx.x) * VEC;         // first sample of this thread inside the frame
+    if (i0 >= N) continue;
+    if (a.only_irregular && !a.only_irregular[s].irregular) continue;
+    const float *src = a.in + (size_t)sf * plan.el[a.e].n_in * N + i0;
+    render_thread<LAYOUT, NREC, VEC, false>(plan, a, s, sf, i0, src, N);
+  }
 }
 
 // ---- bulk-copy (TMA) / mbarrier helpers used by the single-kernel paths
@@ -718,6 +742,8 @@ struct ResampleArgs {
   int cap_a, cap_b, hist_b;
   int max_out;             // grid covers this many outputs per stream
   int flush;
+  int n_streams;
+  const int *gate;         // non-null: return at once when *gate == 0
 };
 
 static __global__ void __launch_bounds__(128) k_resample(const __grid_constant__ KernelPlan plan, ResampleArgs a) {
@@ -809,17 +835,19 @@ struct Resample2Args {
 static __global__ void __launch_bounds__(128) k_resample_interp(const __grid_constant__ KernelPlan plan, Resample2Args b) {
   extern __shared__ __align__(16) float rs_smem[];
   const ResampleArgs &a = b.r;
+  if (a.gate && *a.gate == 0) return;
   const int Nf = plan.rs_filt_len, os = plan.rs_oversample;
   const int trow = Nf + 1;
   float4 *s_tab = reinterpret_cast<float4 *>(rs_smem);              // [os][Nf + 1]
   float *s_x = rs_smem + (size_t)4 * os * trow;                      // [2][span]
   for (int i = threadIdx.x; i < os * trow; i += blockDim.x) s_tab[i] = b.tab4[i];
 
-  const int s = blockIdx.y;
+  // (gridDim.y may be smaller than the stream count: the launch for the irregular streams of a submit strides over them)
+  for (int s = blockIdx.y; s < a.n_streams; s += gridDim.y) {
   const int u0 = blockIdx.x * blockDim.x, u = u0 + threadIdx.x;
   const SubmitRec sr = a.submit[s];
   const int n_out = a.flush ? (sr.lim_len - (plan.limiter ? kLimDelay : 0)) : sr.lim_len;
-  if (u0 >= n_out) return;
+  if (u0 >= n_out) continue;
   const long long num = plan.rs_num, den = plan.rs_den;
   const long long in_start = a.state[s].rs_in_total - sr.in_len;     // stream position of tl_a[rs_hist]
   // first input (index into the tl_a row) needed by the block's first output
@@ -877,6 +905,8 @@ static __global__ void __launch_bounds__(128) k_resample_interp(const __grid_con
     }
   }
   if (live && a.pk) a.pk[(size_t)s * a.cap_b + a.hist_b + u] = peak;
+  __syncthreads();                                                    // the staged inputs are consumed before the next stream's arrive
+  }
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -892,6 +922,8 @@ struct WmaxArgs {
   int cap, hist;
   int flush;
   int sub;             // sub-chunk processed by this launch
+  int n_streams;
+  const int *gate;     // non-null: return at once when *gate == 0
 };
 
 constexpr int kWmTile = 1024;
@@ -899,10 +931,12 @@ constexpr int kWmTile = 1024;
 static __global__ void __launch_bounds__(256) k_window_max(const __grid_constant__ KernelPlan plan, WmaxArgs a) {
   __shared__ float sa[kWmTile + kLimDelay + 16];
   __shared__ float sb[kWmTile + kLimDelay + 16];
-  const int s = blockIdx.y;
+  if (a.gate && *a.gate == 0) return;
+  for (int s = blockIdx.y; s < a.n_streams; s += gridDim.y) {
+  __syncthreads();                                         // (the previous stream's scratch is consumed)
   const int len = a.submit[s].sub_off[a.sub + 1];          // instants [sub_off[sub], sub_off[sub+1]) of this submit
   const int k0 = a.submit[s].sub_off[a.sub] + blockIdx.x * kWmTile;
-  if (k0 >= len) return;
+  if (k0 >= len) continue;
   const float *row = a.pk + (size_t)s * a.cap + a.hist;   // row[k] = pk of instant k of this submit
   const int span = kWmTile + kLimDelay;                    // instants k0-240 .. k0+1023
   for (int i = threadIdx.x; i < span + 16; i += blockDim.x) {
@@ -942,6 +976,7 @@ static __global__ void __launch_bounds__(256) k_window_max(const __grid_constant
     int k = k0 + i;
     if (k < len) out[k] = fmaxf(fmaxf(src[i], r64[r]), fmaxf(r32[r], r16[r]));
   }
+  }
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -960,6 +995,7 @@ struct ScanArgs {
   int cap, hist, n_streams;
   int max_len;
   int sub;              // sub-chunk processed by this launch
+  const int *gate;      // non-null: return at once when *gate == 0
 };
 
 // Warp-specialised block of 16 warps per 32 streams:
@@ -988,6 +1024,7 @@ static __global__ void __launch_bounds__(kScanThreads) k_limiter_scan(const __gr
   extern __shared__ float s_acc[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s0 = blockIdx.x * 32;
+  if (a.gate && *a.gate == 0) return;
   const int ja = plan.lim_ja, jr = plan.lim_jr;
   const float thr = plan.lim_thr;
   if (ACC_SMEM)
@@ -1138,6 +1175,8 @@ struct OutputArgs {
   size_t stride_bytes; // per stream
   int cap, hist;
   int sub;             // sub-chunk processed by this launch
+  int n_streams;
+  const int *gate;     // non-null: return at once when *gate == 0
 };
 
 __device__ __forceinline__ int quant16(float x) {
@@ -1180,8 +1219,14 @@ __device__ __forceinline__ void store_sample(char *out, size_t idx, float x) {
 }
 
 template <int BITS>
+__device__ __forceinline__ void k_output_stream(const KernelPlan &plan, const OutputArgs &a, int s);
+template <int BITS>
 static __global__ void __launch_bounds__(256) k_output(const __grid_constant__ KernelPlan plan, OutputArgs a) {
-  const int s = blockIdx.y;
+  if (a.gate && *a.gate == 0) return;
+  for (int s = blockIdx.y; s < a.n_streams; s += gridDim.y) k_output_stream<BITS>(plan, a, s);
+}
+template <int BITS>
+__device__ __forceinline__ void k_output_stream(const KernelPlan &plan, const OutputArgs &a, int s) {
   const SubmitRec sr = a.submit[s];
   const int lo = sr.sub_off[a.sub], hi = sr.sub_off[a.sub + 1];
   // instants are grouped in fours aligned on the time line (so that the float4 loads are aligned)
@@ -1250,11 +1295,13 @@ struct CarryArgs {
   const SubmitRec *submit;
   int rows, cap, hist;
   int use_in_len;     // 1: advance by in_len (pre-resample line), 0: by lim_len
+  const int *gate;    // non-null: return at once when *gate == 0
 };
 
 static __global__ void __launch_bounds__(256) k_carry(CarryArgs a) {
   __shared__ float tmp[256];
   const int s = blockIdx.y, r = blockIdx.x;
+  if (a.gate && *a.gate == 0) return;
   const int len = a.use_in_len ? a.submit[s].in_len : a.submit[s].lim_len;
   if (len == 0) return;
   float *row = a.tl + ((size_t)s * a.rows + r) * a.cap;

@@ -142,7 +142,7 @@ struct PipeArgs {
   size_t stride_bytes;
   int n_frames;
   int row_bytes;                // bytes between the staged rows of a tile (240 instants)
-  int stage_bytes;              // bytes between two input stages (frame record + rows, multiple of 128)
+  int stage_bytes;              // bytes between two input stages (multiple of 128)
   unsigned tpf_magic;           // ceil(2^32 / tiles per frame)
   float neg_zero;               // -0.0f, opaque to the assembler (pipe_mul2)
 };
@@ -491,6 +491,7 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
   extern __shared__ __align__(128) float fsm[];
   __shared__ __align__(8) uint64_t s_bar[NS];
   __shared__ __align__(8) uint64_t s_hbar;     // arrival of the previous submit's history
+  __shared__ __align__(16) FrameRec s_fr[2];   // resolved parameters of the frames being rendered, by frame parity
   __shared__ __align__(16) float s_es[2][32];  // scanner: thr / peak of the steps of a burst
   __shared__ float s_acc[kStreamAccCache];
   __shared__ int s_hot[2][NW], s_apply[2];
@@ -502,9 +503,8 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
   float *WM = Y + NY * 2 * TL;       // [2][TL]      look-ahead maximum, tile t in slot t & 1
   float *G = WM + 2 * TL;            // [2][TL]      gains
   float *SA = G + 2 * TL;            // [2][TL]      suffix maxima of the peaks of tile t (instants r.. of the tile)
-  // input stages (128-byte aligned): [frame record | decoded rows of a tile: nin0 + nin1 rows of TL instants]
+  // input stages (128-byte aligned): the decoded rows of a tile, nin0 + nin1 rows of TL instants
   char *ST = reinterpret_cast<char *>(fsm) + (((NY * 2 + 6) * TL * 4 + 127) & ~127);
-  constexpr int kRecBytes = (int)((sizeof(FrameRec) + 127) & ~(size_t)127);
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   const bool worker = tid < WN;
@@ -585,10 +585,12 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
       uint64_t *bar = &s_bar[tau % NS];
       const int sf = s_it * a.n_frames + f;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, (uint32_t)(a.row_bytes * (nin0 + nin1) + sizeof(FrameRec)));
-      bulk_g2s(st, a.frames + sf, (uint32_t)sizeof(FrameRec), bar);
-      tensor_g2s_2d(st + kRecBytes, &map0, t_off, sf * nin0, bar);
-      if constexpr (SIG::kTwo) tensor_g2s_2d(st + kRecBytes + nin0 * a.row_bytes, &map1, t_off, sf * nin1, bar);
+      // the frame's record travels with the frame's first tile, into the slot of the frame's parity (the frame before last,
+      // whose slot it takes, has been rendered completely by the time any tile of this frame is issued)
+      mbar_expect_tx(bar, (uint32_t)(a.row_bytes * (nin0 + nin1) + (t_off == 0 ? sizeof(FrameRec) : 0)));
+      if (t_off == 0) bulk_g2s(&s_fr[f & 1], a.frames + sf, (uint32_t)sizeof(FrameRec), bar);
+      tensor_g2s_2d(st, &map0, t_off, sf * nin0, bar);
+      if constexpr (SIG::kTwo) tensor_g2s_2d(st + nin0 * a.row_bytes, &map1, t_off, sf * nin1, bar);
     }
   };
 
@@ -605,8 +607,8 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
   auto render = [&](int tau) {
     const int f = TPF == 1 ? tau : (int)__umulhi((unsigned)tau, tpf_magic), t_off = (tau - f * TPF) * TL;
     const char *st = ST + (tau % NS) * a.stage_bytes;
-    const FrameRec &fr = *reinterpret_cast<const FrameRec *>(st);
-    const char *rows = st + kRecBytes + q0r * SIG::kEsz;
+    const FrameRec &fr = s_fr[f & 1];
+    const char *rows = st + q0r * SIG::kEsz;
     const int i0 = t_off + q0r;
     const bool fade_w = t_off + VEC * (tid & ~31) < plan.overlap;   // warp-uniform: some lane is inside the recon cross-fade
 #pragma unroll

@@ -91,6 +91,33 @@ def test_pipe_kernel_other_output_depths():
     compare(dataclasses.replace(S.c2_714_to_B(), limiter=False, bit_depth=0, name="c2_nolimiter_float"), 7, 6, [6], seed=67, s16=True, expect_path=3)
 
 
+def test_pipe_rs_kernel_resampling_pipelines():
+    # k_pipe_rs: render -> pre-resample ring -> FIR -> limiter on chip, for the regular streams of a resampling plan
+    import dataclasses
+    c5 = S.c5_resample()
+    compare(c5, 9, 7, [7], seed=71, expect_path=3)
+    compare(c5, 21, 9, [1, 3, 5], seed=72, s16=True, expect_path=3)
+    compare(S.c5_resample(peak_db=(-2.0, 4.0)), 6, 12, [5, 7], seed=73, expect_path=3)                      # limiter busy
+    down = S.Scenario("stereo_48k_to_44k1", [S.El("channel", S.LY_STEREO, [S.L2, S.R2])], S.TGT_A, in_rate=48000, out_rate=44100,
+                      loudness_gain=0.7, peak_db=(-3.0, 3.0))
+    compare(down, 7, 9, [2, 3, 4], seed=74, expect_path=3)
+    compare(dataclasses.replace(down, bit_depth=24, limiter=False, name="stereo_48k_to_44k1_24bit_nolimiter"), 5, 6, [6], seed=75, s16=True, expect_path=3)
+    c2rs = dataclasses.replace(S.c2_714_to_B(peak_db=(-3.0, 3.0)), in_rate=48000, out_rate=44100, name="c2_714_to_B_44k1")
+    compare(c2rs, 5, 6, [2, 4], seed=76, expect_path=3)
+    c2up = dataclasses.replace(S.c2_714_to_B(), frame_size=1024, in_rate=44100, out_rate=48000, name="c2_714_to_B_44k1_to_48k")
+    compare(c2up, 5, 5, [1, 4], seed=77, s16=True, expect_path=3)
+
+
+def test_pipe_rs_mixed_with_trimmed_streams():
+    # trims on SOME streams: those take the multi-kernel path inside the same submit, the others k_pipe_rs; and a stream
+    # changes path between submits (both keep their histories in the heads of the batch's time lines)
+    def trims_on_every_third_stream(P):
+        P["trim_start"][1::3, 2] = 96
+        P["trim_end"][2::3, 5] = 300
+    compare(S.c5_resample(peak_db=(-3.0, 3.0)), 20, 9, [3, 3, 3], seed=78, expect_path=3, edit_params=trims_on_every_third_stream)
+    compare(S.c5_resample(peak_db=(-3.0, 3.0)), 20, 9, [3, 3, 3], seed=79, s16=True, expect_path=3, edit_params=trims_on_every_third_stream)
+
+
 def test_stream_kernel_still_bit_exact(monkeypatch):
     # k_stream (single float32 stage) stays selectable behind IAMFB_PIPE=0 until k_pipe has replaced it everywhere
     monkeypatch.setenv("IAMFB_PIPE", "0")
