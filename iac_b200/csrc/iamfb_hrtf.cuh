@@ -1,0 +1,253 @@
+// iamfb_hrtf.cuh - binaural (HRTF) rendering of an audio element on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+// What it replaces: IAMF_element_renderer_render_M2B (m2b_rdr.c:103-121: one HRIR pair per loudspeaker channel, BEAR) and
+// IAMF_element_renderer_render_H2B (h2b_rdr.c:109-131: one HRIR pair per ambisonics channel, Resonance Audio) - both hand
+// the planar frame [C][N] to a closed library and get [2][N] back, the filter state living inside the library.  Here:
+//
+//     out[ear][t] = sum_c sum_{k=0..255} h[c][ear][k] * x[c][t - k]                  (256-tap FIR per channel and ear)
+//
+// as EXACT integer arithmetic: the HRIR set is Q15 int16 (tools/gen_hrir.py), the decoded samples are fixed point too
+// (int16 as the codecs produce it, or float32 rounded to Q20), both are split into 8-bit limbs, every limb pair is one
+// int8 tensor-core product accumulated in int32 (TMEM), and the epilogue recombines the limb classes in int64 and rounds
+// ONCE to float32.  The result does not depend on the order of accumulation, so the CPU oracle (oracle/oracle_hrtf.c) is
+// matched bit for bit.
+//
+// The contraction.  Time is cut into blocks of 64 instants.  Output block b of a stream needs input blocks b-4 .. b:
+//     out[64 b + i] = sum_{q=0..4} sum_{j=0..63} h[64 q + i - j] * x[64 (b - q) + j]            (h = 0 outside 0..255)
+// i.e. D[(i, ear)][b] += A_q[(i, ear)][j] * X[j][b - q]: M = 128 rows (64 instants x 2 ears), N = the blocks of a tile
+// (<= 128 consecutive blocks of one stream), K = 64 per (q, channel).  Neither operand is ever materialised:
+//   * A_q is Toeplitz.  With the instants of a block stored in REVERSE order (j' = 63 - j) an 8 x 16 core matrix of the
+//     K-major no-swizzle layout holds G_ear[base + (r >> 1) + u] (r = row: instant pair r >> 1, ear r & 1; u = byte) with
+//     base = 64 q + 4 i4 + 16 kc: it depends on the SUM of the row group, the K core and q only.  One table of 96 core
+//     matrices (12 KB) per (channel, limb) therefore serves all five q, all sixteen row groups and all four K cores: the
+//     shared-memory descriptor just starts at core 16 q + 8 kk and strides 1 core per row group, 4 cores per K core
+//     (the core matrices of an operand overlap - the descriptor is an address generator, nothing more).
+//   * X for shift q is the same staged rows, started 4 - q rows further down: the blocks b0-4 .. b0+NB-1 of a channel are
+//     staged once ([limb][kc][NB + 4 rows][16 bytes]) and serve all five q.
+// Per channel a tile costs 20 * (limb pairs) MMAs of 128 x NB x 32 and moves 12 KB * 2 (tables, L2-resident) + the
+// channel's samples once.
+//
+// Kernel shape (persistent, one CTA per SM, 192 threads): warp 0 = producer (bulk copies into a 4-stage ring, one stage
+// per channel), warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> int64 -> float32 ->
+// the element's binaural frame [S][F][2][N]).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace iamfb {
+
+constexpr int kHrTaps = 256;
+constexpr int kHrBlock = 64;                 // instants per time block (= K of one (q, channel) chunk)
+constexpr int kHrShifts = kHrTaps / kHrBlock + 1;   // input blocks an output block depends on
+constexpr int kHrHist = kHrTaps;             // history instants kept in front of a stream's plane (4 blocks)
+constexpr int kHrCores = 96;                 // core matrices of one (channel, limb) Toeplitz table
+constexpr int kHrTabBytes = kHrCores * 128;  // 12288
+constexpr int kHrHLimbs = 2;                 // Q15 int16 taps: low limb unsigned, high limb signed
+constexpr int kHrMaxXLimbs = 3;
+constexpr int kHrStages = 4;
+constexpr int kHrThreads = 192;
+constexpr int kHrMaxNB = 128;                // blocks per tile (N of the MMA)
+
+// bytes of one pipeline stage for tiles of nb blocks and nl sample limbs
+__host__ __device__ constexpr int hrtf_x_bytes(int nb, int nl) { return nl * 4 * (nb + 4) * 16; }
+__host__ __device__ constexpr int hrtf_stage_bytes(int nb, int nl) { return kHrHLimbs * kHrTabBytes + ((hrtf_x_bytes(nb, nl) + 127) & ~127); }
+
+struct HrtfGemmArgs {
+  const uint8_t *tab;        // [C][2 limbs][96 cores][128]            Toeplitz core tables of the element's channels
+  const uint8_t *planes;     // [S][C][NL][4 kc][NBP][16]              limb planes of the element (k_hrtf_prep)
+  float *out;                // [S][F][2][N] float32                   the element's binaural frames
+  const int *n_present;      // [S]   frames present in this submit
+  const short *frame_of_slot;// [S][F] frame index of the k-th present frame
+  int S, C, NL;              // streams (of this launch), channels, sample limbs
+  int NB, NT, NBP;           // blocks per tile, tiles per stream, blocks per plane row (4 + NT * NB)
+  int F, N;                  // frames per submit, frame size
+  int x_shift;               // out = sum * 2^-(x_shift + 15)
+};
+
+namespace hr {
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n)); }
+__device__ __forceinline__ void bar_expect(uint64_t *b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint64_t *b, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nHR_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra HR_DONE;\nbra HR_WAIT;\nHR_DONE:\n}\n" ::"r"(s32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes),
+               "r"(s32(b))
+               : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes); lbo = bytes between the two K cores of an
+// MMA, sbo = bytes between 8-row groups (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor for kind::i8: int32 accumulate, K-major A and B, M = 128
+__device__ __forceinline__ uint32_t instr_desc_i8(bool a_signed, bool b_signed, int n) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *b) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+}  // namespace hr
+
+// dynamic shared memory: [stages][table 2 x 12288 | X limbs]; static: barriers + the TMEM base address
+static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGemmArgs a) {
+  extern __shared__ __align__(128) uint8_t hr_smem[];
+  __shared__ __align__(8) uint64_t s_full[kHrStages], s_empty[kHrStages], s_tfull, s_tempty;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NB = a.NB, NL = a.NL, C = a.C;
+  const int stage_bytes = hrtf_stage_bytes(NB, NL);
+  const int xrow = (NB + 4) * 16;                 // bytes of one (limb, kc) row group of a stage
+  const int n_tiles = a.S * a.NT;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kHrStages; ++i) { hr::bar_init(&s_full[i], 1); hr::bar_init(&s_empty[i], 1); }
+    hr::bar_init(&s_tfull, 1);
+    hr::bar_init(&s_tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hr::s32(&s_tmem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== producer: one stage per (tile, channel): the channel's two Toeplitz tables + its sample limbs for blocks b0-4 ..
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s = tile / a.NT, b0 = (tile - s * a.NT) * NB;
+        if (a.n_present[s] * a.N <= b0 * kHrBlock) continue;      // nothing of this stream reaches the tile
+        for (int c = 0; c < C; ++c, ++it) {
+          const int st = it % kHrStages;
+          hr::bar_wait(&s_empty[st], ((it / kHrStages) & 1u) ^ 1u);
+          uint8_t *dst = hr_smem + (size_t)st * stage_bytes;
+          hr::bar_expect(&s_full[st], (uint32_t)(kHrHLimbs * kHrTabBytes + NL * 4 * xrow));
+          hr::bulk_load(dst, a.tab + (size_t)c * kHrHLimbs * kHrTabBytes, kHrHLimbs * kHrTabBytes, &s_full[st]);
+          const uint8_t *src = a.planes + ((size_t)(s * C + c) * NL * 4) * a.NBP * 16 + (size_t)b0 * 16;
+          uint8_t *xd = dst + kHrHLimbs * kHrTabBytes;
+          for (int r = 0; r < NL * 4; ++r) hr::bulk_load(xd + r * xrow, src + (size_t)r * a.NBP * 16, (uint32_t)xrow, &s_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s = tile / a.NT, b0 = (tile - s * a.NT) * NB;
+        if (a.n_present[s] * a.N <= b0 * kHrBlock) continue;
+        hr::bar_wait(&s_tempty, (tl & 1u) ^ 1u);                    // the epilogue has drained the accumulators
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t touched = 0;                                      // limb classes that hold a partial sum already
+        for (int c = 0; c < C; ++c, ++it) {
+          const int st = it % kHrStages;
+          hr::bar_wait(&s_full[st], (it / kHrStages) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tab = hr::s32(hr_smem + (size_t)st * stage_bytes);
+          const uint32_t xs = tab + kHrHLimbs * kHrTabBytes;
+          for (int q = 0; q < kHrShifts; ++q)
+            for (int kk = 0; kk < 2; ++kk)
+              for (int xl = 0; xl < NL; ++xl) {
+                const uint64_t bd = hr::smem_desc(xs + (uint32_t)((xl * 4 + 2 * kk) * xrow + (4 - q) * 16), (uint32_t)xrow, 128u);
+                for (int hl = 0; hl < kHrHLimbs; ++hl) {
+                  const uint64_t ad = hr::smem_desc(tab + (uint32_t)(hl * kHrTabBytes + (16 * q + 8 * kk) * 128), 512u, 128u);
+                  const int cls = xl + hl;
+                  hr::mma_i8(tmem + (uint32_t)(cls * NB), ad, bd, hr::instr_desc_i8(hl == kHrHLimbs - 1, xl == NL - 1, NB), (touched >> cls) & 1u);
+                  touched |= 1u << cls;
+                }
+              }
+          hr::mma_commit(&s_empty[st]);                            // the stage is free once these MMAs have read it
+        }
+        hr::mma_commit(&s_tfull);                                  // accumulators complete
+        ++tl;
+      }
+    }
+  } else {
+    // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. : row R = 2 i + ear of every column (= block) of the tile
+    const int quarter = warp & 3;
+    const int R = quarter * 32 + lane, i = R >> 1, ear = R & 1;
+    const float scale = __int_as_float((127 - (a.x_shift + 15)) << 23);   // 2^-(x_shift + 15)
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int s = tile / a.NT, b0 = (tile - s * a.NT) * NB;
+      const int len = a.n_present[s] * a.N;                         // instants of this stream in the submit
+      if (len <= b0 * kHrBlock) continue;
+      hr::bar_wait(&s_tfull, tl & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // running (present-frame slot, offset inside it) of this row's instant in column n
+      int tau = b0 * kHrBlock + i;
+      int slot = tau / a.N, rem = tau - slot * a.N;
+      int f = (tau < len) ? a.frame_of_slot[(size_t)s * a.F + slot] : 0;
+      const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+      for (int n0 = 0; n0 < NB; n0 += 16) {
+        int32_t d[kHrMaxXLimbs + 1][16];
+#pragma unroll
+        for (int cls = 0; cls < kHrMaxXLimbs + 1; ++cls)
+          if (cls <= NL) hr::tmem_ld16(lane_base + (uint32_t)(cls * NB + n0), d[cls]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          long long v = (long long)d[0][k] + ((long long)d[1][k] << 8) + ((long long)d[2][k] << 16);
+          if (NL == 3) v += (long long)d[3][k] << 24;
+          if (tau < len) a.out[(((size_t)s * a.F + f) * 2 + ear) * a.N + rem] = (float)v * scale;
+          tau += kHrBlock;
+          rem += kHrBlock;
+          if (rem >= a.N) {
+            rem -= a.N;
+            ++slot;
+            if (tau < len) f = a.frame_of_slot[(size_t)s * a.F + slot];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) hr::bar_arrive(&s_tempty);
+      ++tl;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+// ---- host: Toeplitz core tables of one channel.  taps = [2 ears][256] Q15; dst = [2 limbs][96 cores][8 rows][16 bytes]
+inline void hrtf_build_table(const int16_t *taps, uint8_t *dst) {
+  for (int hl = 0; hl < kHrHLimbs; ++hl)
+    for (int cb = 0; cb < kHrCores; ++cb)
+      for (int r = 0; r < 8; ++r)
+        for (int u = 0; u < 16; ++u) {
+          const int m = 4 * cb + (r >> 1) + u - (kHrBlock - 1);     // tap index
+          const int ear = r & 1;
+          const int v = (m >= 0 && m < kHrTaps) ? taps[ear * kHrTaps + m] : 0;
+          dst[((hl * kHrCores + cb) * 8 + r) * 16 + u] = (uint8_t)(hl == 0 ? (v & 255) : ((v >> 8) & 255));
+        }
+}
+
+}  // namespace iamfb
