@@ -23,7 +23,7 @@ class ElementDesc(C.Structure):
                 ("first_layer_layout", C.c_int32), ("selected_layer", C.c_int32), ("recon_present", C.c_int32),
                 ("use_dmr", C.c_int32), ("dmr_out_layout", C.c_int32),
                 ("ambi_mode", C.c_int32), ("ambi_channels", C.c_int32), ("ambi_map", C.c_uint8 * MAXS),
-                ("ambi_cols", C.c_int32), ("ambi_matrix", C.c_float * (MAXS * MAXS))]
+                ("ambi_cols", C.c_int32), ("ambi_matrix", C.c_float * (MAXS * MAXS)), ("binaural_hrtf", C.c_int32)]
 
 
 class PlanDesc(C.Structure):
@@ -116,6 +116,8 @@ def lib():
     L.iamfb_ctx_set_timing.argtypes = [vp, C.c_int]
     L.iamfb_ctx_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                        C.POINTER(C.c_uint64)]
+    L.iamfb_get_hrir.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int16)]
+    L.iamfb_hrir_taps.restype = C.c_int
     L.iamfb_target_channels.argtypes = [C.c_int]
     L.iamfb_layout_channels.argtypes = [C.c_int, C.POINTER(C.c_int32)]
     L.iamfb_get_m2m_matrix.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -145,6 +147,22 @@ def get_h2m_matrix(order, target):
     if lib().iamfb_get_h2m_matrix(order, target, C.byref(m), C.byref(n), C.byref(l1), C.byref(l2), buf) != 0:
         return None
     return np.array(buf[: m.value * n.value], np.float32).reshape(n.value, m.value), l1.value, l2.value
+
+
+def layout_channels(layout):
+    """IAChannel ids of a layout in rendering order (IAMF_utils.c:117-133)"""
+    chs = (C.c_int32 * MAXL)()
+    n = lib().iamfb_layout_channels(layout, chs)
+    return [int(chs[i]) for i in range(n)]
+
+
+def get_hrir(kind, index):
+    """[2 ears][taps] Q15 int16 of IAChannel `index` (kind 0) or ambisonics channel `index` (kind 1)"""
+    n = lib().iamfb_hrir_taps()
+    buf = (C.c_int16 * (2 * n))()
+    if lib().iamfb_get_hrir(kind, index, buf) != 0:
+        return None
+    return np.array(buf[:], np.int16).reshape(2, n)
 
 
 def channel_element(layout, chs_in, out_gain=(), demix=None, first_layer_layout=None, selected_layer=0,

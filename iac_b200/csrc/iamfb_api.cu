@@ -131,6 +131,10 @@ struct iamfb_plan {
   float4 *d_interp4;       // k_pipe_rs: cubic interpolation weights per phase
   float4 *d_tab4p;         // k_pipe_rs: the tap items with rs_tab_pad zero items on either side of every row
   int rs_tab_row, rs_tab_pad;
+  // binaural HRTF front end (iamfb_hrtf.cu): non-null when an element is rendered through it; kp / desc then describe the
+  // pipeline BEHIND it (those elements as 2-channel pass-through elements fed with float32 binaural frames)
+  iamfb_hrtf_front *hrtf;
+  int in_rows[kMaxEl];     // rows per frame of the CALLER's input of every element
 };
 
 struct iamfb_batch {
@@ -156,6 +160,7 @@ struct iamfb_batch {
   char *d_pcm;
   int32_t *d_counts;
   size_t stage_frames;     // frames the staging buffers are sized for (0 = not allocated)
+  iamfb_hrtf_batch *hrtf;  // per-stream buffers of the binaural HRTF front end
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -641,6 +646,7 @@ static int fused_variant(const int *tmpl, int n_elements) {
   if (n_elements == 1) return tmpl[0];
   if (n_elements == 2 && tmpl[0] == 7 && tmpl[1] == 11) return 100;
   if (n_elements == 2 && tmpl[0] == 11 && tmpl[1] == 7) return 101;
+  if (n_elements == 2 && tmpl[0] == 1 && tmpl[1] == 1) return 102;    // two binaural frames behind the HRTF front end
   return -1;
 }
 
@@ -673,7 +679,7 @@ static int launch_fused(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa
     FCASE(0, 0, 1, 0, 0) FCASE(1, 1, 2, 0, 0) FCASE(2, 2, 6, 0, 0) FCASE(3, 3, 8, 0, 0) FCASE(4, 4, 10, 0, 0)
     FCASE(5, 5, 8, 0, 0) FCASE(6, 6, 10, 0, 0) FCASE(7, 7, 12, 0, 0) FCASE(8, 8, 6, 0, 0)
     FCASE3(10, -1, 1, 0, 0) FCASE3(11, -1, 4, 0, 0) FCASE3(12, -1, 9, 0, 0) FCASE3(13, -1, 16, 0, 0)
-    FCASE(100, 7, 12, -1, 4) FCASE(101, -1, 4, 7, 12)
+    FCASE(100, 7, 12, -1, 4) FCASE(101, -1, 4, 7, 12) FCASE(102, 1, 2, 1, 2)
     default: return fail(IAMFB_ERR_INTERNAL, "no fused kernel variant");
   }
 #undef FCASE3
@@ -807,11 +813,25 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
     return fail(IAMFB_ERR_BAD_ARG, "bit_depth %d", d->bit_depth);
   if (d->in_rate <= 0 || d->out_rate <= 0) return fail(IAMFB_ERR_BAD_ARG, "rates %d -> %d", d->in_rate, d->out_rate);
   CU(cudaSetDevice(ctx->device));
+  for (int e = 0; e < d->n_elements; ++e)
+    if (d->el[e].n_in < 1 || d->el[e].n_in > IAMFB_MAX_SCENE_CH) return fail(IAMFB_ERR_BAD_ARG, "element %d: n_in %d", e, d->el[e].n_in);
+
+  // elements rendered binaurally through the HRTF front end become 2-channel pass-through elements of the plan built below
+  iamfb_plan_desc back = *d;
+  iamfb_hrtf_front *hf = nullptr;
+  {
+    int r = iamfb_hrtf_front_create(d, &back, &hf);
+    if (r) return r;
+  }
+  const iamfb_plan_desc *orig = d;
+  d = &back;
 
   iamfb_plan *p = new iamfb_plan();
   memset(p, 0, sizeof(*p));
   p->ctx = ctx;
   p->desc = *d;
+  p->hrtf = hf;
+  for (int e = 0; e < d->n_elements; ++e) p->in_rows[e] = orig->el[e].n_in;
   KernelPlan &kp = p->kp;
   kp.frame_size = d->frame_size;
   kp.n_elements = d->n_elements;
@@ -1005,7 +1025,8 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
           if (si) {
             // the second element's rows follow the first's inside a stage: tensor copies land on 128-byte boundaries
             const int n0 = kp.el[0].n_in;
-            if (kp.n_elements > 1 && (((n0 * kStreamTile * 2) & 127) != 0)) si = nullptr;
+            // (behind the HRTF front end the rows are always float32)
+            if (kp.n_elements > 1 && (((n0 * kStreamTile * (p->hrtf ? 4 : 2)) & 127) != 0)) si = nullptr;
           }
           if (si) {
             p->pipe = true;
@@ -1232,6 +1253,7 @@ static int launch_pipe_rs(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, c
 extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
   if (!p) return;
   cudaFree(p->d_start_win); cudaFree(p->d_stop_win); cudaFree(p->d_qf); cudaFree(p->d_sinc); cudaFree(p->d_acc); cudaFree(p->d_tab4); cudaFree(p->d_tab4p); cudaFree(p->d_interp4);
+  iamfb_hrtf_front_destroy(p->hrtf);
   delete p;
 }
 
@@ -1315,6 +1337,10 @@ extern "C" int iamfb_batch_reset(iamfb_batch *b) {
     CU(cudaMemsetAsync(b->d_wm, 0, sizeof(float) * (size_t)b->S * b->cap_b, p->ctx->stream));
     CU(cudaMemsetAsync(b->d_gn, 0, sizeof(float) * (size_t)b->S * b->cap_b, p->ctx->stream));
   }
+  if (b->hrtf) {
+    int r = iamfb_hrtf_batch_reset(p->hrtf, b->hrtf, p->ctx->stream);
+    if (r) return r;
+  }
   CU(cudaStreamSynchronize(p->ctx->stream));
   return IAMFB_OK;
 }
@@ -1358,6 +1384,10 @@ extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, 
     iamfb_batch_destroy(b);
     return r;
   }
+  if (p->hrtf) {
+    int r = iamfb_hrtf_batch_create(p->hrtf, n_streams, max_frames, &b->hrtf);
+    if (r) { iamfb_batch_destroy(b); return r; }
+  }
   int r = iamfb_batch_reset(b);
   if (r) { iamfb_batch_destroy(b); return r; }
   *out = b;
@@ -1381,6 +1411,7 @@ extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
   cudaFree(b->d_tl_a); cudaFree(b->d_tl_b); cudaFree(b->d_pk); cudaFree(b->d_wm); cudaFree(b->d_gn);
   cudaFree(b->d_hist_y); cudaFree(b->d_hist_pk);
   for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_wide[e]);
+  iamfb_hrtf_batch_destroy(b->hrtf);
   free_staging(b);
   delete b;
 }
@@ -1502,7 +1533,13 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
   if (s_cnt < 0) s_cnt = b->S;
-  iamfb_io wio;
+  iamfb_io wio, hio;
+  if (p->hrtf && !flush) {
+    // binaural HRTF front end: the elements it renders reach the kernels below as float32 [2][N] frames
+    int r = iamfb_hrtf_run(ctx, p->hrtf, b->hrtf, io, F, s_lo, s_cnt, &hio);
+    if (r) return r;
+    io = &hio;
+  }
   // resampling plans: k_pipe_rs renders the regular streams, the multi-kernel path below the irregular ones
   const bool rs_native = p->rs_pipe && !flush && !io->gain_ramp[0] && !io->out_gain_ramp;
   const bool s16_in = !flush && io->in_format == IAMFB_IN_S16 &&
@@ -1800,8 +1837,8 @@ static int ensure_staging(iamfb_batch *b, int F) {
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void **ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 16); };
   for (int el = 0; el < kp.n_elements; ++el) {
-    alloc((void **)&b->d_in[el], sizeof(float) * S * F * kp.el[el].n_in * N);
-    alloc((void **)&b->d_in16[el], sizeof(int16_t) * S * F * kp.el[el].n_in * N);
+    alloc((void **)&b->d_in[el], sizeof(float) * S * F * b->plan->in_rows[el] * N);
+    alloc((void **)&b->d_in16[el], sizeof(int16_t) * S * F * b->plan->in_rows[el] * N);
     alloc((void **)&b->d_ramp[el], sizeof(float) * S * F * N);
   }
   alloc((void **)&b->d_oramp, sizeof(float) * S * F * N);
@@ -1861,7 +1898,7 @@ extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F
     if (!cnt) continue;
     CU(cudaMemcpyAsync(b->d_params + s_lo * F, io->params + s_lo * F, sizeof(iamfb_frame_params) * cnt * F, cudaMemcpyHostToDevice, ctx->h2d));
     for (int e = 0; e < kp.n_elements; ++e) {
-      const size_t per = (size_t)F * kp.el[e].n_in * N;
+      const size_t per = (size_t)F * p->in_rows[e] * N;
       if (s16)
         CU(cudaMemcpyAsync(b->d_in16[e] + s_lo * per, (const int16_t *)io->in[e] + s_lo * per, sizeof(int16_t) * cnt * per, cudaMemcpyHostToDevice, ctx->h2d));
       else

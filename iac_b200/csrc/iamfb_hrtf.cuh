@@ -36,6 +36,8 @@
 
 #include <cstdint>
 
+#include "iamf_b200.h"
+
 namespace iamfb {
 
 constexpr int kHrTaps = 256;
@@ -235,6 +237,133 @@ static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGe
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+// ---- k_hrtf_index: which frames of the submit feed the renderer.  A frame that is absent (trim_start == 0xFFFF) or trimmed
+// completely (dropped before rendering, IAMF_decoder.c:3354-3358) never reaches the binaural renderer; the present frames of
+// a stream are rendered as one continuous signal (slot k = the k-th present frame).
+struct HrtfIndexArgs {
+  const iamfb_frame_params *params;   // [S][F]
+  int *n_present;                     // [S]
+  short *frame_of_slot;               // [S][F]
+  short *slot_of_frame;               // [S][F]  (-1: not rendered)
+  int S, F, N;
+};
+static __global__ void __launch_bounds__(128) k_hrtf_index(const HrtfIndexArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.S) return;
+  int n = 0;
+  for (int f = 0; f < a.F; ++f) {
+    const iamfb_frame_params &p = a.params[(size_t)s * a.F + f];
+    const bool present = p.trim_start != 0xFFFF && p.trim_start != a.N && p.trim_end != a.N;
+    a.slot_of_frame[(size_t)s * a.F + f] = present ? (short)n : (short)-1;
+    if (present) a.frame_of_slot[(size_t)s * a.F + n++] = (short)f;
+  }
+  a.n_present[s] = n;
+}
+
+// ---- k_hrtf_prep: decoded rows -> the renderer's input channels (channel order / output gain of the de-mixer,
+// demixer.c:421-430,636-664; ambisonics channel mapping or projection, IAMF_core_decoder.c:105-130) -> Q20 fixed point ->
+// limb planes in the operand order of k_hrtf_gemm ([limb][kc][block][16 bytes], instants of a block reversed), with the
+// last 256 instants of the previous submit in front.  One thread = 16 consecutive instants of one channel.
+struct HrtfPrepArgs {
+  const void *in;            // [S][F][n_in][N] float32 or int16
+  uint8_t *planes;           // [S][C][NL][4][NBP][16]
+  const int *hist_in;        // [S][C][256] Q20, the previous submit's last instants
+  int *hist_out;             // [S][C][256]
+  const int *n_present;      // [S]
+  const short *frame_of_slot;// [S][F]
+  int C, n_in, NL, NBP, F, N;
+  int mode;                  // 0: row (x gain), 1: projection
+  int row[IAMFB_MAX_SCENE_CH];
+  float gain[IAMFB_MAX_SCENE_CH];       // 1.0 = none (the multiply is skipped, as dmx_gainup skips unflagged channels)
+  int proj_cols;
+  float proj[IAMFB_MAX_SCENE_CH * IAMFB_MAX_SCENE_CH];   // [col][C]
+};
+__device__ __forceinline__ int hrtf_quantise(float x) {     // oracle_hrtf.c: orc_hrtf_quantise
+  float v = x * 1048576.0f;
+  v = fminf(fmaxf(v, -8388607.0f), 8388607.0f);
+  return __float2int_rn(v);
+}
+template <bool S16>
+static __global__ void __launch_bounds__(256) k_hrtf_prep(const HrtfPrepArgs a) {
+  const int sc = blockIdx.y, s = sc / a.C, c = sc - s * a.C;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;        // 16-instant group of the plane (16 history groups first)
+  const int len = a.n_present[s] * a.N;
+  if (gi >= (kHrHist + len) / 16) return;
+  int xq[16];
+  if (gi < kHrHist / 16) {
+    const int4 *h = reinterpret_cast<const int4 *>(a.hist_in + (size_t)sc * kHrHist + 16 * gi);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int4 v = h[k]; xq[4 * k] = v.x; xq[4 * k + 1] = v.y; xq[4 * k + 2] = v.z; xq[4 * k + 3] = v.w; }
+  } else {
+    const int tau = 16 * gi - kHrHist, slot = tau / a.N, i = tau - slot * a.N;
+    const int f = a.frame_of_slot[(size_t)s * a.F + slot];
+    const size_t frame = ((size_t)s * a.F + f) * a.n_in * a.N + i;
+    auto load16 = [&](int row, float (&v)[16]) {
+      if constexpr (S16) {
+        const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(a.in) + frame + (size_t)row * a.N);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int4 w = p[h];
+          const int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            v[8 * h + 2 * k] = (float)(short)(ww[k] & 0xffff) / 32768.f;
+            v[8 * h + 2 * k + 1] = (float)(short)(ww[k] >> 16) / 32768.f;
+          }
+        }
+      } else {
+        const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(a.in) + frame + (size_t)row * a.N);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float4 w = p[k]; v[4 * k] = w.x; v[4 * k + 1] = w.y; v[4 * k + 2] = w.z; v[4 * k + 3] = w.w; }
+      }
+    };
+    float v[16];
+    if (a.mode == 0) {
+      load16(a.row[c], v);
+      const float g = a.gain[c];
+      if (g != 1.0f) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] *= g;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = .0f;
+      for (int l = 0; l < a.proj_cols; ++l) {
+        float t[16];
+        load16(l, t);
+        const float m = a.proj[l * a.C + c];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] += t[k] * m;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xq[k] = hrtf_quantise(v[k]);
+  }
+  // the last 256 instants (old history included when the submit is shorter) are the next submit's history
+  {
+    const int p0 = 16 * gi - len;                 // index on the next history of this group's first instant
+    if (p0 >= 0) {
+      int4 *h = reinterpret_cast<int4 *>(a.hist_out + (size_t)sc * kHrHist + p0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[k] = make_int4(xq[4 * k], xq[4 * k + 1], xq[4 * k + 2], xq[4 * k + 3]);
+    }
+  }
+  // limbs, instants reversed inside the block: byte u of (kc, block) = instant 63 - 16 kc - u
+  const int bp = gi >> 2, kc = 3 - (gi & 3);
+  const int shift = a.NL == 2 ? 5 : 0;            // 16-bit content travels as two limbs (Q15), anything else as three (Q20)
+  for (int l = 0; l < a.NL; ++l) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t r = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r |= (uint32_t)(((xq[15 - (4 * q + u)] >> shift) >> (8 * l)) & 255) << (8 * u);
+      w[q] = r;
+    }
+    *reinterpret_cast<uint4 *>(a.planes + ((((size_t)sc * a.NL + l) * 4 + kc) * a.NBP + bp) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 // ---- host: Toeplitz core tables of one channel.  taps = [2 ears][256] Q15; dst = [2 limbs][96 cores][8 rows][16 bytes]

@@ -83,7 +83,7 @@ struct ScopedKernelTimer {
   X(4, 5, 8, 0, 0, 1, 2, 4, 7)    X(5, 4, 10, 0, 0, 1, 2, 4, 7)  X(6, 2, 6, 0, 0, 1, 2, 4, 7)    X(7, 2, 6, 0, 0, 0, 2, 4, 7)   \
   X(8, 1, 2, 0, 0, 1, 2, 4, 7)    X(9, 1, 2, 0, 0, 13, 2, 4, 7)                                                                \
   X(10, -1, 16, 0, 0, 7, 4, 2, 3) X(11, 7, 12, -1, 4, 13, 2, 4, 7) X(12, -1, 4, 7, 12, 7, 4, 2, 3)                             \
-  X(13, 7, 12, 0, 0, 1, 4, 2, 7) X(14, -1, 16, 0, 0, 7, 2, 4, 3)
+  X(13, 7, 12, 0, 0, 1, 4, 2, 7) X(14, -1, 16, 0, 0, 7, 2, 4, 3) X(15, 1, 2, 1, 2, 13, 2, 4, 7)
 #define IAMFB_PIPE_GROUP_OF(id) ((id) == 0 ? 0 : ((id) == 10 ? 1 : ((id) == 12 ? 2 : ((id) == 11 ? 3 : ((id) == 13 ? 4 : ((id) == 14 ? 5 : (4 + (id) % 3)))))))
 constexpr int kPipeGroups = 7;
 
@@ -100,3 +100,14 @@ int iamfb_pipe_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelP
                       const CUtensorMap &m0, const CUtensorMap &m1);
 namespace iamfb { struct PipeRsArgs; }
 int iamfb_pipe_rs_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelPlan &kp, const iamfb::PipeRsArgs &pa, int S);
+
+// ---- binaural HRTF front end (iamfb_hrtf.cu)
+struct iamfb_hrtf_front;
+struct iamfb_hrtf_batch;
+int iamfb_hrtf_front_create(const iamfb_plan_desc *d, iamfb_plan_desc *back, iamfb_hrtf_front **out);
+void iamfb_hrtf_front_destroy(iamfb_hrtf_front *h);
+int iamfb_hrtf_batch_create(const iamfb_hrtf_front *h, int S, int Fmax, iamfb_hrtf_batch **out);
+int iamfb_hrtf_batch_reset(const iamfb_hrtf_front *h, iamfb_hrtf_batch *b, cudaStream_t st);
+void iamfb_hrtf_batch_destroy(iamfb_hrtf_batch *b);
+int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *b, const iamfb_io *io, int F, int s_lo, int s_cnt,
+                   iamfb_io *out_io);

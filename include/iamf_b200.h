@@ -109,6 +109,13 @@ typedef struct iamfb_element_desc {
   uint8_t ambi_map[IAMFB_MAX_SCENE_CH];      /* mono: output channel i <- decoded row ambi_map[i] */
   int32_t ambi_cols;                         /* projection: substreams + coupled substreams */
   float ambi_matrix[IAMFB_MAX_SCENE_CH * IAMFB_MAX_SCENE_CH]; /* projection: [col][row], q_to_float(q15) */
+  /* -- binaural target only -- */
+  int32_t binaural_hrtf;                     /* 1: render this element with the HRTF renderer (256-tap HRIR pair per channel,
+                                                iamfb_get_hrir) instead of the stereo rows of the matrix tables - what a
+                                                reference built with DISABLE_BINAURALIZER == 0 does for channel-based
+                                                elements with headphones_rendering_mode == 1 (IAMF_decoder.c:2565-2573,
+                                                m2b_rdr.c:103-121) and for every scene-based element (:2606-2612,
+                                                h2b_rdr.c:109-131).  0: the as-built behaviour (stereo matrices). */
 } iamfb_element_desc;
 
 typedef struct iamfb_plan_desc {
@@ -230,6 +237,12 @@ int iamfb_layout_channels(int layout, int32_t *chs);        /* rendering order, 
 int iamfb_get_m2m_matrix(int layout, int target, int32_t *m, int32_t *n, float *mat);
 /* copies the [n][m] HOA->channel matrix for (order -> target) and its LFE slots */
 int iamfb_get_h2m_matrix(int order, int target, int32_t *m, int32_t *n, int32_t *lfe1, int32_t *lfe2, float *mat);
+
+/* the in-repo HRIR set of the binaural renderer (synthetic, tools/gen_hrir.py): copies the [2 ears][iamfb_hrir_taps()]
+ * Q15 taps of IAChannel `index` (kind == IAMFB_EL_CHANNEL; the role BEAR's default.tf plays for m2b_rdr.c:56) or of
+ * ambisonics channel `index` in ACN order (kind == IAMFB_EL_SCENE; h2b_rdr.c:60) */
+int iamfb_get_hrir(int kind, int index, int16_t *taps);
+int iamfb_hrir_taps(void);
 
 #ifdef __cplusplus
 }

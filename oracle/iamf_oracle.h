@@ -178,7 +178,18 @@ typedef struct OrcElementCfg {
   int ambi_cols;
   /* render matrix (M2M [n_in_layout][n_out] or H2M [n_out_mat][n_in]) */
   const float *mat; int mat_in, mat_out; int lfe1, lfe2;
+  /* binaural HRTF rendering instead of the matrix (m2b_rdr.c / h2b_rdr.c; oracle_hrtf.c): one Q15 HRIR pair per
+     renderer input channel, [mat_in][2][ORC_HRTF_TAPS]; NULL => off */
+  const int16_t *hrtf_taps;
 } OrcElementCfg;
+
+#define ORC_HRTF_TAPS 256
+typedef struct OrcHrtf OrcHrtf;
+OrcHrtf *orc_hrtf_open(int n_ch, const int16_t *taps);
+void orc_hrtf_close(OrcHrtf *h);
+int32_t orc_hrtf_quantise(float x);
+/* in [n_ch][n] planar -> out [2][n] planar; the filter state is carried from call to call */
+void orc_hrtf_render(OrcHrtf *h, const float *in, float *out, int n);
 
 typedef struct OrcStreamCfg {
   int frame_size, in_rate, out_rate;

@@ -19,6 +19,7 @@ struct OrcStream {
   OrcStreamCfg cfg;
   OrcDemixer *dmx[2];
   OrcDownmixer *dmr[2];
+  OrcHrtf *hrtf[2];
   OrcResampler *rs;
   OrcLimiter *lim;
   float *buf[2][2]; /* per element: reconstructed, rendered */
@@ -63,6 +64,10 @@ OrcStream *orc_stream_open(const OrcStreamCfg *cfg) {
       }
     }
   }
+  for (int e = 0; e < cfg->n_elements; ++e)
+    if (cfg->el[e].hrtf_taps) /* IAMF_element_renderer_init_M2B / _H2B, IAMF_decoder.c:2491-2508 */
+      s->hrtf[e] = orc_hrtf_open(cfg->el[e].type == ORC_EL_CHANNEL ? orc_layout_channel_count(cfg->el[e].layout) : cfg->el[e].n_in,
+                                 cfg->el[e].hrtf_taps);
   s->mix = (float *)calloc(s->cap, sizeof(float));
   s->tmp = (float *)calloc(s->cap, sizeof(float));
   if (cfg->in_rate != cfg->out_rate) s->rs = orc_resampler_open(cfg->out_channels, cfg->in_rate, cfg->out_rate, 4);
@@ -79,6 +84,7 @@ void orc_stream_close(OrcStream *s) {
   for (int e = 0; e < 2; ++e) {
     orc_demixer_close(s->dmx[e]);
     orc_dmr_close(s->dmr[e]);
+    orc_hrtf_close(s->hrtf[e]);
     free(s->buf[e][0]); free(s->buf[e][1]);
   }
   orc_resampler_close(s->rs);
@@ -111,7 +117,9 @@ int orc_stream_decode(OrcStream *s, float *const *in, const OrcFrameParams *fp, 
     if (drop) continue;
     /* iamf_stream_render, IAMF_decoder.c:2536-2651 */
     memset(ren, 0, sizeof(float) * co * n);
-    if (el->type == ORC_EL_CHANNEL) {
+    if (s->hrtf[e]) { /* :2565-2573, :2606-2612: the binaural renderer takes the place of the matrix */
+      orc_hrtf_render(s->hrtf[e], rec, ren, n);
+    } else if (el->type == ORC_EL_CHANNEL) {
       if (s->dmr[e]) {
         if (fp[e].dmx_mode > -1) orc_dmr_set_mode_weight(s->dmr[e], fp[e].dmx_mode, -1);
         orc_dmr_downmix(s->dmr[e], rec, ren, 0, n, n);

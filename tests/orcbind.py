@@ -21,7 +21,8 @@ class ElementCfg(C.Structure):
                 ("first_layer_layout", C.c_int), ("selected_layer", C.c_int),
                 ("use_dmr", C.c_int), ("dmr_out_layout", C.c_int),
                 ("ambi_mode", C.c_int), ("ambi_map", C.c_uint8 * 16), ("ambi_matrix", f32p), ("ambi_cols", C.c_int),
-                ("mat", f32p), ("mat_in", C.c_int), ("mat_out", C.c_int), ("lfe1", C.c_int), ("lfe2", C.c_int)]
+                ("mat", f32p), ("mat_in", C.c_int), ("mat_out", C.c_int), ("lfe1", C.c_int), ("lfe2", C.c_int),
+                ("hrtf_taps", C.POINTER(C.c_int16))]
 
 
 class StreamCfg(C.Structure):

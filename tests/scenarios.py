@@ -43,6 +43,7 @@ class El:
     mapping: Optional[list] = None
     projection: Optional[np.ndarray] = None    # [cols][rows]
     mix_gain: float = 1.0
+    hrtf: bool = False                         # binaural target: HRTF renderer instead of the stereo matrix rows
 
     @property
     def n_in(self):
@@ -100,6 +101,33 @@ def c4_714_foa_binaural(**kw):
     e0 = El("channel", LY_714, [L7, R7, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, CC, LFE], mix_gain=g)
     e1 = El("scene", channels=4, mix_gain=g)
     return Scenario("c4_714_foa_to_binaural", [e0, e1], TGT_BIN, **kw)
+
+
+def c4_hrtf(**kw):
+    """configuration 4 with the HRTF renderer: 7.1.4 (M2B, one HRIR pair per loudspeaker) + first-order ambisonics (H2B)"""
+    sc = c4_714_foa_binaural(**kw)
+    sc.name = "c4_714_foa_to_binaural_hrtf"
+    for el in sc.elements:
+        el.hrtf = True
+    return sc
+
+
+def hrtf_cases():
+    rng = np.random.default_rng(11)
+    proj = (rng.integers(-20000, 20000, (5, 4)) / np.float32(32768)).astype(np.float32)
+    return [
+        c4_hrtf(),
+        Scenario("hrtf_510_gain_24bit", [El("channel", LY_510, [L5, R5, SL5, SR5, CC, LFE], out_gain=[(L5, 1.3), (R5, 1.3)],
+                                            hrtf=True, mix_gain=0.5)], TGT_BIN, bit_depth=24),
+        Scenario("hrtf_toa_float", [El("scene", channels=16, hrtf=True, mix_gain=0.25)], TGT_BIN, bit_depth=0),
+        Scenario("hrtf_foa_projection_trims", [El("scene", channels=4, projection=proj, hrtf=True)], TGT_BIN,
+                 trims={0: (312, 0), 2: (960, 0), 5: (0, 100), 6: (0, 960)}, out_gain=0.7),
+        Scenario("hrtf_stereo_plus_matrix_714", [El("channel", LY_STEREO, [L2, R2], hrtf=True, mix_gain=0.6),
+                                                 El("channel", LY_714, [L7, R7, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, CC, LFE],
+                                                    mix_gain=0.5)], TGT_BIN),
+        Scenario("hrtf_mono_1024_to_44k1", [El("channel", LY_MONO, [MONO], hrtf=True)], TGT_BIN, frame_size=1024,
+                 out_rate=44100, limiter=False),
+    ]
 
 
 def c5_resample(**kw):
@@ -216,6 +244,7 @@ def plan_desc(sc: Scenario):
                                       el.selected_layer, bool(el.recon_flags), el.dmr_out_layout)
         else:
             d.el[e] = scene_element(el.channels, el.n_in, el.mapping, el.projection)
+        d.el[e].binaural_hrtf = 1 if el.hrtf else 0
     d.target = sc.target
     d.loudness_gain = sc.loudness_gain
     d.limiter = 1 if sc.limiter else 0
@@ -282,6 +311,16 @@ def _orc_cfg(sc: Scenario, keep):
                 mp = el.mapping if el.mapping is not None else list(range(el.channels))
                 for i, m in enumerate(mp):
                     oe.ambi_map[i] = m
+        if el.hrtf and sc.target == TGT_BIN:
+            # one HRIR pair per renderer input: the layout's channels in rendering order / the ambisonics channels in ACN order
+            from iac_b200.binding import get_hrir, layout_channels
+            if el.kind == "channel":
+                taps = np.stack([get_hrir(0, ch) for ch in layout_channels(el.layout)])
+            else:
+                taps = np.stack([get_hrir(1, m) for m in range(el.channels)])
+            taps = np.ascontiguousarray(taps, np.int16)
+            keep.append(taps)
+            oe.hrtf_taps = taps.ctypes.data_as(C.POINTER(C.c_int16))
     return cfg
 
 

@@ -1,0 +1,79 @@
+"""GPU parity of the binaural HRTF renderer (tcgen05 int8 contraction, iac_b200/csrc/iamfb_hrtf.cuh) through the C ABI.
+
+PARITY UNPINNED BY THE REFERENCE: m2b_rdr.c / h2b_rdr.c call closed libraries that are absent from the reference tree
+(SURVEY 8c), so the checker is the self-oracle oracle/oracle_hrtf.c (exact integer FIR, rounded once) inside the pinned
+pipeline oracle.  The renderer is exact integer arithmetic, so the bar is still BIT-EXACT - float output and 16/24-bit
+PCM alike (north_star allows 1e-5 of full scale / +-1 LSB)."""
+import numpy as np
+import pytest
+
+import scenarios as S
+from test_gpu_parity import compare
+
+pytestmark = pytest.mark.gpu
+
+CASES = S.hrtf_cases()
+
+
+@pytest.mark.parametrize("sc", CASES, ids=[s.name for s in CASES])
+def test_hrtf_single_submit(sc):
+    compare(sc, 5, 6, [6], seed=31)
+
+
+@pytest.mark.parametrize("sc", CASES, ids=[s.name for s in CASES])
+def test_hrtf_ragged_submits(sc):
+    # the filter state (255 instants per channel) crosses submit boundaries of every length, incl. a 1-frame submit
+    compare(sc, 21, 12, [1, 4, 2, 5], seed=32)
+
+
+def test_hrtf_int16_upload_two_limbs():
+    # 16-bit decoded PCM travels as two limbs (Q15) instead of three (Q20): same bits out
+    compare(S.c4_hrtf(), 70, 5, [2, 3], seed=33, s16=True)
+    compare(S.hrtf_cases()[2], 9, 4, [4], seed=34, s16=True)
+
+
+def test_hrtf_missing_frames_keep_the_filter_state():
+    # streams that have no frame in some steps (trim_start 0xFFFF): the renderer sees their present frames as one signal
+    sc = S.c4_hrtf()
+
+    def edit(P):
+        P["trim_start"][1::3, 2] = 0xFFFF
+        P["trim_start"][2::5, 0:3] = 0xFFFF
+    from gpu_harness import run_product
+    n, F = 11, 8
+    inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 35)
+    P, ramps, oramp = S.synth_params(sc, n, F, seed=0x77 + 35)
+    edit(P)
+    got, _ = run_product(sc, inputs, P, ramps, oramp, splits=[3, 5])
+    # the oracle is fed the present frames only (a stream without a frame in a step is simply not called)
+    for s in range(n):
+        keep = [f for f in range(F) if P["trim_start"][s, f] != 0xFFFF]
+        ref = S.run_oracle(sc, [x[s:s + 1][:, keep] for x in inputs], P[s:s + 1][:, keep])[0]
+        cnt = [c for f, c in enumerate(got[s][0][:F]) if f in keep] + got[s][0][F:]
+        assert cnt == ref[0], f"stream {s}: counts"
+        assert np.array_equal(got[s][1], ref[1]), f"stream {s}: PCM differs"
+
+
+def test_hrtf_full_size_config4():
+    # BASELINE.json configs[3] at its stream count: 16 distinct streams replicated over 2048 must give the same bytes
+    # wherever they sit, equal to the oracle
+    from gpu_harness import run_product
+    sc = S.c4_hrtf()
+    n, F, reps = 16, 4, 128
+    inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 36)
+    P, _, _ = S.synth_params(sc, n, F, seed=0x77 + 36)
+    big = [np.tile(x, (reps, 1, 1, 1)) for x in inputs]
+    got, _ = run_product(sc, big, np.tile(P, (reps, 1)), splits=[F])
+    ref = S.run_oracle(sc, inputs, P)
+    for s in range(n * reps):
+        assert got[s][0] == ref[s % n][0]
+        assert np.array_equal(got[s][1], ref[s % n][1]), f"stream {s}"
+
+
+def test_hrtf_refuses_what_it_does_not_render():
+    from iac_b200 import Engine
+    sc = S.c2_714_to_B()
+    sc.target = S.TGT_BIN
+    sc.elements[0].hrtf = True            # scalable element whose channels are derived by the de-mixer
+    with pytest.raises(Exception):
+        Engine(S.plan_desc(sc), 4, 2)

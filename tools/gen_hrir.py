@@ -7,7 +7,8 @@ The reference's binaural path hands the planar frames to two closed libraries (B
 default.tf; Resonance Audio: spherical-harmonic-domain HRIRs) that are absent from the tree (SURVEY 8c, m2b_rdr.c:103-121,
 h2b_rdr.c:109-131), so no reference data exists to carry.  This set stands in for them: a rigid-sphere head model
 (Woodworth inter-aural delay, first-order head shadow), three pinna echoes and a short decaying diffuse tail, 256 taps
-at 48 kHz, written as IEEE-754 bit patterns so that the product and the test oracle read exactly the same numbers.
+at 48 kHz, written as Q15 int16 (what 16-bit SOFA / WAV HRIR sets hold): the renderer is an exact integer contraction on
+the int8 tensor cores (iac_b200/csrc/iamfb_hrtf.cuh), so the product and the test oracle agree bit for bit.
 
   speaker set  (M2B): one (left ear, right ear) pair per IAChannel id 1..23 (IAMF_types.h:61-90)
   ambisonic set (H2B): one pair per ACN channel 0..15 (SN3D), = the speaker-domain responses of a 14-direction virtual
@@ -104,19 +105,22 @@ def main():
             for m in range(16):
                 amb[m, e] += (2.0 / len(dirs)) * y[m] * h
     amb = amb.astype(np.float32)
-    pool = np.concatenate([spk.reshape(-1), amb.reshape(-1)]).view(np.uint32)
+    allf = np.concatenate([spk.reshape(-1), amb.reshape(-1)]).astype(np.float64)
+    peak = float(np.abs(allf).max())
+    assert peak < 1.0, peak
+    pool = np.clip(np.rint(allf * 32768.0), -32767, 32767).astype(np.int16)
     sha = hashlib.sha256(pool.tobytes()).hexdigest()
     with open(OUT, "w") as f:
         f.write("// GENERATED by tools/gen_hrir.py - do not edit.  Synthetic HRIR set of the binaural renderer (see the generator).\n")
-        f.write(f"// {TAPS} taps at 48 kHz as IEEE-754 bit patterns; speaker set [24 IAChannel ids][2 ears][taps], then the\n")
-        f.write(f"// ambisonic set [16 ACN channels][2 ears][taps].  sha256 {sha}\n")
+        f.write(f"// {TAPS} taps at 48 kHz, Q15 int16; speaker set [24 IAChannel ids][2 ears][taps], then the ambisonic set\n")
+        f.write(f"// [16 ACN channels][2 ears][taps].  peak {peak:.6f}  sha256 {sha}\n")
         f.write(f"static constexpr int k_hrir_taps = {TAPS};\n")
-        f.write(f"static constexpr uint32_t k_hrir_amb_off = {24 * 2 * TAPS}u;\n")
-        f.write("static const uint32_t k_hrir_pool[] = {\n")
-        for i in range(0, len(pool), 8):
-            f.write("  " + ", ".join(f"0x{v:08x}u" for v in pool[i:i + 8]) + ",\n")
+        f.write(f"static constexpr int k_hrir_amb_off = {24 * 2 * TAPS};\n")
+        f.write("static const int16_t k_hrir_q15[] = {\n")
+        for i in range(0, len(pool), 16):
+            f.write("  " + ", ".join(str(int(v)) for v in pool[i:i + 16]) + ",\n")
         f.write("};\n")
-    print(OUT, len(pool), "words", sha)
+    print(OUT, len(pool), "taps", "peak", peak, sha)
 
 
 if __name__ == "__main__":
