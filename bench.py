@@ -35,6 +35,9 @@ CONFIGS = {
     "c2": dict(streams=1024, frames=16, desc="1024 base-profile streams, 7.1.4 scalable (2.0 -> 7.1.4) with recon-gain demixing -> sound system B (0+5+0)"),
     "c3": dict(streams=4096, frames=8, desc="4096 streams of 3rd-order ambisonics (16 ch) -> sound system H (9+10+3)"),
     "c4": dict(streams=2048, frames=8, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural (as built: stereo matrices)"),
+    "c4h": dict(streams=2048, frames=8, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural with HRTF convolution (256-tap in-repo HRIR set, "
+                                             "exact int8 tensor-core contraction; self-oracle, parity unpinned by the reference)",
+                in_format="s16"),   # the decoded PCM is handed over as the int16 the codecs produce: two limbs per sample instead of three
     "c5": dict(streams=2048, frames=16, desc="2048 streams/GPU, stereo 44.1->48 kHz resample, loudness -24 LKFS, limiter, 16-bit"),
 }
 
@@ -102,7 +105,7 @@ def cpu_reference(cfg, n_frames, reps=1, warm=0):
     kind, sample, seconds)."""
     import multiprocessing as mp
     import refbind
-    kind = "reference" if refbind.have_ref() else "port"
+    kind = "reference" if (refbind.have_ref() and cfg != "c4h") else "port"   # (the reference is built without its binauraliser)
     import orcbind
     orcbind.lib()   # make sure liboracle.so exists before the workers start (refstreams uses its scalar helpers)
     workers = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
@@ -327,6 +330,22 @@ class DeviceWorkload:
         except Exception:
             pass
         pipe = alg / (ms_per_submit / 1e3) / 1e9
+        if dom == "k_hrtf_gemm":
+            # the HRTF contraction is tensor-bound: int8 MACs ISSUED (every limb pair of every tile, Toeplitz padding included)
+            # against twice the measured dense bf16 rate (kind::i8 runs at twice the 16-bit rate); "useful" counts one
+            # multiply-add per sample, tap and ear
+            audio = out_per_submit / self.sc.out_rate
+            ch = sum(el.n_in for el in self.sc.elements if getattr(el, "hrtf", False))
+            useful = audio * self.sc.in_rate * ch * 256 * 2
+            limb_pairs = 2 * (2 if self.in_format == "s16" else 3)
+            issued = useful * limb_pairs * (320.0 / 256.0)
+            t = kernels[dom]["ms_per_submit"] / 1e3
+            peak_t = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
+            return dict(bound="tensor", kernel=dom, achieved=2 * issued / t / 1e12, peak=peak_t, unit="int8 TOP/s", frac=2 * issued / t / 1e12 / peak_t,
+                        traffic=None, peak_source="2 x MEASURED_PEAKS.json bf16_tflops (int8 dense rate)" if "bf16_tflops" in peaks else "2 x 2250 nominal",
+                        useful_fir_tmacs=useful / t / 1e12, limb_pairs=limb_pairs,
+                        pipeline=dict(achieved=pipe, frac=pipe / peak_gbs, note="all kernels of a submit, algorithmic bytes / submit time, vs HBM peak"),
+                        kernels=kernels)
         return dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
                     traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=alg / dom_launches,
                     pipeline=dict(achieved=pipe, frac=pipe / peak_gbs, note="all kernels of a submit, algorithmic bytes / submit time"),
@@ -398,6 +417,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.in_format == "f32" and "in_format" in CONFIGS[cfg]:
+        args.in_format = CONFIGS[cfg]["in_format"]
     w = DeviceWorkload(cfg, S_, F, rank, local, dev, stream, args.peak_ref, args.peak_db, args.in_format)
     sc = w.sc
 
@@ -430,7 +451,7 @@ def run_gpu(args):
             print(json.dumps({"metric": "rendered audio-sec/sec", "value": value, "ms_per_step": ms_max / args.steps,
                               "ms_per_submit": ms_per_submit, "submits_per_step": R,
                               "gpu_launches": int(launches), "quick": True, "peak_ref": args.peak_ref,
-                              "streams_above_limiter_threshold": w.active_frac, "kernel_path": w.eng.kernel_path}))
+                              "streams_above_limiter_threshold": w.active_frac, "kernel_path": w.eng.kernel_path_s16 if w.in_format == "s16" else w.eng.kernel_path}))
         w.close()
         return
 
@@ -506,7 +527,7 @@ def run_gpu(args):
                 continue
             torch.cuda.empty_cache()
             wo = DeviceWorkload(oc, CONFIGS[oc]["streams"], CONFIGS[oc]["frames"], rank, local, dev, stream, args.peak_ref, "",
-                                args.in_format)
+                                CONFIGS[oc].get("in_format", args.in_format))
             for _ in range(3):
                 wo.submit()
             pr = timed_submits(wo, 4, barrier) / 4.0
@@ -518,10 +539,10 @@ def run_gpu(args):
             ro = wo.roofline(ko, to_max / no, ops)
             others[oc] = dict(value=shard.job_throughput(to_max, oo, wo.sc.out_rate, steps=1), unit="audio-s/s",
                               ms_per_submit=to_max / no, submits_timed=no, streams_per_gpu=wo.S, frames_per_submit=wo.F,
-                              workload=CONFIGS[oc]["desc"], kernel_path=wo.eng.kernel_path,
+                              workload=CONFIGS[oc]["desc"], kernel_path=wo.eng.kernel_path_s16 if wo.in_format == "s16" else wo.eng.kernel_path, input_format=wo.in_format,
                               streams_above_limiter_threshold=wo.active_frac,
-                              roofline=dict(kernel=ro["kernel"], achieved=ro["achieved"], peak=ro["peak"], frac=ro["frac"],
-                                            traffic=ro["traffic"], pipeline_frac=ro["pipeline"]["frac"],
+                              roofline=dict(bound=ro["bound"], kernel=ro["kernel"], achieved=ro["achieved"], peak=ro["peak"], unit=ro["unit"],
+                                            frac=ro["frac"], traffic=ro["traffic"], pipeline_frac=ro["pipeline"]["frac"],
                                             kernels={k: round(v["ms_per_submit"], 5) for k, v in ko.items()}))
             wo.close()
             del wo
@@ -543,7 +564,7 @@ def run_gpu(args):
                        "l2_policy": "the inputs of one submit are larger than L2 (126 MB); nothing is re-read from cache across submits",
                        "limiter_active_peak_range_db": list(sc.peak_db),
                        "peak_reference": ("pre-limiter peak of the rendered mix" if w.calibrated else "decoded input channels"),
-                       "streams_above_limiter_threshold": w.active_frac, "kernel_path": w.eng.kernel_path},
+                       "streams_above_limiter_threshold": w.active_frac, "kernel_path": w.eng.kernel_path_s16 if w.in_format == "s16" else w.eng.kernel_path},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "frames_per_step": Fe, "steps": ke, "ms_per_step": te_max_ms / ke, "input": "int16 PCM as decoded (IAMFB_IN_S16)",
                     "gpu_launches": int(e2e_launches),

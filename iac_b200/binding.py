@@ -96,6 +96,8 @@ def lib():
     L.iamfb_selftest_quotient.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
     L.iamfb_plan_kernel_path.argtypes = [vp]
     L.iamfb_plan_kernel_path.restype = C.c_int
+    L.iamfb_plan_kernel_path_fmt.argtypes = [vp, C.c_int]
+    L.iamfb_plan_kernel_path_fmt.restype = C.c_int
     L.iamfb_plan_max_out_samples.argtypes = [vp, C.c_int]
     L.iamfb_plan_out_stride_bytes.argtypes = [vp, C.c_int]
     L.iamfb_plan_out_stride_bytes.restype = C.c_size_t
@@ -226,7 +228,8 @@ class Engine:
         _check(L.iamfb_plan_create(self.ctx, C.byref(desc), C.byref(self.plan)), "iamfb_plan_create")
         _check(L.iamfb_batch_create(self.plan, n_streams, max_frames, C.byref(self.batch)), "iamfb_batch_create")
         self.out_channels = L.iamfb_plan_out_channels(self.plan)
-        self.kernel_path = L.iamfb_plan_kernel_path(self.plan)   # 0 multi-kernel, 1 k_fused, 2 k_stream
+        self.kernel_path = L.iamfb_plan_kernel_path(self.plan)   # 0 multi-kernel, 1 k_fused, 2 k_stream, 3 k_pipe (float32 submits)
+        self.kernel_path_s16 = L.iamfb_plan_kernel_path_fmt(self.plan, 1)   # the same for int16 submits
         self.bytes_per_sample = desc.bit_depth // 8 if desc.bit_depth else 4
 
     def close(self):

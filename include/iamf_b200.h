@@ -189,11 +189,14 @@ int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *desc, iamfb_plan **
 void iamfb_plan_destroy(iamfb_plan *plan);
 int iamfb_plan_out_channels(const iamfb_plan *plan);
 /* diagnostic: which kernels serve this plan - IAMFB_PATH_MULTI (one kernel per stage), IAMFB_PATH_FUSED (k_fused: one
- * kernel per submit), IAMFB_PATH_STREAM (k_stream: pipelined per-stream kernel; trimmed / flushed streams of a submit
- * still take k_fused), IAMFB_PATH_PIPE (k_pipe: the same pipeline with double-buffered int16 / float32 staging for
- * channel-based, scene-based and two-element signatures).  Results are bit-identical on every path. */
+ * kernel per submit), IAMFB_PATH_STREAM (k_stream: pipelined per-stream kernel with one float32 stage, 16-bit channel-based
+ * single-element signatures; trimmed / flushed streams of a submit still take k_fused), IAMFB_PATH_PIPE (k_pipe /
+ * k_pipe_rs: the same pipeline for channel-based, scene-based, two-element and resampling signatures, any output depth,
+ * two int16 stages or one float32 stage).  Where both exist float32 submits take k_stream and int16 submits k_pipe.
+ * Results are bit-identical on every path. */
 enum { IAMFB_PATH_MULTI = 0, IAMFB_PATH_FUSED = 1, IAMFB_PATH_STREAM = 2, IAMFB_PATH_PIPE = 3 };
-int iamfb_plan_kernel_path(const iamfb_plan *plan);
+int iamfb_plan_kernel_path(const iamfb_plan *plan);                      /* for float32 submits */
+int iamfb_plan_kernel_path_fmt(const iamfb_plan *plan, int in_format);   /* IAMFB_IN_F32 | IAMFB_IN_S16 */
 /* upper bound of samples per channel one submit of n_frames can produce for one stream */
 int iamfb_plan_max_out_samples(const iamfb_plan *plan, int n_frames);
 /* bytes between consecutive streams in the pcm buffer for a submit of n_frames */

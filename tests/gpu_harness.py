@@ -12,7 +12,8 @@ def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, 
     assert sum(splits) == F
     eng = Engine(S.plan_desc(sc), n_streams, max(splits), device=device)
     if expect_path is not None:
-        assert eng.kernel_path == expect_path, f"{sc.name}: kernel path {eng.kernel_path}, expected {expect_path}"
+        path = eng.kernel_path_s16 if s16 else eng.kernel_path
+        assert path == expect_path, f"{sc.name}: kernel path {path}, expected {expect_path}"
     co = eng.out_channels
     bps = eng.bytes_per_sample
     counts = [[] for _ in range(n_streams)]

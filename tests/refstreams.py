@@ -40,8 +40,9 @@ def case(name, **kw):
             return dict(demix_mode={0: int(P["dmx_mode0"][s, f])}, recon=rg)
     elif name == "c3":
         sc, st, api = S.c3_toa_to_H(**kw), G.cfg_toa(), dict(sound_system=7)
-    elif name == "c4":
-        sc = S.c4_714_foa_binaural(**kw)
+    elif name in ("c4", "c4h"):
+        # c4h: the same mix through the HRTF renderer (the reference as built cannot run it: bench.py's CPU leg for it is the port)
+        sc = S.c4_hrtf(**kw) if name == "c4h" else S.c4_714_foa_binaural(**kw)
         sc.elements[0].mix_gain = lin(-0x0300)
         sc.elements[1].mix_gain = lin(-0x0300)
         st, api = G.cfg_714_foa(), dict(binaural=True)

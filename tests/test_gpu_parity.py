@@ -74,11 +74,17 @@ def test_sequential_fused_kernel_still_bit_exact(monkeypatch):
     compare(S.c1_stereo(peak_db=(-3.0, 3.0)), 5, 6, [6], seed=4, expect_path=1)
 
 
-def test_pipe_kernel_serves_the_named_configurations():
-    # k_pipe (double-buffered int16 / float32 staging) serves configs 1-4: channel-based, scene-based and two-element mixes
+def test_pipe_kernel_serves_the_named_configurations(monkeypatch):
+    # k_pipe (double-buffered int16 / float32 staging) serves configs 1-4: channel-based, scene-based and two-element mixes.
+    # Where k_stream exists too (16-bit channel-based single-element plans: configs 1-2) it keeps the float32 submits
     for sc in (S.c1_stereo(), S.c2_714_to_B(), S.c3_toa_to_H(), S.c4_714_foa_binaural()):
-        compare(sc, 13, 8, [3, 5], seed=61, expect_path=3)             # float32 staging, one stage
+        both = len(sc.elements) == 1 and sc.elements[0].kind == "channel"
+        compare(sc, 13, 8, [3, 5], seed=61, expect_path=2 if both else 3)
         compare(sc, 13, 8, [3, 5], seed=62, s16=True, expect_path=3)   # int16 staging, two stages
+    monkeypatch.setenv("IAMFB_STREAM", "0")                            # k_pipe with its one float32 stage for configs 1-2 as well
+    for sc in (S.c1_stereo(), S.c2_714_to_B()):
+        compare(sc, 13, 8, [3, 5], seed=61, expect_path=3)
+    monkeypatch.delenv("IAMFB_STREAM")
     compare(S.edge_cases()[9], 9, 6, [2, 4], seed=63, s16=True, expect_path=3)   # FOA + 7.1.4 -> sound system H
 
 
@@ -128,8 +134,9 @@ def test_stream_kernel_still_bit_exact(monkeypatch):
 def test_stream_kernel_mixed_with_trimmed_submits():
     # first submit untrimmed (k_stream), later submits carry trimmed frames (k_fused takes those streams): the limiter
     # history and state must hand over between the two kernels
-    compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31, expect_path=3)
-    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32, expect_path=3)
+    compare(S.c1_stereo(trims={5: (0, 100), 9: (200, 0)}, peak_db=(-2.0, 3.0)), 12, 12, [4, 4, 4], seed=31, expect_path=2)
+    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32, expect_path=2)
+    compare(S.c2_714_to_B(trims={7: (0, 480)}, peak_db=(-3.0, 3.0)), 10, 10, [3, 3, 4], seed=32, s16=True, expect_path=3)   # k_pipe <-> k_fused
 
 
 def test_stream_and_fused_kernels_side_by_side_in_one_submit():
@@ -139,15 +146,17 @@ def test_stream_and_fused_kernels_side_by_side_in_one_submit():
         P["trim_start"][1::3, 2] = 96
         P["trim_end"][2::3, 5] = 300
         P["trim_start"][2::3, 7] = 959
-    compare(S.c2_714_to_B(peak_db=(-3.0, 3.0)), 23, 9, [3, 3, 3], seed=51, expect_path=3, edit_params=trims_on_every_third_stream)
-    compare(S.c1_stereo(peak_db=(-2.0, 3.0)), 40, 8, [4, 4], seed=52, expect_path=3, edit_params=trims_on_every_third_stream)
+    compare(S.c2_714_to_B(peak_db=(-3.0, 3.0)), 23, 9, [3, 3, 3], seed=51, expect_path=2, edit_params=trims_on_every_third_stream)
+    compare(S.c1_stereo(peak_db=(-2.0, 3.0)), 40, 8, [4, 4], seed=52, expect_path=2, edit_params=trims_on_every_third_stream)
+    compare(S.c1_stereo(peak_db=(-2.0, 3.0)), 40, 8, [4, 4], seed=52, s16=True, expect_path=3, edit_params=trims_on_every_third_stream)
 
 
 def test_stream_kernel_clipping_quantiser():
     # limiter threshold above full scale: samples beyond +-1.0 reach the quantiser and must saturate like
     # FLOAT2INT16 (IAMF_decoder.c:100-103) does
-    compare(S.c1_stereo(threshold_db=6.0, peak_db=(0.0, 8.0)), 9, 6, [6], seed=41, expect_path=3)
-    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42, expect_path=3)
+    compare(S.c1_stereo(threshold_db=6.0, peak_db=(0.0, 8.0)), 9, 6, [6], seed=41, expect_path=2)
+    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42, expect_path=2)
+    compare(S.c2_714_to_B(threshold_db=9.0, peak_db=(-3.0, 3.0)), 7, 5, [2, 3], seed=42, s16=True, expect_path=3)
 
 
 STREAM_CASES = S.stream_kernel_cases()
@@ -156,7 +165,8 @@ STREAM_CASES = S.stream_kernel_cases()
 @pytest.mark.parametrize("sc", STREAM_CASES, ids=[s.name for s in STREAM_CASES])
 def test_stream_kernel_signatures(sc):
     # the other (layout, target) pairs k_stream is instantiated for, layered (de-mixing + recon gain) where the layout allows
-    compare(sc, 11, 9, [4, 5], seed=51, expect_path=3)   # IAMFB_PATH_STREAM
+    compare(sc, 11, 9, [4, 5], seed=51, expect_path=2)             # IAMFB_PATH_STREAM: float32 submits
+    compare(sc, 11, 9, [4, 5], seed=51, s16=True, expect_path=3)   # IAMFB_PATH_PIPE: int16 submits
 
 
 @pytest.mark.parametrize("thr_db", [-1.0, 0.0, -6.0, -0.1, -20.0, 3.0])
