@@ -180,7 +180,7 @@ int iamfb_hrtf_batch_create(const iamfb_hrtf_front *h, int S, int Fmax, iamfb_hr
   b->Fmax = Fmax;
   const int T = Fmax * h->N;
   int nb = (T + kHrBlock - 1) / kHrBlock;
-  nb = (nb + 15) & ~15;
+  nb = (nb + 63) & ~63;   // (the epilogue splits a tile into four column groups of whole 16-column pieces)
   if (nb > kHrMaxNB) nb = kHrMaxNB;
   b->NB = nb;
   b->NT = (T + nb * kHrBlock - 1) / (nb * kHrBlock);
@@ -228,7 +228,7 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
   // tiles for THIS submit's length (the planes are sized for Fmax)
   const int T = F * N;
   int nb = (T + kHrBlock - 1) / kHrBlock;
-  nb = (nb + 15) & ~15;
+  nb = (nb + 63) & ~63;   // (the epilogue splits a tile into four column groups of whole 16-column pieces)
   if (nb > b->NB) nb = b->NB;
   const int nt = (T + nb * kHrBlock - 1) / (nb * kHrBlock);
   const int nbp = b->NBP;
@@ -288,9 +288,16 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
       ga.S = s_cnt; ga.C = C; ga.NL = NL; ga.NB = nb; ga.NT = nt; ga.NBP = nbp; ga.F = F; ga.N = N;
       ga.x_shift = NL == 2 ? 15 : 20;
       const int smem = kHrStages * hrtf_stage_bytes(nb, NL);
-      CU(cudaFuncSetAttribute(k_hrtf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      const int tiles = s_cnt * nt;
-      { ScopedKernelTimer tm_(ctx, "k_hrtf_gemm"); k_hrtf_gemm<<<tiles < sms ? tiles : sms, kHrThreads, smem, st>>>(ga); }
+      const int tiles = s_cnt * nt, grid = tiles < sms ? tiles : sms;
+      if (NL == 2) {
+        CU(cudaFuncSetAttribute(k_hrtf_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ScopedKernelTimer tm_(ctx, "k_hrtf_gemm");
+        k_hrtf_gemm<2><<<grid, kHrThreads, smem, st>>>(ga);
+      } else {
+        CU(cudaFuncSetAttribute(k_hrtf_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ScopedKernelTimer tm_(ctx, "k_hrtf_gemm");
+        k_hrtf_gemm<3><<<grid, kHrThreads, smem, st>>>(ga);
+      }
       HR_LAUNCH_CHECK("k_hrtf_gemm");
     }
     out_io->in[e] = b->d_bin[e];

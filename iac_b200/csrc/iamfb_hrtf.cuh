@@ -27,8 +27,8 @@
 // Per channel a tile costs 20 * (limb pairs) MMAs of 128 x NB x 32 and moves 12 KB * 2 (tables, L2-resident) + the
 // channel's samples once.
 //
-// Kernel shape (persistent, one CTA per SM, 192 threads): warp 0 = producer (bulk copies into a 4-stage ring, one stage
-// per channel), warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> int64 -> float32 ->
+// Kernel shape (persistent, one CTA per SM, 576 threads): warp 0 = producer (bulk copies into a 4-stage ring, one stage
+// per channel), warp 1 = MMA issuer (one elected lane), warps 2-17 = epilogue (TMEM -> registers -> int64 -> float32 ->
 // the element's binaural frame [S][F][2][N]).
 #pragma once
 #include <cuda.h>
@@ -49,7 +49,8 @@ constexpr int kHrTabBytes = kHrCores * 128;  // 12288
 constexpr int kHrHLimbs = 2;                 // Q15 int16 taps: low limb unsigned, high limb signed
 constexpr int kHrMaxXLimbs = 3;
 constexpr int kHrStages = 4;
-constexpr int kHrThreads = 192;
+constexpr int kHrEpiGroups = 4;              // epilogue: column groups, each served by four warps (one per TMEM lane quarter)
+constexpr int kHrThreads = 64 + kHrEpiGroups * 128;
 constexpr int kHrMaxNB = 128;                // blocks per tile (N of the MMA)
 
 // bytes of one pipeline stage for tiles of nb blocks and nl sample limbs
@@ -114,12 +115,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
 }  // namespace hr
 
 // dynamic shared memory: [stages][table 2 x 12288 | X limbs]; static: barriers + the TMEM base address
+template <int NL>
 static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGemmArgs a) {
   extern __shared__ __align__(128) uint8_t hr_smem[];
   __shared__ __align__(8) uint64_t s_full[kHrStages], s_empty[kHrStages], s_tfull, s_tempty;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NB = a.NB, NL = a.NL, C = a.C;
+  const int NB = a.NB, C = a.C;
   const int stage_bytes = hrtf_stage_bytes(NB, NL);
   const int xrow = (NB + 4) * 16;                 // bytes of one (limb, kc) row group of a stage
   const int n_tiles = a.S * a.NT;
@@ -127,7 +129,7 @@ static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGe
   if (threadIdx.x == 0) {
     for (int i = 0; i < kHrStages; ++i) { hr::bar_init(&s_full[i], 1); hr::bar_init(&s_empty[i], 1); }
     hr::bar_init(&s_tfull, 1);
-    hr::bar_init(&s_tempty, 4);
+    hr::bar_init(&s_tempty, 4 * kHrEpiGroups);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -192,10 +194,13 @@ static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGe
       }
     }
   } else {
-    // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. : row R = 2 i + ear of every column (= block) of the tile
-    const int quarter = warp & 3;
+    // ===== epilogue: 16 warps = 4 column groups x 4 lane quarters (a warp reads the TMEM lanes 32 (warp % 4) .. only):
+    // row R = 2 i + ear of a quarter of the tile's columns (= blocks).  One warp per quarter took longer than the tile's
+    // MMAs (every warp is latency-bound on its own dependent instructions); sixteen bring the drain under a fifth of them
+    const int quarter = warp & 3, cg = (warp - 2) >> 2;
     const int R = quarter * 32 + lane, i = R >> 1, ear = R & 1;
     const float scale = __int_as_float((127 - (a.x_shift + 15)) << 23);   // 2^-(x_shift + 15)
+    const int cols = NB / kHrEpiGroups;                                   // columns of this warp (NB is a multiple of 16)
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int s = tile / a.NT, b0 = (tile - s * a.NT) * NB;
@@ -203,28 +208,60 @@ static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGe
       if (len <= b0 * kHrBlock) continue;
       hr::bar_wait(&s_tfull, tl & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // running (present-frame slot, offset inside it) of this row's instant in column n
-      int tau = b0 * kHrBlock + i;
-      int slot = tau / a.N, rem = tau - slot * a.N;
-      int f = (tau < len) ? a.frame_of_slot[(size_t)s * a.F + slot] : 0;
-      const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-      for (int n0 = 0; n0 < NB; n0 += 16) {
-        int32_t d[kHrMaxXLimbs + 1][16];
+      const short *fos = a.frame_of_slot + (size_t)s * a.F;
+      const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cg * cols);
+      // d0 + d1 2^8 + d2 2^16 (+ d3 2^24) exactly, as hi 2^16 + lo with hi = d2 + (d1 >> 8) (+ d3 2^8), lo = d0 + ((d1 & 255) << 8);
+      // int64 -> float32 rounds once
+      auto value = [&](const int32_t (&d)[NL + 1][16], int k) -> float {
+        const int lo = d[0][k] + ((d[1][k] & 255) << 8);
+        long long hi = (long long)(d[2][k] + (d[1][k] >> 8));
+        if constexpr (NL == 3) hi += (long long)d[3][k] << 8;
+        return (float)(hi * 65536 + (long long)lo) * scale;
+      };
+      if ((a.N & (kHrBlock - 1)) == 0) {
+        // frames of whole blocks: a column lies in one frame for every row - the frame walk is warp-uniform
+        const int bpf = a.N / kHrBlock;                                   // blocks per frame
+        int col = b0 + cg * cols;                                          // block index on the stream's time line
+        int slot = col / bpf, brem = col - slot * bpf;
+        const int nblk = len / kHrBlock;
+        float *fbase = a.out + (((size_t)s * a.F + (col < nblk ? fos[slot] : 0)) * 2 + ear) * a.N + i;
+        for (int n0 = 0; n0 < cols; n0 += 16) {
+          int32_t d[NL + 1][16];
 #pragma unroll
-        for (int cls = 0; cls < kHrMaxXLimbs + 1; ++cls)
-          if (cls <= NL) hr::tmem_ld16(lane_base + (uint32_t)(cls * NB + n0), d[cls]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int cls = 0; cls <= NL; ++cls) hr::tmem_ld16(lane_base + (uint32_t)(cls * NB + n0), d[cls]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          long long v = (long long)d[0][k] + ((long long)d[1][k] << 8) + ((long long)d[2][k] << 16);
-          if (NL == 3) v += (long long)d[3][k] << 24;
-          if (tau < len) a.out[(((size_t)s * a.F + f) * 2 + ear) * a.N + rem] = (float)v * scale;
-          tau += kHrBlock;
-          rem += kHrBlock;
-          if (rem >= a.N) {
-            rem -= a.N;
-            ++slot;
-            if (tau < len) f = a.frame_of_slot[(size_t)s * a.F + slot];
+          for (int k = 0; k < 16; ++k) {
+            if (col < nblk) fbase[brem * kHrBlock] = value(d, k);
+            ++col;
+            if (++brem == bpf) {
+              brem = 0;
+              ++slot;
+              fbase = a.out + (((size_t)s * a.F + (col < nblk ? fos[slot] : 0)) * 2 + ear) * a.N + i;
+            }
+          }
+        }
+      } else {
+        // any frame size (a multiple of 16): every row walks the frames on its own
+        int tau = (b0 + cg * cols) * kHrBlock + i;
+        int slot = tau / a.N, rem = tau - slot * a.N;
+        float *dst = a.out + (((size_t)s * a.F + (tau < len ? fos[slot] : 0)) * 2 + ear) * a.N + rem;
+        for (int n0 = 0; n0 < cols; n0 += 16) {
+          int32_t d[NL + 1][16];
+#pragma unroll
+          for (int cls = 0; cls <= NL; ++cls) hr::tmem_ld16(lane_base + (uint32_t)(cls * NB + n0), d[cls]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            if (tau < len) *dst = value(d, k);
+            tau += kHrBlock;
+            rem += kHrBlock;
+            dst += kHrBlock;
+            if (rem >= a.N) {             // next present frame
+              rem -= a.N;
+              ++slot;
+              dst = a.out + (((size_t)s * a.F + (tau < len ? fos[slot] : 0)) * 2 + ear) * a.N + rem;
+            }
           }
         }
       }

@@ -20,7 +20,7 @@ int main(int argc, char **argv) {
   const int N = 960, T = F * N;
   const int x_bits = NL == 2 ? 16 : 24, x_shift = NL == 2 ? 15 : 20;
   int NB = (T + 63) / 64;
-  NB = (NB + 15) & ~15;
+  NB = (NB + 63) & ~63;
   if (NB > kHrMaxNB) NB = kHrMaxNB;
   const int NT = (T + NB * 64 - 1) / (NB * 64), NBP = 4 + NT * NB;
   printf("S %d C %d F %d NL %d  NB %d NT %d NBP %d\n", S, C, F, NL, NB, NT, NBP);
@@ -65,12 +65,13 @@ int main(int argc, char **argv) {
   a.tab = d_tab; a.planes = d_planes; a.out = d_out; a.n_present = d_np; a.frame_of_slot = d_fos;
   a.S = S; a.C = C; a.NL = NL; a.NB = NB; a.NT = NT; a.NBP = NBP; a.F = F; a.N = N; a.x_shift = x_shift;
   const int smem = kHrStages * hrtf_stage_bytes(NB, NL);
-  CK(cudaFuncSetAttribute(k_hrtf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  auto kern = NL == 2 ? k_hrtf_gemm<2> : k_hrtf_gemm<3>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const int grid = S * NT < sms ? S * NT : sms;
   printf("smem %d grid %d\n", smem, grid);
-  k_hrtf_gemm<<<grid, kHrThreads, smem>>>(a);
+  kern<<<grid, kHrThreads, smem>>>(a);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> out((size_t)S * F * 2 * N);
@@ -102,10 +103,10 @@ int main(int argc, char **argv) {
   // timing
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 3; ++i) k_hrtf_gemm<<<grid, kHrThreads, smem>>>(a);
+  for (int i = 0; i < 3; ++i) kern<<<grid, kHrThreads, smem>>>(a);
   cudaEventRecord(e0);
   const int reps = 20;
-  for (int i = 0; i < reps; ++i) k_hrtf_gemm<<<grid, kHrThreads, smem>>>(a);
+  for (int i = 0; i < reps; ++i) kern<<<grid, kHrThreads, smem>>>(a);
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms = 0;
