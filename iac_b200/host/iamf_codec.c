@@ -35,6 +35,46 @@ static int rd24be_ref(const uint8_t *p) { return ((int)((uint32_t)((p[0] | p[1] 
 static int rd32le(const uint8_t *p) { return (int)((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24); }
 static int rd32be(const uint8_t *p) { return (int)((uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | (uint32_t)p[3]); }
 
+/* 16-bit little-endian linear PCM handed on as it is: planar int16 (the engine scales by 1/32768, IAMFB_IN_S16).  Mono
+ * sub-streams are one memcpy, coupled ones a de-interleave */
+static int pcm_decode_s16(const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size, int n_sub, int n_coupled,
+                          int16_t *out, int frame_size) {
+  const int le = cc->conf[0] != 0;
+  if (n_sub <= 0 || cc->conf[1] != 16) return IAMF_ERR_BAD_ARG;
+  const int samples = n_coupled ? (int)(pkt_size[0] / 4) : (int)(pkt_size[0] / 2);
+  for (int c = 0; c < n_sub; ++c)
+    if ((c < n_coupled ? (int)(pkt_size[c] / 4) : (int)(pkt_size[c] / 2)) != samples) return IAMF_ERR_INTERNAL;
+  if (samples > frame_size) return IAMF_ERR_INTERNAL;
+  int ch = 0;
+  for (int c = 0; c < n_sub; ++c) {
+    const uint8_t *p = pkt[c];
+    if (c < n_coupled) {
+      int16_t *l = out + (size_t)samples * ch, *r = l + samples;
+      if (le) {
+        for (int s = 0; s < samples; ++s) {
+          int16_t v[2];
+          memcpy(v, p + 4 * s, 4);
+          l[s] = v[0];
+          r[s] = v[1];
+        }
+      } else {
+        for (int s = 0; s < samples; ++s) {
+          l[s] = (int16_t)(p[4 * s] << 8 | p[4 * s + 1]);
+          r[s] = (int16_t)(p[4 * s + 2] << 8 | p[4 * s + 3]);
+        }
+      }
+      ch += 2;
+    } else {
+      int16_t *d = out + (size_t)samples * ch;
+      if (le) memcpy(d, p, (size_t)samples * 2);
+      else
+        for (int s = 0; s < samples; ++s) d[s] = (int16_t)(p[2 * s] << 8 | p[2 * s + 1]);
+      ch += 1;
+    }
+  }
+  return samples;
+}
+
 static int pcm_decode(const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size, int n_sub, int n_coupled,
                       float *out, int frame_size) {
   const int le = cc->conf[0] != 0, bits = cc->conf[1];
@@ -71,7 +111,7 @@ static int pcm_decode(const ih_codec *cc, uint8_t *const *pkt, const uint32_t *p
 /* one OpusDecoder per sub-stream (stereo for coupled ones), int16 output scaled by 1/32768 like
  * opus/IAMF_opus_decoder.c:119-138; coupled sub-streams first, planar output (opus_multistream2_decoder.c:125-165) */
 static int opus_decode_group(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size,
-                             int n_sub, int n_coupled, float *out, int frame_size) {
+                             int n_sub, int n_coupled, float *out, int16_t *out16, int frame_size) {
   short buf[2 * 5760];
   int ch = 0, samples = 0;
   if (frame_size > 5760) return IAMF_ERR_BAD_ARG;
@@ -88,8 +128,12 @@ static int opus_decode_group(ih_stream *st, int first_sub, const ih_codec *cc, u
     if (n < 0) return IAMF_ERR_INTERNAL;
     if (c && n != samples) return IAMF_ERR_INTERNAL;
     samples = n;
-    for (int k = 0; k < nch; ++k)
-      for (int s = 0; s < n; ++s) out[(size_t)n * (ch + k) + s] = buf[s * nch + k] / 32768.f;
+    for (int k = 0; k < nch; ++k) {
+      if (out16)
+        for (int s = 0; s < n; ++s) out16[(size_t)n * (ch + k) + s] = buf[s * nch + k];
+      else
+        for (int s = 0; s < n; ++s) out[(size_t)n * (ch + k) + s] = buf[s * nch + k] / 32768.f;
+    }
     ch += nch;
   }
   return samples;
@@ -110,7 +154,26 @@ int ih_codec_decode(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *c
   (void)st; (void)first_sub;
   if (cc->codec == IAMF_CODEC_PCM) return pcm_decode(cc, pkt, pkt_size, n_sub, n_coupled, out, frame_size);
 #ifdef IH_HAVE_OPUS
-  if (cc->codec == IAMF_CODEC_OPUS) return opus_decode_group(st, first_sub, cc, pkt, pkt_size, n_sub, n_coupled, out, frame_size);
+  if (cc->codec == IAMF_CODEC_OPUS) return opus_decode_group(st, first_sub, cc, pkt, pkt_size, n_sub, n_coupled, out, 0, frame_size);
+#endif
+  return IAMF_ERR_UNIMPLEMENTED;
+}
+
+/* core decode produces 16-bit samples for this codec configuration (Opus; 16-bit linear PCM): they can be handed to the
+ * engine as int16 (IAMFB_IN_S16) instead of the float scaling of opus/IAMF_opus_decoder.c:133-135, pcm/IAMF_pcm_decoder.c */
+int ih_codec_is_s16(const ih_codec *cc) {
+#ifdef IH_HAVE_OPUS
+  if (cc->codec == IAMF_CODEC_OPUS) return 1;
+#endif
+  return cc->codec == IAMF_CODEC_PCM && cc->conf[1] == 16;
+}
+
+int ih_codec_decode_s16(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size, int n_sub,
+                        int n_coupled, int16_t *out, int frame_size) {
+  (void)st; (void)first_sub;
+  if (cc->codec == IAMF_CODEC_PCM) return pcm_decode_s16(cc, pkt, pkt_size, n_sub, n_coupled, out, frame_size);
+#ifdef IH_HAVE_OPUS
+  if (cc->codec == IAMF_CODEC_OPUS) return opus_decode_group(st, first_sub, cc, pkt, pkt_size, n_sub, n_coupled, 0, out, frame_size);
 #endif
   return IAMF_ERR_UNIMPLEMENTED;
 }

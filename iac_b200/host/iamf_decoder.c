@@ -137,13 +137,12 @@ static void engine_release(IAMF_DecoderHandle h) {
     iamfb_host_free(h->pcm_stage);
     iamfb_host_free(h->fp_stage);
     iamfb_host_free(h->counts_stage);
-    free(h->grp_flags);
   }
-  h->grp_flags = 0;
   h->batch = 0; h->plan = 0; h->ctx = 0;
   for (int e = 0; e < IAMFB_MAX_ELEMENTS; ++e) h->in[e] = h->ramp[e] = 0;
   h->out_ramp = 0; h->pcm_stage = 0; h->fp_stage = 0; h->counts_stage = 0;
   h->group_owner = 1; h->group_size = 1; h->group_index = 0; h->leader = 0;
+  h->group_units = 0; h->group_s16 = 0;
 }
 
 static void db_reset(IAMF_DecoderHandle h) {
@@ -804,7 +803,7 @@ static uint32_t parse_obus(IAMF_DecoderHandle h, const uint8_t *data, uint32_t s
 /* Host part of one temporal unit: core decode of every element into `in[e]`, per-frame parameters into *fp.
  * returns >0 frame ready (samples entering the engine after trimming), 0 dropped / nothing, <0 error.
  * (the loop body of iamf_decoder_internal_decode, IAMF_decoder.c:3336-3457, up to where samples are touched) */
-static int prepare_frame(IAMF_DecoderHandle h, float *const in[], iamfb_frame_params *fp, float *const ramp[], float *out_ramp,
+static int prepare_frame(IAMF_DecoderHandle h, void *const in[], int s16, iamfb_frame_params *fp, float *const ramp[], float *out_ramp,
                          int *use_ramp, int *use_out_ramp) {
   const int N = h->frame_size;
   int lret = 1, real = 0;
@@ -826,13 +825,15 @@ static int prepare_frame(IAMF_DecoderHandle h, float *const in[], iamfb_frame_pa
       ret = 0;
       for (int l = 0; l <= st->layer; ++l) {
         const ih_layer *ly = &el->layers[l];
-        ret = ih_codec_decode(st, sub, st->cc, &st->pkt[sub], &st->pkt_size[sub], ly->n_sub, ly->n_coupled, in[s] + (size_t)ch * N, N);
+        ret = s16 ? ih_codec_decode_s16(st, sub, st->cc, &st->pkt[sub], &st->pkt_size[sub], ly->n_sub, ly->n_coupled, (int16_t *)in[s] + (size_t)ch * N, N)
+                  : ih_codec_decode(st, sub, st->cc, &st->pkt[sub], &st->pkt_size[sub], ly->n_sub, ly->n_coupled, (float *)in[s] + (size_t)ch * N, N);
         if (ret < 0) break;
         sub += ly->n_sub;
         ch += ly->n_sub + ly->n_coupled;
       }
     } else {
-      ret = ih_codec_decode(st, 0, st->cc, st->pkt, st->pkt_size, el->ambi_sub, el->ambi_coupled, in[s], N);
+      ret = s16 ? ih_codec_decode_s16(st, 0, st->cc, st->pkt, st->pkt_size, el->ambi_sub, el->ambi_coupled, (int16_t *)in[s], N)
+                : ih_codec_decode(st, 0, st->cc, st->pkt, st->pkt_size, el->ambi_sub, el->ambi_coupled, (float *)in[s], N);
     }
     for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k) { free(st->pkt[k]); st->pkt[k] = 0; st->pkt_size[k] = 0; }
     st->pkt_count = 0;
@@ -906,7 +907,8 @@ int IAMF_decoder_decode(IAMF_DecoderHandle h, const uint8_t *data, int32_t size,
     if (h->status == IH_STATUS_RECONFIGURE) return IAMF_ERR_INVALID_STATE;
     if (h->status != IH_STATUS_RUN) return 0;
     int use_ramp[IAMFB_MAX_ELEMENTS], use_out_ramp = 0;
-    int ready = prepare_frame(h, h->in, h->fp_stage, h->ramp, h->out_ramp, use_ramp, &use_out_ramp);
+    void *inp[IAMFB_MAX_ELEMENTS] = {h->in[0], h->in[1]};
+    int ready = prepare_frame(h, inp, 0, h->fp_stage, h->ramp, h->out_ramp, use_ramp, &use_out_ramp);
     iamfb_io io;
     memset(&io, 0, sizeof(io));
     for (int e = 0; e < h->n_streams; ++e) {
@@ -950,35 +952,111 @@ static int same_signature(const IAMF_DecoderHandle a, const IAMF_DecoderHandle b
   return memcmp(&a->desc, &b->desc, sizeof(a->desc)) == 0;
 }
 
-static int group_build(IAMF_DecoderHandle *hs, int n) {
+/* ---- a small pool of host threads for the per-handle part of a batch step (bitstream parsing + core decode of the
+ * handles are independent of each other; they write disjoint slots of the group's pinned buffers) */
+#include <pthread.h>
+#include <unistd.h>
+typedef struct {
+  pthread_mutex_t mu;
+  pthread_cond_t cv_work, cv_done;
+  pthread_t th[64];
+  int n_threads, started;
+  unsigned long gen;
+  void (*fn)(void *, int);
+  void *arg;
+  int next, total, pending;
+} ih_pool;
+static ih_pool g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER};
+static pthread_mutex_t g_pool_call = PTHREAD_MUTEX_INITIALIZER;   /* one parallel-for at a time */
+
+static void pool_drain(ih_pool *p) {   /* called with p->mu held */
+  while (p->next < p->total) {
+    const int lo = p->next;
+    int hi = lo + 4;                   /* a few handles per grab */
+    if (hi > p->total) hi = p->total;
+    p->next = hi;
+    pthread_mutex_unlock(&p->mu);
+    for (int i = lo; i < hi; ++i) p->fn(p->arg, i);
+    pthread_mutex_lock(&p->mu);
+    p->pending -= hi - lo;
+  }
+}
+static void *pool_worker(void *v) {
+  ih_pool *p = (ih_pool *)v;
+  unsigned long seen = 0;
+  pthread_mutex_lock(&p->mu);
+  for (;;) {
+    while (p->gen == seen) pthread_cond_wait(&p->cv_work, &p->mu);
+    seen = p->gen;
+    pool_drain(p);
+    if (p->pending == 0) pthread_cond_signal(&p->cv_done);
+  }
+  return 0;
+}
+static void pool_for(int total, void (*fn)(void *, int), void *arg) {
+  ih_pool *p = &g_pool;
+  int want = 1;
+  const char *env = getenv("IAMF_B200_HOST_THREADS");
+  if (env) want = atoi(env);
+  else {
+    long nc = sysconf(_SC_NPROCESSORS_ONLN);
+    want = nc > 1 ? (int)nc : 1;
+  }
+  if (want > 64) want = 64;
+  if (want <= 1 || total < 8) {
+    for (int i = 0; i < total; ++i) fn(arg, i);
+    return;
+  }
+  pthread_mutex_lock(&g_pool_call);
+  pthread_mutex_lock(&p->mu);
+  while (p->started < want - 1) {      /* the calling thread works too */
+    if (pthread_create(&p->th[p->started], 0, pool_worker, p) != 0) break;
+    pthread_detach(p->th[p->started]);
+    ++p->started;
+  }
+  p->fn = fn; p->arg = arg; p->next = 0; p->total = total; p->pending = total;
+  ++p->gen;
+  pthread_cond_broadcast(&p->cv_work);
+  pool_drain(p);
+  while (p->pending > 0) pthread_cond_wait(&p->cv_done, &p->mu);
+  pthread_mutex_unlock(&p->mu);
+  pthread_mutex_unlock(&g_pool_call);
+}
+
+static int group_build(IAMF_DecoderHandle *hs, int n, int units) {
   IAMF_DecoderHandle L = hs[0];
+  int s16 = 1;
   for (int i = 0; i < n; ++i) {
     if (!hs[i] || hs[i]->status != IH_STATUS_RECEIVE || !hs[i]->plan) return IAMF_ERR_INVALID_STATE;
     if (!same_signature(L, hs[i])) return IAMF_ERR_BAD_ARG;
     if (hs[i]->duration || hs[i]->leader) return IAMF_ERR_INVALID_STATE; /* group before the first decode call */
+    for (int e = 0; e < hs[i]->n_streams; ++e)
+      if (!ih_codec_is_s16(hs[i]->streams[e].cc)) s16 = 0;
   }
   /* the leader's context / plan serve the whole group; every member's private single-stream engine is released */
-  const size_t N = (size_t)L->frame_size;
+  const size_t N = (size_t)L->frame_size, F = (size_t)units;
+  const size_t esz = s16 ? sizeof(int16_t) : sizeof(float);
   iamfb_batch *gb = 0;
-  if (iamfb_batch_create(L->plan, n, 1, &gb) != IAMFB_OK) return IAMF_ERR_INTERNAL;
+  if (iamfb_batch_create(L->plan, n, units, &gb) != IAMFB_OK) return IAMF_ERR_INTERNAL;
   iamfb_batch_destroy(L->batch);
   L->batch = gb;
   for (int e = 0; e < L->n_streams; ++e) {
     iamfb_host_free(L->in[e]); iamfb_host_free(L->ramp[e]);
-    L->in[e] = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)L->desc.el[e].n_in * (size_t)n);
-    L->ramp[e] = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)n);
+    L->in[e] = (float *)iamfb_host_alloc(esz * N * (size_t)L->desc.el[e].n_in * (size_t)n * F);
+    L->ramp[e] = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)n * F);
     if (!L->in[e] || !L->ramp[e]) return IAMF_ERR_ALLOC_FAIL;
   }
   iamfb_host_free(L->out_ramp); iamfb_host_free(L->pcm_stage); iamfb_host_free(L->fp_stage); iamfb_host_free(L->counts_stage);
-  L->out_ramp = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)n);
+  L->pcm_stage_size = iamfb_plan_out_stride_bytes(L->plan, units);
+  L->out_ramp = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)n * F);
   L->pcm_stage = (uint8_t *)iamfb_host_alloc(L->pcm_stage_size * (size_t)n);
-  L->fp_stage = (iamfb_frame_params *)iamfb_host_alloc(sizeof(iamfb_frame_params) * (size_t)n);
-  L->counts_stage = (int32_t *)iamfb_host_alloc(sizeof(int32_t) * (size_t)n);
-  free(L->grp_flags);
-  L->grp_flags = (uint8_t *)calloc((size_t)n, 1);
-  if (!L->out_ramp || !L->pcm_stage || !L->fp_stage || !L->counts_stage || !L->grp_flags) return IAMF_ERR_ALLOC_FAIL;
+  L->fp_stage = (iamfb_frame_params *)iamfb_host_alloc(sizeof(iamfb_frame_params) * (size_t)n * F);
+  L->counts_stage = (int32_t *)iamfb_host_alloc(sizeof(int32_t) * (size_t)n * F);
+  if (!L->out_ramp || !L->pcm_stage || !L->fp_stage || !L->counts_stage) return IAMF_ERR_ALLOC_FAIL;
   L->group_size = n;
   L->group_index = 0;
+  L->group_units = units;
+  L->group_s16 = s16;
   for (int i = 1; i < n; ++i) {
     engine_release(hs[i]);
     hs[i]->group_owner = 0;
@@ -990,65 +1068,98 @@ static int group_build(IAMF_DecoderHandle *hs, int n) {
   return IAMF_OK;
 }
 
-int IAMF_decoder_decode_batch(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
-                              void *const *pcm, int *ret) {
-  if (!hs || n <= 0 || !data || !size || !ret || !hs[0]) return IAMF_ERR_BAD_ARG;
+typedef struct {
+  IAMF_DecoderHandle *hs;
+  const uint8_t *const *data;
+  const int32_t *size;
+  int units;
+} ih_step_job;
+
+/* phase 1 of a batch step for handle i: its temporal units of this call, parsed and core-decoded into the handle's slots
+ * [i][f] of the group's pinned buffers */
+static void step_handle(void *v, int i) {
+  const ih_step_job *job = (const ih_step_job *)v;
+  IAMF_DecoderHandle h = job->hs[i], L = job->hs[0];
+  const size_t N = (size_t)L->frame_size;
+  const int F = job->units, s16 = L->group_s16;
+  const size_t esz = s16 ? sizeof(int16_t) : sizeof(float);
+  uint32_t pos = 0;
+  h->unit_used = 0;
+  h->units_done = 0;
+  for (int f = 0; f < F; ++f) {
+    iamfb_frame_params *fp = &L->fp_stage[(size_t)i * F + f];
+    memset(fp, 0, sizeof(*fp));
+    fp->trim_start = 0xFFFF; /* "no frame for this stream in this step": the engine leaves its state untouched */
+    h->unit_ret[f] = 0;
+    h->unit_flags[f] = 0;
+  }
+  if (h->status != IH_STATUS_RECEIVE) { h->unit_ret[0] = IAMF_ERR_INVALID_STATE; return; }
+  for (int f = 0; f < F && pos < (uint32_t)job->size[i]; ++f) {
+    iamfb_frame_params *fp = &L->fp_stage[(size_t)i * F + f];
+    void *in[IAMFB_MAX_ELEMENTS] = {0, 0};
+    float *ramp[IAMFB_MAX_ELEMENTS] = {0, 0};
+    for (int e = 0; e < L->n_streams; ++e) {
+      in[e] = (uint8_t *)L->in[e] + ((size_t)i * F + f) * N * (size_t)L->desc.el[e].n_in * esz;
+      ramp[e] = L->ramp[e] + ((size_t)i * F + f) * N;
+    }
+    int run = 0, use_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, use_out = 0;
+    uint32_t used = parse_obus(h, job->data[i] + pos, (uint32_t)job->size[i] - pos, &run);
+    pos += used;
+    h->unit_used = pos;
+    if (h->status == IH_STATUS_RECONFIGURE) { h->unit_ret[f] = IAMF_ERR_INVALID_STATE; break; }
+    if (h->status != IH_STATUS_RUN) break;      /* the buffer ended inside a temporal unit: the rest comes with the next call */
+    int ready = prepare_frame(h, in, s16, fp, ramp, L->out_ramp + ((size_t)i * F + f) * N, use_ramp, &use_out);
+    h->status = IH_STATUS_RECEIVE;
+    ++h->units_done;
+    if (ready < 0) { h->unit_ret[f] = ready; fp->trim_start = 0xFFFF; continue; }
+    if (ready == 0) { fp->trim_start = (uint16_t)N; fp->trim_end = 0; }
+    h->unit_ret[f] = ready > 0 ? 1 : 0;
+    h->unit_flags[f] = (uint8_t)((use_ramp[0] ? 1 : 0) | (use_ramp[1] ? 2 : 0) | (use_out ? 4 : 0));
+    if (!used) break;
+  }
+}
+
+int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
+                                    void *const *pcm, int *ret, int max_units, int *units_done) {
+  if (!hs || n <= 0 || !data || !size || !ret || !hs[0] || max_units < 1 || max_units > 64) return IAMF_ERR_BAD_ARG;
   IAMF_DecoderHandle L = hs[0];
-  if (L->group_size != n || L->leader) {
-    if (L->group_size > 1 || L->leader) return IAMF_ERR_INVALID_STATE; /* group membership is fixed */
-    int rc = group_build(hs, n);
+  if (L->group_size != n || L->leader || L->group_units != max_units) {
+    if (L->group_size > 1 || L->leader) return IAMF_ERR_INVALID_STATE; /* group membership and step size are fixed */
+    int rc = group_build(hs, n, max_units);
     if (rc != IAMF_OK) return rc;
   }
   for (int i = 1; i < n; ++i)
     if (!hs[i] || hs[i]->leader != L || hs[i]->group_index != i) return IAMF_ERR_BAD_ARG;
   const size_t N = (size_t)L->frame_size;
+  const int F = max_units;
   int n_flush = 0, any_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, any_out_ramp = 0;
   for (int i = 0; i < n; ++i) n_flush += data[i] ? 0 : 1;
   if (n_flush && n_flush != n) return IAMF_ERR_UNIMPLEMENTED; /* a group flushes together */
   if (n_flush) {
     if (iamfb_batch_flush_host(L->batch, L->pcm_stage, L->counts_stage) != IAMFB_OK) return IAMF_ERR_INTERNAL;
   } else {
-    /* phase 1 (host, per handle): parse, core decode into the handle's slot of the shared pinned buffers */
-    for (int i = 0; i < n; ++i) {
-      IAMF_DecoderHandle h = hs[i];
-      iamfb_frame_params *fp = &L->fp_stage[i];
-      float *in[IAMFB_MAX_ELEMENTS] = {0, 0}, *ramp[IAMFB_MAX_ELEMENTS] = {0, 0};
-      for (int e = 0; e < L->n_streams; ++e) {
-        in[e] = L->in[e] + (size_t)i * N * (size_t)L->desc.el[e].n_in;
-        ramp[e] = L->ramp[e] + (size_t)i * N;
+    /* phase 1 (host, per handle, on the pool): parse, core decode into the handle's slots of the shared pinned buffers */
+    ih_step_job job = {hs, data, size, F};
+    pool_for(n, step_handle, &job);
+    for (int i = 0; i < n; ++i)
+      for (int f = 0; f < F; ++f) {
+        const int fl = hs[i]->unit_flags[f];
+        any_ramp[0] |= fl & 1; any_ramp[1] |= (fl >> 1) & 1; any_out_ramp |= (fl >> 2) & 1;
       }
-      int run = 0, use_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, use_out = 0;
-      ret[i] = 0;
-      if (rsize) rsize[i] = 0;
-      memset(fp, 0, sizeof(*fp));
-      fp->trim_start = 0xFFFF; /* "no frame for this stream in this step": the engine leaves its state untouched */
-      L->grp_flags[i] = 0;
-      if (h->status != IH_STATUS_RECEIVE) { ret[i] = IAMF_ERR_INVALID_STATE; continue; }
-      uint32_t used = parse_obus(h, data[i], (uint32_t)size[i], &run);
-      if (rsize) rsize[i] = used;
-      if (h->status == IH_STATUS_RECONFIGURE) { ret[i] = IAMF_ERR_INVALID_STATE; continue; }
-      if (h->status != IH_STATUS_RUN) continue;
-      int ready = prepare_frame(h, in, fp, ramp, L->out_ramp + (size_t)i * N, use_ramp, &use_out);
-      h->status = IH_STATUS_RECEIVE;
-      if (ready < 0) { ret[i] = ready; fp->trim_start = 0xFFFF; continue; }
-      if (ready == 0) { fp->trim_start = (uint16_t)N; fp->trim_end = 0; }
-      ret[i] = ready > 0 ? 1 : 0; /* replaced by the sample count below */
-      for (int e = 0; e < L->n_streams; ++e) any_ramp[e] |= use_ramp[e];
-      any_out_ramp |= use_out;
-      L->grp_flags[i] = (uint8_t)((use_ramp[0] ? 1 : 0) | (use_ramp[1] ? 2 : 0) | (use_out ? 4 : 0));
-    }
     /* a ramp array applies to the whole group: members with a constant gain get a constant ramp (a constant the
      * reference would skip - exactly 1 or not positive, IAMF_decoder.c:1392 - becomes 1.0, which is exact) */
     for (int e = 0; e <= L->n_streams; ++e) {
       const int out = e == L->n_streams;
       if (!(out ? any_out_ramp : any_ramp[e])) continue;
-      for (int i = 0; i < n; ++i) {
-        if (L->grp_flags[i] & (out ? 4 : (1 << e))) continue;
-        float g = out ? L->fp_stage[i].out_gain : L->fp_stage[i].el[e].mix_gain;
-        if (!(g != 1.f && g > 0.f)) g = 1.f;
-        float *dst = (out ? L->out_ramp : L->ramp[e]) + (size_t)i * N;
-        for (size_t k = 0; k < N; ++k) dst[k] = g;
-      }
+      for (int i = 0; i < n; ++i)
+        for (int f = 0; f < F; ++f) {
+          if (hs[i]->unit_flags[f] & (out ? 4 : (1 << e))) continue;
+          const iamfb_frame_params *fp = &L->fp_stage[(size_t)i * F + f];
+          float g = out ? fp->out_gain : fp->el[e].mix_gain;
+          if (!(g != 1.f && g > 0.f)) g = 1.f;
+          float *dst = (out ? L->out_ramp : L->ramp[e]) + ((size_t)i * F + f) * N;
+          for (size_t k = 0; k < N; ++k) dst[k] = g;
+        }
     }
     /* phase 2 (device, once for the group) */
     iamfb_io io;
@@ -1058,21 +1169,39 @@ int IAMF_decoder_decode_batch(IAMF_DecoderHandle *hs, int n, const uint8_t *cons
       if (any_ramp[e]) io.gain_ramp[e] = L->ramp[e];
     }
     if (any_out_ramp) io.out_gain_ramp = L->out_ramp;
+    io.in_format = L->group_s16 ? IAMFB_IN_S16 : IAMFB_IN_F32;
     io.params = L->fp_stage;
     io.pcm = L->pcm_stage;
     io.out_counts = L->counts_stage;
-    if (iamfb_batch_submit_host(L->batch, &io, 1) != IAMFB_OK) return IAMF_ERR_INTERNAL;
+    if (iamfb_batch_submit_host(L->batch, &io, F) != IAMFB_OK) return IAMF_ERR_INTERNAL;
   }
-  /* phase 3: hand every stream's samples back */
+  /* phase 3: hand every stream's samples back (the frames of a stream lie back to back in its row of the PCM buffer) */
   for (int i = 0; i < n; ++i) {
     IAMF_DecoderHandle h = hs[i];
-    if (!n_flush && ret[i] <= 0) continue;
-    const int real = L->counts_stage[i];
-    if (real > 0 && pcm && pcm[i] && h->bit_depth)
-      memcpy(pcm[i], L->pcm_stage + (size_t)i * L->pcm_stage_size, pcm_bytes(h, real));
+    if (rsize) rsize[i] = n_flush ? 0 : h->unit_used;
+    if (units_done) units_done[i] = n_flush ? 0 : h->units_done;
+    int real = 0, err = 0;
+    if (n_flush) real = L->counts_stage[i];
+    else
+      for (int f = 0; f < F; ++f) {
+        if (h->unit_ret[f] < 0 && !err) err = h->unit_ret[f];
+        if (h->unit_ret[f] > 0) {
+          const int c = L->counts_stage[(size_t)i * F + f];
+          real += c;
+          h->last_frame_size = c;
+        }
+      }
+    /* (a flush returns its rows at the pitch of a one-frame submit) */
+    const size_t pitch = n_flush ? iamfb_plan_out_stride_bytes(L->plan, 1) : L->pcm_stage_size;
+    if (real > 0 && pcm && pcm[i] && h->bit_depth) memcpy(pcm[i], L->pcm_stage + (size_t)i * pitch, pcm_bytes(h, real));
     h->duration += (uint64_t)real;
-    h->last_frame_size = real;
-    ret[i] = real;
+    if (n_flush) h->last_frame_size = real;
+    ret[i] = (real == 0 && err) ? err : real;
   }
   return IAMF_OK;
+}
+
+int IAMF_decoder_decode_batch(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
+                              void *const *pcm, int *ret) {
+  return IAMF_decoder_decode_batch_units(hs, n, data, size, rsize, pcm, ret, 1, 0);
 }

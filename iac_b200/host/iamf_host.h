@@ -205,11 +205,16 @@ struct IAMF_Decoder {
   size_t pcm_stage_size;               /* bytes per stream */
   iamfb_frame_params *fp_stage;
   int32_t *counts_stage;
-  uint8_t *grp_flags;                  /* group leader: per member, which gain ramps it supplied this step */
   int frame_size;
   /* batch extension: handles stepping together share the engine of the group leader */
   struct IAMF_Decoder *leader;
   int group_owner, group_size, group_index;
+  int group_units;                     /* leader: temporal units per handle and call the group's buffers are sized for */
+  int group_s16;                       /* leader: the group's decoded frames travel as int16 (IAMFB_IN_S16) */
+  int unit_ret[64];                    /* decode_batch_units scratch: per unit of this handle, what prepare_frame returned */
+  uint8_t unit_flags[64];
+  uint32_t unit_used;                  /* bytes consumed by this call */
+  int units_done;
 };
 
 /* iamf_obu_parse.c */
@@ -239,6 +244,9 @@ int ih_codec_supported(int codec);
 /* decodes the packets of `n_sub` substreams (the first n_coupled are stereo) into planar float; returns samples */
 int ih_codec_decode(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size,
                     int n_sub, int n_coupled, float *out, int frame_size);
+int ih_codec_is_s16(const ih_codec *cc);
+int ih_codec_decode_s16(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size,
+                        int n_sub, int n_coupled, int16_t *out, int frame_size);
 void ih_codec_close(ih_stream *st);
 
 #endif

@@ -152,6 +152,15 @@ int IAMF_decoder_get_last_metadata(IAMF_DecoderHandle handle, int64_t *pts, IAMF
 int IAMF_decoder_decode_batch(IAMF_DecoderHandle *handles, int n, const uint8_t *const *data, const int32_t *size,
                               uint32_t *rsize, void *const *pcm, int *ret);
 
+/* The same for up to max_units (1..64) temporal units per handle and call: data[i]/size[i] holds whole temporal units of
+ * handle i back to back (what is left after max_units, or an incomplete last unit, is not consumed: rsize[i] tells);
+ * pcm[i] receives the units' samples back to back; ret[i] = samples per channel written for handle i (or the error of
+ * its first unit when nothing was written); units_done[i] (optional) = temporal units consumed.  The host part of every
+ * handle (parsing, core decode) runs on a pool of host threads (IAMF_B200_HOST_THREADS, default: the online cores), the
+ * device part once for the whole group.  The first call fixes the group and max_units. */
+int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *handles, int n, const uint8_t *const *data, const int32_t *size,
+                                    uint32_t *rsize, void *const *pcm, int *ret, int max_units, int *units_done);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,29 @@ class Api:
         L.IAMF_decoder_set_pts.argtypes = [vp, C.c_int64, C.c_uint32]
         self.L = L
 
+    def open_configured(self, blob, sound_system=0, binaural=False, bit_depth=16, rate=0, loudness=0.0, limiter=True,
+                        threshold_db=-1.0):
+        """a handle taken through the player's set-up calls and IAMF_decoder_configure (blob = descriptors + first unit)"""
+        L = self.L
+        h = L.IAMF_decoder_open()
+        assert h
+        L.IAMF_decoder_peak_limiter_set_threshold(h, threshold_db)
+        L.IAMF_decoder_set_normalization_loudness(h, loudness)
+        L.IAMF_decoder_set_bit_depth(h, bit_depth)
+        if not limiter:
+            L.IAMF_decoder_peak_limiter_enable(h, 0)
+        if rate:
+            L.IAMF_decoder_set_sampling_rate(h, rate)
+        if binaural:
+            L.IAMF_decoder_output_layout_set_binaural(h)
+        else:
+            L.IAMF_decoder_output_layout_set_sound_system(h, sound_system)
+        rsize = C.c_uint32(0)
+        L.IAMF_decoder_set_pts(h, 0, 90000)
+        ret = L.IAMF_decoder_configure(h, blob, len(blob), C.byref(rsize))
+        assert ret == 0, f"configure -> {ret}"
+        return h
+
     def render(self, descriptors, units, sound_system=0, binaural=False, bit_depth=16, rate=0, loudness=0.0,
                limiter=True, threshold_db=-1.0, flush=True):
         """returns (pcm ndarray [samples][channels], per-call sample counts)"""

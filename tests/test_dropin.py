@@ -218,3 +218,65 @@ def test_decode_batch_matches_per_handle_decode():
         assert counts[s] == single[s][1]
         assert b"".join(got[s]) == single[s][0].tobytes()
         L.IAMF_decoder_close(hs[s])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,n,F,K", [("c2", 21, 9, 4), ("c1", 40, 12, 5), ("c5", 10, 7, 3), ("c4", 9, 6, 6)])
+def test_decode_batch_units_matches_per_handle_decode(cfg, n, F, K):
+    """IAMF_decoder_decode_batch_units: K temporal units per handle and call, int16 ingest (16-bit ipcm), the host part on
+    the thread pool; buffers that end inside a temporal unit or hold fewer units than K; same bytes as one handle, one
+    unit at a time"""
+    sc, st, api_kw, unit_kw = refstreams.case(cfg)
+    inputs = S.synth_inputs(sc, n, F, seed=41)
+    P, _, _ = S.synth_params(sc, n, F, seed=42)
+    refstreams.no_param_gaps(sc, P)
+    desc = st.descriptors()
+    units = [refstreams.temporal_units(sc, st, inputs, P, unit_kw, s) for s in range(n)]
+    api = iamfapi.Api(LIBIAMF)
+    single = [api.render(desc, units[s], **api_kw) for s in range(n)]
+    L = api.L
+    vp = C.c_void_p
+    L.IAMF_decoder_decode_batch_units.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
+                                                  C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+    hs = (vp * n)()
+    ch = sc.out_channels
+    for s in range(n):
+        hs[s] = api.open_configured(desc + units[s][0], **api_kw)
+    bufs = [C.create_string_buffer(2 * 6144 * ch * K) for _ in range(n)]
+    pcm = (vp * n)(*[C.cast(b, vp) for b in bufs])
+    # every handle's stream as one byte string; handle s is fed in pieces that do not line up with its temporal units
+    blob = [b"".join(units[s]) for s in range(n)]
+    pos = [0] * n
+    got = [b"" for _ in range(n)]
+    total = [0] * n
+    rng = np.random.default_rng(7)
+    for _ in range(10 * F):
+        if all(pos[s] >= len(blob[s]) for s in range(n)):
+            break
+        piece = []
+        for s in range(n):
+            left = len(blob[s]) - pos[s]
+            take = left if s % 3 == 0 else min(left, int(rng.integers(1, 3 * len(units[s][0]))))
+            piece.append(blob[s][pos[s]: pos[s] + take])
+        data = (C.c_char_p * n)(*piece)
+        size = (C.c_int32 * n)(*[len(p) for p in piece])
+        rs = (C.c_uint32 * n)()
+        ret = (C.c_int * n)()
+        done = (C.c_int * n)()
+        assert L.IAMF_decoder_decode_batch_units(hs, n, data, size, rs, pcm, ret, K, done) == 0
+        for s in range(n):
+            assert ret[s] >= 0 and done[s] <= K
+            pos[s] += rs[s]
+            total[s] += ret[s]
+            got[s] += bufs[s].raw[: ret[s] * ch * 2]
+    # flush
+    data = (C.c_char_p * n)(*[None] * n)
+    size = (C.c_int32 * n)()
+    ret = (C.c_int * n)()
+    assert L.IAMF_decoder_decode_batch_units(hs, n, data, size, None, pcm, ret, K, None) == 0
+    for s in range(n):
+        got[s] += bufs[s].raw[: ret[s] * ch * 2]
+        assert pos[s] == len(blob[s])
+        assert total[s] + ret[s] == sum(c for c in single[s][1] if c > 0)
+        assert got[s] == single[s][0].tobytes(), f"handle {s}"
+        L.IAMF_decoder_close(hs[s])

@@ -185,3 +185,26 @@ def test_scan_quotient_exhaustive(thr_db):
         assert bad.value == 0, f"{bad.value} quotients differ from thr / w at thr = {thr}"
     finally:
         L.iamfb_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("s16", [False, True], ids=["f32", "s16"])
+@pytest.mark.parametrize("mk", [S.c2_714_to_B, S.c4_714_foa_binaural, S.c5_resample], ids=["c2", "c4", "c5"])
+def test_streams_without_frames_in_some_submits(mk, s16):
+    # handles of a group step through IAMF_decoder_decode_batch_units at their own pace: a stream may have no frame in the
+    # tail of a submit, or in a whole submit (also the last one before the flush) - its state must stay untouched
+    from gpu_harness import run_product
+    sc = mk(peak_db=(-3.0, 3.0))
+    n, F = 12, 9
+    inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 91)
+    P, ramps, oramp = S.synth_params(sc, n, F, seed=0x77 + 91)
+    P["trim_start"][1::3, 6:] = 0xFFFF          # nothing in the last submit
+    P["trim_start"][2::3, 3:6] = 0xFFFF         # nothing in the middle submit
+    P["trim_start"][0::4, 2] = 0xFFFF           # the tail of the first submit
+    P["trim_start"][0::4, 8] = 0xFFFF           # ... and of the last
+    got, _ = run_product(sc, inputs, P, ramps, oramp, splits=[3, 3, 3], s16=s16)
+    for s in range(n):
+        keep = [f for f in range(F) if P["trim_start"][s, f] != 0xFFFF]
+        ref = S.run_oracle(sc, [x[s:s + 1][:, keep] for x in inputs], P[s:s + 1][:, keep])[0]
+        cnt = [c for f, c in enumerate(got[s][0][:F]) if f in keep] + got[s][0][F:]
+        assert cnt == ref[0], f"stream {s}: counts {got[s][0]} vs {ref[0]}"
+        assert np.array_equal(got[s][1], ref[1]), f"stream {s}: PCM differs"
