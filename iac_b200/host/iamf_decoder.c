@@ -124,11 +124,70 @@ static ih_mix *db_mix(IAMF_DecoderHandle h, uint64_t id) {
   return 0;
 }
 
+/* ---- engine objects shared by the handles of a process: one iamfb context per device and one plan per pipeline signature
+ * (the reference needs neither; a context per handle meant ~70 CUDA events, three streams and every constant table once
+ * per handle).  Calls into the engine through a shared entry are serialised by its mutex: distinct handles may still be
+ * used from distinct threads (SURVEY 8b "threading"), the device part of their decode calls then runs one at a time. */
+#include <pthread.h>
+typedef struct ih_shared {
+  struct ih_shared *next;
+  int device, refs;
+  iamfb_plan_desc desc;
+  iamfb_ctx *ctx;
+  iamfb_plan *plan;
+  pthread_mutex_t mu;
+} ih_shared;
+static ih_shared *g_shared = 0;
+static pthread_mutex_t g_shared_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static ih_shared *shared_acquire(int device, const iamfb_plan_desc *d) {
+  pthread_mutex_lock(&g_shared_mu);
+  ih_shared *e = g_shared;
+  for (; e; e = e->next)
+    if (e->device == device && memcmp(&e->desc, d, sizeof(*d)) == 0) break;
+  if (!e) {
+    e = (ih_shared *)calloc(1, sizeof(*e));
+    if (e) {
+      e->device = device;
+      e->desc = *d;
+      pthread_mutex_init(&e->mu, 0);
+      if (iamfb_ctx_create(device, &e->ctx) != IAMFB_OK || iamfb_plan_create(e->ctx, d, &e->plan) != IAMFB_OK) {
+        if (e->ctx) iamfb_ctx_destroy(e->ctx);
+        free(e);
+        e = 0;
+      } else {
+        e->next = g_shared;
+        g_shared = e;
+      }
+    }
+  }
+  if (e) ++e->refs;
+  pthread_mutex_unlock(&g_shared_mu);
+  return e;
+}
+
+static void shared_release(ih_shared *e) {
+  if (!e) return;
+  pthread_mutex_lock(&g_shared_mu);
+  if (--e->refs == 0) {
+    ih_shared **pp = &g_shared;
+    while (*pp && *pp != e) pp = &(*pp)->next;
+    if (*pp) *pp = e->next;
+    iamfb_plan_destroy(e->plan);
+    iamfb_ctx_destroy(e->ctx);
+    pthread_mutex_destroy(&e->mu);
+    free(e);
+  }
+  pthread_mutex_unlock(&g_shared_mu);
+}
+
 static void engine_release(IAMF_DecoderHandle h) {
   if (h->group_owner) {
-    if (h->batch) iamfb_batch_destroy(h->batch);
-    if (h->plan) iamfb_plan_destroy(h->plan);
-    if (h->ctx) iamfb_ctx_destroy(h->ctx);
+    if (h->batch) {
+      if (h->shared) pthread_mutex_lock(&((ih_shared *)h->shared)->mu);
+      iamfb_batch_destroy(h->batch);
+      if (h->shared) pthread_mutex_unlock(&((ih_shared *)h->shared)->mu);
+    }
     for (int e = 0; e < IAMFB_MAX_ELEMENTS; ++e) {
       iamfb_host_free(h->in[e]);
       iamfb_host_free(h->ramp[e]);
@@ -138,6 +197,8 @@ static void engine_release(IAMF_DecoderHandle h) {
     iamfb_host_free(h->fp_stage);
     iamfb_host_free(h->counts_stage);
   }
+  shared_release((ih_shared *)h->shared);
+  h->shared = 0;
   h->batch = 0; h->plan = 0; h->ctx = 0;
   for (int e = 0; e < IAMFB_MAX_ELEMENTS; ++e) h->in[e] = h->ramp[e] = 0;
   h->out_ramp = 0; h->pcm_stage = 0; h->fp_stage = 0; h->counts_stage = 0;
@@ -413,6 +474,25 @@ static int engine_build(IAMF_DecoderHandle h) {
   d->out_rate = (int)h->sampling_rate;
   d->n_elements = h->n_streams;
   for (int i = 0; i < h->n_streams; ++i) fill_element_desc(h, &h->streams[i], &d->el[i]);
+  /* The binauraliser.  The reference compiles it out by default (DISABLE_BINAURALIZER 1, ae_rdr.h:67-69): binaural output
+   * is then the stereo rows of the matrix tables, and that is the default here too.  IAMF_B200_BINAURALIZER=1 is the
+   * run-time counterpart of building the reference with DISABLE_BINAURALIZER 0: scene-based elements always take the HRTF
+   * renderer (IAMF_decoder.c:2606-2612), channel-based ones when the mix presentation says headphones_rendering_mode 1
+   * (:2565-2573) - unless they need the de-mixer (scalable layers), which the HRTF front end does not render. */
+  {
+    const char *benv = getenv("IAMF_B200_BINAURALIZER");
+    if (benv && atoi(benv) && h->layout_type == IAMF_LAYOUT_TYPE_BINAURAL && h->mix) {
+      for (int i = 0; i < h->n_streams; ++i) {
+        const ih_element *el = h->streams[i].el;
+        int mode = 0;
+        for (int k = 0; k < h->mix->n_elements; ++k)
+          if (h->mix->el[k].element_id == el->id) mode = h->mix->el[k].headphones_mode;
+        if (el->type != AUDIO_ELEMENT_CHANNEL_BASED) d->el[i].binaural_hrtf = 1;
+        else if (mode == 1 && h->streams[i].layer == 0 && !d->el[i].recon_present && d->el[i].n_in == h->streams[i].n_layout_ch)
+          d->el[i].binaural_hrtf = 1;
+      }
+    }
+  }
   d->target = h->layout_type == IAMF_LAYOUT_TYPE_BINAURAL ? IAMFB_TARGET_BINAURAL : h->sound_system;
   d->loudness_gain = h->norm_loudness ? ih_db2lin(h->norm_loudness - h->loudness) : 0.f;
   d->limiter = h->limiter_on;
@@ -424,9 +504,26 @@ static int engine_build(IAMF_DecoderHandle h) {
   int dev = 0;
   const char *env = getenv("IAMF_B200_DEVICE");
   if (env) dev = atoi(env);
-  if (iamfb_ctx_create(dev, &h->ctx) != IAMFB_OK) return IAMF_ERR_INTERNAL;
-  if (iamfb_plan_create(h->ctx, d, &h->plan) != IAMFB_OK) return IAMF_ERR_INTERNAL;
-  if (iamfb_batch_create(h->plan, 1, 1, &h->batch) != IAMFB_OK) return IAMF_ERR_INTERNAL;
+  ih_shared *sh = shared_acquire(dev, d);
+  if (!sh) return IAMF_ERR_INTERNAL;
+  h->shared = sh;
+  h->ctx = sh->ctx;
+  h->plan = sh->plan;
+  h->pcm_stage_size = iamfb_plan_out_stride_bytes(h->plan, 1);
+  return IAMF_OK;
+}
+
+/* the handle's own single-stream batch and pinned frame buffers: created by its first IAMF_decoder_decode (handles that
+ * step through IAMF_decoder_decode_batch never need them) */
+static int engine_private(IAMF_DecoderHandle h) {
+  if (h->batch) return IAMF_OK;
+  if (!h->plan) return IAMF_ERR_INTERNAL;
+  const iamfb_plan_desc *d = &h->desc;
+  ih_shared *sh = (ih_shared *)h->shared;
+  pthread_mutex_lock(&sh->mu);
+  const int rc = iamfb_batch_create(h->plan, 1, 1, &h->batch);
+  pthread_mutex_unlock(&sh->mu);
+  if (rc != IAMFB_OK) return IAMF_ERR_INTERNAL;
   const size_t N = (size_t)d->frame_size;
   for (int e = 0; e < h->n_streams; ++e) {
     h->in[e] = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)d->el[e].n_in);
@@ -434,7 +531,6 @@ static int engine_build(IAMF_DecoderHandle h) {
     if (!h->in[e] || !h->ramp[e]) return IAMF_ERR_ALLOC_FAIL;
   }
   h->out_ramp = (float *)iamfb_host_alloc(sizeof(float) * N);
-  h->pcm_stage_size = iamfb_plan_out_stride_bytes(h->plan, 1);
   h->pcm_stage = (uint8_t *)iamfb_host_alloc(h->pcm_stage_size);
   h->fp_stage = (iamfb_frame_params *)iamfb_host_alloc(sizeof(iamfb_frame_params));
   h->counts_stage = (int32_t *)iamfb_host_alloc(sizeof(int32_t));
@@ -898,7 +994,12 @@ int IAMF_decoder_decode(IAMF_DecoderHandle h, const uint8_t *data, int32_t size,
   if (h->status != IH_STATUS_RECEIVE) return IAMF_ERR_INVALID_STATE;
   if (h->leader || h->group_size > 1) return IAMF_ERR_INVALID_STATE; /* grouped handles step through decode_batch */
   if (rsize) *rsize = 0;
-  if (h->n_streams <= 0 || !h->batch) return IAMF_ERR_INTERNAL;
+  if (h->n_streams <= 0 || !h->plan) return IAMF_ERR_INTERNAL;
+  {
+    const int rc = engine_private(h);
+    if (rc != IAMF_OK) return rc;
+  }
+  ih_shared *sh = (ih_shared *)h->shared;
   int real = 0;
   if (data && size > 0) {
     int run = 0;
@@ -927,7 +1028,10 @@ int IAMF_decoder_decode(IAMF_DecoderHandle h, const uint8_t *data, int32_t size,
       io.params = h->fp_stage;
       io.pcm = h->pcm_stage;
       io.out_counts = h->counts_stage;
-      if (iamfb_batch_submit_host(h->batch, &io, 1) != IAMFB_OK) { h->status = IH_STATUS_RECEIVE; return IAMF_ERR_INTERNAL; }
+      pthread_mutex_lock(&sh->mu);
+      const int rc = iamfb_batch_submit_host(h->batch, &io, 1);
+      pthread_mutex_unlock(&sh->mu);
+      if (rc != IAMFB_OK) { h->status = IH_STATUS_RECEIVE; return IAMF_ERR_INTERNAL; }
       real = h->counts_stage[0];
     }
     if (ready <= 0) {
@@ -937,7 +1041,10 @@ int IAMF_decoder_decode(IAMF_DecoderHandle h, const uint8_t *data, int32_t size,
     if (real > 0 && pcm && h->bit_depth) memcpy(pcm, h->pcm_stage, pcm_bytes(h, real));
   }
   if (!data) { /* iamf_delay_buffer_handle, :3250-3301 */
-    if (iamfb_batch_flush_host(h->batch, h->pcm_stage, h->counts_stage) != IAMFB_OK) return IAMF_ERR_INTERNAL;
+    pthread_mutex_lock(&sh->mu);
+    const int rc = iamfb_batch_flush_host(h->batch, h->pcm_stage, h->counts_stage);
+    pthread_mutex_unlock(&sh->mu);
+    if (rc != IAMFB_OK) return IAMF_ERR_INTERNAL;
     real = h->counts_stage[0];
     if (real > 0 && pcm && h->bit_depth) memcpy(pcm, h->pcm_stage, pcm_bytes(h, real));
   }
@@ -1037,8 +1144,12 @@ static int group_build(IAMF_DecoderHandle *hs, int n, int units) {
   const size_t N = (size_t)L->frame_size, F = (size_t)units;
   const size_t esz = s16 ? sizeof(int16_t) : sizeof(float);
   iamfb_batch *gb = 0;
-  if (iamfb_batch_create(L->plan, n, units, &gb) != IAMFB_OK) return IAMF_ERR_INTERNAL;
-  iamfb_batch_destroy(L->batch);
+  ih_shared *sh = (ih_shared *)L->shared;
+  pthread_mutex_lock(&sh->mu);
+  const int brc = iamfb_batch_create(L->plan, n, units, &gb);
+  if (brc == IAMFB_OK && L->batch) iamfb_batch_destroy(L->batch);
+  pthread_mutex_unlock(&sh->mu);
+  if (brc != IAMFB_OK) return IAMF_ERR_INTERNAL;
   L->batch = gb;
   for (int e = 0; e < L->n_streams; ++e) {
     iamfb_host_free(L->in[e]); iamfb_host_free(L->ramp[e]);
@@ -1135,8 +1246,12 @@ int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t
   int n_flush = 0, any_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, any_out_ramp = 0;
   for (int i = 0; i < n; ++i) n_flush += data[i] ? 0 : 1;
   if (n_flush && n_flush != n) return IAMF_ERR_UNIMPLEMENTED; /* a group flushes together */
+  ih_shared *sh = (ih_shared *)L->shared;
   if (n_flush) {
-    if (iamfb_batch_flush_host(L->batch, L->pcm_stage, L->counts_stage) != IAMFB_OK) return IAMF_ERR_INTERNAL;
+    pthread_mutex_lock(&sh->mu);
+    const int frc = iamfb_batch_flush_host(L->batch, L->pcm_stage, L->counts_stage);
+    pthread_mutex_unlock(&sh->mu);
+    if (frc != IAMFB_OK) return IAMF_ERR_INTERNAL;
   } else {
     /* phase 1 (host, per handle, on the pool): parse, core decode into the handle's slots of the shared pinned buffers */
     ih_step_job job = {hs, data, size, F};
@@ -1173,7 +1288,10 @@ int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t
     io.params = L->fp_stage;
     io.pcm = L->pcm_stage;
     io.out_counts = L->counts_stage;
-    if (iamfb_batch_submit_host(L->batch, &io, F) != IAMFB_OK) return IAMF_ERR_INTERNAL;
+    pthread_mutex_lock(&sh->mu);
+    const int src = iamfb_batch_submit_host(L->batch, &io, F);
+    pthread_mutex_unlock(&sh->mu);
+    if (src != IAMFB_OK) return IAMF_ERR_INTERNAL;
   }
   /* phase 3: hand every stream's samples back (the frames of a stream lie back to back in its row of the PCM buffer) */
   for (int i = 0; i < n; ++i) {

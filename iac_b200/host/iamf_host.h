@@ -195,6 +195,7 @@ struct IAMF_Decoder {
   int out_channels;
   IAMF_extradata metadata;
   /* engine */
+  void *shared;                        /* the (context, plan) entry this handle borrows (iamf_decoder.c) */
   iamfb_ctx *ctx;
   iamfb_plan *plan;
   iamfb_batch *batch;

@@ -293,7 +293,7 @@ def cfg_toa():
     return Stream([e], layouts=[("ss", 7, 0)])
 
 
-def cfg_714_foa(binaural=True):
-    e0 = Element(0, "channel", [Layer(L714, 7, 5)], mix_gain_q78=-0x0300)
+def cfg_714_foa(binaural=True, headphones_mode=0):
+    e0 = Element(0, "channel", [Layer(L714, 7, 5)], mix_gain_q78=-0x0300, headphones_mode=headphones_mode)
     e1 = Element(1, "scene", ambi_mode=0, ambi_channels=4, mix_gain_q78=-0x0300, substream_base=7)
     return Stream([e0, e1], layouts=[("bin", 0, 0)] if binaural else [("ss", 9, 0)])

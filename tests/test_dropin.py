@@ -280,3 +280,31 @@ def test_decode_batch_units_matches_per_handle_decode(cfg, n, F, K):
         assert total[s] + ret[s] == sum(c for c in single[s][1] if c > 0)
         assert got[s] == single[s][0].tobytes(), f"handle {s}"
         L.IAMF_decoder_close(hs[s])
+
+
+@pytest.mark.gpu
+def test_binauraliser_switch_through_the_public_api(monkeypatch):
+    """IAMF_B200_BINAURALIZER=1 (the run-time counterpart of the reference's DISABLE_BINAURALIZER 0): configuration 4 through
+    IAMF_decoder_output_layout_set_binaural renders the 7.1.4 element (headphones_rendering_mode 1) with the per-speaker
+    HRIRs and the ambisonics element with the SH-domain ones.  Checked against the pipeline oracle with its HRTF renderer
+    (self-oracle: the reference's binauraliser libraries are absent) - and the switch off still gives the
+    as-built stereo-matrix bytes."""
+    sc, st, api_kw, unit_kw = refstreams.case("c4h")
+    st = G.cfg_714_foa(headphones_mode=1)
+    n, F = 3, 6
+    inputs = S.synth_inputs(sc, n, F, seed=51)
+    P, _, _ = S.synth_params(sc, n, F, seed=52)
+    desc = st.descriptors()
+    api = iamfapi.Api(LIBIAMF)
+    ref = S.run_oracle(sc, inputs, P)
+    asbuilt_sc, _, _, _ = refstreams.case("c4")
+    ref_asbuilt = S.run_oracle(asbuilt_sc, inputs, P)
+    for s in range(n):
+        units = refstreams.temporal_units(sc, st, inputs, P, unit_kw, s)
+        monkeypatch.setenv("IAMF_B200_BINAURALIZER", "1")
+        pcm, counts = api.render(desc, units, **api_kw)
+        assert counts == ref[s][0]
+        assert pcm.tobytes() == ref[s][1].tobytes(), f"stream {s}: HRTF rendering through the public API"
+        monkeypatch.delenv("IAMF_B200_BINAURALIZER")
+        pcm, counts = api.render(desc, units, **api_kw)
+        assert pcm.tobytes() == ref_asbuilt[s][1].tobytes(), f"stream {s}: as built"
