@@ -390,6 +390,61 @@ def copy_ceiling(h2d_bytes, d2h_bytes, dev, reps=5):
     return best
 
 
+def api_leg(cfg, n_handles, K, rank, w, shard, dev, distinct=32, calls=6):
+    """audio-s/s through IAMF_decoder_decode_batch_units: n_handles handles, K temporal units per handle and call"""
+    import ctypes as C
+    import iamfapi
+    import refstreams
+    import scenarios as S
+    sc, st, api_kw, unit_kw = refstreams.case(cfg)
+    inputs = S.synth_inputs(sc, distinct, K, seed=0x1A3F + 977 * rank)
+    P, _, _ = S.synth_params(sc, distinct, K, seed=0x99 + rank)
+    refstreams.no_param_gaps(sc, P)
+    desc = st.descriptors()
+    blobs = [b"".join(refstreams.temporal_units(sc, st, inputs, P, unit_kw, s)) for s in range(distinct)]
+    first = [refstreams.temporal_units(sc, st, inputs, P[:, :1], unit_kw, s)[0] for s in range(distinct)]
+    api = iamfapi.Api(os.path.join(ROOT, "iac_b200", "libiamf.so"))
+    L = api.L
+    vp = C.c_void_p
+    L.IAMF_decoder_decode_batch_units.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
+                                                  C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+    os.environ["IAMF_B200_DEVICE"] = str(dev.index or 0)
+    n = n_handles
+    hs = (vp * n)()
+    for i in range(n):
+        hs[i] = api.open_configured(desc + first[i % distinct], **api_kw)
+    ch = sc.out_channels
+    bps = sc.bit_depth // 8 if sc.bit_depth else 4
+    per = bps * ch * (sc.frame_size * (sc.out_rate // sc.in_rate + 1) + 64) * K
+    big = C.create_string_buffer(per * n)
+    base = C.addressof(big)
+    pcm = (vp * n)(*[base + i * per for i in range(n)])
+    data = (C.c_char_p * n)(*[blobs[i % distinct] for i in range(n)])
+    size = (C.c_int32 * n)(*[len(blobs[i % distinct]) for i in range(n)])
+    rs = (C.c_uint32 * n)()
+    ret = (C.c_int * n)()
+    in_bytes = sum(len(blobs[i % distinct]) for i in range(n))
+
+    def step():
+        rc = L.IAMF_decoder_decode_batch_units(hs, n, data, size, rs, pcm, ret, K, None)
+        assert rc == 0, rc
+    for _ in range(2):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        step()
+    dt = time.perf_counter() - t0
+    out = float(sum(ret[i] for i in range(n)))
+    assert all(rs[i] == size[i] for i in range(n))
+    for i in range(n):
+        L.IAMF_decoder_close(hs[i])
+    ms_max, out_total = shard.aggregate(dt * 1e3, out, device=dev)
+    value = shard.job_throughput(ms_max, out_total, sc.out_rate, steps=calls)
+    return dict(value=value, unit="audio-s/s", ms_per_step=ms_max / calls, handles_per_gpu=n, units_per_call=K,
+                bitstream_bytes_per_step=in_bytes, host_threads=int(os.environ.get("IAMF_B200_HOST_THREADS", "0")) or len(os.sched_getaffinity(0)),
+                entry="IAMF_decoder_decode_batch_units (include/IAMF_decoder.h): ipcm-coded temporal units in, interleaved int16 PCM out")
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -505,6 +560,16 @@ def run_gpu(args):
     ceil_ms_max, _ = shard.aggregate(ceil_s * 1e3, 0.0, device=dev)
     del h_in, h_pcm
 
+    # ---- the same through the PUBLIC API of the drop-in library (include/IAMF_decoder.h + the additive batch call): one
+    # IAMF_DecoderHandle per stream fed ipcm-coded IAMF temporal units (OBU parsing, parameter time lines and core decode on
+    # the host thread pool, int16 hand-over, one device pass per call for the whole group)
+    e2e_api = None
+    if not args.no_api_leg:
+        try:
+            e2e_api = api_leg(cfg, S_, min(Fe, 8), rank, w, shard, dev)
+        except Exception as ex:  # noqa: BLE001
+            e2e_api = {"error": repr(ex)}
+
     # ---- the other BASELINE configurations and the input-referred level of this one, device-resident, ~0.3 s each
     others = {}
     value_input_referred = None
@@ -574,6 +639,7 @@ def run_gpu(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "e2e_api": e2e_api,
             "value_input_referred": value_input_referred,
             "configs": others,
         }
@@ -625,6 +691,7 @@ def main():
     ap.add_argument("--step-ms", type=float, default=60.0, help="target duration of one step (a step = R back-to-back submits)")
     ap.add_argument("--submits-per-step", type=int, default=0, help="R; 0 = derive it from --step-ms")
     ap.add_argument("--in-format", default="f32", choices=["f32", "s16"], help="device-resident decoded input format")
+    ap.add_argument("--no-api-leg", action="store_true", help="skip the leg through the drop-in library's public API")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--peak-db", default="", help="experiment: override the per-stream peak range, e.g. -40,-30")
     ap.add_argument("--peak-ref", default="rendered", choices=["rendered", "input"],

@@ -8,6 +8,9 @@
  * de-interleaved, substreams concatenated in transmission order.
  */
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "iamf_host.h"
 
@@ -51,7 +54,17 @@ static int pcm_decode_s16(const ih_codec *cc, uint8_t *const *pkt, const uint32_
     if (c < n_coupled) {
       int16_t *l = out + (size_t)samples * ch, *r = l + samples;
       if (le) {
-        for (int s = 0; s < samples; ++s) {
+        int s = 0;
+#if defined(__SSE2__)
+        /* 8 stereo samples per step: L = the low, R = the high half of every 32-bit pair (the values are int16, so the
+         * saturating pack is exact) */
+        for (; s + 8 <= samples; s += 8) {
+          const __m128i a = _mm_loadu_si128((const __m128i *)(p + 4 * s)), b = _mm_loadu_si128((const __m128i *)(p + 4 * s + 16));
+          _mm_storeu_si128((__m128i *)(l + s), _mm_packs_epi32(_mm_srai_epi32(_mm_slli_epi32(a, 16), 16), _mm_srai_epi32(_mm_slli_epi32(b, 16), 16)));
+          _mm_storeu_si128((__m128i *)(r + s), _mm_packs_epi32(_mm_srai_epi32(a, 16), _mm_srai_epi32(b, 16)));
+        }
+#endif
+        for (; s < samples; ++s) {
           int16_t v[2];
           memcpy(v, p + 4 * s, 4);
           l[s] = v[0];

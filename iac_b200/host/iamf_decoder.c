@@ -206,11 +206,13 @@ static void engine_release(IAMF_DecoderHandle h) {
   h->group_units = 0; h->group_s16 = 0;
 }
 
+static void pkt_drop(ih_stream *st, int k);
+
 static void db_reset(IAMF_DecoderHandle h) {
   for (int i = 0; i < h->n_params; ++i) ih_param_clear(&h->params[i]);
   for (int s = 0; s < IAMFB_MAX_ELEMENTS; ++s) {
     ih_codec_close(&h->streams[s]);
-    for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k) { free(h->streams[s].pkt[k]); h->streams[s].pkt[k] = 0; }
+    for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k) pkt_drop(&h->streams[s], k);
   }
   h->n_codecs = h->n_elements = h->n_mixes = h->n_params = 0;
   h->have_header = 0;
@@ -369,7 +371,7 @@ static float best_loudness(IAMF_DecoderHandle h, const ih_mix *m) {
 /* iamf_stream_new + iamf_stream_set_output_layout, IAMF_decoder.c:1617-1825 */
 static int stream_setup(IAMF_DecoderHandle h, ih_stream *st, const ih_element *el, const ih_codec *cc) {
   ih_codec_close(st);
-  for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k) free(st->pkt[k]);
+  for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k) pkt_drop(st, k);
   memset(st, 0, sizeof(*st));
   st->el = el;
   st->cc = cc;
@@ -826,7 +828,26 @@ static void stream_update_parameter(ih_stream *st, const ih_param_item *pi) {
 
 /* iamf_decoder_internal_parse_OBUs, IAMF_decoder.c:2871-2944.  returns bytes consumed; *run = every stream has a
  * packet for each of its sub-streams */
-static uint32_t parse_obus(IAMF_DecoderHandle h, const uint8_t *data, uint32_t size, int *run) {
+/* a sub-stream packet is either owned (malloc'ed copy: the caller's buffer need not outlive the call, IAMF_decoder.c:2113-2120)
+ * or - inside a batch step, until the step ends - borrowed from the caller's buffer (bit k of pkt_borrowed) */
+static void pkt_drop(ih_stream *st, int k) {
+  if (!((st->pkt_borrowed >> k) & 1u)) free(st->pkt[k]);
+  st->pkt_borrowed &= ~(1u << k);
+  st->pkt[k] = 0;
+  st->pkt_size[k] = 0;
+}
+/* packets still borrowed when a batch step ends (its buffer stopped inside a temporal unit) become owned copies */
+static void pkt_own_all(ih_stream *st) {
+  for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k)
+    if ((st->pkt_borrowed >> k) & 1u) {
+      uint8_t *c = (uint8_t *)malloc(st->pkt_size[k] ? st->pkt_size[k] : 1);
+      if (c) memcpy(c, st->pkt[k], st->pkt_size[k]);
+      st->pkt[k] = c;
+      st->pkt_borrowed &= ~(1u << k);
+    }
+}
+
+static uint32_t parse_obus(IAMF_DecoderHandle h, const uint8_t *data, uint32_t size, int *run, int borrow) {
   uint32_t pos = 0;
   ih_obu o;
   *run = 0;
@@ -876,9 +897,14 @@ static uint32_t parse_obus(IAMF_DecoderHandle h, const uint8_t *data, uint32_t s
           st->etrim = o.trim_end;
         }
         if (!st->pkt[idx]) ++st->pkt_count;
-        free(st->pkt[idx]);
-        st->pkt[idx] = (uint8_t *)malloc(psize ? psize : 1);
-        if (st->pkt[idx]) memcpy(st->pkt[idx], payload, psize);
+        pkt_drop(st, idx);
+        if (borrow) {
+          st->pkt[idx] = (uint8_t *)(uintptr_t)payload;
+          st->pkt_borrowed |= 1u << idx;
+        } else {
+          st->pkt[idx] = (uint8_t *)malloc(psize ? psize : 1);
+          if (st->pkt[idx]) memcpy(st->pkt[idx], payload, psize);
+        }
         st->pkt_size[idx] = psize;
         break;
       }
@@ -931,7 +957,7 @@ static int prepare_frame(IAMF_DecoderHandle h, void *const in[], int s16, iamfb_
       ret = s16 ? ih_codec_decode_s16(st, 0, st->cc, st->pkt, st->pkt_size, el->ambi_sub, el->ambi_coupled, (int16_t *)in[s], N)
                 : ih_codec_decode(st, 0, st->cc, st->pkt, st->pkt_size, el->ambi_sub, el->ambi_coupled, (float *)in[s], N);
     }
-    for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k) { free(st->pkt[k]); st->pkt[k] = 0; st->pkt_size[k] = 0; }
+    for (int k = 0; k < IH_MAX_SUBSTREAMS; ++k) pkt_drop(st, k);
     st->pkt_count = 0;
     if (ret > 0 && ret != N) ret = IAMF_ERR_INTERNAL; /* short frames (frame_padding) need a codec with delay: not supported */
 
@@ -1003,7 +1029,7 @@ int IAMF_decoder_decode(IAMF_DecoderHandle h, const uint8_t *data, int32_t size,
   int real = 0;
   if (data && size > 0) {
     int run = 0;
-    uint32_t used = parse_obus(h, data, (uint32_t)size, &run);
+    uint32_t used = parse_obus(h, data, (uint32_t)size, &run, 0);
     if (rsize) *rsize = used;
     if (h->status == IH_STATUS_RECONFIGURE) return IAMF_ERR_INVALID_STATE;
     if (h->status != IH_STATUS_RUN) return 0;
@@ -1214,7 +1240,7 @@ static void step_handle(void *v, int i) {
       ramp[e] = L->ramp[e] + ((size_t)i * F + f) * N;
     }
     int run = 0, use_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, use_out = 0;
-    uint32_t used = parse_obus(h, job->data[i] + pos, (uint32_t)job->size[i] - pos, &run);
+    uint32_t used = parse_obus(h, job->data[i] + pos, (uint32_t)job->size[i] - pos, &run, 1);
     pos += used;
     h->unit_used = pos;
     if (h->status == IH_STATUS_RECONFIGURE) { h->unit_ret[f] = IAMF_ERR_INVALID_STATE; break; }
@@ -1228,6 +1254,42 @@ static void step_handle(void *v, int i) {
     h->unit_flags[f] = (uint8_t)((use_ramp[0] ? 1 : 0) | (use_ramp[1] ? 2 : 0) | (use_out ? 4 : 0));
     if (!used) break;
   }
+  for (int s = 0; s < h->n_streams; ++s) pkt_own_all(&h->streams[s]);
+}
+
+/* phase 3 of a batch step for handle i: its samples into the caller's buffer */
+typedef struct {
+  IAMF_DecoderHandle *hs;
+  void *const *pcm;
+  int *ret;
+  uint32_t *rsize;
+  int *units_done;
+  int units, flush;
+} ih_out_job;
+static size_t pcm_bytes(IAMF_DecoderHandle h, int samples);
+static void out_handle(void *v, int i) {
+  const ih_out_job *job = (const ih_out_job *)v;
+  IAMF_DecoderHandle h = job->hs[i], L = job->hs[0];
+  const int F = job->units;
+  if (job->rsize) job->rsize[i] = job->flush ? 0 : h->unit_used;
+  if (job->units_done) job->units_done[i] = job->flush ? 0 : h->units_done;
+  int real = 0, err = 0;
+  if (job->flush) real = L->counts_stage[i];
+  else
+    for (int f = 0; f < F; ++f) {
+      if (h->unit_ret[f] < 0 && !err) err = h->unit_ret[f];
+      if (h->unit_ret[f] > 0) {
+        const int c = L->counts_stage[(size_t)i * F + f];
+        real += c;
+        h->last_frame_size = c;
+      }
+    }
+  /* (a flush returns its rows at the pitch of a one-frame submit) */
+  const size_t pitch = job->flush ? iamfb_plan_out_stride_bytes(L->plan, 1) : L->pcm_stage_size;
+  if (real > 0 && job->pcm && job->pcm[i] && h->bit_depth) memcpy(job->pcm[i], L->pcm_stage + (size_t)i * pitch, pcm_bytes(h, real));
+  h->duration += (uint64_t)real;
+  if (job->flush) h->last_frame_size = real;
+  job->ret[i] = (real == 0 && err) ? err : real;
 }
 
 int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
@@ -1293,28 +1355,11 @@ int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t
     pthread_mutex_unlock(&sh->mu);
     if (src != IAMFB_OK) return IAMF_ERR_INTERNAL;
   }
-  /* phase 3: hand every stream's samples back (the frames of a stream lie back to back in its row of the PCM buffer) */
-  for (int i = 0; i < n; ++i) {
-    IAMF_DecoderHandle h = hs[i];
-    if (rsize) rsize[i] = n_flush ? 0 : h->unit_used;
-    if (units_done) units_done[i] = n_flush ? 0 : h->units_done;
-    int real = 0, err = 0;
-    if (n_flush) real = L->counts_stage[i];
-    else
-      for (int f = 0; f < F; ++f) {
-        if (h->unit_ret[f] < 0 && !err) err = h->unit_ret[f];
-        if (h->unit_ret[f] > 0) {
-          const int c = L->counts_stage[(size_t)i * F + f];
-          real += c;
-          h->last_frame_size = c;
-        }
-      }
-    /* (a flush returns its rows at the pitch of a one-frame submit) */
-    const size_t pitch = n_flush ? iamfb_plan_out_stride_bytes(L->plan, 1) : L->pcm_stage_size;
-    if (real > 0 && pcm && pcm[i] && h->bit_depth) memcpy(pcm[i], L->pcm_stage + (size_t)i * pitch, pcm_bytes(h, real));
-    h->duration += (uint64_t)real;
-    if (n_flush) h->last_frame_size = real;
-    ret[i] = (real == 0 && err) ? err : real;
+  /* phase 3 (host, per handle, on the pool): hand every stream's samples back (the frames of a stream lie back to back in
+   * its row of the PCM buffer) */
+  {
+    ih_out_job oj = {hs, pcm, ret, rsize, units_done, F, n_flush ? 1 : 0};
+    pool_for(n, out_handle, &oj);
   }
   return IAMF_OK;
 }

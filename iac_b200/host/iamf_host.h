@@ -151,6 +151,7 @@ typedef struct {
   uint8_t *pkt[IH_MAX_SUBSTREAMS];
   uint32_t pkt_size[IH_MAX_SUBSTREAMS];
   int pkt_count;
+  uint32_t pkt_borrowed;         /* bit k: pkt[k] points into the caller's buffer of the running batch step (not owned) */
   void *codec_state[IH_MAX_SUBSTREAMS]; /* per sub-stream core decoder (Opus), created on first use */
   uint64_t strim, etrim;
   ih_param_item *mix_gain, *demix, *recon;
