@@ -197,6 +197,7 @@ extern "C" int iamfb_ctx_create(int device, iamfb_ctx **out) {
     CU(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
   }
   CU(cudaEventCreateWithFlags(&c->ev_free, cudaEventDisableTiming));
+  for (int i = 0; i < kMaxChunks; ++i) CU(cudaEventCreateWithFlags(&c->ev_back[i], cudaEventDisableTiming | cudaEventBlockingSync));
   *out = c;
   return IAMFB_OK;
 }
@@ -222,7 +223,7 @@ extern "C" void iamfb_ctx_destroy(iamfb_ctx *c) {
   cudaStreamDestroy(c->h2d);
   cudaStreamDestroy(c->d2h);
   for (int i = 0; i < kMaxSub; ++i) { cudaEventDestroy(c->ev_w[i]); cudaEventDestroy(c->ev_s[i]); }
-  for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); }
+  for (int i = 0; i < kMaxChunks; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_back[i]); }
   cudaEventDestroy(c->ev_free);
   delete c;
 }
@@ -1855,11 +1856,16 @@ static int ensure_staging(iamfb_batch *b, int F) {
   return IAMFB_OK;
 }
 
-extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F) {
-  if (!b || !io) return fail(IAMFB_ERR_BAD_ARG, "submit: null argument");
+// Host-resident submit.  hooks == nullptr: the caller's buffers are complete when the call is made.  With hooks the caller
+// produces and consumes them group by group while the device works on the neighbouring groups: fill(s_lo, s_cnt, io) is
+// called right before the inputs of the streams [s_lo, s_lo + s_cnt) are uploaded (it writes their slices of in / params /
+// ramps and may set or clear the ramp pointers of `io` for this group), drain(s_lo, s_cnt) once their PCM and counts are
+// back in host memory.
+static int submit_host(iamfb_batch *b, const iamfb_io *io_in, int F, const iamfb_chunk_hooks *hooks) {
+  if (!b || !io_in) return fail(IAMFB_ERR_BAD_ARG, "submit: null argument");
   if (F <= 0 || F > b->Fmax) return fail(IAMFB_ERR_BAD_ARG, "submit: %d frames (batch sized for %d)", F, b->Fmax);
-  if (!io->params || !io->pcm) return fail(IAMFB_ERR_BAD_ARG, "submit: params / pcm is null");
-  if (io->in_format != IAMFB_IN_F32 && io->in_format != IAMFB_IN_S16) return fail(IAMFB_ERR_BAD_ARG, "submit: in_format %d", io->in_format);
+  if (!io_in->params || !io_in->pcm) return fail(IAMFB_ERR_BAD_ARG, "submit: params / pcm is null");
+  if (io_in->in_format != IAMFB_IN_F32 && io_in->in_format != IAMFB_IN_S16) return fail(IAMFB_ERR_BAD_ARG, "submit: in_format %d", io_in->in_format);
   iamfb_plan *p = b->plan;
   iamfb_ctx *ctx = p->ctx;
   CU(cudaSetDevice(ctx->device));
@@ -1868,16 +1874,10 @@ extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
   const size_t S = b->S, N = kp.frame_size;
-  const bool s16 = io->in_format == IAMFB_IN_S16;
+  const bool s16 = io_in->in_format == IAMFB_IN_S16;
   for (int e = 0; e < kp.n_elements; ++e)
-    if (!io->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
-  iamfb_io dio;
-  memset(&dio, 0, sizeof(dio));
-  for (int e = 0; e < kp.n_elements; ++e) dio.in[e] = s16 ? reinterpret_cast<const float *>(b->d_in16[e]) : b->d_in[e];
-  dio.in_format = io->in_format;
-  dio.params = b->d_params;
-  dio.pcm = b->d_pcm;
-  dio.out_counts = b->d_counts;
+    if (!io_in->in[e]) return fail(IAMFB_ERR_BAD_ARG, "submit: input of element %d is null", e);
+  iamfb_io io = *io_in;
   const size_t stride = iamfb_plan_out_stride_bytes(p, F);
   // groups of streams flow through upload -> kernels -> download on three streams; the fused path can run any stream
   // range, the multi-kernel path runs the batch as one group
@@ -1888,26 +1888,47 @@ extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F
   // the staging buffers are reused by every submit: uploads must not start before the previous submit's kernels are done
   CU(cudaEventRecord(ctx->ev_free, st));
   CU(cudaStreamWaitEvent(ctx->h2d, ctx->ev_free, 0));
-  // rare whole-batch arrays first
-  for (int e = 0; e < kp.n_elements; ++e)
-    if (io->gain_ramp[e]) {
-      CU(cudaMemcpyAsync(b->d_ramp[e], io->gain_ramp[e], sizeof(float) * S * F * N, cudaMemcpyHostToDevice, ctx->h2d));
-      dio.gain_ramp[e] = b->d_ramp[e];
+  int drained = 0;
+  auto drain_to = [&](int upto) -> int {   // groups [drained, upto): wait for their download, hand them to the caller
+    for (; drained < upto; ++drained) {
+      const size_t s_lo = S * drained / n_chunks, s_hi = S * (drained + 1) / n_chunks;
+      if (s_hi == s_lo) continue;
+      CU(cudaEventSynchronize(ctx->ev_back[drained]));
+      hooks->drain(hooks->user, (int)s_lo, (int)(s_hi - s_lo));
     }
-  if (io->out_gain_ramp) {
-    CU(cudaMemcpyAsync(b->d_oramp, io->out_gain_ramp, sizeof(float) * S * F * N, cudaMemcpyHostToDevice, ctx->h2d));
-    dio.out_gain_ramp = b->d_oramp;
-  }
+    return IAMFB_OK;
+  };
   for (int c = 0; c < n_chunks; ++c) {
     const size_t s_lo = S * c / n_chunks, s_hi = S * (c + 1) / n_chunks, cnt = s_hi - s_lo;
     if (!cnt) continue;
-    CU(cudaMemcpyAsync(b->d_params + s_lo * F, io->params + s_lo * F, sizeof(iamfb_frame_params) * cnt * F, cudaMemcpyHostToDevice, ctx->h2d));
+    if (hooks) {
+      io = *io_in;
+      hooks->fill(hooks->user, (int)s_lo, (int)cnt, &io);
+    }
+    iamfb_io dio;
+    memset(&dio, 0, sizeof(dio));
+    for (int e = 0; e < kp.n_elements; ++e) dio.in[e] = s16 ? reinterpret_cast<const float *>(b->d_in16[e]) : b->d_in[e];
+    dio.in_format = io.in_format;
+    dio.params = b->d_params;
+    dio.pcm = b->d_pcm;
+    dio.out_counts = b->d_counts;
+    // animated gains (rare): this group's slices
+    for (int e = 0; e < kp.n_elements; ++e)
+      if (io.gain_ramp[e]) {
+        CU(cudaMemcpyAsync(b->d_ramp[e] + s_lo * F * N, io.gain_ramp[e] + s_lo * F * N, sizeof(float) * cnt * F * N, cudaMemcpyHostToDevice, ctx->h2d));
+        dio.gain_ramp[e] = b->d_ramp[e];
+      }
+    if (io.out_gain_ramp) {
+      CU(cudaMemcpyAsync(b->d_oramp + s_lo * F * N, io.out_gain_ramp + s_lo * F * N, sizeof(float) * cnt * F * N, cudaMemcpyHostToDevice, ctx->h2d));
+      dio.out_gain_ramp = b->d_oramp;
+    }
+    CU(cudaMemcpyAsync(b->d_params + s_lo * F, io.params + s_lo * F, sizeof(iamfb_frame_params) * cnt * F, cudaMemcpyHostToDevice, ctx->h2d));
     for (int e = 0; e < kp.n_elements; ++e) {
       const size_t per = (size_t)F * p->in_rows[e] * N;
       if (s16)
-        CU(cudaMemcpyAsync(b->d_in16[e] + s_lo * per, (const int16_t *)io->in[e] + s_lo * per, sizeof(int16_t) * cnt * per, cudaMemcpyHostToDevice, ctx->h2d));
+        CU(cudaMemcpyAsync(b->d_in16[e] + s_lo * per, (const int16_t *)io.in[e] + s_lo * per, sizeof(int16_t) * cnt * per, cudaMemcpyHostToDevice, ctx->h2d));
       else
-        CU(cudaMemcpyAsync(b->d_in[e] + s_lo * per, io->in[e] + s_lo * per, sizeof(float) * cnt * per, cudaMemcpyHostToDevice, ctx->h2d));
+        CU(cudaMemcpyAsync(b->d_in[e] + s_lo * per, io.in[e] + s_lo * per, sizeof(float) * cnt * per, cudaMemcpyHostToDevice, ctx->h2d));
     }
     CU(cudaEventRecord(ctx->ev_up[c], ctx->h2d));
     CU(cudaStreamWaitEvent(st, ctx->ev_up[c], 0));
@@ -1915,13 +1936,25 @@ extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F
     if (r) return r;
     CU(cudaEventRecord(ctx->ev_done[c], st));
     CU(cudaStreamWaitEvent(ctx->d2h, ctx->ev_done[c], 0));
-    CU(cudaMemcpyAsync((char *)io->pcm + s_lo * stride, b->d_pcm + s_lo * stride, cnt * stride, cudaMemcpyDeviceToHost, ctx->d2h));
-    if (io->out_counts)
-      CU(cudaMemcpyAsync(io->out_counts + s_lo * F, b->d_counts + s_lo * F, sizeof(int32_t) * cnt * F, cudaMemcpyDeviceToHost, ctx->d2h));
+    CU(cudaMemcpyAsync((char *)io.pcm + s_lo * stride, b->d_pcm + s_lo * stride, cnt * stride, cudaMemcpyDeviceToHost, ctx->d2h));
+    if (io.out_counts)
+      CU(cudaMemcpyAsync(io.out_counts + s_lo * F, b->d_counts + s_lo * F, sizeof(int32_t) * cnt * F, cudaMemcpyDeviceToHost, ctx->d2h));
+    if (hooks) {
+      CU(cudaEventRecord(ctx->ev_back[c], ctx->d2h));
+      // two groups stay in flight behind the one being filled next
+      if (c >= 2) { r = drain_to(c - 1); if (r) return r; }
+    }
   }
+  if (hooks) { r = drain_to(n_chunks); if (r) return r; }
   CU(cudaStreamSynchronize(ctx->d2h));
   CU(cudaStreamSynchronize(st));
   return IAMFB_OK;
+}
+
+extern "C" int iamfb_batch_submit_host(iamfb_batch *b, const iamfb_io *io, int F) { return submit_host(b, io, F, nullptr); }
+extern "C" int iamfb_batch_submit_host_hooks(iamfb_batch *b, const iamfb_io *io, int F, const iamfb_chunk_hooks *hooks) {
+  if (!hooks || !hooks->fill || !hooks->drain) return fail(IAMFB_ERR_BAD_ARG, "submit: null hooks");
+  return submit_host(b, io, F, hooks);
 }
 
 extern "C" int iamfb_batch_flush_host(iamfb_batch *b, void *pcm, int32_t *counts) {

@@ -45,6 +45,7 @@ struct iamfb_ctx {
   // kernels of the previous group and the download of the one before overlap (PCIe is full duplex)
   cudaStream_t h2d, d2h;
   cudaEvent_t ev_up[kMaxChunks], ev_done[kMaxChunks], ev_free;
+  cudaEvent_t ev_back[kMaxChunks];   // a group's PCM is back in host memory (iamfb_batch_submit_host_hooks)
 };
 
 // optional per-kernel CUDA-event timing (bench.py's roofline leg); events are recorded on the launching stream

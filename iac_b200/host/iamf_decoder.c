@@ -1210,12 +1210,14 @@ typedef struct {
   const uint8_t *const *data;
   const int32_t *size;
   int units;
+  int base;                      /* pool index 0 = handle `base` */
 } ih_step_job;
 
 /* phase 1 of a batch step for handle i: its temporal units of this call, parsed and core-decoded into the handle's slots
  * [i][f] of the group's pinned buffers */
-static void step_handle(void *v, int i) {
+static void step_handle(void *v, int idx) {
   const ih_step_job *job = (const ih_step_job *)v;
+  const int i = job->base + idx;
   IAMF_DecoderHandle h = job->hs[i], L = job->hs[0];
   const size_t N = (size_t)L->frame_size;
   const int F = job->units, s16 = L->group_s16;
@@ -1265,10 +1267,12 @@ typedef struct {
   uint32_t *rsize;
   int *units_done;
   int units, flush;
+  int base;
 } ih_out_job;
 static size_t pcm_bytes(IAMF_DecoderHandle h, int samples);
-static void out_handle(void *v, int i) {
+static void out_handle(void *v, int idx) {
   const ih_out_job *job = (const ih_out_job *)v;
+  const int i = job->base + idx;
   IAMF_DecoderHandle h = job->hs[i], L = job->hs[0];
   const int F = job->units;
   if (job->rsize) job->rsize[i] = job->flush ? 0 : h->unit_used;
@@ -1292,6 +1296,52 @@ static void out_handle(void *v, int i) {
   job->ret[i] = (real == 0 && err) ? err : real;
 }
 
+typedef struct {
+  ih_step_job step;
+  ih_out_job out;
+} ih_group_step;
+
+static void group_fill(void *user, int s_lo, int s_cnt, iamfb_io *io) {
+  ih_group_step *gs = (ih_group_step *)user;
+  IAMF_DecoderHandle *hs = gs->step.hs, L = hs[0];
+  const int F = gs->step.units;
+  const size_t N = (size_t)L->frame_size;
+  ih_step_job job = gs->step;
+  job.base = s_lo;
+  pool_for(s_cnt, step_handle, &job);
+  int any_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, any_out_ramp = 0;
+  for (int i = s_lo; i < s_lo + s_cnt; ++i)
+    for (int f = 0; f < F; ++f) {
+      const int fl = hs[i]->unit_flags[f];
+      any_ramp[0] |= fl & 1; any_ramp[1] |= (fl >> 1) & 1; any_out_ramp |= (fl >> 2) & 1;
+    }
+  /* a ramp array applies to the whole group of streams: members with a constant gain get a constant ramp (a constant the
+   * reference would skip - exactly 1 or not positive, IAMF_decoder.c:1392 - becomes 1.0, which is exact) */
+  for (int e = 0; e <= L->n_streams; ++e) {
+    const int out = e == L->n_streams;
+    if (!(out ? any_out_ramp : any_ramp[e])) continue;
+    for (int i = s_lo; i < s_lo + s_cnt; ++i)
+      for (int f = 0; f < F; ++f) {
+        if (hs[i]->unit_flags[f] & (out ? 4 : (1 << e))) continue;
+        const iamfb_frame_params *fp = &L->fp_stage[(size_t)i * F + f];
+        float g = out ? fp->out_gain : fp->el[e].mix_gain;
+        if (!(g != 1.f && g > 0.f)) g = 1.f;
+        float *dst = (out ? L->out_ramp : L->ramp[e]) + ((size_t)i * F + f) * N;
+        for (size_t k = 0; k < N; ++k) dst[k] = g;
+      }
+  }
+  for (int e = 0; e < L->n_streams; ++e) io->gain_ramp[e] = any_ramp[e] ? L->ramp[e] : 0;
+  io->out_gain_ramp = any_out_ramp ? L->out_ramp : 0;
+}
+
+static void group_drain(void *user, int s_lo, int s_cnt) {
+  ih_group_step *gs = (ih_group_step *)user;
+  ih_out_job job = gs->out;
+  job.base = s_lo;
+  job.flush = 0;
+  pool_for(s_cnt, out_handle, &job);
+}
+
 int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
                                     void *const *pcm, int *ret, int max_units, int *units_done) {
   if (!hs || n <= 0 || !data || !size || !ret || !hs[0] || max_units < 1 || max_units > 64) return IAMF_ERR_BAD_ARG;
@@ -1303,9 +1353,8 @@ int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t
   }
   for (int i = 1; i < n; ++i)
     if (!hs[i] || hs[i]->leader != L || hs[i]->group_index != i) return IAMF_ERR_BAD_ARG;
-  const size_t N = (size_t)L->frame_size;
   const int F = max_units;
-  int n_flush = 0, any_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, any_out_ramp = 0;
+  int n_flush = 0;
   for (int i = 0; i < n; ++i) n_flush += data[i] ? 0 : 1;
   if (n_flush && n_flush != n) return IAMF_ERR_UNIMPLEMENTED; /* a group flushes together */
   ih_shared *sh = (ih_shared *)L->shared;
@@ -1315,50 +1364,31 @@ int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t
     pthread_mutex_unlock(&sh->mu);
     if (frc != IAMFB_OK) return IAMF_ERR_INTERNAL;
   } else {
-    /* phase 1 (host, per handle, on the pool): parse, core decode into the handle's slots of the shared pinned buffers */
-    ih_step_job job = {hs, data, size, F};
-    pool_for(n, step_handle, &job);
-    for (int i = 0; i < n; ++i)
-      for (int f = 0; f < F; ++f) {
-        const int fl = hs[i]->unit_flags[f];
-        any_ramp[0] |= fl & 1; any_ramp[1] |= (fl >> 1) & 1; any_out_ramp |= (fl >> 2) & 1;
-      }
-    /* a ramp array applies to the whole group: members with a constant gain get a constant ramp (a constant the
-     * reference would skip - exactly 1 or not positive, IAMF_decoder.c:1392 - becomes 1.0, which is exact) */
-    for (int e = 0; e <= L->n_streams; ++e) {
-      const int out = e == L->n_streams;
-      if (!(out ? any_out_ramp : any_ramp[e])) continue;
-      for (int i = 0; i < n; ++i)
-        for (int f = 0; f < F; ++f) {
-          if (hs[i]->unit_flags[f] & (out ? 4 : (1 << e))) continue;
-          const iamfb_frame_params *fp = &L->fp_stage[(size_t)i * F + f];
-          float g = out ? fp->out_gain : fp->el[e].mix_gain;
-          if (!(g != 1.f && g > 0.f)) g = 1.f;
-          float *dst = (out ? L->out_ramp : L->ramp[e]) + ((size_t)i * F + f) * N;
-          for (size_t k = 0; k < N; ++k) dst[k] = g;
-        }
-    }
-    /* phase 2 (device, once for the group) */
+    /* The step runs group by group of handles (iamfb_batch_submit_host_hooks): phase 1 - parse + core decode of a group
+     * into its slots of the pinned buffers, on the pool - right before the group's upload; phase 3 - its samples back into
+     * the callers' buffers - once its download is done; the device works on the neighbouring groups meanwhile */
+    ih_group_step gs;
+    memset(&gs, 0, sizeof(gs));
+    gs.step.hs = hs; gs.step.data = data; gs.step.size = size; gs.step.units = F;
+    gs.out.hs = hs; gs.out.pcm = pcm; gs.out.ret = ret; gs.out.rsize = rsize; gs.out.units_done = units_done; gs.out.units = F;
     iamfb_io io;
     memset(&io, 0, sizeof(io));
-    for (int e = 0; e < L->n_streams; ++e) {
-      io.in[e] = L->in[e];
-      if (any_ramp[e]) io.gain_ramp[e] = L->ramp[e];
-    }
-    if (any_out_ramp) io.out_gain_ramp = L->out_ramp;
+    for (int e = 0; e < L->n_streams; ++e) io.in[e] = L->in[e];
     io.in_format = L->group_s16 ? IAMFB_IN_S16 : IAMFB_IN_F32;
     io.params = L->fp_stage;
     io.pcm = L->pcm_stage;
     io.out_counts = L->counts_stage;
+    iamfb_chunk_hooks hk = {group_fill, group_drain, &gs};
     pthread_mutex_lock(&sh->mu);
-    const int src = iamfb_batch_submit_host(L->batch, &io, F);
+    const int src = iamfb_batch_submit_host_hooks(L->batch, &io, F, &hk);
     pthread_mutex_unlock(&sh->mu);
     if (src != IAMFB_OK) return IAMF_ERR_INTERNAL;
+    return IAMF_OK;
   }
   /* phase 3 (host, per handle, on the pool): hand every stream's samples back (the frames of a stream lie back to back in
    * its row of the PCM buffer) */
   {
-    ih_out_job oj = {hs, pcm, ret, rsize, units_done, F, n_flush ? 1 : 0};
+    ih_out_job oj = {hs, pcm, ret, rsize, units_done, F, 1, 0};
     pool_for(n, out_handle, &oj);
   }
   return IAMF_OK;

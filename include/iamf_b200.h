@@ -211,6 +211,18 @@ int iamfb_batch_reset(iamfb_batch *batch);  /* back to the state right after IAM
 int iamfb_batch_submit_device(iamfb_batch *batch, const iamfb_io *io, int n_frames);
 /* host-resident: copies inputs H2D (pinned staging), runs, copies pcm + counts back, synchronises */
 int iamfb_batch_submit_host(iamfb_batch *batch, const iamfb_io *io, int n_frames);
+/* the same with the caller producing and consuming its host buffers group by group while the device works on the
+ * neighbouring groups of streams: fill(user, s_lo, s_cnt, io) is called right before the inputs of the streams
+ * [s_lo, s_lo + s_cnt) are uploaded - it writes their slices of in / params / ramps and may set or clear io->gain_ramp[] /
+ * io->out_gain_ramp for this group -, drain(user, s_lo, s_cnt) once their pcm / out_counts slices are back in host memory.
+ * (What the drop-in host layer uses to overlap bitstream parsing + core decode of one group of handles with the upload,
+ * kernels and download of the others.) */
+typedef struct iamfb_chunk_hooks {
+  void (*fill)(void *user, int s_lo, int s_cnt, iamfb_io *io);
+  void (*drain)(void *user, int s_lo, int s_cnt);
+  void *user;
+} iamfb_chunk_hooks;
+int iamfb_batch_submit_host_hooks(iamfb_batch *batch, const iamfb_io *io, int n_frames, const iamfb_chunk_hooks *hooks);
 /* end of stream (IAMF_decoder_decode(data == NULL)): resampler tail + limiter tail. pcm [S][stride for 1 frame],
  * out_counts [S]. */
 int iamfb_batch_flush_device(iamfb_batch *batch, void *pcm, int32_t *out_counts);
