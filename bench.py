@@ -99,6 +99,57 @@ def _cpu_worker(cfg, kind, n_frames, idx, reps, barrier, q):
         q.put((idx, repr(e)))
 
 
+def cpu_reference_c(cfg, n_frames, reps=1, warm=0, distinct=8):
+    """the unmodified reference through its public API from the C harness oracle/ref_harness.c (one thread per host core,
+    every thread renders whole streams start to finish) - no Python in the timed region"""
+    import ctypes as C
+    import refbind
+    import refstreams
+    import scenarios as S
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+    H = C.CDLL(so, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+
+    class RefStream(C.Structure):
+        _fields_ = [("desc", C.c_char_p), ("desc_len", C.c_int), ("n_units", C.c_int), ("units", C.POINTER(C.c_char_p)),
+                    ("unit_len", C.POINTER(C.c_int))]
+
+    class RefJob(C.Structure):
+        _fields_ = [("n_streams", C.c_int), ("streams", C.POINTER(RefStream)), ("renders", C.c_int), ("threads", C.c_int),
+                    ("sound_system", C.c_int), ("bit_depth", C.c_int), ("rate", C.c_int), ("limiter", C.c_int),
+                    ("loudness", C.c_float), ("threshold_db", C.c_float), ("out_channels", C.c_int)]
+    H.ref_harness_run.argtypes = [C.POINTER(RefJob), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    sc, st, api_kw, unit_kw = refstreams.case(cfg)
+    inputs = S.synth_inputs(sc, distinct, n_frames, seed=0x1A3F)
+    P, _, _ = S.synth_params(sc, distinct, n_frames, seed=0x77)
+    refstreams.no_param_gaps(sc, P)
+    desc = st.descriptors()
+    keep, streams = [], (RefStream * distinct)()
+    for s in range(distinct):
+        units = refstreams.temporal_units(sc, st, inputs, P, unit_kw, s)
+        ua = (C.c_char_p * len(units))(*units)
+        ul = (C.c_int * len(units))(*[len(u) for u in units])
+        keep += [units, ua, ul]
+        streams[s] = RefStream(desc, len(desc), len(units), ua, ul)
+    workers = max(1, len(os.sched_getaffinity(0)))
+    job = RefJob(distinct, streams, workers * CPU_RENDERS, workers, -1 if api_kw.get("binaural") else api_kw.get("sound_system", 0),
+                 api_kw.get("bit_depth", 16), api_kw.get("rate", 0), 1 if api_kw.get("limiter", True) else 0,
+                 api_kw.get("loudness", 0.0), api_kw.get("threshold_db", -1.0), sc.out_channels)
+    vals, secs = [], []
+    for k in range(warm + reps):
+        sec, smp = C.c_double(0), C.c_longlong(0)
+        rc = H.ref_harness_run(C.byref(job), C.byref(sec), C.byref(smp))
+        if rc:
+            raise RuntimeError("reference harness: a stream failed to render")
+        if k >= warm:
+            vals.append(smp.value / float(sc.out_rate) / sec.value)
+            secs.append(sec.value)
+    what = (f"{workers} threads (one per host core) x {CPU_RENDERS} streams x {n_frames} frames of the same workload per step, "
+            "unmodified reference decoder (oracle/_ref/libiamf_ref.so) through IAMF_decoder_configure/decode on ipcm-coded "
+            "streams, driven from C (oracle/ref_harness.c)")
+    return dict(value=float(np.mean(vals)), unit="audio-s/s", cores=workers, kind="reference", sample=what,
+                seconds=float(np.mean(secs)), per_rep=vals)
+
+
 def cpu_reference(cfg, n_frames, reps=1, warm=0):
     """times the reference CPU implementation of the path on ALL host cores: one process per core, each rendering
     CPU_RENDERS streams x n_frames frames per rep.  Returns dict(value audio-s/s (mean over reps), per_rep, cores,
@@ -106,6 +157,8 @@ def cpu_reference(cfg, n_frames, reps=1, warm=0):
     import multiprocessing as mp
     import refbind
     kind = "reference" if (refbind.have_ref() and cfg != "c4h") else "port"   # (the reference is built without its binauraliser)
+    if kind == "reference" and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")):
+        return cpu_reference_c(cfg, n_frames, reps, warm)
     import orcbind
     orcbind.lib()   # make sure liboracle.so exists before the workers start (refstreams uses its scalar helpers)
     workers = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
