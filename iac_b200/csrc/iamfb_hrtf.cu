@@ -273,7 +273,8 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
       dim3 grid((groups + 255) / 256, s_cnt * C);
       {
         ScopedKernelTimer tm_(ctx, "k_hrtf_prep");
-        if (s16) k_hrtf_prep<true><<<grid, 256, 0, st>>>(pa);
+        if (s16 && he.plain) k_hrtf_prep_s16<<<grid, 256, 0, st>>>(pa);
+        else if (s16) k_hrtf_prep<true><<<grid, 256, 0, st>>>(pa);
         else k_hrtf_prep<false><<<grid, 256, 0, st>>>(pa);
       }
       HR_LAUNCH_CHECK("k_hrtf_prep");
