@@ -421,26 +421,27 @@ def timed_submits(w, n_submits, barrier):
     return e0.elapsed_time(e1)
 
 
-def copy_ceiling(h2d_bytes, d2h_bytes, dev, reps=5):
-    """the same bytes as plain pinned copies, both directions at once on two streams (what the box's host path can move)"""
+def copy_ceiling(h2d_bytes, d2h_bytes, dev, barrier, reps=5):
+    """the same bytes as plain pinned copies, both directions at once on two streams (what the box's host path can move).
+    Every rep starts behind a barrier, so that under torchrun all ranks copy at the same time; the median rep counts."""
     import torch
     up_h = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
     dn_h = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
     up_d = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
     dn_d = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
     s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    best = None
-    for _ in range(reps + 1):
-        torch.cuda.synchronize()
+    times = []
+    for k in range(reps + 1):
+        barrier()
         t0 = time.perf_counter()
         with torch.cuda.stream(s_up):
             up_d.copy_(up_h, non_blocking=True)
         with torch.cuda.stream(s_dn):
             dn_h.copy_(dn_d, non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best
+        if k:
+            times.append(time.perf_counter() - t0)
+    return float(np.median(times))
 
 
 def api_leg(cfg, n_handles, K, rank, w, shard, dev, distinct=32, calls=6):
@@ -462,6 +463,9 @@ def api_leg(cfg, n_handles, K, rank, w, shard, dev, distinct=32, calls=6):
     L.IAMF_decoder_decode_batch_units.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
                                                   C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
     os.environ["IAMF_B200_DEVICE"] = str(dev.index or 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if "IAMF_B200_HOST_THREADS" not in os.environ:    # the ranks of a box share its host cores
+        os.environ["IAMF_B200_HOST_THREADS"] = str(max(2, len(os.sched_getaffinity(0)) // world))
     n = n_handles
     hs = (vp * n)()
     for i in range(n):
@@ -609,7 +613,7 @@ def run_gpu(args):
     # the same bytes as two plain pinned copies running against each other on this rank (all ranks at once under
     # torchrun): the ceiling the host path of this box sets for the end-to-end step
     barrier()
-    ceil_s = copy_ceiling(int(h2d), int(d2h), dev)
+    ceil_s = copy_ceiling(int(h2d), int(d2h), dev, barrier)
     ceil_ms_max, _ = shard.aggregate(ceil_s * 1e3, 0.0, device=dev)
     del h_in, h_pcm
 
@@ -687,7 +691,7 @@ def run_gpu(args):
                     "frames_per_step": Fe, "steps": ke, "ms_per_step": te_max_ms / ke, "input": "int16 PCM as decoded (IAMFB_IN_S16)",
                     "gpu_launches": int(e2e_launches),
                     "copy_ceiling_ms": ceil_ms_max, "frac_of_copy_ceiling": ceil_ms_max / (te_max_ms / ke),
-                    "copy_ceiling_note": "the step's H2D and D2H bytes as two plain pinned copies running against each other, all ranks at once"},
+                    "copy_ceiling_note": "the step's H2D and D2H bytes as two plain pinned copies running against each other, all ranks at once behind a barrier (median of 5), max over ranks"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -726,9 +730,9 @@ def run_reference(args):
 
 
 def main():
-    # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints exactly ONE line on stdout: NCCL's version banner (printed at NCCL_DEBUG=VERSION and above) and
+    # anything else it logs go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
