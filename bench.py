@@ -100,8 +100,8 @@ def _cpu_worker(cfg, kind, n_frames, idx, reps, barrier, q):
 
 
 def cpu_reference_c(cfg, n_frames, reps=1, warm=0, distinct=8):
-    """the unmodified reference through its public API from the C harness oracle/ref_harness.c (one thread per host core,
-    every thread renders whole streams start to finish) - no Python in the timed region"""
+    """the unmodified reference through its public API from the C harness oracle/ref_harness.c (one worker process per host
+    core, every worker renders whole streams start to finish) - no Python in the timed region"""
     import ctypes as C
     import refbind
     import refstreams
@@ -143,7 +143,7 @@ def cpu_reference_c(cfg, n_frames, reps=1, warm=0, distinct=8):
         if k >= warm:
             vals.append(smp.value / float(sc.out_rate) / sec.value)
             secs.append(sec.value)
-    what = (f"{workers} threads (one per host core) x {CPU_RENDERS} streams x {n_frames} frames of the same workload per step, "
+    what = (f"{workers} worker processes (one per host core) x {CPU_RENDERS} streams x {n_frames} frames of the same workload per step, "
             "unmodified reference decoder (oracle/_ref/libiamf_ref.so) through IAMF_decoder_configure/decode on ipcm-coded "
             "streams, driven from C (oracle/ref_harness.c)")
     return dict(value=float(np.mean(vals)), unit="audio-s/s", cores=workers, kind="reference", sample=what,
