@@ -65,7 +65,8 @@ def frame_params_array(n_streams, n_frames):
 
 class Io(C.Structure):
     _fields_ = [("in_", C.c_void_p * MAXE), ("params", C.c_void_p), ("gain_ramp", C.c_void_p * MAXE),
-                ("out_gain_ramp", C.c_void_p), ("pcm", C.c_void_p), ("out_counts", C.c_void_p), ("in_format", C.c_int32)]
+                ("out_gain_ramp", C.c_void_p), ("pcm", C.c_void_p), ("out_counts", C.c_void_p), ("in_format", C.c_int32),
+                ("gain_segs", C.c_void_p * MAXE), ("out_gain_segs", C.c_void_p)]
 
 
 _lib = None

@@ -161,6 +161,8 @@ struct iamfb_batch {
   int32_t *d_counts;
   size_t stage_frames;     // frames the staging buffers are sized for (0 = not allocated)
   iamfb_hrtf_batch *hrtf;  // per-stream buffers of the binaural HRTF front end
+  float *d_seg_ramp[kMaxEl], *d_seg_oramp;   // per-sample gains expanded from gain segments (k_gain_expand)
+  iamfb_gain_ramp *d_segs[kMaxEl + 1];       // host-resident submits: the uploaded segment records
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1417,6 +1419,9 @@ extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
   cudaFree(b->d_hist_y); cudaFree(b->d_hist_pk);
   for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_wide[e]);
   iamfb_hrtf_batch_destroy(b->hrtf);
+  for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_seg_ramp[e]);
+  cudaFree(b->d_seg_oramp);
+  for (int e = 0; e <= kMaxEl; ++e) cudaFree(b->d_segs[e]);
   free_staging(b);
   delete b;
 }
@@ -1529,6 +1534,60 @@ static int widen_streams(iamfb_batch *b, const iamfb_io *io, int F, int s_lo, in
   return IAMFB_OK;
 }
 
+// ---- k_gain_expand: animated mix gains from their parameter segments (iamfb_gain_ramp) to per-sample gains, with the
+// reference's expressions in the reference's precision (mix_gain_bezier_linear / _quad, IAMF_decoder.c:639-664; pow(x, 2)
+// of a double is x * x exactly).  One block per (stream, frame); a frame without segments gets the constant of its
+// iamfb_frame_params (a constant the reference would skip - exactly 1 or not positive, :1392 - becomes 1.0: exact).
+static __global__ void __launch_bounds__(256) k_gain_expand(const iamfb_gain_ramp *__restrict__ segs, const iamfb_frame_params *__restrict__ params,
+                                                            float *__restrict__ ramp, int N, int element) {
+  const size_t sf = blockIdx.x;
+  const iamfb_gain_ramp &r = segs[sf];
+  float *g = ramp + sf * (size_t)N;
+  if (r.n_segs <= 0) {
+    float c = element < 0 ? params[sf].out_gain : params[sf].el[element].mix_gain;
+    if (!(c != 1.f && c > 0.f)) c = 1.f;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) g[k] = c;
+    return;
+  }
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    int base = 0, q = 0;
+    while (q < r.n_segs && q < IAMFB_MAX_GAIN_SEGS && k >= base + r.seg[q].count) base += r.seg[q++].count;
+    float v = 1.f;
+    if (q < r.n_segs && q < IAMFB_MAX_GAIN_SEGS) {
+      const iamfb_gain_seg &sg = r.seg[q];
+      const int i = sg.offset + (k - base);
+      const float s = sg.start, e = sg.end, c = sg.control;
+      if (sg.type == 0) {
+        v = s;
+      } else if (sg.type == 1) {
+        v = s + (e - s) * i / sg.interval;
+      } else {
+        const long long alpha = (long long)sg.interval - 2 * (long long)sg.ct;
+        float a;
+        if (alpha) {
+          a = (float)((sqrt((double)sg.ct * (double)sg.ct + (double)(alpha * i)) - (double)sg.ct) / (double)alpha);
+        } else {
+          a = (float)i;
+          a /= (float)(2 * sg.ct);
+        }
+        v = (float)((double)(s + e - 2 * c) * ((double)a * (double)a) + (double)(2 * a * (c - s)) + (double)s);
+      }
+    }
+    g[k] = v;
+  }
+}
+
+// per-batch float ramp buffers for device-resident submits with gain segments (host-resident submits use the staging ones)
+static int ensure_ramps(iamfb_batch *b) {
+  const KernelPlan &kp = b->plan->kp;
+  const size_t n = (size_t)b->S * b->Fmax * kp.frame_size;
+  for (int e = 0; e <= kp.n_elements; ++e) {
+    float **p = e == kp.n_elements ? &b->d_seg_oramp : &b->d_seg_ramp[e];
+    if (!*p && cudaMalloc((void **)p, sizeof(float) * n) != cudaSuccess) return fail(IAMFB_ERR_ALLOC_FAIL, "gain ramp buffers");
+  }
+  return IAMFB_OK;
+}
+
 // runs the kernels of one submit (or flush) for the streams [s_lo, s_lo + s_cnt) of the batch; all pointers in `io`,
 // `pcm` and `counts` are DEVICE pointers to the whole batch's arrays (stream 0 first)
 static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, void *pcm, int32_t *counts, size_t stride,
@@ -1538,7 +1597,30 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   const KernelPlan &kp = p->kp;
   cudaStream_t st = ctx->stream;
   if (s_cnt < 0) s_cnt = b->S;
-  iamfb_io wio, hio;
+  iamfb_io wio, hio, gio;
+  if (!flush && (io->gain_segs[0] || io->gain_segs[1] || io->out_gain_segs)) {
+    // animated mix gains arrive as parameter segments: evaluated here, on the device, into the ramp arrays the kernels read
+    int r = ensure_ramps(b);
+    if (r) return r;
+    gio = *io;
+    const size_t off = (size_t)s_lo * F;
+    for (int e = 0; e <= kp.n_elements; ++e) {
+      const bool out = e == kp.n_elements;
+      const iamfb_gain_ramp *sg = out ? io->out_gain_segs : io->gain_segs[e];
+      if (!sg) continue;
+      float *dst = out ? b->d_seg_oramp : b->d_seg_ramp[e];
+      {
+        ScopedKernelTimer tm_(ctx, "k_gain_expand");
+        k_gain_expand<<<(unsigned)((size_t)s_cnt * F), 256, 0, st>>>(sg + off, io->params + off, dst + off * kp.frame_size, kp.frame_size, out ? -1 : e);
+      }
+      cudaError_t e_ = cudaGetLastError();
+      if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_gain_expand failed: %s", cudaGetErrorString(e_));
+      ++ctx->launches;
+      if (out) { gio.out_gain_ramp = dst; gio.out_gain_segs = nullptr; }
+      else { gio.gain_ramp[e] = dst; gio.gain_segs[e] = nullptr; }
+    }
+    io = &gio;
+  }
   if (p->hrtf && !flush) {
     // binaural HRTF front end: the elements it renders reach the kernels below as float32 [2][N] frames
     int r = iamfb_hrtf_run(ctx, p->hrtf, b->hrtf, io, F, s_lo, s_cnt, &hio);
@@ -1921,6 +2003,16 @@ static int submit_host(iamfb_batch *b, const iamfb_io *io_in, int F, const iamfb
     if (io.out_gain_ramp) {
       CU(cudaMemcpyAsync(b->d_oramp + s_lo * F * N, io.out_gain_ramp + s_lo * F * N, sizeof(float) * cnt * F * N, cudaMemcpyHostToDevice, ctx->h2d));
       dio.out_gain_ramp = b->d_oramp;
+    }
+    // ... or their parameter segments (272 bytes per frame), expanded on the device by run_pipeline
+    for (int e = 0; e <= kp.n_elements; ++e) {
+      const iamfb_gain_ramp *sg = e == kp.n_elements ? io.out_gain_segs : io.gain_segs[e];
+      if (!sg) continue;
+      if (!b->d_segs[e] && cudaMalloc((void **)&b->d_segs[e], sizeof(iamfb_gain_ramp) * S * b->Fmax) != cudaSuccess)
+        return fail(IAMFB_ERR_ALLOC_FAIL, "gain segment staging");
+      CU(cudaMemcpyAsync(b->d_segs[e] + s_lo * F, sg + s_lo * F, sizeof(iamfb_gain_ramp) * cnt * F, cudaMemcpyHostToDevice, ctx->h2d));
+      if (e == kp.n_elements) dio.out_gain_segs = b->d_segs[e];
+      else dio.gain_segs[e] = b->d_segs[e];
     }
     CU(cudaMemcpyAsync(b->d_params + s_lo * F, io.params + s_lo * F, sizeof(iamfb_frame_params) * cnt * F, cudaMemcpyHostToDevice, ctx->h2d));
     for (int e = 0; e < kp.n_elements; ++e) {

@@ -200,7 +200,7 @@ static void engine_release(IAMF_DecoderHandle h) {
   shared_release((ih_shared *)h->shared);
   h->shared = 0;
   h->batch = 0; h->plan = 0; h->ctx = 0;
-  for (int e = 0; e < IAMFB_MAX_ELEMENTS; ++e) h->in[e] = h->ramp[e] = 0;
+  for (int e = 0; e < IAMFB_MAX_ELEMENTS; ++e) { h->in[e] = 0; h->ramp[e] = 0; }
   h->out_ramp = 0; h->pcm_stage = 0; h->fp_stage = 0; h->counts_stage = 0;
   h->group_owner = 1; h->group_size = 1; h->group_index = 0; h->leader = 0;
   h->group_units = 0; h->group_s16 = 0;
@@ -529,10 +529,10 @@ static int engine_private(IAMF_DecoderHandle h) {
   const size_t N = (size_t)d->frame_size;
   for (int e = 0; e < h->n_streams; ++e) {
     h->in[e] = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)d->el[e].n_in);
-    h->ramp[e] = (float *)iamfb_host_alloc(sizeof(float) * N);
+    h->ramp[e] = (iamfb_gain_ramp *)iamfb_host_alloc(sizeof(iamfb_gain_ramp));
     if (!h->in[e] || !h->ramp[e]) return IAMF_ERR_ALLOC_FAIL;
   }
-  h->out_ramp = (float *)iamfb_host_alloc(sizeof(float) * N);
+  h->out_ramp = (iamfb_gain_ramp *)iamfb_host_alloc(sizeof(iamfb_gain_ramp));
   h->pcm_stage = (uint8_t *)iamfb_host_alloc(h->pcm_stage_size);
   h->fp_stage = (iamfb_frame_params *)iamfb_host_alloc(sizeof(iamfb_frame_params));
   h->counts_stage = (int32_t *)iamfb_host_alloc(sizeof(int32_t));
@@ -925,15 +925,19 @@ static uint32_t parse_obus(IAMF_DecoderHandle h, const uint8_t *data, uint32_t s
 /* Host part of one temporal unit: core decode of every element into `in[e]`, per-frame parameters into *fp.
  * returns >0 frame ready (samples entering the engine after trimming), 0 dropped / nothing, <0 error.
  * (the loop body of iamf_decoder_internal_decode, IAMF_decoder.c:3336-3457, up to where samples are touched) */
-static int prepare_frame(IAMF_DecoderHandle h, void *const in[], int s16, iamfb_frame_params *fp, float *const ramp[], float *out_ramp,
-                         int *use_ramp, int *use_out_ramp) {
+static int prepare_frame(IAMF_DecoderHandle h, void *const in[], int s16, iamfb_frame_params *fp, iamfb_gain_ramp *const ramp[],
+                         iamfb_gain_ramp *out_ramp, int *use_ramp, int *use_out_ramp) {
   const int N = h->frame_size;
   int lret = 1, real = 0;
   uint64_t frame_pts = 0;
   memset(fp, 0, sizeof(*fp));
   fp->out_gain = 1.0f;
-  for (int e = 0; e < IAMFB_MAX_ELEMENTS; ++e) { fp->el[e].dmx_mode = -1; fp->el[e].mix_gain = 1.0f; use_ramp[e] = 0; }
+  for (int e = 0; e < IAMFB_MAX_ELEMENTS; ++e) {
+    fp->el[e].dmx_mode = -1; fp->el[e].mix_gain = 1.0f; use_ramp[e] = 0;
+    if (ramp[e]) ramp[e]->n_segs = 0;
+  }
   *use_out_ramp = 0;
+  out_ramp->n_segs = 0;
   for (int s = 0; s < h->n_streams; ++s) {
     ih_stream *st = &h->streams[s];
     const ih_element *el = st->el;
@@ -992,6 +996,7 @@ static int prepare_frame(IAMF_DecoderHandle h, void *const in[], int s16, iamfb_
       int kind = ih_mix_gain_unit(st->mix_gain, pts + (uint64_t)st->strim, samples, st->cc->rate, &g, ramp[s]);
       if (kind == 1) fp->el[s].mix_gain = g;
       else if (kind == 2) use_ramp[s] = 1;
+      else if (kind < 0) lret = IAMF_ERR_UNIMPLEMENTED;   /* a frame spanning more than 8 gain segments */
     }
     if (el->type == AUDIO_ELEMENT_CHANNEL_BASED && h->metadata.param && st->dmx_mode >= 0)
       h->metadata.param->dmixp_mode = (uint32_t)st->dmx_mode;
@@ -1007,6 +1012,7 @@ static int prepare_frame(IAMF_DecoderHandle h, void *const in[], int s16, iamfb_
     int kind = ih_mix_gain_unit(h->out_gain_item, frame_pts + (uint64_t)h->streams[0].strim, real, h->streams[0].cc->rate, &g, out_ramp);
     if (kind == 1) fp->out_gain = g;
     else if (kind == 2) *use_out_ramp = 1;
+    else if (kind < 0) return IAMF_ERR_UNIMPLEMENTED;
   }
   ih_params_elapse(h, (uint64_t)real, (uint32_t)h->streams[0].cc->rate);
   return real;
@@ -1040,9 +1046,9 @@ int IAMF_decoder_decode(IAMF_DecoderHandle h, const uint8_t *data, int32_t size,
     memset(&io, 0, sizeof(io));
     for (int e = 0; e < h->n_streams; ++e) {
       io.in[e] = h->in[e];
-      if (use_ramp[e]) io.gain_ramp[e] = h->ramp[e];
+      if (use_ramp[e]) io.gain_segs[e] = h->ramp[e];
     }
-    if (use_out_ramp) io.out_gain_ramp = h->out_ramp;
+    if (use_out_ramp) io.out_gain_segs = h->out_ramp;
     if (ready <= 0) {
       /* dropped frame: keep the device-side parameter state in step (trim == frame size), return what decode did */
       if (ready == 0) {
@@ -1180,12 +1186,12 @@ static int group_build(IAMF_DecoderHandle *hs, int n, int units) {
   for (int e = 0; e < L->n_streams; ++e) {
     iamfb_host_free(L->in[e]); iamfb_host_free(L->ramp[e]);
     L->in[e] = (float *)iamfb_host_alloc(esz * N * (size_t)L->desc.el[e].n_in * (size_t)n * F);
-    L->ramp[e] = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)n * F);
+    L->ramp[e] = (iamfb_gain_ramp *)iamfb_host_alloc(sizeof(iamfb_gain_ramp) * (size_t)n * F);
     if (!L->in[e] || !L->ramp[e]) return IAMF_ERR_ALLOC_FAIL;
   }
   iamfb_host_free(L->out_ramp); iamfb_host_free(L->pcm_stage); iamfb_host_free(L->fp_stage); iamfb_host_free(L->counts_stage);
   L->pcm_stage_size = iamfb_plan_out_stride_bytes(L->plan, units);
-  L->out_ramp = (float *)iamfb_host_alloc(sizeof(float) * N * (size_t)n * F);
+  L->out_ramp = (iamfb_gain_ramp *)iamfb_host_alloc(sizeof(iamfb_gain_ramp) * (size_t)n * F);
   L->pcm_stage = (uint8_t *)iamfb_host_alloc(L->pcm_stage_size * (size_t)n);
   L->fp_stage = (iamfb_frame_params *)iamfb_host_alloc(sizeof(iamfb_frame_params) * (size_t)n * F);
   L->counts_stage = (int32_t *)iamfb_host_alloc(sizeof(int32_t) * (size_t)n * F);
@@ -1236,10 +1242,10 @@ static void step_handle(void *v, int idx) {
   for (int f = 0; f < F && pos < (uint32_t)job->size[i]; ++f) {
     iamfb_frame_params *fp = &L->fp_stage[(size_t)i * F + f];
     void *in[IAMFB_MAX_ELEMENTS] = {0, 0};
-    float *ramp[IAMFB_MAX_ELEMENTS] = {0, 0};
+    iamfb_gain_ramp *ramp[IAMFB_MAX_ELEMENTS] = {0, 0};
     for (int e = 0; e < L->n_streams; ++e) {
       in[e] = (uint8_t *)L->in[e] + ((size_t)i * F + f) * N * (size_t)L->desc.el[e].n_in * esz;
-      ramp[e] = L->ramp[e] + ((size_t)i * F + f) * N;
+      ramp[e] = L->ramp[e] + ((size_t)i * F + f);
     }
     int run = 0, use_ramp[IAMFB_MAX_ELEMENTS] = {0, 0}, use_out = 0;
     uint32_t used = parse_obus(h, job->data[i] + pos, (uint32_t)job->size[i] - pos, &run, 1);
@@ -1247,7 +1253,7 @@ static void step_handle(void *v, int idx) {
     h->unit_used = pos;
     if (h->status == IH_STATUS_RECONFIGURE) { h->unit_ret[f] = IAMF_ERR_INVALID_STATE; break; }
     if (h->status != IH_STATUS_RUN) break;      /* the buffer ended inside a temporal unit: the rest comes with the next call */
-    int ready = prepare_frame(h, in, s16, fp, ramp, L->out_ramp + ((size_t)i * F + f) * N, use_ramp, &use_out);
+    int ready = prepare_frame(h, in, s16, fp, ramp, L->out_ramp + ((size_t)i * F + f), use_ramp, &use_out);
     h->status = IH_STATUS_RECEIVE;
     ++h->units_done;
     if (ready < 0) { h->unit_ret[f] = ready; fp->trim_start = 0xFFFF; continue; }
@@ -1305,7 +1311,6 @@ static void group_fill(void *user, int s_lo, int s_cnt, iamfb_io *io) {
   ih_group_step *gs = (ih_group_step *)user;
   IAMF_DecoderHandle *hs = gs->step.hs, L = hs[0];
   const int F = gs->step.units;
-  const size_t N = (size_t)L->frame_size;
   ih_step_job job = gs->step;
   job.base = s_lo;
   pool_for(s_cnt, step_handle, &job);
@@ -1315,23 +1320,17 @@ static void group_fill(void *user, int s_lo, int s_cnt, iamfb_io *io) {
       const int fl = hs[i]->unit_flags[f];
       any_ramp[0] |= fl & 1; any_ramp[1] |= (fl >> 1) & 1; any_out_ramp |= (fl >> 2) & 1;
     }
-  /* a ramp array applies to the whole group of streams: members with a constant gain get a constant ramp (a constant the
-   * reference would skip - exactly 1 or not positive, IAMF_decoder.c:1392 - becomes 1.0, which is exact) */
-  for (int e = 0; e <= L->n_streams; ++e) {
-    const int out = e == L->n_streams;
-    if (!(out ? any_out_ramp : any_ramp[e])) continue;
-    for (int i = s_lo; i < s_lo + s_cnt; ++i)
-      for (int f = 0; f < F; ++f) {
-        if (hs[i]->unit_flags[f] & (out ? 4 : (1 << e))) continue;
-        const iamfb_frame_params *fp = &L->fp_stage[(size_t)i * F + f];
-        float g = out ? fp->out_gain : fp->el[e].mix_gain;
-        if (!(g != 1.f && g > 0.f)) g = 1.f;
-        float *dst = (out ? L->out_ramp : L->ramp[e]) + ((size_t)i * F + f) * N;
-        for (size_t k = 0; k < N; ++k) dst[k] = g;
-      }
-  }
-  for (int e = 0; e < L->n_streams; ++e) io->gain_ramp[e] = any_ramp[e] ? L->ramp[e] : 0;
-  io->out_gain_ramp = any_out_ramp ? L->out_ramp : 0;
+  /* a segment array applies to the whole group of streams: frames without segments (n_segs 0; every slot without a
+   * frame too) take the constant of their iamfb_frame_params on the device */
+  for (int i = s_lo; i < s_lo + s_cnt; ++i)
+    for (int f = 0; f < F; ++f) {
+      const int fl = hs[i]->unit_flags[f];
+      for (int e = 0; e < L->n_streams; ++e)
+        if (!(fl & (1 << e))) L->ramp[e][(size_t)i * F + f].n_segs = 0;
+      if (!(fl & 4)) L->out_ramp[(size_t)i * F + f].n_segs = 0;
+    }
+  for (int e = 0; e < L->n_streams; ++e) io->gain_segs[e] = any_ramp[e] ? L->ramp[e] : 0;
+  io->out_gain_segs = any_out_ramp ? L->out_ramp : 0;
 }
 
 static void group_drain(void *user, int s_lo, int s_cnt) {

@@ -202,7 +202,7 @@ struct IAMF_Decoder {
   iamfb_batch *batch;
   iamfb_plan_desc desc;
   float *in[IAMFB_MAX_ELEMENTS];      /* pinned: decoded planar frame of each element */
-  float *ramp[IAMFB_MAX_ELEMENTS], *out_ramp;
+  iamfb_gain_ramp *ramp[IAMFB_MAX_ELEMENTS], *out_ramp;   /* pinned: animated mix gains as parameter segments, per frame slot */
   uint8_t *pcm_stage;
   size_t pcm_stage_size;               /* bytes per stream */
   iamfb_frame_params *fp_stage;
@@ -238,8 +238,9 @@ void ih_param_push(ih_param_item *pi, ih_segment *segs);
 void ih_param_clear(ih_param_item *pi);
 const ih_segment *ih_param_segment_at(const ih_param_item *pi, uint64_t pts);
 void ih_params_elapse(struct IAMF_Decoder *d, uint64_t duration, uint32_t rate);
-/* returns 0 = no unit, 1 = constant in *gain, 2 = per-sample gains written to ramp[0..count) */
-int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rate, float *gain, float *ramp);
+/* returns 0 = no unit, 1 = constant in *gain, 2 = animated: the covering parameter segments in *segs (evaluated on the
+ * device), -1 = more segments than iamfb_gain_ramp holds */
+int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rate, float *gain, iamfb_gain_ramp *segs);
 
 /* iamf_codec.c */
 int ih_codec_supported(int codec);

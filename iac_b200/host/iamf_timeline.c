@@ -94,31 +94,22 @@ void ih_params_elapse(struct IAMF_Decoder *d, uint64_t duration, uint32_t rate) 
   }
 }
 
-/* mix_gain_bezier_linear / _quad, IAMF_decoder.c:639-664 */
-static void ramp_linear(float s, float e, int d, int o, int l, float *g) {
-  int oe = o + l;
-  for (int i = o, k = 0; i < oe; ++i, ++k) g[k] = s + (e - s) * i / d;
-}
-
-static void ramp_bezier(float s, float e, int d, float c, int ct, int o, int l, float *g) {
-  int oe = o + l;
-  int64_t alpha = d - 2 * ct;
-  float a = 1.0f;
-  for (int i = o, k = 0; i < oe; ++i, ++k) {
-    if (alpha) {
-      a = (sqrt(pow(ct, 2) + alpha * i) - ct) / alpha;
-    } else {
-      a = i;
-      a /= (2 * ct);
-    }
-    g[k] = (s + e - 2 * c) * pow(a, 2) + 2 * a * (c - s) + s;
-  }
-}
-
 /* iamf_database_parameter_get_mix_gain_unit, IAMF_decoder.c:857-982.
  * returns 0 when there is no unit (or the unit covers fewer samples than the frame: iamf_frame_gain then applies
- * nothing, :1385-1390), 1 for a constant, 2 for per-sample gains. */
-int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rate, float *gain, float *ramp) {
+ * nothing, :1385-1390), 1 for a constant in *gain, 2 for an animated gain: *segs then lists the parameter segments that
+ * cover the frame's samples - which segment, from which position inside it, for how many samples - and the per-sample
+ * gains (mix_gain_bezier_linear / _quad, :639-664) are evaluated on the device (k_gain_expand);
+ * -1 when the frame spans more segments than iamfb_gain_ramp holds. */
+static int seg_push(iamfb_gain_ramp *r, int type, int count, int offset, int interval, int ct, float s, float e, float c) {
+  if (count <= 0) return 0;
+  if (r->n_segs >= IAMFB_MAX_GAIN_SEGS) return -1;
+  iamfb_gain_seg *g = &r->seg[r->n_segs++];
+  g->type = type; g->count = count; g->offset = offset; g->interval = interval; g->ct = ct;
+  g->start = s; g->end = e; g->control = c;
+  return 0;
+}
+
+int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rate, float *gain, iamfb_gain_ramp *segs) {
   if (!pi) return 0;
   uint64_t start = 0;
   int use_default = 0;
@@ -131,8 +122,9 @@ int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rat
   float ratio = 1.f;
   if ((uint64_t)rate != pi->def->rate) ratio = (rate + 0.1f) / pi->def->rate;
   int64_t sgd = 0;
-  int left = duration, count = 0, have_ramp = 0;
+  int left = duration, count = 0, have_ramp = 0, overflow = 0;
   float constant = 0.f;
+  segs->n_segs = 0;
   for (const ih_segment *seg = pi->head; seg; seg = seg->next) {
     int64_t minterval = (int64_t)(seg->interval * ratio);
     sgd += minterval;
@@ -144,13 +136,13 @@ int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rat
         } else if (!count) {
           have_ramp = 1;
           count = (int)(sgd - (int64_t)start);
-          for (int i = 0; i < count; ++i) ramp[i] = seg->g_start;
+          overflow |= seg_push(segs, 0, count, 0, 0, 0, seg->g_start, 0.f, 0.f);
           start = (uint64_t)sgd;
         } else {
           int e = count + (int)minterval;
           if (e >= duration) e = duration;
           else start = (uint64_t)sgd;
-          for (int i = count; i < e; ++i) ramp[i] = seg->g_start;
+          overflow |= seg_push(segs, 0, e - count, 0, 0, 0, seg->g_start, 0.f, 0.f);
           count = e;
         }
       } else {
@@ -166,19 +158,20 @@ int ih_mix_gain_unit(const ih_param_item *pi, uint64_t pt, int duration, int rat
           left -= dd;
         }
         if (seg->anim == ANIMATION_TYPE_LINEAR)
-          ramp_linear(seg->g_start, seg->g_end, (int)minterval, off, dd, ramp + count);
+          overflow |= seg_push(segs, 1, dd, off, (int)minterval, 0, seg->g_start, seg->g_end, 0.f);
         else
-          ramp_bezier(seg->g_start, seg->g_end, (int)minterval, seg->g_control,
-                      (int)(seg->g_ctime * (minterval + .1f)), off, dd, ramp + count);
+          overflow |= seg_push(segs, 2, dd, off, (int)minterval, (int)(seg->g_ctime * (minterval + .1f)), seg->g_start, seg->g_end,
+                               seg->g_control);
         count += dd;
       }
     }
     if (count == duration) break;
   }
-  if (duration > count) return 0;
+  if (duration > count) { segs->n_segs = 0; return 0; }
   if (!have_ramp) {
+    segs->n_segs = 0;
     *gain = constant;
     return 1;
   }
-  return 2;
+  return overflow ? -1 : 2;
 }

@@ -145,6 +145,25 @@ typedef struct iamfb_frame_params {
                                    trim_start == 0xFFFF: the stream has NO frame in this step (its state is untouched) */
 } iamfb_frame_params;
 
+/* Animated mix gain of one (stream, frame) as the parameter segments that cover the frame's samples after trimming
+ * (iamf_database_parameter_get_mix_gain_unit, IAMF_decoder.c:857-982): the per-sample gains are evaluated ON THE DEVICE
+ * with the reference's expressions (mix_gain_bezier_linear / _quad, :639-664) instead of travelling as N floats per frame.
+ *   type 0 step:   g = start
+ *   type 1 linear: g = start + (end - start) * i / interval                       (float)
+ *   type 2 Bezier: alpha = interval - 2 ct;  a = alpha ? (sqrt(ct^2 + alpha i) - ct) / alpha : i / (2 ct)   (double / float)
+ *                  g = (start + end - 2 control) a^2 + 2 a (control - start) + start                        (double)
+ * for i = offset .. offset + count - 1 (position inside the segment).  n_segs == 0: the constant of iamfb_frame_params
+ * applies to the frame. */
+#define IAMFB_MAX_GAIN_SEGS 8
+typedef struct iamfb_gain_seg {
+  int32_t type, count, offset, interval, ct;
+  float start, end, control;
+} iamfb_gain_seg;
+typedef struct iamfb_gain_ramp {
+  int32_t n_segs, pad_[3];
+  iamfb_gain_seg seg[IAMFB_MAX_GAIN_SEGS];
+} iamfb_gain_ramp;
+
 typedef struct iamfb_ctx iamfb_ctx;
 typedef struct iamfb_plan iamfb_plan;
 typedef struct iamfb_batch iamfb_batch;
@@ -156,6 +175,8 @@ typedef struct iamfb_batch iamfb_batch;
  *   params         iamfb_frame_params [S][F]
  *   gain_ramp[e]   optional float32 [S][F][N]   per-sample element mix gains (animated mix gain), NULL = constants
  *   out_gain_ramp  optional float32 [S][F][N]
+ *   gain_segs[e]   optional iamfb_gain_ramp [S][F]  the same as parameter segments, evaluated on the device (takes the
+ *   out_gain_segs                                   place of the float arrays; k_gain_expand)
  *   pcm            bytes [S][out_stride_bytes]  interleaved PCM of each stream, out_counts tell how much is valid
  *   out_counts     int32 [S][F]                 samples per channel produced by each frame (what IAMF_decoder_decode
  *                                               returns for that temporal unit)
@@ -173,6 +194,8 @@ typedef struct iamfb_io {
                           [S][F][n_in][N] shape - what Opus / AAC / 16-bit ipcm core decode produces BEFORE the codec glue
                           scales it by 1/32768 (opus/IAMF_opus_decoder.c:133-135); the scaling then happens on the
                           device (exact: a power of two), halving the host-to-device traffic */
+  const iamfb_gain_ramp *gain_segs[IAMFB_MAX_ELEMENTS];
+  const iamfb_gain_ramp *out_gain_segs;
 } iamfb_io;
 
 /* ---- context: one per GPU / host thread ---- */

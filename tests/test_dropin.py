@@ -308,3 +308,91 @@ def test_binauraliser_switch_through_the_public_api(monkeypatch):
         monkeypatch.delenv("IAMF_B200_BINAURALIZER")
         pcm, counts = api.render(desc, units, **api_kw)
         assert pcm.tobytes() == ref_asbuilt[s][1].tobytes(), f"stream {s}: as built"
+
+
+def _animated_units(st, sc, inputs, P, n_frames, seed, trim_first=0):
+    """temporal units whose element / output mix gains are animated: step, linear and Bezier parameter blocks"""
+    rng = np.random.default_rng(seed)
+    units = []
+    for f in range(n_frames):
+        mg = {}
+        for pid in [e.mixgain_pid() for e in st.elements] + [st.OUT_GAIN_PID]:
+            kind = int(rng.integers(0, 4))
+            q = [int(v) for v in rng.integers(-0x0600, 0x0200, 3)]
+            if kind == 0:
+                continue                                     # no block this frame: the default gain applies
+            mg[pid] = ("step", q[0]) if kind == 1 else (("linear", q[0], q[1]) if kind == 2 else
+                                                         ("bezier", q[0], q[1], q[2], int(rng.integers(1, 255))))
+        pcm = [refstreams.to_i16(inputs[e][0, f]) for e in range(len(sc.elements))]
+        units.append(st.temporal_unit(pcm, mix_gain=mg, trim_start=trim_first if f == 0 else 0))
+    return units
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,trim", [("c1", 0), ("c1", 312), ("c4", 0), ("c5", 100)])
+def test_animated_mix_gains_match_the_reference(cfg, trim):
+    """element and output mix gains animated per frame (step / linear / quadratic Bezier parameter blocks,
+    IAMF_decoder.c:639-664,857-982), a start-trimmed first frame (the gain time line is read at the pts AFTER trimming,
+    :1379): the drop-in library against the compiled reference, byte for byte.  The ramps are evaluated ON THE DEVICE from
+    the segment descriptions (k_gain_expand)."""
+    import refbind
+    if not refbind.have_ref():
+        pytest.skip("compiled reference not available")
+    sc, st, api_kw, unit_kw = refstreams.case(cfg)
+    F = 9
+    inputs = S.synth_inputs(sc, 1, F, seed=61)
+    P, _, _ = S.synth_params(sc, 1, F, seed=62)
+    units = _animated_units(st, sc, inputs, P, F, seed=63 + trim, trim_first=trim)
+    desc = st.descriptors()
+    ref_pcm, ref_counts = iamfapi.Api(refbind.REF_SO).render(desc, units, **api_kw)
+    pcm, counts = iamfapi.Api(LIBIAMF).render(desc, units, **api_kw)
+    assert counts == ref_counts
+    assert pcm.tobytes() == ref_pcm.tobytes()
+
+
+@pytest.mark.gpu
+def test_animated_mix_gains_in_a_batch_step():
+    """the same through IAMF_decoder_decode_batch_units: handles with and without animated gains in one group (frames
+    without segments take their constant on the device), several temporal units per call"""
+    import refbind
+    if not refbind.have_ref():
+        pytest.skip("compiled reference not available")
+    sc, st, api_kw, unit_kw = refstreams.case("c1")
+    n, F, K = 7, 8, 3
+    inputs = S.synth_inputs(sc, n, F, seed=71)
+    P, _, _ = S.synth_params(sc, n, F, seed=72)
+    desc = st.descriptors()
+    units = []
+    for s in range(n):
+        one = [x[s:s + 1] for x in inputs]
+        if s % 2:
+            units.append(_animated_units(st, sc, one, P, F, seed=80 + s))
+        else:
+            units.append(refstreams.temporal_units(sc, st, one, P[s:s + 1], unit_kw, 0))
+    ref = [iamfapi.Api(refbind.REF_SO).render(desc, units[s], **api_kw) for s in range(n)]
+    api = iamfapi.Api(LIBIAMF)
+    L = api.L
+    vp = C.c_void_p
+    L.IAMF_decoder_decode_batch_units.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
+                                                  C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+    hs = (vp * n)(*[api.open_configured(desc + units[s][0], **api_kw) for s in range(n)])
+    ch = sc.out_channels
+    bufs = [C.create_string_buffer(2 * 6144 * ch * K) for _ in range(n)]
+    pcm = (vp * n)(*[C.cast(b, vp) for b in bufs])
+    got = [b"" for _ in range(n)]
+    for f0 in list(range(0, F, K)) + [None]:
+        if f0 is None:
+            piece = [None] * n
+        else:
+            piece = [b"".join(units[s][f0:f0 + K]) for s in range(n)]
+        data = (C.c_char_p * n)(*piece)
+        size = (C.c_int32 * n)(*[len(p) if p else 0 for p in piece])
+        rs = (C.c_uint32 * n)()
+        ret = (C.c_int * n)()
+        assert L.IAMF_decoder_decode_batch_units(hs, n, data, size, rs, pcm, ret, K, None) == 0
+        for s in range(n):
+            assert ret[s] >= 0
+            got[s] += bufs[s].raw[: ret[s] * ch * 2]
+    for s in range(n):
+        assert got[s] == ref[s][0].tobytes(), f"handle {s}"
+        L.IAMF_decoder_close(hs[s])
