@@ -58,12 +58,13 @@ def build_cuda(force=False, verbose=False):
 HOST = os.path.join(PKG, "host")
 DROPIN = os.path.join(PKG, "libiamf.so")
 REF_OPUS = "/root/reference/dep_codecs/lib/libopus.a"
+REF_FLAC = "/root/reference/dep_codecs/lib/libFLAC.a"
 
 
 def build_dropin(force=False):
     """the drop-in libiamf.so: plain-C host layer (include/IAMF_decoder.h API) on top of libiamf_b200.so.
-    Opus entropy decode is linked from the reference tree's prebuilt libopus.a when that exists (authoring
-    container); without it the library is built ipcm-only."""
+    Opus / FLAC entropy decode is linked from the reference tree's prebuilt libopus.a / libFLAC.a when they exist
+    (authoring container); without them the library is built ipcm-only."""
     srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".c")]
     deps = srcs + [os.path.join(HOST, "iamf_host.h"), os.path.join(HOST, "libiamf.map"), os.path.join(ROOT, "include", "IAMF_decoder.h"),
                    os.path.join(ROOT, "include", "iamf_b200.h"), LIB]
@@ -73,6 +74,8 @@ def build_dropin(force=False):
            "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-o", DROPIN] + srcs
     if os.path.exists(REF_OPUS):
         cmd += ["-DIH_HAVE_OPUS", REF_OPUS]
+    if os.path.exists(REF_FLAC):
+        cmd += ["-DIH_HAVE_FLAC", REF_FLAC]
     cmd += ["-L" + PKG, "-l:libiamf_b200.so", "-Wl,-rpath,$ORIGIN", "-Wl,--exclude-libs,ALL",
             "-Wl,--version-script=" + os.path.join(HOST, "libiamf.map"), "-lm"]
     print("[iac_b200.build]", " ".join(cmd), file=sys.stderr)

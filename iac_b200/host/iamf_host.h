@@ -247,6 +247,8 @@ int ih_codec_supported(int codec);
 /* decodes the packets of `n_sub` substreams (the first n_coupled are stereo) into planar float; returns samples */
 int ih_codec_decode(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size,
                     int n_sub, int n_coupled, float *out, int frame_size);
+int ih_flac_rate(const uint8_t *conf, int size);
+int ih_flac_bits(const uint8_t *conf, int size);
 int ih_codec_is_s16(const ih_codec *cc);
 int ih_codec_decode_s16(ih_stream *st, int first_sub, const ih_codec *cc, uint8_t *const *pkt, const uint32_t *pkt_size,
                         int n_sub, int n_coupled, int16_t *out, int frame_size);

@@ -132,6 +132,7 @@ int ih_parse_codec(const ih_obu *o, ih_codec *c) {
   (void)ih_rd_u16(&r); /* roll distance */
   c->conf_size = (int)o->payload_size - (int)ih_rd_tell(&r);
   if (c->conf_size < 0) return IAMF_ERR_INVALID_PACKET;
+  const int full_conf = c->conf_size;
   if (c->conf_size > (int)sizeof(c->conf)) c->conf_size = sizeof(c->conf);
   ih_rd_bytes(&r, c->conf, (uint32_t)c->conf_size);
   switch (fourcc(cc4)) {
@@ -146,6 +147,11 @@ int ih_parse_codec(const ih_obu *o, ih_codec *c) {
   c->rate = -1;
   if (c->codec == IAMF_CODEC_PCM && c->conf_size >= 6) c->rate = rd_be32(c->conf + 2);
   else if (c->codec == IAMF_CODEC_OPUS && c->conf_size >= 8) c->rate = rd_be32(c->conf + 4);
+  else if (c->codec == IAMF_CODEC_FLAC) {
+    /* (a decoder config with more metadata than the 64 bytes kept here is not supported) */
+    if (full_conf > (int)sizeof(c->conf)) return IAMF_ERR_UNIMPLEMENTED;
+    c->rate = ih_flac_rate(c->conf, c->conf_size);
+  }
   return IAMF_OK;
 }
 

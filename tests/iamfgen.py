@@ -144,14 +144,67 @@ class OpusEncoders:
         return buf.raw[:n]
 
 
+class FlacEncoder:
+    """libFLAC stream encoder from oracle/_ref/libFLAC_ref.so (the reference tree's own prebuilt libFLAC): one FLAC frame
+    per call - a fresh encoder per frame, frames are self-contained"""
+    import os as _os
+    SO = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "..", "oracle", "_ref", "libFLAC_ref.so")
+
+    @classmethod
+    def available(cls):
+        import os
+        return os.path.exists(cls.SO)
+
+    def __init__(self, rate, bits=16):
+        import ctypes as C
+        self.C, self.rate, self.bits = C, rate, bits
+        L = C.CDLL(self.SO)
+        L.FLAC__stream_encoder_new.restype = C.c_void_p
+        for f in ("set_channels", "set_bits_per_sample", "set_sample_rate", "set_blocksize", "set_compression_level"):
+            getattr(L, "FLAC__stream_encoder_" + f).argtypes = [C.c_void_p, C.c_uint32]
+        self.WCB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p)
+        L.FLAC__stream_encoder_init_stream.argtypes = [C.c_void_p, self.WCB, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.FLAC__stream_encoder_process_interleaved.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.FLAC__stream_encoder_finish.argtypes = [C.c_void_p]
+        L.FLAC__stream_encoder_delete.argtypes = [C.c_void_p]
+        self.L = L
+
+    def encode(self, key, x):
+        """x: int [channels][n] -> the bytes of ONE FLAC frame"""
+        C, L = self.C, self.L
+        ch, n = x.shape
+        frames = []
+
+        def cb(enc, buf, nbytes, samples, cur, client):
+            if samples:                                   # (samples == 0: stream marker / metadata)
+                frames.append(bytes(bytearray(buf[:nbytes])))
+            return 0
+        wcb = self.WCB(cb)
+        e = L.FLAC__stream_encoder_new()
+        L.FLAC__stream_encoder_set_channels(e, ch)
+        L.FLAC__stream_encoder_set_bits_per_sample(e, self.bits)
+        L.FLAC__stream_encoder_set_sample_rate(e, self.rate)
+        L.FLAC__stream_encoder_set_blocksize(e, n)
+        L.FLAC__stream_encoder_set_compression_level(e, 5)
+        assert L.FLAC__stream_encoder_init_stream(e, wcb, None, None, None, None) == 0
+        inter = np.ascontiguousarray(np.asarray(x, np.int32).T)
+        assert L.FLAC__stream_encoder_process_interleaved(e, inter.ctypes.data, n)
+        L.FLAC__stream_encoder_finish(e)
+        L.FLAC__stream_encoder_delete(e)
+        assert len(frames) == 1, len(frames)
+        return frames[0]
+
+
 @dataclass
 class Stream:
     elements: List[Element]
     frame_size: int = 960
     rate: int = 48000
     profile: int = 1
-    codec: str = "ipcm"            # "ipcm" (16-bit little-endian) | "opus" (needs oracle/_ref/libopus_ref.so)
+    codec: str = "ipcm"            # "ipcm" (16-bit little-endian) | "opus" | "flac" (need oracle/_ref/lib{opus,FLAC}_ref.so)
     _opus: Optional[object] = None
+    _flac: Optional[object] = None
+    flac_bits: int = 16
     out_gain_q78: int = 0
     layouts: List[tuple] = field(default_factory=lambda: [("ss", 0, 0)])  # ("ss", sound_system, loudness_q78) | ("bin", 0, q78)
     OUT_GAIN_PID = 400
@@ -163,6 +216,13 @@ class Stream:
             # OpusHead-like decoder config, big endian (opus/IAMF_opus_decoder.c:56-99): version, channels(2), pre-skip,
             # input rate, output gain, mapping family 0
             cc = leb128(0) + b"Opus" + leb128(self.frame_size) + s16be(-4) + bytes([1, 2]) + struct.pack(">HIhB", 0, self.rate, 0, 0)
+        elif self.codec == "flac":
+            # decoder config = the METADATA_BLOCKs without the "fLaC" marker: one STREAMINFO (last block), stereo - the
+            # decoder patches the channel count for mono sub-streams (flac_multistream_decoder.c:124-150,206-217)
+            si = struct.pack(">HH", self.frame_size, self.frame_size) + b"\0" * 6
+            v = (self.rate << 44) | (1 << 41) | ((self.flac_bits - 1) << 36)
+            si += v.to_bytes(8, "big") + b"\0" * 16
+            cc = leb128(0) + b"fLaC" + leb128(self.frame_size) + s16be(0) + bytes([0x80, 0, 0, 34]) + si
         else:
             # codec config: id 0, ipcm, 16-bit LE
             cc = leb128(0) + b"ipcm" + leb128(self.frame_size) + s16be(0) + bytes([1, 16]) + struct.pack(">I", self.rate)
@@ -244,7 +304,7 @@ class Stream:
                 p += leb128(2) + s16be(g[1]) + s16be(g[2]) + s16be(g[3]) + bytes([g[4]])
             out += obu(OBU_PARAMETER_BLOCK, p)
         for e, x in zip(self.elements, pcm):
-            x = np.asarray(x, np.int16)
+            x = np.asarray(x, np.int32 if (self.codec == "flac" and self.flac_bits > 16) else np.int16)
             ch = 0
             sid = e.substream_base
             groups = [(l.n_substreams, l.n_coupled) for l in e.layers] if e.kind == "channel" else \
@@ -256,6 +316,10 @@ class Stream:
                         if self._opus is None:
                             self._opus = OpusEncoders(self.rate)
                         payload = self._opus.encode(sid, x[ch:ch + nch])
+                    elif self.codec == "flac":
+                        if self._flac is None:
+                            self._flac = FlacEncoder(self.rate, self.flac_bits)
+                        payload = self._flac.encode(sid, x[ch:ch + nch])
                     elif nch == 2:
                         payload = np.ascontiguousarray(x[ch:ch + 2].T).astype("<i2").tobytes()
                     else:

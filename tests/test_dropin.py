@@ -396,3 +396,59 @@ def test_animated_mix_gains_in_a_batch_step():
     for s in range(n):
         assert got[s] == ref[s][0].tobytes(), f"handle {s}"
         L.IAMF_decoder_close(hs[s])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,bits", [("c1", 16), ("c2", 16), ("c4", 16), ("c1", 24)])
+def test_flac_coded_streams_match_reference(cfg, bits):
+    """FLAC core decode (libFLAC through its public API, one stream decoder per sub-stream, the channel count of the
+    config's STREAMINFO patched for mono sub-streams - flac/flac_multistream_decoder.c) in front of the GPU path: FLAC-coded
+    streams against the compiled reference, byte for byte; 16-bit FLAC also through the batch call (int16 hand-over)"""
+    import dataclasses
+    import refbind
+    if not (refbind.have_ref() and G.FlacEncoder.available()):
+        pytest.skip("compiled reference / libFLAC encoder not available")
+    sc, st, api_kw, unit_kw = refstreams.case(cfg)
+    st = dataclasses.replace(st, codec="flac", flac_bits=bits)
+    F, n = 6, 3
+    inputs = S.synth_inputs(sc, n, F, seed=81)
+    P, _, _ = S.synth_params(sc, n, F, seed=82)
+    refstreams.no_param_gaps(sc, P)
+    desc = st.descriptors()
+
+    def units_of(s):
+        out = []
+        for f in range(F):
+            kw = dict(unit_kw(f, P, s) if unit_kw else {})
+            pcm = [refstreams.to_i16(inputs[e][s, f]).astype(np.int32) * (1 << (bits - 16)) + (s if bits > 16 else 0)
+                   for e in range(len(sc.elements))]
+            out.append(st.temporal_unit(pcm, **kw))
+        return out
+    units = [units_of(s) for s in range(n)]
+    ref = [iamfapi.Api(refbind.REF_SO).render(desc, units[s], **api_kw) for s in range(n)]
+    api = iamfapi.Api(LIBIAMF)
+    for s in range(n):
+        pcm, counts = api.render(desc, units[s], **api_kw)
+        assert counts == ref[s][1]
+        assert pcm.tobytes() == ref[s][0].tobytes(), f"stream {s}"
+    # the batch call (16-bit FLAC travels to the device as int16)
+    L = api.L
+    vp = C.c_void_p
+    L.IAMF_decoder_decode_batch_units.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
+                                                  C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+    hs = (vp * n)(*[api.open_configured(desc + units[s][0], **api_kw) for s in range(n)])
+    ch, K = sc.out_channels, 4
+    bufs = [C.create_string_buffer(2 * 6144 * ch * K) for _ in range(n)]
+    pcm = (vp * n)(*[C.cast(b, vp) for b in bufs])
+    got = [b"" for _ in range(n)]
+    for f0 in list(range(0, F, K)) + [None]:
+        piece = [None] * n if f0 is None else [b"".join(units[s][f0:f0 + K]) for s in range(n)]
+        data = (C.c_char_p * n)(*piece)
+        size = (C.c_int32 * n)(*[len(p) if p else 0 for p in piece])
+        ret = (C.c_int * n)()
+        assert L.IAMF_decoder_decode_batch_units(hs, n, data, size, None, pcm, ret, K, None) == 0
+        for s in range(n):
+            got[s] += bufs[s].raw[: ret[s] * ch * 2]
+    for s in range(n):
+        assert got[s] == ref[s][0].tobytes(), f"handle {s} (batch)"
+        L.IAMF_decoder_close(hs[s])
