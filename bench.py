@@ -395,7 +395,7 @@ class DeviceWorkload:
             t = kernels[dom]["ms_per_submit"] / 1e3
             peak_t = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
             return dict(bound="tensor", kernel=dom, achieved=2 * issued / t / 1e12, peak=peak_t, unit="int8 TOP/s", frac=2 * issued / t / 1e12 / peak_t,
-                        traffic=None, peak_source="2 x MEASURED_PEAKS.json bf16_tflops (int8 dense rate)" if "bf16_tflops" in peaks else "2 x 2250 nominal",
+                        traffic=traffic, peak_source="2 x MEASURED_PEAKS.json bf16_tflops (int8 dense rate)" if "bf16_tflops" in peaks else "2 x 2250 nominal",
                         useful_fir_tmacs=useful / t / 1e12, limb_pairs=limb_pairs,
                         pipeline=dict(achieved=pipe, frac=pipe / peak_gbs, note="all kernels of a submit, algorithmic bytes / submit time, vs HBM peak"),
                         kernels=kernels)
