@@ -255,7 +255,9 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
     const int NL = (s16 && he.plain) ? 2 : 3;
     const size_t in_per = (size_t)F * he.n_in * N;
     uint8_t *planes = b->d_planes[e] + (size_t)s_lo * C * NL * 4 * nbp * 16;
-    {
+    // 16-bit PCM that reaches the renderer untouched: the contraction kernel makes its limb rows itself (no prep pass)
+    const bool raw = s16 && he.plain && (N % 8) == 0 && !getenv("IAMFB_HRTF_PREP");
+    if (!raw) {
       HrtfPrepArgs pa;
       memset(&pa, 0, sizeof(pa));
       pa.in = s16 ? (const void *)(reinterpret_cast<const int16_t *>(io->in[e]) + (size_t)s_lo * in_per) : (const void *)(io->in[e] + (size_t)s_lo * in_per);
@@ -288,16 +290,25 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
       ga.frame_of_slot = b->d_fos + (size_t)s_lo * F;
       ga.S = s_cnt; ga.C = C; ga.NL = NL; ga.NB = nb; ga.NT = nt; ga.NBP = nbp; ga.F = F; ga.N = N;
       ga.x_shift = NL == 2 ? 15 : 20;
-      const int smem = kHrStages * hrtf_stage_bytes(nb, NL);
+      ga.raw_in = reinterpret_cast<const int16_t *>(io->in[e]) + (size_t)s_lo * in_per;
+      ga.n_in = he.n_in;
+      for (int m = 0; m < C; ++m) ga.row[m] = he.row[m];
+      ga.hist_in = b->d_hist[e][par ^ 1] + (size_t)s_lo * C * kHrHist;
+      ga.hist_out = b->d_hist[e][par] + (size_t)s_lo * C * kHrHist;
+      const int smem = kHrStages * hrtf_stage_bytes(nb, NL) + (raw ? 2 * hrtf_raw_bytes(nb) : 0);
       const int tiles = s_cnt * nt, grid = tiles < sms ? tiles : sms;
-      if (NL == 2) {
-        CU(cudaFuncSetAttribute(k_hrtf_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      if (raw) {
+        CU(cudaFuncSetAttribute(k_hrtf_gemm<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ScopedKernelTimer tm_(ctx, "k_hrtf_gemm");
-        k_hrtf_gemm<2><<<grid, kHrThreads, smem, st>>>(ga);
+        k_hrtf_gemm<2, true><<<grid, kHrThreads + kHrConvThreads, smem, st>>>(ga);
+      } else if (NL == 2) {
+        CU(cudaFuncSetAttribute(k_hrtf_gemm<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ScopedKernelTimer tm_(ctx, "k_hrtf_gemm");
+        k_hrtf_gemm<2, false><<<grid, kHrThreads, smem, st>>>(ga);
       } else {
-        CU(cudaFuncSetAttribute(k_hrtf_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_hrtf_gemm<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ScopedKernelTimer tm_(ctx, "k_hrtf_gemm");
-        k_hrtf_gemm<3><<<grid, kHrThreads, smem, st>>>(ga);
+        k_hrtf_gemm<3, false><<<grid, kHrThreads, smem, st>>>(ga);
       }
       HR_LAUNCH_CHECK("k_hrtf_gemm");
     }

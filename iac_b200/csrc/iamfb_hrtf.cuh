@@ -67,7 +67,16 @@ struct HrtfGemmArgs {
   int NB, NT, NBP;           // blocks per tile, tiles per stream, blocks per plane row (4 + NT * NB)
   int F, N;                  // frames per submit, frame size
   int x_shift;               // out = sum * 2^-(x_shift + 15)
+  // RAW variant (16-bit PCM that reaches the renderer untouched): the limb rows are made inside the kernel from the decoded
+  // frames themselves - no limb planes, no k_hrtf_prep
+  const int16_t *raw_in;     // [S][F][n_in][N]
+  int n_in;
+  int row[IAMFB_MAX_SCENE_CH];   // decoded row of renderer input c
+  const int *hist_in;        // [S][C][256] Q20: the previous submit's last instants
+  int *hist_out;             // [S][C][256]
 };
+constexpr int kHrConvThreads = 128;          // RAW variant: converter warps (int16 rows -> limb rows in operand order)
+__host__ __device__ constexpr int hrtf_raw_bytes(int nb) { return ((nb + 4) * kHrBlock * 2 + 127) & ~127; }
 
 namespace hr {
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,10 +124,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
 }  // namespace hr
 
 // dynamic shared memory: [stages][table 2 x 12288 | X limbs]; static: barriers + the TMEM base address
-template <int NL>
-static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGemmArgs a) {
+template <int NL, bool RAW>
+static __global__ void __launch_bounds__(kHrThreads + (RAW ? kHrConvThreads : 0), 1) k_hrtf_gemm(const HrtfGemmArgs a) {
   extern __shared__ __align__(128) uint8_t hr_smem[];
   __shared__ __align__(8) uint64_t s_full[kHrStages], s_empty[kHrStages], s_tfull, s_tempty;
+  __shared__ __align__(8) uint64_t s_rfull[2], s_rempty[2];   // RAW: the two raw-row buffers behind the stages
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NB = a.NB, C = a.C;
@@ -127,7 +137,9 @@ static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGe
   const int n_tiles = a.S * a.NT;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kHrStages; ++i) { hr::bar_init(&s_full[i], 1); hr::bar_init(&s_empty[i], 1); }
+    // (RAW: a stage is full when its tables have landed AND the converter warps have written its limb rows)
+    for (int i = 0; i < kHrStages; ++i) { hr::bar_init(&s_full[i], RAW ? 2 : 1); hr::bar_init(&s_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { hr::bar_init(&s_rfull[i], 1); hr::bar_init(&s_rempty[i], 1); }
     hr::bar_init(&s_tfull, 1);
     hr::bar_init(&s_tempty, 4 * kHrEpiGroups);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -152,11 +164,33 @@ static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGe
           const int st = it % kHrStages;
           hr::bar_wait(&s_empty[st], ((it / kHrStages) & 1u) ^ 1u);
           uint8_t *dst = hr_smem + (size_t)st * stage_bytes;
-          hr::bar_expect(&s_full[st], (uint32_t)(kHrHLimbs * kHrTabBytes + NL * 4 * xrow));
-          hr::bulk_load(dst, a.tab + (size_t)c * kHrHLimbs * kHrTabBytes, kHrHLimbs * kHrTabBytes, &s_full[st]);
-          const uint8_t *src = a.planes + ((size_t)(s * C + c) * NL * 4) * a.NBP * 16 + (size_t)b0 * 16;
-          uint8_t *xd = dst + kHrHLimbs * kHrTabBytes;
-          for (int r = 0; r < NL * 4; ++r) hr::bulk_load(xd + r * xrow, src + (size_t)r * a.NBP * 16, (uint32_t)xrow, &s_full[st]);
+          if constexpr (RAW) {
+            hr::bar_expect(&s_full[st], (uint32_t)(kHrHLimbs * kHrTabBytes));
+            hr::bulk_load(dst, a.tab + (size_t)c * kHrHLimbs * kHrTabBytes, kHrHLimbs * kHrTabBytes, &s_full[st]);
+            // the channel's decoded int16 row for the instants [64 b0 - 256, 64 (b0 + NB)) of the stream's time line, frame
+            // piece by frame piece (present frames only; the instants before the submit come from the history)
+            const int rb = it & 1;
+            hr::bar_wait(&s_rempty[rb], ((it >> 1) & 1u) ^ 1u);
+            uint8_t *raw = hr_smem + (size_t)kHrStages * stage_bytes + (size_t)rb * hrtf_raw_bytes(NB);
+            const int len = a.n_present[s] * a.N;
+            const int t0 = b0 * kHrBlock - kHrHist, t1 = min(len, (b0 + NB) * kHrBlock);
+            int t = max(t0, 0);
+            hr::bar_expect(&s_rfull[rb], (uint32_t)(max(t1 - t, 0) * 2));
+            while (t < t1) {
+              const int slot = t / a.N, off = t - slot * a.N;
+              const int cnt = min(a.N - off, t1 - t);
+              const int f = a.frame_of_slot[(size_t)s * a.F + slot];
+              hr::bulk_load(raw + (size_t)(t - t0) * 2, a.raw_in + (((size_t)s * a.F + f) * a.n_in + a.row[c]) * a.N + off, (uint32_t)(cnt * 2),
+                            &s_rfull[rb]);
+              t += cnt;
+            }
+          } else {
+            hr::bar_expect(&s_full[st], (uint32_t)(kHrHLimbs * kHrTabBytes + NL * 4 * xrow));
+            hr::bulk_load(dst, a.tab + (size_t)c * kHrHLimbs * kHrTabBytes, kHrHLimbs * kHrTabBytes, &s_full[st]);
+            const uint8_t *src = a.planes + ((size_t)(s * C + c) * NL * 4) * a.NBP * 16 + (size_t)b0 * 16;
+            uint8_t *xd = dst + kHrHLimbs * kHrTabBytes;
+            for (int r = 0; r < NL * 4; ++r) hr::bulk_load(xd + r * xrow, src + (size_t)r * a.NBP * 16, (uint32_t)xrow, &s_full[st]);
+          }
         }
       }
     }
@@ -191,6 +225,70 @@ static __global__ void __launch_bounds__(kHrThreads, 1) k_hrtf_gemm(const HrtfGe
         }
         hr::mma_commit(&s_tfull);                                  // accumulators complete
         ++tl;
+      }
+    }
+  } else if (RAW && warp >= kHrThreads / 32) {
+    // ===== converters (RAW): the staged int16 row of a channel -> its two byte planes in operand order ([limb][kc][block][16],
+    // instants of a block reversed: byte u of (kc, block) = instant 63 - 16 kc - u), 16 instants per thread and step; they also
+    // carry the filter history: the submit's last 256 instants go out as Q20 for the next submit, the previous submit's come in
+    if constexpr (RAW) {
+      const int ct = threadIdx.x - kHrThreads;
+      // streams without a frame in this submit keep their history
+      for (int s = blockIdx.x; s < a.S; s += gridDim.x)
+        if (a.n_present[s] == 0)
+          for (int i = ct; i < C * kHrHist; i += kHrConvThreads) a.hist_out[(size_t)s * C * kHrHist + i] = a.hist_in[(size_t)s * C * kHrHist + i];
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s = tile / a.NT, b0 = (tile - s * a.NT) * NB;
+        const int len = a.n_present[s] * a.N;
+        if (len <= b0 * kHrBlock) continue;
+        const int t0 = b0 * kHrBlock - kHrHist;
+        for (int c = 0; c < C; ++c, ++it) {
+          const int st = it % kHrStages, rb = it & 1;
+          hr::bar_wait(&s_rfull[rb], (it >> 1) & 1u);
+          const uint8_t *raw = hr_smem + (size_t)kHrStages * stage_bytes + (size_t)rb * hrtf_raw_bytes(NB);
+          uint8_t *xs = hr_smem + (size_t)st * stage_bytes + kHrHLimbs * kHrTabBytes;
+          const size_t hbase = ((size_t)s * C + c) * kHrHist;
+          for (int g = ct; g < (NB + 4) * 4; g += kHrConvThreads) {
+            const int tau = t0 + 16 * g;
+            uint32_t w[8];
+            if (tau < 0) {
+              const int4 *h = reinterpret_cast<const int4 *>(a.hist_in + hbase + kHrHist + tau);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int4 v = h[k];
+                w[2 * k] = ((uint32_t)(v.x >> 5) & 0xffffu) | ((uint32_t)(v.y >> 5) << 16);
+                w[2 * k + 1] = ((uint32_t)(v.z >> 5) & 0xffffu) | ((uint32_t)(v.w >> 5) << 16);
+              }
+            } else {
+              const uint4 v0 = *reinterpret_cast<const uint4 *>(raw + 32 * g), v1 = *reinterpret_cast<const uint4 *>(raw + 32 * g + 16);
+              w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+            }
+            const int p0 = tau + kHrHist - len;            // index on the next history of this group's first instant
+            if (p0 >= 0 && p0 < kHrHist && tau < len) {
+              int4 *h = reinterpret_cast<int4 *>(a.hist_out + hbase + p0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                h[k] = make_int4((int)(short)(w[2 * k] & 0xffffu) << 5, (int)(short)(w[2 * k] >> 16) << 5, (int)(short)(w[2 * k + 1] & 0xffffu) << 5,
+                                 (int)(short)(w[2 * k + 1] >> 16) << 5);
+            }
+            const int bp = g >> 2, kc = 3 - (g & 3);
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              lo[q] = __byte_perm(w[7 - 2 * q], w[6 - 2 * q], 0x4602);
+              hi[q] = __byte_perm(w[7 - 2 * q], w[6 - 2 * q], 0x5713);
+            }
+            *reinterpret_cast<uint4 *>(xs + (size_t)((0 * 4 + kc) * (NB + 4) + bp) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4 *>(xs + (size_t)((1 * 4 + kc) * (NB + 4) + bp) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the tensor core reads the rows through the async proxy
+          asm volatile("bar.sync 3, %0;" ::"n"(kHrConvThreads) : "memory");
+          if (ct == 0) {
+            hr::bar_arrive(&s_full[st]);
+            hr::bar_arrive(&s_rempty[rb]);
+          }
+        }
       }
     }
   } else {

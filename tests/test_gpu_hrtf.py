@@ -26,13 +26,23 @@ def test_hrtf_ragged_submits(sc):
     compare(sc, 21, 12, [1, 4, 2, 5], seed=32)
 
 
+@pytest.mark.parametrize("sc", [c for c in CASES if all(e.hrtf for e in c.elements)], ids=[c.name for c in CASES if all(e.hrtf for e in c.elements)])
+def test_hrtf_ragged_submits_int16(sc):
+    # the same with int16 hand-over: elements whose PCM reaches the renderer untouched take the contraction kernel's RAW
+    # variant (limb rows made in the kernel, history in / out by its converter warps), the others the two-limb prep pass;
+    # 14 frames in one submit = two tiles per stream
+    compare(sc, 21, 12, [1, 4, 2, 5], seed=37, s16=True)
+    compare(sc, 5, 14, [14], seed=38, s16=True)
+
+
 def test_hrtf_int16_upload_two_limbs():
     # 16-bit decoded PCM travels as two limbs (Q15) instead of three (Q20): same bits out
     compare(S.c4_hrtf(), 70, 5, [2, 3], seed=33, s16=True)
     compare(S.hrtf_cases()[2], 9, 4, [4], seed=34, s16=True)
 
 
-def test_hrtf_missing_frames_keep_the_filter_state():
+@pytest.mark.parametrize("s16", [False, True], ids=["f32", "s16"])
+def test_hrtf_missing_frames_keep_the_filter_state(s16):
     # streams that have no frame in some steps (trim_start 0xFFFF): the renderer sees their present frames as one signal
     sc = S.c4_hrtf()
 
@@ -44,7 +54,8 @@ def test_hrtf_missing_frames_keep_the_filter_state():
     inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 35)
     P, ramps, oramp = S.synth_params(sc, n, F, seed=0x77 + 35)
     edit(P)
-    got, _ = run_product(sc, inputs, P, ramps, oramp, splits=[3, 5])
+    P["trim_start"][4::5, 3:] = 0xFFFF           # nothing at all in the second submit
+    got, _ = run_product(sc, inputs, P, ramps, oramp, splits=[3, 5], s16=s16)
     # the oracle is fed the present frames only (a stream without a frame in a step is simply not called)
     for s in range(n):
         keep = [f for f in range(F) if P["trim_start"][s, f] != 0xFFFF]
@@ -63,7 +74,7 @@ def test_hrtf_full_size_config4():
     inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 36)
     P, _, _ = S.synth_params(sc, n, F, seed=0x77 + 36)
     big = [np.tile(x, (reps, 1, 1, 1)) for x in inputs]
-    got, _ = run_product(sc, big, np.tile(P, (reps, 1)), splits=[F])
+    got, _ = run_product(sc, big, np.tile(P, (reps, 1)), splits=[F], s16=True)
     ref = S.run_oracle(sc, inputs, P)
     for s in range(n * reps):
         assert got[s][0] == ref[s % n][0]

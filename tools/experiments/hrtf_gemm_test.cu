@@ -63,9 +63,11 @@ int main(int argc, char **argv) {
   CK(cudaMemset(d_out, 0xff, sizeof(float) * S * F * 2 * N));
   HrtfGemmArgs a;
   a.tab = d_tab; a.planes = d_planes; a.out = d_out; a.n_present = d_np; a.frame_of_slot = d_fos;
+  memset(&a, 0, sizeof(a));
+  a.tab = d_tab; a.planes = d_planes; a.out = d_out; a.n_present = d_np; a.frame_of_slot = d_fos;
   a.S = S; a.C = C; a.NL = NL; a.NB = NB; a.NT = NT; a.NBP = NBP; a.F = F; a.N = N; a.x_shift = x_shift;
   const int smem = kHrStages * hrtf_stage_bytes(NB, NL);
-  auto kern = NL == 2 ? k_hrtf_gemm<2> : k_hrtf_gemm<3>;
+  auto kern = NL == 2 ? k_hrtf_gemm<2, false> : k_hrtf_gemm<3, false>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
