@@ -360,8 +360,15 @@ class DeviceWorkload:
         torch.cuda.synchronize()
         timing = self.eng.get_timing()
         self.eng.set_timing(False)
-        return {k: dict(ms_per_launch=v[0] / max(v[1], 1), launches_per_submit=v[1] / submits, ms_per_submit=v[0] / submits)
-                for k, v in timing.items()}
+        # per launch: the MEDIAN of the launches for a kernel launched once per submit (a launch that was pre-empted or met a
+        # clock dip does not move it); the mean for kernels with several, differently sized launches per submit
+        out = {}
+        for k, v in timing.items():
+            once = v[1] <= submits
+            per = v[2] if once else v[0] / max(v[1], 1)
+            out[k] = dict(ms_per_launch=per, launches_per_submit=v[1] / submits, ms_per_submit=per * v[1] / submits,
+                          mean_ms_per_launch=v[0] / max(v[1], 1), statistic="median" if once else "mean")
+        return out
 
     def roofline(self, kernels, ms_per_submit, out_per_submit):
         peaks = {}
@@ -567,7 +574,7 @@ def run_gpu(args):
         w.close()
         return
 
-    kernels = w.kernel_timing(min(args.steps * R, 40))
+    kernels = w.kernel_timing(min(args.steps * R, 120))
     roofline = w.roofline(kernels, ms_per_submit, out_per_submit)
 
     # ---- end to end through the host-buffer entry point of the C ABI: pinned host memory -> H2D -> kernels -> D2H every

@@ -121,6 +121,7 @@ def lib():
                                        C.POINTER(C.c_uint64)]
     L.iamfb_get_hrir.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int16)]
     L.iamfb_hrir_taps.restype = C.c_int
+    L.iamfb_ctx_get_timing_median.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.iamfb_target_channels.argtypes = [C.c_int]
     L.iamfb_layout_channels.argtypes = [C.c_int, C.POINTER(C.c_int32)]
     L.iamfb_get_m2m_matrix.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -259,13 +260,14 @@ class Engine:
         _check(self.L.iamfb_ctx_set_timing(self.ctx, 1 if enable else 0), "iamfb_ctx_set_timing")
 
     def get_timing(self):
-        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream"""
+        """{kernel name: (total ms, launches, median ms per launch)} measured with CUDA events on the launching stream"""
         out, i = {}, 0
         while True:
-            name, ms, n = C.c_char_p(), C.c_double(), C.c_uint64()
+            name, ms, n, med = C.c_char_p(), C.c_double(), C.c_uint64(), C.c_double()
             if self.L.iamfb_ctx_get_timing(self.ctx, i, C.byref(name), C.byref(ms), C.byref(n)) != 0:
                 return out
-            out[name.value.decode()] = (ms.value, n.value)
+            self.L.iamfb_ctx_get_timing_median(self.ctx, i, C.byref(med))
+            out[name.value.decode()] = (ms.value, n.value, med.value)
             i += 1
 
     def synchronize(self):

@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -249,6 +251,7 @@ extern "C" int iamfb_ctx_get_timing(iamfb_ctx *c, int index, const char **name, 
       float ms = 0.f;
       cudaEventElapsedTime(&ms, p.first, p.second);
       k.total_ms += ms;
+      k.samples.push_back(ms);
       c->event_pool.push_back(p.first);
       c->event_pool.push_back(p.second);
     }
@@ -257,6 +260,19 @@ extern "C" int iamfb_ctx_get_timing(iamfb_ctx *c, int index, const char **name, 
   if (name) *name = k.name;
   if (total_ms) *total_ms = k.total_ms;
   if (launches) *launches = k.launches;
+  return IAMFB_OK;
+}
+
+extern "C" int iamfb_ctx_get_timing_median(iamfb_ctx *c, int index, double *median_ms) {
+  double total = 0;
+  uint64_t n = 0;
+  const char *name = nullptr;
+  int r = iamfb_ctx_get_timing(c, index, &name, &total, &n);   // (drains the pending events)
+  if (r) return r;
+  std::vector<float> v = c->timers[index].samples;
+  if (v.empty()) { if (median_ms) *median_ms = 0; return IAMFB_OK; }
+  std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
+  if (median_ms) *median_ms = v[v.size() / 2];
   return IAMFB_OK;
 }
 

@@ -1,5 +1,7 @@
 // iamfb_hrtf.cu - host side of the binaural (HRTF) front end: which elements take it, their Toeplitz tables, the
-// per-batch buffers, and the three launches per element and submit (k_hrtf_index once, k_hrtf_prep, k_hrtf_gemm).
+// per-batch buffers, and the launches per submit: k_hrtf_index once, then per element k_hrtf_gemm - its RAW variant straight
+// from the decoded int16 frames when they reach the renderer untouched, else k_hrtf_prep (gains, projection, float32
+// input -> Q20 limb planes) in front of it.
 //
 // A plan with HRTF elements is the front end below followed by an ordinary plan in which every such element has become a
 // 2-channel pass-through element (the rendered [2][N] frame takes the place of the decoded frame, exactly where the
@@ -190,7 +192,6 @@ int iamfb_hrtf_batch_create(const iamfb_hrtf_front *h, int S, int Fmax, iamfb_hr
   for (int e = 0; e < h->n_elements; ++e) {
     if (!h->el[e].on) continue;
     const size_t C = h->el[e].C;
-    alloc((void **)&b->d_planes[e], (size_t)S * C * kHrMaxXLimbs * 4 * b->NBP * 16);
     alloc((void **)&b->d_hist[e][0], sizeof(int) * (size_t)S * C * kHrHist);
     alloc((void **)&b->d_hist[e][1], sizeof(int) * (size_t)S * C * kHrHist);
     alloc((void **)&b->d_bin[e], sizeof(float) * (size_t)S * Fmax * 2 * h->N);
@@ -254,9 +255,13 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
     const int C = he.C;
     const int NL = (s16 && he.plain) ? 2 : 3;
     const size_t in_per = (size_t)F * he.n_in * N;
-    uint8_t *planes = b->d_planes[e] + (size_t)s_lo * C * NL * 4 * nbp * 16;
     // 16-bit PCM that reaches the renderer untouched: the contraction kernel makes its limb rows itself (no prep pass)
-    const bool raw = s16 && he.plain && (N % 8) == 0 && !getenv("IAMFB_HRTF_PREP");
+    const bool raw = s16 && he.plain;
+    if (!raw && !b->d_planes[e]) {   // limb planes: only submits that need the prep pass pay for them
+      if (cudaMalloc((void **)&b->d_planes[e], (size_t)b->S * C * kHrMaxXLimbs * 4 * nbp * 16) != cudaSuccess)
+        return fail(IAMFB_ERR_ALLOC_FAIL, "binaural HRTF rendering: limb planes");
+    }
+    uint8_t *planes = raw ? nullptr : b->d_planes[e] + (size_t)s_lo * C * NL * 4 * nbp * 16;
     if (!raw) {
       HrtfPrepArgs pa;
       memset(&pa, 0, sizeof(pa));
@@ -275,8 +280,7 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
       dim3 grid((groups + 255) / 256, s_cnt * C);
       {
         ScopedKernelTimer tm_(ctx, "k_hrtf_prep");
-        if (s16 && he.plain) k_hrtf_prep_s16<<<grid, 256, 0, st>>>(pa);
-        else if (s16) k_hrtf_prep<true><<<grid, 256, 0, st>>>(pa);
+        if (s16) k_hrtf_prep<true><<<grid, 256, 0, st>>>(pa);
         else k_hrtf_prep<false><<<grid, 256, 0, st>>>(pa);
       }
       HR_LAUNCH_CHECK("k_hrtf_prep");

@@ -501,53 +501,6 @@ static __global__ void __launch_bounds__(256) k_hrtf_prep(const HrtfPrepArgs a) 
   }
 }
 
-// ---- the same for 16-bit decoded PCM that reaches the renderer untouched (no output gain, no projection: what Opus / AAC /
-// 16-bit ipcm elements are): the two limbs of a sample ARE the two bytes of the int16 - the pass is a byte de-interleave
-// with the block reversal, 2 x 16-byte loads, 8 byte permutes and 2 x 16-byte stores per 16 instants (the float32 detour
-// of k_hrtf_prep - x / 32768 -> Q20 -> >> 5 - gives the same bytes)
-static __global__ void __launch_bounds__(256) k_hrtf_prep_s16(const HrtfPrepArgs a) {
-  const int sc = blockIdx.y, s = sc / a.C, c = sc - s * a.C;
-  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-  const int len = a.n_present[s] * a.N;
-  if (gi >= (kHrHist + len) / 16) return;
-  uint32_t w[8];                                   // 16 instants as int16 pairs (Q15)
-  if (gi < kHrHist / 16) {
-    const int4 *h = reinterpret_cast<const int4 *>(a.hist_in + (size_t)sc * kHrHist + 16 * gi);   // Q20
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int4 v = h[k];
-      w[2 * k] = ((uint32_t)(v.x >> 5) & 0xffffu) | ((uint32_t)(v.y >> 5) << 16);
-      w[2 * k + 1] = ((uint32_t)(v.z >> 5) & 0xffffu) | ((uint32_t)(v.w >> 5) << 16);
-    }
-  } else {
-    const int tau = 16 * gi - kHrHist, slot = tau / a.N, i = tau - slot * a.N;
-    const int f = a.frame_of_slot[(size_t)s * a.F + slot];
-    const int4 *p = reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(a.in) + (((size_t)s * a.F + f) * a.n_in + a.row[c]) * a.N + i);
-    const int4 v0 = p[0], v1 = p[1];
-    w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
-  }
-  {
-    const int p0 = 16 * gi - len;                 // index on the next history of this group's first instant
-    if (p0 >= 0) {
-      int4 *h = reinterpret_cast<int4 *>(a.hist_out + (size_t)sc * kHrHist + p0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        h[k] = make_int4((int)(short)(w[2 * k] & 0xffffu) << 5, (int)(short)(w[2 * k] >> 16) << 5, (int)(short)(w[2 * k + 1] & 0xffffu) << 5,
-                         (int)(short)(w[2 * k + 1] >> 16) << 5);
-    }
-  }
-  // byte u of (kc, block) = instant 15 - u of the group: word q of a limb = instants 15-4q, 14-4q, 13-4q, 12-4q
-  const int bp = gi >> 2, kc = 3 - (gi & 3);
-  uint32_t lo[4], hi[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    lo[q] = __byte_perm(w[7 - 2 * q], w[6 - 2 * q], 0x4602);
-    hi[q] = __byte_perm(w[7 - 2 * q], w[6 - 2 * q], 0x5713);
-  }
-  *reinterpret_cast<uint4 *>(a.planes + ((((size_t)sc * 2 + 0) * 4 + kc) * a.NBP + bp) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  *reinterpret_cast<uint4 *>(a.planes + ((((size_t)sc * 2 + 1) * 4 + kc) * a.NBP + bp) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-}
-
 // ---- host: Toeplitz core tables of one channel.  taps = [2 ears][256] Q15; dst = [2 limbs][96 cores][8 rows][16 bytes]
 inline void hrtf_build_table(const int16_t *taps, uint8_t *dst) {
   for (int hl = 0; hl < kHrHLimbs; ++hl)

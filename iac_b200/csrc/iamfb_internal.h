@@ -25,6 +25,7 @@ struct KernelTimer {
   double total_ms;
   uint64_t launches;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<float> samples;   // per-launch durations (the median is robust against a launch that was pre-empted)
 };
 
 constexpr int kMaxChunks = 32;
@@ -63,7 +64,7 @@ struct ScopedKernelTimer {
   ScopedKernelTimer(iamfb_ctx *c, const char *name, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
     if (!c->timing) return;
     for (auto &k : c->timers) if (!strcmp(k.name, name)) t = &k;
-    if (!t) { c->timers.push_back(KernelTimer{name, 0.0, 0, {}}); t = &c->timers.back(); }
+    if (!t) { c->timers.push_back(KernelTimer{name, 0.0, 0, {}, {}}); t = &c->timers.back(); }
     a = get(c); b = get(c);
     cudaEventRecord(a, st);
   }

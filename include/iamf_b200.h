@@ -262,6 +262,7 @@ uint64_t iamfb_ctx_launch_count(const iamfb_ctx *ctx);
  * figure; off by default).  iamfb_ctx_get_timing iterates index = 0,1,... until it returns non-zero. */
 int iamfb_ctx_set_timing(iamfb_ctx *ctx, int enable);
 int iamfb_ctx_get_timing(iamfb_ctx *ctx, int index, const char **name, double *total_ms, uint64_t *launches);
+int iamfb_ctx_get_timing_median(iamfb_ctx *ctx, int index, double *median_ms);   /* median duration of one launch */
 
 /* self-test (used by tests/): compares the branch-free division of k_stream's limiter scan with the IEEE division
  * `thr / w` for EVERY float w of the range the kernel uses it in (2^-60 .. 2^60); *mismatches receives the count of
