@@ -137,6 +137,12 @@ struct iamfb_plan {
   // pipeline BEHIND it (those elements as 2-channel pass-through elements fed with float32 binaural frames)
   iamfb_hrtf_front *hrtf;
   int in_rows[kMaxEl];     // rows per frame of the CALLER's input of every element
+  // HRTF elements whose layout channels the de-mixer derives (scalable layers, recon gain): de-mixed in front of the renderer
+  // from their OWN plan / per-stream state (kp and the batch's state describe the pipeline behind the front end)
+  KernelPlan *kp_front;
+  bool front_demix[kMaxEl];
+  int front_tmpl[kMaxEl];
+  StreamState init_state_front;
 };
 
 struct iamfb_batch {
@@ -163,6 +169,10 @@ struct iamfb_batch {
   int32_t *d_counts;
   size_t stage_frames;     // frames the staging buffers are sized for (0 = not allocated)
   iamfb_hrtf_batch *hrtf;  // per-stream buffers of the binaural HRTF front end
+  StreamState *d_state_f;   // HRTF front de-mixing: its own state / resolved frames / submit records, the de-mixed channels
+  FrameRec *d_frames_f;
+  SubmitRec *d_submit_f;
+  float *d_demixed[kMaxEl];
   float *d_seg_ramp[kMaxEl], *d_seg_oramp;   // per-sample gains expanded from gain segments (k_gain_expand)
   iamfb_gain_ramp *d_segs[kMaxEl + 1];       // host-resident submits: the uploaded segment records
 };
@@ -851,6 +861,26 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
   p->desc = *d;
   p->hrtf = hf;
   for (int e = 0; e < d->n_elements; ++e) p->in_rows[e] = orig->el[e].n_in;
+  if (hf) {
+    bool any = false;
+    for (int e = 0; e < d->n_elements; ++e) any |= iamfb_hrtf_needs_demix(hf, e);
+    if (any) {
+      p->kp_front = new KernelPlan();
+      memset(p->kp_front, 0, sizeof(KernelPlan));
+      p->kp_front->frame_size = orig->frame_size;
+      p->kp_front->n_elements = orig->n_elements;
+      p->kp_front->out_channels = k_target_channels[orig->target];
+      p->kp_front->overlap = (orig->frame_size / 8) / 2;
+      memset(&p->init_state_front, 0, sizeof(p->init_state_front));
+      p->init_state_front.lim_j = -1;
+      p->init_state_front.lim_start = p->init_state_front.lim_end = -1.f;
+      for (int e = 0; e < d->n_elements; ++e) {   // (every element: k_resolve walks them all)
+        int r = build_element(*orig, e, *p->kp_front, p->front_tmpl[e], p->init_state_front);
+        if (r != IAMFB_OK) { iamfb_plan_destroy(p); return r; }
+        p->front_demix[e] = iamfb_hrtf_needs_demix(hf, e);
+      }
+    }
+  }
   KernelPlan &kp = p->kp;
   kp.frame_size = d->frame_size;
   kp.n_elements = d->n_elements;
@@ -1274,6 +1304,7 @@ extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
   if (!p) return;
   cudaFree(p->d_start_win); cudaFree(p->d_stop_win); cudaFree(p->d_qf); cudaFree(p->d_sinc); cudaFree(p->d_acc); cudaFree(p->d_tab4); cudaFree(p->d_tab4p); cudaFree(p->d_interp4);
   iamfb_hrtf_front_destroy(p->hrtf);
+  delete p->kp_front;
   delete p;
 }
 
@@ -1364,6 +1395,11 @@ extern "C" int iamfb_batch_reset(iamfb_batch *b) {
     int r = iamfb_hrtf_batch_reset(p->hrtf, b->hrtf, p->ctx->stream);
     if (r) return r;
   }
+  std::vector<StreamState> init_f;
+  if (b->d_state_f) {
+    init_f.assign(b->S, p->init_state_front);
+    CU(cudaMemcpyAsync(b->d_state_f, init_f.data(), sizeof(StreamState) * b->S, cudaMemcpyHostToDevice, p->ctx->stream));
+  }
   CU(cudaStreamSynchronize(p->ctx->stream));
   return IAMFB_OK;
 }
@@ -1411,6 +1447,19 @@ extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, 
     int r = iamfb_hrtf_batch_create(p->hrtf, n_streams, max_frames, &b->hrtf);
     if (r) { iamfb_batch_destroy(b); return r; }
   }
+  if (p->kp_front) {
+    alloc((void **)&b->d_state_f, sizeof(StreamState) * n_streams);
+    alloc((void **)&b->d_frames_f, sizeof(FrameRec) * (size_t)n_streams * max_frames);
+    alloc((void **)&b->d_submit_f, sizeof(SubmitRec) * n_streams);
+    for (int el = 0; el < kp.n_elements; ++el)
+      if (p->front_demix[el])
+        alloc((void **)&b->d_demixed[el], sizeof(float) * (size_t)n_streams * max_frames * p->kp_front->el[el].n_rec * kp.frame_size);
+    if (e != cudaSuccess) {
+      int r = fail(IAMFB_ERR_ALLOC_FAIL, "device allocation failed: %s", cudaGetErrorString(e));
+      iamfb_batch_destroy(b);
+      return r;
+    }
+  }
   int r = iamfb_batch_reset(b);
   if (r) { iamfb_batch_destroy(b); return r; }
   *out = b;
@@ -1435,6 +1484,8 @@ extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
   cudaFree(b->d_hist_y); cudaFree(b->d_hist_pk);
   for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_wide[e]);
   iamfb_hrtf_batch_destroy(b->hrtf);
+  cudaFree(b->d_state_f); cudaFree(b->d_frames_f); cudaFree(b->d_submit_f);
+  for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_demixed[e]);
   for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_seg_ramp[e]);
   cudaFree(b->d_seg_oramp);
   for (int e = 0; e <= kMaxEl; ++e) cudaFree(b->d_segs[e]);
@@ -1521,7 +1572,7 @@ static int ensure_wide(iamfb_batch *b) {
   const KernelPlan &kp = b->plan->kp;
   for (int e = 0; e < kp.n_elements; ++e)
     if (!b->d_wide[e]) {
-      cudaError_t er = cudaMalloc((void **)&b->d_wide[e], sizeof(float) * (size_t)b->S * b->Fmax * kp.el[e].n_in * kp.frame_size);
+      cudaError_t er = cudaMalloc((void **)&b->d_wide[e], sizeof(float) * (size_t)b->S * b->Fmax * b->plan->in_rows[e] * kp.frame_size);
       if (er != cudaSuccess) return fail(IAMFB_ERR_ALLOC_FAIL, "float32 staging of an int16 submit: %s", cudaGetErrorString(er));
     }
   return IAMFB_OK;
@@ -1534,7 +1585,7 @@ static int widen_streams(iamfb_batch *b, const iamfb_io *io, int F, int s_lo, in
   *wio = *io;
   wio->in_format = IAMFB_IN_F32;
   for (int e = 0; e < kp.n_elements; ++e) {
-    const size_t per = (size_t)F * kp.el[e].n_in * kp.frame_size, n = (size_t)s_cnt * per, n8 = n / 8, off = (size_t)s_lo * per;
+    const size_t per = (size_t)F * b->plan->in_rows[e] * kp.frame_size, n = (size_t)s_cnt * per, n8 = n / 8, off = (size_t)s_lo * per;
     const int16_t *src = reinterpret_cast<const int16_t *>(io->in[e]) + off;
     float *dst = b->d_wide[e] + off;
     {
@@ -1593,6 +1644,48 @@ static __global__ void __launch_bounds__(256) k_gain_expand(const iamfb_gain_ram
   }
 }
 
+// ---- k_hrtf_demix: the channels that enter the binaural renderer for a scalable element - the de-mixer's derivation chain,
+// output gains and recon-gain cross-fade (demixer_demixing, demixer.c:636-664; exactly the first half of k_render's thread),
+// written as float32 [S][F][n_rec][N] in layout order.  Trims do not apply here: the renderer sees the untrimmed frame.
+struct DemixArgs {
+  const float *in;            // [S][F][n_in][N]
+  const iamfb_frame_params *params;
+  const FrameRec *frames;     // resolved with the FRONT plan
+  const float *start_win, *stop_win;
+  float *out;                 // [S][F][NREC][N]
+  int e;
+};
+template <int LAYOUT, int NREC>
+static __global__ void __launch_bounds__(128) k_hrtf_demix(const __grid_constant__ KernelPlan plan, DemixArgs a) {
+  const int N = plan.frame_size;
+  const size_t sf = blockIdx.y;
+  const int i0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (i0 >= N || a.params[sf].trim_start == 0xFFFF) return;
+  const ElPlan &ep = plan.el[a.e];
+  const ElFrame &ef = a.frames[sf].el[a.e];
+  Vec<4> v[kChCount];
+  reconstruct_channels<4, false>(ep, ef, a.in + sf * ep.n_in * N + i0, N, true, 4, v);
+  constexpr unsigned char kOrder[9][12] = {
+      {13}, {14, 15}, {1, 2, 3, 4, 20, 21}, {1, 2, 3, 4, 20, 21, 22, 23}, {1, 2, 3, 4, 20, 21, 9, 10, 11, 12},
+      {1, 2, 3, 4, 5, 6, 7, 8}, {1, 2, 3, 4, 5, 6, 7, 8, 22, 23}, {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12},
+      {18, 19, 3, 4, 16, 17}};
+#pragma unroll
+  for (int m = 0; m < NREC; ++m) {
+    Vec<4> x = v[kOrder[LAYOUT][m]];
+    if ((ef.rmask >> m) & 1u) {   // dmx_rms cross-fade, demixer.c:461-468
+      const float last = ef.rlast[m], cur = ef.rcur[m];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        float st = 0.f, sw = 1.f;
+        if (i < plan.overlap) { st = a.stop_win[i]; sw = a.start_win[i]; }
+        x.v[k] *= last * st + cur * sw;
+      }
+    }
+    *reinterpret_cast<float4 *>(a.out + (sf * NREC + m) * N + i0) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  }
+}
+
 // per-batch float ramp buffers for device-resident submits with gain segments (host-resident submits use the staging ones)
 static int ensure_ramps(iamfb_batch *b) {
   const KernelPlan &kp = b->plan->kp;
@@ -1638,8 +1731,61 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     io = &gio;
   }
   if (p->hrtf && !flush) {
+    const float *demixed[kMaxEl] = {nullptr, nullptr};
+    iamfb_io fio;
+    if (p->kp_front) {
+      // scalable elements in front of the renderer: their frames resolved with the front plan (own de-mixer state), their
+      // layout channels de-mixed into float32
+      if (io->in_format == IAMFB_IN_S16) {
+        int r = widen_streams(b, io, F, s_lo, s_cnt, &fio);
+        if (r) return r;
+        io = &fio;
+      }
+      const KernelPlan &kf = *p->kp_front;
+      ResolveArgs a;
+      memset(&a, 0, sizeof(a));
+      a.params = io->params + (size_t)s_lo * F;
+      a.state = b->d_state_f + s_lo;
+      a.frames = b->d_frames_f + (size_t)s_lo * F;
+      a.submit = b->d_submit_f + s_lo;
+      a.qf_table = p->d_qf;
+      a.n_streams = s_cnt;
+      a.n_frames = F;
+      a.n_sub = 1;
+      a.sub_frame[0] = 0;
+      for (int c = 1; c <= kMaxSub; ++c) a.sub_frame[c] = F;
+      {
+        const int per_block = kResolveThreads / 32;
+        ScopedKernelTimer tm_(ctx, "k_resolve");
+        k_resolve<<<(s_cnt + per_block - 1) / per_block, kResolveThreads, 0, st>>>(kf, a);
+      }
+      { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_resolve (front) failed: %s", cudaGetErrorString(e_)); ++ctx->launches; }
+      for (int e = 0; e < kf.n_elements; ++e) {
+        if (!p->front_demix[e]) continue;
+        DemixArgs da;
+        da.in = io->in[e] + (size_t)s_lo * F * kf.el[e].n_in * kf.frame_size;
+        da.params = io->params + (size_t)s_lo * F;
+        da.frames = b->d_frames_f + (size_t)s_lo * F;
+        da.start_win = p->d_start_win;
+        da.stop_win = p->d_stop_win;
+        da.out = b->d_demixed[e] + (size_t)s_lo * F * kf.el[e].n_rec * kf.frame_size;
+        da.e = e;
+        dim3 grid((kf.frame_size / 4 + 127) / 128, (unsigned)((size_t)s_cnt * F));
+        {
+          ScopedKernelTimer tm_(ctx, "k_hrtf_demix");
+#define DCASE(ID, LAYOUT, NREC) case ID: k_hrtf_demix<LAYOUT, NREC><<<grid, 128, 0, st>>>(kf, da); break;
+          switch (p->front_tmpl[e]) {
+            DCASE(0, 0, 1) DCASE(1, 1, 2) DCASE(2, 2, 6) DCASE(3, 3, 8) DCASE(4, 4, 10) DCASE(5, 5, 8) DCASE(6, 6, 10) DCASE(7, 7, 12) DCASE(8, 8, 6)
+            default: return fail(IAMFB_ERR_INTERNAL, "no de-mixing kernel variant %d", p->front_tmpl[e]);
+          }
+#undef DCASE
+        }
+        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_hrtf_demix failed: %s", cudaGetErrorString(e_)); ++ctx->launches; }
+        demixed[e] = b->d_demixed[e];
+      }
+    }
     // binaural HRTF front end: the elements it renders reach the kernels below as float32 [2][N] frames
-    int r = iamfb_hrtf_run(ctx, p->hrtf, b->hrtf, io, F, s_lo, s_cnt, &hio);
+    int r = iamfb_hrtf_run(ctx, p->hrtf, b->hrtf, io, F, s_lo, s_cnt, &hio, demixed);
     if (r) return r;
     io = &hio;
   }

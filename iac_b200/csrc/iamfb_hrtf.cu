@@ -35,6 +35,8 @@ struct HrtfEl {
   int row[IAMFB_MAX_SCENE_CH];
   float gain[IAMFB_MAX_SCENE_CH];
   bool plain;               // rows pass through untouched: 16-bit submits travel as two limbs
+  bool demix;               // the layout's channels are de-mixed first (scalable layers / recon gain): the renderer reads them
+                            // from a float32 buffer the caller of iamfb_hrtf_run provides
   float proj[IAMFB_MAX_SCENE_CH * IAMFB_MAX_SCENE_CH];
   uint8_t *d_tab;
 };
@@ -94,15 +96,16 @@ int iamfb_hrtf_front_create(const iamfb_plan_desc *d, iamfb_plan_desc *back, iam
         for (int r = 0; r < de.n_in; ++r)
           if (de.chs_in[r] == chs[m]) row = r;
         // a channel the layers do not carry is derived by the de-mixer (demixer.c:127-378) from per-frame parameters
-        if (row < 0 || de.recon_present) {
-          iamfb_hrtf_front_destroy(h);
-          return fail(IAMFB_ERR_UNIMPLEMENTED, "binaural HRTF rendering of a scalable element that needs de-mixing (element %d)", e);
-        }
+        if (row < 0 || de.recon_present) he.demix = true;
         he.row[m] = row;
         he.gain[m] = 1.0f;
         for (int g = 0; g < de.n_out_gain && g < IAMFB_MAX_LAYOUT_CH; ++g)
           if (de.out_gain_ch[g] == chs[m]) { he.gain[m] = de.out_gain[g]; he.plain = false; }
         iamfb_get_hrir(IAMFB_EL_CHANNEL, chs[m], &taps[(size_t)m * 2 * k_hrir_taps]);
+      }
+      if (he.demix) {   // rows = the layout's channels in order, gains already applied by the de-mixer
+        for (int m = 0; m < n; ++m) { he.row[m] = m; he.gain[m] = 1.0f; }
+        he.plain = false;
       }
     } else {
       const int n = de.ambi_channels;
@@ -156,7 +159,7 @@ int iamfb_hrtf_front_create(const iamfb_plan_desc *d, iamfb_plan_desc *back, iam
   return IAMFB_OK;
 }
 
-int iamfb_hrtf_in_rows(const iamfb_hrtf_front *h, int e) { return (h && h->el[e].on) ? h->el[e].n_in : -1; }
+bool iamfb_hrtf_needs_demix(const iamfb_hrtf_front *h, int e) { return h && h->el[e].on && h->el[e].demix; }
 
 void iamfb_hrtf_batch_destroy(iamfb_hrtf_batch *b) {
   if (!b) return;
@@ -217,14 +220,14 @@ int iamfb_hrtf_batch_create(const iamfb_hrtf_front *h, int S, int Fmax, iamfb_hr
 // Renders the HRTF elements of the streams [s_lo, s_lo + s_cnt) for a submit of F frames.  io holds DEVICE pointers with the
 // caller's shapes; out_io receives what the rest of the pipeline takes (the binaural frames in place of those elements).
 int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *b, const iamfb_io *io, int F, int s_lo, int s_cnt,
-                   iamfb_io *out_io) {
+                   iamfb_io *out_io, const float *const *demixed) {
   cudaStream_t st = ctx->stream;
   const int N = h->N;
-  const bool s16 = io->in_format == IAMFB_IN_S16;
+  const bool s16_io = io->in_format == IAMFB_IN_S16;
   *out_io = *io;
   out_io->in_format = IAMFB_IN_F32;
   for (int e = 0; e < h->n_elements; ++e)
-    if (!h->el[e].on && s16)
+    if (!h->el[e].on && s16_io)
       return fail(IAMFB_ERR_UNIMPLEMENTED, "a mix of HRTF-rendered and matrix-rendered elements takes float32 input");
   // tiles for THIS submit's length (the planes are sized for Fmax)
   const int T = F * N;
@@ -253,8 +256,13 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
     const HrtfEl &he = h->el[e];
     if (!he.on) continue;
     const int C = he.C;
+    const bool dm = he.demix;
+    if (dm && !(demixed && demixed[e])) return fail(IAMFB_ERR_INTERNAL, "binaural HRTF rendering: element %d arrives without its de-mixed channels", e);
+    const bool s16 = s16_io && !dm;
+    const int n_in = dm ? C : he.n_in;
+    const void *in_e = dm ? (const void *)demixed[e] : (const void *)io->in[e];
     const int NL = (s16 && he.plain) ? 2 : 3;
-    const size_t in_per = (size_t)F * he.n_in * N;
+    const size_t in_per = (size_t)F * n_in * N;
     // 16-bit PCM that reaches the renderer untouched: the contraction kernel makes its limb rows itself (no prep pass)
     const bool raw = s16 && he.plain;
     if (!raw && !b->d_planes[e]) {   // limb planes: only submits that need the prep pass pay for them
@@ -265,13 +273,14 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
     if (!raw) {
       HrtfPrepArgs pa;
       memset(&pa, 0, sizeof(pa));
-      pa.in = s16 ? (const void *)(reinterpret_cast<const int16_t *>(io->in[e]) + (size_t)s_lo * in_per) : (const void *)(io->in[e] + (size_t)s_lo * in_per);
+      pa.in = s16 ? (const void *)(reinterpret_cast<const int16_t *>(in_e) + (size_t)s_lo * in_per)
+                  : (const void *)(reinterpret_cast<const float *>(in_e) + (size_t)s_lo * in_per);
       pa.planes = planes;
       pa.hist_in = b->d_hist[e][par ^ 1] + (size_t)s_lo * C * kHrHist;
       pa.hist_out = b->d_hist[e][par] + (size_t)s_lo * C * kHrHist;
       pa.n_present = b->d_np + s_lo;
       pa.frame_of_slot = b->d_fos + (size_t)s_lo * F;
-      pa.C = C; pa.n_in = he.n_in; pa.NL = NL; pa.NBP = nbp; pa.F = F; pa.N = N;
+      pa.C = C; pa.n_in = n_in; pa.NL = NL; pa.NBP = nbp; pa.F = F; pa.N = N;
       pa.mode = he.mode;
       for (int m = 0; m < C; ++m) { pa.row[m] = he.row[m]; pa.gain[m] = he.gain[m]; }
       pa.proj_cols = he.proj_cols;
@@ -294,8 +303,8 @@ int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *
       ga.frame_of_slot = b->d_fos + (size_t)s_lo * F;
       ga.S = s_cnt; ga.C = C; ga.NL = NL; ga.NB = nb; ga.NT = nt; ga.NBP = nbp; ga.F = F; ga.N = N;
       ga.x_shift = NL == 2 ? 15 : 20;
-      ga.raw_in = reinterpret_cast<const int16_t *>(io->in[e]) + (size_t)s_lo * in_per;
-      ga.n_in = he.n_in;
+      ga.raw_in = reinterpret_cast<const int16_t *>(in_e) + (size_t)s_lo * in_per;
+      ga.n_in = n_in;
       for (int m = 0; m < C; ++m) ga.row[m] = he.row[m];
       ga.hist_in = b->d_hist[e][par ^ 1] + (size_t)s_lo * C * kHrHist;
       ga.hist_out = b->d_hist[e][par] + (size_t)s_lo * C * kHrHist;

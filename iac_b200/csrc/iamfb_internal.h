@@ -111,5 +111,7 @@ void iamfb_hrtf_front_destroy(iamfb_hrtf_front *h);
 int iamfb_hrtf_batch_create(const iamfb_hrtf_front *h, int S, int Fmax, iamfb_hrtf_batch **out);
 int iamfb_hrtf_batch_reset(const iamfb_hrtf_front *h, iamfb_hrtf_batch *b, cudaStream_t st);
 void iamfb_hrtf_batch_destroy(iamfb_hrtf_batch *b);
+// demixed[e] != null: element e enters the renderer from that float32 [S][F][C][N] buffer (its layout channels, de-mixed)
 int iamfb_hrtf_run(iamfb_ctx *ctx, const iamfb_hrtf_front *h, iamfb_hrtf_batch *b, const iamfb_io *io, int F, int s_lo, int s_cnt,
-                   iamfb_io *out_io);
+                   iamfb_io *out_io, const float *const *demixed);
+bool iamfb_hrtf_needs_demix(const iamfb_hrtf_front *h, int e);

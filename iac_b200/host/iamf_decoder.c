@@ -479,8 +479,8 @@ static int engine_build(IAMF_DecoderHandle h) {
   /* The binauraliser.  The reference compiles it out by default (DISABLE_BINAURALIZER 1, ae_rdr.h:67-69): binaural output
    * is then the stereo rows of the matrix tables, and that is the default here too.  IAMF_B200_BINAURALIZER=1 is the
    * run-time counterpart of building the reference with DISABLE_BINAURALIZER 0: scene-based elements always take the HRTF
-   * renderer (IAMF_decoder.c:2606-2612), channel-based ones when the mix presentation says headphones_rendering_mode 1
-   * (:2565-2573) - unless they need the de-mixer (scalable layers), which the HRTF front end does not render. */
+   * renderer (IAMF_decoder.c:2606-2612), channel-based ones - scalable layers included: the engine de-mixes them in front
+   * of the renderer - when the mix presentation says headphones_rendering_mode 1 (:2565-2573). */
   {
     const char *benv = getenv("IAMF_B200_BINAURALIZER");
     if (benv && atoi(benv) && h->layout_type == IAMF_LAYOUT_TYPE_BINAURAL && h->mix) {
@@ -489,9 +489,7 @@ static int engine_build(IAMF_DecoderHandle h) {
         int mode = 0;
         for (int k = 0; k < h->mix->n_elements; ++k)
           if (h->mix->el[k].element_id == el->id) mode = h->mix->el[k].headphones_mode;
-        if (el->type != AUDIO_ELEMENT_CHANNEL_BASED) d->el[i].binaural_hrtf = 1;
-        else if (mode == 1 && h->streams[i].layer == 0 && !d->el[i].recon_present && d->el[i].n_in == h->streams[i].n_layout_ch)
-          d->el[i].binaural_hrtf = 1;
+        if (el->type != AUDIO_ELEMENT_CHANNEL_BASED || mode == 1) d->el[i].binaural_hrtf = 1;
       }
     }
   }

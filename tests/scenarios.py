@@ -125,6 +125,15 @@ def hrtf_cases():
         Scenario("hrtf_stereo_plus_matrix_714", [El("channel", LY_STEREO, [L2, R2], hrtf=True, mix_gain=0.6),
                                                  El("channel", LY_714, [L7, R7, SL7, SR7, BL7, BR7, HFL, HFR, HBL, HBR, CC, LFE],
                                                     mix_gain=0.5)], TGT_BIN),
+        Scenario("hrtf_714_scalable_recon", [El("channel", LY_714, [L2, R2, L5, R5, SL7, SR7, HFL, HFR, HBL, HBR, CC, LFE],
+                                                out_gain=[(L2, 1.1220184543), (R2, 1.1220184543)], demix=(1, 0),
+                                                first_layer_layout=LY_STEREO, selected_layer=1, recon_flags=0x780, hrtf=True)],
+                 TGT_BIN, peak_db=(-9.0, 0.0)),
+        Scenario("hrtf_514_from_312_plus_foa", [El("channel", LY_514, [L3, R3, CC, LFE, TL, TR, L5, R5, HFL, HFR], demix=(2, 2),
+                                                   first_layer_layout=LY_312, selected_layer=1, recon_flags=0x618, hrtf=True,
+                                                   mix_gain=0.6),
+                                                El("scene", channels=4, hrtf=True, mix_gain=0.5)], TGT_BIN,
+                 trims={0: (312, 0), 3: (960, 0), 5: (0, 200)}),
         Scenario("hrtf_mono_1024_to_44k1", [El("channel", LY_MONO, [MONO], hrtf=True)], TGT_BIN, frame_size=1024,
                  out_rate=44100, limiter=False),
     ]

@@ -81,10 +81,29 @@ def test_hrtf_full_size_config4():
         assert np.array_equal(got[s][1], ref[s % n][1]), f"stream {s}"
 
 
+def test_hrtf_scalable_element_int16_and_missing_frames():
+    # a scalable element (its layout channels derived by the de-mixer, recon gain, output gain) in front of the renderer, with
+    # int16 hand-over (widened for the de-mixer) and streams without frames in some steps: the de-mixer state of the front
+    # end and the filter state stay in step
+    from gpu_harness import run_product
+    sc = S.hrtf_cases()[5]
+    assert sc.name == "hrtf_714_scalable_recon"
+    compare(sc, 9, 7, [3, 4], seed=41, s16=True)
+    n, F = 8, 9
+    inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 42)
+    P, ramps, oramp = S.synth_params(sc, n, F, seed=0x77 + 42)
+    P["trim_start"][1::3, 2] = 0xFFFF
+    P["trim_start"][2::3, 4:] = 0xFFFF
+    got, _ = run_product(sc, inputs, P, ramps, oramp, splits=[4, 5])
+    for s in range(n):
+        keep = [f for f in range(F) if P["trim_start"][s, f] != 0xFFFF]
+        ref = S.run_oracle(sc, [x[s:s + 1][:, keep] for x in inputs], P[s:s + 1][:, keep])[0]
+        assert np.array_equal(got[s][1], ref[1]), f"stream {s}: PCM differs"
+
+
 def test_hrtf_refuses_what_it_does_not_render():
     from iac_b200 import Engine
-    sc = S.c2_714_to_B()
-    sc.target = S.TGT_BIN
-    sc.elements[0].hrtf = True            # scalable element whose channels are derived by the de-mixer
+    sc = S.c4_hrtf()
+    sc.in_rate = sc.out_rate = 44100     # the HRIR set is sampled at 48 kHz
     with pytest.raises(Exception):
         Engine(S.plan_desc(sc), 4, 2)
