@@ -452,3 +452,29 @@ def test_flac_coded_streams_match_reference(cfg, bits):
     for s in range(n):
         assert got[s] == ref[s][0].tobytes(), f"handle {s} (batch)"
         L.IAMF_decoder_close(hs[s])
+
+
+@pytest.mark.gpu
+def test_binauraliser_renders_a_scalable_stream_through_the_public_api(monkeypatch):
+    """configuration 2's stream (2.0 -> 7.1.4 scalable layers, demixing + recon-gain parameter blocks every frame) on
+    headphones with headphones_rendering_mode 1 and IAMF_B200_BINAURALIZER=1: the 7.1.4 layer is de-mixed in front of the
+    HRTF renderer.  Against the pipeline oracle (pinned de-mixer + HRTF self-oracle)."""
+    sc, st, api_kw, unit_kw = refstreams.case("c2")
+    sc.target = S.TGT_BIN
+    sc.elements[0].hrtf = True
+    st.elements[0].headphones_mode = 1
+    api_kw = dict(api_kw, binaural=True)
+    api_kw.pop("sound_system", None)
+    n, F = 2, 7
+    inputs = S.synth_inputs(sc, n, F, seed=91)
+    P, _, _ = S.synth_params(sc, n, F, seed=92)
+    refstreams.no_param_gaps(sc, P)
+    desc = st.descriptors()
+    ref = S.run_oracle(sc, inputs, P)
+    monkeypatch.setenv("IAMF_B200_BINAURALIZER", "1")
+    api = iamfapi.Api(LIBIAMF)
+    for s in range(n):
+        units = refstreams.temporal_units(sc, st, inputs, P, unit_kw, s)
+        pcm, counts = api.render(desc, units, **api_kw)
+        assert counts == ref[s][0]
+        assert pcm.tobytes() == ref[s][1].tobytes(), f"stream {s}"
