@@ -671,7 +671,8 @@ static int build_element(const iamfb_plan_desc &d, int e, KernelPlan &kp, int &t
 // element-signature combinations the fused kernel is instantiated for: every single-element pipeline, and the
 // two-element pairs of the named configurations (7.1.4 + first-order ambisonics in either order); anything else
 // runs on the multi-kernel path
-static int fused_variant(const int *tmpl, int n_elements) {
+static int fused_variant(const int *tmpl, int n_elements, bool dmr0 = false) {
+  if (n_elements == 1 && dmr0) return (tmpl[0] >= 2 && tmpl[0] <= 8) ? 200 + tmpl[0] : -1;   // parametric down-mixer (layouts with surrounds)
   if (n_elements == 1) return tmpl[0];
   if (n_elements == 2 && tmpl[0] == 7 && tmpl[1] == 11) return 100;
   if (n_elements == 2 && tmpl[0] == 11 && tmpl[1] == 7) return 101;
@@ -698,13 +699,22 @@ static int launch_fused(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa
   }
 #define FCASE(ID, L0, N0, L1, N1) \
   case ID: FLAUNCH(L0, N0, L1, N1, 4, 64) break;
+#define FLAUNCH_DMR(L0, N0)                                                                                           \
+  {                                                                                                                   \
+    CU(cudaFuncSetAttribute(k_fused<L0, N0, 0, 0, 4, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ScopedKernelTimer tm_(ctx, "k_fused");                                                                            \
+    k_fused<L0, N0, 0, 0, 4, 64, true><<<S, 64, smem, st>>>(kp, fa);                                                  \
+  }
+#define FCASE_DMR(ID, L0, N0) \
+  case ID: FLAUNCH_DMR(L0, N0) break;
   // scene-based pipelines with many output channels fit few streams per SM: lighter threads, more of them
 #define FCASE3(ID, L0, N0, L1, N1)                                    \
   case ID:                                                            \
     if (p->fused_variant == 1) FLAUNCH(L0, N0, L1, N1, 2, 128)        \
     else FLAUNCH(L0, N0, L1, N1, 4, 64)                               \
     break;
-  switch (fused_variant(p->tmpl, kp.n_elements)) {
+  switch (fused_variant(p->tmpl, kp.n_elements, kp.el[0].renderer == kRdrDMR)) {
+    FCASE_DMR(202, 2, 6) FCASE_DMR(203, 3, 8) FCASE_DMR(204, 4, 10) FCASE_DMR(205, 5, 8) FCASE_DMR(206, 6, 10) FCASE_DMR(207, 7, 12) FCASE_DMR(208, 8, 6)
     FCASE(0, 0, 1, 0, 0) FCASE(1, 1, 2, 0, 0) FCASE(2, 2, 6, 0, 0) FCASE(3, 3, 8, 0, 0) FCASE(4, 4, 10, 0, 0)
     FCASE(5, 5, 8, 0, 0) FCASE(6, 6, 10, 0, 0) FCASE(7, 7, 12, 0, 0) FCASE(8, 8, 6, 0, 0)
     FCASE3(10, -1, 1, 0, 0) FCASE3(11, -1, 4, 0, 0) FCASE3(12, -1, 9, 0, 0) FCASE3(13, -1, 16, 0, 0)
@@ -954,11 +964,12 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
   {
     const char *env = getenv("IAMFB_FUSED");
     const bool want = !env || atoi(env) != 0;
-    bool eligible = want && !kp.resample && (kp.frame_size & 3) == 0 && fused_variant(p->tmpl, kp.n_elements) >= 0;
+    const bool dmr0 = kp.el[0].renderer == kRdrDMR;
+    bool eligible = want && !kp.resample && (kp.frame_size & 3) == 0 && fused_variant(p->tmpl, kp.n_elements, dmr0) >= 0;
     int nin = 0;
     for (int e = 0; e < kp.n_elements; ++e) {
       nin += kp.el[e].n_in;
-      if (kp.el[e].renderer == kRdrDMR) eligible = false;          // the parametric down-mixer stays on the multi-kernel path
+      if (kp.el[e].renderer == kRdrDMR && (e > 0 || kp.n_elements > 1)) eligible = false;   // down-mixer inside a two-element mix: multi-kernel path
       if (kp.el[e].n_rec > kp.el[e].n_in) eligible = false;        // reconstructed rows are written back over the staged ones
     }
     if (eligible) {

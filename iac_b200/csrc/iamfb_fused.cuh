@@ -241,7 +241,9 @@ __device__ __forceinline__ void fused_reconstruct(const KernelPlan &plan, const 
 // (a trimmed tile is compacted afterwards), so every access is a whole aligned quad.
 //   in_q  the block's staged tile at the thread's samples (rows tl floats apart)
 //   yt    the thread's slots in the mixed time line (&Y[0][ring position], rows rs floats apart)
-template <int LAYOUT, int NREC, int VEC>
+// DMR: the element is rendered by the parametric down-mixer (DMRenderer_downmix, downmix_renderer.c:218-242) instead of a
+// matrix: the output channels are picked from the layout's channels and the ordered two-term sums of their dependencies
+template <int LAYOUT, int NREC, int VEC, bool DMR = false>
 __device__ __forceinline__ void fused_element(const KernelPlan &plan, const FusedArgs &a, int e, const FrameRec &fr,
                                               int sf, int i0, bool first, bool last, float *in_q, int tl, float *yt, int rs,
                                               float *pkt) {
@@ -252,12 +254,23 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
   const ElFrame &ef = fr.el[e];
   const int co = plan.out_channels;
   float *ine = byte_off(in_q, ep.f_row_off);
+  V4 dv[DMR ? kChCount : 1];   // DMR: every IAChannel's value (inputs, then the down-mixer's dependent channels)
   if constexpr (LAYOUT >= 0) {
     V4 x[NREC];
     fused_reconstruct<LAYOUT, NREC, VEC>(plan, a, ep, ef, in_q, i0, x);
-    // the reconstructed layout channels replace the staged rows (this thread's samples only; all its reads are done)
+    if constexpr (DMR) {
 #pragma unroll
-    for (int m = 0; m < NREC; ++m) stsv<VEC>(ine + (size_t)m * tl, x[m]);
+      for (int c = 0; c < kChCount; ++c)
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) dv[c].v[k] = 0.f;
+#pragma unroll
+      for (int m = 0; m < NREC; ++m) dv[fused_order(LAYOUT, m)] = x[m];
+      dmr_prepare<VEC>(ep, ef, dv);
+    } else {
+      // the reconstructed layout channels replace the staged rows (this thread's samples only; all its reads are done)
+#pragma unroll
+      for (int m = 0; m < NREC; ++m) stsv<VEC>(ine + (size_t)m * tl, x[m]);
+    }
   } else {
     // scene based: a mono mapping is a row permutation (folded into the matrix offsets), a projection an ordered
     // mat-vec (IAMF_core_decoder.c:105-130) whose result replaces the staged rows
@@ -309,7 +322,9 @@ __device__ __forceinline__ void fused_element(const KernelPlan &plan, const Fuse
 #pragma unroll
     for (int k = 0; k < kVec; ++k) y.v[k] = 0.f;
     const int q1 = ep.f_csr_ptr[oc + 1];
-    if constexpr (LAYOUT >= 0) {
+    if constexpr (DMR) {
+      if (oc < ep.dmr_n_out) y = pick_channel<VEC>(dv, ep.dmr_out_ch[oc]);
+    } else if constexpr (LAYOUT >= 0) {
       // channel matrices: a handful of entries per row
 #pragma unroll 2
       for (int q = ep.f_csr_ptr[oc]; q < q1; ++q) {
@@ -483,8 +498,8 @@ static __device__ __noinline__ void fused_scan(const float *wm, const float *ew,
 // thread's serial instruction stream: pipelines that fit many streams per SM (small tiles) run 4 samples per thread
 // in 64-thread blocks (fewest instructions); pipelines whose rings are large (few streams per SM) spread a tile over
 // more, lighter threads to keep the SM's schedulers fed.
-template <int L0, int N0, int L1, int N1, int VEC, int THREADS>
-static __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS == 128 ? 4 : 2))) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
+template <int L0, int N0, int L1, int N1, int VEC, int THREADS, bool DMR0 = false>
+static __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? (DMR0 ? 5 : 7) : (THREADS == 128 ? 4 : 2))) k_fused(const __grid_constant__ KernelPlan plan, FusedArgs a) {
   constexpr int kVec = VEC;
   constexpr int kFusedThreads = THREADS;
   typedef Vec<VEC> V4;
@@ -658,7 +673,7 @@ static __global__ void __launch_bounds__(THREADS, (THREADS == 64 ? 7 : (THREADS 
         if (pos >= C) pos -= C;
         float *yt = Y + pos;
         float *pkt = plan.limiter ? PK + pos : nullptr;
-        fused_element<L0, N0, VEC>(plan, a, 0, fr, sf, i0, true, N1 == 0, IN + q, TL, yt, C, pkt);
+        fused_element<L0, N0, VEC, DMR0>(plan, a, 0, fr, sf, i0, true, N1 == 0, IN + q, TL, yt, C, pkt);
         if constexpr (N1 > 0) fused_element<L1, N1, VEC>(plan, a, 1, fr, sf, i0, false, true, IN + q, TL, yt, C, pkt);
       }
       // a trimmed tile: move its surviving samples [lo_t, hi_t) to the front of the tile (iamf_frame_trim,

@@ -208,3 +208,20 @@ def test_streams_without_frames_in_some_submits(mk, s16):
         cnt = [c for f, c in enumerate(got[s][0][:F]) if f in keep] + got[s][0][F:]
         assert cnt == ref[0], f"stream {s}: counts {got[s][0]} vs {ref[0]}"
         assert np.array_equal(got[s][1], ref[1]), f"stream {s}: PCM differs"
+
+
+def test_parametric_downmixer_on_the_fused_kernel(monkeypatch):
+    # DMRenderer plans (downmix_renderer.c: element with demixing info toward a layout with fewer surrounds / tops) run in
+    # k_fused's down-mixer variant - one kernel per submit instead of the multi-kernel path, which stays correct behind
+    # IAMFB_FUSED=0
+    dmr = [sc for sc in S.edge_cases() if "dmr" in sc.name]
+    assert len(dmr) == 2
+    more = S.Scenario("714_scalable_dmr_to_514", [S.El("channel", S.LY_714, [S.L2, S.R2, S.L5, S.R5, S.SL7, S.SR7, S.HFL, S.HFR, S.HBL, S.HBR, S.CC, S.LFE],
+                                                       out_gain=[(S.L2, 1.1), (S.R2, 1.1)], demix=(1, 0), first_layer_layout=S.LY_STEREO,
+                                                       selected_layer=1, recon_flags=0x780, dmr_out_layout=S.LY_514)], S.TGT_D,
+                      peak_db=(-6.0, 3.0), trims={0: (100, 0), 7: (0, 333)})
+    for sc in dmr + [more]:
+        compare(sc, 9, 8, [3, 5], seed=101, expect_path=1)
+        compare(sc, 9, 8, [3, 5], seed=101, s16=True, expect_path=1)
+    monkeypatch.setenv("IAMFB_FUSED", "0")
+    compare(more, 5, 6, [6], seed=102, expect_path=0)
