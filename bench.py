@@ -574,8 +574,18 @@ def run_gpu(args):
         w.close()
         return
 
-    kernels = w.kernel_timing(min(args.steps * R, 120))
+    # per-kernel times come from a separate pass (events around every launch).  A kernel cannot take longer than the whole
+    # submit it is part of took in the sustained region above: a pass whose dominant kernel says otherwise met a clock dip
+    # (seen once: 0.265 ms against a 0.229 ms submit) and is repeated, at most twice; the passes taken are reported
+    passes = []
+    for _ in range(3):
+        kernels = w.kernel_timing(min(args.steps * R, 120))
+        dom_ms = max(v["ms_per_submit"] for v in kernels.values())
+        passes.append(round(dom_ms, 6))
+        if dom_ms <= ms_per_submit * 1.02:
+            break
     roofline = w.roofline(kernels, ms_per_submit, out_per_submit)
+    roofline["timing_passes_dominant_ms"] = passes
 
     # ---- end to end through the host-buffer entry point of the C ABI: pinned host memory -> H2D -> kernels -> D2H every
     # step.  The host buffers hold what core decode produces for this workload - int16 PCM (Opus / AAC / 16-bit ipcm),

@@ -1223,6 +1223,8 @@ static int launch_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa,
   pa.frames = fa.frames; pa.start_win = fa.start_win; pa.stop_win = fa.stop_win; pa.submit = fa.submit; pa.state = fa.state;
   pa.acc = fa.acc; pa.hist_y = fa.hist_y; pa.hist_pk = fa.hist_pk; pa.pcm = fa.pcm; pa.stride_bytes = fa.stride_bytes;
   pa.n_frames = fa.n_frames;
+  for (int e = 0; e < kp.n_elements; ++e) pa.gain_ramp[e] = fa.gain_ramp[e];
+  pa.out_gain_ramp = fa.out_gain_ramp;
   pa.row_bytes = kStreamTile * (s16 ? 2 : 4);
   pa.stage_bytes = (nin * pa.row_bytes + 127) & ~127;
   // active output channels of the signature (rows of the time line): every channel some matrix row of an element lands on
@@ -1866,8 +1868,10 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
     fa.tile = p->fused_tile;
     fa.only_irregular = 0;
     fa.in_s16 = s16_in ? 1 : 0;
-    const bool stream_first = p->stream && !s16_in;
-    if (p->pipe && !stream_first && !flush && !io->gain_ramp[0] && !io->gain_ramp[1] && !io->out_gain_ramp) {
+    const bool ramps = !flush && (io->gain_ramp[0] || io->gain_ramp[1] || io->out_gain_ramp);   // (io is null in a flush)
+    // (k_stream has no animated-gain form: those submits take k_pipe, which has)
+    const bool stream_first = p->stream && !s16_in && !(ramps && p->pipe);
+    if (p->pipe && !stream_first && !flush) {
       // untrimmed streams: the pipelined kernel; the rest (flagged by k_resolve): k_fused
       int r = launch_pipe(ctx, p, fa, S, s16_in);
       if (r) return r;

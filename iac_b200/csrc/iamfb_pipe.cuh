@@ -145,6 +145,8 @@ struct PipeArgs {
   int stage_bytes;              // bytes between two input stages (multiple of 128)
   unsigned tpf_magic;           // ceil(2^32 / tiles per frame)
   float neg_zero;               // -0.0f, opaque to the assembler (pipe_mul2)
+  const float *gain_ramp[kMaxEl];   // optional [S][F][N]: animated element mix gains (per sample; k_gain_expand or the caller)
+  const float *out_gain_ramp;       // optional [S][F][N]: animated output mix gain
 };
 
 template <int VEC>
@@ -419,6 +421,29 @@ __device__ __forceinline__ void pipe_mix(Vec<VEC> (&y)[NYY], const Vec<VEC> (&y1
   }
 }
 template <class SIG, class E, int OC, int VEC, int NYY>
+__device__ __forceinline__ void pipe_scale_v(Vec<VEC> (&y)[NYY], const Vec<VEC> &g) {   // ... x its per-sample mix gains
+  if constexpr (OC < SIG::CO) {
+    if constexpr (E::any(OC)) {
+      constexpr int row = SIG::yrow(OC);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) y[row].v[k] *= g.v[k];
+    }
+    pipe_scale_v<SIG, E, OC + 1, VEC, NYY>(y, g);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> pipe_ldg(const float *p) {   // VEC consecutive floats from global memory (aligned)
+  Vec<VEC> r;
+  if constexpr (VEC == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  }
+  return r;
+}
+template <class SIG, class E, int OC, int VEC, int NYY>
 __device__ __forceinline__ void pipe_scale(Vec<VEC> (&y)[NYY], float g) {   // the element's channels x its mix gain
   if constexpr (OC < SIG::CO) {
     if constexpr (E::any(OC)) {
@@ -614,8 +639,12 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
 #pragma unroll
     for (int r = 0; r < NY; ++r) yh[r] = vzero<VEC>();
     pipe_render_element<SIG, E0, VEC, NY>(plan, ep0, fr.el[0], rows, a.row_bytes, i0, fade_w, a.start_win, a.stop_win, yh, a.neg_zero);
-    // element mix gain (iamf_frame_gain IAMF_decoder.c:1392): skipped when it is 1 (or not positive)
-    {
+    // element mix gain (iamf_frame_gain IAMF_decoder.c:1392): a constant, skipped when it is 1 (or not positive) - or one
+    // gain per sample (animated mix gain, :1395-1405), always applied
+    const size_t gidx = ((size_t)s * a.n_frames + f) * plan.frame_size + i0;
+    if (a.gain_ramp[0]) {   // (block-uniform)
+      pipe_scale_v<SIG, E0, 0, VEC, NY>(yh, pipe_ldg<VEC>(a.gain_ramp[0] + gidx));
+    } else {
       const float eg = fr.el[0].gain;
       if (eg != 1.f && eg > 0.f) pipe_scale<SIG, E0, 0, VEC, NY>(yh, eg);
     }
@@ -625,13 +654,24 @@ k_pipe(const __grid_constant__ KernelPlan plan, PipeArgs a, const __grid_constan
       for (int r = 0; r < NY; ++r) y1[r] = vzero<VEC>();
       pipe_render_element<SIG, E1, VEC, NY>(plan, plan.el[1], fr.el[1], rows + nin0 * a.row_bytes, a.row_bytes, i0, fade_w, a.start_win,
                                             a.stop_win, y1, a.neg_zero);
-      const float eg = fr.el[1].gain;
-      if (eg != 1.f && eg > 0.f) pipe_scale<SIG, E1, 0, VEC, NY>(y1, eg);
+      if (a.gain_ramp[1]) {
+        pipe_scale_v<SIG, E1, 0, VEC, NY>(y1, pipe_ldg<VEC>(a.gain_ramp[1] + gidx));
+      } else {
+        const float eg = fr.el[1].gain;
+        if (eg != 1.f && eg > 0.f) pipe_scale<SIG, E1, 0, VEC, NY>(y1, eg);
+      }
       pipe_mix<SIG, 0, VEC, NY>(yh, y1);
     }
     // output mix gain (:3463-3469), loudness (:3480-3484, :3211) - each skipped when it is 1 - and the peak of every instant
     const float ogain = fr.out_gain;
-    const bool og_on = ogain != 1.f && ogain > 0.f;
+    const bool og_on = ogain != 1.f && ogain > 0.f && !a.out_gain_ramp;
+    if (a.out_gain_ramp) {   // animated output mix gain (:3463-3469): one gain per sample, every channel
+      const V og = pipe_ldg<VEC>(a.out_gain_ramp + gidx);
+#pragma unroll
+      for (int r = 0; r < NY; ++r)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) yh[r].v[k] *= og.v[k];
+    }
     const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
     V peak = vzero<VEC>();
     if (og_on | loud_on | (bits == 0)) {          // (block-uniform; rarely taken)

@@ -6,7 +6,7 @@ import scenarios as S
 from iac_b200 import Engine
 
 
-def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0, s16=False, expect_path=None):
+def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, device=0, s16=False, expect_path=None, kernels=None):
     n_streams, F = P.shape
     splits = splits or [F]
     assert sum(splits) == F
@@ -14,6 +14,8 @@ def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, 
     if expect_path is not None:
         path = eng.kernel_path_s16 if s16 else eng.kernel_path
         assert path == expect_path, f"{sc.name}: kernel path {path}, expected {expect_path}"
+    if kernels is not None:   # the caller wants to know which kernels ran (name -> launches)
+        eng.set_timing(True)
     co = eng.out_channels
     bps = eng.bytes_per_sample
     counts = [[] for _ in range(n_streams)]
@@ -38,5 +40,7 @@ def run_product(sc, inputs, P, ramps=None, oramp=None, splits=None, flush=True, 
             counts[s].append(int(cnt[s]))
             chunks[s].append(pcm[s, : int(cnt[s]) * co * bps].copy())
     launches = eng.launch_count()
+    if kernels is not None:
+        kernels.update({k: int(v[1]) for k, v in eng.get_timing().items()})
     eng.close()
     return {s: (counts[s], np.concatenate(chunks[s]) if chunks[s] else np.zeros(0, np.uint8)) for s in range(n_streams)}, launches

@@ -225,3 +225,25 @@ def test_parametric_downmixer_on_the_fused_kernel(monkeypatch):
         compare(sc, 9, 8, [3, 5], seed=101, s16=True, expect_path=1)
     monkeypatch.setenv("IAMFB_FUSED", "0")
     compare(more, 5, 6, [6], seed=102, expect_path=0)
+
+
+def test_animated_gains_inside_the_pipelined_kernel():
+    # per-sample element / output mix gains (animated mix gain) are applied by k_pipe itself; only streams with trimmed /
+    # missing frames of such a submit are left to k_fused
+    import dataclasses
+    from gpu_harness import run_product
+    for sc in (S.c1_stereo(ramp=True, out_gain=1.2, peak_db=(-3.0, 3.0)), S.c2_714_to_B(ramp=True),
+               S.c4_714_foa_binaural(ramp=True), dataclasses.replace(S.c3_toa_to_H(ramp=True), bit_depth=24)):
+        sc.name += "_ramps"
+        n, F = 9, 8
+        inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 111)
+        P, ramps, oramp = S.synth_params(sc, n, F, seed=0x77 + 111)
+        P["trim_start"][2::4, 3] = 200                      # some streams irregular in the second submit
+        for s16 in (False, True):
+            ran = {}
+            got, _ = run_product(sc, inputs, P, ramps, oramp, splits=[3, 5], s16=s16, kernels=ran)
+            assert ran.get("k_pipe", 0) >= 2 and "k_stream" not in ran, f"{sc.name}: kernels {ran}"
+            ref = S.run_oracle(sc, inputs, P, ramps, oramp)
+            for s in range(n):
+                assert got[s][0] == ref[s][0], f"{sc.name}: stream {s} counts"
+                assert np.array_equal(got[s][1], ref[s][1]), f"{sc.name}: stream {s} PCM differs (s16={s16})"
