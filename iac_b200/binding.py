@@ -29,7 +29,8 @@ class ElementDesc(C.Structure):
 class PlanDesc(C.Structure):
     _fields_ = [("frame_size", C.c_int32), ("in_rate", C.c_int32), ("out_rate", C.c_int32), ("n_elements", C.c_int32),
                 ("el", ElementDesc * MAXE), ("target", C.c_int32), ("loudness_gain", C.c_float),
-                ("limiter", C.c_int32), ("limiter_threshold_db", C.c_float), ("bit_depth", C.c_int32)]
+                ("limiter", C.c_int32), ("limiter_threshold_db", C.c_float), ("bit_depth", C.c_int32),
+                ("arithmetic", C.c_int32)]    # 0 exact (bit-identical to the reference), 1 IAMFB_ARITH_FMA (tolerance mode)
 
 
 class _ElParams(C.Structure):
@@ -97,6 +98,8 @@ def lib():
     L.iamfb_selftest_quotient.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
     L.iamfb_plan_kernel_path.argtypes = [vp]
     L.iamfb_plan_kernel_path.restype = C.c_int
+    L.iamfb_plan_arithmetic.argtypes = [vp]
+    L.iamfb_plan_arithmetic.restype = C.c_int
     L.iamfb_plan_kernel_path_fmt.argtypes = [vp, C.c_int]
     L.iamfb_plan_kernel_path_fmt.restype = C.c_int
     L.iamfb_plan_max_out_samples.argtypes = [vp, C.c_int]
@@ -232,6 +235,7 @@ class Engine:
         self.out_channels = L.iamfb_plan_out_channels(self.plan)
         self.kernel_path = L.iamfb_plan_kernel_path(self.plan)   # 0 multi-kernel, 1 k_fused, 2 k_stream, 3 k_pipe (float32 submits)
         self.kernel_path_s16 = L.iamfb_plan_kernel_path_fmt(self.plan, 1)   # the same for int16 submits
+        self.arithmetic = L.iamfb_plan_arithmetic(self.plan)                # 1: an IAMFB_ARITH_FMA kernel variant serves the plan
         self.bytes_per_sample = desc.bit_depth // 8 if desc.bit_depth else 4
 
     def close(self):

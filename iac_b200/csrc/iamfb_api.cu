@@ -130,6 +130,7 @@ struct iamfb_plan {
   // k_pipe_rs (iamfb_pipe_rs.cuh): the resampling pipelines' regular streams; irregular ones and flushes: multi-kernel path
   bool rs_pipe;
   int rs_pipe_sig, rs_ring, rs_mirror;
+  bool fma;                // IAMFB_ARITH_FMA asked for (the signature's fused variant is used where there is one)
   float4 *d_interp4;       // k_pipe_rs: cubic interpolation weights per phase
   float4 *d_tab4p;         // k_pipe_rs: the tap items with rs_tab_pad zero items on either side of every row
   int rs_tab_row, rs_tab_pad;
@@ -850,6 +851,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
   if (d->target < 0 || d->target >= IAMFB_TARGET_COUNT) return fail(IAMFB_ERR_BAD_ARG, "target %d", d->target);
   if (d->bit_depth != 0 && d->bit_depth != 16 && d->bit_depth != 24 && d->bit_depth != 32)
     return fail(IAMFB_ERR_BAD_ARG, "bit_depth %d", d->bit_depth);
+  if (d->arithmetic != IAMFB_ARITH_EXACT && d->arithmetic != IAMFB_ARITH_FMA) return fail(IAMFB_ERR_BAD_ARG, "arithmetic %d", d->arithmetic);
   if (d->in_rate <= 0 || d->out_rate <= 0) return fail(IAMFB_ERR_BAD_ARG, "rates %d -> %d", d->in_rate, d->out_rate);
   CU(cudaSetDevice(ctx->device));
   for (int e = 0; e < d->n_elements; ++e)
@@ -1081,7 +1083,7 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
               }
             }
           }
-          const PipeSigInfo *si = ok ? iamfb_pipe_find(key[0][0], key[0][1], kp.n_elements > 1 ? key[1][0] : 0, kp.n_elements > 1 ? key[1][1] : 0, d->target) : nullptr;
+          const PipeSigInfo *si = ok ? iamfb_pipe_find(key[0][0], key[0][1], kp.n_elements > 1 ? key[1][0] : 0, kp.n_elements > 1 ? key[1][1] : 0, d->target, d->arithmetic == IAMFB_ARITH_FMA) : nullptr;
           if (si) {
             // the second element's rows follow the first's inside a stage: tensor copies land on 128-byte boundaries
             const int n0 = kp.el[0].n_in;
@@ -1173,24 +1175,31 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
 
 // ---- k_pipe dispatch (the instantiations live in iamfb_pipe_g<N>.cu)
 static const PipeSigInfo k_pipe_sigs[] = {
-#define X(id, L0, N0, L1, N1, T, NW, VEC, MINB) {id, L0, N0, L1, N1, T, NW, VEC},
+#define X(id, L0, N0, L1, N1, T, NW, VEC, MINB) {id, L0, N0, L1, N1, T, NW, VEC, 0},
     IAMFB_PIPE_SIGS(X)
 #undef X
+#define X(id, L0, N0, L1, N1, T, NW, VEC, MINB) {id, L0, N0, L1, N1, T, NW, VEC, 1},
+    IAMFB_PIPE_SIGS_FMA(X)
+#undef X
 };
-const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target) {
+const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target, bool fma) {
+  if (fma)
+    for (const PipeSigInfo &si : k_pipe_sigs)
+      if (si.fma && si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
   const char *alt = getenv("IAMFB_PIPE_ALT");   // experiment: the alternative thread shape of a signature (ids >= 13)
   if (alt && atoi(alt))
     for (const PipeSigInfo &si : k_pipe_sigs)
-      if (si.id >= 13 && si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
+      if (si.id >= 13 && !si.fma && si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
   for (const PipeSigInfo &si : k_pipe_sigs)
-    if (si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
+    if (!si.fma && si.l0 == l0 && si.n0 == n0 && si.n1 == n1 && (n1 == 0 || si.l1 == l1) && si.target == target) return &si;
   return nullptr;
 }
 #define G(n) int iamfb_pipe_launch_g##n(iamfb_ctx *, int, bool, const KernelPlan &, const PipeArgs &, int, size_t, const CUtensorMap &, const CUtensorMap &);
-G(0) G(1) G(2) G(3) G(4) G(5) G(6)
+G(0) G(1) G(2) G(3) G(4) G(5) G(6) G(7)
 #undef G
 int iamfb_pipe_launch(iamfb_ctx *ctx, int sig_id, bool s16, const KernelPlan &kp, const PipeArgs &pa, int S, size_t smem, const CUtensorMap &m0,
                       const CUtensorMap &m1) {
+  if (sig_id >= kPipeFmaFirstId) return iamfb_pipe_launch_g7(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);   // IAMFB_ARITH_FMA variants
   switch (IAMFB_PIPE_GROUP_OF(sig_id)) {
     case 0: return iamfb_pipe_launch_g0(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
     case 1: return iamfb_pipe_launch_g1(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
@@ -1362,6 +1371,10 @@ extern "C" int iamfb_plan_kernel_path_fmt(const iamfb_plan *p, int in_format) {
   return p->pipe ? IAMFB_PATH_PIPE : IAMFB_PATH_FUSED;
 }
 extern "C" int iamfb_plan_kernel_path(const iamfb_plan *p) { return iamfb_plan_kernel_path_fmt(p, IAMFB_IN_F32); }
+extern "C" int iamfb_plan_arithmetic(const iamfb_plan *p) {
+  if (!p) return -1;
+  return (p->pipe && p->pipe_sig >= kPipeFmaFirstId) ? IAMFB_ARITH_FMA : IAMFB_ARITH_EXACT;
+}
 
 extern "C" int iamfb_plan_max_out_samples(const iamfb_plan *p, int n_frames) {
   if (!p) return 0;

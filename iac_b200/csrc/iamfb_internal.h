@@ -88,13 +88,16 @@ struct ScopedKernelTimer {
   X(13, 7, 12, 0, 0, 1, 4, 2, 7) X(14, -1, 16, 0, 0, 7, 2, 4, 3) X(15, 1, 2, 1, 2, 13, 2, 4, 7)
 #define IAMFB_PIPE_GROUP_OF(id) ((id) == 0 ? 0 : ((id) == 10 ? 1 : ((id) == 12 ? 2 : ((id) == 11 ? 3 : ((id) == 13 ? 4 : ((id) == 14 ? 5 : (4 + (id) % 3)))))))
 constexpr int kPipeGroups = 7;
+// IAMFB_ARITH_FMA variants (same columns): the dense contraction of the signature fuses multiply and add
+#define IAMFB_PIPE_SIGS_FMA(X) X(48, -1, 16, 0, 0, 7, 4, 2, 3)   /* (the 2 x 4 thread shape measured 18 % slower) */
+constexpr int kPipeFmaFirstId = 48;
 
 // ---- k_pipe_rs (iamfb_pipe_rs.cuh): resampling pipelines.  X(id, L0, N0, TARGET, NW, VEC, MINB): one channel-based element
 #define IAMFB_PIPE_RS_SIGS(X) X(32, 1, 2, 0, 2, 4, 4) X(33, 7, 12, 1, 2, 4, 4) X(34, 1, 2, 0, 4, 2, 7) X(35, 1, 2, 0, 4, 2, 5) X(36, 1, 2, 0, 2, 4, 6)
 
-struct PipeSigInfo { int id, l0, n0, l1, n1, target, nw, vec; };
-// signature serving (element kinds / layouts, target), or nullptr
-const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target);
+struct PipeSigInfo { int id, l0, n0, l1, n1, target, nw, vec, fma; };
+// signature serving (element kinds / layouts, target), or nullptr; fma: prefer the IAMFB_ARITH_FMA variant when there is one
+const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target, bool fma);
 
 namespace iamfb { struct PipeArgs; }
 // launches k_pipe<sig, s16> over S streams; returns IAMFB_OK or an error (the launch itself is checked by the caller)

@@ -91,12 +91,13 @@ struct PipeNoEl {
 // One pipeline signature.  (L0, N0) / (L1, N1): layout (or -1 = scene-based) and renderer input count of the elements,
 // N1 == 0 for a single element.  S16: the decoded rows are staged as int16.  NSTAGE input stages, NW worker warps of VEC
 // instants per thread, MINB blocks per SM the register allocation aims at.
-template <int L0, int N0, int L1, int N1, int TARGET, bool S16, int NSTAGE_, int NW_, int VEC_, int MINB_>
+template <int L0, int N0, int L1, int N1, int TARGET, bool S16, int NSTAGE_, int NW_, int VEC_, int MINB_, bool FMA_ = false>
 struct PipeSig {
   typedef PipeEl<L0, N0, TARGET> E0;
   typedef typename std::conditional<(N1 > 0), PipeEl<L1, (N1 > 0 ? N1 : 1), TARGET>, PipeNoEl>::type E1;
   static constexpr bool kTwo = N1 > 0;
   static constexpr bool kS16 = S16;
+  static constexpr bool kFma = FMA_;   // IAMFB_ARITH_FMA: the dense contractions fuse multiply and add (tolerance mode)
   static constexpr int kStages = NSTAGE_, NW = NW_, VEC = VEC_, kMinBlocks = MINB_;
   static constexpr int kThreads = (NW_ + 1) * 32, kWorkers = NW_ * 32;
   static constexpr int CO = kPipeTargetCh[TARGET];
@@ -224,6 +225,11 @@ __device__ __forceinline__ void pipe_mac2(float &y0, float &y1, float v0, float 
       "mov.b64 ry, {%0,%1}; add.rn.f32x2 ry, ry, rt; mov.b64 {%0,%1}, ry;}"
       : "+f"(y0), "+f"(y1) : "f"(v0), "f"(v1), "f"(c), "f"(nz));
 }
+// IAMFB_ARITH_FMA: y += v * c with ONE rounding (not the reference's two)
+__device__ __forceinline__ void pipe_fma2(float &y0, float &y1, float v0, float v1, float c) {
+  asm("{.reg .b64 rv, rc, ry; mov.b64 rv, {%2,%3}; mov.b64 rc, {%4,%4}; mov.b64 ry, {%0,%1}; fma.rn.f32x2 ry, rv, rc, ry; mov.b64 {%0,%1}, ry;}"
+      : "+f"(y0), "+f"(y1) : "f"(v0), "f"(v1), "f"(c));
+}
 template <class SIG, class E, int M, int OC, int VEC, int NYY>
 __device__ __forceinline__ void pipe_mat_col(Vec<VEC> (&y)[NYY], const Vec<VEC> &v, float nz) {
   if constexpr (OC < SIG::CO) {
@@ -234,6 +240,7 @@ __device__ __forceinline__ void pipe_mat_col(Vec<VEC> (&y)[NYY], const Vec<VEC> 
 #pragma unroll
         for (int k = 0; k < VEC; k += 2) {
           if constexpr (E::first_nz(M, OC)) pipe_mul2(y[row].v[k], y[row].v[k + 1], v.v[k], v.v[k + 1], c, nz);
+          else if constexpr (SIG::kFma) pipe_fma2(y[row].v[k], y[row].v[k + 1], v.v[k], v.v[k + 1], c);
           else pipe_mac2(y[row].v[k], y[row].v[k + 1], v.v[k], v.v[k + 1], c, nz);
         }
       } else if constexpr (E::first_nz(M, OC)) {

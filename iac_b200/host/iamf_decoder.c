@@ -498,6 +498,12 @@ static int engine_build(IAMF_DecoderHandle h) {
   d->limiter = h->limiter_on;
   d->limiter_threshold_db = h->threshold_db;
   d->bit_depth = h->bit_depth ? (int)h->bit_depth : 16; /* bit_depth 0: rendered but never copied out (:121-167) */
+  {
+    /* default: bit-identical to the reference.  IAMF_B200_ARITH=fma lets the HOA matrix and the resampler FIR fuse multiply
+     * and add (half the FP32 work, PCM within +-1 LSB of the reference's; include/iamf_b200.h, IAMFB_ARITH_FMA). */
+    const char *aenv = getenv("IAMF_B200_ARITH");
+    d->arithmetic = (aenv && (!strcmp(aenv, "fma") || !strcmp(aenv, "1"))) ? IAMFB_ARITH_FMA : IAMFB_ARITH_EXACT;
+  }
   h->frame_size = d->frame_size;
 
   engine_release(h);

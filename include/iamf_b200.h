@@ -128,7 +128,19 @@ typedef struct iamfb_plan_desc {
   int32_t limiter;                           /* IAMF_decoder_peak_limiter_enable */
   float limiter_threshold_db;                /* IAMF_decoder_peak_limiter_set_threshold (default -1 dBFS) */
   int32_t bit_depth;                         /* 16 | 24 | 32 ; 0 => float32 interleaved (test/debug output) */
+  int32_t arithmetic;                        /* IAMFB_ARITH_EXACT (0, default): every expression in the reference's order and
+                                                precision - the PCM is bit-identical to the reference decoder's.
+                                                IAMFB_ARITH_FMA: the dense contraction of the path that is bound by the FP32
+                                                pipe - the HOA-to-loudspeaker matrix (h2m_rdr.c:1088-1150) - fuses each
+                                                multiply with its add (one rounding instead of two, same summation order):
+                                                half the FP32 work; the PCM then agrees with the reference within +-1 LSB at
+                                                16 bit, +-2 LSB at 24 bit (one 24-bit LSB is two float32 ulps near full
+                                                scale) and 2e-7 of full scale as float (BASELINE's tolerance: 1e-5) instead
+                                                of bit for bit.  Signatures without such a variant run the exact kernels
+                                                (the resampler FIR was measured too: it is bound by shared-memory traffic,
+                                                fusing gains nothing there). */
 } iamfb_plan_desc;
+enum { IAMFB_ARITH_EXACT = 0, IAMFB_ARITH_FMA = 1 };
 
 /* Raw per-(stream,frame) parameters = what the parameter-block OBUs of one temporal unit resolve to before the
  * reference calls the stage functions (IAMF_decoder.c:2131-2151, 2324-2349, 3425-3469). */
@@ -220,6 +232,9 @@ int iamfb_plan_out_channels(const iamfb_plan *plan);
 enum { IAMFB_PATH_MULTI = 0, IAMFB_PATH_FUSED = 1, IAMFB_PATH_STREAM = 2, IAMFB_PATH_PIPE = 3 };
 int iamfb_plan_kernel_path(const iamfb_plan *plan);                      /* for float32 submits */
 int iamfb_plan_kernel_path_fmt(const iamfb_plan *plan, int in_format);   /* IAMFB_IN_F32 | IAMFB_IN_S16 */
+/* the arithmetic the plan's kernels really use: IAMFB_ARITH_FMA only when it was asked for AND the signature has such a
+ * variant (third-order ambisonics -> sound system H); IAMFB_ARITH_EXACT otherwise */
+int iamfb_plan_arithmetic(const iamfb_plan *plan);
 /* upper bound of samples per channel one submit of n_frames can produce for one stream */
 int iamfb_plan_max_out_samples(const iamfb_plan *plan, int n_frames);
 /* bytes between consecutive streams in the pcm buffer for a submit of n_frames */

@@ -72,6 +72,7 @@ class Scenario:
     ramp: bool = False                         # animated element/output mix gains
     trims: Optional[dict] = None               # {frame index: (trim_start, trim_end)}
     peak_db: tuple = (-12.0, 2.0)              # per-stream peak level range (uniform), SURVEY 8d
+    arithmetic: int = 0                        # product only: 1 = IAMFB_ARITH_FMA (tolerance mode); the oracle is always exact
 
     @property
     def out_channels(self):
@@ -259,6 +260,7 @@ def plan_desc(sc: Scenario):
     d.limiter = 1 if sc.limiter else 0
     d.limiter_threshold_db = sc.threshold_db
     d.bit_depth = sc.bit_depth
+    d.arithmetic = sc.arithmetic
     return d
 
 

@@ -247,3 +247,51 @@ def test_animated_gains_inside_the_pipelined_kernel():
             for s in range(n):
                 assert got[s][0] == ref[s][0], f"{sc.name}: stream {s} counts"
                 assert np.array_equal(got[s][1], ref[s][1]), f"{sc.name}: stream {s} PCM differs (s16={s16})"
+
+
+def _pcm_values(sc, raw):
+    """interleaved PCM bytes -> float64 values in units of one LSB (16 / 24 / 32 bit) or of full scale (float output)"""
+    if sc.bit_depth == 0:
+        return raw.view(np.float32).astype(np.float64)
+    if sc.bit_depth == 16:
+        return raw.view(np.int16).astype(np.float64)
+    if sc.bit_depth == 32:
+        return raw.view(np.int32).astype(np.float64)
+    b = raw.reshape(-1, 3).astype(np.int32)
+    v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+    return np.where(v >= 1 << 23, v - (1 << 24), v).astype(np.float64)
+
+
+def test_fma_arithmetic_stays_within_the_stated_tolerance():
+    # IAMFB_ARITH_FMA (include/iamf_b200.h): the HOA matrix fuses multiply and add - no longer bit for bit, but within
+    # BASELINE.json's tolerance against the (exact) oracle: +-1 LSB at 16 bit, 1e-5 of full scale as float (measured: 2e-7);
+    # at 24 bit one LSB is two float32 ulps near full scale, so the bound there is +-2 LSB.
+    # Signatures without a fused variant must stay bit-identical under the switch.
+    import dataclasses
+    from gpu_harness import run_product
+    cases = [(S.c3_toa_to_H(), 1.0), (dataclasses.replace(S.c3_toa_to_H(), bit_depth=24), 2.0),
+             (dataclasses.replace(S.c3_toa_to_H(), bit_depth=0), 1e-6), (dataclasses.replace(S.c3_toa_to_H(), limiter=False), 1.0),
+             (S.c5_resample(), 0.0), (S.c2_714_to_B(), 0.0)]
+    for k, (sc, tol) in enumerate(cases):
+        sc = dataclasses.replace(sc, arithmetic=1, name=sc.name + "_fma")
+        n, F = 21, 10
+        inputs = S.synth_inputs(sc, n, F, seed=0x1A3F + 300 + k)
+        P, ramps, oramp = S.synth_params(sc, n, F, seed=0x77 + 300 + k)
+        ref = S.run_oracle(sc, inputs, P, ramps, oramp)
+        for s16 in (False, True):
+            from iac_b200 import Engine
+            eng = Engine(S.plan_desc(sc), 1, 1)
+            assert eng.arithmetic == (1 if tol else 0), f"{sc.name}: arithmetic {eng.arithmetic}"
+            eng.close()
+            got, _ = run_product(sc, inputs, P, ramps, oramp, splits=[4, 6], s16=s16)
+            worst, differing = 0.0, 0
+            for s in range(n):
+                assert got[s][0] == ref[s][0], f"{sc.name}: stream {s} counts"
+                a, b = _pcm_values(sc, got[s][1]), _pcm_values(sc, ref[s][1])
+                assert a.shape == b.shape
+                d = np.abs(a - b)
+                worst = max(worst, float(d.max()))
+                differing += int((d != 0).sum())
+            assert worst <= tol, f"{sc.name}: differs from the oracle by {worst} (allowed {tol}), s16={s16}"
+            if tol:
+                assert differing > 0, f"{sc.name}: identical to the exact kernels - the fused variant did not run?"
