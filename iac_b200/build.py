@@ -83,9 +83,29 @@ def build_dropin(force=False):
     return DROPIN
 
 
+PLAYER_SRC = os.path.join(PKG, "player")
+PLAYER = os.path.join(PKG, "iamfplayer_b200")
+
+
+def build_player(force=False):
+    """the command-line player (IAMF bitstream / MP4 in, WAV + .met out) on top of libiamf.so: own WAV writer and MP4 reader"""
+    srcs = [os.path.join(PLAYER_SRC, f) for f in sorted(os.listdir(PLAYER_SRC)) if f.endswith(".c")]
+    deps = srcs + [os.path.join(PLAYER_SRC, f) for f in os.listdir(PLAYER_SRC) if f.endswith(".h")] + [
+        os.path.join(ROOT, "include", "IAMF_decoder.h"), DROPIN]
+    if not force and not _stale(PLAYER, deps):
+        return PLAYER
+    cmd = [os.environ.get("CC", "gcc"), "-std=c99", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + PLAYER_SRC, "-o", PLAYER] + srcs + [
+        "-L" + PKG, "-l:libiamf.so", "-Wl,-rpath,$ORIGIN"]
+    print("[iac_b200.build]", " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return PLAYER
+
+
 def build_all(force=False):
     build_cuda(force)
-    return build_dropin(force)
+    lib = build_dropin(force)
+    build_player(force)
+    return lib
 
 
 if __name__ == "__main__":

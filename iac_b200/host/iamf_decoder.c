@@ -554,9 +554,29 @@ static void metadata_init(IAMF_DecoderHandle h) {
                                                                                          : SOUND_SYSTEM_INVALID;
   m->bitdepth = h->bit_depth;
   m->sampling_rate = IH_OUTPUT_RATE;
-  m->output_sound_mode = h->layout_type == IAMF_LAYOUT_TYPE_BINAURAL ? IAMF_SOUND_MODE_BINAURAL
-                         : h->sound_system == SOUND_SYSTEM_A         ? IAMF_SOUND_MODE_STEREO
-                                                                     : IAMF_SOUND_MODE_MULTICHANNEL;
+  /* iamf_presentation_get_output_sound_mode (IAMF_decoder.c:1555-1578): every element contributes a mode - a scene-based one
+   * the mode of the OUTPUT layout (:358-370), a channel-based one the mode of its own selected layer layout - and the
+   * modes combine (:241-254: equal -> that mode, binaural with anything else -> n/a, otherwise multichannel) */
+  {
+    int mode = IAMF_SOUND_MODE_NONE;
+    for (int i = 0; i < h->n_streams; ++i) {
+      const ih_stream *st = &h->streams[i];
+      int sm;
+      if (st->el->type != AUDIO_ELEMENT_CHANNEL_BASED)
+        sm = h->layout_type == IAMF_LAYOUT_TYPE_BINAURAL ? IAMF_SOUND_MODE_BINAURAL
+             : h->sound_system == SOUND_SYSTEM_A         ? IAMF_SOUND_MODE_STEREO
+                                                         : IAMF_SOUND_MODE_MULTICHANNEL;
+      else
+        sm = (st->layout == IA_CHANNEL_LAYOUT_MONO || st->layout == IA_CHANNEL_LAYOUT_STEREO) ? IAMF_SOUND_MODE_STEREO
+             : st->layout == IA_CHANNEL_LAYOUT_BINAURAL                                          ? IAMF_SOUND_MODE_BINAURAL
+                                                                                                 : IAMF_SOUND_MODE_MULTICHANNEL;
+      if (mode == IAMF_SOUND_MODE_NONE) mode = sm;
+      else if (sm == IAMF_SOUND_MODE_NONE || sm == mode) { /* unchanged */ }
+      else if (mode == IAMF_SOUND_MODE_BINAURAL || sm == IAMF_SOUND_MODE_BINAURAL) mode = IAMF_SOUND_MODE_NA;
+      else mode = IAMF_SOUND_MODE_MULTICHANNEL;
+    }
+    m->output_sound_mode = (IAMF_SoundMode)mode;
+  }
   m->num_loudness_layouts = mix->n_layouts;
   if (mix->n_layouts > 0) {
     m->loudness_layout = (IAMF_Layout *)calloc((size_t)mix->n_layouts, sizeof(IAMF_Layout));
