@@ -217,6 +217,11 @@ extern "C" int iamfb_ctx_create(int device, iamfb_ctx **out) {
   return IAMFB_OK;
 }
 
+extern "C" int iamfb_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" int iamfb_ctx_set_stream(iamfb_ctx *c, void *stream) {
   if (!c) return fail(IAMFB_ERR_BAD_ARG, "null ctx");
   if (c->own_stream) cudaStreamDestroy(c->stream);

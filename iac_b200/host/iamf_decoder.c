@@ -206,6 +206,49 @@ static void engine_release(IAMF_DecoderHandle h) {
   h->group_units = 0; h->group_s16 = 0;
 }
 
+/* ---- the GPUs of this process (streams shard over the GPUs of a box, no exchange between them).
+ * IAMF_B200_DEVICES = "all" | a count | a comma-separated list of device ordinals; without it the one device
+ * IAMF_B200_DEVICE names (default 0).  Handles are dealt round the list as they are configured; a batch call splits its
+ * handles over the list - handle i to entry i mod D - and runs one host thread per device (batch_units below). */
+#define IH_MAX_DEVICES 16
+static int g_devs[IH_MAX_DEVICES], g_ndev = 0;
+static unsigned g_next_dev = 0;
+static pthread_once_t g_devs_once = PTHREAD_ONCE_INIT;
+static void devices_parse(void) {
+  const char *list = getenv("IAMF_B200_DEVICES");
+  const char *one = getenv("IAMF_B200_DEVICE");
+  g_ndev = 0;
+  if (list && *list) {
+    if (!strcmp(list, "all") || !strchr(list, ',')) {
+      int have = iamfb_device_count(), want = strcmp(list, "all") ? atoi(list) : have;
+      if (want > have && have > 0) want = have;
+      for (int i = 0; i < want && i < IH_MAX_DEVICES; ++i) g_devs[g_ndev++] = i;
+    } else {
+      for (const char *p = list; *p && g_ndev < IH_MAX_DEVICES;) {
+        g_devs[g_ndev++] = atoi(p);
+        p = strchr(p, ',');
+        if (!p) break;
+        ++p;
+      }
+    }
+  }
+  if (g_ndev <= 0) { g_devs[0] = one ? atoi(one) : 0; g_ndev = 1; }
+}
+static void devices_init(void) { pthread_once(&g_devs_once, devices_parse); }
+
+/* (re)binds a configured handle to `device`: its (context, plan) entry of that device */
+static int engine_bind(IAMF_DecoderHandle h, int device) {
+  if (h->shared && ((ih_shared *)h->shared)->device == device) return IAMF_OK;
+  engine_release(h);
+  ih_shared *sh = shared_acquire(device, &h->desc);
+  if (!sh) return IAMF_ERR_INTERNAL;
+  h->shared = sh;
+  h->ctx = sh->ctx;
+  h->plan = sh->plan;
+  h->pcm_stage_size = iamfb_plan_out_stride_bytes(h->plan, 1);
+  return IAMF_OK;
+}
+
 static void pkt_drop(ih_stream *st, int k);
 
 static void db_reset(IAMF_DecoderHandle h) {
@@ -506,17 +549,13 @@ static int engine_build(IAMF_DecoderHandle h) {
   }
   h->frame_size = d->frame_size;
 
+  /* handles are dealt round the process's devices in the order they are configured */
   engine_release(h);
-  int dev = 0;
-  const char *env = getenv("IAMF_B200_DEVICE");
-  if (env) dev = atoi(env);
-  ih_shared *sh = shared_acquire(dev, d);
-  if (!sh) return IAMF_ERR_INTERNAL;
-  h->shared = sh;
-  h->ctx = sh->ctx;
-  h->plan = sh->plan;
-  h->pcm_stage_size = iamfb_plan_out_stride_bytes(h->plan, 1);
-  return IAMF_OK;
+  devices_init();
+  pthread_mutex_lock(&g_shared_mu);
+  const int dev = g_devs[g_next_dev++ % g_ndev];
+  pthread_mutex_unlock(&g_shared_mu);
+  return engine_bind(h, dev);
 }
 
 /* the handle's own single-stream batch and pinned frame buffers: created by its first IAMF_decoder_decode (handles that
@@ -1365,12 +1404,17 @@ static void group_drain(void *user, int s_lo, int s_cnt) {
   pool_for(s_cnt, out_handle, &job);
 }
 
-int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
-                                    void *const *pcm, int *ret, int max_units, int *units_done) {
+/* one step of the handles that share ONE device (device < 0: wherever the first handle was configured) */
+static int batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
+                       void *const *pcm, int *ret, int max_units, int *units_done, int device) {
   if (!hs || n <= 0 || !data || !size || !ret || !hs[0] || max_units < 1 || max_units > 64) return IAMF_ERR_BAD_ARG;
   IAMF_DecoderHandle L = hs[0];
   if (L->group_size != n || L->leader || L->group_units != max_units) {
     if (L->group_size > 1 || L->leader) return IAMF_ERR_INVALID_STATE; /* group membership and step size are fixed */
+    if (device >= 0 && L->status == IH_STATUS_RECEIVE && L->plan && !L->duration) {
+      int brc = engine_bind(L, device);   /* the group lives where its leader's plan lives */
+      if (brc != IAMF_OK) return brc;
+    }
     int rc = group_build(hs, n, max_units);
     if (rc != IAMF_OK) return rc;
   }
@@ -1415,6 +1459,72 @@ int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t
     pool_for(n, out_handle, &oj);
   }
   return IAMF_OK;
+}
+
+/* ---- the public call: the handles split over the process's devices (handle i -> device i mod D), one host thread per
+ * device stepping its share (its own context, group batch and pinned buffers); no exchange between the devices ---- */
+typedef struct {
+  IAMF_DecoderHandle *hs;
+  const uint8_t **data;
+  int32_t *size;
+  uint32_t *rsize;
+  void **pcm;
+  int *ret, *units_done;
+  int n, max_units, device, rc;
+} ih_dev_job;
+static void *dev_thread(void *v) {
+  ih_dev_job *j = (ih_dev_job *)v;
+  j->rc = batch_units(j->hs, j->n, (const uint8_t *const *)j->data, j->size, j->rsize, (void *const *)j->pcm, j->ret, j->max_units,
+                      j->units_done, j->device);
+  return 0;
+}
+
+int IAMF_decoder_decode_batch_units(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,
+                                    void *const *pcm, int *ret, int max_units, int *units_done) {
+  if (!hs || n <= 0 || !data || !size || !ret || !hs[0] || max_units < 1 || max_units > 64) return IAMF_ERR_BAD_ARG;
+  devices_init();
+  int D = g_ndev < n ? g_ndev : n;
+  if (D <= 1) return batch_units(hs, n, data, size, rsize, pcm, ret, max_units, units_done, g_ndev > 1 || getenv("IAMF_B200_DEVICES") ? g_devs[0] : -1);
+  /* device-major copies of the per-handle arrays (the handles' own buffers are not copied) */
+  const size_t per = sizeof(IAMF_DecoderHandle) + sizeof(uint8_t *) + sizeof(int32_t) + sizeof(uint32_t) + sizeof(void *) + 2 * sizeof(int);
+  uint8_t *mem = (uint8_t *)calloc((size_t)n, per);
+  if (!mem) return IAMF_ERR_ALLOC_FAIL;
+  IAMF_DecoderHandle *hs2 = (IAMF_DecoderHandle *)mem;
+  const uint8_t **data2 = (const uint8_t **)(hs2 + n);
+  void **pcm2 = (void **)(data2 + n);
+  int32_t *size2 = (int32_t *)(pcm2 + n);
+  uint32_t *rsize2 = (uint32_t *)(size2 + n);
+  int *ret2 = (int *)(rsize2 + n), *units2 = ret2 + n;
+  ih_dev_job job[IH_MAX_DEVICES];
+  pthread_t th[IH_MAX_DEVICES];
+  int at = 0;
+  for (int d = 0; d < D; ++d) {
+    ih_dev_job *j = &job[d];
+    j->hs = hs2 + at; j->data = data2 + at; j->size = size2 + at; j->rsize = rsize2 + at; j->pcm = pcm2 + at; j->ret = ret2 + at;
+    j->units_done = units2 + at; j->max_units = max_units; j->device = g_devs[d]; j->rc = IAMF_OK; j->n = 0;
+    for (int i = d; i < n; i += D, ++at, ++j->n) {
+      hs2[at] = hs[i]; data2[at] = data[i]; size2[at] = size[i]; pcm2[at] = pcm ? pcm[i] : 0;
+    }
+    if (!pcm) j->pcm = 0;
+  }
+  int started[IH_MAX_DEVICES] = {0};
+  for (int d = 1; d < D; ++d) started[d] = pthread_create(&th[d], 0, dev_thread, &job[d]) == 0;
+  dev_thread(&job[0]);
+  int rc = job[0].rc;
+  for (int d = 1; d < D; ++d) {
+    if (started[d]) pthread_join(th[d], 0);
+    else dev_thread(&job[d]);
+    if (rc == IAMF_OK) rc = job[d].rc;
+  }
+  at = 0;
+  for (int d = 0; d < D; ++d)
+    for (int i = d; i < n; i += D, ++at) {
+      ret[i] = ret2[at];
+      if (rsize) rsize[i] = rsize2[at];
+      if (units_done) units_done[i] = units2[at];
+    }
+  free(mem);
+  return rc;
 }
 
 int IAMF_decoder_decode_batch(IAMF_DecoderHandle *hs, int n, const uint8_t *const *data, const int32_t *size, uint32_t *rsize,

@@ -211,6 +211,7 @@ typedef struct iamfb_io {
 } iamfb_io;
 
 /* ---- context: one per GPU / host thread ---- */
+int iamfb_device_count(void);   /* CUDA devices visible to the process (0 when there is none or no driver) */
 int iamfb_ctx_create(int device, iamfb_ctx **ctx);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the framework's current stream */
 int iamfb_ctx_set_stream(iamfb_ctx *ctx, void *cuda_stream);

@@ -14,6 +14,7 @@ import importlib.util
 import os
 import shutil
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -478,3 +479,63 @@ def test_binauraliser_renders_a_scalable_stream_through_the_public_api(monkeypat
         pcm, counts = api.render(desc, units, **api_kw)
         assert counts == ref[s][0]
         assert pcm.tobytes() == ref[s][1].tobytes(), f"stream {s}"
+
+
+def _batch_units_run(n, F, K, env):
+    """n handles of configuration 2 through IAMF_decoder_decode_batch_units in a child process with `env` set; returns the
+    concatenated PCM of every handle"""
+    import json
+    code = f"""
+import ctypes as C, os, sys, json, base64
+sys.path.insert(0, {os.path.join(ROOT, 'tests')!r}); sys.path.insert(0, {ROOT!r})
+import numpy as np, scenarios as S, refstreams, iamfapi
+sc, st, api_kw, unit_kw = refstreams.case("c2")
+n, F, K = {n}, {F}, {K}
+inputs = S.synth_inputs(sc, n, F, seed=41); P, _, _ = S.synth_params(sc, n, F, seed=42); refstreams.no_param_gaps(sc, P)
+desc = st.descriptors()
+units = [refstreams.temporal_units(sc, st, inputs, P, unit_kw, s) for s in range(n)]
+api = iamfapi.Api({LIBIAMF!r}); L = api.L; vp = C.c_void_p
+L.IAMF_decoder_open.restype = vp
+L.IAMF_decoder_decode_batch_units.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+hs = (vp * n)()
+for s in range(n):
+    h = L.IAMF_decoder_open(); L.IAMF_decoder_peak_limiter_set_threshold(vp(h), C.c_float(-1.0)); L.IAMF_decoder_set_bit_depth(vp(h), 16)
+    L.IAMF_decoder_output_layout_set_sound_system(vp(h), 1)
+    blob = desc + units[s][0]; r = C.c_uint32(0)
+    assert L.IAMF_decoder_configure(vp(h), blob, len(blob), C.byref(r)) == 0 and r.value == len(desc)
+    hs[s] = h
+bufs = [C.create_string_buffer(K * 960 * 6 * 2) for _ in range(n)]
+pcm = (vp * n)(*[C.addressof(b) for b in bufs])
+out = [b"" for _ in range(n)]
+for f0 in list(range(0, F, K)) + [None]:
+    blobs = [None if f0 is None else b"".join(units[s][f0:f0 + K]) for s in range(n)]
+    data = (C.c_char_p * n)(*blobs); size = (C.c_int32 * n)(*[0 if b is None else len(b) for b in blobs])
+    rs = (C.c_uint32 * n)(); ret = (C.c_int * n)(); ud = (C.c_int * n)()
+    rc = L.IAMF_decoder_decode_batch_units(hs, n, data, size, rs, pcm, ret, K, ud)
+    assert rc == 0, rc
+    for s in range(n):
+        if ret[s] > 0: out[s] += bufs[s].raw[: ret[s] * 12]
+print("RESULT " + json.dumps([base64.b64encode(o).decode() for o in out]))
+"""
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=e)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import base64
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    return [base64.b64decode(x) for x in json.loads(line[7:])]
+
+
+@pytest.mark.gpu
+def test_batch_call_split_over_a_device_list_matches_one_device():
+    """IAMF_B200_DEVICES: the handles of a batch call are dealt round the device list (handle i -> entry i mod D), one host
+    thread, context and group batch per entry; same bytes as on one device.  With a single GPU the list names it twice -
+    the split, the threads and the scatter of the results are exercised all the same; with two or more GPUs visible the
+    list is the first two devices."""
+    import torch
+    one = _batch_units_run(11, 9, 4, {"IAMF_B200_DEVICES": "0"})
+    lst = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    two = _batch_units_run(11, 9, 4, {"IAMF_B200_DEVICES": lst})
+    three = _batch_units_run(11, 9, 4, {"IAMF_B200_DEVICES": lst + ",0"})
+    assert all(len(x) > 1000 for x in one)
+    assert one == two and one == three
