@@ -1202,8 +1202,23 @@ const PipeSigInfo *iamfb_pipe_find(int l0, int n0, int l1, int n1, int target, b
 #define G(n) int iamfb_pipe_launch_g##n(iamfb_ctx *, int, bool, const KernelPlan &, const PipeArgs &, int, size_t, const CUtensorMap &, const CUtensorMap &);
 G(0) G(1) G(2) G(3) G(4) G(5) G(6) G(7)
 #undef G
+#define G(n) int iamfb_pipe_launch_r##n(iamfb_ctx *, int, bool, const KernelPlan &, const PipeArgs &, int, size_t, const CUtensorMap &, const CUtensorMap &);
+G(0) G(1) G(2) G(3) G(4) G(5) G(6) G(7)
+#undef G
 int iamfb_pipe_launch(iamfb_ctx *ctx, int sig_id, bool s16, const KernelPlan &kp, const PipeArgs &pa, int S, size_t smem, const CUtensorMap &m0,
                       const CUtensorMap &m1) {
+  if (pa.gain_ramp[0] || pa.gain_ramp[kMaxEl - 1] || pa.out_gain_ramp) {   // animated mix gains: the k_pipe<SIG, true> instantiations
+    if (sig_id >= kPipeFmaFirstId) return iamfb_pipe_launch_r7(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    switch (IAMFB_PIPE_GROUP_OF(sig_id)) {
+      case 0: return iamfb_pipe_launch_r0(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+      case 1: return iamfb_pipe_launch_r1(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+      case 2: return iamfb_pipe_launch_r2(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+      case 3: return iamfb_pipe_launch_r3(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+      case 4: return iamfb_pipe_launch_r4(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+      case 5: return iamfb_pipe_launch_r5(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+      default: return iamfb_pipe_launch_r6(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
+    }
+  }
   if (sig_id >= kPipeFmaFirstId) return iamfb_pipe_launch_g7(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);   // IAMFB_ARITH_FMA variants
   switch (IAMFB_PIPE_GROUP_OF(sig_id)) {
     case 0: return iamfb_pipe_launch_g0(ctx, sig_id, s16, kp, pa, S, smem, m0, m1);
