@@ -573,7 +573,10 @@ def run_gpu(args):
     if args.quick:
         sampler.stop_flag = True
         if rank == 0:
-            print(json.dumps({"metric": "rendered audio-sec/sec", "value": value, "ms_per_step": ms_max / args.steps,
+            extra = {}
+            if os.environ.get("IAMFB_BENCH_KERNELS"):      # per-kernel CUDA-event times of the quick run (development aid)
+                extra["kernels"] = {k: round(v["ms_per_submit"], 5) for k, v in w.kernel_timing(40).items()}
+            print(json.dumps({**extra, "metric": "rendered audio-sec/sec", "value": value, "ms_per_step": ms_max / args.steps,
                               "ms_per_submit": ms_per_submit, "submits_per_step": R,
                               "gpu_launches": int(launches), "quick": True, "peak_ref": args.peak_ref,
                               "streams_above_limiter_threshold": w.active_frac, "kernel_path": w.eng.kernel_path_s16 if w.in_format == "s16" else w.eng.kernel_path}))

@@ -32,6 +32,7 @@ constexpr int kMaxChunks = 32;
 
 struct iamfb_ctx {
   int device;
+  int n_sm;                // multiprocessors of the device
   cudaStream_t stream;
   bool own_stream;
   uint64_t launches;
@@ -105,6 +106,13 @@ int iamfb_pipe_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelP
                       const CUtensorMap &m0, const CUtensorMap &m1);
 namespace iamfb { struct PipeRsArgs; }
 int iamfb_pipe_rs_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelPlan &kp, const iamfb::PipeRsArgs &pa, int S);
+// split form of the resampling pipelines: k_resample_ls (one stream per lane) + k_pipe_rs<PRE> (the limiter half), the
+// second optionally launched beside the first (programmatic dependent launch, chunks handed over through flags)
+int iamfb_pipe_rs_lim_launch(iamfb_ctx *ctx, int sig_id, const iamfb::KernelPlan &kp, const iamfb::PipeRsArgs &pa, int S, bool beside);
+namespace iamfb { struct ResampleLsArgs; struct PreRenderArgs; }
+int iamfb_pipe_prerender_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelPlan &kp, const iamfb::PreRenderArgs &pa, int S, int F);
+int iamfb_resample_ls_blocks_resident(int smem_bytes);
+int iamfb_resample_ls_launch(iamfb_ctx *ctx, const iamfb::KernelPlan &kp, const iamfb::ResampleLsArgs &a, int blocks, int smem_bytes);
 
 // ---- binaural HRTF front end (iamfb_hrtf.cu)
 struct iamfb_hrtf_front;

@@ -37,9 +37,67 @@ struct PipeRsArgs {
   int ring, mirror;             // ring entries (multiple of 4), entries repeated behind the end (>= filt_len, multiple of 4)
   int off_pkr, off_ring, off_tab, off_stage;   // byte offsets of the shared-memory areas behind the time line
   int smem_bytes;
+  // PRE variant (the resampler ran in front, k_resample_ls): the resampled, clamped, loudness-scaled time line
+  const float *tl_pre;          // [S][co][tl_pre_stride], output u of this submit at tl_pre_off + u
+  int tl_pre_stride, tl_pre_off;
+  const int *ready;             // non-null: k_resample_ls is still running beside this kernel - ready[(s / 32) * ready_stride + c]
+  int ready_stride, ready_chunk, ready_seq;   // == ready_seq once outputs [c * ready_chunk, (c + 1) * ready_chunk) of the 32 streams are in memory
+};
+
+// k_pipe_prerender: the render stage of k_pipe_rs on its own (split form) - the regular streams' decoded frames (float32 or
+// int16, straight from memory) through reconstruction, the compile-time matrix and the element / output mix gains onto the
+// pre-resample time line tl_a[S][co][cap] at hist + f * N, one thread per 4 instants.  Same expressions as render_in below.
+struct PreRenderArgs {
+  PipeArgs p;
+  float *tl;
+  int cap, hist;
 };
 
 template <class SIG>
+__global__ void __launch_bounds__(128) k_pipe_prerender(const __grid_constant__ KernelPlan plan, PreRenderArgs b) {
+  typedef typename SIG::E0 E0;
+  constexpr int VEC = 4, CO = SIG::CO, NY = SIG::NY;
+  typedef Vec<VEC> V;
+  const PipeArgs &a = b.p;
+  const int N = plan.frame_size;
+  const int f = blockIdx.y, s = blockIdx.z;
+  const int i0 = (blockIdx.x * 128 + threadIdx.x) * VEC;
+  if (a.submit[s].irregular) return;          // rendered by the multi-kernel path (block-uniform)
+  const bool live = i0 < N;
+  const int i0r = live ? i0 : 0;
+  const ElPlan &ep0 = plan.el[0];
+  const int nin = ep0.n_in;
+  const FrameRec &fr = a.frames[(size_t)s * a.n_frames + f];
+  const char *rows = reinterpret_cast<const char *>(a.in[0]) + (((size_t)s * a.n_frames + f) * nin) * (size_t)N * SIG::kEsz + (size_t)i0r * SIG::kEsz;
+  const bool fade_w = __any_sync(0xffffffffu, i0r < plan.overlap);
+  V y[NY];
+#pragma unroll
+  for (int r = 0; r < NY; ++r) y[r] = vzero<VEC>();
+  pipe_render_element<SIG, E0, VEC, NY>(plan, ep0, fr.el[0], rows, N * SIG::kEsz, i0r, fade_w, a.start_win, a.stop_win, y, a.neg_zero);
+  const float eg = fr.el[0].gain, og = fr.out_gain;
+  if (eg != 1.f && eg > 0.f) pipe_scale<SIG, E0, 0, VEC, NY>(y, eg);
+  if (og != 1.f && og > 0.f) {
+#pragma unroll
+    for (int r = 0; r < NY; ++r)
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) y[r].v[q] *= og;
+  }
+  if (!live) return;
+#pragma unroll 1
+  for (int c = 0; c < CO; ++c) {
+    const int r = pipe_yrow_rt<SIG>(c);
+    if (r < 0) continue;
+    V v = y[0];
+#pragma unroll
+    for (int rr = 1; rr < NY; ++rr)
+      if (rr == r) v = y[rr];
+    float *dst = b.tl + ((size_t)s * CO + c) * b.cap + b.hist + (size_t)f * N + i0;
+    __stcg(reinterpret_cast<float4 *>(dst), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+  }
+}
+
+// PRE = true: the limiter half only - the resampler's outputs come from memory (tl_pre) instead of the ring + FIR
+template <class SIG, bool PRE = false>
 __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(const __grid_constant__ KernelPlan plan, PipeRsArgs b) {
   typedef typename SIG::E0 E0;
   constexpr int VEC = SIG::VEC, NW = SIG::NW, CO = SIG::CO, NY = SIG::NY, WN = SIG::kWorkers, NS = SIG::kStages;
@@ -81,10 +139,10 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
   if (tid == 0) {
     mbar_init(&s_hbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    uint32_t bytes = (uint32_t)(os * b.tab_row * sizeof(float4));
+    uint32_t bytes = PRE ? 0u : (uint32_t)(os * b.tab_row * sizeof(float4));
     if (limiter) bytes += (uint32_t)((NY + 1) * kLimDelay * sizeof(float));
     mbar_expect_tx(&s_hbar, bytes);
-    bulk_g2s(const_cast<float4 *>(TAB), b.tab4, (uint32_t)(os * b.tab_row * sizeof(float4)), &s_hbar);
+    if (!PRE) bulk_g2s(const_cast<float4 *>(TAB), b.tab4, (uint32_t)(os * b.tab_row * sizeof(float4)), &s_hbar);
     if (limiter) {
 #pragma unroll 1
       for (int c = 0; c < CO; ++c) {
@@ -96,6 +154,7 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
   }
   for (int i = tid; i < kStreamAccCache; i += SIG::kThreads) s_acc[i] = (limiter && i <= plan.lim_jr + 3) ? a.acc[i] : 0.f;
   // ring and stages start from zeros (whatever the filter's zero taps meet must be finite)
+  if constexpr (!PRE) {
   for (int i = tid; i < NP * RGM; i += SIG::kThreads)
     if (i % RGM >= RH && !(i % RGM >= RG && i % RGM - RG < RH)) RING[i] = make_float2(0.f, 0.f);
   for (int i = tid; i < NS * a.stage_bytes / 4; i += SIG::kThreads) reinterpret_cast<float *>(ST)[i] = 0.f;
@@ -116,7 +175,8 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
     RING[p * RGM + k] = v;
     if (k < b.mirror) RING[p * RGM + RG + k] = v;
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  if constexpr (!PRE) asm volatile("griddepcontrol.wait;" ::: "memory");   // (PRE: launched behind finished kernels, or beside the resampler)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
   mbar_wait(&s_hbar, 0u);
@@ -322,6 +382,67 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
     if (limiter && has) stsv<VEC>(PKR + (tau & 1) * TL + q0, peak);
   };
 
+  // PRE: output tile tau of the resampled time line -> yh (loaded one tile ahead into yn: the load's latency hides behind
+  // the previous tile's limiter work), peaks as above
+  V yn[NY];
+#pragma unroll
+  for (int r = 0; r < NY; ++r) yn[r] = vzero<VEC>();
+  auto pre_wait = [&](int tau) {          // (all lanes of a worker warp) until the resampler's chunks under tile tau are in memory
+    if (b.ready == nullptr) return;
+    const int u_lo = tau * TL, u_hi = min(L, u_lo + TL) - 1;
+    if (u_hi < u_lo) return;
+    const int c_lo = u_lo / b.ready_chunk, c_hi = u_hi / b.ready_chunk;
+    const int *flag = b.ready + (size_t)(s >> 5) * b.ready_stride;
+    for (int c = c_lo + lane; c <= c_hi; c += 32) {      // (at most a few chunks per tile)
+      int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag + c) : "memory");
+        if (v != b.ready_seq) __nanosleep(64);
+      } while (v != b.ready_seq);
+    }
+    __syncwarp();
+  };
+  auto pre_load = [&](int tau) {
+    const int u0 = tau * TL + q0r;
+#pragma unroll 1
+    for (int c = 0; c < CO; ++c) {
+      const int r = pipe_yrow_rt<SIG>(c);
+      if (r < 0) continue;
+      const float *src = b.tl_pre + ((size_t)s * CO + c) * b.tl_pre_stride + b.tl_pre_off + u0;
+      V v;
+      bool done = false;
+      if constexpr (VEC == 4) {
+        if (((b.tl_pre_stride | b.tl_pre_off) & 3) == 0) {
+          const float4 f = __ldcg(reinterpret_cast<const float4 *>(src));
+          v.v[0] = f.x; v.v[1] = f.y; v.v[2] = f.z; v.v[3] = f.w;
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v.v[k] = __ldcg(src + k);
+      }
+#pragma unroll
+      for (int rr = 0; rr < NY; ++rr)
+        if (rr == r) yn[rr] = v;
+    }
+  };
+  auto pre_take = [&](int tau) {
+    const int u0 = tau * TL + q0r;
+    V peak = vzero<VEC>();
+#pragma unroll
+    for (int r = 0; r < NY; ++r)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float v = (u0 + k < L) ? yn[r].v[k] : 0.f;        // beyond the submit's last output (ragged tile)
+        yh[r].v[k] = v;
+        peak.v[k] = fmaxf(peak.v[k], fabsf(v));
+      }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) pkh.v[k] = has ? peak.v[k] : 0.f;
+    if (limiter && has) stsv<VEC>(PKR + (tau & 1) * TL + q0, peak);
+  };
+
   float pre[VEC], suf[VEC];
   auto wmax_scan = [&]() {
     float inc[VEC];
@@ -417,13 +538,31 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
   __syncthreads();
 
   if (worker) {
+    if constexpr (!PRE) {
 #pragma unroll
-    for (int q = 0; q < NS; ++q)
-      if (q < K) issue_in(q);
+      for (int q = 0; q < NS; ++q)
+        if (q < K) issue_in(q);
+    } else if (T > 0) {
+      pre_wait(0);
+      pre_load(0);
+    }
     int filled = 0;                  // input tiles rendered into the ring so far
 #pragma unroll 1
     for (int t = -1; t <= T; ++t) {
       if (t >= 0) output_and_store(t - 1, t >= 1, t < T);
+      if constexpr (PRE) {
+        if (t + 1 < T) {
+          const int tau = t + 1;
+          pre_take(tau);
+          if (tau + 1 < T) {
+            pre_wait(tau + 1);
+            pre_load(tau + 1);
+          }
+          if (limiter) wmax_scan();
+          asm volatile("bar.sync 1, %0;" ::"n"(WN) : "memory");
+          if (limiter) wmax_combine(tau);
+        }
+      } else
       if (t + 1 < T) {
         const int tau = t + 1;
         // the tile's (first tap, phase) and the input its last output reaches
@@ -463,7 +602,7 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
       asm volatile("bar.sync 2, %0;" ::"n"(SIG::kThreads) : "memory");
     }
     // input tiles no output of this submit reached yet (their samples are the next submit's history)
-    while (filled < K) {
+    while (!PRE && filled < K) {
       mbar_wait(&s_bar[filled % NS], (uint32_t)(filled / NS) & 1u);
       render_in(filled);
       asm volatile("bar.sync 1, %0;" ::"n"(WN) : "memory");
@@ -519,6 +658,7 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
     }
   }
   // the last RH pre-resample samples (ring entries of the input instants [in_len - RH, in_len))
+  if constexpr (!PRE)
   for (int i = tid; i < NP * RH; i += SIG::kThreads) {
     const int p = i / RH, k = i - p * RH;
     const float2 v = RING[p * RGM + (in_len + k) % RG];      // instant in_len - RH + k sits at entry (in_len - RH + k + RH) mod RG

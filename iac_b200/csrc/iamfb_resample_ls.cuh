@@ -1,0 +1,259 @@
+// iamfb_resample_ls.cuh - k_resample_ls: the interpolating resampler (resampler_basic_interpolate_single, resample.c:357-418)
+// with the LANES OF A WARP ON 32 DIFFERENT STREAMS.
+//
+// Why: in a block-per-stream FIR every lane owns outputs of its own phase, so every lane needs its own four-tap item per
+// step - 16 bytes of shared-memory traffic per 8 multiply-adds, which is what bounds k_pipe_rs (shared-memory pipe 75 %
+// busy, FP32 pipe 58 %).  Streams that run in step have the SAME phase at the same output index: with one
+// stream per lane the tap items are warp-uniform (one broadcast read per warp instead of 32 distinct ones) and only the
+// inputs are per lane - the loop is left with the FP32 pipe as its bound.
+//
+// Work item = (group of 32 streams, chunk of `chunk` consecutive outputs).  A warp stages, for each of its streams, the
+// inputs the chunk spans (channel pairs interleaved, row stride odd: lanes hit different banks) from the pre-resample time
+// line tl_a[S][co][cap_a] (k_render's output; the previous submit's last rs_hist inputs in front), then walks the chunk in
+// groups of 4 consecutive outputs exactly like k_pipe_rs: one pass over the inputs of the four outputs, the rows of the
+// tap table carrying zero items outside each output's window (adding +-0 to a sum that started at +0 is exact), four
+// accumulators per channel over j ascending, packed exact multiply-add for the two channels of a pair, cubic blend with the
+// per-phase weights tabulated at plan time, clamp to +-1 (resample.c:84), loudness.  Bit for bit the reference's sums.
+//
+// Lanes whose streams are at another phase (a stream that joined the batch later, lost a frame, ...) are served in further
+// passes of the same warp (grouped by the phase of the chunk's first output); irregular streams of the submit (trims,
+// missing frames) are skipped - the multi-kernel path renders them.  The kernel is persistent: the grid strides over the
+// work items in an order that lets k_pipe_rs<PRE> (the limiter half, launched BESIDE this kernel by a programmatic
+// dependent launch) consume the chunks while later ones are produced; ready[group][chunk] = seq is the hand-over.
+#pragma once
+#include "iamfb_pipe.cuh"
+
+namespace iamfb {
+
+struct ResampleLsArgs {
+  const float *src;             // tl_a [S][co][cap_a]; this submit's first input instant at index rs_hist
+  float *dst;                   // tl_b [S][co][cap_b]; output u of this submit at hist_b + u
+  const SubmitRec *submit;      // [S] (irregular streams are skipped)
+  const StreamState *state;     // [S]
+  const float4 *tab4;           // [oversample][tab_row] tap items, tab_pad zero items on either side of a row
+  const float4 *interp4;        // [den] cubic weights per phase
+  int tab_row, tab_pad;
+  int cap_a, cap_b, hist_b;
+  int n_streams, co;
+  int chunk;                    // outputs per work item (multiple of 4)
+  int n_chunks;                 // chunks that cover the longest stream of the submit
+  int span;                     // inputs staged per stream and chunk (row stride in float2, odd)
+  int set_groups;               // stream groups per set: the work items are ordered set by set, chunk by chunk inside a set
+  int *ready;                   // [groups][n_chunks] or null
+  int seq;
+  float neg_zero;
+};
+
+constexpr int kLsWarps = 8;     // warps per block, one staging area each: two per scheduler - one stages while the other computes
+
+__device__ __forceinline__ void ls_cp4(void *dst_smem, const void *src, bool valid) {   // 4-byte asynchronous copy, zeros when !valid
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_constant__ KernelPlan plan, ResampleLsArgs a) {
+  extern __shared__ __align__(16) float ls_smem[];
+  const int Nf = (int)plan.rs_filt_len, os = (int)plan.rs_oversample, den = (int)plan.rs_den;
+  const int fa = plan.rs_frac_adv, ia = plan.rs_int_adv;
+  const int trow = a.tab_row, pad = a.tab_pad;
+  float4 *TAB = reinterpret_cast<float4 *>(ls_smem);                             // [os][trow]
+  const int tab_items = os * trow;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  float4 *CI = TAB + tab_items;                                                    // [den] cubic weights per phase
+  float2 *X = reinterpret_cast<float2 *>(CI + den + (den + 3) / 4) + (size_t)wi * 32 * a.span;    // [32 streams][span] channel pairs
+  for (int i = threadIdx.x; i < tab_items; i += NWARPS * 32) TAB[i] = a.tab4[i];
+  for (int i = threadIdx.x; i < den; i += NWARPS * 32) CI[i] = a.interp4[i];
+  int *OFFROW = reinterpret_cast<int *>(CI + den);                                 // [den] first item of the phase's tap row
+  for (int i = threadIdx.x; i < den; i += NWARPS * 32) OFFROW[i] = (i * os / den) * trow + pad;
+  // the limiter half may start now: every block of this grid is resident from here on (grid <= what fits the device)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();
+
+  const int groups = (a.n_streams + 31) / 32;
+  const int n_sets = (groups + a.set_groups - 1) / a.set_groups;
+  const int steps = Nf + 3 * (ia + 1);
+  const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
+  const int co = a.co;
+  const long long total = (long long)groups * a.n_chunks;
+  const int warps = gridDim.x * NWARPS;
+  // the two warps of a scheduler take turns: the second starts half a work item late, so that one stages (and runs the
+  // per-chunk prologue) while the other keeps the FP32 pipe busy - all items last the same, the offset persists
+  if (((wi >> 2) ^ wi) & 1) {      // (differs inside a pair whether schedulers take warps w, w + 4 or w, w + 1)
+    const long long t0 = clock64(), d = (long long)(a.chunk / 4) * steps * 64;
+    while (clock64() - t0 < d) __nanosleep(200);
+  }
+
+  for (long long item = (long long)blockIdx.x + (long long)wi * gridDim.x; item < total; item += warps) {
+    // item -> (set, chunk, group inside the set): sets in order, chunks in order inside a set, groups fastest
+    int g, c;
+    {
+      const long long per_set = (long long)a.set_groups * a.n_chunks;
+      const int set = (int)(item / per_set);
+      const int gs = min(a.set_groups, groups - set * a.set_groups);       // groups of this set (the last may be smaller)
+      const long long r = item - (long long)set * per_set;
+      // (sets in front of the last are full; inside the last set the items past gs * n_chunks do not exist)
+      if (r >= (long long)gs * a.n_chunks) continue;
+      c = (int)(r / gs);
+      g = set * a.set_groups + (int)(r - (long long)c * gs);
+      (void)n_sets;
+    }
+    const int s = g * 32 + lane;
+    const int u0 = c * a.chunk;
+    // this lane's stream: length, position and phase of the chunk's first output
+    int L = 0, pos0 = 0, phi0 = -1;
+    if (s < a.n_streams) {
+      const SubmitRec sr = a.submit[s];
+      if (!sr.irregular && u0 < sr.lim_len) {
+        L = sr.lim_len;
+        const long long in_start = a.state[s].rs_in_total - sr.in_len;
+        const long long n = sr.rs_out_first + u0;
+        // q(n) = Nf/2 + floor(n * num / den) is the LAST input of output n; index into the tl_a row
+        pos0 = (int)((long long)(Nf / 2) + (n * (long long)plan.rs_num) / den - (Nf - 1) - in_start + plan.rs_hist);
+        phi0 = (int)((n * (long long)fa) % den);
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, phi0 >= 0);
+    if (todo == 0u) {
+      if (a.ready && lane == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ready + (size_t)g * a.n_chunks + c), "r"(a.seq) : "memory");
+      }
+      continue;
+    }
+    for (int c0 = 0; c0 < co; c0 += 2) {
+      const bool two = c0 + 1 < co;
+      // ---- stage the inputs of the chunk: row st of X = stream 32 g + st, entries [pos0(st), pos0(st) + span)
+      __syncwarp();
+      // (asynchronous 4-byte copies, all of them in flight at once: the rows of 32 streams are 32 different places in memory)
+      {
+        // element index of the lane's own first staged input, < 0 for a lane without work; in_rng: the whole row exists
+        const long long my_off = phi0 >= 0 ? ((long long)s * co + c0) * a.cap_a + pos0 : -1;
+        const bool fast = __all_sync(0xffffffffu, phi0 < 0 || (pos0 >= 0 && pos0 + a.span <= a.cap_a));
+        const uint32_t xb = (uint32_t)__cvta_generic_to_shared(X) + (uint32_t)lane * 8u;
+        if (fast) {
+#pragma unroll 4
+          for (int st = 0; st < 32; ++st) {
+            const long long o = __shfl_sync(0xffffffffu, my_off, st);
+            const bool on = o >= 0;                                                   // (warp-uniform)
+            const float *r0 = a.src + (on ? o : 0) + lane;
+            const float *r1 = two ? r0 + a.cap_a : r0;
+            uint32_t d = xb + (uint32_t)(st * a.span) * 8u;
+            for (int k = lane; k < a.span; k += 32) {
+              const int n0 = on ? 4 : 0, n1 = (on && two) ? 4 : 0;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(r0), "r"(n0) : "memory");
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4u), "l"(r1), "r"(n1) : "memory");
+              r0 += 32; r1 += 32; d += 256u;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int st = 0; st < 32; ++st) {
+            const int p0 = __shfl_sync(0xffffffffu, pos0, st);
+            const int ph = __shfl_sync(0xffffffffu, phi0, st);
+            if (ph < 0) continue;                                                      // (warp-uniform)
+            const float *r0 = a.src + ((size_t)(g * 32 + st) * co + c0) * a.cap_a;
+            const float *r1 = two ? r0 + a.cap_a : r0;
+            for (int k = lane; k < a.span; k += 32) {
+              const int idx = p0 + k;
+              const bool in = idx >= 0 && idx < a.cap_a;
+              const int ic = in ? idx : 0;
+              float2 *d = X + st * a.span + k;
+              ls_cp4(&d->x, r0 + ic, in);
+              ls_cp4(&d->y, r1 + ic, in && two);
+            }
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      // ---- passes over the phases present in the warp (one when the streams run in step)
+      unsigned left = todo;
+      while (left) {
+        const int leader = __ffs(left) - 1;
+        const int phl = __shfl_sync(0xffffffffu, phi0, leader);
+        const unsigned mine = __ballot_sync(0xffffffffu, phi0 == phl);
+        left &= ~mine;
+        if (phi0 != phl) continue;
+        const float2 *xrow = X + lane * a.span;
+        float *d0 = a.dst + ((size_t)s * co + c0) * a.cap_b + a.hist_b + u0;
+        float *d1 = d0 + a.cap_b;
+        const bool al4 = ((a.cap_b | a.hist_b) & 3) == 0;
+        // walk the chunk in groups of four outputs; (rel, ph) = first tap (relative to pos0) and phase of the group's first output
+        int rel = 0, ph = phl;
+        const int n_here = min(a.chunk, L - u0);
+#pragma unroll 1
+        for (int m = 0; m < n_here; m += 4) {
+          int phi[4], dk[4];
+          {
+            int pp = ph, pos = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              phi[k] = pp;
+              dk[k] = pos;
+              pp += fa; pos += ia;
+              if (pp >= den) { pp -= den; pos += 1; }
+            }
+            // (pp, pos) now describe the next group's first output
+            const float4 *tp[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tp[k] = TAB + OFFROW[phi[k]] - dk[k];
+            float acc[4][4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[k][q][0] = acc[k][q][1] = 0.f;
+            const float2 *xp = xrow + rel;
+#pragma unroll 4
+            for (int i = 0; i < steps; ++i) {
+              const float2 x = xp[i];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 t = tp[k][i];
+                pipe_mac2(acc[k][0][0], acc[k][0][1], x.x, x.y, t.x, a.neg_zero);
+                pipe_mac2(acc[k][1][0], acc[k][1][1], x.x, x.y, t.y, a.neg_zero);
+                pipe_mac2(acc[k][2][0], acc[k][2][1], x.x, x.y, t.z, a.neg_zero);
+                pipe_mac2(acc[k][3][0], acc[k][3][1], x.x, x.y, t.w, a.neg_zero);
+              }
+            }
+            float o[2][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // cubic_coef of the output's phase (resample.c:246-256), tabulated per phase at plan time
+              const float4 ci = CI[phi[k]];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float sum = ci.x * acc[k][0][h] + ci.y * acc[k][1][h] + ci.z * acc[k][2][h] + ci.w * acc[k][3][h];
+                sum = (sum < -1.0f) ? -1.0f : ((sum > 1.0f) ? 1.0f : sum);      // FLTADJUST, resample.c:84
+                if (loud_on) sum *= plan.loud_gain;
+                if (m + k >= n_here) sum = 0.f;
+                o[h][k] = sum;
+              }
+            }
+            if (al4) {
+              __stcg(reinterpret_cast<float4 *>(d0 + m), make_float4(o[0][0], o[0][1], o[0][2], o[0][3]));
+              if (two) __stcg(reinterpret_cast<float4 *>(d1 + m), make_float4(o[1][0], o[1][1], o[1][2], o[1][3]));
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                __stcg(d0 + m + k, o[0][k]);
+                if (two) __stcg(d1 + m + k, o[1][k]);
+              }
+            }
+            rel += pos;
+            ph = pp;
+          }
+        }
+      }
+    }
+    if (a.ready) {
+      __syncwarp();
+      __threadfence();
+      if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ready + (size_t)g * a.n_chunks + c), "r"(a.seq) : "memory");
+    }
+  }
+}
+
+}  // namespace iamfb

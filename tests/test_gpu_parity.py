@@ -124,6 +124,26 @@ def test_pipe_rs_mixed_with_trimmed_streams():
     compare(S.c5_resample(peak_db=(-3.0, 3.0)), 20, 9, [3, 3, 3], seed=79, s16=True, expect_path=3, edit_params=trims_on_every_third_stream)
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"], ids=["one_kernel", "split_behind", "split_beside"])
+def test_resampling_pipeline_forms_bit_exact(monkeypatch, mode):
+    # the three forms of a resampling pipeline: k_pipe_rs alone; k_resample_ls (one stream per lane) with the limiter half
+    # (k_pipe_rs<PRE>) behind it; the limiter half BESIDE the resampler (chunks handed over through flags).  Same PCM.
+    import dataclasses
+    monkeypatch.setenv("IAMFB_RS_SPLIT", mode)
+    test_pipe_rs_kernel_resampling_pipelines()
+    test_pipe_rs_mixed_with_trimmed_streams()
+    # several groups of 32 streams, the last one ragged; small work items; streams at different resampler phases inside a
+    # group (a start trim in the first submit shifts every third stream)
+    monkeypatch.setenv("IAMFB_LS_CHUNK", "16")
+    monkeypatch.setenv("IAMFB_LS_SET", "1")
+    def shift_every_third(P):
+        P["trim_start"][1::3, 0] = 100
+        P["trim_start"][2::5, 1] = 37
+    compare(S.c5_resample(peak_db=(-3.0, 3.0)), 77, 8, [2, 3, 3], seed=81, expect_path=3, edit_params=shift_every_third)
+    c2up = dataclasses.replace(S.c2_714_to_B(), frame_size=1024, in_rate=44100, out_rate=48000, name="c2_714_to_B_44k1_to_48k")
+    compare(c2up, 40, 4, [1, 3], seed=82, expect_path=3)
+
+
 def test_stream_kernel_still_bit_exact(monkeypatch):
     # k_stream (single float32 stage) stays selectable behind IAMFB_PIPE=0 until k_pipe has replaced it everywhere
     monkeypatch.setenv("IAMFB_PIPE", "0")
