@@ -135,9 +135,8 @@ struct iamfb_plan {
   float4 *d_interp4;       // k_pipe_rs: cubic interpolation weights per phase
   float4 *d_tab4p;         // k_pipe_rs: the tap items with rs_tab_pad zero items on either side of every row
   int rs_tab_row, rs_tab_pad;
-  // split form of the resampling pipelines (k_resample_ls + k_pipe_rs<PRE>): 0 = one kernel (k_pipe_rs), 1 = the two kernels
-  // one after the other, 2 = the limiter half beside the resampler (chunks handed over through flags)
-  int rs_split;
+  // split form of the resampling pipelines (k_pipe_prerender + k_resample_ls + k_pipe_rs<PRE>) instead of the one kernel k_pipe_rs
+  bool rs_split;
   int rs_ls_chunk;         // outputs per work item of k_resample_ls
   // binaural HRTF front end (iamfb_hrtf.cu): non-null when an element is rendered through it; kp / desc then describe the
   // pipeline BEHIND it (those elements as 2-channel pass-through elements fed with float32 binaural frames)
@@ -165,8 +164,6 @@ struct iamfb_batch {
   unsigned submit_seq;
   SubmitRec *d_submit_mk;  // resampling plans served by k_pipe_rs: the records the multi-kernel path works from (regular streams zeroed)
   float *d_tl_a, *d_tl_b, *d_pk, *d_wm, *d_gn;
-  int *d_ls_ready;         // k_resample_ls -> k_pipe_rs<PRE>: [groups of 32 streams][chunks] = sequence number of the submit
-  int ls_chunks, ls_seq;
   float *d_hist_y, *d_hist_pk;   // fused path: limiter delay line / peak ring carried between submits
   // staging for the host-resident path
   float *d_in[kMaxEl];
@@ -1182,17 +1179,15 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
       p->rs_pipe = true;
       p->rs_pipe_sig = sig;
       {
-        // the split form: 2 = resampler with one stream per lane + the limiter half beside it (default),
-        // 1 = the same two kernels one after the other, 0 = the single kernel k_pipe_rs
+        // the split form is the default; IAMFB_RS_SPLIT=0 forces the single kernel k_pipe_rs (test hook)
         const char *sp = getenv("IAMFB_RS_SPLIT");
-        p->rs_split = sp ? atoi(sp) : 0;
-        if (p->rs_split < 0 || p->rs_split > 2) p->rs_split = 0;
+        p->rs_split = !sp || atoi(sp) != 0;
         const char *ck = getenv("IAMFB_LS_CHUNK");
         p->rs_ls_chunk = ck ? (atoi(ck) & ~3) : 32;
         if (p->rs_ls_chunk < 8 || p->rs_ls_chunk > 256) p->rs_ls_chunk = 32;
         // the staging areas of a block's warps must fit the SM: smaller work items for long filters / down-sampling ratios
         while (p->rs_ls_chunk > 8 && rs_ls_smem(p, p->rs_ls_chunk, nullptr) > 200 * 1024) p->rs_ls_chunk -= 4;
-        if (rs_ls_smem(p, p->rs_ls_chunk, nullptr) > 200 * 1024) p->rs_split = 0;
+        if (rs_ls_smem(p, p->rs_ls_chunk, nullptr) > 200 * 1024) p->rs_split = false;
       }
       for (int c = 0; c < kChCount; ++c) kp.el[0].f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
     }
@@ -1326,8 +1321,8 @@ static int rs_ls_smem(const iamfb_plan *p, int chunk, int *span_out) {
   return (int)((kp.rs_oversample * p->rs_tab_row + kp.rs_den + (kp.rs_den + 3) / 4) * sizeof(float4)) + kLsWarps * 32 * span * 8;
 }
 
-// pre: 0 = the whole pipeline in k_pipe_rs; 1 / 2 = the limiter half only (k_pipe_rs<PRE>) behind / beside k_resample_ls
-static int launch_pipe_rs(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, const iamfb_io *io, int F, bool s16, int pre = 0) {
+// pre: the limiter half only (k_pipe_rs<PRE>) behind k_resample_ls, else the whole pipeline in k_pipe_rs
+static int launch_pipe_rs(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, const iamfb_io *io, int F, bool s16, bool pre = false) {
   const KernelPlan &kp = p->kp;
   const int co = kp.out_channels;
   PipeRsArgs ra;
@@ -1369,15 +1364,12 @@ static int launch_pipe_rs(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, c
   } else {
     ra.off_ring = ra.off_tab = ra.off_stage = off;    // (not used by the limiter half)
     ra.tl_pre = b->d_tl_b; ra.tl_pre_stride = b->cap_b; ra.tl_pre_off = kp.hist;
-    if (pre == 2) {
-      ra.ready = b->d_ls_ready; ra.ready_stride = b->ls_chunks; ra.ready_chunk = p->rs_ls_chunk; ra.ready_seq = b->ls_seq;
-    }
   }
   ra.smem_bytes = off;
   static thread_local KernelPlan kpl;
   kpl = kp;
   for (int c = 0; c < kChCount; ++c) kpl.el[0].s_row_off[c] = kp.el[0].src_row[c] >= 0 ? kp.el[0].src_row[c] * pa.row_bytes : -1;
-  int r = pre ? iamfb_pipe_rs_lim_launch(ctx, p->rs_pipe_sig, kpl, ra, b->S, pre == 2) : iamfb_pipe_rs_launch(ctx, p->rs_pipe_sig, s16, kpl, ra, b->S);
+  int r = pre ? iamfb_pipe_rs_lim_launch(ctx, p->rs_pipe_sig, kpl, ra, b->S) : iamfb_pipe_rs_launch(ctx, p->rs_pipe_sig, s16, kpl, ra, b->S);
   if (r) return r;
   cudaError_t e_ = cudaGetLastError();
   if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_pipe_rs failed: %s", cudaGetErrorString(e_));
@@ -1386,12 +1378,11 @@ static int launch_pipe_rs(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, c
 }
 
 // split form of a resampling pipeline, regular streams: k_pipe_prerender -> tl_a, k_resample_ls (one stream per lane) -> tl_b,
-// k_pipe_rs<PRE> (limiter, PCM) behind or beside it, then the resampler history to the head of tl_a.  The irregular streams of
-// the submit follow on the multi-kernel path (gated), exactly as behind k_pipe_rs.
+// k_pipe_rs<PRE> (limiter, PCM; it also carries the resampler history to the head of tl_a).  The irregular streams of the
+// submit follow on the multi-kernel path (gated), exactly as behind k_pipe_rs.
 static int launch_rs_split(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, const iamfb_io *io, int F, bool s16) {
   const KernelPlan &kp = p->kp;
   const int co = kp.out_channels, S = b->S, N = kp.frame_size;
-  cudaStream_t st = ctx->stream;
   {
     PreRenderArgs ra;
     memset(&ra, 0, sizeof(ra));
@@ -1412,7 +1403,6 @@ static int launch_rs_split(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, 
     if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_pipe_prerender failed: %s", cudaGetErrorString(e_));
     ++ctx->launches;
   }
-  const bool beside = p->rs_split == 2;
   {
     ResampleLsArgs la;
     memset(&la, 0, sizeof(la));
@@ -1420,21 +1410,11 @@ static int launch_rs_split(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, 
     la.tab4 = p->d_tab4p; la.interp4 = p->d_interp4; la.tab_row = p->rs_tab_row; la.tab_pad = p->rs_tab_pad;
     la.cap_a = b->cap_a; la.cap_b = b->cap_b; la.hist_b = kp.hist; la.n_streams = S; la.co = co;
     la.chunk = p->rs_ls_chunk;
-    la.n_chunks = b->ls_chunks;
+    la.n_chunks = (iamfb_plan_max_out_samples(p, F) + la.chunk - 1) / la.chunk;
     la.neg_zero = -0.0f;
     const int smem_ls = rs_ls_smem(p, la.chunk, &la.span);
     const int groups = (S + 31) / 32;
-    la.set_groups = groups;
-    if (beside) {
-      la.ready = b->d_ls_ready;
-      la.seq = ++b->ls_seq;
-      // a set = the stream groups whose limiter blocks are resident together next to this kernel's blocks
-      const char *sg = getenv("IAMFB_LS_SET");
-      la.set_groups = sg ? atoi(sg) : 20;
-      if (la.set_groups < 1 || la.set_groups > groups) la.set_groups = groups;
-    }
-    if (iamfb_resample_ls_blocks_resident(smem_ls) < 1) return fail(IAMFB_ERR_INTERNAL, "k_resample_ls does not fit (%d bytes of shared memory)", smem_ls);
-    int blocks = ctx->n_sm;      // ONE block per SM: the limiter half takes the rest of the SM when it runs beside
+    int blocks = ctx->n_sm;      // persistent: one block of kLsWarps warps per SM
     const long long items = (long long)groups * la.n_chunks;
     if ((long long)blocks * kLsWarps > items) blocks = (int)((items + kLsWarps - 1) / kLsWarps);
     int r = iamfb_resample_ls_launch(ctx, kp, la, blocks, smem_ls);
@@ -1443,16 +1423,7 @@ static int launch_rs_split(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, 
     if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_resample_ls failed: %s", cudaGetErrorString(e_));
     ++ctx->launches;
   }
-  int r = launch_pipe_rs(ctx, p, b, io, F, false, beside ? 2 : 1);
-  if (r) return r;
-  CarryArgs c;
-  c.tl = b->d_tl_a; c.submit = b->d_submit; c.rows = co; c.cap = b->cap_a; c.hist = kp.rs_hist; c.use_in_len = 1; c.gate = nullptr;
-  c.skip_irregular = 1;
-  { ScopedKernelTimer tm_(ctx, "k_carry"); k_carry<<<dim3(co, S), 256, 0, st>>>(c); }
-  cudaError_t e_ = cudaGetLastError();
-  if (e_ != cudaSuccess) return fail(IAMFB_ERR_CUDA, "launch of k_carry failed: %s", cudaGetErrorString(e_));
-  ++ctx->launches;
-  return IAMFB_OK;
+  return launch_pipe_rs(ctx, p, b, io, F, false, true);
 }
 
 extern "C" void iamfb_plan_destroy(iamfb_plan *p) {
@@ -1538,8 +1509,6 @@ extern "C" int iamfb_batch_reset(iamfb_batch *b) {
   std::vector<StreamState> init(b->S, p->init_state);
   CU(cudaMemcpyAsync(b->d_state, init.data(), sizeof(StreamState) * b->S, cudaMemcpyHostToDevice, p->ctx->stream));
   if (b->d_gate) CU(cudaMemsetAsync(b->d_gate, 0, 2 * sizeof(int), p->ctx->stream));
-  if (b->d_ls_ready) CU(cudaMemsetAsync(b->d_ls_ready, 0, sizeof(int) * (size_t)((b->S + 31) / 32) * b->ls_chunks, p->ctx->stream));
-  b->ls_seq = 0;
   const int co = p->kp.out_channels;
   if (b->d_tl_a) CU(cudaMemsetAsync(b->d_tl_a, 0, sizeof(float) * (size_t)b->S * co * b->cap_a, p->ctx->stream));
   if (b->d_tl_b) CU(cudaMemsetAsync(b->d_tl_b, 0, sizeof(float) * (size_t)b->S * co * b->cap_b, p->ctx->stream));
@@ -1585,10 +1554,6 @@ extern "C" int iamfb_batch_create(iamfb_plan *p, int n_streams, int max_frames, 
   alloc((void **)&b->d_submit, sizeof(SubmitRec) * n_streams);
   if (p->rs_pipe) alloc((void **)&b->d_submit_mk, sizeof(SubmitRec) * n_streams);
   if (p->rs_pipe) alloc((void **)&b->d_gate, 2 * sizeof(int));
-  if (p->rs_pipe && p->rs_split) {
-    b->ls_chunks = (iamfb_plan_max_out_samples(p, max_frames) + p->rs_ls_chunk - 1) / p->rs_ls_chunk + 1;
-    alloc((void **)&b->d_ls_ready, sizeof(int) * (size_t)((n_streams + 31) / 32) * b->ls_chunks);
-  }
   if (kp.resample) alloc((void **)&b->d_tl_a, sizeof(float) * (size_t)n_streams * co * b->cap_a);
   if (p->fused) {
     if (kp.limiter) {
@@ -1644,7 +1609,7 @@ static void free_staging(iamfb_batch *b) {
 
 extern "C" void iamfb_batch_destroy(iamfb_batch *b) {
   if (!b) return;
-  cudaFree(b->d_state); cudaFree(b->d_frames); cudaFree(b->d_submit); cudaFree(b->d_submit_mk); cudaFree(b->d_gate); cudaFree(b->d_ls_ready);
+  cudaFree(b->d_state); cudaFree(b->d_frames); cudaFree(b->d_submit); cudaFree(b->d_submit_mk); cudaFree(b->d_gate);
   cudaFree(b->d_tl_a); cudaFree(b->d_tl_b); cudaFree(b->d_pk); cudaFree(b->d_wm); cudaFree(b->d_gn);
   cudaFree(b->d_hist_y); cudaFree(b->d_hist_pk);
   for (int e = 0; e < kMaxEl; ++e) cudaFree(b->d_wide[e]);
@@ -1956,7 +1921,7 @@ static int run_pipeline(iamfb_batch *b, const iamfb_io *io, int F, bool flush, v
   }
   // resampling plans: k_pipe_rs renders the regular streams, the multi-kernel path below the irregular ones
   const bool rs_native = p->rs_pipe && !flush && !io->gain_ramp[0] && !io->out_gain_ramp;
-  const bool rs_split = rs_native && p->rs_split != 0 && b->d_ls_ready != nullptr;
+  const bool rs_split = rs_native && p->rs_split;
   const bool s16_in = !flush && io->in_format == IAMFB_IN_S16 &&
                       ((p->fused && p->s16_native && !(p->stream && !p->pipe)) || rs_native);
   if (!flush && io->in_format == IAMFB_IN_S16 && !s16_in) {

@@ -106,9 +106,8 @@ int iamfb_pipe_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelP
                       const CUtensorMap &m0, const CUtensorMap &m1);
 namespace iamfb { struct PipeRsArgs; }
 int iamfb_pipe_rs_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelPlan &kp, const iamfb::PipeRsArgs &pa, int S);
-// split form of the resampling pipelines: k_resample_ls (one stream per lane) + k_pipe_rs<PRE> (the limiter half), the
-// second optionally launched beside the first (programmatic dependent launch, chunks handed over through flags)
-int iamfb_pipe_rs_lim_launch(iamfb_ctx *ctx, int sig_id, const iamfb::KernelPlan &kp, const iamfb::PipeRsArgs &pa, int S, bool beside);
+// split form of the resampling pipelines: k_pipe_prerender + k_resample_ls (one stream per lane) + k_pipe_rs<PRE> (the limiter half)
+int iamfb_pipe_rs_lim_launch(iamfb_ctx *ctx, int sig_id, const iamfb::KernelPlan &kp, const iamfb::PipeRsArgs &pa, int S);
 namespace iamfb { struct ResampleLsArgs; struct PreRenderArgs; }
 int iamfb_pipe_prerender_launch(iamfb_ctx *ctx, int sig_id, bool s16, const iamfb::KernelPlan &kp, const iamfb::PreRenderArgs &pa, int S, int F);
 int iamfb_resample_ls_blocks_resident(int smem_bytes);

@@ -1296,14 +1296,12 @@ struct CarryArgs {
   int rows, cap, hist;
   int use_in_len;     // 1: advance by in_len (pre-resample line), 0: by lim_len
   const int *gate;    // non-null: return at once when *gate == 0
-  int skip_irregular = 0;   // 1: only the streams the submit does not flag irregular (the others are carried by the launch of their own path)
 };
 
 static __global__ void __launch_bounds__(256) k_carry(CarryArgs a) {
   __shared__ float tmp[256];
   const int s = blockIdx.y, r = blockIdx.x;
   if (a.gate && *a.gate == 0) return;
-  if (a.skip_irregular && a.submit[s].irregular) return;
   const int len = a.use_in_len ? a.submit[s].in_len : a.submit[s].lim_len;
   if (len == 0) return;
   float *row = a.tl + ((size_t)s * a.rows + r) * a.cap;

@@ -28,7 +28,7 @@ int launch_rs(iamfb_ctx *ctx, const KernelPlan &kp, const PipeRsArgs &pa, int S,
   lc.stream = ctx->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;   // may start under k_resolve / beside k_resample_ls (griddepcontrol in the kernels)
+  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;   // may start under k_resolve (griddepcontrol in the kernels)
   lc.attrs = at;
   lc.numAttrs = 1;
   CU(cudaLaunchKernelEx(&lc, k_pipe_rs<SIG, PRE>, kp, pa));
@@ -36,10 +36,10 @@ int launch_rs(iamfb_ctx *ctx, const KernelPlan &kp, const PipeRsArgs &pa, int S,
 }
 }  // namespace
 
-// the limiter half of a resampling pipeline behind (or beside) k_resample_ls
-int iamfb_pipe_rs_lim_launch(iamfb_ctx *ctx, int sig_id, const KernelPlan &kp, const PipeRsArgs &pa, int S, bool beside) {
+// the limiter half of a resampling pipeline behind k_resample_ls
+int iamfb_pipe_rs_lim_launch(iamfb_ctx *ctx, int sig_id, const KernelPlan &kp, const PipeRsArgs &pa, int S) {
 #define X(id, L0, N0, T, NW, VEC, MINB)                                                                     \
-  if (sig_id == id) return launch_rs<PipeSig<L0, N0, 0, 0, T, false, 2, NW, VEC, MINB>, true>(ctx, kp, pa, S, beside);
+  if (sig_id == id) return launch_rs<PipeSig<L0, N0, 0, 0, T, false, 2, NW, VEC, MINB>, true>(ctx, kp, pa, S, false);
   IAMFB_PIPE_RS_SIGS(X)
 #undef X
   return fail(IAMFB_ERR_INTERNAL, "no k_pipe_rs signature %d", sig_id);

@@ -40,8 +40,6 @@ struct PipeRsArgs {
   // PRE variant (the resampler ran in front, k_resample_ls): the resampled, clamped, loudness-scaled time line
   const float *tl_pre;          // [S][co][tl_pre_stride], output u of this submit at tl_pre_off + u
   int tl_pre_stride, tl_pre_off;
-  const int *ready;             // non-null: k_resample_ls is still running beside this kernel - ready[(s / 32) * ready_stride + c]
-  int ready_stride, ready_chunk, ready_seq;   // == ready_seq once outputs [c * ready_chunk, (c + 1) * ready_chunk) of the 32 streams are in memory
 };
 
 // k_pipe_prerender: the render stage of k_pipe_rs on its own (split form) - the regular streams' decoded frames (float32 or
@@ -97,8 +95,12 @@ __global__ void __launch_bounds__(128) k_pipe_prerender(const __grid_constant__ 
 }
 
 // PRE = true: the limiter half only - the resampler's outputs come from memory (tl_pre) instead of the ring + FIR
+// resident blocks per SM the limiter half is compiled for: it holds no ring, table or stages, and with 14 blocks of 96
+// threads a batch of 2048 streams is ONE wave (measured: 0.304 -> 0.265 ms per submit of configuration 5, spills included)
+template <class SIG>
+constexpr int pipe_rs_pre_minb() { return 2048 / SIG::kThreads < 14 ? 2048 / SIG::kThreads : 14; }
 template <class SIG, bool PRE = false>
-__global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(const __grid_constant__ KernelPlan plan, PipeRsArgs b) {
+__global__ void __launch_bounds__(SIG::kThreads, PRE ? pipe_rs_pre_minb<SIG>() : SIG::kMinBlocks) k_pipe_rs(const __grid_constant__ KernelPlan plan, PipeRsArgs b) {
   typedef typename SIG::E0 E0;
   constexpr int VEC = SIG::VEC, NW = SIG::NW, CO = SIG::CO, NY = SIG::NY, WN = SIG::kWorkers, NS = SIG::kStages;
   constexpr int TL = kStreamTile, NP = (NY + 1) / 2;
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
     if (k < b.mirror) RING[p * RGM + RG + k] = v;
   }
   }
-  if constexpr (!PRE) asm volatile("griddepcontrol.wait;" ::: "memory");   // (PRE: launched behind finished kernels, or beside the resampler)
+  if constexpr (!PRE) asm volatile("griddepcontrol.wait;" ::: "memory");   // (PRE: launched behind finished kernels)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
   mbar_wait(&s_hbar, 0u);
@@ -387,21 +389,6 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
   V yn[NY];
 #pragma unroll
   for (int r = 0; r < NY; ++r) yn[r] = vzero<VEC>();
-  auto pre_wait = [&](int tau) {          // (all lanes of a worker warp) until the resampler's chunks under tile tau are in memory
-    if (b.ready == nullptr) return;
-    const int u_lo = tau * TL, u_hi = min(L, u_lo + TL) - 1;
-    if (u_hi < u_lo) return;
-    const int c_lo = u_lo / b.ready_chunk, c_hi = u_hi / b.ready_chunk;
-    const int *flag = b.ready + (size_t)(s >> 5) * b.ready_stride;
-    for (int c = c_lo + lane; c <= c_hi; c += 32) {      // (at most a few chunks per tile)
-      int v;
-      do {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag + c) : "memory");
-        if (v != b.ready_seq) __nanosleep(64);
-      } while (v != b.ready_seq);
-    }
-    __syncwarp();
-  };
   auto pre_load = [&](int tau) {
     const int u0 = tau * TL + q0r;
 #pragma unroll 1
@@ -543,7 +530,6 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
       for (int q = 0; q < NS; ++q)
         if (q < K) issue_in(q);
     } else if (T > 0) {
-      pre_wait(0);
       pre_load(0);
     }
     int filled = 0;                  // input tiles rendered into the ring so far
@@ -554,10 +540,7 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
         if (t + 1 < T) {
           const int tau = t + 1;
           pre_take(tau);
-          if (tau + 1 < T) {
-            pre_wait(tau + 1);
-            pre_load(tau + 1);
-          }
+          if (tau + 1 < T) pre_load(tau + 1);
           if (limiter) wmax_scan();
           asm volatile("bar.sync 1, %0;" ::"n"(WN) : "memory");
           if (limiter) wmax_combine(tau);
@@ -657,7 +640,16 @@ __global__ void __launch_bounds__(SIG::kThreads, SIG::kMinBlocks) k_pipe_rs(cons
       a.hist_pk[(size_t)s * b.hist_pk_stride + i] = PKR[(tile & 1) * TL + off];
     }
   }
-  // the last RH pre-resample samples (ring entries of the input instants [in_len - RH, in_len))
+  // the last RH pre-resample samples: PRE - from the tail of this submit's inputs on the pre-resample time line to its head
+  // (in_len >= one frame >= 240 > RH: source and destination do not overlap; the resampler in front has finished)
+  if constexpr (PRE) {
+    for (int i = tid; i < CO * RH; i += SIG::kThreads) {
+      const int c = i / RH, k = i - c * RH;
+      float *row = b.hist_rs + ((size_t)s * CO + c) * b.hist_rs_stride;
+      row[k] = row[in_len + k];
+    }
+  }
+  // otherwise the ring entries of the input instants [in_len - RH, in_len)
   if constexpr (!PRE)
   for (int i = tid; i < NP * RH; i += SIG::kThreads) {
     const int p = i / RH, k = i - p * RH;

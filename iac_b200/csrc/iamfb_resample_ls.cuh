@@ -17,9 +17,10 @@
 //
 // Lanes whose streams are at another phase (a stream that joined the batch later, lost a frame, ...) are served in further
 // passes of the same warp (grouped by the phase of the chunk's first output); irregular streams of the submit (trims,
-// missing frames) are skipped - the multi-kernel path renders them.  The kernel is persistent: the grid strides over the
-// work items in an order that lets k_pipe_rs<PRE> (the limiter half, launched BESIDE this kernel by a programmatic
-// dependent launch) consume the chunks while later ones are produced; ready[group][chunk] = seq is the hand-over.
+// missing frames) are skipped - the multi-kernel path renders them.  The kernel is persistent: one block of 8 warps per SM
+// (two per scheduler, each with its own staging area) strides over the work items; k_pipe_rs<PRE> (the limiter half) follows.
+// Measured with the limiter half BESIDE this kernel (chunks handed over through flags): no gain - the staging areas leave
+// no shared memory for its blocks, and with fewer resampler warps the FP32 pipe idles more than the overlap saves.
 #pragma once
 #include "iamfb_pipe.cuh"
 
@@ -38,9 +39,6 @@ struct ResampleLsArgs {
   int chunk;                    // outputs per work item (multiple of 4)
   int n_chunks;                 // chunks that cover the longest stream of the submit
   int span;                     // inputs staged per stream and chunk (row stride in float2, odd)
-  int set_groups;               // stream groups per set: the work items are ordered set by set, chunk by chunk inside a set
-  int *ready;                   // [groups][n_chunks] or null
-  int seq;
   float neg_zero;
 };
 
@@ -67,12 +65,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
   for (int i = threadIdx.x; i < den; i += NWARPS * 32) CI[i] = a.interp4[i];
   int *OFFROW = reinterpret_cast<int *>(CI + den);                                 // [den] first item of the phase's tap row
   for (int i = threadIdx.x; i < den; i += NWARPS * 32) OFFROW[i] = (i * os / den) * trow + pad;
-  // the limiter half may start now: every block of this grid is resident from here on (grid <= what fits the device)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
 
   const int groups = (a.n_streams + 31) / 32;
-  const int n_sets = (groups + a.set_groups - 1) / a.set_groups;
   const int steps = Nf + 3 * (ia + 1);
   const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
   const int co = a.co;
@@ -86,19 +81,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
   }
 
   for (long long item = (long long)blockIdx.x + (long long)wi * gridDim.x; item < total; item += warps) {
-    // item -> (set, chunk, group inside the set): sets in order, chunks in order inside a set, groups fastest
-    int g, c;
-    {
-      const long long per_set = (long long)a.set_groups * a.n_chunks;
-      const int set = (int)(item / per_set);
-      const int gs = min(a.set_groups, groups - set * a.set_groups);       // groups of this set (the last may be smaller)
-      const long long r = item - (long long)set * per_set;
-      // (sets in front of the last are full; inside the last set the items past gs * n_chunks do not exist)
-      if (r >= (long long)gs * a.n_chunks) continue;
-      c = (int)(r / gs);
-      g = set * a.set_groups + (int)(r - (long long)c * gs);
-      (void)n_sets;
-    }
+    const int c = (int)(item / groups), g = (int)(item - (long long)c * groups);     // chunks in order, groups fastest
     const int s = g * 32 + lane;
     const int u0 = c * a.chunk;
     // this lane's stream: length, position and phase of the chunk's first output
@@ -115,13 +98,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
       }
     }
     unsigned todo = __ballot_sync(0xffffffffu, phi0 >= 0);
-    if (todo == 0u) {
-      if (a.ready && lane == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ready + (size_t)g * a.n_chunks + c), "r"(a.seq) : "memory");
-      }
-      continue;
-    }
+    if (todo == 0u) continue;
     for (int c0 = 0; c0 < co; c0 += 2) {
       const bool two = c0 + 1 < co;
       // ---- stage the inputs of the chunk: row st of X = stream 32 g + st, entries [pos0(st), pos0(st) + span)
@@ -247,11 +224,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
           }
         }
       }
-    }
-    if (a.ready) {
-      __syncwarp();
-      __threadfence();
-      if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ready + (size_t)g * a.n_chunks + c), "r"(a.seq) : "memory");
     }
   }
 }

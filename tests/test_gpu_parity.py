@@ -124,10 +124,10 @@ def test_pipe_rs_mixed_with_trimmed_streams():
     compare(S.c5_resample(peak_db=(-3.0, 3.0)), 20, 9, [3, 3, 3], seed=79, s16=True, expect_path=3, edit_params=trims_on_every_third_stream)
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"], ids=["one_kernel", "split_behind", "split_beside"])
+@pytest.mark.parametrize("mode", ["0", "1"], ids=["one_kernel", "split"])
 def test_resampling_pipeline_forms_bit_exact(monkeypatch, mode):
-    # the three forms of a resampling pipeline: k_pipe_rs alone; k_resample_ls (one stream per lane) with the limiter half
-    # (k_pipe_rs<PRE>) behind it; the limiter half BESIDE the resampler (chunks handed over through flags).  Same PCM.
+    # the two forms of a resampling pipeline: k_pipe_rs alone (IAMFB_RS_SPLIT=0, test hook) and the default split form -
+    # k_pipe_prerender, k_resample_ls (one stream per lane), k_pipe_rs<PRE> (the limiter half).  Same PCM.
     import dataclasses
     monkeypatch.setenv("IAMFB_RS_SPLIT", mode)
     test_pipe_rs_kernel_resampling_pipelines()
@@ -135,7 +135,6 @@ def test_resampling_pipeline_forms_bit_exact(monkeypatch, mode):
     # several groups of 32 streams, the last one ragged; small work items; streams at different resampler phases inside a
     # group (a start trim in the first submit shifts every third stream)
     monkeypatch.setenv("IAMFB_LS_CHUNK", "16")
-    monkeypatch.setenv("IAMFB_LS_SET", "1")
     def shift_every_third(P):
         P["trim_start"][1::3, 0] = 100
         P["trim_start"][2::5, 1] = 37
