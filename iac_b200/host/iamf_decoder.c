@@ -356,6 +356,7 @@ static int internal_init(IAMF_DecoderHandle h, const uint8_t *data, uint32_t siz
       if (!used || o.type == IH_OBU_SEQUENCE_HEADER) break;
       pos += used;
     }
+    if (pos > size) pos = size;   /* (a first OBU that is no sequence header is stepped over repeatedly: never past the buffer) */
   }
   if (used || (h->flags & IH_FLAG_MAGIC)) pos += read_descriptors(h, data + pos, size - pos);
   *rsize = pos;
