@@ -95,6 +95,25 @@ __global__ void __launch_bounds__(128) k_pipe_prerender(const __grid_constant__ 
 }
 
 // PRE = true: the limiter half only - the resampler's outputs come from memory (tl_pre) instead of the ring + FIR
+// output channel that owns row r of the time line (inverse of SIG::yrow)
+template <class SIG>
+__host__ __device__ constexpr int pipe_rs_row_channel(int r) {
+  for (int c = 0; c < SIG::CO; ++c)
+    if (SIG::yrow(c) == r) return c;
+  return 0;
+}
+
+// f(row, channel) for every row of the time line, the channel a compile-time constant (a constexpr function called in a
+// run-time expression would be evaluated on the device, where the tables it reads do not exist)
+template <class SIG, int R, class F>
+__device__ __forceinline__ void pipe_rs_rows(F &&f) {
+  if constexpr (R < SIG::NY) {
+    constexpr int c = pipe_rs_row_channel<SIG>(R);
+    f(R, c);
+    pipe_rs_rows<SIG, R + 1>(f);
+  }
+}
+
 // resident blocks per SM the limiter half is compiled for: it holds no ring, table or stages, and with 14 blocks of 96
 // threads a batch of 2048 streams is ONE wave (measured: 0.304 -> 0.265 ms per submit of configuration 5, spills included)
 template <class SIG>
@@ -391,28 +410,24 @@ __global__ void __launch_bounds__(SIG::kThreads, PRE ? pipe_rs_pre_minb<SIG>() :
   for (int r = 0; r < NY; ++r) yn[r] = vzero<VEC>();
   auto pre_load = [&](int tau) {
     const int u0 = tau * TL + q0r;
-#pragma unroll 1
-    for (int c = 0; c < CO; ++c) {
-      const int r = pipe_yrow_rt<SIG>(c);
-      if (r < 0) continue;
+    const bool vec = ((b.tl_pre_stride | b.tl_pre_off) & 3) == 0;
+    // (row -> channel is a compile-time map: the loads land in yn[] without a dependent select, so that their latency hides
+    // behind the limiter work of the tile in between)
+    pipe_rs_rows<SIG, 0>([&](int r, int c) {
       const float *src = b.tl_pre + ((size_t)s * CO + c) * b.tl_pre_stride + b.tl_pre_off + u0;
-      V v;
       bool done = false;
       if constexpr (VEC == 4) {
-        if (((b.tl_pre_stride | b.tl_pre_off) & 3) == 0) {
+        if (vec) {
           const float4 f = __ldcg(reinterpret_cast<const float4 *>(src));
-          v.v[0] = f.x; v.v[1] = f.y; v.v[2] = f.z; v.v[3] = f.w;
+          yn[r].v[0] = f.x; yn[r].v[1] = f.y; yn[r].v[2] = f.z; yn[r].v[3] = f.w;
           done = true;
         }
       }
       if (!done) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v.v[k] = __ldcg(src + k);
+        for (int k = 0; k < VEC; ++k) yn[r].v[k] = __ldcg(src + k);
       }
-#pragma unroll
-      for (int rr = 0; rr < NY; ++rr)
-        if (rr == r) yn[rr] = v;
-    }
+    });
   };
   auto pre_take = [&](int tau) {
     const int u0 = tau * TL + q0r;
