@@ -666,6 +666,14 @@ static int enable_mix(IAMF_DecoderHandle h, const ih_mix *mix) {
     }
     /* iamf_stream_new: max_frame_size (IAMF_decoder.c:1628-1630) */
     uint32_t mfs = 1024 < cc->frame_size ? (uint32_t)cc->frame_size * 6 : 6144;
+    /* (never less than what one call can really write: a frame resampled to the output rate, or the flush of the
+     * limiter delay + resampler tail - more than 6 frames' worth only for ratios the reference's own buffers do not hold) */
+    if (cc->rate > 0 && h->sampling_rate && (int)h->sampling_rate != cc->rate) {
+      const uint64_t rs = ((uint64_t)cc->frame_size * h->sampling_rate + cc->rate - 1) / (uint64_t)cc->rate + 2;
+      const uint64_t fl = 240 + 64 + 256ull * h->sampling_rate / (uint64_t)cc->rate;
+      if (rs > mfs) mfs = (uint32_t)rs;
+      if (fl > mfs) mfs = (uint32_t)fl;
+    }
     if (mfs > h->info.max_frame_size) h->info.max_frame_size = mfs;
     ++h->n_streams;
   }

@@ -152,6 +152,10 @@ int ih_parse_codec(const ih_obu *o, ih_codec *c) {
     if (full_conf > (int)sizeof(c->conf)) return IAMF_ERR_UNIMPLEMENTED;
     c->rate = ih_flac_rate(c->conf, c->conf_size);
   }
+  /* a damaged config must not reach the buffer arithmetic: a rate of a few hertz against the 48 kHz output would make one
+   * frame hundreds of thousands of samples long (the reference sizes its own buffers by max_frame_size alone) */
+  if (c->frame_size < 1 || c->frame_size > 65536) return IAMF_ERR_INVALID_PACKET;
+  if (c->rate != -1 && (c->rate < 8000 || c->rate > 192000)) return IAMF_ERR_UNIMPLEMENTED;
   return IAMF_OK;
 }
 

@@ -161,6 +161,10 @@ int main(int argc, char **argv) {
       /* a heap copy of exactly len bytes: reads past the end are caught by the sanitizer */
       uint8_t *exact = (uint8_t *)malloc(len ? len : 1);
       memcpy(exact, buf, len);
+      if (getenv("FUZZ_DUMP")) {      /* the input about to run, for reproducing a finding */
+        FILE *df = fopen(getenv("FUZZ_DUMP"), "wb");
+        if (df) { fwrite(exact, 1, len, df); fclose(df); }
+      }
       if (is_mp4) run_mp4(argv[fi], exact, len);
       else if (it % 4 == 3 && len >= n) run_batch(src, n, exact, len);     /* (descriptors untouched only when nothing was cut in front) */
       else run_decoder(exact, len);
