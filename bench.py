@@ -412,10 +412,23 @@ class DeviceWorkload:
                         useful_fir_tmacs=useful / t / 1e12, limb_pairs=limb_pairs,
                         pipeline=dict(achieved=pipe, frac=pipe / peak_gbs, note="all kernels of a submit, algorithmic bytes / submit time, vs HBM peak"),
                         kernels=kernels)
-        return dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
-                    traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=alg / dom_launches,
-                    pipeline=dict(achieved=pipe, frac=pipe / peak_gbs, note="all kernels of a submit, algorithmic bytes / submit time"),
-                    kernels=kernels)
+        ro = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak_gbs, unit="GB/s", frac=achieved / peak_gbs,
+                  traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=alg / dom_launches,
+                  pipeline=dict(achieved=pipe, frac=pipe / peak_gbs, note="all kernels of a submit, algorithmic bytes / submit time"),
+                  kernels=kernels)
+        if dom in ("k_resample_ls", "k_pipe_rs") and self.sc.in_rate != self.sc.out_rate:
+            # the resampler FIR is bound by the FP32 pipe, not by HBM (the contract's roofline above stays the HBM one): the
+            # reference's sums are 4 accumulators x filt_len taps per output and channel, every product rounded before it is
+            # added (2 lane-operations per tap), against 128 FP32 lanes per SM at the device's clock
+            import torch
+            pr = torch.cuda.get_device_properties(self.dev)
+            nf = 64 if self.sc.out_rate >= self.sc.in_rate else (((64 * self.sc.in_rate // self.sc.out_rate) - 1) & ~7) + 8
+            ops = out_per_submit * self.sc.out_channels * 4 * nf * 2
+            peak_ops = pr.multi_processor_count * 128 * float(getattr(pr, "clock_rate", 1965000)) * 1e3
+            t = kernels[dom]["ms_per_submit"] / 1e3
+            ro["fp32_pipe"] = dict(lane_ops_per_submit=ops, peak_lane_ops_per_s=peak_ops, floor_ms=ops / peak_ops * 1e3,
+                                   frac=ops / t / peak_ops, note="exact (separately rounded) multiply-adds of the resampler FIR vs 128 FP32 lanes per SM")
+        return ro
 
     def close(self):
         self.eng.close()
@@ -691,7 +704,8 @@ def run_gpu(args):
                               streams_above_limiter_threshold=wo.active_frac,
                               roofline=dict(bound=ro["bound"], kernel=ro["kernel"], achieved=ro["achieved"], peak=ro["peak"], unit=ro["unit"],
                                             frac=ro["frac"], traffic=ro["traffic"], pipeline_frac=ro["pipeline"]["frac"],
-                                            kernels={k: round(v["ms_per_submit"], 5) for k, v in ko.items()}))
+                                            kernels={k: round(v["ms_per_submit"], 5) for k, v in ko.items()},
+                                            **({"fp32_pipe": ro["fp32_pipe"]} if "fp32_pipe" in ro else {})))
             wo.close()
             del wo
         w = w_keep
