@@ -416,8 +416,12 @@ __global__ void __launch_bounds__(SIG::kThreads, PRE ? pipe_rs_pre_minb<SIG>() :
     pipe_rs_rows<SIG, 0>([&](int r, int c) {
       const float *src = b.tl_pre + ((size_t)s * CO + c) * b.tl_pre_stride + b.tl_pre_off + u0;
       bool done = false;
+      if (u0 >= L) {                 // (a ragged last tile: nothing is read behind the submit's last output)
+        yn[r] = vzero<VEC>();
+        done = true;
+      }
       if constexpr (VEC == 4) {
-        if (vec) {
+        if (vec && !done) {
           const float4 f = __ldcg(reinterpret_cast<const float4 *>(src));
           yn[r].v[0] = f.x; yn[r].v[1] = f.y; yn[r].v[2] = f.z; yn[r].v[3] = f.w;
           done = true;
