@@ -137,7 +137,8 @@ struct iamfb_plan {
   int rs_tab_row, rs_tab_pad;
   // split form of the resampling pipelines (k_pipe_prerender + k_resample_ls + k_pipe_rs<PRE>) instead of the one kernel k_pipe_rs
   bool rs_split;
-  int rs_ls_chunk;         // outputs per work item of k_resample_ls
+  int rs_ls_chunk;         // outputs per work item of k_resample_ls (upper bound unless fixed)
+  bool rs_ls_chunk_fixed;
   // binaural HRTF front end (iamfb_hrtf.cu): non-null when an element is rendered through it; kp / desc then describe the
   // pipeline BEHIND it (those elements as 2-channel pass-through elements fed with float32 binaural frames)
   iamfb_hrtf_front *hrtf;
@@ -151,6 +152,7 @@ struct iamfb_plan {
 };
 
 static int rs_ls_smem(const iamfb_plan *p, int chunk, int *span_out);
+static const int kLsSmemMax = 226 * 1024;   // dynamic shared memory of a k_resample_ls block (one block per SM; the SM offers 227 KB)
 
 struct iamfb_batch {
   iamfb_plan *plan;
@@ -1182,12 +1184,15 @@ extern "C" int iamfb_plan_create(iamfb_ctx *ctx, const iamfb_plan_desc *d, iamfb
         // the split form is the default; IAMFB_RS_SPLIT=0 forces the single kernel k_pipe_rs (test hook)
         const char *sp = getenv("IAMFB_RS_SPLIT");
         p->rs_split = !sp || atoi(sp) != 0;
+        // outputs per work item of k_resample_ls: the largest the staging areas allow (<= 36); a launch picks the size
+        // at or below it that leaves the least idle work in the last round of its persistent warps.  IAMFB_LS_CHUNK fixes it.
         const char *ck = getenv("IAMFB_LS_CHUNK");
-        p->rs_ls_chunk = ck ? (atoi(ck) & ~3) : 32;
-        if (p->rs_ls_chunk < 8 || p->rs_ls_chunk > 256) p->rs_ls_chunk = 32;
+        p->rs_ls_chunk = ck ? (atoi(ck) & ~3) : 36;
+        p->rs_ls_chunk_fixed = ck != nullptr;
+        if (p->rs_ls_chunk < 8 || p->rs_ls_chunk > 256) p->rs_ls_chunk = 36;
         // the staging areas of a block's warps must fit the SM: smaller work items for long filters / down-sampling ratios
-        while (p->rs_ls_chunk > 8 && rs_ls_smem(p, p->rs_ls_chunk, nullptr) > 200 * 1024) p->rs_ls_chunk -= 4;
-        if (rs_ls_smem(p, p->rs_ls_chunk, nullptr) > 200 * 1024) p->rs_split = false;
+        while (p->rs_ls_chunk > 8 && rs_ls_smem(p, p->rs_ls_chunk, nullptr) > kLsSmemMax) p->rs_ls_chunk -= 4;
+        if (rs_ls_smem(p, p->rs_ls_chunk, nullptr) > kLsSmemMax) p->rs_split = false;
       }
       for (int c = 0; c < kChCount; ++c) kp.el[0].f_gain[c] = ((ep.gain_mask >> c) & 1u) ? ep.gain[c] : 1.0f;
     }
@@ -1409,11 +1414,21 @@ static int launch_rs_split(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, 
     la.src = b->d_tl_a; la.dst = b->d_tl_b; la.submit = b->d_submit; la.state = b->d_state;
     la.tab4 = p->d_tab4p; la.interp4 = p->d_interp4; la.tab_row = p->rs_tab_row; la.tab_pad = p->rs_tab_pad;
     la.cap_a = b->cap_a; la.cap_b = b->cap_b; la.hist_b = kp.hist; la.n_streams = S; la.co = co;
+    const int groups = (S + 31) / 32;
+    const int max_out = iamfb_plan_max_out_samples(p, F);
     la.chunk = p->rs_ls_chunk;
-    la.n_chunks = (iamfb_plan_max_out_samples(p, F) + la.chunk - 1) / la.chunk;
+    if (!p->rs_ls_chunk_fixed) {
+      // every round of the persistent warps lasts one chunk: the size with the fewest (rounds x chunk) wins, ties to the larger
+      long long best = -1;
+      for (int c = p->rs_ls_chunk; c >= 16 && c >= p->rs_ls_chunk - 16; c -= 4) {
+        const long long items = (long long)groups * ((max_out + c - 1) / c), warps = (long long)ctx->n_sm * kLsWarps;
+        const long long cost = ((items + warps - 1) / warps) * c;
+        if (best < 0 || cost < best) { best = cost; la.chunk = c; }
+      }
+    }
+    la.n_chunks = (max_out + la.chunk - 1) / la.chunk;
     la.neg_zero = -0.0f;
     const int smem_ls = rs_ls_smem(p, la.chunk, &la.span);
-    const int groups = (S + 31) / 32;
     int blocks = ctx->n_sm;      // persistent: one block of kLsWarps warps per SM
     const long long items = (long long)groups * la.n_chunks;
     if ((long long)blocks * kLsWarps > items) blocks = (int)((items + kLsWarps - 1) / kLsWarps);
