@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
 #pragma unroll
               for (int q = 0; q < 4; ++q) acc[k][q][0] = acc[k][q][1] = 0.f;
             const float2 *xp = xrow + rel;
-#pragma unroll 4
+#pragma unroll 8
             for (int i = 0; i < steps; ++i) {
               const float2 x = xp[i];
 #pragma unroll
