@@ -5,11 +5,12 @@
 // step - 16 bytes of shared-memory traffic per 8 multiply-adds, which is what bounds k_pipe_rs (shared-memory pipe 75 %
 // busy, FP32 pipe 58 %).  Streams that run in step have the SAME phase at the same output index: with one
 // stream per lane the tap items are warp-uniform (one broadcast read per warp instead of 32 distinct ones) and only the
-// inputs are per lane - the loop is left with the FP32 pipe as its bound.
+// inputs are per lane - the loop is left with the FP32 pipe as its bound (an 8-byte input per lane and four broadcast 16-byte
+// tap items per step: 10 shared-memory wavefronts against 64 cycles of FP32 work; measured: DESIGN.md 4.3).
 //
 // Work item = (group of 32 streams, chunk of `chunk` consecutive outputs).  A warp stages, for each of its streams, the
 // inputs the chunk spans (channel pairs interleaved, row stride odd: lanes hit different banks) from the pre-resample time
-// line tl_a[S][co][cap_a] (k_render's output; the previous submit's last rs_hist inputs in front), then walks the chunk in
+// line tl_a[S][co][cap_a] (k_pipe_prerender's output; the previous submit's last rs_hist inputs in front), then walks the chunk in
 // groups of 4 consecutive outputs exactly like k_pipe_rs: one pass over the inputs of the four outputs, the rows of the
 // tap table carrying zero items outside each output's window (adding +-0 to a sum that started at +0 is exact), four
 // accumulators per channel over j ascending, packed exact multiply-add for the two channels of a pair, cubic blend with the
