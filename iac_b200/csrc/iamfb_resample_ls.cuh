@@ -43,7 +43,9 @@ struct ResampleLsArgs {
   float neg_zero;
 };
 
-constexpr int kLsWarps = 8;     // warps per block, one staging area each: two per scheduler - one stages while the other computes
+constexpr int kLsWarps = 12;    // warps per block = 6 pairs; a pair shares ONE staging area that covers 2 x chunk outputs (the two
+                                // halves' inputs overlap by the filter length: 35 % less shared memory per warp than an area each,
+                                // which is what lets three warps per scheduler fit the SM)
 
 __device__ __forceinline__ void ls_cp4(void *dst_smem, const void *src, bool valid) {   // 4-byte asynchronous copy, zeros when !valid
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
@@ -61,7 +63,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
   const int tab_items = os * trow;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   float4 *CI = TAB + tab_items;                                                    // [den] cubic weights per phase
-  float2 *X = reinterpret_cast<float2 *>(CI + den + (den + 3) / 4) + (size_t)wi * 32 * a.span;    // [32 streams][span] channel pairs
+  const int pi = wi >> 1, half = wi & 1;                                           // pair of warps, this warp's half of the pair's outputs
+  float2 *X = reinterpret_cast<float2 *>(CI + den + (den + 3) / 4) + (size_t)pi * 32 * a.span;    // [32 streams][span] channel pairs
   for (int i = threadIdx.x; i < tab_items; i += NWARPS * 32) TAB[i] = a.tab4[i];
   for (int i = threadIdx.x; i < den; i += NWARPS * 32) CI[i] = a.interp4[i];
   int *OFFROW = reinterpret_cast<int *>(CI + den);                                 // [den] first item of the phase's tap row
@@ -72,47 +75,57 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
   const int steps = Nf + 3 * (ia + 1);
   const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
   const int co = a.co;
-  const long long total = (long long)groups * a.n_chunks;
-  const int warps = gridDim.x * NWARPS;
-  // the two warps of a scheduler take turns: the second starts half a work item late, so that one stages (and runs the
-  // per-chunk prologue) while the other keeps the FP32 pipe busy - all items last the same, the offset persists
-  if (((wi >> 2) ^ wi) & 1) {      // (differs inside a pair whether schedulers take warps w, w + 4 or w, w + 1)
+  const long long total = (long long)groups * a.n_chunks;       // (n_chunks counts the pairs' items of 2 x chunk outputs)
+  const int pairs = gridDim.x * (NWARPS / 2);
+  // the pairs of a scheduler take turns: every other pair starts half an item late, so that one stages while the others
+  // keep the FP32 pipe busy - all items last the same, the offset persists
+  if (pi & 1) {
     const long long t0 = clock64(), d = (long long)(a.chunk / 4) * steps * 64;
     while (clock64() - t0 < d) __nanosleep(200);
   }
+  const int bar_id = 1 + pi;              // named barrier of the pair (0 is the block's)
 
-  for (long long item = (long long)blockIdx.x + (long long)wi * gridDim.x; item < total; item += warps) {
+  for (long long item = (long long)blockIdx.x + (long long)pi * gridDim.x; item < total; item += pairs) {
     const int c = (int)(item / groups), g = (int)(item - (long long)c * groups);     // chunks in order, groups fastest
     const int s = g * 32 + lane;
-    const int u0 = c * a.chunk;
-    // this lane's stream: length, position and phase of the chunk's first output
-    int L = 0, pos0 = 0, phi0 = -1;
+    const int us = c * 2 * a.chunk;       // first output of the pair's item
+    const int u0 = us + half * a.chunk;   // first output of this warp's half
+    // this lane's stream: length; position of the item's first input (what is staged); position and phase of the half's
+    // first output.  Both warps of the pair compute the same for the item.
+    int L = 0, pos_s = 0, pos0 = 0, phi0 = -1;
+    bool act_s = false;
     if (s < a.n_streams) {
       const SubmitRec sr = a.submit[s];
-      if (!sr.irregular && u0 < sr.lim_len) {
+      if (!sr.irregular && us < sr.lim_len) {
         L = sr.lim_len;
+        act_s = true;
         const long long in_start = a.state[s].rs_in_total - sr.in_len;
-        const long long n = sr.rs_out_first + u0;
         // q(n) = Nf/2 + floor(n * num / den) is the LAST input of output n; index into the tl_a row
-        pos0 = (int)((long long)(Nf / 2) + (n * (long long)plan.rs_num) / den - (Nf - 1) - in_start + plan.rs_hist);
-        phi0 = (int)((n * (long long)fa) % den);
+        const long long ns = sr.rs_out_first + us;
+        pos_s = (int)((long long)(Nf / 2) + (ns * (long long)plan.rs_num) / den - (Nf - 1) - in_start + plan.rs_hist);
+        if (u0 < L) {
+          const long long n = sr.rs_out_first + u0;
+          pos0 = (int)((long long)(Nf / 2) + (n * (long long)plan.rs_num) / den - (Nf - 1) - in_start + plan.rs_hist);
+          phi0 = (int)((n * (long long)fa) % den);
+        }
       }
     }
-    unsigned todo = __ballot_sync(0xffffffffu, phi0 >= 0);
-    if (todo == 0u) continue;
+    if (__ballot_sync(0xffffffffu, act_s) == 0u) continue;       // (the same decision in both warps of the pair)
+    const unsigned todo = __ballot_sync(0xffffffffu, phi0 >= 0);
     for (int c0 = 0; c0 < co; c0 += 2) {
       const bool two = c0 + 1 < co;
-      // ---- stage the inputs of the chunk: row st of X = stream 32 g + st, entries [pos0(st), pos0(st) + span)
-      __syncwarp();
+      // ---- stage the inputs of the item: row st of X = stream 32 g + st, entries [pos_s(st), pos_s(st) + span); each warp
+      // of the pair brings 16 of the 32 rows
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // (the other half has finished with the previous rows)
       // (asynchronous 4-byte copies, all of them in flight at once: the rows of 32 streams are 32 different places in memory)
       {
-        // element index of the lane's own first staged input, < 0 for a lane without work; in_rng: the whole row exists
-        const long long my_off = phi0 >= 0 ? ((long long)s * co + c0) * a.cap_a + pos0 : -1;
-        const bool fast = __all_sync(0xffffffffu, phi0 < 0 || (pos0 >= 0 && pos0 + a.span <= a.cap_a));
+        // element index of the lane's own first staged input, < 0 for a lane without work
+        const long long my_off = act_s ? ((long long)s * co + c0) * a.cap_a + pos_s : -1;
+        const bool fast = __all_sync(0xffffffffu, !act_s || (pos_s >= 0 && pos_s + a.span <= a.cap_a));
         const uint32_t xb = (uint32_t)__cvta_generic_to_shared(X) + (uint32_t)lane * 8u;
         if (fast) {
 #pragma unroll 4
-          for (int st = 0; st < 32; ++st) {
+          for (int st = 16 * half; st < 16 * half + 16; ++st) {
             const long long o = __shfl_sync(0xffffffffu, my_off, st);
             const bool on = o >= 0;                                                   // (warp-uniform)
             const float *r0 = a.src + (on ? o : 0) + lane;
@@ -127,10 +140,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
           }
         } else {
 #pragma unroll 1
-          for (int st = 0; st < 32; ++st) {
-            const int p0 = __shfl_sync(0xffffffffu, pos0, st);
-            const int ph = __shfl_sync(0xffffffffu, phi0, st);
-            if (ph < 0) continue;                                                      // (warp-uniform)
+          for (int st = 16 * half; st < 16 * half + 16; ++st) {
+            const int p0 = __shfl_sync(0xffffffffu, pos_s, st);
+            const int on = __shfl_sync(0xffffffffu, act_s ? 1 : 0, st);
+            if (!on) continue;                                                         // (warp-uniform)
             const float *r0 = a.src + ((size_t)(g * 32 + st) * co + c0) * a.cap_a;
             const float *r1 = two ? r0 + a.cap_a : r0;
             for (int k = lane; k < a.span; k += 32) {
@@ -146,7 +159,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // (both warps' rows are in)
       // ---- passes over the phases present in the warp (one when the streams run in step)
       unsigned left = todo;
       while (left) {
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
         float *d1 = d0 + a.cap_b;
         const bool al4 = ((a.cap_b | a.hist_b) & 3) == 0;
         // walk the chunk in groups of four outputs; (rel, ph) = first tap (relative to pos0) and phase of the group's first output
-        int rel = 0, ph = phl;
+        int rel = pos0 - pos_s, ph = phl;
         const int n_here = min(a.chunk, L - u0);
 #pragma unroll 1
         for (int m = 0; m < n_here; m += 4) {
