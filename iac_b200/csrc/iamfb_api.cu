@@ -1320,11 +1320,11 @@ static int launch_pipe(iamfb_ctx *ctx, const iamfb_plan *p, const FusedArgs &fa,
 static int rs_ls_smem(const iamfb_plan *p, int chunk, int *span_out) {
   const KernelPlan &kp = p->kp;
   const int steps = (int)kp.rs_filt_len + 3 * ((int)kp.rs_int_adv + 1);
-  // (a pair of warps shares one staging area: the inputs of 2 x chunk outputs)
-  const int span = ((int)(((unsigned long long)(2 * chunk) * kp.rs_num) / kp.rs_den) + 3 + steps) | 1;
+  // (a team of warps shares one staging area: the inputs of kLsTeam x chunk outputs)
+  const int span = ((int)(((unsigned long long)(kLsTeam * chunk) * kp.rs_num) / kp.rs_den) + 3 + steps) | 1;
   if (span_out) *span_out = span;
   if (kp.rs_den > 2048) return 1 << 30;       // (the per-phase weights would not fit next to the staging areas)
-  return (int)((kp.rs_oversample * p->rs_tab_row + kp.rs_den + (kp.rs_den + 3) / 4) * sizeof(float4)) + (kLsWarps / 2) * 32 * span * 8;
+  return (int)((kp.rs_oversample * p->rs_tab_row + kp.rs_den + (kp.rs_den + 3) / 4) * sizeof(float4)) + (kLsWarps / kLsTeam) * 32 * span * 8;
 }
 
 // pre: the limiter half only (k_pipe_rs<PRE>) behind k_resample_ls, else the whole pipeline in k_pipe_rs
@@ -1422,17 +1422,17 @@ static int launch_rs_split(iamfb_ctx *ctx, const iamfb_plan *p, iamfb_batch *b, 
       // every round of the persistent warps lasts one chunk: the size with the fewest (rounds x chunk) wins, ties to the larger
       long long best = -1;
       for (int c = p->rs_ls_chunk; c >= 16 && c >= p->rs_ls_chunk - 16; c -= 4) {
-        const long long items = (long long)groups * ((max_out + 2 * c - 1) / (2 * c)), pairs = (long long)ctx->n_sm * (kLsWarps / 2);
-        const long long cost = ((items + pairs - 1) / pairs) * c;
+        const long long items = (long long)groups * ((max_out + kLsTeam * c - 1) / (kLsTeam * c)), teams = (long long)ctx->n_sm * (kLsWarps / kLsTeam);
+        const long long cost = ((items + teams - 1) / teams) * c;
         if (best < 0 || cost < best) { best = cost; la.chunk = c; }
       }
     }
-    la.n_chunks = (max_out + 2 * la.chunk - 1) / (2 * la.chunk);      // work items: 2 x chunk outputs of 32 streams for a pair of warps
+    la.n_chunks = (max_out + kLsTeam * la.chunk - 1) / (kLsTeam * la.chunk);      // work items: kLsTeam x chunk outputs of 32 streams for a team of warps
     la.neg_zero = -0.0f;
     const int smem_ls = rs_ls_smem(p, la.chunk, &la.span);
     int blocks = ctx->n_sm;      // persistent: one block of kLsWarps warps per SM
     const long long items = (long long)groups * la.n_chunks;
-    if ((long long)blocks * (kLsWarps / 2) > items) blocks = (int)((items + kLsWarps / 2 - 1) / (kLsWarps / 2));
+    if ((long long)blocks * (kLsWarps / kLsTeam) > items) blocks = (int)((items + kLsWarps / kLsTeam - 1) / (kLsWarps / kLsTeam));
     int r = iamfb_resample_ls_launch(ctx, kp, la, blocks, smem_ls);
     if (r) return r;
     cudaError_t e_ = cudaGetLastError();

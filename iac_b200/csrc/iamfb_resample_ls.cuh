@@ -8,7 +8,7 @@
 // inputs are per lane - the loop is left with the FP32 pipe as its bound (an 8-byte input per lane and four broadcast 16-byte
 // tap items per step: 10 shared-memory wavefronts against 64 cycles of FP32 work; measured: DESIGN.md 4.3).
 //
-// Work item = (group of 32 streams, chunk of `chunk` consecutive outputs).  A warp stages, for each of its streams, the
+// Work item = (group of 32 streams, kLsTeam chunks of `chunk` consecutive outputs, one per warp of a team).  The team stages, for each stream, the
 // inputs the chunk spans (channel pairs interleaved, row stride odd: lanes hit different banks) from the pre-resample time
 // line tl_a[S][co][cap_a] (k_pipe_prerender's output; the previous submit's last rs_hist inputs in front), then walks the chunk in
 // groups of 4 consecutive outputs exactly like k_pipe_rs: one pass over the inputs of the four outputs, the rows of the
@@ -18,8 +18,8 @@
 //
 // Lanes whose streams are at another phase (a stream that joined the batch later, lost a frame, ...) are served in further
 // passes of the same warp (grouped by the phase of the chunk's first output); irregular streams of the submit (trims,
-// missing frames) are skipped - the multi-kernel path renders them.  The kernel is persistent: one block of 8 warps per SM
-// (two per scheduler, each with its own staging area) strides over the work items; k_pipe_rs<PRE> (the limiter half) follows.
+// missing frames) are skipped - the multi-kernel path renders them.  The kernel is persistent: one block per SM
+// (the block shape and the shared staging areas: below) strides over the work items; k_pipe_rs<PRE> (the limiter half) follows.
 // Measured with the limiter half BESIDE this kernel (chunks handed over through flags): no gain - the staging areas leave
 // no shared memory for its blocks, and with fewer resampler warps the FP32 pipe idles more than the overlap saves.
 #pragma once
@@ -43,9 +43,20 @@ struct ResampleLsArgs {
   float neg_zero;
 };
 
-constexpr int kLsWarps = 12;    // warps per block = 6 pairs; a pair shares ONE staging area that covers 2 x chunk outputs (the two
-                                // halves' inputs overlap by the filter length: 35 % less shared memory per warp than an area each,
-                                // which is what lets three warps per scheduler fit the SM)
+// Block shape (compile-time; -D overrides exist for A/B builds, tools/gpu_variants.sh).  12 warps per SM in 3 TEAMS of 4: the
+// warps of a team share ONE staging area that covers 4 x chunk consecutive outputs of 32 streams - neighbouring chunks'
+// inputs overlap by the filter length, so one area for four chunks needs 45 % less shared memory per warp than an area
+// each (which is what lets three warps per scheduler fit the SM), and a team's four warps sit on the four schedulers.
+// Measured on C5 (ms per launch): an area per warp, 8 warps 1.36; teams of 2 (12 warps) 1.30; of 3 1.248; of 4 1.233;
+// of 6 1.244; 16 warps in teams of 4 / 8: 1.28 / 1.29 (128 registers per thread and smaller chunks).
+#ifndef IAMFB_LS_TEAM
+#define IAMFB_LS_TEAM 4
+#endif
+#ifndef IAMFB_LS_WARPS
+#define IAMFB_LS_WARPS 12
+#endif
+constexpr int kLsTeam = IAMFB_LS_TEAM;      // warps that share one staging area
+constexpr int kLsWarps = IAMFB_LS_WARPS;    // warps per block (one block per SM)
 
 __device__ __forceinline__ void ls_cp4(void *dst_smem, const void *src, bool valid) {   // 4-byte asynchronous copy, zeros when !valid
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
@@ -63,7 +74,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
   const int tab_items = os * trow;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   float4 *CI = TAB + tab_items;                                                    // [den] cubic weights per phase
-  const int pi = wi >> 1, half = wi & 1;                                           // pair of warps, this warp's half of the pair's outputs
+  const int pi = wi / kLsTeam, half = wi % kLsTeam;                                // team, this warp's part of the team's outputs
   float2 *X = reinterpret_cast<float2 *>(CI + den + (den + 3) / 4) + (size_t)pi * 32 * a.span;    // [32 streams][span] channel pairs
   for (int i = threadIdx.x; i < tab_items; i += NWARPS * 32) TAB[i] = a.tab4[i];
   for (int i = threadIdx.x; i < den; i += NWARPS * 32) CI[i] = a.interp4[i];
@@ -75,23 +86,23 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
   const int steps = Nf + 3 * (ia + 1);
   const bool loud_on = plan.loud_gain != 0.f && plan.loud_gain != 1.0f;
   const int co = a.co;
-  const long long total = (long long)groups * a.n_chunks;       // (n_chunks counts the pairs' items of 2 x chunk outputs)
-  const int pairs = gridDim.x * (NWARPS / 2);
-  // the pairs of a scheduler take turns: every other pair starts half an item late, so that one stages while the others
-  // keep the FP32 pipe busy - all items last the same, the offset persists
-  if (pi & 1) {
+  const long long total = (long long)groups * a.n_chunks;       // (n_chunks counts the teams' items of kLsTeam x chunk outputs)
+  const int teams = gridDim.x * (NWARPS / kLsTeam);
+  // the teams take turns: every other team starts half an item late, so that one stages while the others keep the FP32
+  // pipe busy - all items last the same, the offset persists
+if (pi & 1) {
     const long long t0 = clock64(), d = (long long)(a.chunk / 4) * steps * 64;
     while (clock64() - t0 < d) __nanosleep(200);
   }
-  const int bar_id = 1 + pi;              // named barrier of the pair (0 is the block's)
+  const int bar_id = 1 + pi;              // named barrier of the team (0 is the block's)
 
-  for (long long item = (long long)blockIdx.x + (long long)pi * gridDim.x; item < total; item += pairs) {
+  for (long long item = (long long)blockIdx.x + (long long)pi * gridDim.x; item < total; item += teams) {
     const int c = (int)(item / groups), g = (int)(item - (long long)c * groups);     // chunks in order, groups fastest
     const int s = g * 32 + lane;
-    const int us = c * 2 * a.chunk;       // first output of the pair's item
-    const int u0 = us + half * a.chunk;   // first output of this warp's half
-    // this lane's stream: length; position of the item's first input (what is staged); position and phase of the half's
-    // first output.  Both warps of the pair compute the same for the item.
+    const int us = c * kLsTeam * a.chunk; // first output of the team's item
+    const int u0 = us + half * a.chunk;   // first output of this warp's part
+    // this lane's stream: length; position of the item's first input (what is staged); position and phase of the part's
+    // first output.  All warps of the team compute the same for the item.
     int L = 0, pos_s = 0, pos0 = 0, phi0 = -1;
     bool act_s = false;
     if (s < a.n_streams) {
@@ -110,13 +121,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
         }
       }
     }
-    if (__ballot_sync(0xffffffffu, act_s) == 0u) continue;       // (the same decision in both warps of the pair)
+    if (__ballot_sync(0xffffffffu, act_s) == 0u) continue;       // (the same decision in every warp of the team)
     const unsigned todo = __ballot_sync(0xffffffffu, phi0 >= 0);
     for (int c0 = 0; c0 < co; c0 += 2) {
       const bool two = c0 + 1 < co;
-      // ---- stage the inputs of the item: row st of X = stream 32 g + st, entries [pos_s(st), pos_s(st) + span); each warp
-      // of the pair brings 16 of the 32 rows
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // (the other half has finished with the previous rows)
+      // ---- stage the inputs of the item: row st of X = stream 32 g + st, entries [pos_s(st), pos_s(st) + span); the warps
+      // of the team bring the rows in turn
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kLsTeam * 32) : "memory");     // (the others have finished with the previous rows)
       // (asynchronous 4-byte copies, all of them in flight at once: the rows of 32 streams are 32 different places in memory)
       {
         // element index of the lane's own first staged input, < 0 for a lane without work
@@ -125,7 +136,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
         const uint32_t xb = (uint32_t)__cvta_generic_to_shared(X) + (uint32_t)lane * 8u;
         if (fast) {
 #pragma unroll 4
-          for (int st = 16 * half; st < 16 * half + 16; ++st) {
+          for (int st = half; st < 32; st += kLsTeam) {
             const long long o = __shfl_sync(0xffffffffu, my_off, st);
             const bool on = o >= 0;                                                   // (warp-uniform)
             const float *r0 = a.src + (on ? o : 0) + lane;
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
           }
         } else {
 #pragma unroll 1
-          for (int st = 16 * half; st < 16 * half + 16; ++st) {
+          for (int st = half; st < 32; st += kLsTeam) {
             const int p0 = __shfl_sync(0xffffffffu, pos_s, st);
             const int on = __shfl_sync(0xffffffffu, act_s ? 1 : 0, st);
             if (!on) continue;                                                         // (warp-uniform)
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_resample_ls(const __grid_con
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // (both warps' rows are in)
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kLsTeam * 32) : "memory");     // (every warp's rows are in)
       // ---- passes over the phases present in the warp (one when the streams run in step)
       unsigned left = todo;
       while (left) {
