@@ -31,7 +31,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 CONFIGS = {
-    "c1": dict(streams=1024, frames=32, desc="simple-profile stereo -> sound system A"),
+    # (configs[0] is ONE stream on the CPU; the batch is ours to size: 72 streams per SM.  The submit lasts as long as its
+    # loudest streams' serial limiter recurrence, so a batch of several waves keeps the SMs busy behind the quiet streams:
+    # 1024 x 32 frames 1.21 M audio-s/s, 5328 x 32 2.64 M, 10656 x 16 2.98 M, 21312 x 16 3.20 M - profiles/r2_c1_c2_batch_sizes.log)
+    "c1": dict(streams=10656, frames=16, desc="10656 simple-profile stereo streams -> sound system A"),
     "c2": dict(streams=1024, frames=16, desc="1024 base-profile streams, 7.1.4 scalable (2.0 -> 7.1.4) with recon-gain demixing -> sound system B (0+5+0)"),
     "c3": dict(streams=4096, frames=8, desc="4096 streams of 3rd-order ambisonics (16 ch) -> sound system H (9+10+3)"),
     "c4": dict(streams=2048, frames=8, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural (as built: stereo matrices)"),

@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 K = 16
 FULL = [
     (S.c1_stereo, 1024, 6),               # configs[0] is one stream on the CPU; the batched form of the same pipeline
+    (S.c1_stereo, 10656, 3),              # ... at the batch size bench.py runs it with (several waves of k_stream blocks)
     (S.c2_714_to_B, 1024, 6),             # configs[1]
     (S.c3_toa_to_H, 4096, 3),             # configs[2]
     (S.c4_714_foa_binaural, 2048, 4),     # configs[3]
@@ -31,7 +32,7 @@ def _tile(a, n):
     return np.concatenate([a] * reps, axis=0)[:n]
 
 
-@pytest.mark.parametrize("mk,n_streams,F", FULL, ids=[f[0].__name__ for f in FULL])
+@pytest.mark.parametrize("mk,n_streams,F", FULL, ids=[f"{f[0].__name__}-{f[1]}" for f in FULL])
 def test_full_size_replicas_and_split_invariance(mk, n_streams, F):
     from gpu_harness import run_product
     sc = mk()
