@@ -36,16 +36,16 @@ CONFIGS = {
     # 1024 x 32 frames 1.21 M audio-s/s, 5328 x 32 2.64 M, 10656 x 16 2.98 M, 21312 x 16 3.20 M - profiles/r2_c1_c2_batch_sizes.log)
     "c1": dict(streams=10656, frames=16, desc="10656 simple-profile stereo streams -> sound system A"),
     "c2": dict(streams=1024, frames=16, desc="1024 base-profile streams, 7.1.4 scalable (2.0 -> 7.1.4) with recon-gain demixing -> sound system B (0+5+0)"),
-    "c3": dict(streams=4096, frames=8, desc="4096 streams of 3rd-order ambisonics (16 ch) -> sound system H (9+10+3)"),
-    "c4": dict(streams=2048, frames=8, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural (as built: stereo matrices)"),
-    "c4h": dict(streams=2048, frames=8, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural with HRTF convolution (256-tap in-repo HRIR set, "
+    "c3": dict(streams=4096, frames=16, desc="4096 streams of 3rd-order ambisonics (16 ch) -> sound system H (9+10+3)"),
+    "c4": dict(streams=2048, frames=16, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural (as built: stereo matrices)"),
+    "c4h": dict(streams=2048, frames=16, desc="2048 streams, 7.1.4 + FOA mix presentation -> binaural with HRTF convolution (256-tap in-repo HRIR set, "
                                              "exact int8 tensor-core contraction; self-oracle, parity unpinned by the reference)",
                 in_format="s16"),   # the decoded PCM is handed over as the int16 the codecs produce: two limbs per sample instead of three
     "c5": dict(streams=2048, frames=16, desc="2048 streams/GPU, stereo 44.1->48 kHz resample, loudness -24 LKFS, limiter, 16-bit"),
     # the FP32-bound configuration again in the engine's tolerance mode (IAMFB_ARITH_FMA, include/iamf_b200.h): the HOA matrix
     # fuses multiply and add; PCM within +-1 LSB of the reference instead of bit-identical
     # (tests/test_gpu_parity.py::test_fma_arithmetic_stays_within_the_stated_tolerance).  Never the headline.
-    "c3f": dict(streams=4096, frames=8, base="c3", arithmetic=1,
+    "c3f": dict(streams=4096, frames=16, base="c3", arithmetic=1,
                 desc="c3 in tolerance mode (IAMFB_ARITH_FMA: fused multiply-add in the HOA matrix, +-1 LSB instead of bit-exact)"),
 }
 
