@@ -24,7 +24,7 @@ static size_t mutate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
   size_t len = n;
   const int edits = 1 + (int)(rnd() % 4);
   for (int e = 0; e < edits && len > 0; ++e) {
-    const uint32_t kind = rnd() % 8;
+    const uint32_t kind = rnd() % 11;
     const size_t at = (rnd() & 1) ? rnd() % len : rnd() % (len < 400 ? len : 400);    /* half of the edits in the descriptors */
     switch (kind) {
       case 0: dst[at] ^= (uint8_t)(1u << (rnd() % 8)); break;
@@ -37,6 +37,22 @@ static size_t mutate(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {
         size_t span = 1 + rnd() % 32;
         if (at + span > len) span = len - at;
         if (len + span <= cap) { memmove(dst + at + span, dst + at, len - at); len += span; }
+        break;
+      }
+      case 8: {                                                             /* a size / count field blown up: 5-byte leb128 */
+        static const uint8_t big[5] = {0xff, 0xff, 0xff, 0xff, 0x0f};
+        size_t k = 1 + rnd() % 5;
+        if (at + k > len) k = len - at;
+        memcpy(dst + at, big + 5 - k, k);
+        if (k > 1) dst[at] |= 0x80;
+        break;
+      }
+      case 9: dst[at] = (uint8_t)(rnd() % 9); break;                       /* a small count / enum value */
+      case 10: {                                                            /* a span copied over another place (OBUs re-ordered / repeated) */
+        size_t span = 1 + rnd() % 64, to = rnd() % len;
+        if (at + span > len) span = len - at;
+        if (to + span > len) span = len - to;
+        memmove(dst + to, dst + at, span);
         break;
       }
       default: {                                                            /* delete a span */
