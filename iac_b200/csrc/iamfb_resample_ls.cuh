@@ -59,6 +59,7 @@ struct ResampleLsArgs {
 #endif
 constexpr int kLsTeam = IAMFB_LS_TEAM;      // warps that share one staging area
 constexpr int kLsWarps = IAMFB_LS_WARPS;    // warps per block (one block per SM)
+static_assert(kLsWarps % kLsTeam == 0 && kLsWarps / kLsTeam <= 15 && kLsWarps <= 32, "teams tile the block; one named barrier (1..15) per team");
 
 __device__ __forceinline__ void ls_cp4(void *dst_smem, const void *src, bool valid) {   // 4-byte asynchronous copy, zeros when !valid
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
